@@ -1,0 +1,193 @@
+/* newsreclib_b200 C ABI: the sm_100a implementation of NewsRecLib's two-tower hot path
+ * (NewsEncoder -> UserEncoder -> click score, + soft-target CE, backward, Adam).
+ *
+ * Drop-in boundary.  The reference (andreeaiana/newsreclib @ f29aea8) is pure Python and has
+ * no FFI of its own; what a maintainer would bind is the set of torch.nn forward calls on the
+ * path.  Every entry point below names the reference interface it replaces (file:line, paths
+ * relative to the reference root).  INTEGRATION.md shows the ctypes stub the reference side
+ * would add.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types; all pointers are DEVICE pointers unless the
+ *     name ends in _host; caller owns every buffer, nothing is allocated or freed here
+ *   - all launches go to the cudaStream_t passed as `stream` (void* to keep this header C)
+ *   - return 0 on success, negative nrl_status on failure; nrl_last_error() gives the text
+ *   - float = fp32, ids / segment ids = int64 (what the reference collate emits,
+ *     newsreclib/data/components/rec_dataset.py:148-168)
+ *   - gradient outputs ACCUMULATE (+=) into the caller's buffers (autograd semantics); zero
+ *     them first if that is what you want
+ *   - precision: NRL_PREC_BF16X3 (default; three bf16 tensor-core passes on hi/lo split
+ *     operands, fp32-equivalent: logits within 1e-4 of the reference) or NRL_PREC_BF16
+ *     (single pass, for the bf16 configuration)
+ */
+#ifndef NRL_H_
+#define NRL_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  NRL_OK = 0,
+  NRL_ERR_INVALID_ARG = -1,
+  NRL_ERR_WORKSPACE_TOO_SMALL = -2,
+  NRL_ERR_CUDA = -3,
+  NRL_ERR_UNSUPPORTED = -4
+} nrl_status;
+
+enum { NRL_PREC_BF16X3 = 0, NRL_PREC_BF16 = 1 };
+
+/* One "MHSA + additive pooling" block: the parameters of nn.MultiheadAttention followed by
+ * AdditiveAttention, as held by MHSAAddAtt (encoders/news/text.py:218-219) and by the NRMS
+ * UserEncoder (encoders/user/nrms.py:27-30).  state_dict names in comments. */
+typedef struct {
+  const float* in_proj_weight;  /* multihead_attention.in_proj_weight  [3E, E] */
+  const float* in_proj_bias;    /* multihead_attention.in_proj_bias    [3E]    */
+  const float* out_proj_weight; /* multihead_attention.out_proj.weight [E, E]  */
+  const float* out_proj_bias;   /* multihead_attention.out_proj.bias   [E]     */
+  const float* add_weight;      /* additive_attention.linear.weight    [Q, E]  */
+  const float* add_bias;        /* additive_attention.linear.bias      [Q]     */
+  const float* add_query;       /* additive_attention.query            [Q]     */
+} nrl_block_params;
+
+typedef struct {
+  float* in_proj_weight;
+  float* in_proj_bias;
+  float* out_proj_weight;
+  float* out_proj_bias;
+  float* add_weight;
+  float* add_bias;
+  float* add_query;
+} nrl_block_grads;
+
+typedef struct {
+  int embed_dim;  /* E  (configs/model/nrms.yaml:19) */
+  int num_heads;  /* h  (:20); E / h must be 16, 20 or 32 */
+  int query_dim;  /* Q  (:21) */
+} nrl_dims;
+
+const char* nrl_version(void);
+const char* nrl_last_error(void);
+
+/* ---- MHSAAddAtt.forward, encoders/news/text.py:222-236 (title ids -> news vectors) -------
+ * ids [n_news, L] int64; table [V1, E]; out [n_news, E].  training != 0 applies the two
+ * nn.Dropout(p) sites (text.py:225,230) with the counter-based mask keyed by `seed`.
+ * `ws` keeps the activations for nrl_news_encoder_bwd. */
+size_t nrl_news_encoder_ws_bytes(long long n_news, int L, nrl_dims dims);
+int nrl_news_encoder_fwd(const long long* ids, long long n_news, int L, const float* table,
+                         long long V1, const nrl_block_params* params, nrl_dims dims,
+                         float dropout_p, int training, unsigned long long seed, float* out,
+                         void* ws, size_t ws_bytes, int precision, void* stream);
+/* Backward of the above: d_out [n_news, E] -> parameter gradients (+=) and the dense
+ * embedding gradient d_table [V1, E] (+=, row 0 untouched = padding_idx, text.py:215-217). */
+int nrl_news_encoder_bwd(const long long* ids, long long n_news, int L, long long V1,
+                         const nrl_block_params* params, nrl_dims dims, float dropout_p,
+                         int training, unsigned long long seed, const float* d_out,
+                         nrl_block_grads* grads, float* d_table, void* ws, size_t ws_bytes,
+                         int precision, void* stream);
+
+/* ---- NRMS UserEncoder.forward, encoders/user/nrms.py:32-41 -------------------------------
+ * hist [B, Hmax, E] dense (zero padded) -> user [B, E].  attention_axis 0 = reference
+ * behaviour (self-attention across the B impressions at every history position, the
+ * batch_first=False quirk), 1 = along the history. */
+size_t nrl_user_encoder_ws_bytes(int B, int Hmax, nrl_dims dims);
+int nrl_user_encoder_fwd(const float* hist, int B, int Hmax, const nrl_block_params* params,
+                         nrl_dims dims, int attention_axis, float* user, void* ws,
+                         size_t ws_bytes, int precision, void* stream);
+int nrl_user_encoder_bwd(int B, int Hmax, const nrl_block_params* params, nrl_dims dims,
+                         int attention_axis, const float* d_user, nrl_block_grads* grads,
+                         float* d_hist, void* ws, size_t ws_bytes, int precision, void* stream);
+
+/* ---- AdditiveAttention.forward alone, layers/attention.py:24-42 (NAML user encoder,
+ * encoders/user/naml.py:27-31, and the NAML view combiner, encoders/news/news.py:162-163) --
+ * x [G, L, D] -> out [G, D]. */
+size_t nrl_additive_ws_bytes(long long G, int L, int D, int Q);
+int nrl_additive_fwd(const float* x, long long G, int L, int D, int Q, const float* weight,
+                     const float* bias, const float* query, float* out, void* ws,
+                     size_t ws_bytes, int precision, void* stream);
+
+/* ---- torch_geometric.utils.to_dense_batch (2.3.0), call sites nrms_module.py:233,237 ------
+ * seg: sorted int64 segment ids [n]; off: int32 [B+1] CSR offsets (device). */
+int nrl_segment_offsets(const long long* seg, long long n, int B, int* off, void* stream);
+int nrl_to_dense_fwd(const float* x, const int* off, int B, int M, int E, float* dense,
+                     void* stream);
+int nrl_to_dense_bwd(const float* d_dense, const int* off, int B, int M, int E, float* dx,
+                     void* stream);
+/* late fusion, nrms_module.py:243-248 */
+int nrl_late_fusion_fwd(const float* hist_vec, const int* off, int B, int E, float* user,
+                        void* stream);
+int nrl_late_fusion_bwd(const float* d_user, const int* off, int B, int E, float* d_hist_vec,
+                        void* stream);
+
+/* ---- DotProduct.forward, layers/click_predictor.py:9-11 via nrms_module.py:251-253 --------
+ * user [B, E], cand [N_c, E] ragged with offsets -> scores [B, Cmax] (0.0 in padded slots). */
+int nrl_score_fwd(const float* user, const float* cand, const int* cand_off, int B, int Cmax,
+                  int E, float* scores, void* stream);
+int nrl_score_bwd(const float* d_scores, const float* user, const float* cand,
+                  const int* cand_off, int B, int Cmax, int E, float* d_user, float* d_cand,
+                  void* stream);
+
+/* ---- CrossEntropyLoss()(scores, y_true) with float targets, nrms_module.py:277,288 --------
+ * labels [N_c] ragged.  loss_mean (1 float) is overwritten; loss_rows [B] and y_dense
+ * [B, Cmax] are optional (NULL to skip). */
+int nrl_ce_soft_fwd(const float* scores, const float* labels, const int* cand_off, int B,
+                    int Cmax, float* loss_rows, float* loss_mean, float* y_dense, void* stream);
+/* d_scores = g_loss[0] * g_scale * dLoss/dScores (g_loss may be NULL = 1) */
+int nrl_ce_soft_bwd(const float* scores, const float* labels, const int* cand_off, int B,
+                    int Cmax, const float* g_loss, float g_scale, float* d_scores, void* stream);
+
+/* ---- torch.optim.Adam step (configs/model/nrms.yaml:49-52), dense over n elements --------- */
+int nrl_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr,
+                  float beta1, float beta2, float eps, long long step, float grad_scale,
+                  void* stream);
+
+/* ---- NRMSModule.forward + model_step loss + backward, nrms_module.py:230-255,277,288 ------
+ * One call = one pass of the hot path over one batch.  All inputs are device pointers.
+ *   hist_ids [N_h, L], cand_ids [N_c, L], seg_hist [N_h], seg_cand [N_c] (sorted), labels [N_c]
+ *   scores   [B, Cmax]   out
+ *   loss     [1]         out (NULL for pure inference)
+ *   do_backward != 0: parameter gradients (+=) into news_grads / user_grads / d_table.
+ * Hmax / Cmax are the dense widths max_b h_b / max_b c_b (known at collate time). */
+size_t nrl_nrms_ws_bytes(long long n_hist, long long n_cand, int L, int B, int Hmax, int Cmax,
+                         nrl_dims dims);
+int nrl_nrms_step(const long long* hist_ids, const long long* cand_ids, const long long* seg_hist,
+                  const long long* seg_cand, const float* labels, long long n_hist,
+                  long long n_cand, int L, int B, int Hmax, int Cmax, const float* table,
+                  long long V1, const nrl_block_params* news_params,
+                  const nrl_block_params* user_params, nrl_dims dims, int late_fusion,
+                  float dropout_p, int training, unsigned long long seed, float* scores,
+                  float* loss, int do_backward, nrl_block_grads* news_grads,
+                  nrl_block_grads* user_grads, float* d_table, void* ws, size_t ws_bytes,
+                  int precision, void* stream);
+/* Same pass with HOST input buffers (pinned or pageable): copies ids / segments / labels to the
+ * device staging area inside `ws`, runs nrl_nrms_step, copies scores and loss back to
+ * scores_host / loss_host and synchronises the stream.  This is the end-to-end call. */
+int nrl_nrms_step_host(const long long* hist_ids_host, const long long* cand_ids_host,
+                       const long long* seg_hist_host, const long long* seg_cand_host,
+                       const float* labels_host, long long n_hist, long long n_cand, int L, int B,
+                       int Hmax, int Cmax, const float* table, long long V1,
+                       const nrl_block_params* news_params, const nrl_block_params* user_params,
+                       nrl_dims dims, int late_fusion, float dropout_p, int training,
+                       unsigned long long seed, float* scores_host, float* loss_host,
+                       int do_backward, nrl_block_grads* news_grads, nrl_block_grads* user_grads,
+                       float* d_table, void* ws, size_t ws_bytes, int precision, void* stream);
+
+/* ---- test / measurement helpers ----------------------------------------------------------- */
+/* keep[i] = 1 iff element i of dropout site `site` (0 = after the embedding, 1 = after the
+ * MHSA) is kept for (seed, p): lets a test feed the very same mask to the CPU oracle. */
+int nrl_dropout_mask(unsigned char* keep, long long n, unsigned long long seed, int site, float p,
+                     void* stream);
+/* Raw tensor-core GEMM for unit tests: D[M,N] (fp32, ld = N) = A * B^T over K.
+ * mn_major 0: A [M,K], B [N,K] fp32 row-major.  mn_major 1: A [K,M], B [K,N] (D += via atomics,
+ * zero D first).  Operands are split to bf16 planes in `ws`. */
+size_t nrl_gemm_test_ws_bytes(int M, int N, int K);
+int nrl_gemm_test(const float* A, const float* B, float* D, int M, int N, int K, int mn_major,
+                  int precision, void* ws, size_t ws_bytes, void* stream);
+/* number of kernels launched by this library since load (bench.py reports it) */
+long long nrl_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NRL_H_ */

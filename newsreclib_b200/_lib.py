@@ -1,0 +1,103 @@
+"""ctypes binding of the C ABI declared in ``include/nrl.h``.
+
+The shared library is built in-tree (``python __graft_entry__.py`` or
+``newsreclib_b200.build.build()``) as ``newsreclib_b200/libnrl_b200.so``.  There is no CPU
+fallback: importing an op without the library raises, and every non-zero status from the
+library raises ``RuntimeError`` carrying ``nrl_last_error()``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnrl_b200.so")
+
+c_ll_p = C.POINTER(C.c_longlong)
+c_f_p = C.POINTER(C.c_float)
+c_i_p = C.POINTER(C.c_int)
+
+
+class BlockParams(C.Structure):
+    """``nrl_block_params`` / ``nrl_block_grads`` (same layout: seven float pointers)."""
+
+    _fields_ = [
+        ("in_proj_weight", C.c_void_p),
+        ("in_proj_bias", C.c_void_p),
+        ("out_proj_weight", C.c_void_p),
+        ("out_proj_bias", C.c_void_p),
+        ("add_weight", C.c_void_p),
+        ("add_bias", C.c_void_p),
+        ("add_query", C.c_void_p),
+    ]
+
+
+class Dims(C.Structure):
+    _fields_ = [("embed_dim", C.c_int), ("num_heads", C.c_int), ("query_dim", C.c_int)]
+
+
+PREC_BF16X3 = 0
+PREC_BF16 = 1
+
+# name -> (restype, argtypes); every symbol include/nrl.h declares
+_VP, _LL, _I, _F, _ULL, _SZ = C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_ulonglong, C.c_size_t
+_BP = C.POINTER(BlockParams)
+SIGNATURES = {
+    "nrl_version": (C.c_char_p, []),
+    "nrl_last_error": (C.c_char_p, []),
+    "nrl_launch_count": (_LL, []),
+    "nrl_news_encoder_ws_bytes": (_SZ, [_LL, _I, Dims]),
+    "nrl_news_encoder_fwd": (_I, [_VP, _LL, _I, _VP, _LL, _BP, Dims, _F, _I, _ULL, _VP, _VP, _SZ, _I, _VP]),
+    "nrl_news_encoder_bwd": (_I, [_VP, _LL, _I, _LL, _BP, Dims, _F, _I, _ULL, _VP, _BP, _VP, _VP, _SZ, _I, _VP]),
+    "nrl_user_encoder_ws_bytes": (_SZ, [_I, _I, Dims]),
+    "nrl_user_encoder_fwd": (_I, [_VP, _I, _I, _BP, Dims, _I, _VP, _VP, _SZ, _I, _VP]),
+    "nrl_user_encoder_bwd": (_I, [_I, _I, _BP, Dims, _I, _VP, _BP, _VP, _VP, _SZ, _I, _VP]),
+    "nrl_additive_ws_bytes": (_SZ, [_LL, _I, _I, _I]),
+    "nrl_additive_fwd": (_I, [_VP, _LL, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _SZ, _I, _VP]),
+    "nrl_segment_offsets": (_I, [_VP, _LL, _I, _VP, _VP]),
+    "nrl_to_dense_fwd": (_I, [_VP, _VP, _I, _I, _I, _VP, _VP]),
+    "nrl_to_dense_bwd": (_I, [_VP, _VP, _I, _I, _I, _VP, _VP]),
+    "nrl_late_fusion_fwd": (_I, [_VP, _VP, _I, _I, _VP, _VP]),
+    "nrl_late_fusion_bwd": (_I, [_VP, _VP, _I, _I, _VP, _VP]),
+    "nrl_score_fwd": (_I, [_VP, _VP, _VP, _I, _I, _I, _VP, _VP]),
+    "nrl_score_bwd": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _VP, _VP, _VP]),
+    "nrl_ce_soft_fwd": (_I, [_VP, _VP, _VP, _I, _I, _VP, _VP, _VP, _VP]),
+    "nrl_ce_soft_bwd": (_I, [_VP, _VP, _VP, _I, _I, _VP, _F, _VP, _VP]),
+    "nrl_adam_step": (_I, [_VP, _VP, _VP, _VP, _LL, _F, _F, _F, _F, _LL, _F, _VP]),
+    "nrl_nrms_ws_bytes": (_SZ, [_LL, _LL, _I, _I, _I, _I, Dims]),
+    "nrl_nrms_step": (_I, [_VP, _VP, _VP, _VP, _VP, _LL, _LL, _I, _I, _I, _I, _VP, _LL, _BP, _BP, Dims,
+                           _I, _F, _I, _ULL, _VP, _VP, _I, _BP, _BP, _VP, _VP, _SZ, _I, _VP]),
+    "nrl_nrms_step_host": (_I, [_VP, _VP, _VP, _VP, _VP, _LL, _LL, _I, _I, _I, _I, _VP, _LL, _BP, _BP, Dims,
+                                _I, _F, _I, _ULL, _VP, _VP, _I, _BP, _BP, _VP, _VP, _SZ, _I, _VP]),
+    "nrl_dropout_mask": (_I, [_VP, _LL, _ULL, _I, _F, _VP]),
+    "nrl_gemm_test_ws_bytes": (_SZ, [_I, _I, _I]),
+    "nrl_gemm_test": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _VP, _SZ, _VP]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    """Load the library and bind every declared symbol (raises if one is missing)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: newsreclib_b200 has no CPU fallback. Build the sm_100a "
+            "library first with `python __graft_entry__.py` (needs nvcc)."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = load().nrl_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed with status {status}: {msg}")

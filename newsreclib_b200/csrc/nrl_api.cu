@@ -1,0 +1,954 @@
+// C-ABI entry points (include/nrl.h) and the host-side orchestration of the NRMS hot path.
+// Everything below the ABI is CUDA for sm_100a; there is no CPU or library fallback.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cudaTypedefs.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/nrl.h"
+#include "nrl_gemm.cuh"
+#include "nrl_kernels.cuh"
+
+using namespace nrl;
+typedef __nv_bfloat16 bf16;
+
+// ----------------------------------------------------------------------------------------
+// error / bookkeeping
+// ----------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_TRY(expr)                                                                     \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      return fail(NRL_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),    \
+                  __FILE__, __LINE__);                                                     \
+  } while (0)
+#define LAUNCH_CHECK(name)                                                                 \
+  do {                                                                                     \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                    \
+    cudaError_t _e = cudaPeekAtLastError();                                                \
+    if (_e != cudaSuccess)                                                                 \
+      return fail(NRL_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(_e));  \
+  } while (0)
+#define TRY(expr)                 \
+  do {                            \
+    int _s = (expr);              \
+    if (_s != NRL_OK) return _s;  \
+  } while (0)
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+static inline int grid_for(long long work, int per_block, int cap) {
+  long long g = (work + per_block - 1) / per_block;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return (int)g;
+}
+
+struct Device {
+  int sm_count = 0;
+  bool ok = false;
+  PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+};
+static Device g_dev;
+static std::mutex g_dev_mu;
+
+static int device_init() {
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  if (g_dev.ok) return NRL_OK;
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10)
+    return fail(NRL_ERR_UNSUPPORTED, "newsreclib_b200 needs an sm_100 GPU, found sm_%d%d",
+                prop.major, prop.minor);
+  g_dev.sm_count = prop.multiProcessorCount;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess)
+    return fail(NRL_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  g_dev.encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  CUDA_TRY(cudaFuncSetAttribute(nrl_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                GEMM_SMEM_BYTES));
+  g_dev.ok = true;
+  return NRL_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// workspace carving (same sequence in ws_bytes / fwd / bwd -> same offsets)
+// ----------------------------------------------------------------------------------------
+struct Bump {
+  char* base;
+  size_t off = 0;
+  explicit Bump(void* b) : base(static_cast<char*>(b)) {}
+  template <typename T>
+  T* take(size_t n) {
+    off = (off + 1023) & ~size_t(1023);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+struct Dims {
+  int E, H, Q, DH, Ep, Qp, P3;
+};
+static int make_dims(nrl_dims d, Dims& o) {
+  if (d.embed_dim <= 0 || d.num_heads <= 0 || d.query_dim <= 0 || d.embed_dim % d.num_heads)
+    return fail(NRL_ERR_INVALID_ARG, "bad dims E=%d heads=%d Q=%d", d.embed_dim, d.num_heads,
+                d.query_dim);
+  o.E = d.embed_dim; o.H = d.num_heads; o.Q = d.query_dim; o.DH = o.E / o.H;
+  if (o.DH != 16 && o.DH != 20 && o.DH != 32)
+    return fail(NRL_ERR_UNSUPPORTED, "head dim %d not built (16, 20, 32)", o.DH);
+  if (o.Q > 256) return fail(NRL_ERR_UNSUPPORTED, "query_dim %d > 256", o.Q);
+  o.Ep = round_up(o.E + 1, 16);
+  o.Qp = round_up(o.Q, 16);
+  o.P3 = round_up(3 * o.E, 16);
+  return NRL_OK;
+}
+
+struct BlockWs {
+  bf16 *win_f, *win_t, *wout_f, *wout_t, *wadd_f, *wadd_t;
+  bf16* x;     // [2][R][Ep]   input planes (ones column at E)
+  float* qkv;  // [R][3E]
+  float* lse;  // [R][H]
+  bf16* o;     // [2][R][Ep]
+  float* y;    // [R][E]       MHSA output (after dropout site 1)
+  bf16* yp;    // [2][R][Ep]
+  float* a;    // [R][Q]       tanh(yW+b)
+  float *s, *w;  // [R]
+  float* dy1;  // [R][E]
+  bf16* dap;   // [2][R][Qp]
+  bf16* dyp;   // [2][R][Ep]
+  float* d_o;  // [R][E]
+  bf16* dqkv;  // [2][R][P3]
+  float* dx;   // [R][E]
+};
+static void carve_block(Bump& b, long long R, const Dims& d, BlockWs& w) {
+  w.win_f = b.take<bf16>(2ull * 3 * d.E * d.Ep);
+  w.win_t = b.take<bf16>(2ull * d.E * d.P3);
+  w.wout_f = b.take<bf16>(2ull * d.E * d.Ep);
+  w.wout_t = b.take<bf16>(2ull * d.E * d.Ep);
+  w.wadd_f = b.take<bf16>(2ull * d.Q * d.Ep);
+  w.wadd_t = b.take<bf16>(2ull * d.E * d.Qp);
+  w.x = b.take<bf16>(2ull * R * d.Ep);
+  w.qkv = b.take<float>((size_t)R * 3 * d.E);
+  w.lse = b.take<float>((size_t)R * d.H);
+  w.o = b.take<bf16>(2ull * R * d.Ep);
+  w.y = b.take<float>((size_t)R * d.E);
+  w.yp = b.take<bf16>(2ull * R * d.Ep);
+  w.a = b.take<float>((size_t)R * d.Q);
+  w.s = b.take<float>((size_t)R);
+  w.w = b.take<float>((size_t)R);
+  w.dy1 = b.take<float>((size_t)R * d.E);
+  w.dap = b.take<bf16>(2ull * R * d.Qp);
+  w.dyp = b.take<bf16>(2ull * R * d.Ep);
+  w.d_o = b.take<float>((size_t)R * d.E);
+  w.dqkv = b.take<bf16>(2ull * R * d.P3);
+  w.dx = b.take<float>((size_t)R * d.E);
+}
+
+// ----------------------------------------------------------------------------------------
+// tensor-core GEMM launcher
+// ----------------------------------------------------------------------------------------
+struct Ctx {
+  cudaStream_t stream;
+  int precision;
+  bool two_planes() const { return precision == NRL_PREC_BF16X3; }
+};
+
+static int make_tmap(CUtensorMap* m, const bf16* base, unsigned long long inner,
+                     unsigned long long rows, unsigned long long pitch, unsigned box_inner,
+                     unsigned box_rows) {
+  cuuint64_t gdim[3] = {inner, rows, 2};
+  cuuint64_t gstr[2] = {pitch * sizeof(bf16), rows * pitch * sizeof(bf16)};
+  cuuint32_t box[3] = {box_inner, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_dev.encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(base), gdim,
+                            gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(NRL_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): inner=%llu rows=%llu pitch=%llu",
+                (int)r, inner, rows, pitch);
+  return NRL_OK;
+}
+
+static int choose_bn(int N, int granule) {
+  int n_tiles = (N + 255) / 256;
+  int bn = round_up((N + n_tiles - 1) / n_tiles, granule);
+  return bn > 256 ? 256 : bn;
+}
+
+// K-major ("NT") GEMM: D[M,N] = A[M,K] * B[N,K]^T.  a/b point at plane 0; plane 1 follows.
+static int gemm_nt(const Ctx& c, const bf16* A, long long M, int a_pitch, const bf16* B, int N,
+                   int b_pitch, int K, const GemmEpi& epi, const char* name) {
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = (int)M; p.N = N; p.K = K;
+  p.BN = choose_bn(epi.hi ? (epi.sp_cols > N ? epi.sp_cols : N) : N, 16);
+  if (epi.score && p.BN < N) return fail(NRL_ERR_UNSUPPORTED, "score fusion needs N <= 256");
+  p.mn_major = 0;
+  if (c.two_planes()) {
+    p.num_segs = 3;
+    p.seg_a[0] = 1; p.seg_b[0] = 0;
+    p.seg_a[1] = 0; p.seg_b[1] = 1;
+    p.seg_a[2] = 0; p.seg_b[2] = 0;
+  } else {
+    p.num_segs = 1;
+  }
+  p.k_splits = 1;
+  p.epi = epi;
+  if (!c.two_planes()) p.epi.lo = nullptr;
+  CUtensorMap ta, tb;
+  TRY(make_tmap(&ta, A, K, M, a_pitch, GEMM_BK, GEMM_BM));
+  TRY(make_tmap(&tb, B, K, N, b_pitch, GEMM_BK, p.BN));
+  const int n_extent = (epi.hi && epi.sp_cols > N) ? epi.sp_cols : N;
+  const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM, n_tiles = (n_extent + p.BN - 1) / p.BN;
+  const int tiles = m_tiles * n_tiles;
+  const int grid = tiles < g_dev.sm_count ? tiles : g_dev.sm_count;
+  nrl_gemm_tc_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, c.stream>>>(ta, tb, p);
+  LAUNCH_CHECK(name);
+  return NRL_OK;
+}
+
+// MN-major ("TN") weight-gradient GEMM: G[M,N] += sum_r A[r, m] * B[r, n], r < R.
+static int gemm_tn(const Ctx& c, const bf16* A, int M, int a_pitch, const bf16* B, int N,
+                   int b_pitch, long long R, const GemmEpi& epi, const char* name) {
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = (int)R;
+  p.BN = choose_bn(N, 64);
+  p.mn_major = 1;
+  if (c.two_planes()) {
+    p.num_segs = 3;
+    p.seg_a[0] = 1; p.seg_b[0] = 0;
+    p.seg_a[1] = 0; p.seg_b[1] = 1;
+    p.seg_a[2] = 0; p.seg_b[2] = 0;
+  } else {
+    p.num_segs = 1;
+  }
+  const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM, n_tiles = (N + p.BN - 1) / p.BN;
+  const int kb_total = (int)((R + GEMM_BK - 1) / GEMM_BK);
+  int ks = (2 * g_dev.sm_count) / (m_tiles * n_tiles);
+  if (ks < 1) ks = 1;
+  if (ks > kb_total) ks = kb_total;
+  // no empty splits: shrink until every split owns at least one k-block
+  while (ks > 1 && (long long)(ks - 1) * ((kb_total + ks - 1) / ks) >= kb_total) --ks;
+  p.k_splits = ks;
+  p.epi = epi;
+  CUtensorMap ta, tb;
+  TRY(make_tmap(&ta, A, a_pitch, R, a_pitch, 64, 64));
+  TRY(make_tmap(&tb, B, b_pitch, R, b_pitch, 64, 64));
+  const int tiles = m_tiles * n_tiles * ks;
+  const int grid = tiles < g_dev.sm_count ? tiles : g_dev.sm_count;
+  nrl_gemm_tc_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, c.stream>>>(ta, tb, p);
+  LAUNCH_CHECK(name);
+  return NRL_OK;
+}
+
+static GemmEpi epi_none() {
+  GemmEpi e;
+  memset(&e, 0, sizeof(e));
+  e.ones_col = -1;
+  return e;
+}
+
+// ----------------------------------------------------------------------------------------
+// small launch helpers
+// ----------------------------------------------------------------------------------------
+static int pack_weights(const Ctx& c, const Dims& d, const nrl_block_params* p, BlockWs& w) {
+  const int tp = c.two_planes() ? 1 : 0;
+  pack_weight_kernel<<<grid_for(3ll * d.E * d.Ep + (long long)d.E * d.P3, 256, 4096), 256, 0, c.stream>>>(
+      p->in_proj_weight, p->in_proj_bias, 3 * d.E, d.E, d.Ep, d.P3, w.win_f, w.win_t, tp);
+  LAUNCH_CHECK("pack_weight(in_proj)");
+  pack_weight_kernel<<<grid_for(2ll * d.E * d.Ep, 256, 4096), 256, 0, c.stream>>>(
+      p->out_proj_weight, p->out_proj_bias, d.E, d.E, d.Ep, d.Ep, w.wout_f, w.wout_t, tp);
+  LAUNCH_CHECK("pack_weight(out_proj)");
+  pack_weight_kernel<<<grid_for((long long)d.Q * d.Ep + (long long)d.E * d.Qp, 256, 4096), 256, 0, c.stream>>>(
+      p->add_weight, p->add_bias, d.Q, d.E, d.Ep, d.Qp, w.wadd_f, w.wadd_t, tp);
+  LAUNCH_CHECK("pack_weight(additive)");
+  return NRL_OK;
+}
+
+struct AttnGeom {
+  int S; long long seq_stride; int NB; long long batch_stride;
+};
+
+template <int DH>
+static void launch_attn_fwd(const Ctx& c, const Dims& d, const AttnGeom& g, const BlockWs& w, long long R) {
+  const long long items = (long long)g.NB * d.H * ((g.S + 31) / 32);
+  attn_fwd_kernel<DH><<<grid_for(items, 4, 1 << 20), 128, 0, c.stream>>>(
+      w.qkv, d.E, d.H, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH), w.o,
+      c.two_planes() ? w.o + R * d.Ep : nullptr, d.Ep, w.lse);
+}
+template <int DH>
+static void launch_attn_bwd(const Ctx& c, const Dims& d, const AttnGeom& g, const BlockWs& w, long long R) {
+  const long long items = (long long)g.NB * d.H;
+  attn_bwd_kernel<DH><<<grid_for(items, 4, 1 << 20), 128, 0, c.stream>>>(
+      w.qkv, w.d_o, d.E, w.o, c.two_planes() ? w.o + R * d.Ep : nullptr, d.Ep, w.lse, d.E, d.H, g.S,
+      g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH), w.dqkv,
+      c.two_planes() ? w.dqkv + R * d.P3 : nullptr, d.P3);
+}
+
+struct DropCfg {
+  int on; float scale; uint32_t thr; unsigned long long seed;
+};
+static DropCfg make_drop(float p, int training, unsigned long long seed) {
+  DropCfg dc;
+  dc.on = (training && p > 0.f) ? 1 : 0;
+  dc.scale = 1.0f / (1.0f - p);
+  dc.thr = drop_threshold(p);
+  dc.seed = seed;
+  return dc;
+}
+
+// MHSA + additive pooling over R rows already staged in w.x (split planes).
+static int block_forward(const Ctx& c, const Dims& d, BlockWs& w, long long R, const AttnGeom& ag,
+                         long long G, int L, const nrl_block_params* prm, const DropCfg& drop,
+                         float* out_vec) {
+  // K3: QKV = X W_in^T + b_in   (bias rides on the ones column)
+  {
+    GemmEpi e = epi_none();
+    e.out = w.qkv; e.ld_out = 3 * d.E; e.out_cols = 3 * d.E;
+    TRY(gemm_nt(c, w.x, R, d.Ep, w.win_f, 3 * d.E, d.Ep, d.Ep, e, "gemm in_proj"));
+  }
+  // K4: per-head softmax(q k^T) v
+  if (d.DH == 16) launch_attn_fwd<16>(c, d, ag, w, R);
+  else if (d.DH == 20) launch_attn_fwd<20>(c, d, ag, w, R);
+  else launch_attn_fwd<32>(c, d, ag, w, R);
+  LAUNCH_CHECK("attn_fwd");
+  // K5: Y = O W_out^T + b_out  (+ dropout site 1), fp32 and split planes
+  {
+    GemmEpi e = epi_none();
+    e.out = w.y; e.ld_out = d.E; e.out_cols = d.E;
+    e.hi = w.yp; e.lo = w.yp + R * d.Ep; e.ld_sp = d.Ep; e.sp_cols = d.Ep; e.ones_col = d.E;
+    if (drop.on) {
+      e.use_dropout = 1; e.drop_scale = drop.scale; e.drop_thr = drop.thr; e.drop_site = 1;
+      e.seed = drop.seed; e.drop_ld = d.E;
+    }
+    TRY(gemm_nt(c, w.o, R, d.Ep, w.wout_f, d.E, d.Ep, d.Ep, e, "gemm out_proj"));
+  }
+  // K6: a = tanh(Y W_add^T + b_add), score = a . query  (fused epilogue)
+  {
+    GemmEpi e = epi_none();
+    e.qvec = prm->add_query; e.tanh_out = w.a; e.ld_tanh = d.Q; e.score = w.s;
+    TRY(gemm_nt(c, w.yp, R, d.Ep, w.wadd_f, d.Q, d.Ep, d.Ep, e, "gemm additive"));
+  }
+  pool_fwd_kernel<<<grid_for(G, 1, 1 << 20), 128, L * sizeof(float), c.stream>>>(w.s, w.y, d.E, L, G, w.w, out_vec);
+  LAUNCH_CHECK("pool_fwd");
+  return NRL_OK;
+}
+
+// Backward of block_forward.  d_vec [G][E] -> w.dx [R][E] (gradient w.r.t. the block input,
+// dropout site 0 applied when drop0.on), parameter gradients accumulated into g.
+static int block_backward(const Ctx& c, const Dims& d, BlockWs& w, long long R, const AttnGeom& ag,
+                          long long G, int L, const nrl_block_params* prm, const DropCfg& drop1,
+                          const DropCfg& drop0, const float* d_vec, nrl_block_grads* g) {
+  bf16* lo_or_null_dap = c.two_planes() ? w.dap + R * d.Qp : nullptr;
+  pool_bwd_kernel<<<grid_for(G, 1, 4 * g_dev.sm_count), 128, (L + d.Q) * sizeof(float), c.stream>>>(
+      d_vec, w.y, w.w, w.a, prm->add_query, d.E, d.Q, d.Qp, L, G, w.dy1, w.dap, lo_or_null_dap,
+      g->add_query);
+  LAUNCH_CHECK("pool_bwd");
+  // dY = dropout1'( dY1 + dApre W_add )  -> split planes
+  {
+    GemmEpi e = epi_none();
+    e.addend = w.dy1; e.ld_add = d.E;
+    e.hi = w.dyp; e.lo = w.dyp + R * d.Ep; e.ld_sp = d.Ep; e.sp_cols = d.Ep; e.ones_col = -1;
+    if (drop1.on) {
+      e.use_dropout = 1; e.drop_scale = drop1.scale; e.drop_thr = drop1.thr; e.drop_site = 1;
+      e.seed = drop1.seed; e.drop_ld = d.E;
+    }
+    TRY(gemm_nt(c, w.dap, R, d.Qp, w.wadd_t, d.E, d.Qp, d.Qp, e, "gemm additive dgrad"));
+  }
+  // dW_add, db_add
+  {
+    GemmEpi e = epi_none();
+    e.gw = g->add_weight; e.ld_gw = d.E; e.gw_cols = d.E; e.gb = g->add_bias;
+    TRY(gemm_tn(c, w.dap, d.Q, d.Qp, w.yp, d.Ep, d.Ep, R, e, "gemm additive wgrad"));
+  }
+  // dO = dY W_out
+  {
+    GemmEpi e = epi_none();
+    e.out = w.d_o; e.ld_out = d.E; e.out_cols = d.E;
+    TRY(gemm_nt(c, w.dyp, R, d.Ep, w.wout_t, d.E, d.Ep, d.Ep, e, "gemm out_proj dgrad"));
+  }
+  // dW_out, db_out
+  {
+    GemmEpi e = epi_none();
+    e.gw = g->out_proj_weight; e.ld_gw = d.E; e.gw_cols = d.E; e.gb = g->out_proj_bias;
+    TRY(gemm_tn(c, w.dyp, d.E, d.Ep, w.o, d.Ep, d.Ep, R, e, "gemm out_proj wgrad"));
+  }
+  if (d.DH == 16) launch_attn_bwd<16>(c, d, ag, w, R);
+  else if (d.DH == 20) launch_attn_bwd<20>(c, d, ag, w, R);
+  else launch_attn_bwd<32>(c, d, ag, w, R);
+  LAUNCH_CHECK("attn_bwd");
+  // dX = dropout0'( dQKV W_in )
+  {
+    GemmEpi e = epi_none();
+    e.out = w.dx; e.ld_out = d.E; e.out_cols = d.E;
+    if (drop0.on) {
+      e.use_dropout = 1; e.drop_scale = drop0.scale; e.drop_thr = drop0.thr; e.drop_site = 0;
+      e.seed = drop0.seed; e.drop_ld = d.E;
+    }
+    TRY(gemm_nt(c, w.dqkv, R, d.P3, w.win_t, d.E, d.P3, d.P3, e, "gemm in_proj dgrad"));
+  }
+  // dW_in, db_in
+  {
+    GemmEpi e = epi_none();
+    e.gw = g->in_proj_weight; e.ld_gw = d.E; e.gw_cols = d.E; e.gb = g->in_proj_bias;
+    TRY(gemm_tn(c, w.dqkv, 3 * d.E, d.P3, w.x, d.Ep, d.Ep, R, e, "gemm in_proj wgrad"));
+  }
+  return NRL_OK;
+}
+
+static int check_common(const void* ws, size_t ws_bytes, size_t need) {
+  if (!ws) return fail(NRL_ERR_INVALID_ARG, "workspace is NULL");
+  if ((reinterpret_cast<uintptr_t>(ws) & 1023) != 0)
+    return fail(NRL_ERR_INVALID_ARG, "workspace must be 1024-byte aligned");
+  if (ws_bytes < need)
+    return fail(NRL_ERR_WORKSPACE_TOO_SMALL, "workspace %zu < required %zu bytes", ws_bytes, need);
+  return NRL_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// news encoder
+// ----------------------------------------------------------------------------------------
+static int news_fwd_impl(const Ctx& c, const Dims& d, BlockWs& w, const long long* ids,
+                         long long n_news, int L, const float* table,
+                         const nrl_block_params* prm, const DropCfg& drop, float* out) {
+  const long long R = n_news * L;
+  TRY(pack_weights(c, d, prm, w));
+  gather_split_kernel<<<grid_for(R, 8, 1 << 20), 256, 0, c.stream>>>(
+      ids, R, table, d.E, d.Ep, w.x, c.two_planes() ? w.x + R * d.Ep : nullptr, nullptr, drop.on,
+      drop.scale, drop.thr, drop.seed);
+  LAUNCH_CHECK("gather_split");
+  AttnGeom ag{L, 1, (int)n_news, L};
+  return block_forward(c, d, w, R, ag, n_news, L, prm, drop, out);
+}
+static int news_bwd_impl(const Ctx& c, const Dims& d, BlockWs& w, const long long* ids,
+                         long long n_news, int L, const nrl_block_params* prm, const DropCfg& drop,
+                         const float* d_out, nrl_block_grads* g, float* d_table) {
+  const long long R = n_news * L;
+  AttnGeom ag{L, 1, (int)n_news, L};
+  TRY(block_backward(c, d, w, R, ag, n_news, L, prm, drop, drop, d_out, g));
+  if (d_table) {
+    emb_grad_kernel<<<grid_for(R, 8, 1 << 20), 256, 0, c.stream>>>(ids, R, w.dx, d.E, d_table);
+    LAUNCH_CHECK("emb_grad");
+  }
+  return NRL_OK;
+}
+
+extern "C" {
+
+const char* nrl_version(void) { return "newsreclib_b200 0.1 (sm_100a, tcgen05)"; }
+const char* nrl_last_error(void) { return g_err; }
+long long nrl_launch_count(void) { return g_launches.load(); }
+
+size_t nrl_news_encoder_ws_bytes(long long n_news, int L, nrl_dims dims) {
+  Dims d;
+  if (make_dims(dims, d) != NRL_OK || n_news < 0 || L <= 0) return 0;
+  Bump b(nullptr);
+  BlockWs w;
+  carve_block(b, n_news * L, d, w);
+  return b.off + 1024;
+}
+
+int nrl_news_encoder_fwd(const long long* ids, long long n_news, int L, const float* table,
+                         long long V1, const nrl_block_params* params, nrl_dims dims,
+                         float dropout_p, int training, unsigned long long seed, float* out,
+                         void* ws, size_t ws_bytes, int precision, void* stream) {
+  Dims d;
+  TRY(make_dims(dims, d));
+  if (!ids || !table || !params || !out || n_news <= 0 || L <= 0 || V1 <= 0)
+    return fail(NRL_ERR_INVALID_ARG, "nrl_news_encoder_fwd: null pointer or empty input");
+  if (dropout_p < 0.f || dropout_p >= 1.f) return fail(NRL_ERR_INVALID_ARG, "dropout_p out of [0,1)");
+  TRY(device_init());
+  TRY(check_common(ws, ws_bytes, nrl_news_encoder_ws_bytes(n_news, L, dims)));
+  Ctx c{static_cast<cudaStream_t>(stream), precision};
+  Bump b(ws);
+  BlockWs w;
+  carve_block(b, n_news * L, d, w);
+  return news_fwd_impl(c, d, w, ids, n_news, L, table, params, make_drop(dropout_p, training, seed), out);
+}
+
+int nrl_news_encoder_bwd(const long long* ids, long long n_news, int L, long long V1,
+                         const nrl_block_params* params, nrl_dims dims, float dropout_p,
+                         int training, unsigned long long seed, const float* d_out,
+                         nrl_block_grads* grads, float* d_table, void* ws, size_t ws_bytes,
+                         int precision, void* stream) {
+  Dims d;
+  TRY(make_dims(dims, d));
+  if (!ids || !params || !d_out || !grads || n_news <= 0 || L <= 0)
+    return fail(NRL_ERR_INVALID_ARG, "nrl_news_encoder_bwd: null pointer or empty input");
+  (void)V1;
+  TRY(device_init());
+  TRY(check_common(ws, ws_bytes, nrl_news_encoder_ws_bytes(n_news, L, dims)));
+  Ctx c{static_cast<cudaStream_t>(stream), precision};
+  Bump b(ws);
+  BlockWs w;
+  carve_block(b, n_news * L, d, w);
+  return news_bwd_impl(c, d, w, ids, n_news, L, params, make_drop(dropout_p, training, seed), d_out,
+                       grads, d_table);
+}
+
+// ----------------------------------------------------------------------------------------
+// user encoder
+// ----------------------------------------------------------------------------------------
+size_t nrl_user_encoder_ws_bytes(int B, int Hmax, nrl_dims dims) {
+  Dims d;
+  if (make_dims(dims, d) != NRL_OK || B <= 0 || Hmax <= 0) return 0;
+  Bump b(nullptr);
+  BlockWs w;
+  carve_block(b, (long long)B * Hmax, d, w);
+  return b.off + 1024;
+}
+
+static AttnGeom user_geom(int B, int Hmax, int axis) {
+  if (axis == 0) return AttnGeom{B, Hmax, Hmax, 1};  // reference: sequence = the B impressions
+  return AttnGeom{Hmax, 1, B, Hmax};                // along the history
+}
+
+int nrl_user_encoder_fwd(const float* hist, int B, int Hmax, const nrl_block_params* params,
+                         nrl_dims dims, int attention_axis, float* user, void* ws,
+                         size_t ws_bytes, int precision, void* stream) {
+  Dims d;
+  TRY(make_dims(dims, d));
+  if (!hist || !params || !user || B <= 0 || Hmax <= 0)
+    return fail(NRL_ERR_INVALID_ARG, "nrl_user_encoder_fwd: null pointer or empty input");
+  TRY(device_init());
+  TRY(check_common(ws, ws_bytes, nrl_user_encoder_ws_bytes(B, Hmax, dims)));
+  Ctx c{static_cast<cudaStream_t>(stream), precision};
+  Bump b(ws);
+  BlockWs w;
+  const long long R = (long long)B * Hmax;
+  carve_block(b, R, d, w);
+  TRY(pack_weights(c, d, params, w));
+  // dense rows -> split planes (identity "scatter": every row present)
+  dense_scatter_kernel<<<grid_for(R, 1, 1 << 20), 128, 0, c.stream>>>(
+      hist, nullptr, (int)R, 1, d.E, d.Ep, nullptr, w.x, c.two_planes() ? w.x + R * d.Ep : nullptr);
+  LAUNCH_CHECK("split_rows");
+  DropCfg nodrop = make_drop(0.f, 0, 0);
+  return block_forward(c, d, w, R, user_geom(B, Hmax, attention_axis), B, Hmax, params, nodrop, user);
+}
+
+int nrl_user_encoder_bwd(int B, int Hmax, const nrl_block_params* params, nrl_dims dims,
+                         int attention_axis, const float* d_user, nrl_block_grads* grads,
+                         float* d_hist, void* ws, size_t ws_bytes, int precision, void* stream) {
+  Dims d;
+  TRY(make_dims(dims, d));
+  if (!params || !d_user || !grads || !d_hist || B <= 0 || Hmax <= 0)
+    return fail(NRL_ERR_INVALID_ARG, "nrl_user_encoder_bwd: null pointer or empty input");
+  TRY(device_init());
+  TRY(check_common(ws, ws_bytes, nrl_user_encoder_ws_bytes(B, Hmax, dims)));
+  Ctx c{static_cast<cudaStream_t>(stream), precision};
+  Bump b(ws);
+  BlockWs w;
+  const long long R = (long long)B * Hmax;
+  carve_block(b, R, d, w);
+  DropCfg nodrop = make_drop(0.f, 0, 0);
+  TRY(block_backward(c, d, w, R, user_geom(B, Hmax, attention_axis), B, Hmax, params, nodrop, nodrop,
+                     d_user, grads));
+  CUDA_TRY(cudaMemcpyAsync(d_hist, w.dx, (size_t)R * d.E * sizeof(float), cudaMemcpyDeviceToDevice,
+                           c.stream));
+  return NRL_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// additive attention alone
+// ----------------------------------------------------------------------------------------
+size_t nrl_additive_ws_bytes(long long G, int L, int D, int Q) {
+  if (G <= 0 || L <= 0 || D <= 0 || Q <= 0) return 0;
+  const long long R = G * L;
+  const int Dp = round_up(D + 1, 16);
+  Bump b(nullptr);
+  b.take<bf16>(2ull * Q * Dp);
+  b.take<bf16>(2ull * D * round_up(Q, 16));
+  b.take<bf16>(2ull * R * Dp);
+  b.take<float>((size_t)R * Q);
+  b.take<float>((size_t)R);
+  b.take<float>((size_t)R);
+  return b.off + 1024;
+}
+
+int nrl_additive_fwd(const float* x, long long G, int L, int D, int Q, const float* weight,
+                     const float* bias, const float* query, float* out, void* ws,
+                     size_t ws_bytes, int precision, void* stream) {
+  if (!x || !weight || !bias || !query || !out || G <= 0 || L <= 0 || D <= 0 || Q <= 0 || Q > 256)
+    return fail(NRL_ERR_INVALID_ARG, "nrl_additive_fwd: bad argument");
+  TRY(device_init());
+  TRY(check_common(ws, ws_bytes, nrl_additive_ws_bytes(G, L, D, Q)));
+  Ctx c{static_cast<cudaStream_t>(stream), precision};
+  const long long R = G * L;
+  const int Dp = round_up(D + 1, 16), Qp = round_up(Q, 16);
+  Bump b(ws);
+  bf16* wf = b.take<bf16>(2ull * Q * Dp);
+  bf16* wt = b.take<bf16>(2ull * D * Qp);
+  bf16* xp = b.take<bf16>(2ull * R * Dp);
+  float* a = b.take<float>((size_t)R * Q);
+  float* s = b.take<float>((size_t)R);
+  float* wgt = b.take<float>((size_t)R);
+  const int tp = c.two_planes() ? 1 : 0;
+  pack_weight_kernel<<<grid_for((long long)Q * Dp + (long long)D * Qp, 256, 4096), 256, 0, c.stream>>>(
+      weight, bias, Q, D, Dp, Qp, wf, wt, tp);
+  LAUNCH_CHECK("pack_weight(additive)");
+  dense_scatter_kernel<<<grid_for(R, 1, 1 << 20), 128, 0, c.stream>>>(
+      x, nullptr, (int)R, 1, D, Dp, nullptr, xp, tp ? xp + R * Dp : nullptr);
+  LAUNCH_CHECK("split_rows");
+  GemmEpi e = epi_none();
+  e.qvec = query; e.tanh_out = a; e.ld_tanh = Q; e.score = s;
+  TRY(gemm_nt(c, xp, R, Dp, wf, Q, Dp, Dp, e, "gemm additive"));
+  pool_fwd_kernel<<<grid_for(G, 1, 1 << 20), 128, L * sizeof(float), c.stream>>>(s, x, D, L, G, wgt, out);
+  LAUNCH_CHECK("pool_fwd");
+  return NRL_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// ragged <-> dense, scorer, loss, optimizer
+// ----------------------------------------------------------------------------------------
+int nrl_segment_offsets(const long long* seg, long long n, int B, int* off, void* stream) {
+  if (!seg || !off || n < 0 || B <= 0) return fail(NRL_ERR_INVALID_ARG, "nrl_segment_offsets: bad argument");
+  segment_offsets_kernel<<<(B + 1 + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(seg, n, B, off);
+  LAUNCH_CHECK("segment_offsets");
+  return NRL_OK;
+}
+
+int nrl_to_dense_fwd(const float* x, const int* off, int B, int M, int E, float* dense, void* stream) {
+  if (!x || !off || !dense || B <= 0 || M <= 0 || E <= 0) return fail(NRL_ERR_INVALID_ARG, "nrl_to_dense_fwd: bad argument");
+  dense_scatter_kernel<<<grid_for((long long)B * M, 1, 1 << 20), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, off, B, M, E, E, dense, nullptr, nullptr);
+  LAUNCH_CHECK("dense_scatter");
+  return NRL_OK;
+}
+
+int nrl_to_dense_bwd(const float* d_dense, const int* off, int B, int M, int E, float* dx, void* stream) {
+  if (!d_dense || !off || !dx || B <= 0 || M <= 0 || E <= 0) return fail(NRL_ERR_INVALID_ARG, "nrl_to_dense_bwd: bad argument");
+  dim3 grid(M, B < 65535 ? B : 65535);
+  dense_gather_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(d_dense, off, B, M, E, dx);
+  LAUNCH_CHECK("dense_gather");
+  return NRL_OK;
+}
+
+int nrl_late_fusion_fwd(const float* hist_vec, const int* off, int B, int E, float* user, void* stream) {
+  if (!hist_vec || !off || !user || B <= 0 || E <= 0) return fail(NRL_ERR_INVALID_ARG, "nrl_late_fusion_fwd: bad argument");
+  late_fusion_fwd_kernel<<<B, 128, 0, static_cast<cudaStream_t>(stream)>>>(hist_vec, off, B, E, user);
+  LAUNCH_CHECK("late_fusion_fwd");
+  return NRL_OK;
+}
+int nrl_late_fusion_bwd(const float* d_user, const int* off, int B, int E, float* d_hist_vec, void* stream) {
+  if (!d_user || !off || !d_hist_vec || B <= 0 || E <= 0) return fail(NRL_ERR_INVALID_ARG, "nrl_late_fusion_bwd: bad argument");
+  late_fusion_bwd_kernel<<<B, 128, 0, static_cast<cudaStream_t>(stream)>>>(d_user, off, B, E, d_hist_vec);
+  LAUNCH_CHECK("late_fusion_bwd");
+  return NRL_OK;
+}
+
+int nrl_score_fwd(const float* user, const float* cand, const int* cand_off, int B, int Cmax, int E,
+                  float* scores, void* stream) {
+  if (!user || !cand || !cand_off || !scores || B <= 0 || Cmax <= 0 || E <= 0)
+    return fail(NRL_ERR_INVALID_ARG, "nrl_score_fwd: bad argument");
+  const long long warps = (long long)B * Cmax;
+  score_fwd_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      user, cand, cand_off, B, Cmax, E, scores);
+  LAUNCH_CHECK("score_fwd");
+  return NRL_OK;
+}
+int nrl_score_bwd(const float* d_scores, const float* user, const float* cand, const int* cand_off,
+                  int B, int Cmax, int E, float* d_user, float* d_cand, void* stream) {
+  if (!d_scores || !user || !cand || !cand_off || !d_user || !d_cand || B <= 0 || Cmax <= 0 || E <= 0)
+    return fail(NRL_ERR_INVALID_ARG, "nrl_score_bwd: bad argument");
+  score_bwd_kernel<<<B, 128, 0, static_cast<cudaStream_t>(stream)>>>(d_scores, user, cand, cand_off, B,
+                                                                     Cmax, E, d_user, d_cand);
+  LAUNCH_CHECK("score_bwd");
+  return NRL_OK;
+}
+
+int nrl_ce_soft_fwd(const float* scores, const float* labels, const int* cand_off, int B, int Cmax,
+                    float* loss_rows, float* loss_mean, float* y_dense, void* stream) {
+  if (!scores || !labels || !cand_off || !loss_mean || B <= 0 || Cmax <= 0)
+    return fail(NRL_ERR_INVALID_ARG, "nrl_ce_soft_fwd: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaMemsetAsync(loss_mean, 0, sizeof(float), st));
+  ce_fwd_kernel<<<(B + 3) / 4, 128, 0, st>>>(scores, labels, cand_off, B, Cmax, loss_rows, loss_mean, y_dense);
+  LAUNCH_CHECK("ce_fwd");
+  return NRL_OK;
+}
+int nrl_ce_soft_bwd(const float* scores, const float* labels, const int* cand_off, int B, int Cmax,
+                    const float* g_loss, float g_scale, float* d_scores, void* stream) {
+  if (!scores || !labels || !cand_off || !d_scores || B <= 0 || Cmax <= 0)
+    return fail(NRL_ERR_INVALID_ARG, "nrl_ce_soft_bwd: bad argument");
+  ce_bwd_kernel<<<(B + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(scores, labels, cand_off, B,
+                                                                           Cmax, g_loss, g_scale, d_scores);
+  LAUNCH_CHECK("ce_bwd");
+  return NRL_OK;
+}
+
+int nrl_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                  float beta2, float eps, long long step, float grad_scale, void* stream) {
+  if (!p || !g || !m || !v || n <= 0 || step <= 0) return fail(NRL_ERR_INVALID_ARG, "nrl_adam_step: bad argument");
+  const double bc1 = 1.0 - std::pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - std::pow((double)beta2, (double)step);
+  TRY(device_init());
+  adam_kernel<<<grid_for(n, 256 * 4, 8 * g_dev.sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      p, g, m, v, n, lr, beta1, beta2, eps, (float)bc1, (float)std::sqrt(bc2), grad_scale);
+  LAUNCH_CHECK("adam");
+  return NRL_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// whole NRMS pass
+// ----------------------------------------------------------------------------------------
+struct NrmsWs {
+  long long* ids;      // [N][L] hist then cand
+  long long* seg_h;    // staging (host variant)
+  long long* seg_c;
+  float* labels;
+  int *hist_off, *cand_off;
+  float* news_vec;     // [N][E]
+  float* user_vec;     // [B][E]
+  float* d_scores;     // [B][Cmax]
+  float* d_user;       // [B][E]
+  float* d_news;       // [N][E]
+  float* scores_dev;   // [B][Cmax] (host variant)
+  float* loss_dev;
+  BlockWs news, user;
+};
+static void carve_nrms(Bump& b, long long nh, long long nc, int L, int B, int Hmax, int Cmax,
+                       const Dims& d, NrmsWs& w) {
+  const long long N = nh + nc;
+  w.ids = b.take<long long>((size_t)N * L);
+  w.seg_h = b.take<long long>((size_t)nh);
+  w.seg_c = b.take<long long>((size_t)nc);
+  w.labels = b.take<float>((size_t)nc);
+  w.hist_off = b.take<int>(B + 1);
+  w.cand_off = b.take<int>(B + 1);
+  w.news_vec = b.take<float>((size_t)N * d.E);
+  w.user_vec = b.take<float>((size_t)B * d.E);
+  w.d_scores = b.take<float>((size_t)B * Cmax);
+  w.d_user = b.take<float>((size_t)B * d.E);
+  w.d_news = b.take<float>((size_t)N * d.E);
+  w.scores_dev = b.take<float>((size_t)B * Cmax);
+  w.loss_dev = b.take<float>(1);
+  carve_block(b, N * L, d, w.news);
+  carve_block(b, (long long)B * Hmax, d, w.user);
+}
+
+size_t nrl_nrms_ws_bytes(long long n_hist, long long n_cand, int L, int B, int Hmax, int Cmax,
+                         nrl_dims dims) {
+  Dims d;
+  if (make_dims(dims, d) != NRL_OK || n_hist <= 0 || n_cand <= 0 || L <= 0 || B <= 0 || Hmax <= 0 || Cmax <= 0)
+    return 0;
+  Bump b(nullptr);
+  NrmsWs w;
+  carve_nrms(b, n_hist, n_cand, L, B, Hmax, Cmax, d, w);
+  return b.off + 1024;
+}
+
+static int nrms_impl(const Ctx& c, const Dims& d, NrmsWs& w, const long long* hist_ids,
+                     const long long* cand_ids, const long long* seg_hist, const long long* seg_cand,
+                     const float* labels, long long nh, long long nc, int L, int B, int Hmax, int Cmax,
+                     const float* table, const nrl_block_params* np, const nrl_block_params* up,
+                     int late_fusion, const DropCfg& drop, float* scores, float* loss, int do_backward,
+                     nrl_block_grads* ng, nrl_block_grads* ug, float* d_table) {
+  const long long N = nh + nc;
+  segment_offsets_kernel<<<(B + 1 + 127) / 128, 128, 0, c.stream>>>(seg_hist, nh, B, w.hist_off);
+  LAUNCH_CHECK("segment_offsets(hist)");
+  segment_offsets_kernel<<<(B + 1 + 127) / 128, 128, 0, c.stream>>>(seg_cand, nc, B, w.cand_off);
+  LAUNCH_CHECK("segment_offsets(cand)");
+  if (hist_ids != w.ids)
+    CUDA_TRY(cudaMemcpyAsync(w.ids, hist_ids, (size_t)nh * L * sizeof(long long), cudaMemcpyDeviceToDevice, c.stream));
+  if (cand_ids != w.ids + nh * L)
+    CUDA_TRY(cudaMemcpyAsync(w.ids + nh * L, cand_ids, (size_t)nc * L * sizeof(long long), cudaMemcpyDeviceToDevice, c.stream));
+  // history and candidate titles share the news encoder: one pass over all N news
+  TRY(news_fwd_impl(c, d, w.news, w.ids, N, L, table, np, drop, w.news_vec));
+  const float* cand_vec = w.news_vec + nh * d.E;
+  const long long Ru = (long long)B * Hmax;
+  DropCfg nodrop = make_drop(0.f, 0, 0);
+  if (!late_fusion) {
+    TRY(pack_weights(c, d, up, w.user));
+    dense_scatter_kernel<<<grid_for(Ru, 1, 1 << 20), 128, 0, c.stream>>>(
+        w.news_vec, w.hist_off, B, Hmax, d.E, d.Ep, nullptr, w.user.x,
+        c.two_planes() ? w.user.x + Ru * d.Ep : nullptr);
+    LAUNCH_CHECK("dense_scatter(hist)");
+    TRY(block_forward(c, d, w.user, Ru, user_geom(B, Hmax, 0), B, Hmax, up, nodrop, w.user_vec));
+  } else {
+    late_fusion_fwd_kernel<<<B, 128, 0, c.stream>>>(w.news_vec, w.hist_off, B, d.E, w.user_vec);
+    LAUNCH_CHECK("late_fusion_fwd");
+  }
+  {
+    const long long warps = (long long)B * Cmax;
+    score_fwd_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, c.stream>>>(w.user_vec, cand_vec, w.cand_off, B,
+                                                                        Cmax, d.E, scores);
+    LAUNCH_CHECK("score_fwd");
+  }
+  if (loss) {
+    CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(float), c.stream));
+    ce_fwd_kernel<<<(B + 3) / 4, 128, 0, c.stream>>>(scores, labels, w.cand_off, B, Cmax, nullptr, loss, nullptr);
+    LAUNCH_CHECK("ce_fwd");
+  }
+  if (!do_backward) return NRL_OK;
+  if (!ng || (!late_fusion && !ug)) return fail(NRL_ERR_INVALID_ARG, "backward requested without gradient buffers");
+  ce_bwd_kernel<<<(B + 3) / 4, 128, 0, c.stream>>>(scores, labels, w.cand_off, B, Cmax, nullptr, 1.0f, w.d_scores);
+  LAUNCH_CHECK("ce_bwd");
+  score_bwd_kernel<<<B, 128, 0, c.stream>>>(w.d_scores, w.user_vec, cand_vec, w.cand_off, B, Cmax, d.E,
+                                            w.d_user, w.d_news + nh * d.E);
+  LAUNCH_CHECK("score_bwd");
+  if (!late_fusion) {
+    TRY(block_backward(c, d, w.user, Ru, user_geom(B, Hmax, 0), B, Hmax, up, nodrop, nodrop, w.d_user, ug));
+    dim3 grid(Hmax, B < 65535 ? B : 65535);
+    dense_gather_kernel<<<grid, 128, 0, c.stream>>>(w.user.dx, w.hist_off, B, Hmax, d.E, w.d_news);
+    LAUNCH_CHECK("dense_gather");
+  } else {
+    late_fusion_bwd_kernel<<<B, 128, 0, c.stream>>>(w.d_user, w.hist_off, B, d.E, w.d_news);
+    LAUNCH_CHECK("late_fusion_bwd");
+  }
+  return news_bwd_impl(c, d, w.news, w.ids, N, L, np, drop, w.d_news, ng, d_table);
+}
+
+static int nrms_check(long long nh, long long nc, int L, int B, int Hmax, int Cmax, const float* table,
+                      long long V1, const nrl_block_params* np, const nrl_block_params* up, int late_fusion,
+                      float dropout_p) {
+  if (nh <= 0 || nc <= 0 || L <= 0 || B <= 0 || Hmax <= 0 || Cmax <= 0 || V1 <= 0)
+    return fail(NRL_ERR_INVALID_ARG, "nrl_nrms_step: empty batch or non-positive size");
+  if (!table || !np || (!late_fusion && !up)) return fail(NRL_ERR_INVALID_ARG, "nrl_nrms_step: null parameter pointer");
+  if (dropout_p < 0.f || dropout_p >= 1.f) return fail(NRL_ERR_INVALID_ARG, "dropout_p out of [0,1)");
+  return NRL_OK;
+}
+
+int nrl_nrms_step(const long long* hist_ids, const long long* cand_ids, const long long* seg_hist,
+                  const long long* seg_cand, const float* labels, long long n_hist, long long n_cand,
+                  int L, int B, int Hmax, int Cmax, const float* table, long long V1,
+                  const nrl_block_params* news_params, const nrl_block_params* user_params,
+                  nrl_dims dims, int late_fusion, float dropout_p, int training,
+                  unsigned long long seed, float* scores, float* loss, int do_backward,
+                  nrl_block_grads* news_grads, nrl_block_grads* user_grads, float* d_table, void* ws,
+                  size_t ws_bytes, int precision, void* stream) {
+  Dims d;
+  TRY(make_dims(dims, d));
+  TRY(nrms_check(n_hist, n_cand, L, B, Hmax, Cmax, table, V1, news_params, user_params, late_fusion, dropout_p));
+  if (!hist_ids || !cand_ids || !seg_hist || !seg_cand || !scores || ((loss || do_backward) && !labels))
+    return fail(NRL_ERR_INVALID_ARG, "nrl_nrms_step: null input pointer");
+  TRY(device_init());
+  TRY(check_common(ws, ws_bytes, nrl_nrms_ws_bytes(n_hist, n_cand, L, B, Hmax, Cmax, dims)));
+  Ctx c{static_cast<cudaStream_t>(stream), precision};
+  Bump b(ws);
+  NrmsWs w;
+  carve_nrms(b, n_hist, n_cand, L, B, Hmax, Cmax, d, w);
+  return nrms_impl(c, d, w, hist_ids, cand_ids, seg_hist, seg_cand, labels, n_hist, n_cand, L, B, Hmax,
+                   Cmax, table, news_params, user_params, late_fusion,
+                   make_drop(dropout_p, training, seed), scores, loss, do_backward, news_grads,
+                   user_grads, d_table);
+}
+
+int nrl_nrms_step_host(const long long* hist_ids_host, const long long* cand_ids_host,
+                       const long long* seg_hist_host, const long long* seg_cand_host,
+                       const float* labels_host, long long n_hist, long long n_cand, int L, int B,
+                       int Hmax, int Cmax, const float* table, long long V1,
+                       const nrl_block_params* news_params, const nrl_block_params* user_params,
+                       nrl_dims dims, int late_fusion, float dropout_p, int training,
+                       unsigned long long seed, float* scores_host, float* loss_host, int do_backward,
+                       nrl_block_grads* news_grads, nrl_block_grads* user_grads, float* d_table,
+                       void* ws, size_t ws_bytes, int precision, void* stream) {
+  Dims d;
+  TRY(make_dims(dims, d));
+  TRY(nrms_check(n_hist, n_cand, L, B, Hmax, Cmax, table, V1, news_params, user_params, late_fusion, dropout_p));
+  if (!hist_ids_host || !cand_ids_host || !seg_hist_host || !seg_cand_host || !scores_host ||
+      ((loss_host || do_backward) && !labels_host))
+    return fail(NRL_ERR_INVALID_ARG, "nrl_nrms_step_host: null input pointer");
+  TRY(device_init());
+  TRY(check_common(ws, ws_bytes, nrl_nrms_ws_bytes(n_hist, n_cand, L, B, Hmax, Cmax, dims)));
+  Ctx c{static_cast<cudaStream_t>(stream), precision};
+  Bump b(ws);
+  NrmsWs w;
+  carve_nrms(b, n_hist, n_cand, L, B, Hmax, Cmax, d, w);
+  CUDA_TRY(cudaMemcpyAsync(w.ids, hist_ids_host, (size_t)n_hist * L * sizeof(long long), cudaMemcpyHostToDevice, c.stream));
+  CUDA_TRY(cudaMemcpyAsync(w.ids + n_hist * L, cand_ids_host, (size_t)n_cand * L * sizeof(long long), cudaMemcpyHostToDevice, c.stream));
+  CUDA_TRY(cudaMemcpyAsync(w.seg_h, seg_hist_host, (size_t)n_hist * sizeof(long long), cudaMemcpyHostToDevice, c.stream));
+  CUDA_TRY(cudaMemcpyAsync(w.seg_c, seg_cand_host, (size_t)n_cand * sizeof(long long), cudaMemcpyHostToDevice, c.stream));
+  if (labels_host)
+    CUDA_TRY(cudaMemcpyAsync(w.labels, labels_host, (size_t)n_cand * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+  TRY(nrms_impl(c, d, w, w.ids, w.ids + n_hist * L, w.seg_h, w.seg_c, w.labels, n_hist, n_cand, L, B, Hmax,
+                Cmax, table, news_params, user_params, late_fusion, make_drop(dropout_p, training, seed),
+                w.scores_dev, loss_host ? w.loss_dev : nullptr, do_backward, news_grads, user_grads, d_table));
+  CUDA_TRY(cudaMemcpyAsync(scores_host, w.scores_dev, (size_t)B * Cmax * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+  if (loss_host)
+    CUDA_TRY(cudaMemcpyAsync(loss_host, w.loss_dev, sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+  CUDA_TRY(cudaStreamSynchronize(c.stream));
+  return NRL_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// test helpers
+// ----------------------------------------------------------------------------------------
+int nrl_dropout_mask(unsigned char* keep, long long n, unsigned long long seed, int site, float p,
+                     void* stream) {
+  if (!keep || n <= 0 || p < 0.f || p >= 1.f) return fail(NRL_ERR_INVALID_ARG, "nrl_dropout_mask: bad argument");
+  dropout_mask_kernel<<<grid_for(n, 256, 1 << 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      keep, n, seed, (uint32_t)site, drop_threshold(p));
+  LAUNCH_CHECK("dropout_mask");
+  return NRL_OK;
+}
+
+size_t nrl_gemm_test_ws_bytes(int M, int N, int K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  Bump b(nullptr);
+  // worst case of the two layouts
+  const long long big = (long long)(M > K ? M : K) + 16, bigp = round_up((M > K ? M : K), 16) + 16;
+  const long long bign = (long long)(N > K ? N : K) + 16;
+  b.take<bf16>(2ull * big * bigp);
+  b.take<bf16>(2ull * bign * (round_up(N > K ? N : K, 16) + 16));
+  return b.off + 1024;
+}
+
+int nrl_gemm_test(const float* A, const float* B, float* D, int M, int N, int K, int mn_major,
+                  int precision, void* ws, size_t ws_bytes, void* stream) {
+  if (!A || !B || !D || M <= 0 || N <= 0 || K <= 0) return fail(NRL_ERR_INVALID_ARG, "nrl_gemm_test: bad argument");
+  TRY(device_init());
+  TRY(check_common(ws, ws_bytes, nrl_gemm_test_ws_bytes(M, N, K)));
+  Ctx c{static_cast<cudaStream_t>(stream), precision};
+  const int tp = c.two_planes() ? 1 : 0;
+  Bump b(ws);
+  const long long big = (long long)(M > K ? M : K) + 16, bigp = round_up((M > K ? M : K), 16) + 16;
+  const long long bign = (long long)(N > K ? N : K) + 16;
+  bf16* ap = b.take<bf16>(2ull * big * bigp);
+  bf16* bp = b.take<bf16>(2ull * bign * (round_up(N > K ? N : K, 16) + 16));
+  if (!mn_major) {
+    const int Kp = round_up(K, 16);
+    dense_scatter_kernel<<<grid_for(M, 1, 1 << 20), 128, 0, c.stream>>>(A, nullptr, M, 1, K, Kp, nullptr, ap, tp ? ap + (long long)M * Kp : nullptr);
+    LAUNCH_CHECK("split_rows(A)");
+    dense_scatter_kernel<<<grid_for(N, 1, 1 << 20), 128, 0, c.stream>>>(B, nullptr, N, 1, K, Kp, nullptr, bp, tp ? bp + (long long)N * Kp : nullptr);
+    LAUNCH_CHECK("split_rows(B)");
+    // the split kernel writes 1.0 at column K when Kp > K; the tensor-map extent is K, so TMA
+    // zero-fills from column K on and the ones column never reaches the MMA.
+    GemmEpi e = epi_none();
+    e.out = D; e.ld_out = N; e.out_cols = N;
+    return gemm_nt(c, ap, M, Kp, bp, N, Kp, K, e, "gemm_test nt");
+  } else {
+    const int Mp = round_up(M, 16), Np = round_up(N, 16);
+    dense_scatter_kernel<<<grid_for(K, 1, 1 << 20), 128, 0, c.stream>>>(A, nullptr, K, 1, M, Mp, nullptr, ap, tp ? ap + (long long)K * Mp : nullptr);
+    LAUNCH_CHECK("split_rows(A)");
+    dense_scatter_kernel<<<grid_for(K, 1, 1 << 20), 128, 0, c.stream>>>(B, nullptr, K, 1, N, Np, nullptr, bp, tp ? bp + (long long)K * Np : nullptr);
+    LAUNCH_CHECK("split_rows(B)");
+    GemmEpi e = epi_none();
+    e.gw = D; e.ld_gw = N; e.gw_cols = N; e.gb = nullptr;
+    return gemm_tn(c, ap, M, Mp, bp, N, Np, K, e, "gemm_test tn");
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,724 @@
+// Memory-bound / small-contraction kernels of the NRMS hot path (sm_100a, fp32 SIMT):
+// weight packing, embedding gather (+dropout, bf16 hi/lo split), per-head self-attention
+// forward/backward (any sequence axis: title tokens, or the reference's batch-axis quirk),
+// additive-attention pooling forward/backward, ragged<->dense, scorer, soft-target CE,
+// embedding-gradient scatter, Adam.
+#pragma once
+#include "nrl_ptx.cuh"
+
+namespace nrl {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// block-wide sum, result broadcast to every thread; `red` holds >= 33 floats
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    float t = lane < nw ? red[lane] : 0.f;
+    t = warp_sum(t);
+    if (lane == 0) red[32] = t;
+  }
+  __syncthreads();
+  return red[32];
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    float t = lane < nw ? red[lane] : -INFINITY;
+    t = warp_max(t);
+    if (lane == 0) red[32] = t;
+  }
+  __syncthreads();
+  return red[32];
+}
+
+// ------------------------------------------------------------------------------------
+// Weight packing.  W [n_out, k_in] fp32 (+ bias [n_out]) ->
+//   wf[plane][n_out][kp]   forward operand, K-major; column k_in holds the bias (the activation
+//                          planes carry a constant 1.0 there), other pad columns 0
+//   wt[plane][k_in][np]    transposed operand for the data-gradient GEMM, pad columns 0
+// ------------------------------------------------------------------------------------
+__global__ void pack_weight_kernel(const float* __restrict__ W, const float* __restrict__ bias,
+                                   int n_out, int k_in, int kp, int np, __nv_bfloat16* wf,
+                                   __nv_bfloat16* wt, int two_planes) {
+  const long long nf = (long long)n_out * kp, nt = (long long)k_in * np;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nf + nt;
+       i += (long long)gridDim.x * blockDim.x) {
+    float x;
+    __nv_bfloat16* dst;
+    long long plane_stride, off;
+    if (i < nf) {
+      int n = (int)(i / kp), k = (int)(i % kp);
+      x = k < k_in ? W[(long long)n * k_in + k] : (k == k_in && bias ? bias[n] : 0.f);
+      dst = wf; plane_stride = nf; off = i;
+    } else {
+      long long j = i - nf;
+      int k = (int)(j / np), n = (int)(j % np);
+      x = n < n_out ? W[(long long)n * k_in + k] : 0.f;
+      dst = wt; plane_stride = nt; off = j;
+    }
+    __nv_bfloat16 h, l;
+    split_bf16(x, h, l);
+    dst[off] = h;
+    if (two_planes) dst[plane_stride + off] = l;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// a2/a3: embedding gather (+ dropout site 0) -> split planes [2][R][ep], ones column at E.
+// One warp per token row; rows of the table are 16-byte aligned when E % 4 == 0.
+// ------------------------------------------------------------------------------------
+__global__ void gather_split_kernel(const long long* __restrict__ ids, long long R,
+                                    const float* __restrict__ table, int E, int ep,
+                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                    float* __restrict__ x_f32, int use_dropout, float drop_scale,
+                                    uint32_t drop_thr, unsigned long long seed) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp0; r < R; r += nwarps) {
+    const long long id = ids[r];
+    const float* src = table + id * E;
+    for (int c = lane * 4; c < ep; c += 128) {
+      float v[4];
+      if (c + 4 <= E && (E & 3) == 0) {
+        float4 t = __ldg(reinterpret_cast<const float4*>(src + c));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = (c + i < E) ? __ldg(src + c + i) : 0.f;
+      }
+      if (use_dropout) {
+        unsigned long long e0 = (unsigned long long)r * (unsigned)E + (unsigned)c;
+        if ((e0 & 3ull) == 0) {
+          Philox4 rr = philox4x32_10(seed, e0 >> 3, 0u);
+          int s0 = (int)(e0 & 7ull);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            v[i] = philox_u16(rr, s0 + i) >= drop_thr ? v[i] * drop_scale : 0.f;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            v[i] = drop_keep(seed, 0u, e0 + i, drop_thr) ? v[i] * drop_scale : 0.f;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (c + i >= E) v[i] = (c + i == E) ? 1.f : 0.f;
+      if (x_f32) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (c + i < E) x_f32[r * E + c + i] = v[i];
+      }
+      __nv_bfloat16 h[4], l[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) split_bf16(v[i], h[i], l[i]);
+      const long long off = r * ep + c;  // ep % 8 == 0 and c % 4 == 0 -> 8-byte aligned
+      *reinterpret_cast<uint2*>(hi + off) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+      if (lo)
+        *reinterpret_cast<uint2*>(lo + off) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// a4 core: per-(batch item, head) softmax(q k^T) v over an arbitrary sequence axis.
+//   row(seq s, batch b) = s * seq_stride + b * batch_stride        (rows of QKV [R, 3E] fp32)
+//   title encoder : S = L,  seq_stride = 1,    NB = #news, batch_stride = L
+//   user encoder  : S = B,  seq_stride = Hmax, NB = Hmax,  batch_stride = 1   (reference quirk)
+// One warp per (b, head, 32-query chunk); keys streamed through per-warp smem in chunks of 32
+// with an online softmax.  Writes O as split planes (+ ones column / zero pad) and the row
+// log-sum-exp for the backward pass.
+// ------------------------------------------------------------------------------------
+template <int DH>
+__global__ void __launch_bounds__(128)
+attn_fwd_kernel(const float* __restrict__ qkv, int E, int heads, int S, long long seq_stride,
+                int NB, long long batch_stride, float scale, __nv_bfloat16* __restrict__ o_hi,
+                __nv_bfloat16* __restrict__ o_lo, int ep, float* __restrict__ lse) {
+  __shared__ __align__(16) float sk[4][32 * DH];
+  __shared__ __align__(16) float sv[4][32 * DH];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qchunks = (S + 31) / 32;
+  const long long items = (long long)NB * heads * qchunks;
+  const int ld = 3 * E;
+  for (long long it = blockIdx.x * 4ll + warp; it < items; it += gridDim.x * 4ll) {
+    const int qc = (int)(it % qchunks);
+    const int h = (int)((it / qchunks) % heads);
+    const int b = (int)(it / ((long long)qchunks * heads));
+    const int t = qc * 32 + lane;
+    const bool q_ok = t < S;
+    const long long qrow = (long long)(q_ok ? t : 0) * seq_stride + (long long)b * batch_stride;
+    float q[DH], o[DH];
+#pragma unroll
+    for (int d = 0; d < DH; d += 4) {
+      float4 t4 = __ldg(reinterpret_cast<const float4*>(qkv + qrow * ld + h * DH + d));
+      q[d] = t4.x * scale; q[d + 1] = t4.y * scale; q[d + 2] = t4.z * scale; q[d + 3] = t4.w * scale;
+      o[d] = o[d + 1] = o[d + 2] = o[d + 3] = 0.f;
+    }
+    float m = -INFINITY, l = 0.f;
+    for (int k0 = 0; k0 < S; k0 += 32) {
+      const int nk = min(32, S - k0);
+      __syncwarp();
+      for (int i = lane; i < nk * (DH / 4); i += 32) {
+        const int u = i / (DH / 4), d4 = i % (DH / 4);
+        const long long krow = (long long)(k0 + u) * seq_stride + (long long)b * batch_stride;
+        reinterpret_cast<float4*>(sk[warp])[u * (DH / 4) + d4] =
+            __ldg(reinterpret_cast<const float4*>(qkv + krow * ld + E + h * DH) + d4);
+        reinterpret_cast<float4*>(sv[warp])[u * (DH / 4) + d4] =
+            __ldg(reinterpret_cast<const float4*>(qkv + krow * ld + 2 * E + h * DH) + d4);
+      }
+      __syncwarp();
+      float s[32];
+      float cmax = -INFINITY;
+#pragma unroll
+      for (int u = 0; u < 32; ++u) {
+        float acc = 0.f;
+        if (u < nk) {
+#pragma unroll
+          for (int d = 0; d < DH; d += 4) {
+            float4 k4 = reinterpret_cast<const float4*>(sk[warp])[u * (DH / 4) + d / 4];
+            acc += q[d] * k4.x + q[d + 1] * k4.y + q[d + 2] * k4.z + q[d + 3] * k4.w;
+          }
+          cmax = fmaxf(cmax, acc);
+        }
+        s[u] = acc;
+      }
+      const float m_new = fmaxf(m, cmax);
+      const float corr = __expf(m - m_new);  // m = -inf on the first chunk -> 0
+      l *= corr;
+#pragma unroll
+      for (int d = 0; d < DH; ++d) o[d] *= corr;
+#pragma unroll
+      for (int u = 0; u < 32; ++u) {
+        if (u < nk) {
+          const float pu = expf(s[u] - m_new);
+          l += pu;
+#pragma unroll
+          for (int d = 0; d < DH; d += 4) {
+            float4 v4 = reinterpret_cast<const float4*>(sv[warp])[u * (DH / 4) + d / 4];
+            o[d] += pu * v4.x; o[d + 1] += pu * v4.y; o[d + 2] += pu * v4.z; o[d + 3] += pu * v4.w;
+          }
+        }
+      }
+      m = m_new;
+    }
+    if (q_ok) {
+      const float inv = 1.f / l;
+      lse[qrow * heads + h] = m + logf(l);
+      const long long off = qrow * ep + h * DH;  // DH % 4 == 0 -> 8-byte aligned
+#pragma unroll
+      for (int d = 0; d < DH; d += 4) {
+        __nv_bfloat16 hh[4], ll[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split_bf16(o[d + i] * inv, hh[i], ll[i]);
+        *reinterpret_cast<uint2*>(o_hi + off + d) = make_uint2(pack_bf16x2(hh[0], hh[1]), pack_bf16x2(hh[2], hh[3]));
+        if (o_lo)
+          *reinterpret_cast<uint2*>(o_lo + off + d) = make_uint2(pack_bf16x2(ll[0], ll[1]), pack_bf16x2(ll[2], ll[3]));
+      }
+      if (h == 0) {  // pad columns: ones column at E, zeros after
+        for (int c = E; c < ep; ++c) {
+          o_hi[qrow * ep + c] = __float2bfloat16_rn(c == E ? 1.f : 0.f);
+          if (o_lo) o_lo[qrow * ep + c] = __float2bfloat16_rn(0.f);
+        }
+      }
+    }
+  }
+}
+
+// Backward of the attention core.  One warp per (b, head): phase A (lane = query) gives dQ,
+// phase B (lane = key) gives dK / dV; P is recomputed from Q, K and the saved log-sum-exp,
+// D = rowsum(dO * O) from the saved O planes.  Writes dQKV as split planes [2][R][p3].
+template <int DH>
+__global__ void __launch_bounds__(128)
+attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o, long long ld_do,
+                const __nv_bfloat16* __restrict__ o_hi, const __nv_bfloat16* __restrict__ o_lo,
+                int ep, const float* __restrict__ lse, int E, int heads, int S,
+                long long seq_stride, int NB, long long batch_stride, float scale,
+                __nv_bfloat16* __restrict__ g_hi, __nv_bfloat16* __restrict__ g_lo, int p3) {
+  // per-warp staging: "x" rows (k/v in phase A, q/dO in phase B), plus lse / D per row
+  __shared__ __align__(16) float sa[4][32 * DH];
+  __shared__ __align__(16) float sb[4][32 * DH];
+  __shared__ float s_lse[4][32];
+  __shared__ float s_dd[4][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long items = (long long)NB * heads;
+  const int ld = 3 * E;
+  const int chunks = (S + 31) / 32;
+  auto store_split = [&](long long row, int col, const float* v) {
+    const long long off = row * p3 + col;
+#pragma unroll
+    for (int d = 0; d < DH; d += 4) {
+      __nv_bfloat16 hh[4], ll[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) split_bf16(v[d + i], hh[i], ll[i]);
+      *reinterpret_cast<uint2*>(g_hi + off + d) = make_uint2(pack_bf16x2(hh[0], hh[1]), pack_bf16x2(hh[2], hh[3]));
+      if (g_lo)
+        *reinterpret_cast<uint2*>(g_lo + off + d) = make_uint2(pack_bf16x2(ll[0], ll[1]), pack_bf16x2(ll[2], ll[3]));
+    }
+  };
+  for (long long it = blockIdx.x * 4ll + warp; it < items; it += gridDim.x * 4ll) {
+    const int h = (int)(it % heads);
+    const int b = (int)(it / heads);
+    // ---------------- phase A: lane = query, loop over key chunks -> dQ ----------------
+    for (int qc = 0; qc < chunks; ++qc) {
+      const int t = qc * 32 + lane;
+      const bool ok = t < S;
+      const long long row = (long long)(ok ? t : 0) * seq_stride + (long long)b * batch_stride;
+      float q[DH], go[DH], dq[DH];
+      float dd = 0.f;
+#pragma unroll
+      for (int d = 0; d < DH; d += 4) {
+        float4 t4 = __ldg(reinterpret_cast<const float4*>(qkv + row * ld + h * DH + d));
+        q[d] = t4.x * scale; q[d + 1] = t4.y * scale; q[d + 2] = t4.z * scale; q[d + 3] = t4.w * scale;
+        float4 g4 = __ldg(reinterpret_cast<const float4*>(d_o + row * ld_do + h * DH + d));
+        go[d] = g4.x; go[d + 1] = g4.y; go[d + 2] = g4.z; go[d + 3] = g4.w;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float ov = __bfloat162float(o_hi[row * ep + h * DH + d + i]);
+          if (o_lo) ov += __bfloat162float(o_lo[row * ep + h * DH + d + i]);
+          dd += go[d + i] * ov;
+          dq[d + i] = 0.f;
+        }
+      }
+      const float my_lse = lse[row * heads + h];
+      for (int k0 = 0; k0 < S; k0 += 32) {
+        const int nk = min(32, S - k0);
+        __syncwarp();
+        for (int i = lane; i < nk * (DH / 4); i += 32) {
+          const int u = i / (DH / 4), d4 = i % (DH / 4);
+          const long long krow = (long long)(k0 + u) * seq_stride + (long long)b * batch_stride;
+          reinterpret_cast<float4*>(sa[warp])[u * (DH / 4) + d4] =
+              __ldg(reinterpret_cast<const float4*>(qkv + krow * ld + E + h * DH) + d4);
+          reinterpret_cast<float4*>(sb[warp])[u * (DH / 4) + d4] =
+              __ldg(reinterpret_cast<const float4*>(qkv + krow * ld + 2 * E + h * DH) + d4);
+        }
+        __syncwarp();
+        for (int u = 0; u < nk; ++u) {
+          float sc = 0.f, dp = 0.f;
+#pragma unroll
+          for (int d = 0; d < DH; d += 4) {
+            float4 k4 = reinterpret_cast<const float4*>(sa[warp])[u * (DH / 4) + d / 4];
+            float4 v4 = reinterpret_cast<const float4*>(sb[warp])[u * (DH / 4) + d / 4];
+            sc += q[d] * k4.x + q[d + 1] * k4.y + q[d + 2] * k4.z + q[d + 3] * k4.w;
+            dp += go[d] * v4.x + go[d + 1] * v4.y + go[d + 2] * v4.z + go[d + 3] * v4.w;
+          }
+          const float ds = expf(sc - my_lse) * (dp - dd);
+#pragma unroll
+          for (int d = 0; d < DH; d += 4) {
+            float4 k4 = reinterpret_cast<const float4*>(sa[warp])[u * (DH / 4) + d / 4];
+            dq[d] += ds * k4.x; dq[d + 1] += ds * k4.y; dq[d + 2] += ds * k4.z; dq[d + 3] += ds * k4.w;
+          }
+        }
+      }
+      if (ok) {
+#pragma unroll
+        for (int d = 0; d < DH; ++d) dq[d] *= scale;
+        store_split(row, h * DH, dq);
+        if (h == 0) {
+          for (int c = 3 * E; c < p3; ++c) {
+            g_hi[row * p3 + c] = __float2bfloat16_rn(0.f);
+            if (g_lo) g_lo[row * p3 + c] = __float2bfloat16_rn(0.f);
+          }
+        }
+      }
+    }
+    // ---------------- phase B: lane = key, loop over query chunks -> dK, dV ----------------
+    for (int kc = 0; kc < chunks; ++kc) {
+      const int u = kc * 32 + lane;
+      const bool ok = u < S;
+      const long long row = (long long)(ok ? u : 0) * seq_stride + (long long)b * batch_stride;
+      float kk[DH], vv[DH], dk[DH], dv[DH];
+#pragma unroll
+      for (int d = 0; d < DH; d += 4) {
+        float4 k4 = __ldg(reinterpret_cast<const float4*>(qkv + row * ld + E + h * DH + d));
+        float4 v4 = __ldg(reinterpret_cast<const float4*>(qkv + row * ld + 2 * E + h * DH + d));
+        kk[d] = k4.x; kk[d + 1] = k4.y; kk[d + 2] = k4.z; kk[d + 3] = k4.w;
+        vv[d] = v4.x; vv[d + 1] = v4.y; vv[d + 2] = v4.z; vv[d + 3] = v4.w;
+        dk[d] = dk[d + 1] = dk[d + 2] = dk[d + 3] = 0.f;
+        dv[d] = dv[d + 1] = dv[d + 2] = dv[d + 3] = 0.f;
+      }
+      for (int q0 = 0; q0 < S; q0 += 32) {
+        const int nq = min(32, S - q0);
+        __syncwarp();
+        for (int i = lane; i < nq * (DH / 4); i += 32) {
+          const int t = i / (DH / 4), d4 = i % (DH / 4);
+          const long long qrow = (long long)(q0 + t) * seq_stride + (long long)b * batch_stride;
+          float4 q4 = __ldg(reinterpret_cast<const float4*>(qkv + qrow * ld + h * DH) + d4);
+          q4.x *= scale; q4.y *= scale; q4.z *= scale; q4.w *= scale;
+          reinterpret_cast<float4*>(sa[warp])[t * (DH / 4) + d4] = q4;
+          reinterpret_cast<float4*>(sb[warp])[t * (DH / 4) + d4] =
+              __ldg(reinterpret_cast<const float4*>(d_o + qrow * ld_do + h * DH) + d4);
+        }
+        if (lane < nq) {
+          const long long qrow = (long long)(q0 + lane) * seq_stride + (long long)b * batch_stride;
+          float dd = 0.f;
+          for (int d = 0; d < DH; ++d) {
+            float ov = __bfloat162float(o_hi[qrow * ep + h * DH + d]);
+            if (o_lo) ov += __bfloat162float(o_lo[qrow * ep + h * DH + d]);
+            dd += d_o[qrow * ld_do + h * DH + d] * ov;
+          }
+          s_dd[warp][lane] = dd;
+          s_lse[warp][lane] = lse[qrow * heads + h];
+        }
+        __syncwarp();
+        for (int t = 0; t < nq; ++t) {
+          float sc = 0.f, dp = 0.f;
+#pragma unroll
+          for (int d = 0; d < DH; d += 4) {
+            float4 q4 = reinterpret_cast<const float4*>(sa[warp])[t * (DH / 4) + d / 4];
+            float4 g4 = reinterpret_cast<const float4*>(sb[warp])[t * (DH / 4) + d / 4];
+            sc += q4.x * kk[d] + q4.y * kk[d + 1] + q4.z * kk[d + 2] + q4.w * kk[d + 3];
+            dp += g4.x * vv[d] + g4.y * vv[d + 1] + g4.z * vv[d + 2] + g4.w * vv[d + 3];
+          }
+          const float pr = expf(sc - s_lse[warp][t]);
+          const float ds = pr * (dp - s_dd[warp][t]);
+#pragma unroll
+          for (int d = 0; d < DH; d += 4) {
+            float4 q4 = reinterpret_cast<const float4*>(sa[warp])[t * (DH / 4) + d / 4];
+            float4 g4 = reinterpret_cast<const float4*>(sb[warp])[t * (DH / 4) + d / 4];
+            dk[d] += ds * q4.x; dk[d + 1] += ds * q4.y; dk[d + 2] += ds * q4.z; dk[d + 3] += ds * q4.w;
+            dv[d] += pr * g4.x; dv[d + 1] += pr * g4.y; dv[d + 2] += pr * g4.z; dv[d + 3] += pr * g4.w;
+          }
+        }
+      }
+      if (ok) {
+        store_split(row, E + h * DH, dk);
+        store_split(row, 2 * E + h * DH, dv);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// a5: additive pooling.  Group g owns rows g*L .. g*L+L-1.  score[r] = tanh(xW+b).q comes
+// from the GEMM epilogue; here: w = softmax_L(score), out[g] = sum_t w_t * Y[row_t].
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+pool_fwd_kernel(const float* __restrict__ score, const float* __restrict__ Y, int E, int L,
+                long long G, float* __restrict__ w_out, float* __restrict__ out) {
+  extern __shared__ float sw[];  // L weights
+  __shared__ float red[33];
+  for (long long g = blockIdx.x; g < G; g += gridDim.x) {
+    const long long r0 = g * L;
+    float mx = -INFINITY;
+    for (int t = threadIdx.x; t < L; t += blockDim.x) mx = fmaxf(mx, score[r0 + t]);
+    mx = block_max(mx, red);
+    float sum = 0.f;
+    for (int t = threadIdx.x; t < L; t += blockDim.x) {
+      float e = expf(score[r0 + t] - mx);
+      sw[t] = e;
+      sum += e;
+    }
+    sum = block_sum(sum, red);
+    const float inv = 1.f / sum;
+    for (int t = threadIdx.x; t < L; t += blockDim.x) {
+      float w = sw[t] * inv;
+      sw[t] = w;
+      w_out[r0 + t] = w;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < E; c += blockDim.x) {
+      float acc = 0.f;
+      for (int t = 0; t < L; ++t) acc += sw[t] * Y[(r0 + t) * E + c];
+      out[g * E + c] = acc;
+    }
+    __syncthreads();
+  }
+}
+
+// Backward of additive pooling (through softmax, the q-dot and tanh):
+//   dY1[r]   = w_r * dOut[g]                                  (fp32, later += dApre * W_add)
+//   dApre[r] = ds_r * q * (1 - A_r^2),  ds_r = w_r (dOut.Y_r - sum_u w_u dOut.Y_u)   (split planes)
+//   dq      += sum_r ds_r * A_r                                (atomics, once per block)
+__global__ void __launch_bounds__(128)
+pool_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ Y,
+                const float* __restrict__ w, const float* __restrict__ A,
+                const float* __restrict__ qvec, int E, int Q, int qp, int L, long long G,
+                float* __restrict__ dY1, __nv_bfloat16* __restrict__ da_hi,
+                __nv_bfloat16* __restrict__ da_lo, float* __restrict__ dq_accum) {
+  extern __shared__ float sm[];  // [L] ds, then [Q] dq partial
+  float* s_ds = sm;
+  float* s_dq = sm + L;
+  __shared__ float red[33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int j = threadIdx.x; j < Q; j += blockDim.x) s_dq[j] = 0.f;
+  __syncthreads();
+  for (long long g = blockIdx.x; g < G; g += gridDim.x) {
+    const long long r0 = g * L;
+    // dw_t = dOut . Y_t  (one warp per row)
+    for (int t = warp; t < L; t += nw) {
+      float acc = 0.f;
+      for (int c = lane; c < E; c += 32) acc += d_out[g * E + c] * Y[(r0 + t) * E + c];
+      acc = warp_sum(acc);
+      if (lane == 0) s_ds[t] = acc;
+    }
+    __syncthreads();
+    float part = 0.f;
+    for (int t = threadIdx.x; t < L; t += blockDim.x) part += w[r0 + t] * s_ds[t];
+    const float dbar = block_sum(part, red);
+    for (int t = threadIdx.x; t < L; t += blockDim.x) s_ds[t] = w[r0 + t] * (s_ds[t] - dbar);
+    __syncthreads();
+    for (int i = threadIdx.x; i < L * E; i += blockDim.x) {
+      const int t = i / E, c = i % E;
+      dY1[(r0 + t) * E + c] = w[r0 + t] * d_out[g * E + c];
+    }
+    for (int i = threadIdx.x; i < L * qp; i += blockDim.x) {
+      const int t = i / qp, j = i % qp;
+      float v = 0.f;
+      if (j < Q) {
+        const float a = A[(r0 + t) * Q + j];
+        v = s_ds[t] * qvec[j] * (1.f - a * a);
+      }
+      __nv_bfloat16 hh, ll;
+      split_bf16(v, hh, ll);
+      da_hi[(r0 + t) * qp + j] = hh;
+      if (da_lo) da_lo[(r0 + t) * qp + j] = ll;
+    }
+    for (int j = threadIdx.x; j < Q; j += blockDim.x) {
+      float acc = 0.f;
+      for (int t = 0; t < L; ++t) acc += s_ds[t] * A[(r0 + t) * Q + j];
+      s_dq[j] += acc;
+    }
+    __syncthreads();
+  }
+  for (int j = threadIdx.x; j < Q; j += blockDim.x) atomicAdd(dq_accum + j, s_dq[j]);
+}
+
+// ------------------------------------------------------------------------------------
+// a8: ragged -> dense (to_dense_batch) and back.  off[B+1] are CSR offsets of the sorted
+// segment ids.  Dense rows beyond a segment's length are zero (their ones column stays 1:
+// padded history rows still receive the in-projection bias, as in the reference).
+// ------------------------------------------------------------------------------------
+__global__ void segment_offsets_kernel(const long long* __restrict__ seg, long long n, int B,
+                                       int* __restrict__ off) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > B) return;
+  long long lo = 0, hi = n;  // first index with seg[i] >= b
+  while (lo < hi) {
+    long long mid = (lo + hi) >> 1;
+    if (seg[mid] < b) lo = mid + 1; else hi = mid;
+  }
+  off[b] = (int)lo;
+}
+
+__global__ void dense_scatter_kernel(const float* __restrict__ x, const int* __restrict__ off,
+                                     int B, int M, int E, int ep, float* __restrict__ dense,
+                                     __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  for (long long r = blockIdx.x; r < (long long)B * M; r += gridDim.x) {
+    const int b = (int)(r / M), j = (int)(r % M);
+    // off == nullptr: identity (every dense row present, M == 1 per "segment")
+    const int cnt = off ? off[b + 1] - off[b] : M;
+    const float* src = j < cnt ? x + (off ? (long long)(off[b] + j) : r) * E : nullptr;
+    for (int c = threadIdx.x; c < ep; c += blockDim.x) {
+      float v = c < E ? (src ? src[c] : 0.f) : (c == E ? 1.f : 0.f);
+      if (dense && c < E) dense[r * E + c] = v;
+      if (hi) {
+        __nv_bfloat16 hh, ll;
+        split_bf16(v, hh, ll);
+        hi[r * ep + c] = hh;
+        if (lo) lo[r * ep + c] = ll;
+      }
+    }
+  }
+}
+
+__global__ void dense_gather_kernel(const float* __restrict__ d_dense, const int* __restrict__ off,
+                                    int B, int M, int E, float* __restrict__ dx) {
+  for (int b = blockIdx.y; b < B; b += gridDim.y) {
+    const int cnt = off[b + 1] - off[b];
+    for (int j = blockIdx.x; j < cnt; j += gridDim.x)
+      for (int c = threadIdx.x; c < E; c += blockDim.x)
+        dx[(long long)(off[b] + j) * E + c] = d_dense[((long long)b * M + j) * E + c];
+  }
+}
+
+// a10: late fusion, user = sum_j dense[b, j, :] / count_b  (nrms_module.py:243-248)
+__global__ void late_fusion_fwd_kernel(const float* __restrict__ x, const int* __restrict__ off,
+                                       int B, int E, float* __restrict__ user) {
+  const int b = blockIdx.x;
+  const int cnt = off[b + 1] - off[b];
+  for (int c = threadIdx.x; c < E; c += blockDim.x) {
+    float acc = 0.f;
+    for (int j = 0; j < cnt; ++j) acc += x[(long long)(off[b] + j) * E + c];
+    user[(long long)b * E + c] = acc / (float)cnt;
+  }
+}
+__global__ void late_fusion_bwd_kernel(const float* __restrict__ d_user, const int* __restrict__ off,
+                                       int B, int E, float* __restrict__ dx) {
+  const int b = blockIdx.x;
+  const int cnt = off[b + 1] - off[b];
+  for (int j = 0; j < cnt; ++j)
+    for (int c = threadIdx.x; c < E; c += blockDim.x)
+      dx[(long long)(off[b] + j) * E + c] = d_user[(long long)b * E + c] / (float)cnt;
+}
+
+// ------------------------------------------------------------------------------------
+// a11: scorer.  scores[b, c] = user_b . cand[off[b]+c]  (exactly 0.0 in padded slots).
+// One warp per (b, c).
+// ------------------------------------------------------------------------------------
+__global__ void score_fwd_kernel(const float* __restrict__ user, const float* __restrict__ cand,
+                                 const int* __restrict__ off, int B, int C, int E,
+                                 float* __restrict__ scores) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (wid >= (long long)B * C) return;
+  const int b = (int)(wid / C), c = (int)(wid % C);
+  const int cnt = off[b + 1] - off[b];
+  float acc = 0.f;
+  if (c < cnt) {
+    const float* u = user + (long long)b * E;
+    const float* n = cand + (long long)(off[b] + c) * E;
+    for (int i = lane; i < E; i += 32) acc += u[i] * n[i];
+    acc = warp_sum(acc);
+  }
+  if (lane == 0) scores[wid] = acc;
+}
+// d_user[b] = sum_c ds[b,c] cand[b,c];  d_cand[off[b]+c] = ds[b,c] user[b].  Block per b.
+__global__ void score_bwd_kernel(const float* __restrict__ d_scores, const float* __restrict__ user,
+                                 const float* __restrict__ cand, const int* __restrict__ off, int B,
+                                 int C, int E, float* __restrict__ d_user, float* __restrict__ d_cand) {
+  const int b = blockIdx.x;
+  const int cnt = off[b + 1] - off[b];
+  for (int i = threadIdx.x; i < E; i += blockDim.x) {
+    const float u = user[(long long)b * E + i];
+    float acc = 0.f;
+    for (int c = 0; c < cnt; ++c) {
+      const float ds = d_scores[(long long)b * C + c];
+      acc += ds * cand[(long long)(off[b] + c) * E + i];
+      d_cand[(long long)(off[b] + c) * E + i] = ds * u;
+    }
+    d_user[(long long)b * E + i] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// a12: CrossEntropyLoss with float targets over the dense [B, C] score matrix, mean over B.
+// Labels arrive ragged ([N_c], same offsets as the candidates); padded slots have target 0
+// and score 0 and take part in the softmax.  One warp per row.
+// ------------------------------------------------------------------------------------
+__global__ void ce_fwd_kernel(const float* __restrict__ scores, const float* __restrict__ labels,
+                              const int* __restrict__ off, int B, int C, float* __restrict__ loss_rows,
+                              float* __restrict__ loss_mean, float* __restrict__ y_dense) {
+  const int lane = threadIdx.x & 31;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= B) return;
+  const int cnt = off[b + 1] - off[b];
+  float mx = -INFINITY;
+  for (int c = lane; c < C; c += 32) mx = fmaxf(mx, scores[(long long)b * C + c]);
+  mx = warp_max(mx);
+  float se = 0.f;
+  for (int c = lane; c < C; c += 32) se += expf(scores[(long long)b * C + c] - mx);
+  se = warp_sum(se);
+  const float lz = mx + logf(se);
+  float acc = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float y = c < cnt ? labels[off[b] + c] : 0.f;
+    if (y_dense) y_dense[(long long)b * C + c] = y;
+    acc += y * (lz - scores[(long long)b * C + c]);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    if (loss_rows) loss_rows[b] = acc;
+    if (loss_mean) atomicAdd(loss_mean, acc / (float)B);
+  }
+}
+// d s[b,c] = g/B * (softmax(s)[b,c] * sum_c' y[b,c'] - y[b,c])
+__global__ void ce_bwd_kernel(const float* __restrict__ scores, const float* __restrict__ labels,
+                              const int* __restrict__ off, int B, int C,
+                              const float* __restrict__ g_loss, float g_scale,
+                              float* __restrict__ d_scores) {
+  const int lane = threadIdx.x & 31;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= B) return;
+  const int cnt = off[b + 1] - off[b];
+  const float g = (g_loss ? g_loss[0] : 1.f) * g_scale / (float)B;
+  float mx = -INFINITY;
+  for (int c = lane; c < C; c += 32) mx = fmaxf(mx, scores[(long long)b * C + c]);
+  mx = warp_max(mx);
+  float se = 0.f, sy = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    se += expf(scores[(long long)b * C + c] - mx);
+    sy += c < cnt ? labels[off[b] + c] : 0.f;
+  }
+  se = warp_sum(se);
+  sy = warp_sum(sy);
+  for (int c = lane; c < C; c += 32) {
+    const float y = c < cnt ? labels[off[b] + c] : 0.f;
+    const float pr = expf(scores[(long long)b * C + c] - mx) / se;
+    d_scores[(long long)b * C + c] = g * (pr * sy - y);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Embedding gradient: d_table[ids[r]] += dX[r]  (dense [V1, E] table gradient, row 0 = the
+// padding_idx row is skipped so its gradient stays exactly zero, text.py:215-217).
+// One warp per token row, 128-bit vector atomics.
+// ------------------------------------------------------------------------------------
+__global__ void emb_grad_kernel(const long long* __restrict__ ids, long long R,
+                                const float* __restrict__ dX, int E, float* __restrict__ d_table) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp0; r < R; r += nwarps) {
+    const long long id = ids[r];
+    if (id == 0) continue;
+    const float* src = dX + r * E;
+    float* dst = d_table + id * E;
+    if ((E & 3) == 0) {
+      for (int c = lane * 4; c < E; c += 128) {
+        float4 v = *reinterpret_cast<const float4*>(src + c);
+        atomicAdd(reinterpret_cast<float4*>(dst + c), v);
+      }
+    } else {
+      for (int c = lane; c < E; c += 32) atomicAdd(dst + c, src[c]);
+    }
+  }
+}
+
+// torch.optim.Adam (no weight decay / amsgrad), dense over n elements.
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, float lr, float b1, float b2,
+                            float eps, float bc1, float sqrt_bc2, float g_scale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * g_scale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / sqrt_bc2 + eps;
+    p[i] -= (lr / bc1) * (mi / denom);
+  }
+}
+
+__global__ void dropout_mask_kernel(unsigned char* __restrict__ keep, long long n,
+                                    unsigned long long seed, uint32_t site, uint32_t thr) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    keep[i] = drop_keep(seed, site, (unsigned long long)i, thr) ? 1 : 0;
+}
+
+// acc[i] += x[i]
+__global__ void add_inplace_kernel(float* __restrict__ acc, const float* __restrict__ x, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    acc[i] += x[i];
+}
+
+}  // namespace nrl

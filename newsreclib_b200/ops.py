@@ -1,0 +1,324 @@
+"""Torch-facing wrappers of the C ABI: raw calls on ``torch`` CUDA tensors (device pointers
+and the current stream are handed to the library; torch only owns the memory) and the
+``torch.autograd.Function``s the drop-in modules use.
+
+No function here computes anything on the CPU or through ATen kernels on the hot path; a
+missing library or a non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import BlockParams, Dims, PREC_BF16, PREC_BF16X3  # noqa: F401
+
+BLOCK_KEYS = (
+    "multihead_attention.in_proj_weight",
+    "multihead_attention.in_proj_bias",
+    "multihead_attention.out_proj.weight",
+    "multihead_attention.out_proj.bias",
+    "additive_attention.linear.weight",
+    "additive_attention.linear.bias",
+    "additive_attention.query",
+)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (newsreclib_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+    return t
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def block_struct(tensors) -> BlockParams:
+    """Seven tensors in ``BLOCK_KEYS`` order -> ``nrl_block_params``."""
+    s = BlockParams()
+    for (name, _), t in zip(BlockParams._fields_, tensors):
+        setattr(s, name, _p(_chk(t, torch.float32, name)))
+    return s
+
+
+def block_from_dict(params: Dict[str, torch.Tensor], prefix: str):
+    return [params[prefix + k] for k in BLOCK_KEYS]
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    # torch's caching allocator returns 512-byte aligned blocks; over-allocate and slice to 1 KiB
+    buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+    shift = (-buf.data_ptr()) % 1024
+    return buf[shift: shift + nbytes]
+
+
+def dims_of(E: int, H: int, Q: int) -> Dims:
+    return Dims(int(E), int(H), int(Q))
+
+
+# ----------------------------------------------------------------------------------------
+# raw calls
+# ----------------------------------------------------------------------------------------
+def gemm_test(A: torch.Tensor, B: torch.Tensor, mn_major: bool, precision: int = PREC_BF16X3) -> torch.Tensor:
+    lib = _lib.load()
+    _chk(A, torch.float32, "A"); _chk(B, torch.float32, "B")
+    if not mn_major:
+        M, K = A.shape; N = B.shape[0]
+    else:
+        K, M = A.shape; N = B.shape[1]
+    D = torch.zeros(M, N, dtype=torch.float32, device=A.device)
+    ws = workspace(lib.nrl_gemm_test_ws_bytes(M, N, K), A.device)
+    _lib.check(lib.nrl_gemm_test(_p(A), _p(B), _p(D), M, N, K, int(mn_major), precision, _p(ws),
+                                 ws.numel(), _stream()), "nrl_gemm_test")
+    return D
+
+
+def dropout_mask(n: int, seed: int, site: int, p: float, device) -> torch.Tensor:
+    lib = _lib.load()
+    keep = torch.empty(n, dtype=torch.uint8, device=device)
+    _lib.check(lib.nrl_dropout_mask(_p(keep), n, seed, site, p, _stream()), "nrl_dropout_mask")
+    return keep
+
+
+def segment_offsets(seg: torch.Tensor, B: int) -> torch.Tensor:
+    lib = _lib.load()
+    _chk(seg, torch.int64, "segment ids")
+    off = torch.empty(B + 1, dtype=torch.int32, device=seg.device)
+    _lib.check(lib.nrl_segment_offsets(_p(seg), seg.numel(), B, _p(off), _stream()), "nrl_segment_offsets")
+    return off
+
+
+def adam_step(p, g, m, v, step: int, lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0) -> None:
+    lib = _lib.load()
+    for t, n in ((p, "p"), (g, "g"), (m, "m"), (v, "v")):
+        _chk(t, torch.float32, n)
+    _lib.check(lib.nrl_adam_step(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, step,
+                                 grad_scale, _stream()), "nrl_adam_step")
+
+
+def nrms_step(batch: Dict, table: torch.Tensor, news_block, user_block, dims: Dims, *, B: int,
+              Hmax: int, Cmax: int, late_fusion: bool = False, dropout_p: float = 0.0,
+              training: bool = False, seed: int = 0, want_loss: bool = True,
+              grads: Optional[Tuple] = None, ws: Optional[torch.Tensor] = None,
+              precision: int = PREC_BF16X3, scores: Optional[torch.Tensor] = None,
+              loss: Optional[torch.Tensor] = None):
+    """One pass of the hot path on device-resident inputs (``nrl_nrms_step``).
+
+    ``grads`` = (news_grad_tensors[7], user_grad_tensors[7] or None, d_table) enables backward
+    (gradients accumulate).  Returns (scores [B, Cmax], loss [1] or None, ws)."""
+    lib = _lib.load()
+    hist_ids = _chk(batch["x_hist"]["title"], torch.int64, "x_hist.title")
+    cand_ids = _chk(batch["x_cand"]["title"], torch.int64, "x_cand.title")
+    seg_h = _chk(batch["batch_hist"], torch.int64, "batch_hist")
+    seg_c = _chk(batch["batch_cand"], torch.int64, "batch_cand")
+    labels = _chk(batch["labels"], torch.float32, "labels")
+    _chk(table, torch.float32, "table")
+    nh, L = hist_ids.shape
+    nc = cand_ids.shape[0]
+    dev = table.device
+    need = lib.nrl_nrms_ws_bytes(nh, nc, L, B, Hmax, Cmax, dims)
+    if ws is None or ws.numel() < need:
+        ws = workspace(need, dev)
+    if scores is None:
+        scores = torch.empty(B, Cmax, dtype=torch.float32, device=dev)
+    if loss is None and (want_loss or grads is not None):
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+    nb = block_struct(news_block)
+    ub = block_struct(user_block) if user_block is not None else None
+    ng = ug = None
+    d_table = None
+    if grads is not None:
+        ng = block_struct(grads[0])
+        ug = block_struct(grads[1]) if grads[1] is not None else None
+        d_table = grads[2]
+    _lib.check(lib.nrl_nrms_step(
+        _p(hist_ids), _p(cand_ids), _p(seg_h), _p(seg_c), _p(labels), nh, nc, L, B, Hmax, Cmax,
+        _p(table), table.shape[0], C.byref(nb), C.byref(ub) if ub is not None else None, dims,
+        int(late_fusion), float(dropout_p), int(training), int(seed), _p(scores), _p(loss),
+        int(grads is not None), C.byref(ng) if ng is not None else None,
+        C.byref(ug) if ug is not None else None, _p(d_table), _p(ws), ws.numel(), precision,
+        _stream()), "nrl_nrms_step")
+    return scores, loss, ws
+
+
+# ----------------------------------------------------------------------------------------
+# autograd functions used by the drop-in modules
+# ----------------------------------------------------------------------------------------
+class NewsEncoderFn(torch.autograd.Function):
+    """``MHSAAddAtt.forward`` (reference ``encoders/news/text.py:222-236``)."""
+
+    @staticmethod
+    def forward(ctx, ids, table, w_in, b_in, w_out, b_out, w_add, b_add, q_add, num_heads,
+                dropout_p, training, seed, precision):
+        lib = _lib.load()
+        _chk(ids, torch.int64, "ids"); _chk(table, torch.float32, "embedding table")
+        n, L = ids.shape
+        dims = dims_of(table.shape[1], num_heads, q_add.numel())
+        blk = [w_in, b_in, w_out, b_out, w_add, b_add, q_add]
+        out = torch.empty(n, table.shape[1], dtype=torch.float32, device=table.device)
+        ws = workspace(lib.nrl_news_encoder_ws_bytes(n, L, dims), table.device)
+        bs = block_struct(blk)
+        _lib.check(lib.nrl_news_encoder_fwd(_p(ids), n, L, _p(table), table.shape[0], C.byref(bs), dims,
+                                            float(dropout_p), int(training), int(seed), _p(out), _p(ws),
+                                            ws.numel(), precision, _stream()), "nrl_news_encoder_fwd")
+        ctx.save_for_backward(ids, table, *blk)
+        ctx.ws, ctx.dims, ctx.cfg = ws, dims, (float(dropout_p), int(training), int(seed), precision)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        ids, table, *blk = ctx.saved_tensors
+        n, L = ids.shape
+        p, training, seed, precision = ctx.cfg
+        d_out = d_out.contiguous().float()
+        grads = [torch.zeros_like(t) for t in blk]
+        d_table = torch.zeros_like(table)
+        bs, gs = block_struct(blk), block_struct(grads)
+        _lib.check(lib.nrl_news_encoder_bwd(_p(ids), n, L, table.shape[0], C.byref(bs), ctx.dims, p, training,
+                                            seed, _p(d_out), C.byref(gs), _p(d_table), _p(ctx.ws),
+                                            ctx.ws.numel(), precision, _stream()), "nrl_news_encoder_bwd")
+        ctx.ws = None
+        return (None, d_table, *grads, None, None, None, None, None)
+
+
+class UserEncoderFn(torch.autograd.Function):
+    """NRMS ``UserEncoder.forward`` (reference ``encoders/user/nrms.py:32-41``)."""
+
+    @staticmethod
+    def forward(ctx, hist, w_in, b_in, w_out, b_out, w_add, b_add, q_add, num_heads, attention_axis,
+                precision):
+        lib = _lib.load()
+        hist = _chk(hist.contiguous(), torch.float32, "hist")
+        B, Hmax, E = hist.shape
+        dims = dims_of(E, num_heads, q_add.numel())
+        blk = [w_in, b_in, w_out, b_out, w_add, b_add, q_add]
+        user = torch.empty(B, E, dtype=torch.float32, device=hist.device)
+        ws = workspace(lib.nrl_user_encoder_ws_bytes(B, Hmax, dims), hist.device)
+        bs = block_struct(blk)
+        _lib.check(lib.nrl_user_encoder_fwd(_p(hist), B, Hmax, C.byref(bs), dims, int(attention_axis),
+                                            _p(user), _p(ws), ws.numel(), precision, _stream()),
+                   "nrl_user_encoder_fwd")
+        ctx.save_for_backward(*blk)
+        ctx.ws, ctx.dims, ctx.cfg = ws, dims, (B, Hmax, E, int(attention_axis), precision)
+        return user
+
+    @staticmethod
+    def backward(ctx, d_user):
+        lib = _lib.load()
+        blk = list(ctx.saved_tensors)
+        B, Hmax, E, axis, precision = ctx.cfg
+        d_user = d_user.contiguous().float()
+        grads = [torch.zeros_like(t) for t in blk]
+        d_hist = torch.empty(B, Hmax, E, dtype=torch.float32, device=d_user.device)
+        bs, gs = block_struct(blk), block_struct(grads)
+        _lib.check(lib.nrl_user_encoder_bwd(B, Hmax, C.byref(bs), ctx.dims, axis, _p(d_user), C.byref(gs),
+                                            _p(d_hist), _p(ctx.ws), ctx.ws.numel(), precision, _stream()),
+                   "nrl_user_encoder_bwd")
+        ctx.ws = None
+        return (d_hist, *grads, None, None, None)
+
+
+class ToDenseFn(torch.autograd.Function):
+    """``to_dense_batch`` values (torch_geometric 2.3.0; call sites ``nrms_module.py:233,237``)."""
+
+    @staticmethod
+    def forward(ctx, x, off, B, M):
+        lib = _lib.load()
+        x = _chk(x.contiguous(), torch.float32, "x")
+        E = x.shape[1]
+        dense = torch.empty(B, M, E, dtype=torch.float32, device=x.device)
+        _lib.check(lib.nrl_to_dense_fwd(_p(x), _p(off), B, M, E, _p(dense), _stream()), "nrl_to_dense_fwd")
+        ctx.save_for_backward(off)
+        ctx.cfg = (B, M, E, x.shape[0])
+        return dense
+
+    @staticmethod
+    def backward(ctx, d_dense):
+        lib = _lib.load()
+        (off,) = ctx.saved_tensors
+        B, M, E, n = ctx.cfg
+        d_dense = d_dense.contiguous().float()
+        dx = torch.zeros(n, E, dtype=torch.float32, device=d_dense.device)
+        _lib.check(lib.nrl_to_dense_bwd(_p(d_dense), _p(off), B, M, E, _p(dx), _stream()), "nrl_to_dense_bwd")
+        return dx, None, None, None
+
+
+class ScoreFn(torch.autograd.Function):
+    """``DotProduct.forward`` on ragged candidates (``layers/click_predictor.py:9-11``)."""
+
+    @staticmethod
+    def forward(ctx, user, cand, off, B, Cmax):
+        lib = _lib.load()
+        user = _chk(user.contiguous(), torch.float32, "user")
+        cand = _chk(cand.contiguous(), torch.float32, "cand")
+        E = user.shape[1]
+        scores = torch.empty(B, Cmax, dtype=torch.float32, device=user.device)
+        _lib.check(lib.nrl_score_fwd(_p(user), _p(cand), _p(off), B, Cmax, E, _p(scores), _stream()), "nrl_score_fwd")
+        ctx.save_for_backward(user, cand, off)
+        ctx.cfg = (B, Cmax, E)
+        return scores
+
+    @staticmethod
+    def backward(ctx, d_scores):
+        lib = _lib.load()
+        user, cand, off = ctx.saved_tensors
+        B, Cmax, E = ctx.cfg
+        d_scores = d_scores.contiguous().float()
+        d_user = torch.empty_like(user)
+        d_cand = torch.zeros_like(cand)
+        _lib.check(lib.nrl_score_bwd(_p(d_scores), _p(user), _p(cand), _p(off), B, Cmax, E, _p(d_user),
+                                     _p(d_cand), _stream()), "nrl_score_bwd")
+        return d_user, d_cand, None, None, None
+
+
+class CESoftFn(torch.autograd.Function):
+    """``CrossEntropyLoss()(scores, y_true)`` with float targets (``nrms_module.py:277,288``)."""
+
+    @staticmethod
+    def forward(ctx, scores, labels, off):
+        lib = _lib.load()
+        scores = _chk(scores.contiguous(), torch.float32, "scores")
+        labels = _chk(labels.contiguous(), torch.float32, "labels")
+        B, Cmax = scores.shape
+        loss = torch.empty(1, dtype=torch.float32, device=scores.device)
+        _lib.check(lib.nrl_ce_soft_fwd(_p(scores), _p(labels), _p(off), B, Cmax, None, _p(loss), None,
+                                       _stream()), "nrl_ce_soft_fwd")
+        ctx.save_for_backward(scores, labels, off)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        scores, labels, off = ctx.saved_tensors
+        B, Cmax = scores.shape
+        g = g.contiguous().float().reshape(1)
+        d = torch.empty_like(scores)
+        _lib.check(lib.nrl_ce_soft_bwd(_p(scores), _p(labels), _p(off), B, Cmax, _p(g), 1.0, _p(d), _stream()),
+                   "nrl_ce_soft_bwd")
+        return d, None, None
+
+
+def additive_attention(x: torch.Tensor, weight, bias, query, precision: int = PREC_BF16X3) -> torch.Tensor:
+    """``AdditiveAttention.forward`` (``layers/attention.py:24-42``), forward only."""
+    lib = _lib.load()
+    x = _chk(x.contiguous(), torch.float32, "x")
+    G, L, D = x.shape
+    Q = query.numel()
+    out = torch.empty(G, D, dtype=torch.float32, device=x.device)
+    ws = workspace(lib.nrl_additive_ws_bytes(G, L, D, Q), x.device)
+    _lib.check(lib.nrl_additive_fwd(_p(x), G, L, D, Q, _p(_chk(weight, torch.float32, "weight")),
+                                    _p(_chk(bias, torch.float32, "bias")), _p(_chk(query, torch.float32, "query")),
+                                    _p(out), _p(ws), ws.numel(), precision, _stream()), "nrl_additive_fwd")
+    return out

@@ -1,0 +1,99 @@
+"""Shared helpers for the parity tests (test infrastructure; may import the oracle)."""
+import os
+
+import numpy as np
+import torch
+
+from newsreclib_b200.synthetic import make_batch, make_nrms_params
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TITLE = "news_encoder.text_encoders.title."
+USER = "user_encoder."
+
+
+def load_golden(name):
+    g = dict(np.load(os.path.join(GOLD, name + ".npz")))
+    E, H, Q, V, B, max_hist, seed, L = [int(x) for x in g["meta"]]
+    if any(k.startswith("param/") for k in g):
+        params = {k[len("param/"):]: torch.from_numpy(g[k]) for k in g if k.startswith("param/")}
+    else:
+        params = make_nrms_params(V, E, H, Q, seed=seed)
+        chk = np.array([float(v.double().sum()) for v in params.values()])
+        assert np.allclose(chk, g["param_checksum"], rtol=1e-9), "seeded parameter generator drifted"
+    batch = {
+        "x_hist": {"title": torch.from_numpy(g["hist_title"])},
+        "x_cand": {"title": torch.from_numpy(g["cand_title"])},
+        "batch_hist": torch.from_numpy(g["batch_hist"]),
+        "batch_cand": torch.from_numpy(g["batch_cand"]),
+        "labels": torch.from_numpy(g["labels"]),
+    }
+    return g, params, batch, dict(E=E, H=H, Q=Q, V=V, B=B, L=L)
+
+
+def rel_err(a, b):
+    a = torch.as_tensor(a, dtype=torch.float64).cpu()
+    b = torch.as_tensor(b, dtype=torch.float64).cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def batch_sizes(batch):
+    B = int(batch["batch_hist"].max()) + 1
+    Hmax = int(torch.bincount(batch["batch_hist"], minlength=B).max())
+    Cmax = int(torch.bincount(batch["batch_cand"], minlength=B).max())
+    return B, Hmax, Cmax
+
+
+def to_dev(batch, dev="cuda"):
+    return {
+        "x_hist": {"title": batch["x_hist"]["title"].to(dev)},
+        "x_cand": {"title": batch["x_cand"]["title"].to(dev)},
+        "batch_hist": batch["batch_hist"].to(dev),
+        "batch_cand": batch["batch_cand"].to(dev),
+        "labels": batch["labels"].to(dev),
+    }
+
+
+def oracle_run(params, batch, H, masks=None, dropout_p=0.0, late_fusion=False, grad=True):
+    """Oracle forward (+ autograd backward) on CPU; returns scores, loss, grads."""
+    from oracle import nrms_oracle as O
+
+    ps = {k: v.clone().requires_grad_(grad) for k, v in params.items()}
+    scores = O.nrms_forward(batch, ps, H, late_fusion=late_fusion, masks=masks, dropout_p=dropout_p)
+    loss = O.nrms_loss(batch, scores)
+    grads = None
+    if grad:
+        loss.backward()
+        grads = {k: (v.grad.detach().clone() if v.grad is not None else torch.zeros_like(v)) for k, v in ps.items()}
+        grads[TITLE + "embedding_layer.weight"][0] = 0  # padding_idx=0 (text.py:215-217)
+    return scores.detach(), loss.detach(), grads
+
+
+def gpu_run(params, batch, H, precision=0, do_backward=True, dropout_p=0.0, training=False, seed=0,
+            late_fusion=False):
+    """The CUDA path through the C ABI (nrl_nrms_step)."""
+    from newsreclib_b200 import ops
+
+    dev = "cuda"
+    P = {k: v.to(dev).contiguous() for k, v in params.items()}
+    b = to_dev(batch, dev)
+    B, Hmax, Cmax = batch_sizes(batch)
+    table = P[TITLE + "embedding_layer.weight"]
+    E = table.shape[1]
+    Q = P[TITLE + "additive_attention.query"].numel()
+    nb = ops.block_from_dict(P, TITLE)
+    ub = ops.block_from_dict(P, USER)
+    grads = None
+    if do_backward:
+        grads = ([torch.zeros_like(t) for t in nb], [torch.zeros_like(t) for t in ub], torch.zeros_like(table))
+    scores, loss, _ = ops.nrms_step(b, table, nb, None if late_fusion else ub, ops.dims_of(E, H, Q), B=B,
+                                    Hmax=Hmax, Cmax=Cmax, late_fusion=late_fusion, dropout_p=dropout_p,
+                                    training=training, seed=seed, grads=grads, precision=precision)
+    torch.cuda.synchronize()
+    out_g = None
+    if do_backward:
+        out_g = {TITLE + "embedding_layer.weight": grads[2].cpu()}
+        for k, t in zip(ops.BLOCK_KEYS, grads[0]):
+            out_g[TITLE + k] = t.cpu()
+        for k, t in zip(ops.BLOCK_KEYS, grads[1]):
+            out_g[USER + k] = t.cpu()
+    return scores.cpu(), loss.cpu().reshape(()), out_g

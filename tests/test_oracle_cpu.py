@@ -1,0 +1,133 @@
+"""CPU suite (-m "not gpu"): the oracle against the committed golden fixtures (minted from the
+reference's own modules by oracle/make_golden.py), host logic, and the C-ABI export check."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLD, TITLE, USER, load_golden, oracle_run, rel_err
+from oracle import nrms_oracle as O
+
+
+@pytest.mark.parametrize("name", ["nrms_tiny", "nrms_mind", "nrms_b8"])
+def test_oracle_matches_reference_golden(name):
+    g, params, batch, d = load_golden(name)
+    assert float(g["oracle_vs_reference_maxrel"]) < 2e-4
+    scores, loss, grads = oracle_run(params, batch, d["H"])
+    # fp32 noise floor between two CPU evaluations of the same math
+    assert rel_err(scores, g["scores"]) < 1e-5
+    assert rel_err(loss, g["loss"]) < 1e-6
+    title, _ = O.split_params(params)
+    assert rel_err(O.mhsa_add_att(batch["x_hist"]["title"], title, d["H"]), g["hist_vec"]) < 1e-5
+    for k, v in g.items():
+        if k.startswith("grad/"):
+            assert rel_err(grads[k[5:]], v) < 2e-4, k
+        elif k.startswith("gradsample/"):
+            assert rel_err(grads[k[11:]].reshape(-1)[::7], v) < 2e-4, k
+    # padded candidate slots score exactly 0, embedding row 0 has exactly zero gradient
+    B = d["B"]
+    cnt = torch.bincount(batch["batch_cand"], minlength=B)
+    for b in range(B):
+        assert torch.all(scores[b, cnt[b]:] == 0)
+    assert float(grads[TITLE + "embedding_layer.weight"][0].abs().max()) == 0.0
+
+
+def test_embedding_gather_bit_exact_including_row0():
+    table = torch.randn(17, 12)
+    ids = torch.tensor([[0, 3, 16], [0, 0, 5]])
+    out = O.embedding_gather(table, ids)
+    assert torch.equal(out[0, 0], table[0]) and torch.equal(out[1, 2], table[5])
+    assert out[0, 0].abs().sum() > 0  # row 0 is a real row, not zeros
+
+
+def test_to_dense_batch_semantics():
+    x = torch.arange(12.0).reshape(6, 2)
+    batch = torch.tensor([0, 0, 0, 2, 2, 3])  # segment 1 is empty
+    dense, mask = O.to_dense_batch(x, batch)
+    assert dense.shape == (4, 3, 2) and mask.shape == (4, 3)
+    assert torch.equal(dense[0], x[:3]) and torch.equal(dense[2, :2], x[3:5])
+    assert torch.all(dense[1] == 0) and not mask[1].any()
+    assert mask.sum() == 6
+
+
+def test_user_coupling_quirk():
+    g = dict(np.load(os.path.join(GOLD, "user_coupling.npz")))
+    E, H, Q = [int(x) for x in g["meta"]]
+    p = {k[len("param/"):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("param/")}
+    u = O.nrms_user_encoder(torch.from_numpy(g["h"]), p, H)
+    u2 = O.nrms_user_encoder(torch.from_numpy(g["h2"]), p, H)
+    assert rel_err(u, g["u"]) < 1e-5 and rel_err(u2, g["u2"]) < 1e-5
+    # perturbing impression 1 changes impression 0 (batch_first=False quirk, user/nrms.py:34-36)
+    assert float((u2[0] - u[0]).abs().max()) > 1e-3
+
+
+def test_naml_golden():
+    g = dict(np.load(os.path.join(GOLD, "naml_news.npz")))
+    V, E, F_, W, Q, C_, CE = [int(x) for x in g["meta"]]
+    news = {k[len("news/"):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("news/")}
+    tp = {k[len("text_encoders.title."):]: v for k, v in news.items() if k.startswith("text_encoders.title.")}
+    cp = {k[len("category_encoders.category."):]: v for k, v in news.items() if k.startswith("category_encoders.category.")}
+    lp = {k[len("combine_layer."):]: v for k, v in news.items() if k.startswith("combine_layer.")}
+    views = [O.cnn_add_att(torch.from_numpy(g["title"]), tp, W), O.cnn_add_att(torch.from_numpy(g["abstract"]), tp, W),
+             O.linear_category_encoder(torch.from_numpy(g["category"]), cp)]
+    vec = O.additive_attention(torch.stack(views, 1), lp["linear.weight"], lp["linear.bias"], lp["query"])
+    assert rel_err(vec, g["news_vec"]) < 2e-5  # view pooling is permutation invariant
+    up = {k[len("user/"):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("user/")}
+    assert rel_err(O.naml_user_encoder(torch.from_numpy(g["user_in"]), up), g["user_vec"]) < 2e-5
+
+
+def test_ce_soft_matches_torch_and_multi_positive():
+    s = torch.randn(5, 7)
+    y = torch.zeros(5, 7); y[:, 1] = 1; y[2, 4] = 1  # a multi-positive row (sum y > 1)
+    assert rel_err(O.ce_soft(s, y), torch.nn.CrossEntropyLoss()(s, y)) < 1e-6
+
+
+def test_adam_restatement_matches_torch():
+    torch.manual_seed(0)
+    p0 = torch.randn(1000)
+    p_ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([p_ref], lr=1e-4)
+    p, m, v = p0.clone(), torch.zeros(1000), torch.zeros(1000)
+    for step in range(1, 4):
+        g = torch.randn(1000) * (step == 2 and 0.0 or 1.0)  # a zero-gradient step still moves p
+        p_ref.grad = g.clone(); opt.step()
+        O.adam_step(p, g, m, v, step)
+    assert rel_err(p, p_ref.detach()) < 1e-6
+
+
+def test_synthetic_batch_layout():
+    from newsreclib_b200.synthetic import make_batch
+    b = make_batch(8, 1000, hist="ragged", cand="eval", seed=5)
+    assert b["x_hist"]["title"].shape[1] == 30 and b["x_hist"]["title"].dtype == torch.int64
+    assert torch.all(b["batch_hist"][1:] >= b["batch_hist"][:-1])  # sorted segment ids
+    assert int(b["batch_hist"].max()) == 7 and b["labels"].dtype == torch.float32
+    assert int(b["x_hist"]["title"].max()) <= 1000 and int(b["x_hist"]["title"].min()) == 0
+    cnt = torch.bincount(b["batch_cand"])
+    assert cnt.min() >= 2 and cnt.max() <= 300
+
+
+def test_cabi_exports_every_declared_symbol():
+    """The shared library loads and exports every function include/nrl.h declares."""
+    from newsreclib_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "nrl.h")).read()
+    declared = set(re.findall(r"\b(nrl_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/nrl.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib.nrl_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.nrl_version()
+
+
+def test_product_path_refuses_cpu_tensors():
+    from newsreclib_b200 import ops
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ops.gemm_test(torch.zeros(4, 16), torch.zeros(4, 16), False)
