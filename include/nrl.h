@@ -186,6 +186,12 @@ int nrl_gemm_test(const float* A, const float* B, float* D, int M, int N, int K,
                   int precision, void* ws, size_t ws_bytes, void* stream);
 /* number of kernels launched by this library since load (bench.py reports it) */
 long long nrl_launch_count(void);
+/* Per-launch device timing for bench.py's roofline leg: after nrl_profile_start(stream) one
+ * CUDA event is recorded on `stream` after every launch of this library; nrl_profile_stop
+ * synchronises, fills names[i*name_stride..] / ms[i] (duration of launch i = end_i - end_{i-1}
+ * on the in-order stream) and returns the number of records (<= max_records). */
+int nrl_profile_start(void* stream);
+int nrl_profile_stop(char* names, int name_stride, float* ms, int max_records);
 
 #ifdef __cplusplus
 }

@@ -47,6 +47,8 @@ SIGNATURES = {
     "nrl_version": (C.c_char_p, []),
     "nrl_last_error": (C.c_char_p, []),
     "nrl_launch_count": (_LL, []),
+    "nrl_profile_start": (_I, [_VP]),
+    "nrl_profile_stop": (_I, [_VP, _I, _VP, _I]),
     "nrl_news_encoder_ws_bytes": (_SZ, [_LL, _I, Dims]),
     "nrl_news_encoder_fwd": (_I, [_VP, _LL, _I, _VP, _LL, _BP, Dims, _F, _I, _ULL, _VP, _VP, _SZ, _I, _VP]),
     "nrl_news_encoder_bwd": (_I, [_VP, _LL, _I, _LL, _BP, Dims, _F, _I, _ULL, _VP, _BP, _VP, _VP, _SZ, _I, _VP]),

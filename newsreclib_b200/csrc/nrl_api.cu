@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "../../include/nrl.h"
 #include "nrl_gemm.cuh"
@@ -39,12 +40,34 @@ static int fail(int code, const char* fmt, ...) {
       return fail(NRL_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),    \
                   __FILE__, __LINE__);                                                     \
   } while (0)
+// Optional per-launch timing (bench.py's roofline leg): when enabled, one CUDA event is
+// recorded on the profiled stream after every launch; on an in-order stream the duration of
+// launch i is end_i - end_{i-1}.
+struct Profiler {
+  bool on = false;
+  cudaStream_t stream = nullptr;
+  std::vector<cudaEvent_t> pool;
+  std::vector<const char*> names;
+  size_t used = 0;
+};
+static Profiler g_prof;
+static void prof_mark(const char* name) {
+  if (!g_prof.on) return;
+  if (g_prof.used == g_prof.pool.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    g_prof.pool.push_back(e);
+  }
+  cudaEventRecord(g_prof.pool[g_prof.used++], g_prof.stream);
+  g_prof.names.push_back(name);
+}
 #define LAUNCH_CHECK(name)                                                                 \
   do {                                                                                     \
     g_launches.fetch_add(1, std::memory_order_relaxed);                                    \
     cudaError_t _e = cudaPeekAtLastError();                                                \
     if (_e != cudaSuccess)                                                                 \
       return fail(NRL_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(_e));  \
+    prof_mark(name);                                                                       \
   } while (0)
 #define TRY(expr)                 \
   do {                            \
@@ -363,9 +386,9 @@ static int block_backward(const Ctx& c, const Dims& d, BlockWs& w, long long R, 
                           long long G, int L, const nrl_block_params* prm, const DropCfg& drop1,
                           const DropCfg& drop0, const float* d_vec, nrl_block_grads* g) {
   bf16* lo_or_null_dap = c.two_planes() ? w.dap + R * d.Qp : nullptr;
-  pool_bwd_kernel<<<grid_for(G, 1, 4 * g_dev.sm_count), 128, (L + d.Q) * sizeof(float), c.stream>>>(
+  pool_bwd_kernel<<<grid_for(G, 1, 4 * g_dev.sm_count), 128, (L + 2 * d.Q) * sizeof(float), c.stream>>>(
       d_vec, w.y, w.w, w.a, prm->add_query, d.E, d.Q, d.Qp, L, G, w.dy1, w.dap, lo_or_null_dap,
-      g->add_query);
+      g->add_query, g->add_bias);
   LAUNCH_CHECK("pool_bwd");
   // dY = dropout1'( dY1 + dApre W_add )  -> split planes
   {
@@ -381,7 +404,7 @@ static int block_backward(const Ctx& c, const Dims& d, BlockWs& w, long long R, 
   // dW_add, db_add
   {
     GemmEpi e = epi_none();
-    e.gw = g->add_weight; e.ld_gw = d.E; e.gw_cols = d.E; e.gb = g->add_bias;
+    e.gw = g->add_weight; e.ld_gw = d.E; e.gw_cols = d.E; e.gb = nullptr;  // db: fp32 in pool_bwd
     TRY(gemm_tn(c, w.dap, d.Q, d.Qp, w.yp, d.Ep, d.Ep, R, e, "gemm additive wgrad"));
   }
   // dO = dY W_out
@@ -461,6 +484,31 @@ extern "C" {
 const char* nrl_version(void) { return "newsreclib_b200 0.1 (sm_100a, tcgen05)"; }
 const char* nrl_last_error(void) { return g_err; }
 long long nrl_launch_count(void) { return g_launches.load(); }
+
+int nrl_profile_start(void* stream) {
+  g_prof.stream = static_cast<cudaStream_t>(stream);
+  g_prof.used = 0;
+  g_prof.names.clear();
+  g_prof.on = true;
+  prof_mark("<start>");
+  return NRL_OK;
+}
+int nrl_profile_stop(char* names, int name_stride, float* ms, int max_records) {
+  g_prof.on = false;
+  if (g_prof.used == 0) return 0;
+  CUDA_TRY(cudaEventSynchronize(g_prof.pool[g_prof.used - 1]));
+  int n = 0;
+  for (size_t i = 1; i < g_prof.used && n < max_records; ++i, ++n) {
+    float t = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&t, g_prof.pool[i - 1], g_prof.pool[i]));
+    if (ms) ms[n] = t;
+    if (names && name_stride > 0) {
+      strncpy(names + (size_t)n * name_stride, g_prof.names[i], name_stride - 1);
+      names[(size_t)n * name_stride + name_stride - 1] = 0;
+    }
+  }
+  return n;
+}
 
 size_t nrl_news_encoder_ws_bytes(long long n_news, int L, nrl_dims dims) {
   Dims d;

@@ -446,18 +446,22 @@ pool_fwd_kernel(const float* __restrict__ score, const float* __restrict__ Y, in
 //   dY1[r]   = w_r * dOut[g]                                  (fp32, later += dApre * W_add)
 //   dApre[r] = ds_r * q * (1 - A_r^2),  ds_r = w_r (dOut.Y_r - sum_u w_u dOut.Y_u)   (split planes)
 //   dq      += sum_r ds_r * A_r                                (atomics, once per block)
+//   db      += sum_r dApre[r]   (fp32: the terms cancel almost exactly because sum_t ds_t = 0
+//                                per group, so this sum is NOT routed through the bf16 split)
 __global__ void __launch_bounds__(128)
 pool_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ Y,
                 const float* __restrict__ w, const float* __restrict__ A,
                 const float* __restrict__ qvec, int E, int Q, int qp, int L, long long G,
                 float* __restrict__ dY1, __nv_bfloat16* __restrict__ da_hi,
-                __nv_bfloat16* __restrict__ da_lo, float* __restrict__ dq_accum) {
-  extern __shared__ float sm[];  // [L] ds, then [Q] dq partial
+                __nv_bfloat16* __restrict__ da_lo, float* __restrict__ dq_accum,
+                float* __restrict__ db_accum) {
+  extern __shared__ float sm[];  // [L] ds, then [Q] dq partial, then [Q] db partial
   float* s_ds = sm;
   float* s_dq = sm + L;
+  float* s_db = sm + L + Q;
   __shared__ float red[33];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int j = threadIdx.x; j < Q; j += blockDim.x) s_dq[j] = 0.f;
+  for (int j = threadIdx.x; j < Q; j += blockDim.x) { s_dq[j] = 0.f; s_db[j] = 0.f; }
   __syncthreads();
   for (long long g = blockIdx.x; g < G; g += gridDim.x) {
     const long long r0 = g * L;
@@ -491,13 +495,22 @@ pool_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ Y,
       if (da_lo) da_lo[(r0 + t) * qp + j] = ll;
     }
     for (int j = threadIdx.x; j < Q; j += blockDim.x) {
-      float acc = 0.f;
-      for (int t = 0; t < L; ++t) acc += s_ds[t] * A[(r0 + t) * Q + j];
+      float acc = 0.f, accb = 0.f;
+      const float qj = qvec[j];
+      for (int t = 0; t < L; ++t) {
+        const float a = A[(r0 + t) * Q + j];
+        acc += s_ds[t] * a;
+        accb += s_ds[t] * qj * (1.f - a * a);
+      }
       s_dq[j] += acc;
+      s_db[j] += accb;
     }
     __syncthreads();
   }
-  for (int j = threadIdx.x; j < Q; j += blockDim.x) atomicAdd(dq_accum + j, s_dq[j]);
+  for (int j = threadIdx.x; j < Q; j += blockDim.x) {
+    atomicAdd(dq_accum + j, s_dq[j]);
+    atomicAdd(db_accum + j, s_db[j]);
+  }
 }
 
 // ------------------------------------------------------------------------------------

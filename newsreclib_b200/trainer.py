@@ -1,0 +1,123 @@
+"""Fused NRMS training step on one GPU (one process per GPU under ``torch.distributed``).
+
+``NRMSTrainer`` owns ONE flat fp32 parameter buffer (embedding table, title block, user block,
+in the reference's ``state_dict`` order and names), one flat gradient buffer and
+the Adam moments.  A step is three library calls on the current CUDA stream:
+
+    zero grads (one memset)  ->  nrl_nrms_step (forward + CE + backward, ~45 kernels)
+    [-> one NCCL all-reduce of the flat gradient buffer when world_size > 1]
+    ->  nrl_adam_step (dense Adam over the flat buffer, torch.optim.Adam semantics)
+
+The path shards by impression batch (each rank runs its own ``batch_size`` impressions, as
+Lightning DDP does for the reference, ``configs/trainer/ddp.yaml``); the only exchange is the
+gradient all-reduce, averaged by ``grad_scale = 1 / world_size`` inside the Adam kernel.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib, ops
+
+TITLE = "news_encoder.text_encoders.title."
+USER = "user_encoder."
+
+
+class NRMSTrainer:
+    def __init__(self, params: Dict[str, torch.Tensor], num_heads: int, *, device="cuda",
+                 dropout_p: float = 0.2, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
+                 precision: int = ops.PREC_BF16X3, late_fusion: bool = False, seed: int = 1234,
+                 process_group=None) -> None:
+        _lib.load()
+        self.device = torch.device(device)
+        self.keys = [TITLE + "embedding_layer.weight"] + [TITLE + k for k in ops.BLOCK_KEYS] + \
+                    [USER + k for k in ops.BLOCK_KEYS]
+        shapes = [tuple(params[k].shape) for k in self.keys]
+        sizes = [params[k].numel() for k in self.keys]
+        # every tensor starts on a 16-byte boundary (the table gradient uses 128-bit atomics)
+        offs, total = [], 0
+        for n in sizes:
+            offs.append(total)
+            total += (n + 3) // 4 * 4
+        self.flat = torch.zeros(total, dtype=torch.float32, device=self.device)
+        self.grad = torch.zeros_like(self.flat)
+        self.m = torch.zeros_like(self.flat)
+        self.v = torch.zeros_like(self.flat)
+        self.params, self.grads = {}, {}
+        for k, o, n, shp in zip(self.keys, offs, sizes, shapes):
+            self.params[k] = self.flat[o:o + n].view(shp)
+            self.grads[k] = self.grad[o:o + n].view(shp)
+            self.params[k].copy_(params[k])
+        self.table = self.params[self.keys[0]]
+        E = self.table.shape[1]
+        Q = self.params[TITLE + "additive_attention.query"].numel()
+        self.dims = ops.dims_of(E, num_heads, Q)
+        self.news_block = ops.block_from_dict(self.params, TITLE)
+        self.user_block = ops.block_from_dict(self.params, USER)
+        self.grad_pack = (ops.block_from_dict(self.grads, TITLE), ops.block_from_dict(self.grads, USER),
+                          self.grads[self.keys[0]])
+        self.dropout_p, self.lr, self.betas, self.eps = dropout_p, lr, betas, eps
+        self.precision, self.late_fusion, self.seed = precision, late_fusion, seed
+        self.step_count = 0
+        self.ws: Optional[torch.Tensor] = None
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if self._dist() else 1
+        self._structs = None
+
+    def _dist(self) -> bool:
+        return torch.distributed.is_available() and torch.distributed.is_initialized()
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        """Reference-named parameters (loadable into the reference's NRMSModule)."""
+        return {k: v.detach().clone() for k, v in self.params.items()}
+
+    # ------------------------------------------------------------------ steps
+    def _finish(self) -> None:
+        if self.world > 1:
+            torch.distributed.all_reduce(self.grad, group=self.pg)
+        self.step_count += 1
+        ops.adam_step(self.flat, self.grad, self.m, self.v, self.step_count, self.lr, self.betas[0],
+                      self.betas[1], self.eps, grad_scale=1.0 / self.world)
+
+    def train_step(self, batch: Dict, B: int, Hmax: int, Cmax: int, training: bool = True):
+        """Device-resident batch -> (scores [B, Cmax], loss [1]) device tensors; no host sync."""
+        self.grad.zero_()
+        scores, loss, self.ws = ops.nrms_step(
+            batch, self.table, self.news_block, self.user_block, self.dims, B=B, Hmax=Hmax, Cmax=Cmax,
+            late_fusion=self.late_fusion, dropout_p=self.dropout_p, training=training,
+            seed=self.seed + self.step_count, grads=self.grad_pack, ws=self.ws, precision=self.precision)
+        self._finish()
+        return scores, loss
+
+    def train_step_host(self, hb: Dict, B: int, Hmax: int, Cmax: int, scores_host: torch.Tensor,
+                        loss_host: torch.Tensor, training: bool = True) -> None:
+        """End-to-end step from HOST buffers (``nrl_nrms_step_host``): ids / segment ids / labels
+        are copied host->device, the step runs, scores and loss are copied back and the stream is
+        synchronised; then the gradient exchange and the Adam update are enqueued."""
+        lib = _lib.load()
+        hist_ids, cand_ids = hb["x_hist"]["title"], hb["x_cand"]["title"]
+        nh, L = hist_ids.shape
+        nc = cand_ids.shape[0]
+        need = lib.nrl_nrms_ws_bytes(nh, nc, L, B, Hmax, Cmax, self.dims)
+        if self.ws is None or self.ws.numel() < need:
+            self.ws = ops.workspace(need, self.device)
+        self.grad.zero_()
+        nb, ub = ops.block_struct(self.news_block), ops.block_struct(self.user_block)
+        ng, ug = ops.block_struct(self.grad_pack[0]), ops.block_struct(self.grad_pack[1])
+        _lib.check(lib.nrl_nrms_step_host(
+            hist_ids.data_ptr(), cand_ids.data_ptr(), hb["batch_hist"].data_ptr(), hb["batch_cand"].data_ptr(),
+            hb["labels"].data_ptr(), nh, nc, L, B, Hmax, Cmax, self.table.data_ptr(), self.table.shape[0],
+            C.byref(nb), C.byref(ub), self.dims, int(self.late_fusion), float(self.dropout_p), int(training),
+            int(self.seed + self.step_count), scores_host.data_ptr(), loss_host.data_ptr(), 1, C.byref(ng),
+            C.byref(ug), self.grad_pack[2].data_ptr(), self.ws.data_ptr(), self.ws.numel(), self.precision,
+            torch.cuda.current_stream().cuda_stream), "nrl_nrms_step_host")
+        self._finish()
+
+    @torch.no_grad()
+    def eval_forward(self, batch: Dict, B: int, Hmax: int, Cmax: int):
+        scores, loss, self.ws = ops.nrms_step(
+            batch, self.table, self.news_block, self.user_block, self.dims, B=B, Hmax=Hmax, Cmax=Cmax,
+            late_fusion=self.late_fusion, dropout_p=0.0, training=False, ws=self.ws, precision=self.precision)
+        return scores, loss
