@@ -113,6 +113,7 @@ static int device_init() {
   g_dev.ok = true;
   return NRL_OK;
 }
+static int attn_attrs_init();
 
 // ----------------------------------------------------------------------------------------
 // workspace carving (same sequence in ws_bytes / fwd / bwd -> same offsets)
@@ -315,20 +316,51 @@ struct AttnGeom {
   int S; long long seq_stride; int NB; long long batch_stride;
 };
 
+constexpr int ATTN_FWD_SMEM_BUDGET = 110 * 1024;
+constexpr int ATTN_BWD_SMEM_BUDGET = 100 * 1024;
+
+template <int DH>
+static int attn_set_attrs() {
+  CUDA_TRY(cudaFuncSetAttribute(attn_fwd_tile_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                ATTN_FWD_SMEM_BUDGET));
+  CUDA_TRY(cudaFuncSetAttribute(attn_bwd_tile_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                ATTN_BWD_SMEM_BUDGET));
+  return NRL_OK;
+}
+
 template <int DH>
 static void launch_attn_fwd(const Ctx& c, const Dims& d, const AttnGeom& g, const BlockWs& w, long long R) {
+  bf16* lo = c.two_planes() ? w.o + R * d.Ep : nullptr;
+  const size_t per_head = (size_t)g.S * 3 * DH * sizeof(float);
+  int hp = (int)(ATTN_FWD_SMEM_BUDGET / per_head);
+  if (hp > d.H) hp = d.H;
+  if (hp >= 1) {  // tile-resident fast path
+    const int passes = (d.H + hp - 1) / hp;
+    attn_fwd_tile_kernel<DH><<<grid_for((long long)g.NB * passes, 1, 8 * g_dev.sm_count), 256, hp * per_head, c.stream>>>(
+        w.qkv, d.E, d.H, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH), hp, w.o, lo, d.Ep, w.lse);
+    return;
+  }
   const long long items = (long long)g.NB * d.H * ((g.S + 31) / 32);
   attn_fwd_kernel<DH><<<grid_for(items, 4, 1 << 20), 128, 0, c.stream>>>(
-      w.qkv, d.E, d.H, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH), w.o,
-      c.two_planes() ? w.o + R * d.Ep : nullptr, d.Ep, w.lse);
+      w.qkv, d.E, d.H, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH), w.o, lo, d.Ep, w.lse);
 }
 template <int DH>
 static void launch_attn_bwd(const Ctx& c, const Dims& d, const AttnGeom& g, const BlockWs& w, long long R) {
+  bf16* lo = c.two_planes() ? w.dqkv + R * d.P3 : nullptr;
+  const size_t per_head = (size_t)g.S * (5 * DH + 2) * sizeof(float);
+  int hp = (int)(ATTN_BWD_SMEM_BUDGET / per_head);
+  if (hp > d.H) hp = d.H;
+  if (hp >= 1) {
+    const int passes = (d.H + hp - 1) / hp;
+    attn_bwd_tile_kernel<DH><<<grid_for((long long)g.NB * passes, 1, 8 * g_dev.sm_count), 256, hp * per_head, c.stream>>>(
+        w.qkv, w.d_o, d.E, w.lse, d.E, d.H, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH), hp,
+        w.dqkv, lo, d.P3);
+    return;
+  }
   const long long items = (long long)g.NB * d.H;
   attn_bwd_kernel<DH><<<grid_for(items, 4, 1 << 20), 128, 0, c.stream>>>(
       w.qkv, w.d_o, d.E, w.o, c.two_planes() ? w.o + R * d.Ep : nullptr, d.Ep, w.lse, d.E, d.H, g.S,
-      g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH), w.dqkv,
-      c.two_planes() ? w.dqkv + R * d.P3 : nullptr, d.P3);
+      g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH), w.dqkv, lo, d.P3);
 }
 
 struct DropCfg {
@@ -343,10 +375,21 @@ static DropCfg make_drop(float p, int training, unsigned long long seed) {
   return dc;
 }
 
+static int attn_attrs_init() {
+  static bool done = false;
+  if (done) return NRL_OK;
+  TRY(attn_set_attrs<16>());
+  TRY(attn_set_attrs<20>());
+  TRY(attn_set_attrs<32>());
+  done = true;
+  return NRL_OK;
+}
+
 // MHSA + additive pooling over R rows already staged in w.x (split planes).
 static int block_forward(const Ctx& c, const Dims& d, BlockWs& w, long long R, const AttnGeom& ag,
                          long long G, int L, const nrl_block_params* prm, const DropCfg& drop,
                          float* out_vec) {
+  TRY(attn_attrs_init());
   // K3: QKV = X W_in^T + b_in   (bias rides on the ones column)
   {
     GemmEpi e = epi_none();
@@ -385,15 +428,16 @@ static int block_forward(const Ctx& c, const Dims& d, BlockWs& w, long long R, c
 static int block_backward(const Ctx& c, const Dims& d, BlockWs& w, long long R, const AttnGeom& ag,
                           long long G, int L, const nrl_block_params* prm, const DropCfg& drop1,
                           const DropCfg& drop0, const float* d_vec, nrl_block_grads* g) {
+  TRY(attn_attrs_init());
   bf16* lo_or_null_dap = c.two_planes() ? w.dap + R * d.Qp : nullptr;
-  pool_bwd_kernel<<<grid_for(G, 1, 4 * g_dev.sm_count), 128, (L + 2 * d.Q) * sizeof(float), c.stream>>>(
-      d_vec, w.y, w.w, w.a, prm->add_query, d.E, d.Q, d.Qp, L, G, w.dy1, w.dap, lo_or_null_dap,
+  pool_bwd_kernel<<<grid_for(G, 1, 8 * g_dev.sm_count), 256, L * sizeof(float), c.stream>>>(
+      d_vec, w.y, w.w, w.a, prm->add_query, d.E, d.Q, d.Qp, L, G, nullptr, w.dap, lo_or_null_dap,
       g->add_query, g->add_bias);
   LAUNCH_CHECK("pool_bwd");
-  // dY = dropout1'( dY1 + dApre W_add )  -> split planes
+  // dY = dropout1'( w_r * dVec[g] + dApre W_add )  -> split planes
   {
     GemmEpi e = epi_none();
-    e.addend = w.dy1; e.ld_add = d.E;
+    e.add_w = w.w; e.add_vec = d_vec; e.ld_addvec = d.E; e.add_L = L;  // + w_r * dVec[g(r)]
     e.hi = w.dyp; e.lo = w.dyp + R * d.Ep; e.ld_sp = d.Ep; e.sp_cols = d.Ep; e.ones_col = -1;
     if (drop1.on) {
       e.use_dropout = 1; e.drop_scale = drop1.scale; e.drop_thr = drop1.thr; e.drop_site = 1;

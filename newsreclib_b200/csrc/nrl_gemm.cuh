@@ -28,12 +28,16 @@ constexpr int GEMM_A_BYTES = GEMM_BM * 128;  // 16 KB
 constexpr int GEMM_B_BYTES = 256 * 128;      // 32 KB (BN <= 256)
 constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES;
 constexpr int GEMM_THREADS = 192;
-constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int GEMM_EPI_STAGE_BYTES = 4 * (32 * 33 * 4 + 32 * 4);  // per epilogue warp: [32][33] fp32 + 32 keep words
+constexpr int GEMM_SMEM_BYTES =
+    GEMM_STAGES * GEMM_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + GEMM_EPI_STAGE_BYTES;
 constexpr int GEMM_TMEM_COLS = 512;
 
 struct GemmEpi {
-  // v = acc (+ addend) ; optional dropout ; then any of the sinks below.
-  const float* addend;  long long ld_add;
+  // x = acc (+ addend) ; optional dropout ; then any of the sinks below.
+  const float* addend;  long long ld_add;             // x += addend[row, col]
+  const float* add_w;   const float* add_vec; long long ld_addvec; int add_L;
+                                                      // x += add_w[row] * add_vec[row / add_L, col]
   float* out;           long long ld_out;  int out_cols;   // fp32 row-major sink, cols < out_cols
   __nv_bfloat16* hi;    __nv_bfloat16* lo; long long ld_sp; int sp_cols; int ones_col;
   float drop_scale;     uint32_t drop_thr; uint32_t drop_site; unsigned long long seed; int drop_ld;
@@ -69,97 +73,80 @@ __device__ __forceinline__ void gemm_tile_coords(const GemmParams& p, int tile, 
   kb1 = min(kb_total, kb0 + kb_per);
 }
 
-__device__ __forceinline__ void gemm_epilogue_chunk(const GemmEpi& e, int row, int col0, int N,
-                                                    bool row_ok, float* v, float& score_acc) {
-  // v[16] = accumulator columns col0 .. col0+15 of this thread's row
-  if (!row_ok) return;
-  if (e.addend) {
+// keep-bits of 32 consecutive elements starting at flat index e0 (bit i = element e0 + i)
+__device__ __forceinline__ uint32_t drop_keep_bits32(unsigned long long seed, uint32_t site,
+                                                     unsigned long long e0, uint32_t thr) {
+  uint32_t bits = 0;
+  unsigned long long g = e0 >> 3;
+  int slot = (int)(e0 & 7ull);
+  Philox4 r = philox4x32_10(seed, g, site);
 #pragma unroll
-    for (int i = 0; i < 16; ++i)
-      if (col0 + i < N) v[i] += __ldg(e.addend + (long long)row * e.ld_add + col0 + i);
-  }
-  if (e.use_dropout) {
-    // col0 is a multiple of 16 and drop_ld a multiple of 8 -> two aligned groups of 8
-    unsigned long long base = (unsigned long long)row * (unsigned)e.drop_ld + (unsigned)col0;
-    if ((base & 7ull) == 0) {
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        Philox4 r = philox4x32_10(e.seed, (base >> 3) + g, e.drop_site);
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          v[g * 8 + i] = philox_u16(r, i) >= e.drop_thr ? v[g * 8 + i] * e.drop_scale : 0.f;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 16; ++i)
-        v[i] = drop_keep(e.seed, e.drop_site, base + i, e.drop_thr) ? v[i] * e.drop_scale : 0.f;
+  for (int i = 0; i < 32; ++i) {
+    if (philox_u16(r, slot) >= thr) bits |= (1u << i);
+    if (++slot == 8 && i != 31) {
+      slot = 0;
+      r = philox4x32_10(seed, ++g, site);
     }
   }
+  return bits;
+}
+
+// Epilogue of one 32-row x (<=32)-column block of the accumulator, executed by one warp.
+// Phase 1 (thread = row, straight out of TMEM): tanh / query-dot and the dropout keep-bits;
+// the block is then transposed through a padded smem stage so that in phase 2 (lane = column)
+// every global load / store / atomic of the warp covers one contiguous row segment.
+__device__ __forceinline__ void gemm_epilogue_block(const GemmEpi& e, int M, int N, int row_base,
+                                                    int col_base, int ncol, float* v,
+                                                    float* stage /*[32][33]*/, uint32_t* kbits /*[32]*/,
+                                                    float& score_acc) {
+  const int lane = threadIdx.x & 31;
+  const int my_row = row_base + lane;
   if (e.qvec) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      float a = (col0 + i < N) ? tanhf(v[i]) : 0.f;
+    for (int i = 0; i < 32; ++i) {
+      const int col = col_base + i;
+      float a = 0.f;
+      if (i < ncol && col < N) {
+        a = tanhf(v[i]);
+        score_acc += a * __ldg(e.qvec + col);
+      }
       v[i] = a;
-      if (col0 + i < N) score_acc += a * __ldg(e.qvec + col0 + i);
-    }
-    if (e.tanh_out) {
-      float* dst = e.tanh_out + (long long)row * e.ld_tanh + col0;
-      if (col0 + 16 <= N && (e.ld_tanh & 3) == 0) {
-#pragma unroll
-        for (int i = 0; i < 16; i += 4)
-          *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (col0 + i < N) dst[i] = v[i];
-      }
     }
   }
-  if (e.out) {
-    float* dst = e.out + (long long)row * e.ld_out + col0;
-    if (col0 + 16 <= e.out_cols && (e.ld_out & 3) == 0) {
+  if (e.use_dropout) {
+    kbits[lane] = drop_keep_bits32(e.seed, e.drop_site,
+                                   (unsigned long long)my_row * (unsigned)e.drop_ld + (unsigned)col_base,
+                                   e.drop_thr);
+  }
 #pragma unroll
-      for (int i = 0; i < 16; i += 4)
-        *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (col0 + i < e.out_cols) dst[i] = v[i];
+  for (int i = 0; i < 32; ++i) stage[lane * 33 + i] = v[i];
+  __syncwarp();
+  const int col = col_base + lane;
+  const bool lane_ok = lane < ncol;
+  const int rows = min(32, M - row_base);
+  for (int r = 0; r < rows; ++r) {
+    const long long row = row_base + r;
+    float x = stage[r * 33 + lane];
+    if (e.addend && lane_ok && col < N) x += __ldg(e.addend + row * e.ld_add + col);
+    if (e.add_w && lane_ok && col < N)
+      x += __ldg(e.add_w + row) * __ldg(e.add_vec + (row / e.add_L) * e.ld_addvec + col);
+    if (e.use_dropout) x = ((kbits[r] >> lane) & 1u) ? x * e.drop_scale : 0.f;
+    if (!lane_ok) continue;
+    if (e.tanh_out && col < N) e.tanh_out[row * e.ld_tanh + col] = x;
+    if (e.out && col < e.out_cols) e.out[row * e.ld_out + col] = x;
+    if (e.hi && col < e.sp_cols) {
+      const float val = col < N ? x : (col == e.ones_col ? 1.f : 0.f);
+      __nv_bfloat16 h, l;
+      split_bf16(val, h, l);
+      e.hi[row * e.ld_sp + col] = h;
+      if (e.lo) e.lo[row * e.ld_sp + col] = l;
+    }
+    if (e.gw) {
+      if (col < e.gw_cols) atomicAdd(e.gw + row * e.ld_gw + col, x);
+      else if (col == e.gw_cols && e.gb) atomicAdd(e.gb + row, x);
     }
   }
-  if (e.hi) {
-    if (col0 < e.sp_cols) {
-      uint32_t h[8], l[8];
-#pragma unroll
-      for (int i = 0; i < 16; i += 2) {
-        float a = (col0 + i < N) ? v[i] : (col0 + i == e.ones_col ? 1.f : 0.f);
-        float b = (col0 + i + 1 < N) ? v[i + 1] : (col0 + i + 1 == e.ones_col ? 1.f : 0.f);
-        __nv_bfloat16 ah, al, bh, bl;
-        split_bf16(a, ah, al);
-        split_bf16(b, bh, bl);
-        h[i >> 1] = pack_bf16x2(ah, bh);
-        l[i >> 1] = pack_bf16x2(al, bl);
-      }
-      // sp_cols and ld_sp are multiples of 8 -> 16-byte aligned half-chunks
-      long long off = (long long)row * e.ld_sp + col0;
-      if (col0 + 8 <= e.sp_cols) {
-        *reinterpret_cast<uint4*>(e.hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
-        if (e.lo) *reinterpret_cast<uint4*>(e.lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
-      }
-      if (col0 + 16 <= e.sp_cols) {
-        *reinterpret_cast<uint4*>(e.hi + off + 8) = make_uint4(h[4], h[5], h[6], h[7]);
-        if (e.lo) *reinterpret_cast<uint4*>(e.lo + off + 8) = make_uint4(l[4], l[5], l[6], l[7]);
-      }
-    }
-  }
-  if (e.gw) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      int c = col0 + i;
-      if (c < e.gw_cols) atomicAdd(e.gw + (long long)row * e.ld_gw + c, v[i]);
-      else if (c == e.gw_cols && e.gb) atomicAdd(e.gb + row, v[i]);
-    }
-  }
+  __syncwarp();
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -174,6 +161,8 @@ nrl_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * GEMM_STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * GEMM_STAGES + 2 + s); };
   const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * GEMM_STAGES + 4);
+  float* epi_stage = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) +
+                                              GEMM_STAGES * GEMM_STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -295,18 +284,26 @@ nrl_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       if (kb0 >= kb1) continue;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int row = m0 + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
+      const int row_base = m0 + quarter * 32;
       const uint32_t t_row = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(quarter * 32) << 16);
       float score_acc = 0.f;
-      // columns that any sink of this tile can consume
-      int col_end = min(p.BN, max(max(p.N, p.epi.hi ? p.epi.sp_cols : 0), p.epi.gw ? p.epi.gw_cols + 1 : 0) - n0);
-      for (int c = 0; c < col_end; c += 16) {
-        float v[16];
+      // columns that any sink of this tile can consume (multiple of 16)
+      const int col_end = min(p.BN, ((max(max(p.N, p.epi.hi ? p.epi.sp_cols : 0), p.epi.gw ? p.epi.gw_cols + 1 : 0) - n0) + 15) & ~15);
+      float* stage = epi_stage + (warp - 2) * (32 * 33 + 32);
+      uint32_t* kbits = reinterpret_cast<uint32_t*>(stage + 32 * 33);
+      for (int c = 0; c < col_end; c += 32) {
+        const int ncol = min(32, col_end - c);
+        float v[32];
         tmem_ld16(t_row + (uint32_t)c, v);
-        gemm_epilogue_chunk(p.epi, row, n0 + c, p.N, row_ok, v, score_acc);
+        if (ncol > 16) tmem_ld16(t_row + (uint32_t)c + 16u, v + 16);
+        else {
+#pragma unroll
+          for (int i = 16; i < 32; ++i) v[i] = 0.f;
+        }
+        if (row_base < p.M)
+          gemm_epilogue_block(p.epi, p.M, p.N, row_base, n0 + c, ncol, v, stage, kbits, score_acc);
       }
-      if (p.epi.score && row_ok) p.epi.score[row] = score_acc;
+      if (p.epi.score && row_base + lane < p.M) p.epi.score[row_base + lane] = score_acc;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));

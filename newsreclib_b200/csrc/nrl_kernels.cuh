@@ -406,6 +406,270 @@ attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o, lo
 }
 
 // ------------------------------------------------------------------------------------
+// Tile-resident attention (the fast path).  One CTA per batch item b and head group: the
+// Q|K|V slices of `hp` heads for all S sequence rows are staged in shared memory with fully
+// coalesced row-segment loads (cp.async-free: 16-byte __ldg -> st.shared), every warp then
+// owns (head, 32-query chunk) items with lane = query and walks the keys in smem (broadcast
+// reads), and the result tile is written back with coalesced row segments.  Chosen whenever
+// one head of the sequence fits the smem budget; otherwise the streaming kernels above run.
+// smem row layout: [ q(hp*DH) | k(hp*DH) | v(hp*DH) ]  (+ [ dO | dQ ] in the backward kernel)
+// ------------------------------------------------------------------------------------
+template <int DH>
+__global__ void __launch_bounds__(256, 2)
+attn_fwd_tile_kernel(const float* __restrict__ qkv, int E, int heads, int S, long long seq_stride,
+                     int NB, long long batch_stride, float scale, int hp,
+                     __nv_bfloat16* __restrict__ o_hi, __nv_bfloat16* __restrict__ o_lo, int ep,
+                     float* __restrict__ lse) {
+  extern __shared__ __align__(16) float tile[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int passes = (heads + hp - 1) / hp;
+  const int ld = 3 * E;
+  const int qchunks = (S + 31) / 32;
+  for (long long work = blockIdx.x; work < (long long)NB * passes; work += gridDim.x) {
+    const int b = (int)(work / passes), pass = (int)(work % passes);
+    const int h0 = pass * hp, nh = min(hp, heads - h0);
+    const int W = nh * DH;       // floats per q / k / v segment
+    const int P = 3 * W;         // smem row pitch
+    const int segv = W / 4;      // float4 per segment
+    __syncthreads();
+    for (int i = threadIdx.x; i < S * 3 * segv; i += blockDim.x) {
+      const int srow = i / (3 * segv), rem = i % (3 * segv), seg = rem / segv, c4 = rem % segv;
+      const long long grow = (long long)srow * seq_stride + (long long)b * batch_stride;
+      reinterpret_cast<float4*>(tile + (long long)srow * P + seg * W)[c4] =
+          __ldg(reinterpret_cast<const float4*>(qkv + grow * ld + seg * E + h0 * DH) + c4);
+    }
+    __syncthreads();
+    for (int it = warp; it < nh * qchunks; it += nwarps) {
+      const int hl = it / qchunks, qc = it % qchunks;
+      const int t = qc * 32 + lane;
+      const bool ok = t < S;
+      const float* qrow = tile + (long long)(ok ? t : 0) * P + hl * DH;
+      float q[DH], o[DH];
+#pragma unroll
+      for (int d = 0; d < DH; d += 4) {
+        float4 t4 = *reinterpret_cast<const float4*>(qrow + d);
+        q[d] = t4.x * scale; q[d + 1] = t4.y * scale; q[d + 2] = t4.z * scale; q[d + 3] = t4.w * scale;
+        o[d] = o[d + 1] = o[d + 2] = o[d + 3] = 0.f;
+      }
+      float m = -INFINITY;
+      for (int u = 0; u < S; ++u) {
+        const float* kr = tile + (long long)u * P + W + hl * DH;
+        float acc = 0.f;
+#pragma unroll
+        for (int d = 0; d < DH; d += 4) {
+          float4 k4 = *reinterpret_cast<const float4*>(kr + d);
+          acc += q[d] * k4.x + q[d + 1] * k4.y + q[d + 2] * k4.z + q[d + 3] * k4.w;
+        }
+        m = fmaxf(m, acc);
+      }
+      float l = 0.f;
+      for (int u = 0; u < S; ++u) {
+        const float* kr = tile + (long long)u * P + W + hl * DH;
+        const float* vr = kr + W;
+        float acc = 0.f;
+#pragma unroll
+        for (int d = 0; d < DH; d += 4) {
+          float4 k4 = *reinterpret_cast<const float4*>(kr + d);
+          acc += q[d] * k4.x + q[d + 1] * k4.y + q[d + 2] * k4.z + q[d + 3] * k4.w;
+        }
+        const float pu = expf(acc - m);
+        l += pu;
+#pragma unroll
+        for (int d = 0; d < DH; d += 4) {
+          float4 v4 = *reinterpret_cast<const float4*>(vr + d);
+          o[d] += pu * v4.x; o[d + 1] += pu * v4.y; o[d + 2] += pu * v4.z; o[d + 3] += pu * v4.w;
+        }
+      }
+      __syncwarp();
+      if (ok) {
+        const float inv = 1.f / l;
+        // the q slice of (t, head) is read by this lane only: reuse it for the output row
+        float* orow = tile + (long long)t * P + hl * DH;
+#pragma unroll
+        for (int d = 0; d < DH; ++d) orow[d] = o[d] * inv;
+        const long long grow = (long long)t * seq_stride + (long long)b * batch_stride;
+        lse[grow * heads + h0 + hl] = m + logf(l);
+      }
+    }
+    __syncthreads();
+    // coalesced write-back of the [S, W] output tile as split planes
+    for (int i = threadIdx.x; i < S * (W / 2); i += blockDim.x) {
+      const int srow = i / (W / 2), c = (i % (W / 2)) * 2;
+      const long long grow = (long long)srow * seq_stride + (long long)b * batch_stride;
+      const float2 val = *reinterpret_cast<const float2*>(tile + (long long)srow * P + c);
+      __nv_bfloat16 ah, al, bh, bl;
+      split_bf16(val.x, ah, al);
+      split_bf16(val.y, bh, bl);
+      const long long off = grow * ep + h0 * DH + c;
+      *reinterpret_cast<uint32_t*>(o_hi + off) = pack_bf16x2(ah, bh);
+      if (o_lo) *reinterpret_cast<uint32_t*>(o_lo + off) = pack_bf16x2(al, bl);
+    }
+    if (pass == 0) {
+      for (int i = threadIdx.x; i < S * (ep - E); i += blockDim.x) {
+        const int srow = i / (ep - E), c = E + i % (ep - E);
+        const long long grow = (long long)srow * seq_stride + (long long)b * batch_stride;
+        o_hi[grow * ep + c] = __float2bfloat16_rn(c == E ? 1.f : 0.f);
+        if (o_lo) o_lo[grow * ep + c] = __float2bfloat16_rn(0.f);
+      }
+    }
+  }
+}
+
+template <int DH>
+__global__ void __launch_bounds__(256, 2)
+attn_bwd_tile_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o, long long ld_do,
+                     const float* __restrict__ lse, int E, int heads, int S, long long seq_stride,
+                     int NB, long long batch_stride, float scale, int hp,
+                     __nv_bfloat16* __restrict__ g_hi, __nv_bfloat16* __restrict__ g_lo, int p3) {
+  extern __shared__ __align__(16) float tile[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int passes = (heads + hp - 1) / hp;
+  const int ld = 3 * E;
+  const int chunks = (S + 31) / 32;
+  for (long long work = blockIdx.x; work < (long long)NB * passes; work += gridDim.x) {
+    const int b = (int)(work / passes), pass = (int)(work % passes);
+    const int h0 = pass * hp, nh = min(hp, heads - h0);
+    const int W = nh * DH;
+    const int P = 5 * W;  // [q | k | v | dO | dQ]
+    const int segv = W / 4;
+    float* s_lse = tile + (long long)S * P;   // [S][nh]
+    float* s_dd = s_lse + S * nh;             // [S][nh]
+    __syncthreads();
+    for (int i = threadIdx.x; i < S * 4 * segv; i += blockDim.x) {
+      const int srow = i / (4 * segv), rem = i % (4 * segv), seg = rem / segv, c4 = rem % segv;
+      const long long grow = (long long)srow * seq_stride + (long long)b * batch_stride;
+      const float4* src = seg < 3 ? reinterpret_cast<const float4*>(qkv + grow * ld + seg * E + h0 * DH)
+                                  : reinterpret_cast<const float4*>(d_o + grow * ld_do + h0 * DH);
+      reinterpret_cast<float4*>(tile + (long long)srow * P + seg * W)[c4] = __ldg(src + c4);
+    }
+    for (int i = threadIdx.x; i < S * nh; i += blockDim.x) {
+      const int srow = i / nh, hl = i % nh;
+      const long long grow = (long long)srow * seq_stride + (long long)b * batch_stride;
+      s_lse[i] = lse[grow * heads + h0 + hl];
+    }
+    __syncthreads();
+    // ---- phase A: lane = query.  sweep 1: D_t = sum_u p dp;  sweep 2: dq_t ----
+    for (int it = warp; it < nh * chunks; it += nwarps) {
+      const int hl = it / chunks, qc = it % chunks;
+      const int t = qc * 32 + lane;
+      const bool ok = t < S;
+      const float* base = tile + (long long)(ok ? t : 0) * P + hl * DH;
+      float q[DH], go[DH], dq[DH];
+#pragma unroll
+      for (int d = 0; d < DH; d += 4) {
+        float4 t4 = *reinterpret_cast<const float4*>(base + d);
+        float4 g4 = *reinterpret_cast<const float4*>(base + 3 * W + d);
+        q[d] = t4.x * scale; q[d + 1] = t4.y * scale; q[d + 2] = t4.z * scale; q[d + 3] = t4.w * scale;
+        go[d] = g4.x; go[d + 1] = g4.y; go[d + 2] = g4.z; go[d + 3] = g4.w;
+        dq[d] = dq[d + 1] = dq[d + 2] = dq[d + 3] = 0.f;
+      }
+      const float my_lse = s_lse[(ok ? t : 0) * nh + hl];
+      float dd = 0.f;
+      for (int u = 0; u < S; ++u) {
+        const float* kr = tile + (long long)u * P + W + hl * DH;
+        float sc = 0.f, dp = 0.f;
+#pragma unroll
+        for (int d = 0; d < DH; d += 4) {
+          float4 k4 = *reinterpret_cast<const float4*>(kr + d);
+          float4 v4 = *reinterpret_cast<const float4*>(kr + W + d);
+          sc += q[d] * k4.x + q[d + 1] * k4.y + q[d + 2] * k4.z + q[d + 3] * k4.w;
+          dp += go[d] * v4.x + go[d + 1] * v4.y + go[d + 2] * v4.z + go[d + 3] * v4.w;
+        }
+        dd += expf(sc - my_lse) * dp;
+      }
+      for (int u = 0; u < S; ++u) {
+        const float* kr = tile + (long long)u * P + W + hl * DH;
+        float sc = 0.f, dp = 0.f;
+#pragma unroll
+        for (int d = 0; d < DH; d += 4) {
+          float4 k4 = *reinterpret_cast<const float4*>(kr + d);
+          float4 v4 = *reinterpret_cast<const float4*>(kr + W + d);
+          sc += q[d] * k4.x + q[d + 1] * k4.y + q[d + 2] * k4.z + q[d + 3] * k4.w;
+          dp += go[d] * v4.x + go[d + 1] * v4.y + go[d + 2] * v4.z + go[d + 3] * v4.w;
+        }
+        const float ds = expf(sc - my_lse) * (dp - dd);
+#pragma unroll
+        for (int d = 0; d < DH; d += 4) {
+          float4 k4 = *reinterpret_cast<const float4*>(kr + d);
+          dq[d] += ds * k4.x; dq[d + 1] += ds * k4.y; dq[d + 2] += ds * k4.z; dq[d + 3] += ds * k4.w;
+        }
+      }
+      if (ok) {
+        float* dst = tile + (long long)t * P + 4 * W + hl * DH;
+#pragma unroll
+        for (int d = 0; d < DH; ++d) dst[d] = dq[d] * scale;
+        s_dd[t * nh + hl] = dd;
+      }
+    }
+    __syncthreads();
+    // ---- phase B: lane = key -> dK, dV (written in place over the K / V slices) ----
+    for (int it = warp; it < nh * chunks; it += nwarps) {
+      const int hl = it / chunks, kc = it % chunks;
+      const int u = kc * 32 + lane;
+      const bool ok = u < S;
+      float* krow = tile + (long long)(ok ? u : 0) * P + W + hl * DH;
+      float kk[DH], vv[DH], dk[DH], dv[DH];
+#pragma unroll
+      for (int d = 0; d < DH; d += 4) {
+        float4 k4 = *reinterpret_cast<const float4*>(krow + d);
+        float4 v4 = *reinterpret_cast<const float4*>(krow + W + d);
+        kk[d] = k4.x; kk[d + 1] = k4.y; kk[d + 2] = k4.z; kk[d + 3] = k4.w;
+        vv[d] = v4.x; vv[d + 1] = v4.y; vv[d + 2] = v4.z; vv[d + 3] = v4.w;
+        dk[d] = dk[d + 1] = dk[d + 2] = dk[d + 3] = 0.f;
+        dv[d] = dv[d + 1] = dv[d + 2] = dv[d + 3] = 0.f;
+      }
+      for (int t = 0; t < S; ++t) {
+        const float* qr = tile + (long long)t * P + hl * DH;
+        float sc = 0.f, dp = 0.f;
+#pragma unroll
+        for (int d = 0; d < DH; d += 4) {
+          float4 q4 = *reinterpret_cast<const float4*>(qr + d);
+          float4 g4 = *reinterpret_cast<const float4*>(qr + 3 * W + d);
+          sc += q4.x * kk[d] + q4.y * kk[d + 1] + q4.z * kk[d + 2] + q4.w * kk[d + 3];
+          dp += g4.x * vv[d] + g4.y * vv[d + 1] + g4.z * vv[d + 2] + g4.w * vv[d + 3];
+        }
+        const float pr = expf(sc * scale - s_lse[t * nh + hl]);
+        const float ds = pr * (dp - s_dd[t * nh + hl]) * scale;
+#pragma unroll
+        for (int d = 0; d < DH; d += 4) {
+          float4 q4 = *reinterpret_cast<const float4*>(qr + d);
+          float4 g4 = *reinterpret_cast<const float4*>(qr + 3 * W + d);
+          dk[d] += ds * q4.x; dk[d + 1] += ds * q4.y; dk[d + 2] += ds * q4.z; dk[d + 3] += ds * q4.w;
+          dv[d] += pr * g4.x; dv[d + 1] += pr * g4.y; dv[d + 2] += pr * g4.z; dv[d + 3] += pr * g4.w;
+        }
+      }
+      __syncwarp();
+      if (ok) {
+#pragma unroll
+        for (int d = 0; d < DH; ++d) { krow[d] = dk[d]; krow[W + d] = dv[d]; }
+      }
+    }
+    __syncthreads();
+    // ---- coalesced write-back: dQ | dK | dV row segments -> split planes ----
+    for (int i = threadIdx.x; i < S * 3 * (W / 2); i += blockDim.x) {
+      const int srow = i / (3 * (W / 2)), rem = i % (3 * (W / 2)), seg = rem / (W / 2), c = (rem % (W / 2)) * 2;
+      const long long grow = (long long)srow * seq_stride + (long long)b * batch_stride;
+      const int ssrc = seg == 0 ? 4 : seg;  // dQ lives in segment 4, dK / dV replaced segments 1 / 2
+      const float2 val = *reinterpret_cast<const float2*>(tile + (long long)srow * P + ssrc * W + c);
+      __nv_bfloat16 ah, al, bh, bl;
+      split_bf16(val.x, ah, al);
+      split_bf16(val.y, bh, bl);
+      const long long off = grow * p3 + seg * E + h0 * DH + c;
+      *reinterpret_cast<uint32_t*>(g_hi + off) = pack_bf16x2(ah, bh);
+      if (g_lo) *reinterpret_cast<uint32_t*>(g_lo + off) = pack_bf16x2(al, bl);
+    }
+    if (pass == 0 && p3 > 3 * E) {
+      for (int i = threadIdx.x; i < S * (p3 - 3 * E); i += blockDim.x) {
+        const int srow = i / (p3 - 3 * E), c = 3 * E + i % (p3 - 3 * E);
+        const long long grow = (long long)srow * seq_stride + (long long)b * batch_stride;
+        g_hi[grow * p3 + c] = __float2bfloat16_rn(0.f);
+        if (g_lo) g_lo[grow * p3 + c] = __float2bfloat16_rn(0.f);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // a5: additive pooling.  Group g owns rows g*L .. g*L+L-1.  score[r] = tanh(xW+b).q comes
 // from the GEMM epilogue; here: w = softmax_L(score), out[g] = sum_t w_t * Y[row_t].
 // ------------------------------------------------------------------------------------
@@ -448,24 +712,22 @@ pool_fwd_kernel(const float* __restrict__ score, const float* __restrict__ Y, in
 //   dq      += sum_r ds_r * A_r                                (atomics, once per block)
 //   db      += sum_r dApre[r]   (fp32: the terms cancel almost exactly because sum_t ds_t = 0
 //                                per group, so this sum is NOT routed through the bf16 split)
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 pool_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ Y,
                 const float* __restrict__ w, const float* __restrict__ A,
                 const float* __restrict__ qvec, int E, int Q, int qp, int L, long long G,
                 float* __restrict__ dY1, __nv_bfloat16* __restrict__ da_hi,
                 __nv_bfloat16* __restrict__ da_lo, float* __restrict__ dq_accum,
                 float* __restrict__ db_accum) {
-  extern __shared__ float sm[];  // [L] ds, then [Q] dq partial, then [Q] db partial
+  extern __shared__ float sm[];  // [L] ds
   float* s_ds = sm;
-  float* s_dq = sm + L;
-  float* s_db = sm + L + Q;
   __shared__ float red[33];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int j = threadIdx.x; j < Q; j += blockDim.x) { s_dq[j] = 0.f; s_db[j] = 0.f; }
-  __syncthreads();
+  // this thread owns columns j = tid, tid + blockDim, ... of the [*, qp] tanh matrix
+  float dq_acc[2] = {0.f, 0.f}, db_acc[2] = {0.f, 0.f};  // qp <= 2 * blockDim (Q <= 256... host checks)
   for (long long g = blockIdx.x; g < G; g += gridDim.x) {
     const long long r0 = g * L;
-    // dw_t = dOut . Y_t  (one warp per row)
+    // dw_t = dOut . Y_t  (one warp per row, coalesced over E)
     for (int t = warp; t < L; t += nw) {
       float acc = 0.f;
       for (int c = lane; c < E; c += 32) acc += d_out[g * E + c] * Y[(r0 + t) * E + c];
@@ -478,38 +740,36 @@ pool_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ Y,
     const float dbar = block_sum(part, red);
     for (int t = threadIdx.x; t < L; t += blockDim.x) s_ds[t] = w[r0 + t] * (s_ds[t] - dbar);
     __syncthreads();
-    for (int i = threadIdx.x; i < L * E; i += blockDim.x) {
-      const int t = i / E, c = i % E;
-      dY1[(r0 + t) * E + c] = w[r0 + t] * d_out[g * E + c];
+    if (dY1) {  // otherwise the data-gradient GEMM adds w_r * dOut[g] in its epilogue
+      for (int t = 0; t < L; ++t)
+        for (int c = threadIdx.x; c < E; c += blockDim.x)
+          dY1[(r0 + t) * E + c] = w[r0 + t] * d_out[g * E + c];
     }
-    for (int i = threadIdx.x; i < L * qp; i += blockDim.x) {
-      const int t = i / qp, j = i % qp;
-      float v = 0.f;
-      if (j < Q) {
-        const float a = A[(r0 + t) * Q + j];
-        v = s_ds[t] * qvec[j] * (1.f - a * a);
-      }
-      __nv_bfloat16 hh, ll;
-      split_bf16(v, hh, ll);
-      da_hi[(r0 + t) * qp + j] = hh;
-      if (da_lo) da_lo[(r0 + t) * qp + j] = ll;
-    }
-    for (int j = threadIdx.x; j < Q; j += blockDim.x) {
-      float acc = 0.f, accb = 0.f;
-      const float qj = qvec[j];
+    // single pass over A: dApre (split planes), and the dq / db partial sums of this thread's columns
+    int slot = 0;
+    for (int j = threadIdx.x; j < qp; j += blockDim.x, ++slot) {
+      const bool in = j < Q;
+      const float qj = in ? qvec[j] : 0.f;
+      float aq = 0.f, ab = 0.f;
       for (int t = 0; t < L; ++t) {
-        const float a = A[(r0 + t) * Q + j];
-        acc += s_ds[t] * a;
-        accb += s_ds[t] * qj * (1.f - a * a);
+        const float a = in ? A[(r0 + t) * Q + j] : 0.f;
+        const float v = s_ds[t] * qj * (1.f - a * a);
+        __nv_bfloat16 hh, ll;
+        split_bf16(v, hh, ll);
+        da_hi[(r0 + t) * qp + j] = hh;
+        if (da_lo) da_lo[(r0 + t) * qp + j] = ll;
+        aq += s_ds[t] * a;
+        ab += v;
       }
-      s_dq[j] += acc;
-      s_db[j] += accb;
+      dq_acc[slot] += aq;
+      db_acc[slot] += ab;
     }
     __syncthreads();
   }
-  for (int j = threadIdx.x; j < Q; j += blockDim.x) {
-    atomicAdd(dq_accum + j, s_dq[j]);
-    atomicAdd(db_accum + j, s_db[j]);
+  int slot = 0;
+  for (int j = threadIdx.x; j < Q; j += blockDim.x, ++slot) {
+    atomicAdd(dq_accum + j, dq_acc[slot]);
+    atomicAdd(db_accum + j, db_acc[slot]);
   }
 }
 

@@ -1,0 +1,118 @@
+"""GPU tests of the drop-in boundary: the reference-shaped modules (same constructor kwargs and
+state_dict keys) driven like the reference drives them, against the CPU oracle."""
+import functools
+
+import pytest
+import torch
+
+from helpers import TITLE, grad_tolerances, oracle_run, rel_err, to_dev
+from newsreclib_b200.synthetic import make_batch, make_nrms_params
+
+pytestmark = pytest.mark.gpu
+
+OUTPUTS = {"train": ["preds", "targets", "cand_news_size"], "val": ["preds", "targets", "cand_news_size"],
+           "test": ["preds", "targets", "cand_news_size", "hist_news_size", "user_ids", "cand_news_ids"]}
+
+
+def make_module(params, late_fusion=False, p=0.2):
+    from newsreclib_b200.models.general_rec.nrms_module import NRMSModule
+    m = NRMSModule(
+        dataset_attributes=["title", "category"], attributes2encode=["title"], outputs=OUTPUTS,
+        dual_loss_training=False, dual_loss_coef=None, loss="cross_entropy_loss", late_fusion=late_fusion,
+        temperature=None, use_plm=False, pretrained_embeddings_path=None, plm_model=None, frozen_layers=None,
+        embed_dim=300, num_heads=15, query_dim=200, dropout_probability=p, top_k_list=[5, 10],
+        num_categ_classes=18, num_sent_classes=3, save_recs=False, recs_fpath=None,
+        optimizer=functools.partial(torch.optim.Adam, lr=1e-4), scheduler=None,
+        pretrained_embeddings=params[TITLE + "embedding_layer.weight"])
+    return m
+
+
+def full_batch(batch, dev="cuda"):
+    b = to_dev(batch, dev)
+    for side in ("x_hist", "x_cand"):
+        for k in ("category", "sentiment", "news_ids"):
+            b[side][k] = batch[side][k].to(dev)
+    b["user_ids"] = batch["user_ids"].to(dev)
+    b["user_idx"] = batch["user_idx"].to(dev)
+    return b
+
+
+def test_nrms_module_forward_backward_matches_oracle():
+    V = 2500
+    params = make_nrms_params(V, seed=21)
+    batch = make_batch(12, V, hist="ragged", cand="train", seed=21, max_hist=15)
+    m = make_module(params)
+    missing = m.load_state_dict(params, strict=True)  # reference key names load as-is
+    assert not missing.missing_keys and not missing.unexpected_keys
+    m = m.cuda().eval()
+    b = full_batch(batch)
+    scores = m(b)
+    rs, rl, rg = oracle_run(params, batch, 15)
+    assert rel_err(scores, rs) <= 1e-4
+    out = m.model_step(b)
+    assert len(out) == 11
+    loss, preds, targets, cand_size, hist_size = out[:5]
+    assert rel_err(loss, rl) <= 1e-4
+    assert torch.equal(cand_size.cpu(), torch.bincount(batch["batch_cand"]))
+    assert torch.equal(hist_size.cpu(), torch.bincount(batch["batch_hist"]))
+    assert preds.numel() == batch["labels"].numel() and torch.equal(targets.cpu(), batch["labels"])
+    loss.backward()
+    tols = grad_tolerances(params, batch, 15, 1e-3, rg)
+    for k, p in m.named_parameters():
+        assert p.grad is not None, k
+        assert rel_err(p.grad, rg[k]) <= tols[k], k
+    assert float(m.news_encoder.text_encoders["title"].embedding_layer.weight.grad[0].abs().max()) == 0.0
+
+
+def test_nrms_module_trains_and_roundtrips_state_dict():
+    V = 1500
+    params = make_nrms_params(V, seed=5)
+    m = make_module(params).cuda().train()
+    m.load_state_dict(params)
+    opt = m.configure_optimizers()["optimizer"]
+    losses = []
+    batch = full_batch(make_batch(8, V, hist="ragged", seed=5, max_hist=10))
+    for step in range(8):
+        opt.zero_grad()
+        loss = m.training_step(batch, step)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert all(l == l for l in losses) and losses[-1] < losses[0]  # finite and overfitting one batch
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    m2 = make_module(params).cuda().eval()
+    m2.load_state_dict(sd)
+    m.eval()
+    assert torch.equal(m(batch), m2(batch))  # deterministic in eval mode
+    metrics = m.on_train_epoch_end()
+    assert {"train/auc", "train/mrr", "train/ndcg@5", "train/ndcg@10"} <= set(metrics)
+
+
+def test_late_fusion_module():
+    V = 1200
+    params = make_nrms_params(V, seed=8)
+    batch = make_batch(5, V, hist="ragged", seed=8, max_hist=6)
+    m = make_module(params, late_fusion=True)
+    m.load_state_dict({k: v for k, v in params.items() if k.startswith(TITLE)}, strict=True)
+    m = m.cuda().eval()
+    rs, _, _ = oracle_run(params, batch, 15, late_fusion=True, grad=False)
+    assert rel_err(m(full_batch(batch)), rs) <= 1e-4
+
+
+def test_component_interfaces():
+    from newsreclib_b200.models.components.layers.attention import AdditiveAttention
+    from newsreclib_b200.models.components.layers.click_predictor import DotProduct
+    from oracle import nrms_oracle as O
+    with pytest.raises(ValueError):
+        AdditiveAttention(input_dim=300.0, query_dim=200)
+    from newsreclib_b200.models.components.encoders.news.text import MHSAAddAtt
+    with pytest.raises(ValueError):
+        MHSAAddAtt(torch.randn(10, 300), 300, 15, 200, 1)  # dropout_probability must be a float
+    torch.manual_seed(0)
+    add = AdditiveAttention(400, 200).cuda()
+    x = torch.randn(7, 3, 400).cuda()  # NAML view combiner shape (news.py:162-163)
+    with torch.no_grad():
+        ref = O.additive_attention(x.cpu(), add.linear.weight.cpu(), add.linear.bias.cpu(), add.query.cpu())
+    assert rel_err(add(x), ref) <= 1e-4
+    u, c = torch.randn(6, 1, 300).cuda(), torch.randn(6, 300, 9).cuda()
+    assert rel_err(DotProduct()(u, c), torch.bmm(u, c).squeeze(1)) <= 1e-5
