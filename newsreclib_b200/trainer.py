@@ -25,6 +25,57 @@ TITLE = "news_encoder.text_encoders.title."
 USER = "user_encoder."
 
 
+class FlatParams:
+    """ONE flat fp32 buffer holding every parameter under the reference's ``state_dict`` names,
+    plus same-shaped gradient / Adam-moment buffers.  Pure host-side bookkeeping (works on any
+    device, so the world_size-2 gloo tests exercise it on CPU).  Every tensor starts on a
+    16-byte boundary (the table gradient uses 128-bit atomics)."""
+
+    def __init__(self, params: Dict[str, torch.Tensor], keys, device) -> None:
+        self.keys = list(keys)
+        shapes = [tuple(params[k].shape) for k in self.keys]
+        sizes = [params[k].numel() for k in self.keys]
+        self.offsets, total = [], 0
+        for n in sizes:
+            self.offsets.append(total)
+            total += (n + 3) // 4 * 4
+        self.flat = torch.zeros(total, dtype=torch.float32, device=device)
+        self.grad = torch.zeros_like(self.flat)
+        self.m = torch.zeros_like(self.flat)
+        self.v = torch.zeros_like(self.flat)
+        self.params, self.grads = {}, {}
+        for k, o, n, shp in zip(self.keys, self.offsets, sizes, shapes):
+            self.params[k] = self.flat[o:o + n].view(shp)
+            self.grads[k] = self.grad[o:o + n].view(shp)
+            self.params[k].copy_(params[k])
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        return {k: v.detach().clone() for k, v in self.params.items()}
+
+
+class GradExchange:
+    """The path's single exchange step: sum the flat gradient buffer over the ranks (NCCL over
+    NVLink on GPUs, gloo in the CPU tests) and hand back the ``1 / world_size`` factor the Adam
+    kernel folds into its gradient read — together the mean Lightning DDP applies for the
+    reference (``configs/trainer/ddp.yaml``).  world_size 1 = no-op."""
+
+    def __init__(self, process_group=None) -> None:
+        self.pg = process_group
+        on = torch.distributed.is_available() and torch.distributed.is_initialized()
+        self.world = torch.distributed.get_world_size(process_group) if on else 1
+
+    def all_reduce(self, flat_grad: torch.Tensor) -> float:
+        if self.world > 1:
+            torch.distributed.all_reduce(flat_grad, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+        return 1.0 / self.world
+
+    @staticmethod
+    def rank_seed(base_seed: int, rank: int, step: int) -> int:
+        """Dropout seed of (rank, step): ranks must not share masks (they see different
+        impressions), and a rank must never reuse a seed across steps."""
+        return (int(base_seed) + 1000003 * int(rank) + int(step)) & ((1 << 62) - 1)
+
+
 class NRMSTrainer:
     def __init__(self, params: Dict[str, torch.Tensor], num_heads: int, *, device="cuda",
                  dropout_p: float = 0.2, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
@@ -34,22 +85,9 @@ class NRMSTrainer:
         self.device = torch.device(device)
         self.keys = [TITLE + "embedding_layer.weight"] + [TITLE + k for k in ops.BLOCK_KEYS] + \
                     [USER + k for k in ops.BLOCK_KEYS]
-        shapes = [tuple(params[k].shape) for k in self.keys]
-        sizes = [params[k].numel() for k in self.keys]
-        # every tensor starts on a 16-byte boundary (the table gradient uses 128-bit atomics)
-        offs, total = [], 0
-        for n in sizes:
-            offs.append(total)
-            total += (n + 3) // 4 * 4
-        self.flat = torch.zeros(total, dtype=torch.float32, device=self.device)
-        self.grad = torch.zeros_like(self.flat)
-        self.m = torch.zeros_like(self.flat)
-        self.v = torch.zeros_like(self.flat)
-        self.params, self.grads = {}, {}
-        for k, o, n, shp in zip(self.keys, offs, sizes, shapes):
-            self.params[k] = self.flat[o:o + n].view(shp)
-            self.grads[k] = self.grad[o:o + n].view(shp)
-            self.params[k].copy_(params[k])
+        self.fp = FlatParams(params, self.keys, self.device)
+        self.flat, self.grad, self.m, self.v = self.fp.flat, self.fp.grad, self.fp.m, self.fp.v
+        self.params, self.grads = self.fp.params, self.fp.grads
         self.table = self.params[self.keys[0]]
         E = self.table.shape[1]
         Q = self.params[TITLE + "additive_attention.query"].numel()
@@ -62,12 +100,11 @@ class NRMSTrainer:
         self.precision, self.late_fusion, self.seed = precision, late_fusion, seed
         self.step_count = 0
         self.ws: Optional[torch.Tensor] = None
-        self.pg = process_group
-        self.world = torch.distributed.get_world_size(process_group) if self._dist() else 1
+        self.exchange = GradExchange(process_group)
+        self.world = self.exchange.world
+        on = torch.distributed.is_available() and torch.distributed.is_initialized()
+        self.rank = torch.distributed.get_rank(process_group) if on else 0
         self._structs = None
-
-    def _dist(self) -> bool:
-        return torch.distributed.is_available() and torch.distributed.is_initialized()
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
         """Reference-named parameters (loadable into the reference's NRMSModule)."""
@@ -75,11 +112,10 @@ class NRMSTrainer:
 
     # ------------------------------------------------------------------ steps
     def _finish(self) -> None:
-        if self.world > 1:
-            torch.distributed.all_reduce(self.grad, group=self.pg)
+        scale = self.exchange.all_reduce(self.grad)
         self.step_count += 1
         ops.adam_step(self.flat, self.grad, self.m, self.v, self.step_count, self.lr, self.betas[0],
-                      self.betas[1], self.eps, grad_scale=1.0 / self.world)
+                      self.betas[1], self.eps, grad_scale=scale)
 
     def train_step(self, batch: Dict, B: int, Hmax: int, Cmax: int, training: bool = True):
         """Device-resident batch -> (scores [B, Cmax], loss [1]) device tensors; no host sync."""
@@ -87,7 +123,7 @@ class NRMSTrainer:
         scores, loss, self.ws = ops.nrms_step(
             batch, self.table, self.news_block, self.user_block, self.dims, B=B, Hmax=Hmax, Cmax=Cmax,
             late_fusion=self.late_fusion, dropout_p=self.dropout_p, training=training,
-            seed=self.seed + self.step_count, grads=self.grad_pack, ws=self.ws, precision=self.precision)
+            seed=GradExchange.rank_seed(self.seed, self.rank, self.step_count), grads=self.grad_pack, ws=self.ws, precision=self.precision)
         self._finish()
         return scores, loss
 
@@ -110,7 +146,7 @@ class NRMSTrainer:
             hist_ids.data_ptr(), cand_ids.data_ptr(), hb["batch_hist"].data_ptr(), hb["batch_cand"].data_ptr(),
             hb["labels"].data_ptr(), nh, nc, L, B, Hmax, Cmax, self.table.data_ptr(), self.table.shape[0],
             C.byref(nb), C.byref(ub), self.dims, int(self.late_fusion), float(self.dropout_p), int(training),
-            int(self.seed + self.step_count), scores_host.data_ptr(), loss_host.data_ptr(), 1, C.byref(ng),
+            GradExchange.rank_seed(self.seed, self.rank, self.step_count), scores_host.data_ptr(), loss_host.data_ptr(), 1, C.byref(ng),
             C.byref(ug), self.grad_pack[2].data_ptr(), self.ws.data_ptr(), self.ws.numel(), self.precision,
             torch.cuda.current_stream().cuda_stream), "nrl_nrms_step_host")
         self._finish()
