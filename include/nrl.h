@@ -184,6 +184,11 @@ int nrl_dropout_mask(unsigned char* keep, long long n, unsigned long long seed, 
 size_t nrl_gemm_test_ws_bytes(int M, int N, int K);
 int nrl_gemm_test(const float* A, const float* B, float* D, int M, int N, int K, int mn_major,
                   int precision, void* ws, size_t ws_bytes, void* stream);
+/* Same NT GEMM through the split-plane sink (the layout the encoder GEMMs hand to the next GEMM):
+ * out [M, Np] fp32 = hi + lo of the stored bf16 planes, Np = round_up(N + 1, 16); column N reads
+ * 1.0 (the bias column) and the remaining pad columns 0. */
+int nrl_gemm_test_planes(const float* A, const float* B, float* out, int M, int N, int K,
+                         int precision, void* ws, size_t ws_bytes, void* stream);
 /* number of kernels launched by this library since load (bench.py reports it) */
 long long nrl_launch_count(void);
 /* Per-launch device timing for bench.py's roofline leg: after nrl_profile_start(stream) one

@@ -75,6 +75,7 @@ SIGNATURES = {
     "nrl_dropout_mask": (_I, [_VP, _LL, _ULL, _I, _F, _VP]),
     "nrl_gemm_test_ws_bytes": (_SZ, [_I, _I, _I]),
     "nrl_gemm_test": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _VP, _SZ, _VP]),
+    "nrl_gemm_test_planes": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _VP, _SZ, _VP]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -109,7 +109,7 @@ static int device_init() {
     return fail(NRL_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   g_dev.encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
   CUDA_TRY(cudaFuncSetAttribute(nrl_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                GEMM_SMEM_BYTES));
+                                GEMM_SMEM_LIMIT));
   g_dev.ok = true;
   return NRL_OK;
 }
@@ -215,52 +215,82 @@ static int make_tmap(CUtensorMap* m, const bf16* base, unsigned long long inner,
   return NRL_OK;
 }
 
-static int choose_bn(int N, int granule) {
-  int n_tiles = (N + 255) / 256;
-  int bn = round_up((N + n_tiles - 1) / n_tiles, granule);
-  return bn > 256 ? 256 : bn;
+// fp32 sink [rows, cols] with row pitch ld (floats): 32 x 32 boxes, SWIZZLE_128B staging
+static int make_tmap_f32(CUtensorMap* m, const float* base, unsigned long long cols,
+                         unsigned long long rows, unsigned long long ld) {
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld & 3))
+    return fail(NRL_ERR_INVALID_ARG, "fp32 GEMM sink must be 16-byte aligned with a pitch that is a multiple of 4 floats");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {ld * sizeof(float)};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_dev.encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr,
+                            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(NRL_ERR_CUDA, "cuTensorMapEncodeTiled(f32 sink) failed (%d): cols=%llu rows=%llu ld=%llu",
+                (int)r, cols, rows, ld);
+  return NRL_OK;
+}
+// split-plane bf16 sink [planes][rows][pitch]: 32 x 32 x planes boxes, SWIZZLE_64B staging
+static int make_tmap_planes(CUtensorMap* m, const bf16* base, unsigned long long cols,
+                            unsigned long long rows, unsigned long long pitch, int planes) {
+  cuuint64_t gdim[3] = {cols, rows, (cuuint64_t)planes};
+  cuuint64_t gstr[2] = {pitch * sizeof(bf16), rows * pitch * sizeof(bf16)};
+  cuuint32_t box[3] = {32, 32, (cuuint32_t)planes};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_dev.encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(base), gdim, gstr,
+                            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(NRL_ERR_CUDA, "cuTensorMapEncodeTiled(plane sink) failed (%d): cols=%llu rows=%llu pitch=%llu",
+                (int)r, cols, rows, pitch);
+  return NRL_OK;
 }
 
-// K-major ("NT") GEMM: D[M,N] = A[M,K] * B[N,K]^T.  a/b point at plane 0; plane 1 follows.
-static int gemm_nt(const Ctx& c, const bf16* A, long long M, int a_pitch, const bf16* B, int N,
-                   int b_pitch, int K, const GemmEpi& epi, const char* name) {
-  GemmParams p;
-  memset(&p, 0, sizeof(p));
-  p.M = (int)M; p.N = N; p.K = K;
-  p.BN = choose_bn(epi.hi ? (epi.sp_cols > N ? epi.sp_cols : N) : N, 16);
-  if (epi.score && p.BN < N) return fail(NRL_ERR_UNSUPPORTED, "score fusion needs N <= 256");
-  p.mn_major = 0;
-  if (c.two_planes()) {
-    p.num_segs = 3;
-    p.seg_a[0] = 1; p.seg_b[0] = 0;
-    p.seg_a[1] = 0; p.seg_b[1] = 1;
-    p.seg_a[2] = 0; p.seg_b[2] = 0;
-  } else {
-    p.num_segs = 1;
+// Host-side description of where a GEMM's result goes (turned into tensor maps + GemmEpi).
+struct Sinks {
+  float* f32 = nullptr; long long ld_f32 = 0; int f32_cols = 0; bool reduce = false;  // fp32 [M, f32_cols]
+  bf16* sp = nullptr; long long ld_sp = 0; int sp_cols = 0; int ones_col = -1;       // planes [2][M, sp_cols]
+};
+
+static int launch_gemm(const Ctx& c, GemmParams& p, const CUtensorMap& ta, const CUtensorMap& tb,
+                       const Sinks& sk, const char* name) {
+  CUtensorMap tout, tsp;
+  memset(&tout, 0, sizeof(tout));
+  memset(&tsp, 0, sizeof(tsp));
+  p.epi.f32_sink = 0; p.epi.sp_sink = 0;
+  if (sk.f32) {
+    TRY(make_tmap_f32(&tout, sk.f32, sk.f32_cols, p.M, sk.ld_f32));
+    p.epi.f32_sink = sk.reduce ? 2 : 1;
+    p.epi.f32_cols = sk.f32_cols;
   }
-  p.k_splits = 1;
-  p.epi = epi;
-  if (!c.two_planes()) p.epi.lo = nullptr;
-  CUtensorMap ta, tb;
-  TRY(make_tmap(&ta, A, K, M, a_pitch, GEMM_BK, GEMM_BM));
-  TRY(make_tmap(&tb, B, K, N, b_pitch, GEMM_BK, p.BN));
-  const int n_extent = (epi.hi && epi.sp_cols > N) ? epi.sp_cols : N;
-  const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM, n_tiles = (n_extent + p.BN - 1) / p.BN;
-  const int tiles = m_tiles * n_tiles;
-  const int grid = tiles < g_dev.sm_count ? tiles : g_dev.sm_count;
-  nrl_gemm_tc_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, c.stream>>>(ta, tb, p);
+  if (sk.sp) {
+    TRY(make_tmap_planes(&tsp, sk.sp, sk.sp_cols, p.M, sk.ld_sp, c.two_planes() ? 2 : 1));
+    p.epi.sp_sink = 1;
+    p.epi.sp_cols = sk.sp_cols;
+    p.epi.sp_two = c.two_planes() ? 1 : 0;
+    p.epi.ones_col = sk.ones_col;
+  }
+  p.epi_buf_bytes = (sk.f32 && sk.sp) ? 8192 : 4096;
+  const int stage_bytes = GEMM_A_BYTES + (p.mn_major ? (p.BN + 63) / 64 * 8192 : p.BN * 128);
+  int stages = (GEMM_SMEM_LIMIT - 1024 - GEMM_BAR_BYTES - 8 * p.epi_buf_bytes) / stage_bytes;
+  if (stages > GEMM_MAX_STAGES) stages = GEMM_MAX_STAGES;
+  if (stages < 2) return fail(NRL_ERR_UNSUPPORTED, "GEMM tile does not fit shared memory");
+  p.stages = stages;
+  const int smem = 1024 + stages * stage_bytes + 8 * p.epi_buf_bytes + GEMM_BAR_BYTES;
+  const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM, n_tiles = (p.n_extent + p.BN - 1) / p.BN;
+  const int tiles = m_tiles * n_tiles * p.k_splits;
+  // unit = whole m-block when there are enough m-blocks to fill the machine twice over
+  p.tiles_per_unit = (p.k_splits == 1 && n_tiles > 1 && m_tiles >= 2 * g_dev.sm_count) ? n_tiles : 1;
+  const int units = tiles / p.tiles_per_unit;
+  const int grid = units < g_dev.sm_count ? units : g_dev.sm_count;
+  nrl_gemm_tc_kernel<<<grid, GEMM_THREADS, smem, c.stream>>>(ta, tb, tout, tsp, p);
   LAUNCH_CHECK(name);
   return NRL_OK;
 }
 
-// MN-major ("TN") weight-gradient GEMM: G[M,N] += sum_r A[r, m] * B[r, n], r < R.
-static int gemm_tn(const Ctx& c, const bf16* A, int M, int a_pitch, const bf16* B, int N,
-                   int b_pitch, long long R, const GemmEpi& epi, const char* name) {
-  GemmParams p;
-  memset(&p, 0, sizeof(p));
-  p.M = M; p.N = N; p.K = (int)R;
-  p.BN = choose_bn(N, 64);
-  p.mn_major = 1;
+static void set_segs(const Ctx& c, GemmParams& p) {
   if (c.two_planes()) {
     p.num_segs = 3;
     p.seg_a[0] = 1; p.seg_b[0] = 0;
@@ -269,23 +299,61 @@ static int gemm_tn(const Ctx& c, const bf16* A, int M, int a_pitch, const bf16* 
   } else {
     p.num_segs = 1;
   }
+}
+
+// K-major ("NT") GEMM: D[M,N] = A[M,K] * B[N,K]^T.  a/b point at plane 0; plane 1 follows.
+static int gemm_nt(const Ctx& c, const bf16* A, long long M, int a_pitch, const bf16* B, int N,
+                   int b_pitch, int K, const GemmEpi& epi, const Sinks& sk, const char* name) {
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = (int)M; p.N = N; p.K = K;
+  p.n_extent = (sk.sp && sk.sp_cols > N) ? sk.sp_cols : N;
+  p.BN = p.n_extent >= 256 ? 256 : round_up(p.n_extent, 16);
+  if (epi.score && p.BN < N) return fail(NRL_ERR_UNSUPPORTED, "score fusion needs N <= 256");
+  p.mn_major = 0;
+  set_segs(c, p);
+  p.k_splits = 1;
+  p.epi = epi;
+  CUtensorMap ta, tb;
+  TRY(make_tmap(&ta, A, K, M, a_pitch, GEMM_BK, GEMM_BM));
+  TRY(make_tmap(&tb, B, K, N, b_pitch, GEMM_BK, p.BN));
+  return launch_gemm(c, p, ta, tb, sk, name);
+}
+
+// MN-major ("TN") weight-gradient GEMM: G[M,N] += sum_r A[r, m] * B[r, n], r < R (split-K,
+// partial tiles are TMA-reduced into G).  Accumulator column gb_col (the ones column of B)
+// goes to the bias gradient gb[m].
+static int gemm_tn(const Ctx& c, const bf16* A, int M, int a_pitch, const bf16* B, int N,
+                   int b_pitch, long long R, float* gw, long long ld_gw, int gw_cols, float* gb,
+                   const char* name) {
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = (int)R;
+  p.n_extent = N;
+  {
+    const int nt = (N + 255) / 256;
+    p.BN = round_up((N + nt - 1) / nt, 16);
+  }
+  p.mn_major = 1;
+  set_segs(c, p);
   const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM, n_tiles = (N + p.BN - 1) / p.BN;
   const int kb_total = (int)((R + GEMM_BK - 1) / GEMM_BK);
-  int ks = (2 * g_dev.sm_count) / (m_tiles * n_tiles);
+  int ks = g_dev.sm_count / m_tiles;  // every n-block's tiles fill the machine once
   if (ks < 1) ks = 1;
   if (ks > kb_total) ks = kb_total;
   // no empty splits: shrink until every split owns at least one k-block
   while (ks > 1 && (long long)(ks - 1) * ((kb_total + ks - 1) / ks) >= kb_total) --ks;
   p.k_splits = ks;
-  p.epi = epi;
+  memset(&p.epi, 0, sizeof(p.epi));
+  p.epi.ones_col = -1;
+  p.epi.gb = gb; p.epi.gb_col = gw_cols;
+  Sinks sk;
+  sk.f32 = gw; sk.ld_f32 = ld_gw; sk.f32_cols = gw_cols; sk.reduce = true;
   CUtensorMap ta, tb;
   TRY(make_tmap(&ta, A, a_pitch, R, a_pitch, 64, 64));
   TRY(make_tmap(&tb, B, b_pitch, R, b_pitch, 64, 64));
-  const int tiles = m_tiles * n_tiles * ks;
-  const int grid = tiles < g_dev.sm_count ? tiles : g_dev.sm_count;
-  nrl_gemm_tc_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, c.stream>>>(ta, tb, p);
-  LAUNCH_CHECK(name);
-  return NRL_OK;
+  (void)n_tiles;
+  return launch_gemm(c, p, ta, tb, sk, name);
 }
 
 static GemmEpi epi_none() {
@@ -319,18 +387,41 @@ struct AttnGeom {
 constexpr int ATTN_FWD_SMEM_BUDGET = 110 * 1024;
 constexpr int ATTN_BWD_SMEM_BUDGET = 100 * 1024;
 
+constexpr int ATTN_S32_SMEM_BUDGET = 96 * 1024;
+
 template <int DH>
 static int attn_set_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(attn_fwd_tile_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 ATTN_FWD_SMEM_BUDGET));
   CUDA_TRY(cudaFuncSetAttribute(attn_bwd_tile_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 ATTN_BWD_SMEM_BUDGET));
+  CUDA_TRY(cudaFuncSetAttribute(attn_fwd_s32_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                ATTN_S32_SMEM_BUDGET));
+  CUDA_TRY(cudaFuncSetAttribute(attn_bwd_s32_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                ATTN_S32_SMEM_BUDGET));
   return NRL_OK;
+}
+
+// heads per CTA of the S <= 32 kernels: the largest divisor of H that is <= 5 (else 4);
+// the kernels are compiled for at most 160 threads
+static int attn_head_group(int H) {
+  for (int hg = 5; hg >= 2; --hg)
+    if (H % hg == 0) return hg;
+  return H < 4 ? H : 4;
 }
 
 template <int DH>
 static void launch_attn_fwd(const Ctx& c, const Dims& d, const AttnGeom& g, const BlockWs& w, long long R) {
   bf16* lo = c.two_planes() ? w.o + R * d.Ep : nullptr;
+  if (g.S <= 32) {  // register-resident path (title tokens)
+    const int hg = attn_head_group(d.H), groups = (d.H + hg - 1) / hg;
+    const size_t smem = (size_t)g.S * attn_pitch(3 * hg * DH) * sizeof(float);
+    if (smem <= (size_t)ATTN_S32_SMEM_BUDGET) {
+      attn_fwd_s32_kernel<DH><<<grid_for((long long)g.NB * groups, 1, 16 * g_dev.sm_count), 32 * hg, smem, c.stream>>>(
+          w.qkv, d.E, d.H, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH), w.o, lo, d.Ep, w.lse);
+      return;
+    }
+  }
   const size_t per_head = (size_t)g.S * 3 * DH * sizeof(float);
   int hp = (int)(ATTN_FWD_SMEM_BUDGET / per_head);
   if (hp > d.H) hp = d.H;
@@ -347,6 +438,16 @@ static void launch_attn_fwd(const Ctx& c, const Dims& d, const AttnGeom& g, cons
 template <int DH>
 static void launch_attn_bwd(const Ctx& c, const Dims& d, const AttnGeom& g, const BlockWs& w, long long R) {
   bf16* lo = c.two_planes() ? w.dqkv + R * d.P3 : nullptr;
+  if (g.S <= 32) {
+    const int hg = attn_head_group(d.H), groups = (d.H + hg - 1) / hg;
+    const size_t smem = ((size_t)g.S * attn_pitch(4 * hg * DH) + (size_t)hg * 32 * 33) * sizeof(float);
+    if (smem <= (size_t)ATTN_S32_SMEM_BUDGET) {
+      attn_bwd_s32_kernel<DH><<<grid_for((long long)g.NB * groups, 1, 16 * g_dev.sm_count), 32 * hg, smem, c.stream>>>(
+          w.qkv, w.d_o, d.E, w.lse, d.E, d.H, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH),
+          w.dqkv, lo, d.P3);
+      return;
+    }
+  }
   const size_t per_head = (size_t)g.S * (5 * DH + 2) * sizeof(float);
   int hp = (int)(ATTN_BWD_SMEM_BUDGET / per_head);
   if (hp > d.H) hp = d.H;
@@ -393,8 +494,9 @@ static int block_forward(const Ctx& c, const Dims& d, BlockWs& w, long long R, c
   // K3: QKV = X W_in^T + b_in   (bias rides on the ones column)
   {
     GemmEpi e = epi_none();
-    e.out = w.qkv; e.ld_out = 3 * d.E; e.out_cols = 3 * d.E;
-    TRY(gemm_nt(c, w.x, R, d.Ep, w.win_f, 3 * d.E, d.Ep, d.Ep, e, "gemm in_proj"));
+    Sinks sk;
+    sk.f32 = w.qkv; sk.ld_f32 = 3 * d.E; sk.f32_cols = 3 * d.E;
+    TRY(gemm_nt(c, w.x, R, d.Ep, w.win_f, 3 * d.E, d.Ep, d.Ep, e, sk, "gemm in_proj"));
   }
   // K4: per-head softmax(q k^T) v
   if (d.DH == 16) launch_attn_fwd<16>(c, d, ag, w, R);
@@ -404,19 +506,22 @@ static int block_forward(const Ctx& c, const Dims& d, BlockWs& w, long long R, c
   // K5: Y = O W_out^T + b_out  (+ dropout site 1), fp32 and split planes
   {
     GemmEpi e = epi_none();
-    e.out = w.y; e.ld_out = d.E; e.out_cols = d.E;
-    e.hi = w.yp; e.lo = w.yp + R * d.Ep; e.ld_sp = d.Ep; e.sp_cols = d.Ep; e.ones_col = d.E;
+    Sinks sk;
+    sk.f32 = w.y; sk.ld_f32 = d.E; sk.f32_cols = d.E;
+    sk.sp = w.yp; sk.ld_sp = d.Ep; sk.sp_cols = d.Ep; sk.ones_col = d.E;
     if (drop.on) {
       e.use_dropout = 1; e.drop_scale = drop.scale; e.drop_thr = drop.thr; e.drop_site = 1;
       e.seed = drop.seed; e.drop_ld = d.E;
     }
-    TRY(gemm_nt(c, w.o, R, d.Ep, w.wout_f, d.E, d.Ep, d.Ep, e, "gemm out_proj"));
+    TRY(gemm_nt(c, w.o, R, d.Ep, w.wout_f, d.E, d.Ep, d.Ep, e, sk, "gemm out_proj"));
   }
   // K6: a = tanh(Y W_add^T + b_add), score = a . query  (fused epilogue)
   {
     GemmEpi e = epi_none();
-    e.qvec = prm->add_query; e.tanh_out = w.a; e.ld_tanh = d.Q; e.score = w.s;
-    TRY(gemm_nt(c, w.yp, R, d.Ep, w.wadd_f, d.Q, d.Ep, d.Ep, e, "gemm additive"));
+    e.qvec = prm->add_query; e.score = w.s;
+    Sinks sk;
+    sk.f32 = w.a; sk.ld_f32 = d.Q; sk.f32_cols = d.Q;
+    TRY(gemm_nt(c, w.yp, R, d.Ep, w.wadd_f, d.Q, d.Ep, d.Ep, e, sk, "gemm additive"));
   }
   pool_fwd_kernel<<<grid_for(G, 1, 1 << 20), 128, L * sizeof(float), c.stream>>>(w.s, w.y, d.E, L, G, w.w, out_vec);
   LAUNCH_CHECK("pool_fwd");
@@ -438,31 +543,28 @@ static int block_backward(const Ctx& c, const Dims& d, BlockWs& w, long long R, 
   {
     GemmEpi e = epi_none();
     e.add_w = w.w; e.add_vec = d_vec; e.ld_addvec = d.E; e.add_L = L;  // + w_r * dVec[g(r)]
-    e.hi = w.dyp; e.lo = w.dyp + R * d.Ep; e.ld_sp = d.Ep; e.sp_cols = d.Ep; e.ones_col = -1;
+    Sinks sk;
+    sk.sp = w.dyp; sk.ld_sp = d.Ep; sk.sp_cols = d.Ep; sk.ones_col = -1;
     if (drop1.on) {
       e.use_dropout = 1; e.drop_scale = drop1.scale; e.drop_thr = drop1.thr; e.drop_site = 1;
       e.seed = drop1.seed; e.drop_ld = d.E;
     }
-    TRY(gemm_nt(c, w.dap, R, d.Qp, w.wadd_t, d.E, d.Qp, d.Qp, e, "gemm additive dgrad"));
+    TRY(gemm_nt(c, w.dap, R, d.Qp, w.wadd_t, d.E, d.Qp, d.Qp, e, sk, "gemm additive dgrad"));
   }
   // dW_add, db_add
-  {
-    GemmEpi e = epi_none();
-    e.gw = g->add_weight; e.ld_gw = d.E; e.gw_cols = d.E; e.gb = nullptr;  // db: fp32 in pool_bwd
-    TRY(gemm_tn(c, w.dap, d.Q, d.Qp, w.yp, d.Ep, d.Ep, R, e, "gemm additive wgrad"));
-  }
+  // (db_add is summed in fp32 by pool_bwd)
+  TRY(gemm_tn(c, w.dap, d.Q, d.Qp, w.yp, d.Ep, d.Ep, R, g->add_weight, d.E, d.E, nullptr,
+              "gemm additive wgrad"));
   // dO = dY W_out
   {
     GemmEpi e = epi_none();
-    e.out = w.d_o; e.ld_out = d.E; e.out_cols = d.E;
-    TRY(gemm_nt(c, w.dyp, R, d.Ep, w.wout_t, d.E, d.Ep, d.Ep, e, "gemm out_proj dgrad"));
+    Sinks sk;
+    sk.f32 = w.d_o; sk.ld_f32 = d.E; sk.f32_cols = d.E;
+    TRY(gemm_nt(c, w.dyp, R, d.Ep, w.wout_t, d.E, d.Ep, d.Ep, e, sk, "gemm out_proj dgrad"));
   }
   // dW_out, db_out
-  {
-    GemmEpi e = epi_none();
-    e.gw = g->out_proj_weight; e.ld_gw = d.E; e.gw_cols = d.E; e.gb = g->out_proj_bias;
-    TRY(gemm_tn(c, w.dyp, d.E, d.Ep, w.o, d.Ep, d.Ep, R, e, "gemm out_proj wgrad"));
-  }
+  TRY(gemm_tn(c, w.dyp, d.E, d.Ep, w.o, d.Ep, d.Ep, R, g->out_proj_weight, d.E, d.E, g->out_proj_bias,
+              "gemm out_proj wgrad"));
   if (d.DH == 16) launch_attn_bwd<16>(c, d, ag, w, R);
   else if (d.DH == 20) launch_attn_bwd<20>(c, d, ag, w, R);
   else launch_attn_bwd<32>(c, d, ag, w, R);
@@ -470,19 +572,17 @@ static int block_backward(const Ctx& c, const Dims& d, BlockWs& w, long long R, 
   // dX = dropout0'( dQKV W_in )
   {
     GemmEpi e = epi_none();
-    e.out = w.dx; e.ld_out = d.E; e.out_cols = d.E;
+    Sinks sk;
+    sk.f32 = w.dx; sk.ld_f32 = d.E; sk.f32_cols = d.E;
     if (drop0.on) {
       e.use_dropout = 1; e.drop_scale = drop0.scale; e.drop_thr = drop0.thr; e.drop_site = 0;
       e.seed = drop0.seed; e.drop_ld = d.E;
     }
-    TRY(gemm_nt(c, w.dqkv, R, d.P3, w.win_t, d.E, d.P3, d.P3, e, "gemm in_proj dgrad"));
+    TRY(gemm_nt(c, w.dqkv, R, d.P3, w.win_t, d.E, d.P3, d.P3, e, sk, "gemm in_proj dgrad"));
   }
   // dW_in, db_in
-  {
-    GemmEpi e = epi_none();
-    e.gw = g->in_proj_weight; e.ld_gw = d.E; e.gw_cols = d.E; e.gb = g->in_proj_bias;
-    TRY(gemm_tn(c, w.dqkv, 3 * d.E, d.P3, w.x, d.Ep, d.Ep, R, e, "gemm in_proj wgrad"));
-  }
+  TRY(gemm_tn(c, w.dqkv, 3 * d.E, d.P3, w.x, d.Ep, d.Ep, R, g->in_proj_weight, d.E, d.E, g->in_proj_bias,
+              "gemm in_proj wgrad"));
   return NRL_OK;
 }
 
@@ -705,8 +805,10 @@ int nrl_additive_fwd(const float* x, long long G, int L, int D, int Q, const flo
       x, nullptr, (int)R, 1, D, Dp, nullptr, xp, tp ? xp + R * Dp : nullptr);
   LAUNCH_CHECK("split_rows");
   GemmEpi e = epi_none();
-  e.qvec = query; e.tanh_out = a; e.ld_tanh = Q; e.score = s;
-  TRY(gemm_nt(c, xp, R, Dp, wf, Q, Dp, Dp, e, "gemm additive"));
+  e.qvec = query; e.score = s;
+  Sinks sk;
+  sk.f32 = a; sk.ld_f32 = Q; sk.f32_cols = Q;
+  TRY(gemm_nt(c, xp, R, Dp, wf, Q, Dp, Dp, e, sk, "gemm additive"));
   pool_fwd_kernel<<<grid_for(G, 1, 1 << 20), 128, L * sizeof(float), c.stream>>>(s, x, D, L, G, wgt, out);
   LAUNCH_CHECK("pool_fwd");
   return NRL_OK;
@@ -1005,6 +1107,7 @@ size_t nrl_gemm_test_ws_bytes(int M, int N, int K) {
   const long long bign = (long long)(N > K ? N : K) + 16;
   b.take<bf16>(2ull * big * bigp);
   b.take<bf16>(2ull * bign * (round_up(N > K ? N : K, 16) + 16));
+  b.take<bf16>(2ull * M * round_up(N + 1, 16));  // plane sink of nrl_gemm_test_planes
   return b.off + 1024;
 }
 
@@ -1029,18 +1132,45 @@ int nrl_gemm_test(const float* A, const float* B, float* D, int M, int N, int K,
     // the split kernel writes 1.0 at column K when Kp > K; the tensor-map extent is K, so TMA
     // zero-fills from column K on and the ones column never reaches the MMA.
     GemmEpi e = epi_none();
-    e.out = D; e.ld_out = N; e.out_cols = N;
-    return gemm_nt(c, ap, M, Kp, bp, N, Kp, K, e, "gemm_test nt");
+    Sinks sk;
+    sk.f32 = D; sk.ld_f32 = N; sk.f32_cols = N;
+    return gemm_nt(c, ap, M, Kp, bp, N, Kp, K, e, sk, "gemm_test nt");
   } else {
     const int Mp = round_up(M, 16), Np = round_up(N, 16);
     dense_scatter_kernel<<<grid_for(K, 1, 1 << 20), 128, 0, c.stream>>>(A, nullptr, K, 1, M, Mp, nullptr, ap, tp ? ap + (long long)K * Mp : nullptr);
     LAUNCH_CHECK("split_rows(A)");
     dense_scatter_kernel<<<grid_for(K, 1, 1 << 20), 128, 0, c.stream>>>(B, nullptr, K, 1, N, Np, nullptr, bp, tp ? bp + (long long)K * Np : nullptr);
     LAUNCH_CHECK("split_rows(B)");
-    GemmEpi e = epi_none();
-    e.gw = D; e.ld_gw = N; e.gw_cols = N; e.gb = nullptr;
-    return gemm_tn(c, ap, M, Mp, bp, N, Np, K, e, "gemm_test tn");
+    return gemm_tn(c, ap, M, Mp, bp, N, Np, K, D, N, N, nullptr, "gemm_test tn");
   }
+}
+
+int nrl_gemm_test_planes(const float* A, const float* B, float* out, int M, int N, int K, int precision,
+                         void* ws, size_t ws_bytes, void* stream) {
+  if (!A || !B || !out || M <= 0 || N <= 0 || K <= 0) return fail(NRL_ERR_INVALID_ARG, "nrl_gemm_test_planes: bad argument");
+  TRY(device_init());
+  TRY(check_common(ws, ws_bytes, nrl_gemm_test_ws_bytes(M, N, K)));
+  Ctx c{static_cast<cudaStream_t>(stream), precision};
+  const int tp = c.two_planes() ? 1 : 0;
+  Bump b(ws);
+  const long long big = (long long)(M > K ? M : K) + 16, bigp = round_up((M > K ? M : K), 16) + 16;
+  const long long bign = (long long)(N > K ? N : K) + 16;
+  bf16* ap = b.take<bf16>(2ull * big * bigp);
+  bf16* bp = b.take<bf16>(2ull * bign * (round_up(N > K ? N : K, 16) + 16));
+  const int Np = round_up(N + 1, 16), Kp = round_up(K, 16);
+  bf16* dp = b.take<bf16>(2ull * M * Np);
+  dense_scatter_kernel<<<grid_for(M, 1, 1 << 20), 128, 0, c.stream>>>(A, nullptr, M, 1, K, Kp, nullptr, ap, tp ? ap + (long long)M * Kp : nullptr);
+  LAUNCH_CHECK("split_rows(A)");
+  dense_scatter_kernel<<<grid_for(N, 1, 1 << 20), 128, 0, c.stream>>>(B, nullptr, N, 1, K, Kp, nullptr, bp, tp ? bp + (long long)N * Kp : nullptr);
+  LAUNCH_CHECK("split_rows(B)");
+  GemmEpi e = epi_none();
+  Sinks sk;
+  sk.sp = dp; sk.ld_sp = Np; sk.sp_cols = Np; sk.ones_col = N;
+  TRY(gemm_nt(c, ap, M, Kp, bp, N, Kp, K, e, sk, "gemm_test planes"));
+  planes_to_f32_kernel<<<grid_for((long long)M * Np, 256, 1 << 16), 256, 0, c.stream>>>(
+      dp, tp ? dp + (long long)M * Np : nullptr, (long long)M * Np, out);
+  LAUNCH_CHECK("planes_to_f32");
+  return NRL_OK;
 }
 
 }  // extern "C"

@@ -670,6 +670,260 @@ attn_bwd_tile_kernel(const float* __restrict__ qkv, const float* __restrict__ d_
 }
 
 // ------------------------------------------------------------------------------------
+// Register-resident attention for short sequences (S <= 32: the 30-token titles).  One CTA =
+// one batch item x one group of `hg` heads, one warp per head, lane = query (phase A) / key
+// (phase B).  The whole score row of a query lives in registers (fully unrolled, 32
+// independent FMA chains), K / V rows are broadcast reads from the smem tile, whose row pitch
+// is an odd number of 16-byte words so that row-strided float4 accesses are conflict free.
+// ------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ int attn_pitch(int floats) {  // floats % 4 == 0
+  while (((floats >> 2) & 1) == 0) floats += 4;
+  return floats;
+}
+
+template <int DH>
+__global__ void __launch_bounds__(160, 4)
+attn_fwd_s32_kernel(const float* __restrict__ qkv, int E, int heads, int S, long long seq_stride,
+                    int NB, long long batch_stride, float scale, __nv_bfloat16* __restrict__ o_hi,
+                    __nv_bfloat16* __restrict__ o_lo, int ep, float* __restrict__ lse) {
+  extern __shared__ __align__(16) float tile[];  // [S][P]: q | k | v of the head group
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, hg = blockDim.x >> 5;
+  const int groups = (heads + hg - 1) / hg;
+  const int ld = 3 * E;
+  for (long long work = blockIdx.x; work < (long long)NB * groups; work += gridDim.x) {
+    const int b = (int)(work / groups), grp = (int)(work % groups);
+    const int h0 = grp * hg, nh = min(hg, heads - h0);
+    const int W = nh * DH, P = attn_pitch(3 * W), segv = W / 4;
+    __syncthreads();
+    for (int i = threadIdx.x; i < S * 3 * segv; i += blockDim.x) {
+      const int srow = i / (3 * segv), rem = i - srow * 3 * segv, seg = rem / segv, c4 = rem - seg * segv;
+      const long long grow = (long long)srow * seq_stride + (long long)b * batch_stride;
+      reinterpret_cast<float4*>(tile + srow * P + seg * W)[c4] =
+          __ldg(reinterpret_cast<const float4*>(qkv + grow * ld + seg * E + h0 * DH) + c4);
+    }
+    __syncthreads();
+    if (warp < nh) {
+      const bool ok = lane < S;
+      float* qrow = tile + (ok ? lane : 0) * P + warp * DH;
+      float q[DH];
+#pragma unroll
+      for (int d = 0; d < DH; d += 4) {
+        const float4 t4 = *reinterpret_cast<const float4*>(qrow + d);
+        q[d] = t4.x * scale; q[d + 1] = t4.y * scale; q[d + 2] = t4.z * scale; q[d + 3] = t4.w * scale;
+      }
+      float sc[32];
+      float m = -INFINITY;
+#pragma unroll
+      for (int u = 0; u < 32; ++u) {
+        sc[u] = -INFINITY;
+        if (u < S) {
+          const float* kr = tile + u * P + W + warp * DH;
+          float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+          for (int d = 0; d < DH; d += 4) {
+            const float4 k4 = *reinterpret_cast<const float4*>(kr + d);
+            a0 += q[d] * k4.x; a1 += q[d + 1] * k4.y; a0 += q[d + 2] * k4.z; a1 += q[d + 3] * k4.w;
+          }
+          sc[u] = a0 + a1;
+          m = fmaxf(m, sc[u]);
+        }
+      }
+      float l = 0.f;
+#pragma unroll
+      for (int u = 0; u < 32; ++u) {
+        const float pu = (u < S) ? expf(sc[u] - m) : 0.f;
+        sc[u] = pu;
+        l += pu;
+      }
+      float o[DH];
+#pragma unroll
+      for (int d = 0; d < DH; ++d) o[d] = 0.f;
+#pragma unroll
+      for (int u = 0; u < 32; ++u) {
+        if (u < S) {
+          const float* vr = tile + u * P + 2 * W + warp * DH;
+#pragma unroll
+          for (int d = 0; d < DH; d += 4) {
+            const float4 v4 = *reinterpret_cast<const float4*>(vr + d);
+            o[d] += sc[u] * v4.x; o[d + 1] += sc[u] * v4.y; o[d + 2] += sc[u] * v4.z; o[d + 3] += sc[u] * v4.w;
+          }
+        }
+      }
+      if (ok) {  // the q slice of (row, head) is read by this lane only: it becomes the output row
+        const float inv = 1.f / l;
+#pragma unroll
+        for (int d = 0; d < DH; d += 4)
+          *reinterpret_cast<float4*>(qrow + d) = make_float4(o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv);
+        const long long grow = (long long)lane * seq_stride + (long long)b * batch_stride;
+        lse[grow * heads + h0 + warp] = m + logf(l);
+      }
+    }
+    __syncthreads();
+    // write-back of the [S, W] output tile as split planes, 4 columns (8 bytes) per thread
+    for (int i = threadIdx.x; i < S * segv; i += blockDim.x) {
+      const int srow = i / segv, c = (i - srow * segv) * 4;
+      const long long grow = (long long)srow * seq_stride + (long long)b * batch_stride;
+      const float4 val = *reinterpret_cast<const float4*>(tile + srow * P + c);
+      __nv_bfloat16 h[4], l4[4];
+      split_bf16(val.x, h[0], l4[0]); split_bf16(val.y, h[1], l4[1]);
+      split_bf16(val.z, h[2], l4[2]); split_bf16(val.w, h[3], l4[3]);
+      const long long off = grow * ep + h0 * DH + c;
+      *reinterpret_cast<uint2*>(o_hi + off) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+      if (o_lo) *reinterpret_cast<uint2*>(o_lo + off) = make_uint2(pack_bf16x2(l4[0], l4[1]), pack_bf16x2(l4[2], l4[3]));
+    }
+    if (grp == 0) {
+      for (int i = threadIdx.x; i < S * (ep - E); i += blockDim.x) {
+        const int srow = i / (ep - E), c = E + i % (ep - E);
+        const long long grow = (long long)srow * seq_stride + (long long)b * batch_stride;
+        o_hi[grow * ep + c] = __float2bfloat16_rn(c == E ? 1.f : 0.f);
+        if (o_lo) o_lo[grow * ep + c] = __float2bfloat16_rn(0.f);
+      }
+    }
+  }
+}
+
+// Backward, S <= 32.  Phase A (lane = query t): p[u], dS[u] for all keys in registers, dq.
+// dS and P are then transposed through a per-warp [32][33] smem buffer so that phase B
+// (lane = key u) gets dK = dS^T (scale q) and dV = P^T dO without recomputing any product.
+// smem row: q | k | v | dO of the head group; dq / dk / dv replace q / k / v before write-back.
+template <int DH>
+__global__ void __launch_bounds__(160, 3)
+attn_bwd_s32_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o, long long ld_do,
+                    const float* __restrict__ lse, int E, int heads, int S, long long seq_stride,
+                    int NB, long long batch_stride, float scale, __nv_bfloat16* __restrict__ g_hi,
+                    __nv_bfloat16* __restrict__ g_lo, int p3) {
+  extern __shared__ __align__(16) float tile[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, hg = blockDim.x >> 5;
+  const int groups = (heads + hg - 1) / hg;
+  const int ld = 3 * E;
+  const int Pmax = attn_pitch(4 * hg * DH);
+  float* tbuf = tile + S * Pmax + warp * (32 * 33);
+  for (long long work = blockIdx.x; work < (long long)NB * groups; work += gridDim.x) {
+    const int b = (int)(work / groups), grp = (int)(work % groups);
+    const int h0 = grp * hg, nh = min(hg, heads - h0);
+    const int W = nh * DH, P = attn_pitch(4 * W), segv = W / 4;
+    __syncthreads();
+    for (int i = threadIdx.x; i < S * 4 * segv; i += blockDim.x) {
+      const int srow = i / (4 * segv), rem = i - srow * 4 * segv, seg = rem / segv, c4 = rem - seg * segv;
+      const long long grow = (long long)srow * seq_stride + (long long)b * batch_stride;
+      const float4* src = seg < 3 ? reinterpret_cast<const float4*>(qkv + grow * ld + seg * E + h0 * DH)
+                                  : reinterpret_cast<const float4*>(d_o + grow * ld_do + h0 * DH);
+      reinterpret_cast<float4*>(tile + srow * P + seg * W)[c4] = __ldg(src + c4);
+    }
+    __syncthreads();
+    if (warp < nh) {
+      const bool ok = lane < S;
+      float* base = tile + (ok ? lane : 0) * P + warp * DH;
+      const long long grow_l = (long long)(ok ? lane : 0) * seq_stride + (long long)b * batch_stride;
+      const float my_lse = lse[grow_l * heads + h0 + warp];
+      float pr[32], ds[32], dq[DH];
+      {
+        float q[DH], go[DH];
+#pragma unroll
+        for (int d = 0; d < DH; d += 4) {
+          const float4 t4 = *reinterpret_cast<const float4*>(base + d);
+          const float4 g4 = *reinterpret_cast<const float4*>(base + 3 * W + d);
+          q[d] = t4.x * scale; q[d + 1] = t4.y * scale; q[d + 2] = t4.z * scale; q[d + 3] = t4.w * scale;
+          go[d] = g4.x; go[d + 1] = g4.y; go[d + 2] = g4.z; go[d + 3] = g4.w;
+          dq[d] = dq[d + 1] = dq[d + 2] = dq[d + 3] = 0.f;
+        }
+        float dd = 0.f;
+#pragma unroll
+        for (int u = 0; u < 32; ++u) {
+          pr[u] = 0.f; ds[u] = 0.f;
+          if (u < S) {
+            const float* kr = tile + u * P + W + warp * DH;
+            float s0 = 0.f, s1 = 0.f, p0 = 0.f, p1 = 0.f;
+#pragma unroll
+            for (int d = 0; d < DH; d += 4) {
+              const float4 k4 = *reinterpret_cast<const float4*>(kr + d);
+              const float4 v4 = *reinterpret_cast<const float4*>(kr + W + d);
+              s0 += q[d] * k4.x; s1 += q[d + 1] * k4.y; s0 += q[d + 2] * k4.z; s1 += q[d + 3] * k4.w;
+              p0 += go[d] * v4.x; p1 += go[d + 1] * v4.y; p0 += go[d + 2] * v4.z; p1 += go[d + 3] * v4.w;
+            }
+            const float pu = ok ? expf(s0 + s1 - my_lse) : 0.f;
+            pr[u] = pu;
+            ds[u] = p0 + p1;
+            dd += pu * ds[u];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 32; ++u) {
+          ds[u] = pr[u] * (ds[u] - dd);
+          if (u < S) {
+            const float* kr = tile + u * P + W + warp * DH;
+#pragma unroll
+            for (int d = 0; d < DH; d += 4) {
+              const float4 k4 = *reinterpret_cast<const float4*>(kr + d);
+              dq[d] += ds[u] * k4.x; dq[d + 1] += ds[u] * k4.y; dq[d + 2] += ds[u] * k4.z; dq[d + 3] += ds[u] * k4.w;
+            }
+          }
+        }
+      }
+      // ---- transpose dS, then P: lane t holds row t, wants column `lane` ----
+      float dk[DH], dv[DH];
+#pragma unroll
+      for (int d = 0; d < DH; ++d) { dk[d] = 0.f; dv[d] = 0.f; }
+#pragma unroll
+      for (int u = 0; u < 32; ++u) tbuf[lane * 33 + u] = ds[u];
+      __syncwarp();
+#pragma unroll
+      for (int t = 0; t < 32; ++t) ds[t] = tbuf[t * 33 + lane];
+      __syncwarp();
+#pragma unroll
+      for (int u = 0; u < 32; ++u) tbuf[lane * 33 + u] = pr[u];
+      __syncwarp();
+#pragma unroll
+      for (int t = 0; t < 32; ++t) pr[t] = tbuf[t * 33 + lane];
+      // ---- phase B: lane = key.  dk = scale * sum_t dS[t][u] q_t ; dv = sum_t P[t][u] dO_t ----
+#pragma unroll
+      for (int t = 0; t < 32; ++t) {
+        if (t < S) {
+          const float* qr = tile + t * P + warp * DH;
+#pragma unroll
+          for (int d = 0; d < DH; d += 4) {
+            const float4 q4 = *reinterpret_cast<const float4*>(qr + d);
+            const float4 g4 = *reinterpret_cast<const float4*>(qr + 3 * W + d);
+            dk[d] += ds[t] * q4.x; dk[d + 1] += ds[t] * q4.y; dk[d + 2] += ds[t] * q4.z; dk[d + 3] += ds[t] * q4.w;
+            dv[d] += pr[t] * g4.x; dv[d + 1] += pr[t] * g4.y; dv[d + 2] += pr[t] * g4.z; dv[d + 3] += pr[t] * g4.w;
+          }
+        }
+      }
+      __syncwarp();  // every lane is done reading this head's q / k / v / dO slices
+      if (ok) {
+#pragma unroll
+        for (int d = 0; d < DH; d += 4) {
+          *reinterpret_cast<float4*>(base + d) = make_float4(dq[d] * scale, dq[d + 1] * scale, dq[d + 2] * scale, dq[d + 3] * scale);
+          *reinterpret_cast<float4*>(base + W + d) = make_float4(dk[d] * scale, dk[d + 1] * scale, dk[d + 2] * scale, dk[d + 3] * scale);
+          *reinterpret_cast<float4*>(base + 2 * W + d) = make_float4(dv[d], dv[d + 1], dv[d + 2], dv[d + 3]);
+        }
+      }
+    }
+    __syncthreads();
+    // ---- write-back: dQ | dK | dV row segments -> split planes, 4 columns per thread ----
+    for (int i = threadIdx.x; i < S * 3 * segv; i += blockDim.x) {
+      const int srow = i / (3 * segv), rem = i - srow * 3 * segv, seg = rem / segv, c = (rem - seg * segv) * 4;
+      const long long grow = (long long)srow * seq_stride + (long long)b * batch_stride;
+      const float4 val = *reinterpret_cast<const float4*>(tile + srow * P + seg * W + c);
+      __nv_bfloat16 h[4], l4[4];
+      split_bf16(val.x, h[0], l4[0]); split_bf16(val.y, h[1], l4[1]);
+      split_bf16(val.z, h[2], l4[2]); split_bf16(val.w, h[3], l4[3]);
+      const long long off = grow * p3 + seg * E + h0 * DH + c;
+      *reinterpret_cast<uint2*>(g_hi + off) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+      if (g_lo) *reinterpret_cast<uint2*>(g_lo + off) = make_uint2(pack_bf16x2(l4[0], l4[1]), pack_bf16x2(l4[2], l4[3]));
+    }
+    if (grp == 0 && p3 > 3 * E) {
+      for (int i = threadIdx.x; i < S * (p3 - 3 * E); i += blockDim.x) {
+        const int srow = i / (p3 - 3 * E), c = 3 * E + i % (p3 - 3 * E);
+        const long long grow = (long long)srow * seq_stride + (long long)b * batch_stride;
+        g_hi[grow * p3 + c] = __float2bfloat16_rn(0.f);
+        if (g_lo) g_lo[grow * p3 + c] = __float2bfloat16_rn(0.f);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // a5: additive pooling.  Group g owns rows g*L .. g*L+L-1.  score[r] = tanh(xW+b).q comes
 // from the GEMM epilogue; here: w = softmax_L(score), out[g] = sum_t w_t * Y[row_t].
 // ------------------------------------------------------------------------------------
@@ -985,6 +1239,14 @@ __global__ void dropout_mask_kernel(unsigned char* __restrict__ keep, long long 
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
     keep[i] = drop_keep(seed, site, (unsigned long long)i, thr) ? 1 : 0;
+}
+
+// out[i] = hi[i] + lo[i]  (test helper: read back a split-plane GEMM sink)
+__global__ void planes_to_f32_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                     long long n, float* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    out[i] = __bfloat162float(hi[i]) + (lo ? __bfloat162float(lo[i]) : 0.f);
 }
 
 // acc[i] += x[i]

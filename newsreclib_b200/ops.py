@@ -84,6 +84,20 @@ def gemm_test(A: torch.Tensor, B: torch.Tensor, mn_major: bool, precision: int =
     return D
 
 
+def gemm_test_planes(A: torch.Tensor, B: torch.Tensor, precision: int = PREC_BF16X3) -> torch.Tensor:
+    """NT GEMM through the split-plane sink; returns hi + lo as fp32 ``[M, round_up(N + 1, 16)]``."""
+    lib = _lib.load()
+    _chk(A, torch.float32, "A"); _chk(B, torch.float32, "B")
+    M, K = A.shape
+    N = B.shape[0]
+    Np = (N + 1 + 15) // 16 * 16
+    out = torch.empty(M, Np, dtype=torch.float32, device=A.device)
+    ws = workspace(lib.nrl_gemm_test_ws_bytes(M, N, K), A.device)
+    _lib.check(lib.nrl_gemm_test_planes(_p(A), _p(B), _p(out), M, N, K, precision, _p(ws), ws.numel(),
+                                        _stream()), "nrl_gemm_test_planes")
+    return out
+
+
 def dropout_mask(n: int, seed: int, site: int, p: float, device) -> torch.Tensor:
     lib = _lib.load()
     keep = torch.empty(n, dtype=torch.uint8, device=device)

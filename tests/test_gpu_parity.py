@@ -33,6 +33,22 @@ def test_gemm_nt_tcgen05(shape):
     assert e3 < 3e-5 and e1 < 2e-2
 
 
+@pytest.mark.parametrize("shape", [(128, 16, 16), (300, 208, 304), (1000, 300, 304), (4000, 900, 304)])
+def test_gemm_plane_sink(shape):
+    """The bf16 hi/lo plane sink (TMA store of a [2, 32, 32] box): values, ones column, zero pad."""
+    from newsreclib_b200 import ops
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M + N)
+    A = torch.randn(M, K, generator=g).cuda()
+    B = torch.randn(N, K, generator=g).cuda()
+    ref = (A.double() @ B.double().t())
+    out = ops.gemm_test_planes(A, B).cpu()
+    assert rel_err(out[:, :N], ref) < 4e-5          # 3-pass product, then rounded to 16 mantissa bits
+    assert torch.all(out[:, N] == 1.0) and torch.all(out[:, N + 1:] == 0.0)
+    out1 = ops.gemm_test_planes(A, B, ops.PREC_BF16).cpu()
+    assert rel_err(out1[:, :N], ref) < 2e-2 and torch.all(out1[:, N] == 1.0)
+
+
 @pytest.mark.parametrize("shape", [(128, 64, 64), (180, 64, 333), (200, 304, 777), (900, 304, 5000),
                                    (300, 304, 20000)])
 def test_gemm_tn_tcgen05(shape):
