@@ -273,7 +273,7 @@ static int launch_gemm(const Ctx& c, GemmParams& p, const CUtensorMap& ta, const
     p.epi.ones_col = sk.ones_col;
   }
   p.epi_buf_bytes = (sk.f32 && sk.sp) ? 8192 : 4096;
-  const int stage_bytes = GEMM_A_BYTES + (p.mn_major ? (p.BN + 63) / 64 * 8192 : p.BN * 128);
+  const int stage_bytes = p.planes * (GEMM_A_BYTES + (p.mn_major ? (p.BN + 63) / 64 * 8192 : p.BN * 128));
   int stages = (GEMM_SMEM_LIMIT - 1024 - GEMM_BAR_BYTES - 8 * p.epi_buf_bytes) / stage_bytes;
   if (stages > GEMM_MAX_STAGES) stages = GEMM_MAX_STAGES;
   if (stages < 2) return fail(NRL_ERR_UNSUPPORTED, "GEMM tile does not fit shared memory");
@@ -290,14 +290,18 @@ static int launch_gemm(const Ctx& c, GemmParams& p, const CUtensorMap& ta, const
   return NRL_OK;
 }
 
-static void set_segs(const Ctx& c, GemmParams& p) {
-  if (c.two_planes()) {
-    p.num_segs = 3;
-    p.seg_a[0] = 1; p.seg_b[0] = 0;
-    p.seg_a[1] = 0; p.seg_b[1] = 1;
-    p.seg_a[2] = 0; p.seg_b[2] = 0;
-  } else {
-    p.num_segs = 1;
+static void set_segs(const Ctx& c, GemmParams& p) { p.planes = c.two_planes() ? 2 : 1; }
+
+// balanced n-tiles: as few tiles as possible (<= 256 columns each), all the same width, and
+// narrow enough that at least two pipeline stages fit beside the epilogue staging buffers
+static int balanced_bn(int n_extent, int planes, bool both_sinks, int mn_major) {
+  const int avail = GEMM_SMEM_LIMIT - 1024 - GEMM_BAR_BYTES - 8 * (both_sinks ? 8192 : 4096);
+  for (int nt = (n_extent + 255) / 256;; ++nt) {
+    // multiple of 32: the epilogue stores 32-column boxes, which must not straddle two n-tiles
+    // (the overhang of the LAST tile lies outside the tensor and is clipped by TMA)
+    const int bn = round_up((n_extent + nt - 1) / nt, 32);
+    const int stage = planes * (GEMM_A_BYTES + (mn_major ? (bn + 63) / 64 * 8192 : bn * 128));
+    if (avail / stage >= 2 || bn <= 32) return bn;
   }
 }
 
@@ -308,10 +312,10 @@ static int gemm_nt(const Ctx& c, const bf16* A, long long M, int a_pitch, const 
   memset(&p, 0, sizeof(p));
   p.M = (int)M; p.N = N; p.K = K;
   p.n_extent = (sk.sp && sk.sp_cols > N) ? sk.sp_cols : N;
-  p.BN = p.n_extent >= 256 ? 256 : round_up(p.n_extent, 16);
-  if (epi.score && p.BN < N) return fail(NRL_ERR_UNSUPPORTED, "score fusion needs N <= 256");
   p.mn_major = 0;
   set_segs(c, p);
+  p.BN = balanced_bn(p.n_extent, p.planes, sk.f32 && sk.sp, 0);
+  if (epi.score && p.BN < N) return fail(NRL_ERR_UNSUPPORTED, "score fusion needs a single n-tile (N <= 256)");
   p.k_splits = 1;
   p.epi = epi;
   CUtensorMap ta, tb;
@@ -330,12 +334,9 @@ static int gemm_tn(const Ctx& c, const bf16* A, int M, int a_pitch, const bf16* 
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = (int)R;
   p.n_extent = N;
-  {
-    const int nt = (N + 255) / 256;
-    p.BN = round_up((N + nt - 1) / nt, 16);
-  }
   p.mn_major = 1;
   set_segs(c, p);
+  p.BN = balanced_bn(N, p.planes, false, 1);
   const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM, n_tiles = (N + p.BN - 1) / p.BN;
   const int kb_total = (int)((R + GEMM_BK - 1) / GEMM_BK);
   int ks = g_dev.sm_count / m_tiles;  // every n-block's tiles fill the machine once

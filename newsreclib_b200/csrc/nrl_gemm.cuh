@@ -2,9 +2,13 @@
 //
 //   D[m, n] = sum over segments s, sum_k  A_{pa[s]}[m, k] * B_{pb[s]}[n, k]          (fp32 in TMEM)
 //
-// A and B are "split-plane" bf16 matrices (plane 0 = hi, plane 1 = lo, see nrl_ptx.cuh).  One
-// segment (hi*hi) is a plain bf16 GEMM; three segments (lo*hi, hi*lo, hi*hi) reproduce an fp32
-// GEMM to ~2e-5 relative, which is what the 1e-4 logit-parity bar of the reference needs.
+// A and B are "split-plane" bf16 matrices (plane 0 = hi, plane 1 = lo, see nrl_ptx.cuh).  With
+// one plane this is a plain bf16 GEMM; with two planes every k-step issues three MMAs
+// (lo*hi, hi*lo, hi*hi) which reproduce an fp32 GEMM to ~2e-5 relative, which is what the 1e-4
+// logit-parity bar of the reference needs.  A pipeline stage holds ALL planes of one k-block
+// (A_hi, A_lo, B_hi, B_lo), each loaded once: on B200 this kernel is bound by the L2 -> SM fill
+// bandwidth (~6.3 KB/clk chip-wide), so three MMAs per four tile loads is 1.5x the intensity of
+// re-streaming the operands once per pass.
 //
 // Two operand layouts:
 //   mn_major = 0  ("NT"):  A[M, K] and B[N, K] row-major, K contiguous (forward / dgrad GEMMs).
@@ -59,12 +63,10 @@ struct GemmEpi {
 
 struct GemmParams {
   int M, N, K;  // K (reduction extent) is a multiple of 16
-  int BN;       // n-tile width (multiple of 16)
+  int BN;       // n-tile width (multiple of 32: epilogue boxes never straddle n-tiles)
   int n_extent; // columns the epilogue must produce (max over sinks, >= N)
   int mn_major;
-  int num_segs;
-  int seg_a[3];
-  int seg_b[3];
+  int planes;   // 1 = bf16 (hi only), 2 = hi + lo (three MMAs per k-step)
   int k_splits;
   int stages;
   int epi_buf_bytes;   // staging bytes per epilogue warp per buffer (4096 or 8192)
@@ -126,7 +128,7 @@ nrl_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_boxes = (uint32_t)(p.BN + 63) / 64u;  // mn_major: 64-column boxes of 8 KB
   const uint32_t b_bytes = p.mn_major ? b_boxes * 8192u : (uint32_t)p.BN * 128u;
-  const uint32_t stage_bytes = GEMM_A_BYTES + b_bytes;
+  const uint32_t stage_bytes = (uint32_t)p.planes * (GEMM_A_BYTES + b_bytes);
   const uint32_t epi_base = smem_base + (uint32_t)p.stages * stage_bytes;
   const uint32_t bar_base = epi_base + 8u * (uint32_t)p.epi_buf_bytes;
   // barrier layout (8 B each): full[S], empty[S], tmem_full[2], tmem_empty[2], then tmem ptr
@@ -176,30 +178,30 @@ nrl_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = GEMM_A_BYTES + b_bytes;
+      const uint32_t tx_bytes = stage_bytes;
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
         for (int j = 0; j < tpu; ++j) {
           const GemmTile t = gemm_tile(p, unit * tpu + j, m_tiles, n_tiles, kb_total);
           if (t.kb0 >= t.kb1) continue;
-          for (int s = 0; s < p.num_segs; ++s) {
-            for (int kb = t.kb0; kb < t.kb1; ++kb) {
-              mbar_wait(empty_bar(stage), phase ^ 1u);
-              mbar_expect_tx(full_bar(stage), tx_bytes);
-              const uint32_t a_dst = smem_base + stage * stage_bytes;
-              const uint32_t b_dst = a_dst + GEMM_A_BYTES;
+          for (int kb = t.kb0; kb < t.kb1; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_expect_tx(full_bar(stage), tx_bytes);
+            const uint32_t a_dst = smem_base + stage * stage_bytes;
+            const uint32_t b_dst = a_dst + (uint32_t)p.planes * GEMM_A_BYTES;
+            for (int pl = 0; pl < p.planes; ++pl) {
               if (!p.mn_major) {
-                tma_load_3d(a_dst, &tmA, full_bar(stage), kb * GEMM_BK, t.m0, p.seg_a[s]);
-                tma_load_3d(b_dst, &tmB, full_bar(stage), kb * GEMM_BK, t.n0, p.seg_b[s]);
+                tma_load_3d(a_dst + pl * GEMM_A_BYTES, &tmA, full_bar(stage), kb * GEMM_BK, t.m0, pl);
+                tma_load_3d(b_dst + pl * b_bytes, &tmB, full_bar(stage), kb * GEMM_BK, t.n0, pl);
               } else {
                 for (int q = 0; q < 2; ++q)
-                  tma_load_3d(a_dst + q * 8192, &tmA, full_bar(stage), t.m0 + q * 64, kb * GEMM_BK,
-                              p.seg_a[s]);
+                  tma_load_3d(a_dst + pl * GEMM_A_BYTES + q * 8192, &tmA, full_bar(stage), t.m0 + q * 64,
+                              kb * GEMM_BK, pl);
                 for (int q = 0; q < (int)b_boxes; ++q)
-                  tma_load_3d(b_dst + q * 8192, &tmB, full_bar(stage), t.n0 + q * 64, kb * GEMM_BK,
-                              p.seg_b[s]);
+                  tma_load_3d(b_dst + pl * b_bytes + q * 8192, &tmB, full_bar(stage), t.n0 + q * 64,
+                              kb * GEMM_BK, pl);
               }
-              if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
         }
       }
@@ -220,28 +222,30 @@ nrl_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
           uint32_t accumulate = 0;
-          for (int s = 0; s < p.num_segs; ++s) {
-            for (int kb = t.kb0; kb < t.kb1; ++kb) {
-              mbar_wait(full_bar(stage), phase);
-              tc_fence_after();
-              const uint32_t a_src = smem_base + stage * stage_bytes;
-              const uint32_t b_src = a_src + GEMM_A_BYTES;
-              const int nks = min(GEMM_BK / 16, (p.K - kb * GEMM_BK + 15) / 16);
-              for (int k = 0; k < nks; ++k) {
-                uint64_t ad, bd;
-                if (!p.mn_major) {
-                  ad = umma_desc_sw128(a_src + k * 32, 16, 1024);
-                  bd = umma_desc_sw128(b_src + k * 32, 16, 1024);
-                } else {
-                  ad = umma_desc_sw128(a_src + k * 2048, 8192, 1024);
-                  bd = umma_desc_sw128(b_src + k * 2048, 8192, 1024);
-                }
-                umma_bf16(d_tmem, ad, bd, idesc, accumulate);
-                accumulate = 1;
+          for (int kb = t.kb0; kb < t.kb1; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t a_src = smem_base + stage * stage_bytes;
+            const uint32_t b_src = a_src + (uint32_t)p.planes * GEMM_A_BYTES;
+            const int nks = min(GEMM_BK / 16, (p.K - kb * GEMM_BK + 15) / 16);
+            for (int k = 0; k < nks; ++k) {
+              const uint32_t koff = p.mn_major ? k * 2048 : k * 32;
+              const uint32_t lbo = p.mn_major ? 8192 : 16;
+              const uint64_t a_hi = umma_desc_sw128(a_src + koff, lbo, 1024);
+              const uint64_t b_hi = umma_desc_sw128(b_src + koff, lbo, 1024);
+              if (p.planes == 2) {
+                const uint64_t a_lo = umma_desc_sw128(a_src + GEMM_A_BYTES + koff, lbo, 1024);
+                const uint64_t b_lo = umma_desc_sw128(b_src + b_bytes + koff, lbo, 1024);
+                umma_bf16(d_tmem, a_lo, b_hi, idesc, accumulate);
+                umma_bf16(d_tmem, a_hi, b_lo, idesc, 1);
+                umma_bf16(d_tmem, a_hi, b_hi, idesc, 1);
+              } else {
+                umma_bf16(d_tmem, a_hi, b_hi, idesc, accumulate);
               }
-              umma_commit(empty_bar(stage));
-              if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+              accumulate = 1;
             }
+            umma_commit(empty_bar(stage));
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
           umma_commit(tfull_bar(acc));
           acc ^= 1;
