@@ -4,5 +4,3 @@ tail -5 gpurun_out/pytest_gpu.log
 timeout 600 python bench.py --steps 50 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err
 cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_ncu.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:nrl_gemm_tc_kernel -s 18 -c 18 -o gpurun_out/prof_gemm python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/prof_gemm.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_.*s32 -s 2 -c 2 -o gpurun_out/prof_attn python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/prof_attn.log 2>&1

@@ -132,7 +132,7 @@ struct Bump {
 };
 
 struct Dims {
-  int E, H, Q, DH, Ep, Qp, P3;
+  int E, H, Q, DH, Ep, Qp, P3, MW;
 };
 static int make_dims(nrl_dims d, Dims& o) {
   if (d.embed_dim <= 0 || d.num_heads <= 0 || d.query_dim <= 0 || d.embed_dim % d.num_heads)
@@ -145,6 +145,7 @@ static int make_dims(nrl_dims d, Dims& o) {
   o.Ep = round_up(o.E + 1, 16);
   o.Qp = round_up(o.Q, 16);
   o.P3 = round_up(3 * o.E, 16);
+  o.MW = (o.E + 31) / 32;
   return NRL_OK;
 }
 
@@ -164,6 +165,7 @@ struct BlockWs {
   float* d_o;  // [R][E]
   bf16* dqkv;  // [2][R][P3]
   float* dx;   // [R][E]
+  uint32_t *mask0, *mask1;  // [R][MW] dropout keep-bit words of the two sites
 };
 static void carve_block(Bump& b, long long R, const Dims& d, BlockWs& w) {
   w.win_f = b.take<bf16>(2ull * 3 * d.E * d.Ep);
@@ -187,6 +189,8 @@ static void carve_block(Bump& b, long long R, const Dims& d, BlockWs& w) {
   w.d_o = b.take<float>((size_t)R * d.E);
   w.dqkv = b.take<bf16>(2ull * R * d.P3);
   w.dx = b.take<float>((size_t)R * d.E);
+  w.mask0 = b.take<uint32_t>((size_t)R * d.MW);
+  w.mask1 = b.take<uint32_t>((size_t)R * d.MW);
 }
 
 // ----------------------------------------------------------------------------------------
@@ -468,6 +472,10 @@ static void launch_attn_bwd(const Ctx& c, const Dims& d, const AttnGeom& g, cons
 struct DropCfg {
   int on; float scale; uint32_t thr; unsigned long long seed;
 };
+static void epi_dropout(GemmEpi& e, const DropCfg& dc, const uint32_t* words, int mw) {
+  if (!dc.on) return;
+  e.drop_words = words; e.drop_mw = mw; e.drop_scale = dc.scale;
+}
 static DropCfg make_drop(float p, int training, unsigned long long seed) {
   DropCfg dc;
   dc.on = (training && p > 0.f) ? 1 : 0;
@@ -510,10 +518,7 @@ static int block_forward(const Ctx& c, const Dims& d, BlockWs& w, long long R, c
     Sinks sk;
     sk.f32 = w.y; sk.ld_f32 = d.E; sk.f32_cols = d.E;
     sk.sp = w.yp; sk.ld_sp = d.Ep; sk.sp_cols = d.Ep; sk.ones_col = d.E;
-    if (drop.on) {
-      e.use_dropout = 1; e.drop_scale = drop.scale; e.drop_thr = drop.thr; e.drop_site = 1;
-      e.seed = drop.seed; e.drop_ld = d.E;
-    }
+    epi_dropout(e, drop, w.mask1, d.MW);
     TRY(gemm_nt(c, w.o, R, d.Ep, w.wout_f, d.E, d.Ep, d.Ep, e, sk, "gemm out_proj"));
   }
   // K6: a = tanh(Y W_add^T + b_add), score = a . query  (fused epilogue)
@@ -546,10 +551,7 @@ static int block_backward(const Ctx& c, const Dims& d, BlockWs& w, long long R, 
     e.add_w = w.w; e.add_vec = d_vec; e.ld_addvec = d.E; e.add_L = L;  // + w_r * dVec[g(r)]
     Sinks sk;
     sk.sp = w.dyp; sk.ld_sp = d.Ep; sk.sp_cols = d.Ep; sk.ones_col = -1;
-    if (drop1.on) {
-      e.use_dropout = 1; e.drop_scale = drop1.scale; e.drop_thr = drop1.thr; e.drop_site = 1;
-      e.seed = drop1.seed; e.drop_ld = d.E;
-    }
+    epi_dropout(e, drop1, w.mask1, d.MW);
     TRY(gemm_nt(c, w.dap, R, d.Qp, w.wadd_t, d.E, d.Qp, d.Qp, e, sk, "gemm additive dgrad"));
   }
   // dW_add, db_add
@@ -575,10 +577,7 @@ static int block_backward(const Ctx& c, const Dims& d, BlockWs& w, long long R, 
     GemmEpi e = epi_none();
     Sinks sk;
     sk.f32 = w.dx; sk.ld_f32 = d.E; sk.f32_cols = d.E;
-    if (drop0.on) {
-      e.use_dropout = 1; e.drop_scale = drop0.scale; e.drop_thr = drop0.thr; e.drop_site = 0;
-      e.seed = drop0.seed; e.drop_ld = d.E;
-    }
+    epi_dropout(e, drop0, w.mask0, d.MW);
     TRY(gemm_nt(c, w.dqkv, R, d.P3, w.win_t, d.E, d.P3, d.P3, e, sk, "gemm in_proj dgrad"));
   }
   // dW_in, db_in
@@ -604,9 +603,14 @@ static int news_fwd_impl(const Ctx& c, const Dims& d, BlockWs& w, const long lon
                          const nrl_block_params* prm, const DropCfg& drop, float* out) {
   const long long R = n_news * L;
   TRY(pack_weights(c, d, prm, w));
+  if (drop.on) {
+    dropout_words_kernel<<<grid_for(2 * R * d.MW, 256, 16 * g_dev.sm_count), 256, 0, c.stream>>>(
+        drop.seed, drop.thr, R, d.E, d.MW, w.mask0, w.mask1);
+    LAUNCH_CHECK("dropout_words");
+  }
   gather_split_kernel<<<grid_for(R, 8, 1 << 20), 256, 0, c.stream>>>(
-      ids, R, table, d.E, d.Ep, w.x, c.two_planes() ? w.x + R * d.Ep : nullptr, nullptr, drop.on,
-      drop.scale, drop.thr, drop.seed);
+      ids, R, table, d.E, d.Ep, w.x, c.two_planes() ? w.x + R * d.Ep : nullptr, nullptr,
+      drop.on ? w.mask0 : nullptr, d.MW, drop.scale);
   LAUNCH_CHECK("gather_split");
   AttnGeom ag{L, 1, (int)n_news, L};
   return block_forward(c, d, w, R, ag, n_news, L, prm, drop, out);

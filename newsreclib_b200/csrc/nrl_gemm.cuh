@@ -49,8 +49,7 @@ constexpr int GEMM_TMEM_COLS = 512;
 struct GemmEpi {
   // x = acc ; x += add_w[row] * add_vec[row / add_L, col] ; dropout ; tanh + query dot ; sinks
   const float* add_w;   const float* add_vec; long long ld_addvec; int add_L;
-  int   use_dropout;    float drop_scale;     uint32_t drop_thr;   uint32_t drop_site;
-  unsigned long long seed; int drop_ld;
+  const uint32_t* drop_words; int drop_mw; float drop_scale;  // keep-bit words [row][drop_mw], or null
   const float* qvec;    float* score;         // x = tanh(x); score[row] = sum_col x * qvec[col]
   int f32_sink;         // 0 none, 1 TMA store of x to tmOut, 2 TMA reduce-add of x into tmOut
   int f32_cols;         // column extent of tmOut
@@ -300,11 +299,9 @@ nrl_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 }
               }
             }
-            if (e.use_dropout) {
-              const uint32_t bits = drop_keep_bits32(
-                  e.seed, e.drop_site,
-                  (unsigned long long)(row_ok ? row : 0) * (unsigned)e.drop_ld + (unsigned)col_base,
-                  e.drop_thr);
+            if (e.drop_words) {  // col_base % 32 == 0: one word holds this chunk's keep-bits
+              const uint32_t bits =
+                  row_ok ? __ldg(e.drop_words + (long long)row * e.drop_mw + (col_base >> 5)) : 0u;
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = ((bits >> i) & 1u) ? v[i] * e.drop_scale : 0.f;
             }
@@ -313,7 +310,7 @@ nrl_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               for (int i = 0; i < 32; ++i) {
                 float a = 0.f;
                 if (col_base + i < p.N) {
-                  a = tanhf(v[i]);
+                  a = tanh_fast(v[i]);
                   score_acc += a * __ldg(e.qvec + col_base + i);
                 }
                 v[i] = a;

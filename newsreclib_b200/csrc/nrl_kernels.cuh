@@ -87,8 +87,8 @@ __global__ void pack_weight_kernel(const float* __restrict__ W, const float* __r
 __global__ void gather_split_kernel(const long long* __restrict__ ids, long long R,
                                     const float* __restrict__ table, int E, int ep,
                                     __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                                    float* __restrict__ x_f32, int use_dropout, float drop_scale,
-                                    uint32_t drop_thr, unsigned long long seed) {
+                                    float* __restrict__ x_f32, const uint32_t* __restrict__ drop_words,
+                                    int drop_mw, float drop_scale) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -104,19 +104,10 @@ __global__ void gather_split_kernel(const long long* __restrict__ ids, long long
 #pragma unroll
         for (int i = 0; i < 4; ++i) v[i] = (c + i < E) ? __ldg(src + c + i) : 0.f;
       }
-      if (use_dropout) {
-        unsigned long long e0 = (unsigned long long)r * (unsigned)E + (unsigned)c;
-        if ((e0 & 3ull) == 0) {
-          Philox4 rr = philox4x32_10(seed, e0 >> 3, 0u);
-          int s0 = (int)(e0 & 7ull);
+      if (drop_words && c < E) {  // c % 4 == 0: the four keep-bits sit in one word
+        const uint32_t bits = __ldg(drop_words + r * drop_mw + (c >> 5)) >> (c & 31);
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            v[i] = philox_u16(rr, s0 + i) >= drop_thr ? v[i] * drop_scale : 0.f;
-        } else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            v[i] = drop_keep(seed, 0u, e0 + i, drop_thr) ? v[i] * drop_scale : 0.f;
-        }
+        for (int i = 0; i < 4; ++i) v[i] = ((bits >> i) & 1u) ? v[i] * drop_scale : 0.f;
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
@@ -681,6 +672,29 @@ __host__ __device__ __forceinline__ int attn_pitch(int floats) {  // floats % 4 
   return floats;
 }
 
+// packed fp32 pairs (Blackwell FFMA2: two FMAs per issued instruction)
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+constexpr float NRL_LOG2E = 1.4426950408889634f;
+constexpr float NRL_LN2 = 0.6931471805599453f;
+
+// Cooperative tile copy helper: thread -> (row sub-index, 16-byte column) computed once per work
+// item; rows are then walked with a fixed stride (no div/mod in the loop).
+struct TileMap {
+  int r0, rstep, col;  // col in float4 units within the row's [nseg * segv] vector; r0 < 0: idle
+};
+__device__ __forceinline__ TileMap tile_map(int per_row) {
+  TileMap m;
+  const int rpp = blockDim.x / per_row;
+  if (rpp >= 1) {
+    m.rstep = rpp;
+    m.r0 = (int)threadIdx.x < rpp * per_row ? (int)threadIdx.x / per_row : -1;
+    m.col = (int)threadIdx.x % per_row;
+  } else {
+    m.rstep = 0; m.r0 = 0; m.col = 0;
+  }
+  return m;
+}
+
 template <int DH>
 __global__ void __launch_bounds__(160, 4)
 attn_fwd_s32_kernel(const float* __restrict__ qkv, int E, int heads, int S, long long seq_stride,
@@ -690,26 +704,43 @@ attn_fwd_s32_kernel(const float* __restrict__ qkv, int E, int heads, int S, long
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, hg = blockDim.x >> 5;
   const int groups = (heads + hg - 1) / hg;
   const int ld = 3 * E;
+  const float qscale = scale * NRL_LOG2E;  // scores live in the log2 domain: p = 2^(s - m)
   for (long long work = blockIdx.x; work < (long long)NB * groups; work += gridDim.x) {
     const int b = (int)(work / groups), grp = (int)(work % groups);
     const int h0 = grp * hg, nh = min(hg, heads - h0);
     const int W = nh * DH, P = attn_pitch(3 * W), segv = W / 4;
     __syncthreads();
-    for (int i = threadIdx.x; i < S * 3 * segv; i += blockDim.x) {
-      const int srow = i / (3 * segv), rem = i - srow * 3 * segv, seg = rem / segv, c4 = rem - seg * segv;
-      const long long grow = (long long)srow * seq_stride + (long long)b * batch_stride;
-      reinterpret_cast<float4*>(tile + srow * P + seg * W)[c4] =
-          __ldg(reinterpret_cast<const float4*>(qkv + grow * ld + seg * E + h0 * DH) + c4);
+    {
+      const TileMap tm = tile_map(3 * segv);
+      if (tm.rstep > 0) {
+        if (tm.r0 >= 0) {
+          const int seg = tm.col / segv, c4 = tm.col - seg * segv;
+          const float* src0 = qkv + seg * E + h0 * DH + 4 * c4;
+          float* dst0 = tile + seg * W + 4 * c4;
+          for (int srow = tm.r0; srow < S; srow += tm.rstep) {
+            const long long grow = (long long)srow * seq_stride + (long long)b * batch_stride;
+            *reinterpret_cast<float4*>(dst0 + srow * P) = __ldg(reinterpret_cast<const float4*>(src0 + grow * ld));
+          }
+        }
+      } else {
+        for (int i = threadIdx.x; i < S * 3 * segv; i += blockDim.x) {
+          const int srow = i / (3 * segv), rem = i - srow * 3 * segv, seg = rem / segv, c4 = rem - seg * segv;
+          const long long grow = (long long)srow * seq_stride + (long long)b * batch_stride;
+          reinterpret_cast<float4*>(tile + srow * P + seg * W)[c4] =
+              __ldg(reinterpret_cast<const float4*>(qkv + grow * ld + seg * E + h0 * DH) + c4);
+        }
+      }
     }
     __syncthreads();
     if (warp < nh) {
       const bool ok = lane < S;
       float* qrow = tile + (ok ? lane : 0) * P + warp * DH;
-      float q[DH];
+      float2 q2[DH / 2];
 #pragma unroll
       for (int d = 0; d < DH; d += 4) {
         const float4 t4 = *reinterpret_cast<const float4*>(qrow + d);
-        q[d] = t4.x * scale; q[d + 1] = t4.y * scale; q[d + 2] = t4.z * scale; q[d + 3] = t4.w * scale;
+        q2[d / 2] = make_float2(t4.x * qscale, t4.y * qscale);
+        q2[d / 2 + 1] = make_float2(t4.z * qscale, t4.w * qscale);
       }
       float sc[32];
       float m = -INFINITY;
@@ -718,34 +749,37 @@ attn_fwd_s32_kernel(const float* __restrict__ qkv, int E, int heads, int S, long
         sc[u] = -INFINITY;
         if (u < S) {
           const float* kr = tile + u * P + W + warp * DH;
-          float a0 = 0.f, a1 = 0.f;
+          float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
 #pragma unroll
           for (int d = 0; d < DH; d += 4) {
             const float4 k4 = *reinterpret_cast<const float4*>(kr + d);
-            a0 += q[d] * k4.x; a1 += q[d + 1] * k4.y; a0 += q[d + 2] * k4.z; a1 += q[d + 3] * k4.w;
+            a0 = ffma2(q2[d / 2], make_float2(k4.x, k4.y), a0);
+            a1 = ffma2(q2[d / 2 + 1], make_float2(k4.z, k4.w), a1);
           }
-          sc[u] = a0 + a1;
+          sc[u] = (a0.x + a0.y) + (a1.x + a1.y);
           m = fmaxf(m, sc[u]);
         }
       }
       float l = 0.f;
 #pragma unroll
       for (int u = 0; u < 32; ++u) {
-        const float pu = (u < S) ? expf(sc[u] - m) : 0.f;
+        const float pu = (u < S) ? ex2_approx(sc[u] - m) : 0.f;
         sc[u] = pu;
         l += pu;
       }
-      float o[DH];
+      float2 o2[DH / 2];
 #pragma unroll
-      for (int d = 0; d < DH; ++d) o[d] = 0.f;
+      for (int d = 0; d < DH / 2; ++d) o2[d] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int u = 0; u < 32; ++u) {
         if (u < S) {
           const float* vr = tile + u * P + 2 * W + warp * DH;
+          const float2 p2 = make_float2(sc[u], sc[u]);
 #pragma unroll
           for (int d = 0; d < DH; d += 4) {
             const float4 v4 = *reinterpret_cast<const float4*>(vr + d);
-            o[d] += sc[u] * v4.x; o[d + 1] += sc[u] * v4.y; o[d + 2] += sc[u] * v4.z; o[d + 3] += sc[u] * v4.w;
+            o2[d / 2] = ffma2(p2, make_float2(v4.x, v4.y), o2[d / 2]);
+            o2[d / 2 + 1] = ffma2(p2, make_float2(v4.z, v4.w), o2[d / 2 + 1]);
           }
         }
       }
@@ -753,23 +787,32 @@ attn_fwd_s32_kernel(const float* __restrict__ qkv, int E, int heads, int S, long
         const float inv = 1.f / l;
 #pragma unroll
         for (int d = 0; d < DH; d += 4)
-          *reinterpret_cast<float4*>(qrow + d) = make_float4(o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv);
+          *reinterpret_cast<float4*>(qrow + d) =
+              make_float4(o2[d / 2].x * inv, o2[d / 2].y * inv, o2[d / 2 + 1].x * inv, o2[d / 2 + 1].y * inv);
         const long long grow = (long long)lane * seq_stride + (long long)b * batch_stride;
-        lse[grow * heads + h0 + warp] = m + logf(l);
+        lse[grow * heads + h0 + warp] = m * NRL_LN2 + logf(l);  // natural-log LSE of the scaled scores
       }
     }
     __syncthreads();
     // write-back of the [S, W] output tile as split planes, 4 columns (8 bytes) per thread
-    for (int i = threadIdx.x; i < S * segv; i += blockDim.x) {
-      const int srow = i / segv, c = (i - srow * segv) * 4;
-      const long long grow = (long long)srow * seq_stride + (long long)b * batch_stride;
-      const float4 val = *reinterpret_cast<const float4*>(tile + srow * P + c);
-      __nv_bfloat16 h[4], l4[4];
-      split_bf16(val.x, h[0], l4[0]); split_bf16(val.y, h[1], l4[1]);
-      split_bf16(val.z, h[2], l4[2]); split_bf16(val.w, h[3], l4[3]);
-      const long long off = grow * ep + h0 * DH + c;
-      *reinterpret_cast<uint2*>(o_hi + off) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
-      if (o_lo) *reinterpret_cast<uint2*>(o_lo + off) = make_uint2(pack_bf16x2(l4[0], l4[1]), pack_bf16x2(l4[2], l4[3]));
+    {
+      const TileMap tm = tile_map(segv);
+      const int rstep = tm.rstep > 0 ? tm.rstep : 1;
+      if (tm.rstep > 0 ? tm.r0 >= 0 : true) {
+        for (int idx = (tm.rstep > 0 ? tm.r0 : (int)threadIdx.x); idx < (tm.rstep > 0 ? S : S * segv);
+             idx += (tm.rstep > 0 ? rstep : (int)blockDim.x)) {
+          const int srow = tm.rstep > 0 ? idx : idx / segv;
+          const int c = (tm.rstep > 0 ? tm.col : idx - srow * segv) * 4;
+          const long long grow = (long long)srow * seq_stride + (long long)b * batch_stride;
+          const float4 val = *reinterpret_cast<const float4*>(tile + srow * P + c);
+          __nv_bfloat16 h[4], l4[4];
+          split_bf16(val.x, h[0], l4[0]); split_bf16(val.y, h[1], l4[1]);
+          split_bf16(val.z, h[2], l4[2]); split_bf16(val.w, h[3], l4[3]);
+          const long long off = grow * ep + h0 * DH + c;
+          *reinterpret_cast<uint2*>(o_hi + off) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+          if (o_lo) *reinterpret_cast<uint2*>(o_lo + off) = make_uint2(pack_bf16x2(l4[0], l4[1]), pack_bf16x2(l4[2], l4[3]));
+        }
+      }
     }
     if (grp == 0) {
       for (int i = threadIdx.x; i < S * (ep - E); i += blockDim.x) {
@@ -797,35 +840,56 @@ attn_bwd_s32_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o
   const int groups = (heads + hg - 1) / hg;
   const int ld = 3 * E;
   const int Pmax = attn_pitch(4 * hg * DH);
+  const float qscale = scale * NRL_LOG2E;
   float* tbuf = tile + S * Pmax + warp * (32 * 33);
   for (long long work = blockIdx.x; work < (long long)NB * groups; work += gridDim.x) {
     const int b = (int)(work / groups), grp = (int)(work % groups);
     const int h0 = grp * hg, nh = min(hg, heads - h0);
     const int W = nh * DH, P = attn_pitch(4 * W), segv = W / 4;
     __syncthreads();
-    for (int i = threadIdx.x; i < S * 4 * segv; i += blockDim.x) {
-      const int srow = i / (4 * segv), rem = i - srow * 4 * segv, seg = rem / segv, c4 = rem - seg * segv;
-      const long long grow = (long long)srow * seq_stride + (long long)b * batch_stride;
-      const float4* src = seg < 3 ? reinterpret_cast<const float4*>(qkv + grow * ld + seg * E + h0 * DH)
-                                  : reinterpret_cast<const float4*>(d_o + grow * ld_do + h0 * DH);
-      reinterpret_cast<float4*>(tile + srow * P + seg * W)[c4] = __ldg(src + c4);
+    {
+      const TileMap tm = tile_map(4 * segv);
+      if (tm.rstep > 0) {
+        if (tm.r0 >= 0) {
+          const int seg = tm.col / segv, c4 = tm.col - seg * segv;
+          const float* src0 = seg < 3 ? qkv + seg * E + h0 * DH + 4 * c4 : d_o + h0 * DH + 4 * c4;
+          const long long sld = seg < 3 ? (long long)ld : ld_do;
+          float* dst0 = tile + seg * W + 4 * c4;
+          for (int srow = tm.r0; srow < S; srow += tm.rstep) {
+            const long long grow = (long long)srow * seq_stride + (long long)b * batch_stride;
+            *reinterpret_cast<float4*>(dst0 + srow * P) = __ldg(reinterpret_cast<const float4*>(src0 + grow * sld));
+          }
+        }
+      } else {
+        for (int i = threadIdx.x; i < S * 4 * segv; i += blockDim.x) {
+          const int srow = i / (4 * segv), rem = i - srow * 4 * segv, seg = rem / segv, c4 = rem - seg * segv;
+          const long long grow = (long long)srow * seq_stride + (long long)b * batch_stride;
+          const float4* src = seg < 3 ? reinterpret_cast<const float4*>(qkv + grow * ld + seg * E + h0 * DH)
+                                      : reinterpret_cast<const float4*>(d_o + grow * ld_do + h0 * DH);
+          reinterpret_cast<float4*>(tile + srow * P + seg * W)[c4] = __ldg(src + c4);
+        }
+      }
     }
     __syncthreads();
     if (warp < nh) {
       const bool ok = lane < S;
       float* base = tile + (ok ? lane : 0) * P + warp * DH;
       const long long grow_l = (long long)(ok ? lane : 0) * seq_stride + (long long)b * batch_stride;
-      const float my_lse = lse[grow_l * heads + h0 + warp];
-      float pr[32], ds[32], dq[DH];
+      const float my_lse2 = lse[grow_l * heads + h0 + warp] * NRL_LOG2E;
+      float pr[32], ds[32];
+      float2 dq2[DH / 2];
       {
-        float q[DH], go[DH];
+        float2 q2[DH / 2], go2[DH / 2];
 #pragma unroll
         for (int d = 0; d < DH; d += 4) {
           const float4 t4 = *reinterpret_cast<const float4*>(base + d);
           const float4 g4 = *reinterpret_cast<const float4*>(base + 3 * W + d);
-          q[d] = t4.x * scale; q[d + 1] = t4.y * scale; q[d + 2] = t4.z * scale; q[d + 3] = t4.w * scale;
-          go[d] = g4.x; go[d + 1] = g4.y; go[d + 2] = g4.z; go[d + 3] = g4.w;
-          dq[d] = dq[d + 1] = dq[d + 2] = dq[d + 3] = 0.f;
+          q2[d / 2] = make_float2(t4.x * qscale, t4.y * qscale);
+          q2[d / 2 + 1] = make_float2(t4.z * qscale, t4.w * qscale);
+          go2[d / 2] = make_float2(g4.x, g4.y);
+          go2[d / 2 + 1] = make_float2(g4.z, g4.w);
+          dq2[d / 2] = make_float2(0.f, 0.f);
+          dq2[d / 2 + 1] = make_float2(0.f, 0.f);
         }
         float dd = 0.f;
 #pragma unroll
@@ -833,17 +897,20 @@ attn_bwd_s32_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o
           pr[u] = 0.f; ds[u] = 0.f;
           if (u < S) {
             const float* kr = tile + u * P + W + warp * DH;
-            float s0 = 0.f, s1 = 0.f, p0 = 0.f, p1 = 0.f;
+            float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
+            float2 p0 = make_float2(0.f, 0.f), p1 = make_float2(0.f, 0.f);
 #pragma unroll
             for (int d = 0; d < DH; d += 4) {
               const float4 k4 = *reinterpret_cast<const float4*>(kr + d);
               const float4 v4 = *reinterpret_cast<const float4*>(kr + W + d);
-              s0 += q[d] * k4.x; s1 += q[d + 1] * k4.y; s0 += q[d + 2] * k4.z; s1 += q[d + 3] * k4.w;
-              p0 += go[d] * v4.x; p1 += go[d + 1] * v4.y; p0 += go[d + 2] * v4.z; p1 += go[d + 3] * v4.w;
+              s0 = ffma2(q2[d / 2], make_float2(k4.x, k4.y), s0);
+              s1 = ffma2(q2[d / 2 + 1], make_float2(k4.z, k4.w), s1);
+              p0 = ffma2(go2[d / 2], make_float2(v4.x, v4.y), p0);
+              p1 = ffma2(go2[d / 2 + 1], make_float2(v4.z, v4.w), p1);
             }
-            const float pu = ok ? expf(s0 + s1 - my_lse) : 0.f;
+            const float pu = ok ? ex2_approx((s0.x + s0.y) + (s1.x + s1.y) - my_lse2) : 0.f;
             pr[u] = pu;
-            ds[u] = p0 + p1;
+            ds[u] = (p0.x + p0.y) + (p1.x + p1.y);
             dd += pu * ds[u];
           }
         }
@@ -852,18 +919,17 @@ attn_bwd_s32_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o
           ds[u] = pr[u] * (ds[u] - dd);
           if (u < S) {
             const float* kr = tile + u * P + W + warp * DH;
+            const float2 d2 = make_float2(ds[u], ds[u]);
 #pragma unroll
             for (int d = 0; d < DH; d += 4) {
               const float4 k4 = *reinterpret_cast<const float4*>(kr + d);
-              dq[d] += ds[u] * k4.x; dq[d + 1] += ds[u] * k4.y; dq[d + 2] += ds[u] * k4.z; dq[d + 3] += ds[u] * k4.w;
+              dq2[d / 2] = ffma2(d2, make_float2(k4.x, k4.y), dq2[d / 2]);
+              dq2[d / 2 + 1] = ffma2(d2, make_float2(k4.z, k4.w), dq2[d / 2 + 1]);
             }
           }
         }
       }
       // ---- transpose dS, then P: lane t holds row t, wants column `lane` ----
-      float dk[DH], dv[DH];
-#pragma unroll
-      for (int d = 0; d < DH; ++d) { dk[d] = 0.f; dv[d] = 0.f; }
 #pragma unroll
       for (int u = 0; u < 32; ++u) tbuf[lane * 33 + u] = ds[u];
       __syncwarp();
@@ -876,16 +942,22 @@ attn_bwd_s32_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o
 #pragma unroll
       for (int t = 0; t < 32; ++t) pr[t] = tbuf[t * 33 + lane];
       // ---- phase B: lane = key.  dk = scale * sum_t dS[t][u] q_t ; dv = sum_t P[t][u] dO_t ----
+      float2 dk2[DH / 2], dv2[DH / 2];
+#pragma unroll
+      for (int d = 0; d < DH / 2; ++d) { dk2[d] = make_float2(0.f, 0.f); dv2[d] = make_float2(0.f, 0.f); }
 #pragma unroll
       for (int t = 0; t < 32; ++t) {
         if (t < S) {
           const float* qr = tile + t * P + warp * DH;
+          const float2 d2 = make_float2(ds[t], ds[t]), p2 = make_float2(pr[t], pr[t]);
 #pragma unroll
           for (int d = 0; d < DH; d += 4) {
             const float4 q4 = *reinterpret_cast<const float4*>(qr + d);
             const float4 g4 = *reinterpret_cast<const float4*>(qr + 3 * W + d);
-            dk[d] += ds[t] * q4.x; dk[d + 1] += ds[t] * q4.y; dk[d + 2] += ds[t] * q4.z; dk[d + 3] += ds[t] * q4.w;
-            dv[d] += pr[t] * g4.x; dv[d + 1] += pr[t] * g4.y; dv[d + 2] += pr[t] * g4.z; dv[d + 3] += pr[t] * g4.w;
+            dk2[d / 2] = ffma2(d2, make_float2(q4.x, q4.y), dk2[d / 2]);
+            dk2[d / 2 + 1] = ffma2(d2, make_float2(q4.z, q4.w), dk2[d / 2 + 1]);
+            dv2[d / 2] = ffma2(p2, make_float2(g4.x, g4.y), dv2[d / 2]);
+            dv2[d / 2 + 1] = ffma2(p2, make_float2(g4.z, g4.w), dv2[d / 2 + 1]);
           }
         }
       }
@@ -893,24 +965,40 @@ attn_bwd_s32_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o
       if (ok) {
 #pragma unroll
         for (int d = 0; d < DH; d += 4) {
-          *reinterpret_cast<float4*>(base + d) = make_float4(dq[d] * scale, dq[d + 1] * scale, dq[d + 2] * scale, dq[d + 3] * scale);
-          *reinterpret_cast<float4*>(base + W + d) = make_float4(dk[d] * scale, dk[d + 1] * scale, dk[d + 2] * scale, dk[d + 3] * scale);
-          *reinterpret_cast<float4*>(base + 2 * W + d) = make_float4(dv[d], dv[d + 1], dv[d + 2], dv[d + 3]);
+          *reinterpret_cast<float4*>(base + d) = make_float4(dq2[d / 2].x * scale, dq2[d / 2].y * scale,
+                                                             dq2[d / 2 + 1].x * scale, dq2[d / 2 + 1].y * scale);
+          *reinterpret_cast<float4*>(base + W + d) = make_float4(dk2[d / 2].x * scale, dk2[d / 2].y * scale,
+                                                                 dk2[d / 2 + 1].x * scale, dk2[d / 2 + 1].y * scale);
+          *reinterpret_cast<float4*>(base + 2 * W + d) =
+              make_float4(dv2[d / 2].x, dv2[d / 2].y, dv2[d / 2 + 1].x, dv2[d / 2 + 1].y);
         }
       }
     }
     __syncthreads();
     // ---- write-back: dQ | dK | dV row segments -> split planes, 4 columns per thread ----
-    for (int i = threadIdx.x; i < S * 3 * segv; i += blockDim.x) {
-      const int srow = i / (3 * segv), rem = i - srow * 3 * segv, seg = rem / segv, c = (rem - seg * segv) * 4;
-      const long long grow = (long long)srow * seq_stride + (long long)b * batch_stride;
-      const float4 val = *reinterpret_cast<const float4*>(tile + srow * P + seg * W + c);
-      __nv_bfloat16 h[4], l4[4];
-      split_bf16(val.x, h[0], l4[0]); split_bf16(val.y, h[1], l4[1]);
-      split_bf16(val.z, h[2], l4[2]); split_bf16(val.w, h[3], l4[3]);
-      const long long off = grow * p3 + seg * E + h0 * DH + c;
-      *reinterpret_cast<uint2*>(g_hi + off) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
-      if (g_lo) *reinterpret_cast<uint2*>(g_lo + off) = make_uint2(pack_bf16x2(l4[0], l4[1]), pack_bf16x2(l4[2], l4[3]));
+    {
+      const TileMap tm = tile_map(3 * segv);
+      auto put = [&](int srow, int seg, int c) {
+        const long long grow = (long long)srow * seq_stride + (long long)b * batch_stride;
+        const float4 val = *reinterpret_cast<const float4*>(tile + srow * P + seg * W + c);
+        __nv_bfloat16 h[4], l4[4];
+        split_bf16(val.x, h[0], l4[0]); split_bf16(val.y, h[1], l4[1]);
+        split_bf16(val.z, h[2], l4[2]); split_bf16(val.w, h[3], l4[3]);
+        const long long off = grow * p3 + seg * E + h0 * DH + c;
+        *reinterpret_cast<uint2*>(g_hi + off) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+        if (g_lo) *reinterpret_cast<uint2*>(g_lo + off) = make_uint2(pack_bf16x2(l4[0], l4[1]), pack_bf16x2(l4[2], l4[3]));
+      };
+      if (tm.rstep > 0) {
+        if (tm.r0 >= 0) {
+          const int seg = tm.col / segv, c = (tm.col - seg * segv) * 4;
+          for (int srow = tm.r0; srow < S; srow += tm.rstep) put(srow, seg, c);
+        }
+      } else {
+        for (int i = threadIdx.x; i < S * 3 * segv; i += blockDim.x) {
+          const int srow = i / (3 * segv), rem = i - srow * 3 * segv, seg = rem / segv;
+          put(srow, seg, (rem - seg * segv) * 4);
+        }
+      }
     }
     if (grp == 0 && p3 > 3 * E) {
       for (int i = threadIdx.x; i < S * (p3 - 3 * E); i += blockDim.x) {
@@ -1231,6 +1319,24 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     v[i] = vi;
     const float denom = sqrtf(vi) / sqrt_bc2 + eps;
     p[i] -= (lr / bc1) * (mi / denom);
+  }
+}
+
+// Keep-bit words of the two dropout sites of one encoder pass, drawn ONCE per step by all SMs
+// (the Philox rounds are a long dependent chain: far too slow for the four epilogue warps of
+// the GEMM) and read back by the gather kernel, the GEMM epilogues and the backward pass:
+// words[site][r * mw + w], bit i = element (r, 32 w + i) of site `site` is kept.
+__global__ void dropout_words_kernel(unsigned long long seed, uint32_t thr, long long R, int E, int mw,
+                                     uint32_t* __restrict__ w0, uint32_t* __restrict__ w1) {
+  const long long per_site = R * mw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < 2 * per_site;
+       i += (long long)gridDim.x * blockDim.x) {
+    const uint32_t site = i >= per_site ? 1u : 0u;
+    const long long j = i - site * per_site;
+    const long long r = j / mw;
+    const int w = (int)(j - r * mw);
+    const uint32_t bits = drop_keep_bits32(seed, site, (unsigned long long)r * (unsigned)E + 32u * (unsigned)w, thr);
+    (site ? w1 : w0)[j] = bits;
   }
 }
 

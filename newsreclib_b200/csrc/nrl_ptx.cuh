@@ -236,6 +236,18 @@ __host__ __device__ __forceinline__ bool drop_keep(uint64_t seed, uint32_t site,
   return philox_u16(r, static_cast<int>(e & 7)) >= thr;
 }
 
+// ------------------------------------------------------------------ fast transcendentals
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// tanh(x) = 1 - 2 / (1 + e^(2x)): two MUFU ops, absolute error ~1e-7 (saturates correctly)
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float t = ex2_approx(x * 2.8853900817779268f);
+  return 1.f - __fdividef(2.f, t + 1.f);
+}
+
 // ------------------------------------------------------------------ split bf16 planes
 // x ~= hi + lo with hi = bf16(x), lo = bf16(x - hi): 16 mantissa bits survive, which is what
 // lets three bf16 tensor-core passes (hi*hi + hi*lo + lo*hi) reproduce an fp32 GEMM to ~2e-5.
