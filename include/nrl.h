@@ -63,7 +63,7 @@ typedef struct {
 
 typedef struct {
   int embed_dim;  /* E  (configs/model/nrms.yaml:19) */
-  int num_heads;  /* h  (:20); E / h must be 16, 20 or 32 */
+  int num_heads;  /* h  (:20); E / h must be 16, 20, 32, 48 or 64 */
   int query_dim;  /* Q  (:21) */
 } nrl_dims;
 
@@ -105,6 +105,75 @@ int nrl_user_encoder_bwd(int B, int Hmax, const nrl_block_params* params, nrl_di
 size_t nrl_additive_ws_bytes(long long G, int L, int D, int Q);
 int nrl_additive_fwd(const float* x, long long G, int L, int D, int Q, const float* weight,
                      const float* bias, const float* query, float* out, void* ws,
+                     size_t ws_bytes, int precision, void* stream);
+/* Backward (same `ws` as the forward call): d_out [G, D] -> dx [G, L, D] (overwritten) and the
+ * parameter gradients (+=). */
+int nrl_additive_bwd(const float* x, long long G, int L, int D, int Q, const float* weight,
+                     const float* query, const float* d_out, float* dx, float* g_weight,
+                     float* g_bias, float* g_query, void* ws, size_t ws_bytes, int precision,
+                     void* stream);
+
+/* ---- NAML: CNNAddAtt.forward, encoders/news/text.py:163-176 ---------------------------------
+ * ids [n_news, L] int64 -> out [n_news, F]:  embedding -> dropout -> Conv2d(1, F, (w, E),
+ * padding ((w-1)/2, 0)) -> ReLU -> dropout -> AdditiveAttention(F, Q).  The conv is one K = w*E
+ * tensor-core GEMM over an im2col of the gathered rows.  w must be odd, E % 4 == 0, F % 4 == 0. */
+typedef struct {
+  const float* cnn_weight; /* cnn.weight                        [F, 1, w, E] */
+  const float* cnn_bias;   /* cnn.bias                          [F]          */
+  const float* add_weight; /* additive_attention.linear.weight  [Q, F]       */
+  const float* add_bias;   /* additive_attention.linear.bias    [Q]          */
+  const float* add_query;  /* additive_attention.query          [Q]          */
+} nrl_cnn_params;
+typedef struct {
+  float* cnn_weight;
+  float* cnn_bias;
+  float* add_weight;
+  float* add_bias;
+  float* add_query;
+} nrl_cnn_grads;
+typedef struct {
+  int embed_dim;   /* E  text_embed_dim (configs/model/naml.yaml:20) */
+  int num_filters; /* F  (:23) */
+  int window;      /* w  (:24) */
+  int query_dim;   /* Q  (:25) */
+} nrl_cnn_dims;
+size_t nrl_cnn_encoder_ws_bytes(long long n_news, int L, nrl_cnn_dims dims);
+int nrl_cnn_encoder_fwd(const long long* ids, long long n_news, int L, const float* table,
+                        long long V1, const nrl_cnn_params* params, nrl_cnn_dims dims,
+                        float dropout_p, int training, unsigned long long seed, float* out,
+                        void* ws, size_t ws_bytes, int precision, void* stream);
+int nrl_cnn_encoder_bwd(const long long* ids, long long n_news, int L, long long V1,
+                        const nrl_cnn_params* params, nrl_cnn_dims dims, float dropout_p,
+                        int training, unsigned long long seed, const float* d_out,
+                        nrl_cnn_grads* grads, float* d_table, void* ws, size_t ws_bytes,
+                        int precision, void* stream);
+
+/* ---- NAML: LinearEncoder.forward (category), encoders/news/category.py:73-82 ----------------
+ * ids [n] int64 -> out [n, O] = relu(dropout(table[ids]) W^T + b); table [V1, CE], weight [O, CE].
+ * dropout_p applies only when the module was built with use_dropout (NAML: False). */
+size_t nrl_linear_encoder_ws_bytes(long long n, int embed_dim, int out_dim);
+int nrl_linear_encoder_fwd(const long long* ids, long long n, const float* table, long long V1,
+                           int embed_dim, const float* weight, const float* bias, int out_dim,
+                           float dropout_p, int training, unsigned long long seed, float* out,
+                           void* ws, size_t ws_bytes, int precision, void* stream);
+/* `out` is the forward result (ReLU mask).  Gradients accumulate (+=); d_table row 0 untouched. */
+int nrl_linear_encoder_bwd(const long long* ids, long long n, long long V1, int embed_dim,
+                           const float* weight, int out_dim, float dropout_p, int training,
+                           unsigned long long seed, const float* out, const float* d_out,
+                           float* g_weight, float* g_bias, float* d_table, void* ws,
+                           size_t ws_bytes, int precision, void* stream);
+
+/* ---- PLM text-encoder head: the part of PLM.forward after the transformer, text.py:93-100 ----
+ * x [N, T, E] (last hidden states) -> dropout -> nn.MultiheadAttention over dim 0 (the N news of
+ * the call: batch_first=False quirk, attention_axis 0; 1 = along the T tokens) -> dropout ->
+ * AdditiveAttention over the T tokens -> out [N, E].  E / heads in {16, 20, 32, 48, 64}.
+ * Workspace size: nrl_user_encoder_ws_bytes(N, T, dims). */
+int nrl_plm_head_fwd(const float* x, int N, int T, const nrl_block_params* params, nrl_dims dims,
+                     int attention_axis, float dropout_p, int training, unsigned long long seed,
+                     float* out, void* ws, size_t ws_bytes, int precision, void* stream);
+int nrl_plm_head_bwd(int N, int T, const nrl_block_params* params, nrl_dims dims,
+                     int attention_axis, float dropout_p, int training, unsigned long long seed,
+                     const float* d_out, nrl_block_grads* grads, float* d_x, void* ws,
                      size_t ws_bytes, int precision, void* stream);
 
 /* ---- torch_geometric.utils.to_dense_batch (2.3.0), call sites nrms_module.py:233,237 ------

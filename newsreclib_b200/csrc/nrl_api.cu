@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -16,6 +17,8 @@
 #include "../../include/nrl.h"
 #include "nrl_gemm.cuh"
 #include "nrl_kernels.cuh"
+#include "nrl_attn_mma.cuh"
+#include "nrl_naml.cuh"
 
 using namespace nrl;
 typedef __nv_bfloat16 bf16;
@@ -139,8 +142,8 @@ static int make_dims(nrl_dims d, Dims& o) {
     return fail(NRL_ERR_INVALID_ARG, "bad dims E=%d heads=%d Q=%d", d.embed_dim, d.num_heads,
                 d.query_dim);
   o.E = d.embed_dim; o.H = d.num_heads; o.Q = d.query_dim; o.DH = o.E / o.H;
-  if (o.DH != 16 && o.DH != 20 && o.DH != 32)
-    return fail(NRL_ERR_UNSUPPORTED, "head dim %d not built (16, 20, 32)", o.DH);
+  if (o.DH != 16 && o.DH != 20 && o.DH != 32 && o.DH != 48 && o.DH != 64)
+    return fail(NRL_ERR_UNSUPPORTED, "head dim %d not built (16, 20, 32, 48, 64)", o.DH);
   if (o.Q > 256) return fail(NRL_ERR_UNSUPPORTED, "query_dim %d > 256", o.Q);
   o.Ep = round_up(o.E + 1, 16);
   o.Qp = round_up(o.Q, 16);
@@ -394,16 +397,24 @@ constexpr int ATTN_BWD_SMEM_BUDGET = 100 * 1024;
 
 constexpr int ATTN_S32_SMEM_BUDGET = 96 * 1024;
 
+// NRL_ATTN_SIMT=1 routes S <= 32 attention to the older fp32 SIMT kernels (profiling A/B only)
+static bool attn_force_simt() {
+  static const bool v = [] { const char* e = getenv("NRL_ATTN_SIMT"); return e && e[0] == '1'; }();
+  return v;
+}
+
 template <int DH>
 static int attn_set_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(attn_fwd_tile_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 ATTN_FWD_SMEM_BUDGET));
   CUDA_TRY(cudaFuncSetAttribute(attn_bwd_tile_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 ATTN_BWD_SMEM_BUDGET));
-  CUDA_TRY(cudaFuncSetAttribute(attn_fwd_s32_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                ATTN_S32_SMEM_BUDGET));
-  CUDA_TRY(cudaFuncSetAttribute(attn_bwd_s32_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                ATTN_S32_SMEM_BUDGET));
+  if constexpr (DH <= 32) {
+    CUDA_TRY(cudaFuncSetAttribute(attn_fwd_s32_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  ATTN_S32_SMEM_BUDGET));
+    CUDA_TRY(cudaFuncSetAttribute(attn_bwd_s32_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  ATTN_S32_SMEM_BUDGET));
+  }
   return NRL_OK;
 }
 
@@ -418,7 +429,14 @@ static int attn_head_group(int H) {
 template <int DH>
 static void launch_attn_fwd(const Ctx& c, const Dims& d, const AttnGeom& g, const BlockWs& w, long long R) {
   bf16* lo = c.two_planes() ? w.o + R * d.Ep : nullptr;
-  if (g.S <= 32) {  // register-resident path (title tokens)
+  if constexpr (DH <= 32) {
+  if (g.S <= 32 && !attn_force_simt()) {  // warp-level tensor-core path (title tokens)
+    const long long items = (long long)g.NB * d.H;
+    attn_fwd_mma_kernel<DH><<<(unsigned)((items + 3) / 4), 128, 0, c.stream>>>(
+        w.qkv, d.E, d.H, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH), w.o, lo, d.Ep, w.lse);
+    return;
+  }
+  if (g.S <= 32) {  // register-resident SIMT path (NRL_ATTN_SIMT=1: A/B comparison only)
     const int hg = attn_head_group(d.H), groups = (d.H + hg - 1) / hg;
     const size_t smem = (size_t)g.S * attn_pitch(3 * hg * DH) * sizeof(float);
     if (smem <= (size_t)ATTN_S32_SMEM_BUDGET) {
@@ -426,6 +444,7 @@ static void launch_attn_fwd(const Ctx& c, const Dims& d, const AttnGeom& g, cons
           w.qkv, d.E, d.H, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH), w.o, lo, d.Ep, w.lse);
       return;
     }
+  }
   }
   const size_t per_head = (size_t)g.S * 3 * DH * sizeof(float);
   int hp = (int)(ATTN_FWD_SMEM_BUDGET / per_head);
@@ -443,6 +462,14 @@ static void launch_attn_fwd(const Ctx& c, const Dims& d, const AttnGeom& g, cons
 template <int DH>
 static void launch_attn_bwd(const Ctx& c, const Dims& d, const AttnGeom& g, const BlockWs& w, long long R) {
   bf16* lo = c.two_planes() ? w.dqkv + R * d.P3 : nullptr;
+  if constexpr (DH <= 32) {
+  if (g.S <= 32 && !attn_force_simt()) {
+    const long long items = (long long)g.NB * d.H;
+    attn_bwd_mma_kernel<DH><<<(unsigned)((items + 3) / 4), 128, 0, c.stream>>>(
+        w.qkv, w.d_o, d.E, w.lse, d.E, d.H, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH),
+        w.dqkv, lo, d.P3);
+    return;
+  }
   if (g.S <= 32) {
     const int hg = attn_head_group(d.H), groups = (d.H + hg - 1) / hg;
     const size_t smem = ((size_t)g.S * attn_pitch(4 * hg * DH) + (size_t)hg * 32 * 33) * sizeof(float);
@@ -452,6 +479,7 @@ static void launch_attn_bwd(const Ctx& c, const Dims& d, const AttnGeom& g, cons
           w.dqkv, lo, d.P3);
       return;
     }
+  }
   }
   const size_t per_head = (size_t)g.S * (5 * DH + 2) * sizeof(float);
   int hp = (int)(ATTN_BWD_SMEM_BUDGET / per_head);
@@ -491,6 +519,8 @@ static int attn_attrs_init() {
   TRY(attn_set_attrs<16>());
   TRY(attn_set_attrs<20>());
   TRY(attn_set_attrs<32>());
+  TRY(attn_set_attrs<48>());
+  TRY(attn_set_attrs<64>());
   done = true;
   return NRL_OK;
 }
@@ -510,7 +540,9 @@ static int block_forward(const Ctx& c, const Dims& d, BlockWs& w, long long R, c
   // K4: per-head softmax(q k^T) v
   if (d.DH == 16) launch_attn_fwd<16>(c, d, ag, w, R);
   else if (d.DH == 20) launch_attn_fwd<20>(c, d, ag, w, R);
-  else launch_attn_fwd<32>(c, d, ag, w, R);
+  else if (d.DH == 32) launch_attn_fwd<32>(c, d, ag, w, R);
+  else if (d.DH == 48) launch_attn_fwd<48>(c, d, ag, w, R);
+  else launch_attn_fwd<64>(c, d, ag, w, R);
   LAUNCH_CHECK("attn_fwd");
   // K5: Y = O W_out^T + b_out  (+ dropout site 1), fp32 and split planes
   {
@@ -570,7 +602,9 @@ static int block_backward(const Ctx& c, const Dims& d, BlockWs& w, long long R, 
               "gemm out_proj wgrad"));
   if (d.DH == 16) launch_attn_bwd<16>(c, d, ag, w, R);
   else if (d.DH == 20) launch_attn_bwd<20>(c, d, ag, w, R);
-  else launch_attn_bwd<32>(c, d, ag, w, R);
+  else if (d.DH == 32) launch_attn_bwd<32>(c, d, ag, w, R);
+  else if (d.DH == 48) launch_attn_bwd<48>(c, d, ag, w, R);
+  else launch_attn_bwd<64>(c, d, ag, w, R);
   LAUNCH_CHECK("attn_bwd");
   // dX = dropout0'( dQKV W_in )
   {

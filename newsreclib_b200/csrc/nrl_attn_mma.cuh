@@ -1,0 +1,372 @@
+// Tensor-core self-attention for short sequences (S <= 32: the 30-token titles), sm_100a.
+//
+// One warp owns one (batch item, head): the whole problem -- Q, K, V (and dO) slices of
+// [S <= 32][DH <= 32] -- lives in the warp's registers as bf16 hi/lo fragment blocks, and every
+// contraction (S = QK^T, O = PV; backward: dP = dO V^T, dQ = dS K, dK = dS^T Q, dV = P^T dO)
+// is issued as warp-level mma.sync.m16n8k16 (bf16 in, fp32 accumulate) with the same three-pass
+// hi/lo scheme as the GEMMs (lo*hi + hi*lo + hi*hi), i.e. fp32-equivalent results.  A per-head
+// problem is 30 x 30 x 20: far below the tcgen05 tile (M >= 64, operands through shared-memory
+// descriptors, accumulator in TMEM), which would waste >= 75 % of the issued MMA work on
+// block-diagonal padding and need TMEM round trips for the softmax; the warp-level MMA is the
+// tensor instruction whose shape fits, and keeps softmax / dS in the accumulator registers.
+//
+// Fragment bookkeeping.  A [32 x 32] operand is held as 4 x 4 "blocks" of 8 x 8 elements, one
+// 32-bit register per block per plane, in the canonical row layout
+//     lane (g = lane >> 2, tg = lane & 3) holds  M[8 rb + g][8 cb + 2 tg, 8 cb + 2 tg + 1]
+// which is simultaneously (a) a quarter of the m16n8k16 A fragment, (b) half of the B fragment
+// of the TRANSPOSED operand (B[k][n] = M[n][k]), and (c) the accumulator layout.  Operands that
+// are needed with the other orientation (V in PV, K in dS K, Q / dO in the transposed products,
+// P^T / dS^T) are produced with movmatrix.trans on those registers: nothing is re-read from
+// memory and nothing goes through shared memory.
+#pragma once
+#include "nrl_kernels.cuh"
+
+namespace nrl {
+
+__device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2,
+                                          uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, "
+      "{%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t movm_t(uint32_t x) {
+  uint32_t y;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+// (x, y) -> packed bf16x2 hi (x in the low half) and the bf16x2 of the residuals
+__device__ __forceinline__ void split_pack2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+  const float2 hf = __bfloat1622float2(h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(x - hf.x, y - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// A [32 x 32] operand as 4 x 4 blocks, hi and lo planes.
+struct Blk {
+  uint32_t h[4][4], l[4][4];
+};
+
+// Load rows [0, S) x cols [0, DH) of a row-major fp32 slice (row r at base + r * row_stride
+// floats), scaled, into row-layout blocks; everything outside is zero.
+template <int DH>
+__device__ __forceinline__ void load_blocks(Blk& m, const float* __restrict__ base, long long row_stride,
+                                            int S, float mul, int g, int tg) {
+#pragma unroll
+  for (int rb = 0; rb < 4; ++rb) {
+    const int r = 8 * rb + g;
+    const bool rok = r < S;
+    const float* rp = base + (long long)(rok ? r : 0) * row_stride;
+#pragma unroll
+    for (int cb = 0; cb < 4; ++cb) {
+      if (8 * cb >= DH) {  // compile-time: no such columns
+        m.h[rb][cb] = 0u; m.l[rb][cb] = 0u;
+        continue;
+      }
+      const int c = 8 * cb + 2 * tg;
+      float2 v = make_float2(0.f, 0.f);
+      if (rok && c < DH) v = __ldg(reinterpret_cast<const float2*>(rp + c));
+      split_pack2(v.x * mul, v.y * mul, m.h[rb][cb], m.l[rb][cb]);
+    }
+  }
+}
+
+// c[i][j] += sum over k-steps  A(i, kk) * B(j, kk)   with A blocks a[2i + ..][2kk + ..] (row layout,
+// M x K) and B given as the row-layout blocks of the [N x K] operand b[j][2kk + ..] ("NT" product).
+template <int KSTEPS, int NT>
+__device__ __forceinline__ void mma_nt(float (&c)[2][4][4], const Blk& a, const Blk& b, bool three) {
+#pragma unroll
+  for (int kk = 0; kk < KSTEPS; ++kk)
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        if (three) {
+          mma_16816(c[i][j], a.l[2 * i][2 * kk], a.l[2 * i + 1][2 * kk], a.l[2 * i][2 * kk + 1],
+                    a.l[2 * i + 1][2 * kk + 1], b.h[j][2 * kk], b.h[j][2 * kk + 1]);
+          mma_16816(c[i][j], a.h[2 * i][2 * kk], a.h[2 * i + 1][2 * kk], a.h[2 * i][2 * kk + 1],
+                    a.h[2 * i + 1][2 * kk + 1], b.l[j][2 * kk], b.l[j][2 * kk + 1]);
+        }
+        mma_16816(c[i][j], a.h[2 * i][2 * kk], a.h[2 * i + 1][2 * kk], a.h[2 * i][2 * kk + 1],
+                  a.h[2 * i + 1][2 * kk + 1], b.h[j][2 * kk], b.h[j][2 * kk + 1]);
+      }
+}
+// c[i][j] += A(i, kk) * B(kk, j) with B given as row-layout blocks of the [K x N] operand
+// b[2kk + ..][j] ("NN" product: the B fragments are the movmatrix transposes of those blocks).
+template <int NT>
+__device__ __forceinline__ void mma_nn(float (&c)[2][4][4], const Blk& a, const Blk& b, bool three) {
+#pragma unroll
+  for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const uint32_t bh0 = movm_t(b.h[2 * kk][j]), bh1 = movm_t(b.h[2 * kk + 1][j]);
+      uint32_t bl0 = 0u, bl1 = 0u;
+      if (three) { bl0 = movm_t(b.l[2 * kk][j]); bl1 = movm_t(b.l[2 * kk + 1][j]); }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        if (three) {
+          mma_16816(c[i][j], a.l[2 * i][2 * kk], a.l[2 * i + 1][2 * kk], a.l[2 * i][2 * kk + 1],
+                    a.l[2 * i + 1][2 * kk + 1], bh0, bh1);
+          mma_16816(c[i][j], a.h[2 * i][2 * kk], a.h[2 * i + 1][2 * kk], a.h[2 * i][2 * kk + 1],
+                    a.h[2 * i + 1][2 * kk + 1], bl0, bl1);
+        }
+        mma_16816(c[i][j], a.h[2 * i][2 * kk], a.h[2 * i + 1][2 * kk], a.h[2 * i][2 * kk + 1],
+                  a.h[2 * i + 1][2 * kk + 1], bh0, bh1);
+      }
+    }
+}
+// Accumulator tile set c[2][4][4] (rows 16 i + g (+8), cols 8 j + 2 tg (+1)) -> row-layout blocks.
+__device__ __forceinline__ void acc_to_blocks(Blk& m, const float (&c)[2][4][4]) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      split_pack2(c[i][j][0], c[i][j][1], m.h[2 * i][j], m.l[2 * i][j]);
+      split_pack2(c[i][j][2], c[i][j][3], m.h[2 * i + 1][j], m.l[2 * i + 1][j]);
+    }
+}
+__device__ __forceinline__ void transpose_blocks(Blk& t, const Blk& m, bool three) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      t.h[c][r] = movm_t(m.h[r][c]);
+      t.l[c][r] = three ? movm_t(m.l[r][c]) : 0u;
+    }
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+  return v;
+}
+// Store accumulator tiles c[2][NT][4] (cols < DH, rows < S) as split planes at dst(row) + col.
+template <int DH, int NT>
+__device__ __forceinline__ void store_acc_split(const float (&c)[2][4][4], float mul0, float mul1,
+                                                float mul2, float mul3, __nv_bfloat16* __restrict__ hi,
+                                                __nv_bfloat16* __restrict__ lo, long long pitch,
+                                                const long long (&grow)[4], int S, int col0, int g, int tg) {
+  // mul[rb] scales rows 8 rb + g
+  const float mul[4] = {mul0, mul1, mul2, mul3};
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int rb = 2 * i + half;
+      if (8 * rb + g >= S) continue;
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const int col = 8 * j + 2 * tg;
+        if (col >= DH) continue;
+        uint32_t h, l;
+        split_pack2(c[i][j][2 * half] * mul[rb], c[i][j][2 * half + 1] * mul[rb], h, l);
+        const long long off = grow[rb] * pitch + col0 + col;
+        *reinterpret_cast<uint32_t*>(hi + off) = h;
+        if (lo) *reinterpret_cast<uint32_t*>(lo + off) = l;
+      }
+    }
+}
+
+template <int DH>
+__global__ void __launch_bounds__(128)
+attn_fwd_mma_kernel(const float* __restrict__ qkv, int E, int heads, int S, long long seq_stride,
+                    int NB, long long batch_stride, float scale, __nv_bfloat16* __restrict__ o_hi,
+                    __nv_bfloat16* __restrict__ o_lo, int ep, float* __restrict__ lse) {
+  constexpr int KS = (DH + 15) / 16;  // k-steps over the head dim
+  constexpr int ND = (DH + 7) / 8;    // 8-column blocks of the head dim
+  const int lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
+  const long long item = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (item >= (long long)NB * heads) return;
+  const int b = (int)(item / heads), h = (int)(item % heads);
+  const bool three = o_lo != nullptr;
+  const int ld = 3 * E;
+  const float* base = qkv + (long long)b * batch_stride * ld + h * DH;
+  const long long rstride = seq_stride * ld;
+
+  Blk q, k;
+  load_blocks<DH>(q, base, rstride, S, scale * NRL_LOG2E, g, tg);
+  load_blocks<DH>(k, base + E, rstride, S, 1.f, g, tg);
+  float s[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) s[i][j][c] = 0.f;
+  mma_nt<KS, 4>(s, q, k, three);
+
+  // softmax over the key axis (columns); rows 8 rb + g, rb = 2 i + half
+  float inv_l[4], row_lse[4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float m = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int col = 8 * j + 2 * tg + c;
+          if (col >= S) s[i][j][2 * half + c] = -INFINITY;
+          m = fmaxf(m, s[i][j][2 * half + c]);
+        }
+      m = quad_max(m);
+      float l = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const float p = ex2_approx(s[i][j][2 * half + c] - m);
+          s[i][j][2 * half + c] = p;
+          l += p;
+        }
+      l = quad_sum(l);
+      inv_l[2 * i + half] = 1.f / l;
+      row_lse[2 * i + half] = m * NRL_LN2 + logf(l);
+    }
+  Blk p;
+  acc_to_blocks(p, s);
+  Blk v;
+  load_blocks<DH>(v, base + 2 * E, rstride, S, 1.f, g, tg);
+  float o[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) o[i][j][c] = 0.f;
+  mma_nn<ND>(o, p, v, three);
+
+  long long grow[4];
+#pragma unroll
+  for (int rb = 0; rb < 4; ++rb) grow[rb] = (long long)(8 * rb + g) * seq_stride + (long long)b * batch_stride;
+  store_acc_split<DH, ND>(o, inv_l[0], inv_l[1], inv_l[2], inv_l[3], o_hi, o_lo, ep, grow, S, h * DH, g, tg);
+  if (tg == 0) {
+#pragma unroll
+    for (int rb = 0; rb < 4; ++rb)
+      if (8 * rb + g < S) lse[grow[rb] * heads + h] = row_lse[rb];
+  }
+  if (h == 0) {  // pad columns of the plane rows: ones column at E, zeros after
+    const int npad = ep - E;
+    for (int i = lane; i < S * npad; i += 32) {
+      const int srow = i / npad, c = E + i % npad;
+      const long long gr = (long long)srow * seq_stride + (long long)b * batch_stride;
+      o_hi[gr * ep + c] = __float2bfloat16_rn(c == E ? 1.f : 0.f);
+      if (o_lo) o_lo[gr * ep + c] = __float2bfloat16_rn(0.f);
+    }
+  }
+}
+
+// Backward.  P is recomputed from Q, K and the saved log-sum-exp; D = rowsum(P * dP).
+// Writes dQ | dK | dV as split planes [2][R][p3].
+template <int DH>
+__global__ void __launch_bounds__(128, 2)
+attn_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o, long long ld_do,
+                    const float* __restrict__ lse, int E, int heads, int S, long long seq_stride,
+                    int NB, long long batch_stride, float scale, __nv_bfloat16* __restrict__ g_hi,
+                    __nv_bfloat16* __restrict__ g_lo, int p3) {
+  constexpr int KS = (DH + 15) / 16;
+  constexpr int ND = (DH + 7) / 8;
+  const int lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
+  const long long item = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (item >= (long long)NB * heads) return;
+  const int b = (int)(item / heads), h = (int)(item % heads);
+  const bool three = g_lo != nullptr;
+  const int ld = 3 * E;
+  const float* base = qkv + (long long)b * batch_stride * ld + h * DH;
+  const long long rstride = seq_stride * ld;
+  long long grow[4];
+#pragma unroll
+  for (int rb = 0; rb < 4; ++rb) grow[rb] = (long long)(8 * rb + g) * seq_stride + (long long)b * batch_stride;
+
+  Blk q, k, v, go;
+  load_blocks<DH>(q, base, rstride, S, scale * NRL_LOG2E, g, tg);  // Qs = Q * scale * log2(e)
+  load_blocks<DH>(k, base + E, rstride, S, 1.f, g, tg);
+  load_blocks<DH>(v, base + 2 * E, rstride, S, 1.f, g, tg);
+  load_blocks<DH>(go, d_o + (long long)b * batch_stride * ld_do + h * DH, seq_stride * ld_do, S, 1.f, g, tg);
+  float lse2[4];
+#pragma unroll
+  for (int rb = 0; rb < 4; ++rb)
+    lse2[rb] = (8 * rb + g < S) ? __ldg(lse + grow[rb] * heads + h) * NRL_LOG2E : 0.f;
+
+  float s[2][4][4], dp[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { s[i][j][c] = 0.f; dp[i][j][c] = 0.f; }
+  mma_nt<KS, 4>(s, q, k, three);    // S (log2 domain)  [t][u]
+  mma_nt<KS, 4>(dp, go, v, three);  // dP = dO V^T      [t][u]
+
+  // P = 2^(S - lse2), D_t = sum_u P dP, dS = P (dP - D)   (natural-domain gradient of the scaled scores)
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int rb = 2 * i + half;
+      const bool rok = 8 * rb + g < S;
+      float dd = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int col = 8 * j + 2 * tg + c;
+          const float p = (rok && col < S) ? ex2_approx(s[i][j][2 * half + c] - lse2[rb]) : 0.f;
+          s[i][j][2 * half + c] = p;
+          dd += p * dp[i][j][2 * half + c];
+        }
+      dd = quad_sum(dd);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+          dp[i][j][2 * half + c] = s[i][j][2 * half + c] * (dp[i][j][2 * half + c] - dd);
+    }
+  Blk pb, ds;
+  acc_to_blocks(pb, s);
+  acc_to_blocks(ds, dp);
+
+  float acc[2][4][4];
+  auto zero = [&]() {
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.f;
+  };
+  // dQ = scale * dS K
+  zero();
+  mma_nn<ND>(acc, ds, k, three);
+  store_acc_split<DH, ND>(acc, scale, scale, scale, scale, g_hi, g_lo, p3, grow, S, h * DH, g, tg);
+  // dK = scale * dS^T Q = ln2 * dS^T Qs ;  dV = P^T dO
+  Blk t;
+  transpose_blocks(t, ds, three);
+  zero();
+  mma_nn<ND>(acc, t, q, three);
+  store_acc_split<DH, ND>(acc, NRL_LN2, NRL_LN2, NRL_LN2, NRL_LN2, g_hi, g_lo, p3, grow, S, E + h * DH, g, tg);
+  transpose_blocks(t, pb, three);
+  zero();
+  mma_nn<ND>(acc, t, go, three);
+  store_acc_split<DH, ND>(acc, 1.f, 1.f, 1.f, 1.f, g_hi, g_lo, p3, grow, S, 2 * E + h * DH, g, tg);
+
+  if (h == 0 && p3 > 3 * E) {
+    const int npad = p3 - 3 * E;
+    for (int i = lane; i < S * npad; i += 32) {
+      const int srow = i / npad, c = 3 * E + i % npad;
+      const long long gr = (long long)srow * seq_stride + (long long)b * batch_stride;
+      g_hi[gr * p3 + c] = __float2bfloat16_rn(0.f);
+      if (g_lo) g_lo[gr * p3 + c] = __float2bfloat16_rn(0.f);
+    }
+  }
+}
+
+}  // namespace nrl

@@ -47,8 +47,11 @@ constexpr int GEMM_SMEM_LIMIT = 227 * 1024;
 constexpr int GEMM_TMEM_COLS = 512;
 
 struct GemmEpi {
-  // x = acc ; x += add_w[row] * add_vec[row / add_L, col] ; dropout ; tanh + query dot ; sinks
+  // x = acc ; x += add_w[row] * add_vec[row / add_L, col] ; relu ; dropout ; positive-mask ;
+  // tanh + query dot ; sinks
   const float* add_w;   const float* add_vec; long long ld_addvec; int add_L;
+  int relu;             // x = max(x, 0)  (CNN / category-encoder forward)
+  const float* pos_mask; long long ld_pos;  // x = pos_mask[row, col] > 0 ? x : 0  (ReLU backward)
   const uint32_t* drop_words; int drop_mw; float drop_scale;  // keep-bit words [row][drop_mw], or null
   const float* qvec;    float* score;         // x = tanh(x); score[row] = sum_col x * qvec[col]
   int f32_sink;         // 0 none, 1 TMA store of x to tmOut, 2 TMA reduce-add of x into tmOut
@@ -299,11 +302,28 @@ nrl_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 }
               }
             }
+            if (e.relu) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
             if (e.drop_words) {  // col_base % 32 == 0: one word holds this chunk's keep-bits
               const uint32_t bits =
                   row_ok ? __ldg(e.drop_words + (long long)row * e.drop_mw + (col_base >> 5)) : 0u;
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = ((bits >> i) & 1u) ? v[i] * e.drop_scale : 0.f;
+            }
+            if (e.pos_mask && row_ok) {
+              const float* pm = e.pos_mask + (long long)row * e.ld_pos + col_base;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                if (col_base + 4 * q < p.N) {
+                  const float4 m4 = __ldg(reinterpret_cast<const float4*>(pm) + q);
+                  if (!(m4.x > 0.f)) v[4 * q] = 0.f;
+                  if (!(m4.y > 0.f)) v[4 * q + 1] = 0.f;
+                  if (!(m4.z > 0.f)) v[4 * q + 2] = 0.f;
+                  if (!(m4.w > 0.f)) v[4 * q + 3] = 0.f;
+                }
+              }
             }
             if (e.qvec) {
 #pragma unroll

@@ -93,7 +93,7 @@ __global__ void gather_split_kernel(const long long* __restrict__ ids, long long
   const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long r = warp0; r < R; r += nwarps) {
-    const long long id = ids[r];
+    const long long id = ids ? ids[r] : r;  // ids == nullptr: dense rows (identity gather)
     const float* src = table + id * E;
     for (int c = lane * 4; c < ep; c += 128) {
       float v[4];
@@ -406,7 +406,7 @@ attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o, lo
 // smem row layout: [ q(hp*DH) | k(hp*DH) | v(hp*DH) ]  (+ [ dO | dQ ] in the backward kernel)
 // ------------------------------------------------------------------------------------
 template <int DH>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, DH <= 32 ? 2 : 1)
 attn_fwd_tile_kernel(const float* __restrict__ qkv, int E, int heads, int S, long long seq_stride,
                      int NB, long long batch_stride, float scale, int hp,
                      __nv_bfloat16* __restrict__ o_hi, __nv_bfloat16* __restrict__ o_lo, int ep,
@@ -507,7 +507,7 @@ attn_fwd_tile_kernel(const float* __restrict__ qkv, int E, int heads, int S, lon
 }
 
 template <int DH>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, DH <= 32 ? 2 : 1)
 attn_bwd_tile_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o, long long ld_do,
                      const float* __restrict__ lse, int E, int heads, int S, long long seq_stride,
                      int NB, long long batch_stride, float scale, int hp,

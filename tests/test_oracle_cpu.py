@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import GOLD, TITLE, USER, load_golden, oracle_run, rel_err
+from helpers import GOLD, TITLE, USER, grad_tolerances, load_golden, oracle_run, rel_err
 from oracle import nrms_oracle as O
 
 
@@ -22,11 +22,15 @@ def test_oracle_matches_reference_golden(name):
     assert rel_err(loss, g["loss"]) < 1e-6
     title, _ = O.split_params(params)
     assert rel_err(O.mhsa_add_att(batch["x_hist"]["title"], title, d["H"]), g["hist_vec"]) < 1e-5
+    # per-tensor bar = max(2e-4, 4 x the fp32 oracle's own error against an fp64 run): the
+    # additive-attention bias gradient is a sum that cancels to ~1e-5 of its terms, so two fp32
+    # evaluations on different hosts (BLAS thread counts) differ by more than 2e-4 there
+    tol = grad_tolerances(params, batch, d["H"], 2e-4, ref_grads=grads)
     for k, v in g.items():
         if k.startswith("grad/"):
-            assert rel_err(grads[k[5:]], v) < 2e-4, k
+            assert rel_err(grads[k[5:]], v) < tol[k[5:]], k
         elif k.startswith("gradsample/"):
-            assert rel_err(grads[k[11:]].reshape(-1)[::7], v) < 2e-4, k
+            assert rel_err(grads[k[11:]].reshape(-1)[::7], v) < tol[k[11:]], k
     # padded candidate slots score exactly 0, embedding row 0 has exactly zero gradient
     B = d["B"]
     cnt = torch.bincount(batch["batch_cand"], minlength=B)
