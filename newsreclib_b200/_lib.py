@@ -33,6 +33,22 @@ class BlockParams(C.Structure):
     ]
 
 
+class CnnParams(C.Structure):
+    """``nrl_cnn_params`` / ``nrl_cnn_grads`` (five float pointers)."""
+
+    _fields_ = [
+        ("cnn_weight", C.c_void_p),
+        ("cnn_bias", C.c_void_p),
+        ("add_weight", C.c_void_p),
+        ("add_bias", C.c_void_p),
+        ("add_query", C.c_void_p),
+    ]
+
+
+class CnnDims(C.Structure):
+    _fields_ = [("embed_dim", C.c_int), ("num_filters", C.c_int), ("window", C.c_int), ("query_dim", C.c_int)]
+
+
 class Dims(C.Structure):
     _fields_ = [("embed_dim", C.c_int), ("num_heads", C.c_int), ("query_dim", C.c_int)]
 
@@ -43,6 +59,7 @@ PREC_BF16 = 1
 # name -> (restype, argtypes); every symbol include/nrl.h declares
 _VP, _LL, _I, _F, _ULL, _SZ = C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_ulonglong, C.c_size_t
 _BP = C.POINTER(BlockParams)
+_CP = C.POINTER(CnnParams)
 SIGNATURES = {
     "nrl_version": (C.c_char_p, []),
     "nrl_last_error": (C.c_char_p, []),
@@ -57,6 +74,15 @@ SIGNATURES = {
     "nrl_user_encoder_bwd": (_I, [_I, _I, _BP, Dims, _I, _VP, _BP, _VP, _VP, _SZ, _I, _VP]),
     "nrl_additive_ws_bytes": (_SZ, [_LL, _I, _I, _I]),
     "nrl_additive_fwd": (_I, [_VP, _LL, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _SZ, _I, _VP]),
+    "nrl_additive_bwd": (_I, [_VP, _LL, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _I, _VP]),
+    "nrl_cnn_encoder_ws_bytes": (_SZ, [_LL, _I, CnnDims]),
+    "nrl_cnn_encoder_fwd": (_I, [_VP, _LL, _I, _VP, _LL, _CP, CnnDims, _F, _I, _ULL, _VP, _VP, _SZ, _I, _VP]),
+    "nrl_cnn_encoder_bwd": (_I, [_VP, _LL, _I, _LL, _CP, CnnDims, _F, _I, _ULL, _VP, _CP, _VP, _VP, _SZ, _I, _VP]),
+    "nrl_linear_encoder_ws_bytes": (_SZ, [_LL, _I, _I]),
+    "nrl_linear_encoder_fwd": (_I, [_VP, _LL, _VP, _LL, _I, _VP, _VP, _I, _F, _I, _ULL, _VP, _VP, _SZ, _I, _VP]),
+    "nrl_linear_encoder_bwd": (_I, [_VP, _LL, _LL, _I, _VP, _I, _F, _I, _ULL, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _I, _VP]),
+    "nrl_plm_head_fwd": (_I, [_VP, _I, _I, _BP, Dims, _I, _F, _I, _ULL, _VP, _VP, _SZ, _I, _VP]),
+    "nrl_plm_head_bwd": (_I, [_I, _I, _BP, Dims, _I, _F, _I, _ULL, _VP, _BP, _VP, _VP, _SZ, _I, _VP]),
     "nrl_segment_offsets": (_I, [_VP, _LL, _I, _VP, _VP]),
     "nrl_to_dense_fwd": (_I, [_VP, _VP, _I, _I, _I, _VP, _VP]),
     "nrl_to_dense_bwd": (_I, [_VP, _VP, _I, _I, _I, _VP, _VP]),

@@ -456,7 +456,7 @@ static void launch_attn_fwd(const Ctx& c, const Dims& d, const AttnGeom& g, cons
     return;
   }
   const long long items = (long long)g.NB * d.H * ((g.S + 31) / 32);
-  attn_fwd_kernel<DH><<<grid_for(items, 4, 1 << 20), 128, 0, c.stream>>>(
+  attn_fwd_kernel<DH><<<grid_for(items, attn_stream_warps(DH), 1 << 20), 32 * attn_stream_warps(DH), 0, c.stream>>>(
       w.qkv, d.E, d.H, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH), w.o, lo, d.Ep, w.lse);
 }
 template <int DH>
@@ -492,7 +492,7 @@ static void launch_attn_bwd(const Ctx& c, const Dims& d, const AttnGeom& g, cons
     return;
   }
   const long long items = (long long)g.NB * d.H;
-  attn_bwd_kernel<DH><<<grid_for(items, 4, 1 << 20), 128, 0, c.stream>>>(
+  attn_bwd_kernel<DH><<<grid_for(items, attn_stream_warps(DH), 1 << 20), 32 * attn_stream_warps(DH), 0, c.stream>>>(
       w.qkv, w.d_o, d.E, w.o, c.two_planes() ? w.o + R * d.Ep : nullptr, d.Ep, w.lse, d.E, d.H, g.S,
       g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH), w.dqkv, lo, d.P3);
 }
@@ -757,6 +757,38 @@ static AttnGeom user_geom(int B, int Hmax, int axis) {
   return AttnGeom{Hmax, 1, B, Hmax};                // along the history
 }
 
+// MHSA (+ the two dropout sites when drop.on) + additive pooling over dense rows x [B][Hmax][E]
+static int mhsa_pool_fwd(const Ctx& c, const Dims& d, const float* x, int B, int Hmax, int axis,
+                         const nrl_block_params* params, const DropCfg& drop, float* out, void* ws) {
+  Bump b(ws);
+  BlockWs w;
+  const long long R = (long long)B * Hmax;
+  carve_block(b, R, d, w);
+  TRY(pack_weights(c, d, params, w));
+  if (drop.on) {
+    dropout_words_kernel<<<grid_for(2 * R * d.MW, 256, 16 * g_dev.sm_count), 256, 0, c.stream>>>(
+        drop.seed, drop.thr, R, d.E, d.MW, w.mask0, w.mask1);
+    LAUNCH_CHECK("dropout_words");
+  }
+  // dense rows -> (dropout site 0) -> split planes: the gather kernel with the identity index
+  gather_split_kernel<<<grid_for(R, 8, 1 << 20), 256, 0, c.stream>>>(
+      nullptr, R, x, d.E, d.Ep, w.x, c.two_planes() ? w.x + R * d.Ep : nullptr, nullptr,
+      drop.on ? w.mask0 : nullptr, d.MW, drop.scale);
+  LAUNCH_CHECK("split_rows");
+  return block_forward(c, d, w, R, user_geom(B, Hmax, axis), B, Hmax, params, drop, out);
+}
+static int mhsa_pool_bwd(const Ctx& c, const Dims& d, int B, int Hmax, int axis,
+                         const nrl_block_params* params, const DropCfg& drop, const float* d_out,
+                         nrl_block_grads* grads, float* d_x, void* ws) {
+  Bump b(ws);
+  BlockWs w;
+  const long long R = (long long)B * Hmax;
+  carve_block(b, R, d, w);
+  TRY(block_backward(c, d, w, R, user_geom(B, Hmax, axis), B, Hmax, params, drop, drop, d_out, grads));
+  CUDA_TRY(cudaMemcpyAsync(d_x, w.dx, (size_t)R * d.E * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
+  return NRL_OK;
+}
+
 int nrl_user_encoder_fwd(const float* hist, int B, int Hmax, const nrl_block_params* params,
                          nrl_dims dims, int attention_axis, float* user, void* ws,
                          size_t ws_bytes, int precision, void* stream) {
@@ -767,17 +799,7 @@ int nrl_user_encoder_fwd(const float* hist, int B, int Hmax, const nrl_block_par
   TRY(device_init());
   TRY(check_common(ws, ws_bytes, nrl_user_encoder_ws_bytes(B, Hmax, dims)));
   Ctx c{static_cast<cudaStream_t>(stream), precision};
-  Bump b(ws);
-  BlockWs w;
-  const long long R = (long long)B * Hmax;
-  carve_block(b, R, d, w);
-  TRY(pack_weights(c, d, params, w));
-  // dense rows -> split planes (identity "scatter": every row present)
-  dense_scatter_kernel<<<grid_for(R, 1, 1 << 20), 128, 0, c.stream>>>(
-      hist, nullptr, (int)R, 1, d.E, d.Ep, nullptr, w.x, c.two_planes() ? w.x + R * d.Ep : nullptr);
-  LAUNCH_CHECK("split_rows");
-  DropCfg nodrop = make_drop(0.f, 0, 0);
-  return block_forward(c, d, w, R, user_geom(B, Hmax, attention_axis), B, Hmax, params, nodrop, user);
+  return mhsa_pool_fwd(c, d, hist, B, Hmax, attention_axis, params, make_drop(0.f, 0, 0), user, ws);
 }
 
 int nrl_user_encoder_bwd(int B, int Hmax, const nrl_block_params* params, nrl_dims dims,
@@ -790,66 +812,121 @@ int nrl_user_encoder_bwd(int B, int Hmax, const nrl_block_params* params, nrl_di
   TRY(device_init());
   TRY(check_common(ws, ws_bytes, nrl_user_encoder_ws_bytes(B, Hmax, dims)));
   Ctx c{static_cast<cudaStream_t>(stream), precision};
-  Bump b(ws);
-  BlockWs w;
-  const long long R = (long long)B * Hmax;
-  carve_block(b, R, d, w);
-  DropCfg nodrop = make_drop(0.f, 0, 0);
-  TRY(block_backward(c, d, w, R, user_geom(B, Hmax, attention_axis), B, Hmax, params, nodrop, nodrop,
-                     d_user, grads));
-  CUDA_TRY(cudaMemcpyAsync(d_hist, w.dx, (size_t)R * d.E * sizeof(float), cudaMemcpyDeviceToDevice,
-                           c.stream));
-  return NRL_OK;
+  return mhsa_pool_bwd(c, d, B, Hmax, attention_axis, params, make_drop(0.f, 0, 0), d_user, grads, d_hist, ws);
+}
+
+// PLM head = the same block over x [N][T][E] with both dropout sites (text.py:93-100)
+int nrl_plm_head_fwd(const float* x, int N, int T, const nrl_block_params* params, nrl_dims dims,
+                     int attention_axis, float dropout_p, int training, unsigned long long seed,
+                     float* out, void* ws, size_t ws_bytes, int precision, void* stream) {
+  Dims d;
+  TRY(make_dims(dims, d));
+  if (!x || !params || !out || N <= 0 || T <= 0)
+    return fail(NRL_ERR_INVALID_ARG, "nrl_plm_head_fwd: null pointer or empty input");
+  if (dropout_p < 0.f || dropout_p >= 1.f) return fail(NRL_ERR_INVALID_ARG, "dropout_p out of [0,1)");
+  TRY(device_init());
+  TRY(check_common(ws, ws_bytes, nrl_user_encoder_ws_bytes(N, T, dims)));
+  Ctx c{static_cast<cudaStream_t>(stream), precision};
+  return mhsa_pool_fwd(c, d, x, N, T, attention_axis, params, make_drop(dropout_p, training, seed), out, ws);
+}
+int nrl_plm_head_bwd(int N, int T, const nrl_block_params* params, nrl_dims dims,
+                     int attention_axis, float dropout_p, int training, unsigned long long seed,
+                     const float* d_out, nrl_block_grads* grads, float* d_x, void* ws,
+                     size_t ws_bytes, int precision, void* stream) {
+  Dims d;
+  TRY(make_dims(dims, d));
+  if (!params || !d_out || !grads || !d_x || N <= 0 || T <= 0)
+    return fail(NRL_ERR_INVALID_ARG, "nrl_plm_head_bwd: null pointer or empty input");
+  TRY(device_init());
+  TRY(check_common(ws, ws_bytes, nrl_user_encoder_ws_bytes(N, T, dims)));
+  Ctx c{static_cast<cudaStream_t>(stream), precision};
+  return mhsa_pool_bwd(c, d, N, T, attention_axis, params, make_drop(dropout_p, training, seed), d_out, grads,
+                       d_x, ws);
 }
 
 // ----------------------------------------------------------------------------------------
 // additive attention alone
 // ----------------------------------------------------------------------------------------
+struct AddWs {
+  bf16 *wf, *wt, *xp, *dap;
+  float *a, *s, *w;
+};
+static void carve_add(Bump& b, long long R, int D, int Q, AddWs& w) {
+  const int Dp = round_up(D + 1, 16), Qp = round_up(Q, 16);
+  w.wf = b.take<bf16>(2ull * Q * Dp);
+  w.wt = b.take<bf16>(2ull * D * Qp);
+  w.xp = b.take<bf16>(2ull * R * Dp);
+  w.a = b.take<float>((size_t)R * Q);
+  w.s = b.take<float>((size_t)R);
+  w.w = b.take<float>((size_t)R);
+  w.dap = b.take<bf16>(2ull * R * Qp);
+}
 size_t nrl_additive_ws_bytes(long long G, int L, int D, int Q) {
   if (G <= 0 || L <= 0 || D <= 0 || Q <= 0) return 0;
-  const long long R = G * L;
-  const int Dp = round_up(D + 1, 16);
   Bump b(nullptr);
-  b.take<bf16>(2ull * Q * Dp);
-  b.take<bf16>(2ull * D * round_up(Q, 16));
-  b.take<bf16>(2ull * R * Dp);
-  b.take<float>((size_t)R * Q);
-  b.take<float>((size_t)R);
-  b.take<float>((size_t)R);
+  AddWs w;
+  carve_add(b, G * L, D, Q, w);
   return b.off + 1024;
 }
 
 int nrl_additive_fwd(const float* x, long long G, int L, int D, int Q, const float* weight,
                      const float* bias, const float* query, float* out, void* ws,
                      size_t ws_bytes, int precision, void* stream) {
-  if (!x || !weight || !bias || !query || !out || G <= 0 || L <= 0 || D <= 0 || Q <= 0 || Q > 256)
-    return fail(NRL_ERR_INVALID_ARG, "nrl_additive_fwd: bad argument");
+  if (!x || !weight || !bias || !query || !out || G <= 0 || L <= 0 || D <= 0 || Q <= 0 || Q > 256 || (D & 3))
+    return fail(NRL_ERR_INVALID_ARG, "nrl_additive_fwd: bad argument (need Q <= 256, D %% 4 == 0)");
   TRY(device_init());
   TRY(check_common(ws, ws_bytes, nrl_additive_ws_bytes(G, L, D, Q)));
   Ctx c{static_cast<cudaStream_t>(stream), precision};
   const long long R = G * L;
   const int Dp = round_up(D + 1, 16), Qp = round_up(Q, 16);
   Bump b(ws);
-  bf16* wf = b.take<bf16>(2ull * Q * Dp);
-  bf16* wt = b.take<bf16>(2ull * D * Qp);
-  bf16* xp = b.take<bf16>(2ull * R * Dp);
-  float* a = b.take<float>((size_t)R * Q);
-  float* s = b.take<float>((size_t)R);
-  float* wgt = b.take<float>((size_t)R);
+  AddWs w;
+  carve_add(b, R, D, Q, w);
   const int tp = c.two_planes() ? 1 : 0;
   pack_weight_kernel<<<grid_for((long long)Q * Dp + (long long)D * Qp, 256, 4096), 256, 0, c.stream>>>(
-      weight, bias, Q, D, Dp, Qp, wf, wt, tp);
+      weight, bias, Q, D, Dp, Qp, w.wf, w.wt, tp);
   LAUNCH_CHECK("pack_weight(additive)");
   dense_scatter_kernel<<<grid_for(R, 1, 1 << 20), 128, 0, c.stream>>>(
-      x, nullptr, (int)R, 1, D, Dp, nullptr, xp, tp ? xp + R * Dp : nullptr);
+      x, nullptr, (int)R, 1, D, Dp, nullptr, w.xp, tp ? w.xp + R * Dp : nullptr);
   LAUNCH_CHECK("split_rows");
   GemmEpi e = epi_none();
-  e.qvec = query; e.score = s;
+  e.qvec = query; e.score = w.s;
   Sinks sk;
-  sk.f32 = a; sk.ld_f32 = Q; sk.f32_cols = Q;
-  TRY(gemm_nt(c, xp, R, Dp, wf, Q, Dp, Dp, e, sk, "gemm additive"));
-  pool_fwd_kernel<<<grid_for(G, 1, 1 << 20), 128, L * sizeof(float), c.stream>>>(s, x, D, L, G, wgt, out);
+  sk.f32 = w.a; sk.ld_f32 = Q; sk.f32_cols = Q;
+  TRY(gemm_nt(c, w.xp, R, Dp, w.wf, Q, Dp, Dp, e, sk, "gemm additive"));
+  pool_fwd_kernel<<<grid_for(G, 1, 1 << 20), 128, L * sizeof(float), c.stream>>>(w.s, x, D, L, G, w.w, out);
   LAUNCH_CHECK("pool_fwd");
+  return NRL_OK;
+}
+
+int nrl_additive_bwd(const float* x, long long G, int L, int D, int Q, const float* weight,
+                     const float* query, const float* d_out, float* dx, float* g_weight,
+                     float* g_bias, float* g_query, void* ws, size_t ws_bytes, int precision,
+                     void* stream) {
+  if (!x || !weight || !query || !d_out || !dx || !g_weight || !g_bias || !g_query || G <= 0 || L <= 0 ||
+      D <= 0 || Q <= 0 || Q > 256 || (D & 3))
+    return fail(NRL_ERR_INVALID_ARG, "nrl_additive_bwd: bad argument");
+  (void)weight;
+  TRY(device_init());
+  TRY(check_common(ws, ws_bytes, nrl_additive_ws_bytes(G, L, D, Q)));
+  Ctx c{static_cast<cudaStream_t>(stream), precision};
+  const long long R = G * L;
+  const int Dp = round_up(D + 1, 16), Qp = round_up(Q, 16);
+  Bump b(ws);
+  AddWs w;
+  carve_add(b, R, D, Q, w);
+  const int tp = c.two_planes() ? 1 : 0;
+  pool_bwd_kernel<<<grid_for(G, 1, 8 * g_dev.sm_count), 256, L * sizeof(float), c.stream>>>(
+      d_out, x, w.w, w.a, query, D, Q, Qp, L, G, nullptr, w.dap, tp ? w.dap + R * Qp : nullptr, g_query, g_bias);
+  LAUNCH_CHECK("pool_bwd");
+  {  // dX = w_r * dOut[g] + dApre W
+    GemmEpi e = epi_none();
+    e.add_w = w.w; e.add_vec = d_out; e.ld_addvec = D; e.add_L = L;
+    Sinks sk;
+    sk.f32 = dx; sk.ld_f32 = D; sk.f32_cols = D;
+    TRY(gemm_nt(c, w.dap, R, Qp, w.wt, D, Qp, Qp, e, sk, "gemm additive dgrad"));
+  }
+  TRY(gemm_tn(c, w.dap, Q, Qp, w.xp, Dp, Dp, R, g_weight, D, D, nullptr, "gemm additive wgrad"));
   return NRL_OK;
 }
 
@@ -1123,6 +1200,265 @@ int nrl_nrms_step_host(const long long* hist_ids_host, const long long* cand_ids
   if (loss_host)
     CUDA_TRY(cudaMemcpyAsync(loss_host, w.loss_dev, sizeof(float), cudaMemcpyDeviceToHost, c.stream));
   CUDA_TRY(cudaStreamSynchronize(c.stream));
+  return NRL_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// NAML: CNN text encoder (text.py:163-176) and category encoder (category.py:73-82)
+// ----------------------------------------------------------------------------------------
+struct CnnDims {
+  int E, F, W, Q, Kc, Kp, Fp, Qp, MW0, MW1;
+};
+static int make_cnn_dims(nrl_cnn_dims d, CnnDims& o) {
+  if (d.embed_dim <= 0 || d.num_filters <= 0 || d.window <= 0 || d.query_dim <= 0)
+    return fail(NRL_ERR_INVALID_ARG, "bad CNN dims E=%d F=%d w=%d Q=%d", d.embed_dim, d.num_filters, d.window,
+                d.query_dim);
+  if (!(d.window & 1)) return fail(NRL_ERR_UNSUPPORTED, "even conv window %d not built (output length != L)", d.window);
+  if ((d.embed_dim & 3) || (d.num_filters & 3))
+    return fail(NRL_ERR_UNSUPPORTED, "embed_dim and num_filters must be multiples of 4");
+  if (d.query_dim > 256) return fail(NRL_ERR_UNSUPPORTED, "query_dim %d > 256", d.query_dim);
+  o.E = d.embed_dim; o.F = d.num_filters; o.W = d.window; o.Q = d.query_dim;
+  o.Kc = o.W * o.E;
+  o.Kp = round_up(o.Kc + 1, 16);
+  o.Fp = round_up(o.F + 1, 16);
+  o.Qp = round_up(o.Q, 16);
+  o.MW0 = (o.E + 31) / 32;
+  o.MW1 = (o.F + 31) / 32;
+  return NRL_OK;
+}
+struct CnnWs {
+  bf16 *wconv_f, *wconv_t, *wadd_f, *wadd_t;
+  bf16* A;    // [2][R][Kp]  im2col of the gathered (dropped-out) rows, ones column at w*E
+  float* y;   // [R][F]      relu(conv) after dropout site 1
+  bf16* yp;   // [2][R][Fp]
+  float* a;   // [R][Q]
+  float *s, *w;
+  bf16* dap;  // [2][R][Qp]
+  bf16* dyp;  // [2][R][Fp]
+  float* dA;  // [R][Kc]
+  uint32_t *mask0, *mask1;
+};
+static void carve_cnn(Bump& b, long long R, const CnnDims& d, CnnWs& w) {
+  w.wconv_f = b.take<bf16>(2ull * d.F * d.Kp);
+  w.wconv_t = b.take<bf16>(2ull * d.Kc * d.Fp);
+  w.wadd_f = b.take<bf16>(2ull * d.Q * d.Fp);
+  w.wadd_t = b.take<bf16>(2ull * d.F * d.Qp);
+  w.A = b.take<bf16>(2ull * R * d.Kp);
+  w.y = b.take<float>((size_t)R * d.F);
+  w.yp = b.take<bf16>(2ull * R * d.Fp);
+  w.a = b.take<float>((size_t)R * d.Q);
+  w.s = b.take<float>((size_t)R);
+  w.w = b.take<float>((size_t)R);
+  w.dap = b.take<bf16>(2ull * R * d.Qp);
+  w.dyp = b.take<bf16>(2ull * R * d.Fp);
+  w.dA = b.take<float>((size_t)R * d.Kc);
+  w.mask0 = b.take<uint32_t>((size_t)R * d.MW0);
+  w.mask1 = b.take<uint32_t>((size_t)R * d.MW1);
+}
+
+size_t nrl_cnn_encoder_ws_bytes(long long n_news, int L, nrl_cnn_dims dims) {
+  CnnDims d;
+  if (make_cnn_dims(dims, d) != NRL_OK || n_news <= 0 || L <= 0) return 0;
+  Bump b(nullptr);
+  CnnWs w;
+  carve_cnn(b, n_news * L, d, w);
+  return b.off + 1024;
+}
+
+int nrl_cnn_encoder_fwd(const long long* ids, long long n_news, int L, const float* table,
+                        long long V1, const nrl_cnn_params* prm, nrl_cnn_dims dims,
+                        float dropout_p, int training, unsigned long long seed, float* out,
+                        void* ws, size_t ws_bytes, int precision, void* stream) {
+  CnnDims d;
+  TRY(make_cnn_dims(dims, d));
+  if (!ids || !table || !prm || !out || n_news <= 0 || L <= 0 || V1 <= 0)
+    return fail(NRL_ERR_INVALID_ARG, "nrl_cnn_encoder_fwd: null pointer or empty input");
+  if (dropout_p < 0.f || dropout_p >= 1.f) return fail(NRL_ERR_INVALID_ARG, "dropout_p out of [0,1)");
+  TRY(device_init());
+  TRY(check_common(ws, ws_bytes, nrl_cnn_encoder_ws_bytes(n_news, L, dims)));
+  Ctx c{static_cast<cudaStream_t>(stream), precision};
+  const long long R = n_news * L;
+  Bump b(ws);
+  CnnWs w;
+  carve_cnn(b, R, d, w);
+  const int tp = c.two_planes() ? 1 : 0;
+  const DropCfg drop = make_drop(dropout_p, training, seed);
+  pack_weight_kernel<<<grid_for((long long)d.F * d.Kp + (long long)d.Kc * d.Fp, 256, 4096), 256, 0, c.stream>>>(
+      prm->cnn_weight, prm->cnn_bias, d.F, d.Kc, d.Kp, d.Fp, w.wconv_f, w.wconv_t, tp);
+  LAUNCH_CHECK("pack_weight(conv)");
+  pack_weight_kernel<<<grid_for((long long)d.Q * d.Fp + (long long)d.F * d.Qp, 256, 4096), 256, 0, c.stream>>>(
+      prm->add_weight, prm->add_bias, d.Q, d.F, d.Fp, d.Qp, w.wadd_f, w.wadd_t, tp);
+  LAUNCH_CHECK("pack_weight(additive)");
+  if (drop.on) {
+    dropout_site_words_kernel<<<grid_for(R * d.MW0, 256, 16 * g_dev.sm_count), 256, 0, c.stream>>>(
+        drop.seed, 0u, drop.thr, R, d.E, d.MW0, w.mask0);
+    LAUNCH_CHECK("dropout_words(0)");
+    dropout_site_words_kernel<<<grid_for(R * d.MW1, 256, 16 * g_dev.sm_count), 256, 0, c.stream>>>(
+        drop.seed, 1u, drop.thr, R, d.F, d.MW1, w.mask1);
+    LAUNCH_CHECK("dropout_words(1)");
+  }
+  gather_im2col_kernel<<<grid_for(R, 8, 1 << 20), 256, 0, c.stream>>>(
+      ids, n_news, L, table, d.E, d.W, d.Kp, w.A, tp ? w.A + R * d.Kp : nullptr,
+      drop.on ? w.mask0 : nullptr, d.MW0, drop.scale);
+  LAUNCH_CHECK("gather_im2col");
+  {  // Y = dropout1(relu(A Wc^T + bc)): fp32 + split planes (ones column at F)
+    GemmEpi e = epi_none();
+    e.relu = 1;
+    epi_dropout(e, drop, w.mask1, d.MW1);
+    Sinks sk;
+    sk.f32 = w.y; sk.ld_f32 = d.F; sk.f32_cols = d.F;
+    sk.sp = w.yp; sk.ld_sp = d.Fp; sk.sp_cols = d.Fp; sk.ones_col = d.F;
+    TRY(gemm_nt(c, w.A, R, d.Kp, w.wconv_f, d.F, d.Kp, d.Kp, e, sk, "gemm conv"));
+  }
+  {
+    GemmEpi e = epi_none();
+    e.qvec = prm->add_query; e.score = w.s;
+    Sinks sk;
+    sk.f32 = w.a; sk.ld_f32 = d.Q; sk.f32_cols = d.Q;
+    TRY(gemm_nt(c, w.yp, R, d.Fp, w.wadd_f, d.Q, d.Fp, d.Fp, e, sk, "gemm additive"));
+  }
+  pool_fwd_kernel<<<grid_for(n_news, 1, 1 << 20), 128, L * sizeof(float), c.stream>>>(w.s, w.y, d.F, L, n_news,
+                                                                                       w.w, out);
+  LAUNCH_CHECK("pool_fwd");
+  return NRL_OK;
+}
+
+int nrl_cnn_encoder_bwd(const long long* ids, long long n_news, int L, long long V1,
+                        const nrl_cnn_params* prm, nrl_cnn_dims dims, float dropout_p,
+                        int training, unsigned long long seed, const float* d_out,
+                        nrl_cnn_grads* g, float* d_table, void* ws, size_t ws_bytes,
+                        int precision, void* stream) {
+  CnnDims d;
+  TRY(make_cnn_dims(dims, d));
+  if (!ids || !prm || !d_out || !g || n_news <= 0 || L <= 0)
+    return fail(NRL_ERR_INVALID_ARG, "nrl_cnn_encoder_bwd: null pointer or empty input");
+  (void)V1;
+  TRY(device_init());
+  TRY(check_common(ws, ws_bytes, nrl_cnn_encoder_ws_bytes(n_news, L, dims)));
+  Ctx c{static_cast<cudaStream_t>(stream), precision};
+  const long long R = n_news * L;
+  Bump b(ws);
+  CnnWs w;
+  carve_cnn(b, R, d, w);
+  const int tp = c.two_planes() ? 1 : 0;
+  const DropCfg drop = make_drop(dropout_p, training, seed);
+  pool_bwd_kernel<<<grid_for(n_news, 1, 8 * g_dev.sm_count), 256, L * sizeof(float), c.stream>>>(
+      d_out, w.y, w.w, w.a, prm->add_query, d.F, d.Q, d.Qp, L, n_news, nullptr, w.dap,
+      tp ? w.dap + R * d.Qp : nullptr, g->add_query, g->add_bias);
+  LAUNCH_CHECK("pool_bwd");
+  {  // dPre = relu'(.) dropout1'( w_r dVec + dApre W_add )  -> split planes
+    GemmEpi e = epi_none();
+    e.add_w = w.w; e.add_vec = d_out; e.ld_addvec = d.F; e.add_L = L;
+    epi_dropout(e, drop, w.mask1, d.MW1);
+    e.pos_mask = w.y; e.ld_pos = d.F;
+    Sinks sk;
+    sk.sp = w.dyp; sk.ld_sp = d.Fp; sk.sp_cols = d.Fp; sk.ones_col = -1;
+    TRY(gemm_nt(c, w.dap, R, d.Qp, w.wadd_t, d.F, d.Qp, d.Qp, e, sk, "gemm additive dgrad"));
+  }
+  TRY(gemm_tn(c, w.dap, d.Q, d.Qp, w.yp, d.Fp, d.Fp, R, g->add_weight, d.F, d.F, nullptr,
+              "gemm additive wgrad"));
+  // dWc [F][w*E], dbc [F] (the ones column of the im2col operand)
+  TRY(gemm_tn(c, w.dyp, d.F, d.Fp, w.A, d.Kp, d.Kp, R, g->cnn_weight, d.Kc, d.Kc, g->cnn_bias,
+              "gemm conv wgrad"));
+  if (d_table) {
+    GemmEpi e = epi_none();
+    Sinks sk;
+    sk.f32 = w.dA; sk.ld_f32 = d.Kc; sk.f32_cols = d.Kc;
+    TRY(gemm_nt(c, w.dyp, R, d.Fp, w.wconv_t, d.Kc, d.Fp, d.Fp, e, sk, "gemm conv dgrad"));
+    col2im_emb_grad_kernel<<<grid_for(R, 8, 1 << 20), 256, 0, c.stream>>>(
+        ids, n_news, L, w.dA, d.Kc, d.E, d.W, drop.on ? w.mask0 : nullptr, d.MW0, drop.scale, d_table);
+    LAUNCH_CHECK("col2im_emb_grad");
+  }
+  return NRL_OK;
+}
+
+struct LinWs {
+  bf16 *wf, *wt, *x, *dpre;
+  float* dx;
+  uint32_t* mask0;
+};
+static void carve_lin(Bump& b, long long n, int CE, int O, LinWs& w) {
+  const int Ep = round_up(CE + 1, 16), Op = round_up(O, 16), MW = (CE + 31) / 32;
+  w.wf = b.take<bf16>(2ull * O * Ep);
+  w.wt = b.take<bf16>(2ull * CE * Op);
+  w.x = b.take<bf16>(2ull * n * Ep);
+  w.dpre = b.take<bf16>(2ull * n * Op);
+  w.dx = b.take<float>((size_t)n * CE);
+  w.mask0 = b.take<uint32_t>((size_t)n * MW);
+}
+size_t nrl_linear_encoder_ws_bytes(long long n, int embed_dim, int out_dim) {
+  if (n <= 0 || embed_dim <= 0 || out_dim <= 0) return 0;
+  Bump b(nullptr);
+  LinWs w;
+  carve_lin(b, n, embed_dim, out_dim, w);
+  return b.off + 1024;
+}
+
+int nrl_linear_encoder_fwd(const long long* ids, long long n, const float* table, long long V1,
+                           int CE, const float* weight, const float* bias, int O, float dropout_p,
+                           int training, unsigned long long seed, float* out, void* ws,
+                           size_t ws_bytes, int precision, void* stream) {
+  if (!ids || !table || !weight || !bias || !out || n <= 0 || V1 <= 0 || CE <= 0 || O <= 0 || (CE & 3) || (O & 3))
+    return fail(NRL_ERR_INVALID_ARG, "nrl_linear_encoder_fwd: bad argument (embed_dim, out_dim must be multiples of 4)");
+  if (dropout_p < 0.f || dropout_p >= 1.f) return fail(NRL_ERR_INVALID_ARG, "dropout_p out of [0,1)");
+  TRY(device_init());
+  TRY(check_common(ws, ws_bytes, nrl_linear_encoder_ws_bytes(n, CE, O)));
+  Ctx c{static_cast<cudaStream_t>(stream), precision};
+  Bump b(ws);
+  LinWs w;
+  carve_lin(b, n, CE, O, w);
+  const int tp = c.two_planes() ? 1 : 0;
+  const int Ep = round_up(CE + 1, 16), Op = round_up(O, 16), MW = (CE + 31) / 32;
+  const DropCfg drop = make_drop(dropout_p, training, seed);
+  pack_weight_kernel<<<grid_for((long long)O * Ep + (long long)CE * Op, 256, 4096), 256, 0, c.stream>>>(
+      weight, bias, O, CE, Ep, Op, w.wf, w.wt, tp);
+  LAUNCH_CHECK("pack_weight(linear)");
+  if (drop.on) {
+    dropout_site_words_kernel<<<grid_for(n * MW, 256, 16 * g_dev.sm_count), 256, 0, c.stream>>>(
+        drop.seed, 0u, drop.thr, n, CE, MW, w.mask0);
+    LAUNCH_CHECK("dropout_words(0)");
+  }
+  gather_split_kernel<<<grid_for(n, 8, 1 << 20), 256, 0, c.stream>>>(
+      ids, n, table, CE, Ep, w.x, tp ? w.x + n * Ep : nullptr, nullptr, drop.on ? w.mask0 : nullptr, MW,
+      drop.scale);
+  LAUNCH_CHECK("gather_split");
+  GemmEpi e = epi_none();
+  e.relu = 1;
+  Sinks sk;
+  sk.f32 = out; sk.ld_f32 = O; sk.f32_cols = O;
+  return gemm_nt(c, w.x, n, Ep, w.wf, O, Ep, Ep, e, sk, "gemm linear");
+}
+
+int nrl_linear_encoder_bwd(const long long* ids, long long n, long long V1, int CE,
+                           const float* weight, int O, float dropout_p, int training,
+                           unsigned long long seed, const float* out, const float* d_out,
+                           float* g_weight, float* g_bias, float* d_table, void* ws,
+                           size_t ws_bytes, int precision, void* stream) {
+  if (!ids || !weight || !out || !d_out || !g_weight || !g_bias || n <= 0 || CE <= 0 || O <= 0 || (CE & 3) || (O & 3))
+    return fail(NRL_ERR_INVALID_ARG, "nrl_linear_encoder_bwd: bad argument");
+  (void)V1;
+  TRY(device_init());
+  TRY(check_common(ws, ws_bytes, nrl_linear_encoder_ws_bytes(n, CE, O)));
+  Ctx c{static_cast<cudaStream_t>(stream), precision};
+  Bump b(ws);
+  LinWs w;
+  carve_lin(b, n, CE, O, w);
+  const int tp = c.two_planes() ? 1 : 0;
+  const int Ep = round_up(CE + 1, 16), Op = round_up(O, 16), MW = (CE + 31) / 32;
+  const DropCfg drop = make_drop(dropout_p, training, seed);
+  relu_bwd_split_kernel<<<grid_for(n * Op, 256, 8 * g_dev.sm_count), 256, 0, c.stream>>>(
+      d_out, out, n, O, Op, w.dpre, tp ? w.dpre + n * Op : nullptr);
+  LAUNCH_CHECK("relu_bwd_split");
+  TRY(gemm_tn(c, w.dpre, O, Op, w.x, Ep, Ep, n, g_weight, CE, CE, g_bias, "gemm linear wgrad"));
+  if (d_table) {
+    GemmEpi e = epi_none();
+    epi_dropout(e, drop, w.mask0, MW);
+    Sinks sk;
+    sk.f32 = w.dx; sk.ld_f32 = CE; sk.f32_cols = CE;
+    TRY(gemm_nt(c, w.dpre, n, Op, w.wt, CE, Op, Op, e, sk, "gemm linear dgrad"));
+    emb_grad_kernel<<<grid_for(n, 8, 1 << 20), 256, 0, c.stream>>>(ids, n, w.dx, CE, d_table);
+    LAUNCH_CHECK("emb_grad");
+  }
   return NRL_OK;
 }
 

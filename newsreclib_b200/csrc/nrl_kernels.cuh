@@ -137,18 +137,22 @@ __global__ void gather_split_kernel(const long long* __restrict__ ids, long long
 // with an online softmax.  Writes O as split planes (+ ones column / zero pad) and the row
 // log-sum-exp for the backward pass.
 // ------------------------------------------------------------------------------------
+// warps per CTA of the streaming attention kernels (static smem = 2 * NW * 32 * DH floats <= 48 KB)
+__host__ __device__ constexpr int attn_stream_warps(int dh) { return dh <= 32 ? 4 : 2; }
+
 template <int DH>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(32 * attn_stream_warps(DH))
 attn_fwd_kernel(const float* __restrict__ qkv, int E, int heads, int S, long long seq_stride,
                 int NB, long long batch_stride, float scale, __nv_bfloat16* __restrict__ o_hi,
                 __nv_bfloat16* __restrict__ o_lo, int ep, float* __restrict__ lse) {
-  __shared__ __align__(16) float sk[4][32 * DH];
-  __shared__ __align__(16) float sv[4][32 * DH];
+  __shared__ __align__(16) float sk[attn_stream_warps(DH)][32 * DH];
+  __shared__ __align__(16) float sv[attn_stream_warps(DH)][32 * DH];
+  constexpr int NW = attn_stream_warps(DH);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qchunks = (S + 31) / 32;
   const long long items = (long long)NB * heads * qchunks;
   const int ld = 3 * E;
-  for (long long it = blockIdx.x * 4ll + warp; it < items; it += gridDim.x * 4ll) {
+  for (long long it = blockIdx.x * (long long)NW + warp; it < items; it += gridDim.x * (long long)NW) {
     const int qc = (int)(it % qchunks);
     const int h = (int)((it / qchunks) % heads);
     const int b = (int)(it / ((long long)qchunks * heads));
@@ -236,17 +240,18 @@ attn_fwd_kernel(const float* __restrict__ qkv, int E, int heads, int S, long lon
 // phase B (lane = key) gives dK / dV; P is recomputed from Q, K and the saved log-sum-exp,
 // D = rowsum(dO * O) from the saved O planes.  Writes dQKV as split planes [2][R][p3].
 template <int DH>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(32 * attn_stream_warps(DH))
 attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o, long long ld_do,
                 const __nv_bfloat16* __restrict__ o_hi, const __nv_bfloat16* __restrict__ o_lo,
                 int ep, const float* __restrict__ lse, int E, int heads, int S,
                 long long seq_stride, int NB, long long batch_stride, float scale,
                 __nv_bfloat16* __restrict__ g_hi, __nv_bfloat16* __restrict__ g_lo, int p3) {
   // per-warp staging: "x" rows (k/v in phase A, q/dO in phase B), plus lse / D per row
-  __shared__ __align__(16) float sa[4][32 * DH];
-  __shared__ __align__(16) float sb[4][32 * DH];
-  __shared__ float s_lse[4][32];
-  __shared__ float s_dd[4][32];
+  __shared__ __align__(16) float sa[attn_stream_warps(DH)][32 * DH];
+  __shared__ __align__(16) float sb[attn_stream_warps(DH)][32 * DH];
+  __shared__ float s_lse[attn_stream_warps(DH)][32];
+  __shared__ float s_dd[attn_stream_warps(DH)][32];
+  constexpr int NW = attn_stream_warps(DH);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long items = (long long)NB * heads;
   const int ld = 3 * E;
@@ -263,7 +268,7 @@ attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o, lo
         *reinterpret_cast<uint2*>(g_lo + off + d) = make_uint2(pack_bf16x2(ll[0], ll[1]), pack_bf16x2(ll[2], ll[3]));
     }
   };
-  for (long long it = blockIdx.x * 4ll + warp; it < items; it += gridDim.x * 4ll) {
+  for (long long it = blockIdx.x * (long long)NW + warp; it < items; it += gridDim.x * (long long)NW) {
     const int h = (int)(it % heads);
     const int b = (int)(it / heads);
     // ---------------- phase A: lane = query, loop over key chunks -> dQ ----------------

@@ -1,7 +1,9 @@
 """``NewsEncoder`` with the reference's 11 constructor kwargs
 (``newsreclib/models/components/encoders/news/news.py:38-51``).  The NRMS configuration
-(one text attribute, ``combine_vectors=False``) returns the single text vector; multi-view
-combination by additive attention (NAML) is supported for inference."""
+(one text attribute, ``combine_vectors=False``) returns the single text vector; the NAML
+configuration stacks the title / abstract / category views and combines them with the
+sm_100a ``AdditiveAttention`` (``news.py:162-163``), forward and backward.  ``torch.stack`` of the
+``[N, D]`` view vectors is the only ATen op in between (a 3 x N x D copy, as in the reference)."""
 from typing import Dict, List, Optional
 
 import torch

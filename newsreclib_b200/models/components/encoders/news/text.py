@@ -1,4 +1,5 @@
-"""Text encoders of the hot path.  ``MHSAAddAtt`` keeps the reference's constructor, attribute
+"""Text encoders of the hot path (``MHSAAddAtt`` for NRMS, ``CNNAddAtt`` for NAML, ``PLM`` =
+HF transformer + the sm_100a head).  ``MHSAAddAtt`` keeps the reference's constructor, attribute
 names and ``state_dict`` keys (``newsreclib/models/components/encoders/news/text.py:179-236``):
 stock ``nn.Embedding`` / ``nn.MultiheadAttention`` / ``AdditiveAttention`` / ``nn.Dropout``
 sub-modules are the PARAMETER CONTAINERS (so checkpoints, seeded initial weights, optimizer
@@ -36,3 +37,91 @@ class MHSAAddAtt(nn.Module):
             text.contiguous(), self.embedding_layer.weight, mha.in_proj_weight, mha.in_proj_bias,
             mha.out_proj.weight, mha.out_proj.bias, add.linear.weight, add.linear.bias, add.query,
             self.num_heads, float(self.dropout.p), training, seed, self.precision)
+
+
+class CNNAddAtt(nn.Module):
+    """NAML text encoder (reference ``text.py:112-176``): same constructor, attribute names
+    (``embedding_layer``, ``cnn``, ``additive_attention``, ``dropout``) and ``state_dict`` keys.
+    forward = gather -> dropout -> Conv2d(1, F, (w, E), pad ((w-1)/2, 0)) as ONE K = w*E tcgen05 GEMM
+    over an im2col of the gathered rows -> ReLU -> dropout -> additive pooling."""
+
+    def __init__(self, pretrained_embeddings: torch.Tensor, embed_dim: int, num_filters: int, window_size: int,
+                 query_dim: int, dropout_probability: float) -> None:
+        super().__init__()
+        if not isinstance(dropout_probability, float):
+            raise ValueError(
+                f"Expected keyword argument `dropout_probability` to be a `float` but got {dropout_probability}")
+        self.embedding_layer = nn.Embedding.from_pretrained(
+            torch.as_tensor(pretrained_embeddings, dtype=torch.float32), freeze=False, padding_idx=0)
+        self.cnn = nn.Conv2d(in_channels=1, out_channels=num_filters, kernel_size=(window_size, embed_dim),
+                             padding=(int((window_size - 1) / 2), 0))
+        self.additive_attention = AdditiveAttention(input_dim=num_filters, query_dim=query_dim)
+        self.dropout = nn.Dropout(dropout_probability)
+        self.window_size = window_size
+        self.precision = ops.PREC_BF16X3
+
+    def forward(self, text: torch.Tensor) -> torch.Tensor:
+        """text: int64 ``[N, L]`` -> ``[N, num_filters]``."""
+        add = self.additive_attention
+        training = self.training and self.dropout.p > 0
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if training else 0
+        return ops.CnnEncoderFn.apply(
+            text.contiguous(), self.embedding_layer.weight, self.cnn.weight, self.cnn.bias, add.linear.weight,
+            add.linear.bias, add.query, self.window_size, float(self.dropout.p), training, seed, self.precision)
+
+
+class PLM(nn.Module):
+    """PLM text encoder (reference ``text.py:15-109``), ``use_mhsa=True`` form used by NRMS-PLM /
+    NAML-PLM: the HF transformer (third-party, stays on torch) followed by the
+    sm_100a head -- dropout -> MHSA over dim 0 of ``[N, T, E]`` (the reference passes batch-first
+    states to a ``batch_first=False`` attention, ``text.py:96``, so attention runs across the N news
+    of the call at each token position; ``attention_axis="tokens"`` attends along the tokens
+    instead) -> dropout -> additive pooling over the T tokens (pad tokens included)."""
+
+    def __init__(self, plm_model, frozen_layers, embed_dim: int, use_mhsa: bool, apply_reduce_dim: bool,
+                 reduced_embed_dim, num_heads, query_dim, dropout_probability: float,
+                 attention_axis: str = "reference") -> None:
+        super().__init__()
+        if not isinstance(plm_model, (str, nn.Module)):
+            raise ValueError(f"Expected keyword argument `plm_model` to be a `str` but got {plm_model}")
+        if not isinstance(dropout_probability, float):
+            raise ValueError(
+                f"Expected keyword argument `dropout_probability` to be a `float` but got {dropout_probability}")
+        if attention_axis not in ("reference", "tokens"):
+            raise ValueError(f"attention_axis must be 'reference' or 'tokens', got {attention_axis}")
+        self.use_mhsa = use_mhsa
+        self.apply_reduce_dim = apply_reduce_dim
+        if isinstance(plm_model, nn.Module):  # an already-built transformer (tests, offline images)
+            self.plm_model = plm_model
+        else:
+            from transformers import AutoModel
+            self.plm_model = AutoModel.from_pretrained(plm_model)
+        for name, param in self.plm_model.base_model.named_parameters():  # text.py:70-73
+            for layer in (frozen_layers or []):
+                if "layer." + str(layer) + "." in name:
+                    param.requires_grad = False
+        if self.use_mhsa:
+            assert isinstance(num_heads, int) and num_heads > 0
+            self.multihead_attention = nn.MultiheadAttention(embed_dim=embed_dim, num_heads=num_heads)
+            self.additive_attention = AdditiveAttention(input_dim=embed_dim, query_dim=query_dim)
+            self.dropout = nn.Dropout(p=dropout_probability)
+        if self.apply_reduce_dim:
+            raise NotImplementedError("apply_reduce_dim (MANNeR / MINER configurations) is outside the NRMS/NAML path")
+        self.num_heads = num_heads
+        self.attention_axis = attention_axis
+        self.precision = ops.PREC_BF16X3
+
+    def head(self, states: torch.Tensor) -> torch.Tensor:
+        """``[N, T, E]`` last hidden states -> ``[N, E]`` on the sm_100a path."""
+        mha, add = self.multihead_attention, self.additive_attention
+        training = self.training and self.dropout.p > 0
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if training else 0
+        return ops.PlmHeadFn.apply(
+            states.float(), mha.in_proj_weight, mha.in_proj_bias, mha.out_proj.weight, mha.out_proj.bias,
+            add.linear.weight, add.linear.bias, add.query, self.num_heads,
+            0 if self.attention_axis == "reference" else 1, float(self.dropout.p), training, seed, self.precision)
+
+    def forward(self, text) -> torch.Tensor:
+        if self.use_mhsa:
+            return self.head(self.plm_model(**text)[0])
+        return self.plm_model(**text).last_hidden_state[:, 0, :]

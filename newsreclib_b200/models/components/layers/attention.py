@@ -1,8 +1,10 @@
 """``AdditiveAttention`` with the reference's constructor, parameters and ``state_dict`` keys
-(``newsreclib/models/components/layers/attention.py:6-42``); forward runs the sm_100a path
-(tcgen05 projection with the tanh / query-dot fused in the epilogue, then the softmax pooling
-kernel).  Forward-only as a standalone module (NAML inference); inside the NRMS blocks the
-same math is differentiated by the fused encoder kernels."""
+(``newsreclib/models/components/layers/attention.py:6-42``); forward and backward run the
+sm_100a path (tcgen05 projection with the tanh / query-dot fused in the epilogue, softmax
+pooling kernel; backward through softmax, query dot and tanh + the two gradient GEMMs).
+Used standalone by the NAML view combiner (``encoders/news/news.py:162-163``) and the NAML user
+encoder (``encoders/user/naml.py:27-31``); inside the NRMS blocks the same math is part of the
+fused encoder calls."""
 import torch
 import torch.nn as nn
 
@@ -22,10 +24,6 @@ class AdditiveAttention(nn.Module):
         self.precision = ops.PREC_BF16X3
 
     def forward(self, input_vector: torch.Tensor) -> torch.Tensor:
-        if torch.is_grad_enabled() and (input_vector.requires_grad or self.query.requires_grad):
-            if input_vector.requires_grad:
-                raise RuntimeError("standalone AdditiveAttention is forward-only on the sm_100a path; "
-                                   "wrap the call in torch.no_grad() (training uses the fused NRMS blocks)")
-        with torch.no_grad():
-            return ops.additive_attention(input_vector.float(), self.linear.weight, self.linear.bias,
-                                          self.query, self.precision)
+        """``[G, L, D]`` -> ``[G, D]``: softmax(tanh(xW^T + b) . q) over dim 1, weighted sum of x."""
+        return ops.AdditiveFn.apply(input_vector.float(), self.linear.weight, self.linear.bias, self.query,
+                                    self.precision)

@@ -1,0 +1,103 @@
+"""Shared body of the two-tower recommenders (NRMS, NAML): the reference's ``forward`` /
+``model_step`` / Lightning step hooks are line-for-line identical in ``nrms_module.py:230-535`` and
+``naml_module.py:261-566`` (``diff`` of everything from ``forward`` to EOF is empty), so they live
+once here.  ``forward`` = news encoder over history and candidates -> ragged->dense -> user encoder
+(or the late-fusion mean) -> dot-product scores; everything runs on the sm_100a path."""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import torch
+
+from ... import ops
+from ...data.components.batch import RecommendationBatch
+from ...metrics import ranking_metrics
+from ..abstract_recommender import AbstractRecommneder
+from ..components.layers.click_predictor import DotProduct
+
+
+class TwoTowerRecommender(AbstractRecommneder):
+    late_fusion: bool = False
+
+    # ------------------------------------------------------------------ layout helpers
+    @staticmethod
+    def _layout(batch: RecommendationBatch):
+        """Offsets and dense widths of the ragged batch.  One host sync for (B, Hmax, Cmax), the
+        same information ``to_dense_batch`` fetches with ``batch.max()`` / ``num.max()``."""
+        seg_h, seg_c = batch["batch_hist"], batch["batch_cand"]
+        B = int(batch["user_idx"].numel()) if "user_idx" in batch else int(seg_c[-1]) + 1
+        off_h, off_c = ops.segment_offsets(seg_h, B), ops.segment_offsets(seg_c, B)
+        widths = torch.stack([(off_h[1:] - off_h[:-1]).max(), (off_c[1:] - off_c[:-1]).max()]).tolist()
+        return B, off_h, off_c, int(widths[0]), int(widths[1])
+
+    # ------------------------------------------------------------------ forward (nrms_module.py:230-255)
+    def forward(self, batch: RecommendationBatch) -> torch.Tensor:
+        return self._forward_with_layout(batch, self._layout(batch))
+
+    def _forward_with_layout(self, batch, layout) -> torch.Tensor:
+        B, off_h, off_c, Hmax, Cmax = layout
+        hist_news_vector = self.news_encoder(batch["x_hist"])
+        cand_news_vector = self.news_encoder(batch["x_cand"])
+        if not self.late_fusion:
+            hist_agg = ops.ToDenseFn.apply(hist_news_vector, off_h, B, Hmax)
+            user_vector = self.user_encoder(hist_agg)
+        else:
+            user_vector = ops.LateFusionFn.apply(hist_news_vector, off_h, B)
+        return DotProduct.ragged(user_vector, cand_news_vector, off_c, B, Cmax)
+
+    # ------------------------------------------------------------------ model_step (nrms_module.py:260-362)
+    def model_step(self, batch: RecommendationBatch) -> Tuple[torch.Tensor, ...]:
+        layout = self._layout(batch)
+        B, off_h, off_c, Hmax, Cmax = layout
+        scores = self._forward_with_layout(batch, layout)
+        loss = ops.CESoftFn.apply(scores, batch["labels"].float().contiguous(), off_c)
+        cand_news_size = (off_c[1:] - off_c[:-1]).long()
+        hist_news_size = (off_h[1:] - off_h[:-1]).long()
+        mask_cand = torch.arange(Cmax, device=scores.device)[None, :] < cand_news_size[:, None]
+        preds = self._collect_model_outputs(scores, mask_cand)
+        targets = batch["labels"]                      # ragged order == masked dense order
+        target_categories = batch["x_cand"].get("category")
+        target_sentiments = batch["x_cand"].get("sentiment")
+        hist_categories = batch["x_hist"].get("category")
+        hist_sentiments = batch["x_hist"].get("sentiment")
+        return (loss, preds, targets, cand_news_size, hist_news_size, target_categories, target_sentiments,
+                hist_categories, hist_sentiments, batch["user_ids"] if "user_ids" in batch else None,
+                batch["x_cand"].get("news_ids"))
+
+    # ------------------------------------------------------------------ Lightning hooks
+    def training_step(self, batch: RecommendationBatch, batch_idx: int):
+        loss, preds, targets, cand_news_size, *_ = self.model_step(batch)
+        self.log("train/loss", loss, on_step=True, on_epoch=True, prog_bar=True)
+        self.training_step_outputs = self._collect_step_outputs(self.training_step_outputs, locals())
+        return loss
+
+    def _epoch_metrics(self, outputs, prefix: str) -> Dict[str, torch.Tensor]:
+        preds = self._gather_step_outputs(outputs, "preds")
+        targets = self._gather_step_outputs(outputs, "targets")
+        sizes = self._gather_step_outputs(outputs, "cand_news_size")
+        m = {prefix + k: v for k, v in ranking_metrics(preds, targets, sizes, self.top_k_list).items()}
+        self.log_dict(m, on_step=False, on_epoch=True, prog_bar=True, sync_dist=True)
+        self._clear_epoch_outputs(outputs)
+        return m
+
+    def on_train_epoch_end(self):
+        return self._epoch_metrics(self.training_step_outputs, "train/")
+
+    def validation_step(self, batch: RecommendationBatch, batch_idx: int):
+        loss, preds, targets, cand_news_size, *_ = self.model_step(batch)
+        self.log("val/loss", loss, on_step=False, on_epoch=True, prog_bar=True, sync_dist=True)
+        self.val_step_outputs = self._collect_step_outputs(self.val_step_outputs, locals())
+        return loss
+
+    def on_validation_epoch_end(self):
+        return self._epoch_metrics(self.val_step_outputs, "val/")
+
+    def test_step(self, batch: RecommendationBatch, batch_idx: int):
+        (loss, preds, targets, cand_news_size, hist_news_size, target_categories, target_sentiments,
+         hist_categories, hist_sentiments, user_ids, cand_news_ids) = self.model_step(batch)
+        self.log("test/loss", loss, on_step=False, on_epoch=True, prog_bar=True, sync_dist=True)
+        self.test_step_outputs = self._collect_step_outputs(self.test_step_outputs, locals())
+        return loss
+
+    def on_test_epoch_end(self):
+        return self._epoch_metrics(self.test_step_outputs, "test/")

@@ -13,7 +13,7 @@ from typing import Dict, Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import BlockParams, Dims, PREC_BF16, PREC_BF16X3  # noqa: F401
+from ._lib import BlockParams, CnnDims, CnnParams, Dims, PREC_BF16, PREC_BF16X3  # noqa: F401
 
 BLOCK_KEYS = (
     "multihead_attention.in_proj_weight",
@@ -269,6 +269,31 @@ class ToDenseFn(torch.autograd.Function):
         return dx, None, None, None
 
 
+class LateFusionFn(torch.autograd.Function):
+    """Late fusion (``nrms_module.py:243-248``): user = mean of the impression's clicked-news vectors."""
+
+    @staticmethod
+    def forward(ctx, hist_vec, off, B):
+        lib = _lib.load()
+        hist_vec = _chk(hist_vec.contiguous(), torch.float32, "hist_vec")
+        E = hist_vec.shape[1]
+        user = torch.empty(B, E, dtype=torch.float32, device=hist_vec.device)
+        _lib.check(lib.nrl_late_fusion_fwd(_p(hist_vec), _p(off), B, E, _p(user), _stream()), "nrl_late_fusion_fwd")
+        ctx.save_for_backward(off)
+        ctx.cfg = (B, E, hist_vec.shape[0])
+        return user
+
+    @staticmethod
+    def backward(ctx, d_user):
+        lib = _lib.load()
+        (off,) = ctx.saved_tensors
+        B, E, n = ctx.cfg
+        d_user = d_user.contiguous().float()
+        dx = torch.zeros(n, E, dtype=torch.float32, device=d_user.device)
+        _lib.check(lib.nrl_late_fusion_bwd(_p(d_user), _p(off), B, E, _p(dx), _stream()), "nrl_late_fusion_bwd")
+        return dx, None, None
+
+
 class ScoreFn(torch.autograd.Function):
     """``DotProduct.forward`` on ragged candidates (``layers/click_predictor.py:9-11``)."""
 
@@ -324,15 +349,165 @@ class CESoftFn(torch.autograd.Function):
         return d, None, None
 
 
+class AdditiveFn(torch.autograd.Function):
+    """``AdditiveAttention.forward`` (``layers/attention.py:24-42``): x ``[G, L, D]`` -> ``[G, D]``."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, query, precision):
+        lib = _lib.load()
+        x = _chk(x.contiguous(), torch.float32, "x")
+        G, L, D = x.shape
+        Q = query.numel()
+        out = torch.empty(G, D, dtype=torch.float32, device=x.device)
+        ws = workspace(lib.nrl_additive_ws_bytes(G, L, D, Q), x.device)
+        _lib.check(lib.nrl_additive_fwd(_p(x), G, L, D, Q, _p(_chk(weight, torch.float32, "weight")),
+                                        _p(_chk(bias, torch.float32, "bias")), _p(_chk(query, torch.float32, "query")),
+                                        _p(out), _p(ws), ws.numel(), precision, _stream()), "nrl_additive_fwd")
+        ctx.save_for_backward(x, weight, bias, query)
+        ctx.ws, ctx.precision = ws, precision
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        x, weight, bias, query = ctx.saved_tensors
+        G, L, D = x.shape
+        Q = query.numel()
+        d_out = d_out.contiguous().float()
+        dx = torch.empty_like(x)
+        gw, gb, gq = torch.zeros_like(weight), torch.zeros_like(bias), torch.zeros_like(query)
+        _lib.check(lib.nrl_additive_bwd(_p(x), G, L, D, Q, _p(weight), _p(query), _p(d_out), _p(dx), _p(gw),
+                                        _p(gb), _p(gq), _p(ctx.ws), ctx.ws.numel(), ctx.precision, _stream()),
+                   "nrl_additive_bwd")
+        ctx.ws = None
+        return dx, gw, gb, gq, None
+
+
 def additive_attention(x: torch.Tensor, weight, bias, query, precision: int = PREC_BF16X3) -> torch.Tensor:
-    """``AdditiveAttention.forward`` (``layers/attention.py:24-42``), forward only."""
-    lib = _lib.load()
-    x = _chk(x.contiguous(), torch.float32, "x")
-    G, L, D = x.shape
-    Q = query.numel()
-    out = torch.empty(G, D, dtype=torch.float32, device=x.device)
-    ws = workspace(lib.nrl_additive_ws_bytes(G, L, D, Q), x.device)
-    _lib.check(lib.nrl_additive_fwd(_p(x), G, L, D, Q, _p(_chk(weight, torch.float32, "weight")),
-                                    _p(_chk(bias, torch.float32, "bias")), _p(_chk(query, torch.float32, "query")),
-                                    _p(out), _p(ws), ws.numel(), precision, _stream()), "nrl_additive_fwd")
-    return out
+    return AdditiveFn.apply(x, weight, bias, query, precision)
+
+
+def cnn_struct(tensors) -> CnnParams:
+    s = CnnParams()
+    for (name, _), t in zip(CnnParams._fields_, tensors):
+        setattr(s, name, _p(_chk(t, torch.float32, name)))
+    return s
+
+
+class CnnEncoderFn(torch.autograd.Function):
+    """``CNNAddAtt.forward`` (reference ``encoders/news/text.py:163-176``)."""
+
+    @staticmethod
+    def forward(ctx, ids, table, cnn_w, cnn_b, w_add, b_add, q_add, window, dropout_p, training, seed, precision):
+        lib = _lib.load()
+        _chk(ids, torch.int64, "ids"); _chk(table, torch.float32, "embedding table")
+        n, L = ids.shape
+        F_ = cnn_w.shape[0]
+        dims = CnnDims(int(table.shape[1]), int(F_), int(window), int(q_add.numel()))
+        prm = [cnn_w, cnn_b, w_add, b_add, q_add]
+        need = lib.nrl_cnn_encoder_ws_bytes(n, L, dims)
+        if need == 0:
+            raise RuntimeError("nrl_cnn_encoder: unsupported dims (odd window, E % 4 == 0, F % 4 == 0, Q <= 256)")
+        out = torch.empty(n, F_, dtype=torch.float32, device=table.device)
+        ws = workspace(need, table.device)
+        ps = cnn_struct(prm)
+        _lib.check(lib.nrl_cnn_encoder_fwd(_p(ids), n, L, _p(table), table.shape[0], C.byref(ps), dims,
+                                           float(dropout_p), int(training), int(seed), _p(out), _p(ws),
+                                           ws.numel(), precision, _stream()), "nrl_cnn_encoder_fwd")
+        ctx.save_for_backward(ids, table, *prm)
+        ctx.ws, ctx.dims, ctx.cfg = ws, dims, (float(dropout_p), int(training), int(seed), precision)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        ids, table, *prm = ctx.saved_tensors
+        n, L = ids.shape
+        p, training, seed, precision = ctx.cfg
+        d_out = d_out.contiguous().float()
+        grads = [torch.zeros_like(t) for t in prm]
+        d_table = torch.zeros_like(table)
+        ps, gs = cnn_struct(prm), cnn_struct(grads)
+        _lib.check(lib.nrl_cnn_encoder_bwd(_p(ids), n, L, table.shape[0], C.byref(ps), ctx.dims, p, training, seed,
+                                           _p(d_out), C.byref(gs), _p(d_table), _p(ctx.ws), ctx.ws.numel(),
+                                           precision, _stream()), "nrl_cnn_encoder_bwd")
+        ctx.ws = None
+        return (None, d_table, *grads, None, None, None, None, None)
+
+
+class LinearEncoderFn(torch.autograd.Function):
+    """``LinearEncoder.forward`` with ``linear_transform=True`` (``encoders/news/category.py:73-82``)."""
+
+    @staticmethod
+    def forward(ctx, ids, table, weight, bias, dropout_p, training, seed, precision):
+        lib = _lib.load()
+        ids = _chk(ids.contiguous(), torch.int64, "ids").reshape(-1)
+        _chk(table, torch.float32, "category table")
+        n, CE, O = ids.numel(), table.shape[1], weight.shape[0]
+        out = torch.empty(n, O, dtype=torch.float32, device=table.device)
+        ws = workspace(lib.nrl_linear_encoder_ws_bytes(n, CE, O), table.device)
+        _lib.check(lib.nrl_linear_encoder_fwd(_p(ids), n, _p(table), table.shape[0], CE,
+                                              _p(_chk(weight, torch.float32, "weight")),
+                                              _p(_chk(bias, torch.float32, "bias")), O, float(dropout_p),
+                                              int(training), int(seed), _p(out), _p(ws), ws.numel(), precision,
+                                              _stream()), "nrl_linear_encoder_fwd")
+        ctx.save_for_backward(ids, table, weight, bias, out)
+        ctx.ws, ctx.cfg = ws, (float(dropout_p), int(training), int(seed), precision)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        ids, table, weight, bias, out = ctx.saved_tensors
+        n, CE, O = ids.numel(), table.shape[1], weight.shape[0]
+        p, training, seed, precision = ctx.cfg
+        d_out = d_out.contiguous().float()
+        gw, gb, d_table = torch.zeros_like(weight), torch.zeros_like(bias), torch.zeros_like(table)
+        _lib.check(lib.nrl_linear_encoder_bwd(_p(ids), n, table.shape[0], CE, _p(weight), O, p, training, seed,
+                                              _p(out), _p(d_out), _p(gw), _p(gb), _p(d_table), _p(ctx.ws),
+                                              ctx.ws.numel(), precision, _stream()), "nrl_linear_encoder_bwd")
+        ctx.ws = None
+        return None, d_table, gw, gb, None, None, None, None
+
+
+class PlmHeadFn(torch.autograd.Function):
+    """The post-transformer part of ``PLM.forward`` (``encoders/news/text.py:93-100``): dropout ->
+    MHSA over dim 0 of ``[N, T, E]`` (the reference's ``batch_first=False`` quirk) -> dropout ->
+    additive pooling over the T tokens."""
+
+    @staticmethod
+    def forward(ctx, x, w_in, b_in, w_out, b_out, w_add, b_add, q_add, num_heads, attention_axis, dropout_p,
+                training, seed, precision):
+        lib = _lib.load()
+        x = _chk(x.contiguous(), torch.float32, "x")
+        N, T, E = x.shape
+        dims = dims_of(E, num_heads, q_add.numel())
+        blk = [w_in, b_in, w_out, b_out, w_add, b_add, q_add]
+        need = lib.nrl_user_encoder_ws_bytes(N, T, dims)
+        if need == 0:
+            raise RuntimeError("nrl_plm_head: unsupported dims (E / heads must be 16, 20, 32, 48 or 64; Q <= 256)")
+        out = torch.empty(N, E, dtype=torch.float32, device=x.device)
+        ws = workspace(need, x.device)
+        bs = block_struct(blk)
+        _lib.check(lib.nrl_plm_head_fwd(_p(x), N, T, C.byref(bs), dims, int(attention_axis), float(dropout_p),
+                                        int(training), int(seed), _p(out), _p(ws), ws.numel(), precision,
+                                        _stream()), "nrl_plm_head_fwd")
+        ctx.save_for_backward(*blk)
+        ctx.ws, ctx.dims = ws, dims
+        ctx.cfg = (N, T, E, int(attention_axis), float(dropout_p), int(training), int(seed), precision)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        blk = list(ctx.saved_tensors)
+        N, T, E, axis, p, training, seed, precision = ctx.cfg
+        d_out = d_out.contiguous().float()
+        grads = [torch.zeros_like(t) for t in blk]
+        d_x = torch.empty(N, T, E, dtype=torch.float32, device=d_out.device)
+        bs, gs = block_struct(blk), block_struct(grads)
+        _lib.check(lib.nrl_plm_head_bwd(N, T, C.byref(bs), ctx.dims, axis, p, training, seed, _p(d_out),
+                                        C.byref(gs), _p(d_x), _p(ctx.ws), ctx.ws.numel(), precision, _stream()),
+                   "nrl_plm_head_bwd")
+        ctx.ws = None
+        return (d_x, *grads, None, None, None, None, None, None)

@@ -113,3 +113,37 @@ def make_nrms_params(vocab: int, embed_dim: int = 300, num_heads: int = 15,
     p.update(block("news_encoder.text_encoders.title."))
     p.update(block("user_encoder."))
     return p
+
+
+def make_naml_params(vocab: int, embed_dim: int = 300, num_filters: int = 400, window: int = 3,
+                     query_dim: int = 200, categ_embed_dim: int = 100, num_categories: int = 19,
+                     seed: int = 1234) -> Dict[str, torch.Tensor]:
+    """Random-init NAML parameters under the reference ``state_dict`` key names (SURVEY.md §8b;
+    the ``abstract`` prefix aliases the ``title`` text encoder and is not repeated).  Table ~ N(0,1);
+    conv / linear ~ U(-a, a), a = 1/sqrt(fan_in); queries ~ U(-0.1, 0.1); category table ~ N(0,1)
+    with row 0 zero (``nn.Embedding(padding_idx=0)``, ``category.py:56-58``)."""
+    g = torch.Generator().manual_seed(seed)
+    E, F_, Q, CE = embed_dim, num_filters, query_dim, categ_embed_dim
+
+    def u(*shape, a):
+        return (torch.rand(*shape, generator=g) * 2 - 1) * a
+
+    def add(prefix, dim):
+        a = 1.0 / (dim ** 0.5)
+        return {prefix + "linear.weight": u(Q, dim, a=a), prefix + "linear.bias": u(Q, a=a),
+                prefix + "query": u(Q, a=0.1)}
+
+    t = "news_encoder.text_encoders.title."
+    c = "news_encoder.category_encoders.category."
+    a_conv = 1.0 / ((window * E) ** 0.5)
+    p = {t + "embedding_layer.weight": torch.randn(vocab + 1, E, generator=g),
+         t + "cnn.weight": u(F_, 1, window, E, a=a_conv), t + "cnn.bias": u(F_, a=a_conv)}
+    p.update(add(t + "additive_attention.", F_))
+    ctab = torch.randn(num_categories, CE, generator=g)
+    ctab[0] = 0
+    p[c + "embedding_layer.weight"] = ctab
+    p[c + "linear.weight"] = u(F_, CE, a=1.0 / (CE ** 0.5))
+    p[c + "linear.bias"] = u(F_, a=1.0 / (CE ** 0.5))
+    p.update(add("news_encoder.combine_layer.", F_))
+    p.update(add("user_encoder.additive_attention.", F_))
+    return p

@@ -196,9 +196,149 @@ def naml_case():
     print(f"naml_news: oracle vs reference rel {r:.2e} (news), {r2:.2e} (user)")
 
 
+def naml_step_case(name, V, E, F_, W, Q, CE, B, max_hist, seed, store_params, L=30, LA=50):
+    """Whole NAML step (``naml_module.py:261-286`` + CE + backward) from the reference's own modules."""
+    from newsreclib_b200.synthetic import make_naml_params
+    C = 19
+    params = make_naml_params(V, E, F_, W, Q, CE, C, seed=seed)
+    batch = make_batch(B, V, hist="ragged", max_hist=max_hist, cand="train", seed=seed, max_title_len=L,
+                       abstract_len=LA)
+    text = CNNAddAtt(params["news_encoder.text_encoders.title.embedding_layer.weight"].clone(), E, F_, W, Q, 0.2)
+    categ = LinearEncoder(pretrained_embeddings=None, from_pretrained=False, freeze_pretrained_emb=False,
+                          num_categories=C, embed_dim=CE, use_dropout=False, dropout_probability=None,
+                          linear_transform=True, output_dim=F_)
+    news = NewsEncoder(["title", "abstract", "category"], ["title", "abstract", "category"], False,
+                       text, categ, None, True, "add_att", F_, Q, None)
+    mod = torch.nn.Module()
+    mod.news_encoder, mod.user_encoder = news, NAMLUser(F_, Q)
+    full = dict(params)
+    for k in list(params):
+        if ".text_encoders.title." in k:
+            full[k.replace(".title.", ".abstract.")] = params[k]
+    res = mod.load_state_dict(full, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    mod.eval()
+    hist = news(batch["x_hist"])
+    hist_agg, _ = O.to_dense_batch(hist, batch["batch_hist"])
+    cand = news(batch["x_cand"])
+    cand_agg, _ = O.to_dense_batch(cand, batch["batch_cand"])
+    u = mod.user_encoder(hist_agg)
+    scores = DotProduct()(u.unsqueeze(1), cand_agg.permute(0, 2, 1))
+    y, _ = O.to_dense_batch(batch["labels"], batch["batch_cand"])
+    loss = torch.nn.CrossEntropyLoss()(scores, y)
+    loss.backward()
+    # title / abstract alias one module: named_parameters() yields each tensor once
+    rgrads = {}
+    for k, v in mod.named_parameters():
+        rgrads[k.replace(".abstract.", ".title.")] = v.grad.detach().clone()
+    assert set(rgrads) == set(params), set(rgrads) ^ set(params)
+    # oracle on the same inputs
+    ps = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    oscores = O.naml_forward(batch, ps, W)
+    oloss = O.nrms_loss(batch, oscores)
+    oloss.backward()
+    ograds = {k: v.grad.detach().clone() for k, v in ps.items()}
+    ograds["news_encoder.text_encoders.title.embedding_layer.weight"][0] = 0
+    ograds["news_encoder.category_encoders.category.embedding_layer.weight"][0] = 0
+    worst = max(rel(oscores.detach(), scores.detach()), rel(oloss.detach(), loss.detach()))
+    assert worst < 2e-5, (name, worst)
+    for k, g in rgrads.items():
+        r = rel(ograds[k], g); worst = max(worst, r)
+        assert r < 5e-4, (name, "grad", k, r)
+    out = {
+        "meta": np.array([V, E, F_, W, Q, CE, C, B, max_hist, seed, L, LA], dtype=np.int64),
+        "oracle_vs_reference_maxrel": np.array(worst),
+        "batch_hist": batch["batch_hist"].numpy(), "batch_cand": batch["batch_cand"].numpy(),
+        "labels": batch["labels"].numpy(),
+        "hist_vec": hist.detach().numpy(), "user_vec": u.detach().numpy(),
+        "scores": scores.detach().numpy(), "loss": loss.detach().numpy(),
+        "param_checksum": np.array([float(v.double().sum()) for v in params.values()]),
+    }
+    for side in ("hist", "cand"):
+        for attr in ("title", "abstract", "category"):
+            out[f"{side}_{attr}"] = batch["x_" + side][attr].numpy()
+    for k, g in rgrads.items():
+        g = g.numpy()
+        if store_params or g.size <= 4096 or k.endswith("embedding_layer.weight"):
+            out["grad/" + k] = g
+        else:
+            out["gradsample/" + k] = g.reshape(-1)[::7].copy()
+    if store_params:
+        for k, v in params.items():
+            out["param/" + k] = v.numpy()
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(f"{name}: oracle vs reference max rel {worst:.2e}; loss {float(loss):.6f}; "
+          f"N_h={batch['batch_hist'].numel()} N_c={batch['batch_cand'].numel()}")
+
+
+def plm_head_case(name, hidden, tf_heads, head_heads, Q, N, T, seed):
+    """The reference ``PLM`` class (``text.py:15-109``) around a tiny random RoBERTa saved offline;
+    pins the post-transformer head (dropout -> batch-axis MHSA -> dropout -> additive pooling)."""
+    import tempfile
+    from transformers import RobertaConfig, RobertaModel
+    from newsreclib.models.components.encoders.news.text import PLM
+    torch.manual_seed(seed)
+    cfg = RobertaConfig(vocab_size=120, hidden_size=hidden, num_hidden_layers=2, num_attention_heads=tf_heads,
+                        intermediate_size=2 * hidden, max_position_embeddings=T + 4, pad_token_id=1)
+    with tempfile.TemporaryDirectory() as d:
+        RobertaModel(cfg).save_pretrained(d)
+        ref = PLM(plm_model=d, frozen_layers=[0], embed_dim=hidden, use_mhsa=True, apply_reduce_dim=False,
+                  reduced_embed_dim=None, num_heads=head_heads, query_dim=Q, dropout_probability=0.2).eval()
+    g = torch.Generator().manual_seed(seed)
+    lens = torch.randint(4, T + 1, (N,), generator=g)
+    lens[0] = T
+    ids = torch.randint(3, 120, (N, T), generator=g)
+    att = (torch.arange(T)[None, :] < lens[:, None]).long()
+    ids = torch.where(att.bool(), ids, torch.ones_like(ids))
+    text = {"input_ids": ids, "attention_mask": att}
+    with torch.no_grad():
+        states = ref.plm_model(**text)[0]
+    x = states.clone().requires_grad_(True)
+    # the reference's own forward, with the transformer output substituted by the same tensor
+    class _Fixed(torch.nn.Module):
+        def forward(self, **kw):
+            return (x,)
+    ref.plm_model = _Fixed()
+    out = ref(text)
+    w = torch.randn(N, hidden, generator=g)
+    (out * w).sum().backward()
+    head = {k: v for k, v in ref.state_dict().items()
+            if k.startswith("multihead_attention.") or k.startswith("additive_attention.")}
+    rgrads = {k: v.grad.detach().clone() for k, v in ref.named_parameters()
+              if k.startswith("multihead_attention.") or k.startswith("additive_attention.")}
+    hp = {k: v.clone().requires_grad_(True) for k, v in head.items()}
+    xo = states.clone().requires_grad_(True)
+    oo = O.plm_head(xo, hp, head_heads)
+    (oo * w).sum().backward()
+    worst = rel(oo.detach(), out.detach())
+    assert worst < 2e-5, worst
+    for k, gref in rgrads.items():
+        r = rel(hp[k].grad, gref); worst = max(worst, r)
+        assert r < 5e-4, (k, r)
+    r = rel(xo.grad, x.grad); worst = max(worst, r)
+    assert r < 5e-4, r
+    np.savez_compressed(
+        os.path.join(GOLD, name + ".npz"), meta=np.array([hidden, head_heads, Q, N, T]), x=states.numpy(),
+        w=w.numpy(), out=out.detach().numpy(), dx=x.grad.numpy(), oracle_vs_reference_maxrel=np.array(worst),
+        **{"param/" + k: v.numpy() for k, v in head.items()}, **{"grad/" + k: v.numpy() for k, v in rgrads.items()})
+    print(f"{name}: oracle vs reference PLM head max rel {worst:.2e}")
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(4)
+    only = set(sys.argv[1:])
+    if only:  # mint selected fixtures without touching the committed ones
+        if "naml_tiny" in only:
+            naml_step_case("naml_tiny", V=60, E=32, F_=48, W=3, Q=24, CE=20, B=3, max_hist=5, seed=5,
+                           store_params=True, L=12, LA=16)
+        if "naml_mind" in only:
+            naml_step_case("naml_mind", V=300, E=300, F_=400, W=3, Q=200, CE=100, B=4, max_hist=6, seed=77,
+                           store_params=False)
+        if "plm_head" in only:
+            plm_head_case("plm_head_d48", hidden=96, tf_heads=2, head_heads=2, Q=40, N=12, T=10, seed=3)
+            plm_head_case("plm_head_d64", hidden=128, tf_heads=2, head_heads=2, Q=40, N=40, T=7, seed=4)
+        sys.exit(0)
     # tiny dims: everything stored (params, all grads)
     nrms_case("nrms_tiny", E=60, H=3, Q=40, V=50, B=3, max_hist=5, hist="ragged", cand="train",
               seed=3, store_params=True, max_title_len=12)

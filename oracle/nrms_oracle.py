@@ -242,11 +242,15 @@ def adam_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, lr: float =
 # --------------------------------------------------------------------------------------
 # a13  NAML pieces
 # --------------------------------------------------------------------------------------
-def cnn_add_att(ids: Tensor, p: Dict[str, Tensor], window: int) -> Tensor:
-    """``text.py:163-176`` (eval mode): embedding -> Conv2d(1,F,(w,E),pad((w-1)//2,0)) ->
-    ReLU -> additive pooling over the tokens.  The conv is written as an explicit
-    sliding-window contraction."""
-    x = embedding_gather(p["embedding_layer.weight"], ids)  # [N, L, E]
+def cnn_add_att(ids: Tensor, p: Dict[str, Tensor], window: int, keep1: Optional[Tensor] = None,
+                keep2: Optional[Tensor] = None, dropout_p: float = 0.0) -> Tensor:
+    """``text.py:163-176``: embedding -> dropout -> Conv2d(1,F,(w,E),pad((w-1)//2,0)) -> ReLU ->
+    dropout -> additive pooling over the tokens.  The conv is written as an explicit
+    sliding-window contraction; dropout is expressed through keep masks (``keep1`` ``[N, L, E]``
+    after the embedding, ``keep2`` ``[N, L, F]`` after the ReLU; ``None`` = eval mode)."""
+    x = embedding_gather(p["embedding_layer.weight"], ids)  # [N, L, E]  text.py:165
+    if keep1 is not None:
+        x = x * keep1 / (1.0 - dropout_p)  # text.py:166
     N, L, E = x.shape
     pad = int((window - 1) / 2)
     w = p["cnn.weight"]  # [F, 1, w, E]
@@ -255,14 +259,16 @@ def cnn_add_att(ids: Tensor, p: Dict[str, Tensor], window: int) -> Tensor:
     xp[:, pad : pad + L] = x
     Lout = L + 2 * pad - window + 1
     cols = torch.stack([xp[:, i : i + Lout] for i in range(window)], dim=2)  # [N, Lout, w, E]
-    y = cols.reshape(N * Lout, window * E) @ w.reshape(F_, window * E).t() + p["cnn.bias"]
-    y = torch.relu(y).reshape(N, Lout, F_)
+    y = cols.reshape(N * Lout, window * E) @ w.reshape(F_, window * E).t() + p["cnn.bias"]  # text.py:169
+    y = torch.relu(y).reshape(N, Lout, F_)  # text.py:170
+    if keep2 is not None:
+        y = y * keep2 / (1.0 - dropout_p)  # text.py:171
     return additive_attention(
         y,
         p["additive_attention.linear.weight"],
         p["additive_attention.linear.bias"],
         p["additive_attention.query"],
-    )
+    )  # text.py:174
 
 
 def linear_category_encoder(ids: Tensor, p: Dict[str, Tensor]) -> Tensor:
@@ -276,6 +282,74 @@ def naml_user_encoder(h: Tensor, p: Dict[str, Tensor]) -> Tensor:
     """``encoders/user/naml.py:27-31``: additive pooling over dim 1 only."""
     return additive_attention(
         h,
+        p["additive_attention.linear.weight"],
+        p["additive_attention.linear.bias"],
+        p["additive_attention.query"],
+    )
+
+
+# --------------------------------------------------------------------------------------
+# NAMLModule.forward (naml_module.py:261-286) on reference-named parameters
+# --------------------------------------------------------------------------------------
+def _sub(params: Dict[str, Tensor], prefix: str) -> Dict[str, Tensor]:
+    return {k[len(prefix):]: v for k, v in params.items() if k.startswith(prefix)}
+
+
+def naml_news_encoder(x: Dict[str, Tensor], params: Dict[str, Tensor], window: int,
+                      masks: Optional[Dict[str, Tensor]] = None, dropout_p: float = 0.0) -> Tensor:
+    """``NewsEncoder.forward`` in the NAML configuration (``news.py:134-163``): the SAME text
+    encoder on title and abstract (``news.py:68-77``), the category encoder, then additive
+    attention over the stacked views (order-independent).  ``params`` are relative to
+    ``news_encoder.``; ``masks`` keys: ``title1/title2/abstract1/abstract2``."""
+    tp = _sub(params, "text_encoders.title.")
+    cp = _sub(params, "category_encoders.category.")
+    lp = _sub(params, "combine_layer.")
+    m = masks or {}
+    views = [cnn_add_att(x[name], tp, window, m.get(name + "1"), m.get(name + "2"), dropout_p)
+             for name in ("title", "abstract") if name in x]
+    views.append(linear_category_encoder(x["category"], cp))
+    return additive_attention(torch.stack(views, dim=1), lp["linear.weight"], lp["linear.bias"], lp["query"])
+
+
+def naml_forward(batch: Dict, params: Dict[str, Tensor], window: int, late_fusion: bool = False,
+                 masks: Optional[Dict[str, Dict[str, Tensor]]] = None, dropout_p: float = 0.0) -> Tensor:
+    """``naml_module.py:261-286``.  ``masks`` = {"hist": {...}, "cand": {...}} keep masks."""
+    news = _sub(params, "news_encoder.")
+    m = masks or {}
+    hist = naml_news_encoder(batch["x_hist"], news, window, m.get("hist"), dropout_p)  # :263
+    hist_agg, mask_hist = to_dense_batch(hist, batch["batch_hist"])  # :264
+    cand = naml_news_encoder(batch["x_cand"], news, window, m.get("cand"), dropout_p)  # :267
+    cand_agg, _ = to_dense_batch(cand, batch["batch_cand"])  # :268
+    if not late_fusion:
+        u = naml_user_encoder(hist_agg, _sub(params, "user_encoder."))  # :272
+    else:
+        u = hist_agg.sum(dim=1) / mask_hist.sum(dim=1).unsqueeze(-1)  # :275-279
+    return dot_product(u, cand_agg)  # :282-284
+
+
+# --------------------------------------------------------------------------------------
+# a14  PLM head: the part of PLM.forward after the transformer
+# --------------------------------------------------------------------------------------
+def plm_head(x: Tensor, p: Dict[str, Tensor], num_heads: int, keep1: Optional[Tensor] = None,
+             keep2: Optional[Tensor] = None, dropout_p: float = 0.0) -> Tensor:
+    """``text.py:93-100``: ``x`` = last hidden states ``[N, T, E]`` -> dropout (``:93``) ->
+    ``nn.MultiheadAttention`` called WITHOUT a permute (``:96``; ``batch_first=False``, so dim 0 =
+    the N news of the call is the sequence axis and the T tokens are the batch axis) -> dropout
+    (``:97``) -> additive pooling over dim 1 = tokens (``:100``, pad tokens included)."""
+    if keep1 is not None:
+        x = x * keep1 / (1.0 - dropout_p)
+    y = mha_seq_first(
+        x,
+        p["multihead_attention.in_proj_weight"],
+        p["multihead_attention.in_proj_bias"],
+        p["multihead_attention.out_proj.weight"],
+        p["multihead_attention.out_proj.bias"],
+        num_heads,
+    )
+    if keep2 is not None:
+        y = y * keep2 / (1.0 - dropout_p)
+    return additive_attention(
+        y,
         p["additive_attention.linear.weight"],
         p["additive_attention.linear.bias"],
         p["additive_attention.query"],

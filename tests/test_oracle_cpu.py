@@ -83,6 +83,52 @@ def test_naml_golden():
     assert rel_err(O.naml_user_encoder(torch.from_numpy(g["user_in"]), up), g["user_vec"]) < 2e-5
 
 
+@pytest.mark.parametrize("name", ["naml_tiny", "naml_mind"])
+def test_naml_step_oracle_matches_reference_golden(name):
+    """Whole NAML step (naml_module.py:261-286 + CE + backward) minted from the reference modules."""
+    from newsreclib_b200.synthetic import make_naml_params
+    g = dict(np.load(os.path.join(GOLD, name + ".npz")))
+    V, E, F_, W, Q, CE, C, B, max_hist, seed, L, LA = [int(x) for x in g["meta"]]
+    assert float(g["oracle_vs_reference_maxrel"]) < 5e-4
+    if any(k.startswith("param/") for k in g):
+        params = {k[len("param/"):]: torch.from_numpy(g[k]) for k in g if k.startswith("param/")}
+    else:
+        params = make_naml_params(V, E, F_, W, Q, CE, C, seed=seed)
+        chk = np.array([float(v.double().sum()) for v in params.values()])
+        assert np.allclose(chk, g["param_checksum"], rtol=1e-9), "seeded parameter generator drifted"
+    batch = {"batch_hist": torch.from_numpy(g["batch_hist"]), "batch_cand": torch.from_numpy(g["batch_cand"]),
+             "labels": torch.from_numpy(g["labels"]), "x_hist": {}, "x_cand": {}}
+    for side in ("hist", "cand"):
+        for attr in ("title", "abstract", "category"):
+            batch["x_" + side][attr] = torch.from_numpy(g[f"{side}_{attr}"])
+    ps = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    scores = O.naml_forward(batch, ps, W)
+    loss = O.nrms_loss(batch, scores)
+    assert rel_err(scores.detach(), g["scores"]) < 1e-5 and rel_err(loss.detach(), g["loss"]) < 1e-6
+    loss.backward()
+    for k, v in g.items():
+        if k.startswith("grad/") and not k.endswith("embedding_layer.weight"):
+            assert rel_err(ps[k[5:]].grad, v) < 2e-3, k
+    # multi-view news vectors and the additive user vector
+    news = {k[len("news_encoder."):]: v for k, v in params.items() if k.startswith("news_encoder.")}
+    assert rel_err(O.naml_news_encoder(batch["x_hist"], news, W), g["hist_vec"]) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["plm_head_d48", "plm_head_d64"])
+def test_plm_head_oracle_matches_reference_golden(name):
+    g = dict(np.load(os.path.join(GOLD, name + ".npz")))
+    hidden, heads, Q, N, T = [int(x) for x in g["meta"]]
+    p = {k[len("param/"):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("param/")}
+    x = torch.from_numpy(g["x"]).requires_grad_(True)
+    out = O.plm_head(x, p, heads)
+    assert rel_err(out.detach(), g["out"]) < 1e-5
+    (out * torch.from_numpy(g["w"])).sum().backward()
+    assert rel_err(x.grad, g["dx"]) < 2e-4
+    # the quirk (text.py:96): attention runs across the N news -> perturbing news 1 changes news 0
+    x2 = torch.from_numpy(g["x"]).clone(); x2[1] += 0.5
+    assert float((O.plm_head(x2, p, heads)[0] - out.detach()[0]).abs().max()) > 1e-4
+
+
 def test_ce_soft_matches_torch_and_multi_positive():
     s = torch.randn(5, 7)
     y = torch.zeros(5, 7); y[:, 1] = 1; y[2, 4] = 1  # a multi-positive row (sum y > 1)
