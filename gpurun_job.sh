@@ -1,3 +1,8 @@
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -q --timeout 300 2>&1 | tail -30 > gpurun_out/pytest_gpu.log
-tail -30 gpurun_out/pytest_gpu.log
+timeout 900 python -m pytest tests -m gpu -q --timeout 240 2>&1 | tail -2
+timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench_x.json 2>&1
+python - <<PY
+import json
+d=json.load(open("gpurun_out/bench_x.json"))
+print(round(d["ms_per_step"],3), round(d["roofline"]["kernel_ms_per_step"],3), d["roofline"]["top_kernels_ms_per_step"])
+PY

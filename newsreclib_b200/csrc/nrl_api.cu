@@ -113,6 +113,8 @@ static int device_init() {
   g_dev.encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
   CUDA_TRY(cudaFuncSetAttribute(nrl_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 GEMM_SMEM_LIMIT));
+  CUDA_TRY(cudaFuncSetAttribute(nrl_gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                GEMM_SMEM_LIMIT));
   g_dev.ok = true;
   return NRL_OK;
 }
@@ -135,7 +137,7 @@ struct Bump {
 };
 
 struct Dims {
-  int E, H, Q, DH, Ep, Qp, P3, MW;
+  int E, H, Q, DH, Ep, Qp, P3, MW, LDQ;
 };
 static int make_dims(nrl_dims d, Dims& o) {
   if (d.embed_dim <= 0 || d.num_heads <= 0 || d.query_dim <= 0 || d.embed_dim % d.num_heads)
@@ -149,6 +151,8 @@ static int make_dims(nrl_dims d, Dims& o) {
   o.Qp = round_up(o.Q, 16);
   o.P3 = round_up(3 * o.E, 16);
   o.MW = (o.E + 31) / 32;
+  // fp32 qkv rows start on 128-byte lines: every 32-column TMA store row is one full line
+  o.LDQ = round_up(3 * o.E, 32);
   return NRL_OK;
 }
 
@@ -178,7 +182,7 @@ static void carve_block(Bump& b, long long R, const Dims& d, BlockWs& w) {
   w.wadd_f = b.take<bf16>(2ull * d.Q * d.Ep);
   w.wadd_t = b.take<bf16>(2ull * d.E * d.Qp);
   w.x = b.take<bf16>(2ull * R * d.Ep);
-  w.qkv = b.take<float>((size_t)R * 3 * d.E);
+  w.qkv = b.take<float>((size_t)R * d.LDQ);
   w.lse = b.take<float>((size_t)R * d.H);
   w.o = b.take<bf16>(2ull * R * d.Ep);
   w.y = b.take<float>((size_t)R * d.E);
@@ -255,6 +259,12 @@ static int make_tmap_planes(CUtensorMap* m, const bf16* base, unsigned long long
   return NRL_OK;
 }
 
+// staging buffers per epilogue warp (NRL_GEMM_EPI_BUFS=4: experiment with deeper TMA-store pipelining)
+static int epi_bufs_cfg() {
+  static const int v = [] { const char* e = getenv("NRL_GEMM_EPI_BUFS"); return (e && atoi(e) == 4) ? 4 : 2; }();
+  return v;
+}
+
 // Host-side description of where a GEMM's result goes (turned into tensor maps + GemmEpi).
 struct Sinks {
   float* f32 = nullptr; long long ld_f32 = 0; int f32_cols = 0; bool reduce = false;  // fp32 [M, f32_cols]
@@ -280,12 +290,29 @@ static int launch_gemm(const Ctx& c, GemmParams& p, const CUtensorMap& ta, const
     p.epi.ones_col = sk.ones_col;
   }
   p.epi_buf_bytes = (sk.f32 && sk.sp) ? 8192 : 4096;
+  p.epi_bufs = p.pair ? epi_bufs_cfg() : 2;
+  static const int dbg = [] { const char* e = getenv("NRL_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
+  p.debug = dbg;
+  if (p.pair) {  // CTA pairs (cta_group::2): each CTA stages its 128 rows of A and half of the B tile
+    const int stage_bytes2 = p.planes * (GEMM_A_BYTES + p.BN / 2 * 128);
+    int stages2 = (GEMM_SMEM_LIMIT - 1024 - GEMM_BAR_BYTES - 4 * p.epi_bufs * p.epi_buf_bytes) / stage_bytes2;
+    if (stages2 > GEMM_MAX_STAGES) stages2 = GEMM_MAX_STAGES;
+    if (stages2 < 2) return fail(NRL_ERR_UNSUPPORTED, "pair GEMM tile does not fit shared memory");
+    p.stages = stages2;
+    p.tiles_per_unit = (p.n_extent + p.BN - 1) / p.BN;
+    const int smem2 = 1024 + stages2 * stage_bytes2 + 4 * p.epi_bufs * p.epi_buf_bytes + GEMM_BAR_BYTES;
+    const int m_pairs = (p.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+    const int clusters = m_pairs < g_dev.sm_count / 2 ? m_pairs : g_dev.sm_count / 2;
+    nrl_gemm_tc2_kernel<<<2 * clusters, GEMM_THREADS, smem2, c.stream>>>(ta, tb, tout, tsp, p);
+    LAUNCH_CHECK(name);
+    return NRL_OK;
+  }
   const int stage_bytes = p.planes * (GEMM_A_BYTES + (p.mn_major ? (p.BN + 63) / 64 * 8192 : p.BN * 128));
-  int stages = (GEMM_SMEM_LIMIT - 1024 - GEMM_BAR_BYTES - 8 * p.epi_buf_bytes) / stage_bytes;
+  int stages = (GEMM_SMEM_LIMIT - 1024 - GEMM_BAR_BYTES - 4 * p.epi_bufs * p.epi_buf_bytes) / stage_bytes;
   if (stages > GEMM_MAX_STAGES) stages = GEMM_MAX_STAGES;
   if (stages < 2) return fail(NRL_ERR_UNSUPPORTED, "GEMM tile does not fit shared memory");
   p.stages = stages;
-  const int smem = 1024 + stages * stage_bytes + 8 * p.epi_buf_bytes + GEMM_BAR_BYTES;
+  const int smem = 1024 + stages * stage_bytes + 4 * p.epi_bufs * p.epi_buf_bytes + GEMM_BAR_BYTES;
   const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM, n_tiles = (p.n_extent + p.BN - 1) / p.BN;
   const int tiles = m_tiles * n_tiles * p.k_splits;
   // unit = whole m-block when there are enough m-blocks to fill the machine twice over
@@ -301,13 +328,16 @@ static void set_segs(const Ctx& c, GemmParams& p) { p.planes = c.two_planes() ? 
 
 // balanced n-tiles: as few tiles as possible (<= 256 columns each), all the same width, and
 // narrow enough that at least two pipeline stages fit beside the epilogue staging buffers
-static int balanced_bn(int n_extent, int planes, bool both_sinks, int mn_major) {
-  const int avail = GEMM_SMEM_LIMIT - 1024 - GEMM_BAR_BYTES - 8 * (both_sinks ? 8192 : 4096);
-  for (int nt = (n_extent + 255) / 256;; ++nt) {
+static int balanced_bn(int n_extent, int planes, bool both_sinks, int mn_major, bool single_tile = false,
+                       bool pair = false) {
+  const int avail = GEMM_SMEM_LIMIT - 1024 - GEMM_BAR_BYTES - 4 * (pair ? epi_bufs_cfg() : 2) * (both_sinks ? 8192 : 4096);
+  static const int bn_max = [] { const char* e = getenv("NRL_GEMM_BN_MAX"); return e ? atoi(e) : 256; }();
+  const int cap = single_tile ? 256 : bn_max;
+  for (int nt = (n_extent + cap - 1) / cap;; ++nt) {
     // multiple of 32: the epilogue stores 32-column boxes, which must not straddle two n-tiles
     // (the overhang of the LAST tile lies outside the tensor and is clipped by TMA)
     const int bn = round_up((n_extent + nt - 1) / nt, 32);
-    const int stage = planes * (GEMM_A_BYTES + (mn_major ? (bn + 63) / 64 * 8192 : bn * 128));
+    const int stage = planes * (GEMM_A_BYTES + (mn_major ? (bn + 63) / 64 * 8192 : (pair ? bn / 2 : bn) * 128));
     if (avail / stage >= 2 || bn <= 32) return bn;
   }
 }
@@ -321,13 +351,16 @@ static int gemm_nt(const Ctx& c, const bf16* A, long long M, int a_pitch, const 
   p.n_extent = (sk.sp && sk.sp_cols > N) ? sk.sp_cols : N;
   p.mn_major = 0;
   set_segs(c, p);
-  p.BN = balanced_bn(p.n_extent, p.planes, sk.f32 && sk.sp, 0);
+  // big row-streaming GEMMs run on CTA pairs (NRL_GEMM_PAIR=0 keeps the 1-CTA kernel: A/B runs)
+  static const bool pair_on = [] { const char* e = getenv("NRL_GEMM_PAIR"); return !(e && e[0] == '0'); }();
+  p.pair = (pair_on && (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM) >= g_dev.sm_count / 2) ? 1 : 0;
+  p.BN = balanced_bn(p.n_extent, p.planes, sk.f32 && sk.sp, 0, epi.score != nullptr, p.pair != 0);
   if (epi.score && p.BN < N) return fail(NRL_ERR_UNSUPPORTED, "score fusion needs a single n-tile (N <= 256)");
   p.k_splits = 1;
   p.epi = epi;
   CUtensorMap ta, tb;
   TRY(make_tmap(&ta, A, K, M, a_pitch, GEMM_BK, GEMM_BM));
-  TRY(make_tmap(&tb, B, K, N, b_pitch, GEMM_BK, p.BN));
+  TRY(make_tmap(&tb, B, K, N, b_pitch, GEMM_BK, p.pair ? p.BN / 2 : p.BN));
   return launch_gemm(c, p, ta, tb, sk, name);
 }
 
@@ -433,7 +466,7 @@ static void launch_attn_fwd(const Ctx& c, const Dims& d, const AttnGeom& g, cons
   if (g.S <= 32 && !attn_force_simt()) {  // warp-level tensor-core path (title tokens)
     const long long items = (long long)g.NB * d.H;
     attn_fwd_mma_kernel<DH><<<(unsigned)((items + 3) / 4), 128, 0, c.stream>>>(
-        w.qkv, d.E, d.H, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH), w.o, lo, d.Ep, w.lse);
+        w.qkv, d.E, d.LDQ, d.H, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH), w.o, lo, d.Ep, w.lse);
     return;
   }
   if (g.S <= 32) {  // register-resident SIMT path (NRL_ATTN_SIMT=1: A/B comparison only)
@@ -441,7 +474,7 @@ static void launch_attn_fwd(const Ctx& c, const Dims& d, const AttnGeom& g, cons
     const size_t smem = (size_t)g.S * attn_pitch(3 * hg * DH) * sizeof(float);
     if (smem <= (size_t)ATTN_S32_SMEM_BUDGET) {
       attn_fwd_s32_kernel<DH><<<grid_for((long long)g.NB * groups, 1, 16 * g_dev.sm_count), 32 * hg, smem, c.stream>>>(
-          w.qkv, d.E, d.H, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH), w.o, lo, d.Ep, w.lse);
+          w.qkv, d.E, d.LDQ, d.H, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH), w.o, lo, d.Ep, w.lse);
       return;
     }
   }
@@ -452,12 +485,12 @@ static void launch_attn_fwd(const Ctx& c, const Dims& d, const AttnGeom& g, cons
   if (hp >= 1) {  // tile-resident fast path
     const int passes = (d.H + hp - 1) / hp;
     attn_fwd_tile_kernel<DH><<<grid_for((long long)g.NB * passes, 1, 8 * g_dev.sm_count), 256, hp * per_head, c.stream>>>(
-        w.qkv, d.E, d.H, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH), hp, w.o, lo, d.Ep, w.lse);
+        w.qkv, d.E, d.LDQ, d.H, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH), hp, w.o, lo, d.Ep, w.lse);
     return;
   }
   const long long items = (long long)g.NB * d.H * ((g.S + 31) / 32);
   attn_fwd_kernel<DH><<<grid_for(items, attn_stream_warps(DH), 1 << 20), 32 * attn_stream_warps(DH), 0, c.stream>>>(
-      w.qkv, d.E, d.H, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH), w.o, lo, d.Ep, w.lse);
+      w.qkv, d.E, d.LDQ, d.H, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH), w.o, lo, d.Ep, w.lse);
 }
 template <int DH>
 static void launch_attn_bwd(const Ctx& c, const Dims& d, const AttnGeom& g, const BlockWs& w, long long R) {
@@ -466,7 +499,7 @@ static void launch_attn_bwd(const Ctx& c, const Dims& d, const AttnGeom& g, cons
   if (g.S <= 32 && !attn_force_simt()) {
     const long long items = (long long)g.NB * d.H;
     attn_bwd_mma_kernel<DH><<<(unsigned)((items + 3) / 4), 128, 0, c.stream>>>(
-        w.qkv, w.d_o, d.E, w.lse, d.E, d.H, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH),
+        w.qkv, w.d_o, d.E, w.lse, d.E, d.LDQ, d.H, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH),
         w.dqkv, lo, d.P3);
     return;
   }
@@ -475,7 +508,7 @@ static void launch_attn_bwd(const Ctx& c, const Dims& d, const AttnGeom& g, cons
     const size_t smem = ((size_t)g.S * attn_pitch(4 * hg * DH) + (size_t)hg * 32 * 33) * sizeof(float);
     if (smem <= (size_t)ATTN_S32_SMEM_BUDGET) {
       attn_bwd_s32_kernel<DH><<<grid_for((long long)g.NB * groups, 1, 16 * g_dev.sm_count), 32 * hg, smem, c.stream>>>(
-          w.qkv, w.d_o, d.E, w.lse, d.E, d.H, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH),
+          w.qkv, w.d_o, d.E, w.lse, d.E, d.LDQ, d.H, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH),
           w.dqkv, lo, d.P3);
       return;
     }
@@ -487,13 +520,13 @@ static void launch_attn_bwd(const Ctx& c, const Dims& d, const AttnGeom& g, cons
   if (hp >= 1) {
     const int passes = (d.H + hp - 1) / hp;
     attn_bwd_tile_kernel<DH><<<grid_for((long long)g.NB * passes, 1, 8 * g_dev.sm_count), 256, hp * per_head, c.stream>>>(
-        w.qkv, w.d_o, d.E, w.lse, d.E, d.H, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH), hp,
+        w.qkv, w.d_o, d.E, w.lse, d.E, d.LDQ, d.H, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH), hp,
         w.dqkv, lo, d.P3);
     return;
   }
   const long long items = (long long)g.NB * d.H;
   attn_bwd_kernel<DH><<<grid_for(items, attn_stream_warps(DH), 1 << 20), 32 * attn_stream_warps(DH), 0, c.stream>>>(
-      w.qkv, w.d_o, d.E, w.o, c.two_planes() ? w.o + R * d.Ep : nullptr, d.Ep, w.lse, d.E, d.H, g.S,
+      w.qkv, w.d_o, d.E, w.o, c.two_planes() ? w.o + R * d.Ep : nullptr, d.Ep, w.lse, d.E, d.LDQ, d.H, g.S,
       g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH), w.dqkv, lo, d.P3);
 }
 
@@ -534,7 +567,7 @@ static int block_forward(const Ctx& c, const Dims& d, BlockWs& w, long long R, c
   {
     GemmEpi e = epi_none();
     Sinks sk;
-    sk.f32 = w.qkv; sk.ld_f32 = 3 * d.E; sk.f32_cols = 3 * d.E;
+    sk.f32 = w.qkv; sk.ld_f32 = d.LDQ; sk.f32_cols = 3 * d.E;
     TRY(gemm_nt(c, w.x, R, d.Ep, w.win_f, 3 * d.E, d.Ep, d.Ep, e, sk, "gemm in_proj"));
   }
   // K4: per-head softmax(q k^T) v

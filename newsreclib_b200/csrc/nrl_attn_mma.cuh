@@ -118,6 +118,39 @@ __device__ __forceinline__ void mma_nn(float (&c)[2][4][4], const Blk& a, const 
       }
     }
 }
+// c[i][j] += sum_t X[t][16 i + ..] * Y[t][8 j + ..]  ("TN" product, reduction over the ROWS of both
+// operands): A fragments are movmatrix transposes of X's blocks, B fragments those of Y's blocks,
+// formed just in time so that no transposed copy of X stays live.
+template <int NT>
+__device__ __forceinline__ void mma_tn(float (&c)[2][4][4], const Blk& x, const Blk& y, bool three) {
+#pragma unroll
+  for (int kk = 0; kk < 2; ++kk) {
+    uint32_t bh[NT][2], bl[NT][2];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      bh[j][0] = movm_t(y.h[2 * kk][j]); bh[j][1] = movm_t(y.h[2 * kk + 1][j]);
+      bl[j][0] = three ? movm_t(y.l[2 * kk][j]) : 0u; bl[j][1] = three ? movm_t(y.l[2 * kk + 1][j]) : 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const uint32_t ah0 = movm_t(x.h[2 * kk][2 * i]), ah1 = movm_t(x.h[2 * kk][2 * i + 1]);
+      const uint32_t ah2 = movm_t(x.h[2 * kk + 1][2 * i]), ah3 = movm_t(x.h[2 * kk + 1][2 * i + 1]);
+      uint32_t al0 = 0u, al1 = 0u, al2 = 0u, al3 = 0u;
+      if (three) {
+        al0 = movm_t(x.l[2 * kk][2 * i]); al1 = movm_t(x.l[2 * kk][2 * i + 1]);
+        al2 = movm_t(x.l[2 * kk + 1][2 * i]); al3 = movm_t(x.l[2 * kk + 1][2 * i + 1]);
+      }
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        if (three) {
+          mma_16816(c[i][j], al0, al1, al2, al3, bh[j][0], bh[j][1]);
+          mma_16816(c[i][j], ah0, ah1, ah2, ah3, bl[j][0], bl[j][1]);
+        }
+        mma_16816(c[i][j], ah0, ah1, ah2, ah3, bh[j][0], bh[j][1]);
+      }
+    }
+  }
+}
 // Accumulator tile set c[2][4][4] (rows 16 i + g (+8), cols 8 j + 2 tg (+1)) -> row-layout blocks.
 __device__ __forceinline__ void acc_to_blocks(Blk& m, const float (&c)[2][4][4]) {
 #pragma unroll
@@ -176,7 +209,7 @@ __device__ __forceinline__ void store_acc_split(const float (&c)[2][4][4], float
 
 template <int DH>
 __global__ void __launch_bounds__(128)
-attn_fwd_mma_kernel(const float* __restrict__ qkv, int E, int heads, int S, long long seq_stride,
+attn_fwd_mma_kernel(const float* __restrict__ qkv, int E, int ldq, int heads, int S, long long seq_stride,
                     int NB, long long batch_stride, float scale, __nv_bfloat16* __restrict__ o_hi,
                     __nv_bfloat16* __restrict__ o_lo, int ep, float* __restrict__ lse) {
   constexpr int KS = (DH + 15) / 16;  // k-steps over the head dim
@@ -186,10 +219,9 @@ attn_fwd_mma_kernel(const float* __restrict__ qkv, int E, int heads, int S, long
   if (item >= (long long)NB * heads) return;
   const int b = (int)(item / heads), h = (int)(item % heads);
   const bool three = o_lo != nullptr;
-  const int ld = 3 * E;
+  const int ld = ldq;
   const float* base = qkv + (long long)b * batch_stride * ld + h * DH;
   const long long rstride = seq_stride * ld;
-
   Blk q, k;
   load_blocks<DH>(q, base, rstride, S, scale * NRL_LOG2E, g, tg);
   load_blocks<DH>(k, base + E, rstride, S, 1.f, g, tg);
@@ -267,9 +299,9 @@ attn_fwd_mma_kernel(const float* __restrict__ qkv, int E, int heads, int S, long
 // Backward.  P is recomputed from Q, K and the saved log-sum-exp; D = rowsum(P * dP).
 // Writes dQ | dK | dV as split planes [2][R][p3].
 template <int DH>
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(128, 3)
 attn_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o, long long ld_do,
-                    const float* __restrict__ lse, int E, int heads, int S, long long seq_stride,
+                    const float* __restrict__ lse, int E, int ldq, int heads, int S, long long seq_stride,
                     int NB, long long batch_stride, float scale, __nv_bfloat16* __restrict__ g_hi,
                     __nv_bfloat16* __restrict__ g_lo, int p3) {
   constexpr int KS = (DH + 15) / 16;
@@ -279,7 +311,7 @@ attn_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o
   if (item >= (long long)NB * heads) return;
   const int b = (int)(item / heads), h = (int)(item % heads);
   const bool three = g_lo != nullptr;
-  const int ld = 3 * E;
+  const int ld = ldq;
   const float* base = qkv + (long long)b * batch_stride * ld + h * DH;
   const long long rstride = seq_stride * ld;
   long long grow[4];
@@ -348,14 +380,11 @@ attn_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o
   mma_nn<ND>(acc, ds, k, three);
   store_acc_split<DH, ND>(acc, scale, scale, scale, scale, g_hi, g_lo, p3, grow, S, h * DH, g, tg);
   // dK = scale * dS^T Q = ln2 * dS^T Qs ;  dV = P^T dO
-  Blk t;
-  transpose_blocks(t, ds, three);
   zero();
-  mma_nn<ND>(acc, t, q, three);
+  mma_tn<ND>(acc, ds, q, three);
   store_acc_split<DH, ND>(acc, NRL_LN2, NRL_LN2, NRL_LN2, NRL_LN2, g_hi, g_lo, p3, grow, S, E + h * DH, g, tg);
-  transpose_blocks(t, pb, three);
   zero();
-  mma_nn<ND>(acc, t, go, three);
+  mma_tn<ND>(acc, pb, go, three);
   store_acc_split<DH, ND>(acc, 1.f, 1.f, 1.f, 1.f, g_hi, g_lo, p3, grow, S, 2 * E + h * DH, g, tg);
 
   if (h == 0 && p3 > 3 * E) {

@@ -72,7 +72,10 @@ struct GemmParams {
   int k_splits;
   int stages;
   int epi_buf_bytes;   // staging bytes per epilogue warp per buffer (4096 or 8192)
+  int epi_bufs;        // staging buffers per epilogue warp (2 or 4): TMA stores in flight per warp
   int tiles_per_unit;  // n_tiles (unit = m-block) or 1
+  int pair;            // 1: nrl_gemm_tc2_kernel (CTA pairs, cta_group::2)
+  int debug;           // timing experiments only (NRL_GEMM_DEBUG): 1 = no TMA stores, 2 = no epilogue work
   GemmEpi epi;
 };
 
@@ -122,6 +125,145 @@ __device__ __forceinline__ uint32_t drop_keep_bits32(unsigned long long seed, ui
   return bits;
 }
 
+// Epilogue of one accumulator tile for one epilogue warp (its 32-row TMEM lane quarter): walks
+// the tile in 32-column chunks, applies the fused element-wise work and issues the TMA stores.
+__device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const CUtensorMap* tmOutP,
+                                                   const CUtensorMap* tmSpP, const GemmTile& t,
+                                                   uint32_t t_row, int quarter, int lane,
+                                                   uint32_t my_stage, uint32_t sp_off,
+                                                   uint32_t& chunk_ctr, bool one) {
+    const GemmEpi& e = p.epi;
+    const CUtensorMap& tmOut = *tmOutP;
+    const CUtensorMap& tmSp = *tmSpP;
+    if (p.debug & 2) return;
+    const int row_base = t.m0 + quarter * 32;
+    const int row = row_base + lane;
+    const bool row_ok = row < p.M;
+    float score_acc = 0.f;
+    float addw = 0.f;
+    const float* addv = nullptr;
+    if (e.add_w && row_ok) {
+      addw = __ldg(e.add_w + row);
+      addv = e.add_vec + (long long)(row / e.add_L) * e.ld_addvec;
+    }
+    for (int c = 0; c < t.n_cur; c += 32) {
+      const int col_base = t.n0 + c;
+      float v[32];
+      if (c + 16 < t.n_cur) {
+        tmem_ld32(t_row + (uint32_t)c, v);
+      } else {
+        tmem_ld16(t_row + (uint32_t)c, v);
+#pragma unroll
+        for (int i = 16; i < 32; ++i) v[i] = 0.f;
+      }
+      if (row_base < p.M) {  // warp-uniform: rows past M produce nothing
+        if (addv) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if (col_base + 4 * q < p.N) {
+              const float4 a4 = __ldg(reinterpret_cast<const float4*>(addv + col_base) + q);
+              v[4 * q] += addw * a4.x; v[4 * q + 1] += addw * a4.y;
+              v[4 * q + 2] += addw * a4.z; v[4 * q + 3] += addw * a4.w;
+            }
+          }
+        }
+        if (e.relu) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (e.drop_words) {  // col_base % 32 == 0: one word holds this chunk's keep-bits
+          const uint32_t bits =
+              row_ok ? __ldg(e.drop_words + (long long)row * e.drop_mw + (col_base >> 5)) : 0u;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = ((bits >> i) & 1u) ? v[i] * e.drop_scale : 0.f;
+        }
+        if (e.pos_mask && row_ok) {
+          const float* pm = e.pos_mask + (long long)row * e.ld_pos + col_base;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if (col_base + 4 * q < p.N) {
+              const float4 m4 = __ldg(reinterpret_cast<const float4*>(pm) + q);
+              if (!(m4.x > 0.f)) v[4 * q] = 0.f;
+              if (!(m4.y > 0.f)) v[4 * q + 1] = 0.f;
+              if (!(m4.z > 0.f)) v[4 * q + 2] = 0.f;
+              if (!(m4.w > 0.f)) v[4 * q + 3] = 0.f;
+            }
+          }
+        }
+        if (e.qvec) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float a = 0.f;
+            if (col_base + i < p.N) {
+              a = tanh_fast(v[i]);
+              score_acc += a * __ldg(e.qvec + col_base + i);
+            }
+            v[i] = a;
+          }
+        }
+        if (e.gb && row_ok && e.gb_col >= col_base && e.gb_col < col_base + 32) {
+          float g = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (col_base + i == e.gb_col) g = v[i];
+          atomicAdd(e.gb + row, g);
+        }
+        // ---- staging + TMA store ----
+        const uint32_t buf = my_stage + (chunk_ctr & (uint32_t)(p.epi_bufs - 1)) * (uint32_t)p.epi_buf_bytes;
+        ++chunk_ctr;
+        if (one) {  // the store that last read this buffer is done
+          if (p.epi_bufs == 4) bulk_wait_read<3>(); else bulk_wait_read<1>();
+        }
+        __syncwarp();
+        if (e.f32_sink) {  // [32 rows][32 fp32], 128-byte rows, SWIZZLE_128B
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const uint32_t dst = buf + (uint32_t)lane * 128u + (uint32_t)((q ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(v[4 * q]),
+                         "f"(v[4 * q + 1]), "f"(v[4 * q + 2]), "f"(v[4 * q + 3])
+                         : "memory");
+          }
+        }
+        if (e.sp_sink) {  // [planes][32 rows][32 bf16], 64-byte rows, SWIZZLE_64B
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int i0 = 8 * q + 2 * u;
+              const int c0 = col_base + i0;
+              const float x0 = c0 < p.N ? v[i0] : (c0 == e.ones_col ? 1.f : 0.f);
+              const float x1 = c0 + 1 < p.N ? v[i0 + 1] : (c0 + 1 == e.ones_col ? 1.f : 0.f);
+              __nv_bfloat16 h0, l0, h1, l1;
+              split_bf16(x0, h0, l0);
+              split_bf16(x1, h1, l1);
+              hw[u] = pack_bf16x2(h0, h1);
+              lw[u] = pack_bf16x2(l0, l1);
+            }
+            const uint32_t dst =
+                buf + sp_off + (uint32_t)lane * 64u + (uint32_t)((q ^ ((lane >> 1) & 3)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(hw[0]),
+                         "r"(hw[1]), "r"(hw[2]), "r"(hw[3])
+                         : "memory");
+            if (e.sp_two)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 2048u),
+                           "r"(lw[0]), "r"(lw[1]), "r"(lw[2]), "r"(lw[3])
+                           : "memory");
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (one && !(p.debug & 1)) {
+          if (e.f32_sink == 1 && col_base < e.f32_cols) tma_store_2d(&tmOut, buf, col_base, row_base);
+          else if (e.f32_sink == 2 && col_base < e.f32_cols) tma_reduce_add_2d(&tmOut, buf, col_base, row_base);
+          if (e.sp_sink && col_base < e.sp_cols) tma_store_3d(&tmSp, buf + sp_off, col_base, row_base, 0);
+          bulk_commit();
+        }
+      }
+    }
+    if (e.score && row_ok) e.score[row] = score_acc;
+}
+
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 nrl_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmSp,
@@ -132,7 +274,7 @@ nrl_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const uint32_t b_bytes = p.mn_major ? b_boxes * 8192u : (uint32_t)p.BN * 128u;
   const uint32_t stage_bytes = (uint32_t)p.planes * (GEMM_A_BYTES + b_bytes);
   const uint32_t epi_base = smem_base + (uint32_t)p.stages * stage_bytes;
-  const uint32_t bar_base = epi_base + 8u * (uint32_t)p.epi_buf_bytes;
+  const uint32_t bar_base = epi_base + 4u * (uint32_t)p.epi_bufs * (uint32_t)p.epi_buf_bytes;
   // barrier layout (8 B each): full[S], empty[S], tmem_full[2], tmem_empty[2], then tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (GEMM_MAX_STAGES + s); };
@@ -140,8 +282,12 @@ nrl_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * GEMM_MAX_STAGES + 2 + s); };
   const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * GEMM_MAX_STAGES + 4);
 
-  const int warp = threadIdx.x >> 5;
+  // warp-uniform warp index and ONE elected lane per warp: inside `if (one)` the compiler knows a
+  // single thread is active, so TMA / tcgen05 operands go straight to uniform registers (with
+  // `lane == 0` it emits a vote loop around every UTMALDG / UTCHMMA / UTMASTG)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
+  const bool one = elect_one();
 
   const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
   const int n_tiles = (p.n_extent + p.BN - 1) / p.BN;
@@ -177,7 +323,7 @@ nrl_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (one) {
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = stage_bytes;
@@ -210,7 +356,7 @@ nrl_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (one) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -259,7 +405,7 @@ nrl_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     // ===================== epilogue warps (2..5) =====================
     const GemmEpi& e = p.epi;
     const int quarter = warp & 3;  // TMEM lane quarter this warp may touch
-    const uint32_t my_stage = epi_base + (uint32_t)(warp - 2) * 2u * (uint32_t)p.epi_buf_bytes;
+    const uint32_t my_stage = epi_base + (uint32_t)(warp - 2) * (uint32_t)p.epi_bufs * (uint32_t)p.epi_buf_bytes;
     const uint32_t sp_off = e.f32_sink ? 4096u : 0u;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -270,139 +416,16 @@ nrl_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (t.kb0 >= t.kb1) continue;
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
-        const int row_base = t.m0 + quarter * 32;
-        const int row = row_base + lane;
-        const bool row_ok = row < p.M;
         const uint32_t t_row = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(quarter * 32) << 16);
-        float score_acc = 0.f;
-        float addw = 0.f;
-        const float* addv = nullptr;
-        if (e.add_w && row_ok) {
-          addw = __ldg(e.add_w + row);
-          addv = e.add_vec + (long long)(row / e.add_L) * e.ld_addvec;
-        }
-        for (int c = 0; c < t.n_cur; c += 32) {
-          const int col_base = t.n0 + c;
-          float v[32];
-          if (c + 16 < t.n_cur) {
-            tmem_ld32(t_row + (uint32_t)c, v);
-          } else {
-            tmem_ld16(t_row + (uint32_t)c, v);
-#pragma unroll
-            for (int i = 16; i < 32; ++i) v[i] = 0.f;
-          }
-          if (row_base < p.M) {  // warp-uniform: rows past M produce nothing
-            if (addv) {
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                if (col_base + 4 * q < p.N) {
-                  const float4 a4 = __ldg(reinterpret_cast<const float4*>(addv + col_base) + q);
-                  v[4 * q] += addw * a4.x; v[4 * q + 1] += addw * a4.y;
-                  v[4 * q + 2] += addw * a4.z; v[4 * q + 3] += addw * a4.w;
-                }
-              }
-            }
-            if (e.relu) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-            }
-            if (e.drop_words) {  // col_base % 32 == 0: one word holds this chunk's keep-bits
-              const uint32_t bits =
-                  row_ok ? __ldg(e.drop_words + (long long)row * e.drop_mw + (col_base >> 5)) : 0u;
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = ((bits >> i) & 1u) ? v[i] * e.drop_scale : 0.f;
-            }
-            if (e.pos_mask && row_ok) {
-              const float* pm = e.pos_mask + (long long)row * e.ld_pos + col_base;
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                if (col_base + 4 * q < p.N) {
-                  const float4 m4 = __ldg(reinterpret_cast<const float4*>(pm) + q);
-                  if (!(m4.x > 0.f)) v[4 * q] = 0.f;
-                  if (!(m4.y > 0.f)) v[4 * q + 1] = 0.f;
-                  if (!(m4.z > 0.f)) v[4 * q + 2] = 0.f;
-                  if (!(m4.w > 0.f)) v[4 * q + 3] = 0.f;
-                }
-              }
-            }
-            if (e.qvec) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                float a = 0.f;
-                if (col_base + i < p.N) {
-                  a = tanh_fast(v[i]);
-                  score_acc += a * __ldg(e.qvec + col_base + i);
-                }
-                v[i] = a;
-              }
-            }
-            if (e.gb && row_ok && e.gb_col >= col_base && e.gb_col < col_base + 32) {
-              float g = 0.f;
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (col_base + i == e.gb_col) g = v[i];
-              atomicAdd(e.gb + row, g);
-            }
-            // ---- staging + TMA store ----
-            const uint32_t buf = my_stage + (chunk_ctr & 1u) * (uint32_t)p.epi_buf_bytes;
-            ++chunk_ctr;
-            if (lane == 0) bulk_wait_read<1>();  // the store that last read this buffer is done
-            __syncwarp();
-            if (e.f32_sink) {  // [32 rows][32 fp32], 128-byte rows, SWIZZLE_128B
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const uint32_t dst = buf + (uint32_t)lane * 128u + (uint32_t)((q ^ (lane & 7)) << 4);
-                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(v[4 * q]),
-                             "f"(v[4 * q + 1]), "f"(v[4 * q + 2]), "f"(v[4 * q + 3])
-                             : "memory");
-              }
-            }
-            if (e.sp_sink) {  // [planes][32 rows][32 bf16], 64-byte rows, SWIZZLE_64B
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                uint32_t hw[4], lw[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  const int i0 = 8 * q + 2 * u;
-                  const int c0 = col_base + i0;
-                  const float x0 = c0 < p.N ? v[i0] : (c0 == e.ones_col ? 1.f : 0.f);
-                  const float x1 = c0 + 1 < p.N ? v[i0 + 1] : (c0 + 1 == e.ones_col ? 1.f : 0.f);
-                  __nv_bfloat16 h0, l0, h1, l1;
-                  split_bf16(x0, h0, l0);
-                  split_bf16(x1, h1, l1);
-                  hw[u] = pack_bf16x2(h0, h1);
-                  lw[u] = pack_bf16x2(l0, l1);
-                }
-                const uint32_t dst =
-                    buf + sp_off + (uint32_t)lane * 64u + (uint32_t)((q ^ ((lane >> 1) & 3)) << 4);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(hw[0]),
-                             "r"(hw[1]), "r"(hw[2]), "r"(hw[3])
-                             : "memory");
-                if (e.sp_two)
-                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 2048u),
-                               "r"(lw[0]), "r"(lw[1]), "r"(lw[2]), "r"(lw[3])
-                               : "memory");
-              }
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-              if (e.f32_sink == 1 && col_base < e.f32_cols) tma_store_2d(&tmOut, buf, col_base, row_base);
-              else if (e.f32_sink == 2 && col_base < e.f32_cols) tma_reduce_add_2d(&tmOut, buf, col_base, row_base);
-              if (e.sp_sink && col_base < e.sp_cols) tma_store_3d(&tmSp, buf + sp_off, col_base, row_base, 0);
-              bulk_commit();
-            }
-          }
-        }
-        if (e.score && row_ok) e.score[row] = score_acc;
+        gemm_epilogue_tile(p, &tmOut, &tmSp, t, t_row, quarter, lane, my_stage, sp_off, chunk_ctr, one);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (one) mbar_arrive(tempty_bar(acc));
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
     }
-    if (lane == 0) bulk_wait<0>();
+    if (one) bulk_wait<0>();
   }
 
   tc_fence_before();
@@ -410,6 +433,193 @@ nrl_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, GEMM_TMEM_COLS);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2) of the NT GEMM for the big row-streaming GEMMs.
+// Two CTAs of a cluster (one TPC) own 256 consecutive rows: each loads ITS 128 rows of A and
+// HALF of the B tile (BN / 2 weight rows) per k-block, the leader's MMA thread issues M = 256
+// tcgen05.mma.cta_group::2 instructions that read both CTAs' shared memory and write each CTA's
+// half of the accumulator into that CTA's TMEM.  Per SM this halves the B bytes pulled from L2 per
+// flop -- the 1-CTA kernel is bound by the L2 -> SM fill rate, not by the tensor pipe -- and the
+// smaller stage (A 32 KB + B/2) leaves room for a 3-deep ring.
+//   barriers (same offsets in both CTAs): full[s]  -- used in the LEADER only: 1 arrival (leader
+//   producer, expect_tx of both CTAs' bytes) + the TMA bytes of both CTAs; empty[s] / tmem_full[a]
+//   -- one multicast tcgen05.commit arrival in each CTA; tmem_empty[a] -- leader only, 8 arrivals
+//   (4 epilogue warps of each CTA, the peer's through mapa).
+// Work unit = one 256-row block with all its n-tiles; no split-K (weight gradients stay 1-CTA).
+// ------------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+nrl_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmSp,
+                    const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t half_n = (uint32_t)p.BN / 2u;  // B rows held by each CTA (multiple of 8)
+  const uint32_t b_bytes = half_n * 128u;
+  const uint32_t stage_bytes = (uint32_t)p.planes * (GEMM_A_BYTES + b_bytes);
+  const uint32_t epi_base = smem_base + (uint32_t)p.stages * stage_bytes;
+  const uint32_t bar_base = epi_base + 4u * (uint32_t)p.epi_bufs * (uint32_t)p.epi_buf_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (GEMM_MAX_STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * GEMM_MAX_STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * GEMM_MAX_STAGES + 2 + s); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * GEMM_MAX_STAGES + 4);
+
+  // warp-uniform warp index and ONE elected lane per warp: inside `if (one)` the compiler knows a
+  // single thread is active, so TMA / tcgen05 operands go straight to uniform registers (with
+  // `lane == 0` it emits a vote loop around every UTMALDG / UTCHMMA / UTMASTG)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const bool one = elect_one();
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  const int m_pairs = (p.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+  const int n_tiles = (p.n_extent + p.BN - 1) / p.BN;
+  const int kb_total = (p.K + GEMM_BK - 1) / GEMM_BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 8);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (p.epi.f32_sink) tma_prefetch_desc(&tmOut);
+    if (p.epi.sp_sink) tma_prefetch_desc(&tmSp);
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_ptr_addr, GEMM_TMEM_COLS);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barriers of BOTH CTAs are initialised before anybody signals them
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+
+  auto tile_of = [&](int unit, int j) {
+    GemmTile t;
+    t.m0 = unit * 2 * GEMM_BM + (int)rank * GEMM_BM;  // this CTA's 128 rows
+    t.n0 = j * p.BN;
+    t.n_cur = min(p.BN, (p.n_extent - t.n0 + 15) & ~15);
+    t.kb0 = 0;
+    t.kb1 = kb_total;
+    return t;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (one) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int unit = cluster_id; unit < m_pairs; unit += num_clusters) {
+        for (int j = 0; j < n_tiles; ++j) {
+          const GemmTile t = tile_of(unit, j);
+          const int b_row0 = t.n0 + (int)rank * (t.n_cur / 2);  // my half of the n_cur weight rows
+          for (int kb = 0; kb < kb_total; ++kb) {
+            mbar_wait_cluster(empty_bar(stage), phase ^ 1u);
+            const uint32_t lead_full = mapa_shared(full_bar(stage), 0);
+            if (leader) mbar_expect_tx(full_bar(stage), 2u * stage_bytes);
+            const uint32_t a_dst = smem_base + stage * stage_bytes;
+            const uint32_t b_dst = a_dst + (uint32_t)p.planes * GEMM_A_BYTES;
+            for (int pl = 0; pl < p.planes; ++pl) {
+              tma_load_3d_pair(a_dst + pl * GEMM_A_BYTES, &tmA, lead_full, kb * GEMM_BK, t.m0, pl);
+              tma_load_3d_pair(b_dst + pl * b_bytes, &tmB, lead_full, kb * GEMM_BK, b_row0, pl);
+            }
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (one && leader) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int unit = cluster_id; unit < m_pairs; unit += num_clusters) {
+        for (int j = 0; j < n_tiles; ++j) {
+          const GemmTile t = tile_of(unit, j);
+          const uint32_t idesc = umma_idesc_bf16(2 * GEMM_BM, t.n_cur, 0, 0);
+          mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+          uint32_t accumulate = 0;
+          for (int kb = 0; kb < kb_total; ++kb) {
+            mbar_wait_cluster(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t a_src = smem_base + stage * stage_bytes;
+            const uint32_t b_src = a_src + (uint32_t)p.planes * GEMM_A_BYTES;
+            const int nks = min(GEMM_BK / 16, (p.K - kb * GEMM_BK + 15) / 16);
+            for (int k = 0; k < nks; ++k) {
+              const uint32_t koff = k * 32;
+              const uint64_t a_hi = umma_desc_sw128(a_src + koff, 16, 1024);
+              const uint64_t b_hi = umma_desc_sw128(b_src + koff, 16, 1024);
+              if (p.planes == 2) {
+                const uint64_t a_lo = umma_desc_sw128(a_src + GEMM_A_BYTES + koff, 16, 1024);
+                const uint64_t b_lo = umma_desc_sw128(b_src + b_bytes + koff, 16, 1024);
+                umma_bf16_pair(d_tmem, a_lo, b_hi, idesc, accumulate);
+                umma_bf16_pair(d_tmem, a_hi, b_lo, idesc, 1);
+                umma_bf16_pair(d_tmem, a_hi, b_hi, idesc, 1);
+              } else {
+                umma_bf16_pair(d_tmem, a_hi, b_hi, idesc, accumulate);
+              }
+              accumulate = 1;
+            }
+            umma_commit_pair(empty_bar(stage));  // frees the slot in both CTAs
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+          umma_commit_pair(tfull_bar(acc));  // accumulator halves ready in both CTAs
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5), both CTAs =====================
+    const GemmEpi& e = p.epi;
+    const int quarter = warp & 3;
+    const uint32_t my_stage = epi_base + (uint32_t)(warp - 2) * (uint32_t)p.epi_bufs * (uint32_t)p.epi_buf_bytes;
+    const uint32_t sp_off = e.f32_sink ? 4096u : 0u;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t chunk_ctr = 0;
+    for (int unit = cluster_id; unit < m_pairs; unit += num_clusters) {
+      for (int j = 0; j < n_tiles; ++j) {
+        const GemmTile t = tile_of(unit, j);
+        mbar_wait_cluster(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(quarter * 32) << 16);
+        gemm_epilogue_tile(p, &tmOut, &tmSp, t, t_row, quarter, lane, my_stage, sp_off, chunk_ctr, one);
+        tc_fence_before();
+        __syncwarp();
+        if (one) {
+          if (leader) mbar_arrive(tempty_bar(acc));
+          else mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+    if (one) bulk_wait<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the leader's MMAs read the peer's shared memory: nobody leaves early
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, GEMM_TMEM_COLS);
   }
 }
 

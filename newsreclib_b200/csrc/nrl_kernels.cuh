@@ -142,7 +142,7 @@ __host__ __device__ constexpr int attn_stream_warps(int dh) { return dh <= 32 ? 
 
 template <int DH>
 __global__ void __launch_bounds__(32 * attn_stream_warps(DH))
-attn_fwd_kernel(const float* __restrict__ qkv, int E, int heads, int S, long long seq_stride,
+attn_fwd_kernel(const float* __restrict__ qkv, int E, int ldq, int heads, int S, long long seq_stride,
                 int NB, long long batch_stride, float scale, __nv_bfloat16* __restrict__ o_hi,
                 __nv_bfloat16* __restrict__ o_lo, int ep, float* __restrict__ lse) {
   __shared__ __align__(16) float sk[attn_stream_warps(DH)][32 * DH];
@@ -151,7 +151,7 @@ attn_fwd_kernel(const float* __restrict__ qkv, int E, int heads, int S, long lon
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qchunks = (S + 31) / 32;
   const long long items = (long long)NB * heads * qchunks;
-  const int ld = 3 * E;
+  const int ld = ldq;
   for (long long it = blockIdx.x * (long long)NW + warp; it < items; it += gridDim.x * (long long)NW) {
     const int qc = (int)(it % qchunks);
     const int h = (int)((it / qchunks) % heads);
@@ -243,7 +243,7 @@ template <int DH>
 __global__ void __launch_bounds__(32 * attn_stream_warps(DH))
 attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o, long long ld_do,
                 const __nv_bfloat16* __restrict__ o_hi, const __nv_bfloat16* __restrict__ o_lo,
-                int ep, const float* __restrict__ lse, int E, int heads, int S,
+                int ep, const float* __restrict__ lse, int E, int ldq, int heads, int S,
                 long long seq_stride, int NB, long long batch_stride, float scale,
                 __nv_bfloat16* __restrict__ g_hi, __nv_bfloat16* __restrict__ g_lo, int p3) {
   // per-warp staging: "x" rows (k/v in phase A, q/dO in phase B), plus lse / D per row
@@ -254,7 +254,7 @@ attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o, lo
   constexpr int NW = attn_stream_warps(DH);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long items = (long long)NB * heads;
-  const int ld = 3 * E;
+  const int ld = ldq;
   const int chunks = (S + 31) / 32;
   auto store_split = [&](long long row, int col, const float* v) {
     const long long off = row * p3 + col;
@@ -412,14 +412,14 @@ attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o, lo
 // ------------------------------------------------------------------------------------
 template <int DH>
 __global__ void __launch_bounds__(256, DH <= 32 ? 2 : 1)
-attn_fwd_tile_kernel(const float* __restrict__ qkv, int E, int heads, int S, long long seq_stride,
+attn_fwd_tile_kernel(const float* __restrict__ qkv, int E, int ldq, int heads, int S, long long seq_stride,
                      int NB, long long batch_stride, float scale, int hp,
                      __nv_bfloat16* __restrict__ o_hi, __nv_bfloat16* __restrict__ o_lo, int ep,
                      float* __restrict__ lse) {
   extern __shared__ __align__(16) float tile[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int passes = (heads + hp - 1) / hp;
-  const int ld = 3 * E;
+  const int ld = ldq;
   const int qchunks = (S + 31) / 32;
   for (long long work = blockIdx.x; work < (long long)NB * passes; work += gridDim.x) {
     const int b = (int)(work / passes), pass = (int)(work % passes);
@@ -514,13 +514,13 @@ attn_fwd_tile_kernel(const float* __restrict__ qkv, int E, int heads, int S, lon
 template <int DH>
 __global__ void __launch_bounds__(256, DH <= 32 ? 2 : 1)
 attn_bwd_tile_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o, long long ld_do,
-                     const float* __restrict__ lse, int E, int heads, int S, long long seq_stride,
+                     const float* __restrict__ lse, int E, int ldq, int heads, int S, long long seq_stride,
                      int NB, long long batch_stride, float scale, int hp,
                      __nv_bfloat16* __restrict__ g_hi, __nv_bfloat16* __restrict__ g_lo, int p3) {
   extern __shared__ __align__(16) float tile[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int passes = (heads + hp - 1) / hp;
-  const int ld = 3 * E;
+  const int ld = ldq;
   const int chunks = (S + 31) / 32;
   for (long long work = blockIdx.x; work < (long long)NB * passes; work += gridDim.x) {
     const int b = (int)(work / passes), pass = (int)(work % passes);
@@ -702,13 +702,13 @@ __device__ __forceinline__ TileMap tile_map(int per_row) {
 
 template <int DH>
 __global__ void __launch_bounds__(160, 4)
-attn_fwd_s32_kernel(const float* __restrict__ qkv, int E, int heads, int S, long long seq_stride,
+attn_fwd_s32_kernel(const float* __restrict__ qkv, int E, int ldq, int heads, int S, long long seq_stride,
                     int NB, long long batch_stride, float scale, __nv_bfloat16* __restrict__ o_hi,
                     __nv_bfloat16* __restrict__ o_lo, int ep, float* __restrict__ lse) {
   extern __shared__ __align__(16) float tile[];  // [S][P]: q | k | v of the head group
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, hg = blockDim.x >> 5;
   const int groups = (heads + hg - 1) / hg;
-  const int ld = 3 * E;
+  const int ld = ldq;
   const float qscale = scale * NRL_LOG2E;  // scores live in the log2 domain: p = 2^(s - m)
   for (long long work = blockIdx.x; work < (long long)NB * groups; work += gridDim.x) {
     const int b = (int)(work / groups), grp = (int)(work % groups);
@@ -837,13 +837,13 @@ attn_fwd_s32_kernel(const float* __restrict__ qkv, int E, int heads, int S, long
 template <int DH>
 __global__ void __launch_bounds__(160, 3)
 attn_bwd_s32_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o, long long ld_do,
-                    const float* __restrict__ lse, int E, int heads, int S, long long seq_stride,
+                    const float* __restrict__ lse, int E, int ldq, int heads, int S, long long seq_stride,
                     int NB, long long batch_stride, float scale, __nv_bfloat16* __restrict__ g_hi,
                     __nv_bfloat16* __restrict__ g_lo, int p3) {
   extern __shared__ __align__(16) float tile[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, hg = blockDim.x >> 5;
   const int groups = (heads + hg - 1) / hg;
-  const int ld = 3 * E;
+  const int ld = ldq;
   const int Pmax = attn_pitch(4 * hg * DH);
   const float qscale = scale * NRL_LOG2E;
   float* tbuf = tile + S * Pmax + warp * (32 * 33);

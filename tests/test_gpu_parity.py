@@ -33,6 +33,25 @@ def test_gemm_nt_tcgen05(shape):
     assert e3 < 3e-5 and e1 < 2e-2
 
 
+@pytest.mark.parametrize("shape", [(19000, 304, 304), (19137, 900, 304), (40000, 208, 208), (19000, 300, 912)])
+def test_gemm_nt_cta_pair(shape):
+    """M >= 74 row-pairs of 256 routes the NT GEMM to the cta_group::2 kernel (CTA pairs, M = 256 MMAs,
+    half of the B tile per CTA); ragged M (19137) exercises the all-out-of-bounds peer tile."""
+    from newsreclib_b200 import ops
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M + N)
+    A = torch.randn(M, K, generator=g).cuda()
+    B = torch.randn(N, K, generator=g).cuda()
+    ref = (A.double() @ B.double().t())
+    D3 = ops.gemm_test(A, B, False, ops.PREC_BF16X3)
+    D1 = ops.gemm_test(A, B, False, ops.PREC_BF16)
+    torch.cuda.synchronize()
+    assert rel_err(D3, ref) < 3e-5 and rel_err(D1, ref) < 2e-2
+    out = ops.gemm_test_planes(A, B).cpu()
+    assert rel_err(out[:, :N], ref) < 4e-5
+    assert torch.all(out[:, N] == 1.0) and torch.all(out[:, N + 1:] == 0.0)
+
+
 @pytest.mark.parametrize("shape", [(128, 16, 16), (300, 208, 304), (1000, 300, 304), (4000, 900, 304)])
 def test_gemm_plane_sink(shape):
     """The bf16 hi/lo plane sink (TMA store of a [2, 32, 32] box): values, ones column, zero pad."""
