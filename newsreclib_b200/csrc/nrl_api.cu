@@ -482,6 +482,10 @@ static void launch_attn_fwd(const Ctx& c, const Dims& d, const AttnGeom& g, cons
   const size_t per_head = (size_t)g.S * 3 * DH * sizeof(float);
   int hp = (int)(ATTN_FWD_SMEM_BUDGET / per_head);
   if (hp > d.H) hp = d.H;
+  {  // one (head, 32-query chunk) item per warp (8 warps): more, shorter CTAs fill the machine
+    const int per_cta = 8 / ((g.S + 31) / 32);
+    if (hp > per_cta && per_cta >= 1) hp = per_cta;
+  }
   if (hp >= 1) {  // tile-resident fast path
     const int passes = (d.H + hp - 1) / hp;
     attn_fwd_tile_kernel<DH><<<grid_for((long long)g.NB * passes, 1, 8 * g_dev.sm_count), 256, hp * per_head, c.stream>>>(
@@ -517,6 +521,10 @@ static void launch_attn_bwd(const Ctx& c, const Dims& d, const AttnGeom& g, cons
   const size_t per_head = (size_t)g.S * (5 * DH + 2) * sizeof(float);
   int hp = (int)(ATTN_BWD_SMEM_BUDGET / per_head);
   if (hp > d.H) hp = d.H;
+  {
+    const int per_cta = 8 / ((g.S + 31) / 32);
+    if (hp > per_cta && per_cta >= 1) hp = per_cta;
+  }
   if (hp >= 1) {
     const int passes = (d.H + hp - 1) / hp;
     attn_bwd_tile_kernel<DH><<<grid_for((long long)g.NB * passes, 1, 8 * g_dev.sm_count), 256, hp * per_head, c.stream>>>(

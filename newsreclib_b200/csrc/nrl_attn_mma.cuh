@@ -25,7 +25,7 @@ namespace nrl {
 
 __device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2,
                                           uint32_t a3, uint32_t b0, uint32_t b1) {
-  asm volatile(
+  asm(
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, "
       "{%8, %9}, {%0, %1, %2, %3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
@@ -33,7 +33,7 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a
 }
 __device__ __forceinline__ uint32_t movm_t(uint32_t x) {
   uint32_t y;
-  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(y) : "r"(x));
+  asm("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(y) : "r"(x));
   return y;
 }
 // (x, y) -> packed bf16x2 hi (x in the low half) and the bf16x2 of the residuals
@@ -74,49 +74,70 @@ __device__ __forceinline__ void load_blocks(Blk& m, const float* __restrict__ ba
   }
 }
 
+// The three passes of a k-step are issued pass-major (all (i, j) tiles of one pass, then the next
+// pass): consecutive HMMAs then hit different accumulators instead of forming a dependent chain of
+// three on the same tile.
 // c[i][j] += sum over k-steps  A(i, kk) * B(j, kk)   with A blocks a[2i + ..][2kk + ..] (row layout,
 // M x K) and B given as the row-layout blocks of the [N x K] operand b[j][2kk + ..] ("NT" product).
 template <int KSTEPS, int NT>
 __device__ __forceinline__ void mma_nt(float (&c)[2][4][4], const Blk& a, const Blk& b, bool three) {
 #pragma unroll
-  for (int kk = 0; kk < KSTEPS; ++kk)
+  for (int kk = 0; kk < KSTEPS; ++kk) {
+    if (three) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+          mma_16816(c[i][j], a.l[2 * i][2 * kk], a.l[2 * i + 1][2 * kk], a.l[2 * i][2 * kk + 1],
+                    a.l[2 * i + 1][2 * kk + 1], b.h[j][2 * kk], b.h[j][2 * kk + 1]);
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+          mma_16816(c[i][j], a.h[2 * i][2 * kk], a.h[2 * i + 1][2 * kk], a.h[2 * i][2 * kk + 1],
+                    a.h[2 * i + 1][2 * kk + 1], b.l[j][2 * kk], b.l[j][2 * kk + 1]);
+    }
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int j = 0; j < NT; ++j) {
-        if (three) {
-          mma_16816(c[i][j], a.l[2 * i][2 * kk], a.l[2 * i + 1][2 * kk], a.l[2 * i][2 * kk + 1],
-                    a.l[2 * i + 1][2 * kk + 1], b.h[j][2 * kk], b.h[j][2 * kk + 1]);
-          mma_16816(c[i][j], a.h[2 * i][2 * kk], a.h[2 * i + 1][2 * kk], a.h[2 * i][2 * kk + 1],
-                    a.h[2 * i + 1][2 * kk + 1], b.l[j][2 * kk], b.l[j][2 * kk + 1]);
-        }
+      for (int j = 0; j < NT; ++j)
         mma_16816(c[i][j], a.h[2 * i][2 * kk], a.h[2 * i + 1][2 * kk], a.h[2 * i][2 * kk + 1],
                   a.h[2 * i + 1][2 * kk + 1], b.h[j][2 * kk], b.h[j][2 * kk + 1]);
-      }
+  }
 }
 // c[i][j] += A(i, kk) * B(kk, j) with B given as row-layout blocks of the [K x N] operand
 // b[2kk + ..][j] ("NN" product: the B fragments are the movmatrix transposes of those blocks).
 template <int NT>
 __device__ __forceinline__ void mma_nn(float (&c)[2][4][4], const Blk& a, const Blk& b, bool three) {
 #pragma unroll
-  for (int kk = 0; kk < 2; ++kk)
+  for (int kk = 0; kk < 2; ++kk) {
+    uint32_t bh[NT][2], bl[NT][2];
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
-      const uint32_t bh0 = movm_t(b.h[2 * kk][j]), bh1 = movm_t(b.h[2 * kk + 1][j]);
-      uint32_t bl0 = 0u, bl1 = 0u;
-      if (three) { bl0 = movm_t(b.l[2 * kk][j]); bl1 = movm_t(b.l[2 * kk + 1][j]); }
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        if (three) {
-          mma_16816(c[i][j], a.l[2 * i][2 * kk], a.l[2 * i + 1][2 * kk], a.l[2 * i][2 * kk + 1],
-                    a.l[2 * i + 1][2 * kk + 1], bh0, bh1);
-          mma_16816(c[i][j], a.h[2 * i][2 * kk], a.h[2 * i + 1][2 * kk], a.h[2 * i][2 * kk + 1],
-                    a.h[2 * i + 1][2 * kk + 1], bl0, bl1);
-        }
-        mma_16816(c[i][j], a.h[2 * i][2 * kk], a.h[2 * i + 1][2 * kk], a.h[2 * i][2 * kk + 1],
-                  a.h[2 * i + 1][2 * kk + 1], bh0, bh1);
-      }
+      bh[j][0] = movm_t(b.h[2 * kk][j]); bh[j][1] = movm_t(b.h[2 * kk + 1][j]);
+      bl[j][0] = three ? movm_t(b.l[2 * kk][j]) : 0u; bl[j][1] = three ? movm_t(b.l[2 * kk + 1][j]) : 0u;
     }
+    if (three) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+          mma_16816(c[i][j], a.l[2 * i][2 * kk], a.l[2 * i + 1][2 * kk], a.l[2 * i][2 * kk + 1],
+                    a.l[2 * i + 1][2 * kk + 1], bh[j][0], bh[j][1]);
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+          mma_16816(c[i][j], a.h[2 * i][2 * kk], a.h[2 * i + 1][2 * kk], a.h[2 * i][2 * kk + 1],
+                    a.h[2 * i + 1][2 * kk + 1], bl[j][0], bl[j][1]);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+        mma_16816(c[i][j], a.h[2 * i][2 * kk], a.h[2 * i + 1][2 * kk], a.h[2 * i][2 * kk + 1],
+                  a.h[2 * i + 1][2 * kk + 1], bh[j][0], bh[j][1]);
+  }
 }
 // c[i][j] += sum_t X[t][16 i + ..] * Y[t][8 j + ..]  ("TN" product, reduction over the ROWS of both
 // operands): A fragments are movmatrix transposes of X's blocks, B fragments those of Y's blocks,
@@ -131,24 +152,32 @@ __device__ __forceinline__ void mma_tn(float (&c)[2][4][4], const Blk& x, const 
       bh[j][0] = movm_t(y.h[2 * kk][j]); bh[j][1] = movm_t(y.h[2 * kk + 1][j]);
       bl[j][0] = three ? movm_t(y.l[2 * kk][j]) : 0u; bl[j][1] = three ? movm_t(y.l[2 * kk + 1][j]) : 0u;
     }
+    uint32_t ah[2][4], al[2][4];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      const uint32_t ah0 = movm_t(x.h[2 * kk][2 * i]), ah1 = movm_t(x.h[2 * kk][2 * i + 1]);
-      const uint32_t ah2 = movm_t(x.h[2 * kk + 1][2 * i]), ah3 = movm_t(x.h[2 * kk + 1][2 * i + 1]);
-      uint32_t al0 = 0u, al1 = 0u, al2 = 0u, al3 = 0u;
-      if (three) {
-        al0 = movm_t(x.l[2 * kk][2 * i]); al1 = movm_t(x.l[2 * kk][2 * i + 1]);
-        al2 = movm_t(x.l[2 * kk + 1][2 * i]); al3 = movm_t(x.l[2 * kk + 1][2 * i + 1]);
-      }
+      ah[i][0] = movm_t(x.h[2 * kk][2 * i]); ah[i][1] = movm_t(x.h[2 * kk][2 * i + 1]);
+      ah[i][2] = movm_t(x.h[2 * kk + 1][2 * i]); ah[i][3] = movm_t(x.h[2 * kk + 1][2 * i + 1]);
 #pragma unroll
-      for (int j = 0; j < NT; ++j) {
-        if (three) {
-          mma_16816(c[i][j], al0, al1, al2, al3, bh[j][0], bh[j][1]);
-          mma_16816(c[i][j], ah0, ah1, ah2, ah3, bl[j][0], bl[j][1]);
-        }
-        mma_16816(c[i][j], ah0, ah1, ah2, ah3, bh[j][0], bh[j][1]);
+      for (int r = 0; r < 4; ++r) al[i][r] = 0u;
+      if (three) {
+        al[i][0] = movm_t(x.l[2 * kk][2 * i]); al[i][1] = movm_t(x.l[2 * kk][2 * i + 1]);
+        al[i][2] = movm_t(x.l[2 * kk + 1][2 * i]); al[i][3] = movm_t(x.l[2 * kk + 1][2 * i + 1]);
       }
     }
+    if (three) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) mma_16816(c[i][j], al[i][0], al[i][1], al[i][2], al[i][3], bh[j][0], bh[j][1]);
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) mma_16816(c[i][j], ah[i][0], ah[i][1], ah[i][2], ah[i][3], bl[j][0], bl[j][1]);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < NT; ++j) mma_16816(c[i][j], ah[i][0], ah[i][1], ah[i][2], ah[i][3], bh[j][0], bh[j][1]);
   }
 }
 // Accumulator tile set c[2][4][4] (rows 16 i + g (+8), cols 8 j + 2 tg (+1)) -> row-layout blocks.
@@ -207,24 +236,33 @@ __device__ __forceinline__ void store_acc_split(const float (&c)[2][4][4], float
     }
 }
 
+// ---- operand sources ------------------------------------------------------------------------
+// Global: matrix m of the item lives at base[m] + r * stride[m] (fp32 rows); rows >= S read as 0.
 template <int DH>
-__global__ void __launch_bounds__(128)
-attn_fwd_mma_kernel(const float* __restrict__ qkv, int E, int ldq, int heads, int S, long long seq_stride,
-                    int NB, long long batch_stride, float scale, __nv_bfloat16* __restrict__ o_hi,
-                    __nv_bfloat16* __restrict__ o_lo, int ep, float* __restrict__ lse) {
+struct GmemSrc {
+  const float* base[4];
+  long long stride[4];
+  int S;
+  __device__ __forceinline__ void load(Blk& m, int which, float mul, int g, int tg) const {
+    load_blocks<DH>(m, base[which], stride[which], S, mul, g, tg);
+  }
+  __device__ __forceinline__ float lse2(const float* lse, long long grow, int heads, int h, int /*r*/) const {
+    return __ldg(lse + grow * heads + h) * NRL_LOG2E;
+  }
+};
+// ---- one (batch item, head) problem, forward ----------------------------------------------------
+template <int DH, class Src>
+__device__ __forceinline__ void attn_fwd_item(const Src& src, int E, int heads, int S, long long seq_stride,
+                                              long long batch_stride, float scale, int b, int h,
+                                              __nv_bfloat16* __restrict__ o_hi, __nv_bfloat16* __restrict__ o_lo,
+                                              int ep, float* __restrict__ lse, int lane) {
   constexpr int KS = (DH + 15) / 16;  // k-steps over the head dim
   constexpr int ND = (DH + 7) / 8;    // 8-column blocks of the head dim
-  const int lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
-  const long long item = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  if (item >= (long long)NB * heads) return;
-  const int b = (int)(item / heads), h = (int)(item % heads);
+  const int g = lane >> 2, tg = lane & 3;
   const bool three = o_lo != nullptr;
-  const int ld = ldq;
-  const float* base = qkv + (long long)b * batch_stride * ld + h * DH;
-  const long long rstride = seq_stride * ld;
   Blk q, k;
-  load_blocks<DH>(q, base, rstride, S, scale * NRL_LOG2E, g, tg);
-  load_blocks<DH>(k, base + E, rstride, S, 1.f, g, tg);
+  src.load(q, 0, scale * NRL_LOG2E, g, tg);
+  src.load(k, 1, 1.f, g, tg);
   float s[2][4][4];
 #pragma unroll
   for (int i = 0; i < 2; ++i)
@@ -266,7 +304,7 @@ attn_fwd_mma_kernel(const float* __restrict__ qkv, int E, int ldq, int heads, in
   Blk p;
   acc_to_blocks(p, s);
   Blk v;
-  load_blocks<DH>(v, base + 2 * E, rstride, S, 1.f, g, tg);
+  src.load(v, 2, 1.f, g, tg);
   float o[2][4][4];
 #pragma unroll
   for (int i = 0; i < 2; ++i)
@@ -296,37 +334,30 @@ attn_fwd_mma_kernel(const float* __restrict__ qkv, int E, int ldq, int heads, in
   }
 }
 
-// Backward.  P is recomputed from Q, K and the saved log-sum-exp; D = rowsum(P * dP).
-// Writes dQ | dK | dV as split planes [2][R][p3].
-template <int DH>
-__global__ void __launch_bounds__(128, 3)
-attn_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o, long long ld_do,
-                    const float* __restrict__ lse, int E, int ldq, int heads, int S, long long seq_stride,
-                    int NB, long long batch_stride, float scale, __nv_bfloat16* __restrict__ g_hi,
-                    __nv_bfloat16* __restrict__ g_lo, int p3) {
+// ---- one (batch item, head) problem, backward ---------------------------------------------------
+// P is recomputed from Q, K and the saved log-sum-exp; D = rowsum(P * dP).  Writes dQ | dK | dV as
+// split planes [2][R][p3].
+template <int DH, class Src>
+__device__ __forceinline__ void attn_bwd_item(const Src& src, const float* __restrict__ lse, int E, int heads,
+                                              int S, long long seq_stride, long long batch_stride, float scale,
+                                              int b, int h, __nv_bfloat16* __restrict__ g_hi,
+                                              __nv_bfloat16* __restrict__ g_lo, int p3, int lane) {
   constexpr int KS = (DH + 15) / 16;
   constexpr int ND = (DH + 7) / 8;
-  const int lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
-  const long long item = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  if (item >= (long long)NB * heads) return;
-  const int b = (int)(item / heads), h = (int)(item % heads);
+  const int g = lane >> 2, tg = lane & 3;
   const bool three = g_lo != nullptr;
-  const int ld = ldq;
-  const float* base = qkv + (long long)b * batch_stride * ld + h * DH;
-  const long long rstride = seq_stride * ld;
   long long grow[4];
 #pragma unroll
   for (int rb = 0; rb < 4; ++rb) grow[rb] = (long long)(8 * rb + g) * seq_stride + (long long)b * batch_stride;
 
   Blk q, k, v, go;
-  load_blocks<DH>(q, base, rstride, S, scale * NRL_LOG2E, g, tg);  // Qs = Q * scale * log2(e)
-  load_blocks<DH>(k, base + E, rstride, S, 1.f, g, tg);
-  load_blocks<DH>(v, base + 2 * E, rstride, S, 1.f, g, tg);
-  load_blocks<DH>(go, d_o + (long long)b * batch_stride * ld_do + h * DH, seq_stride * ld_do, S, 1.f, g, tg);
+  src.load(q, 0, scale * NRL_LOG2E, g, tg);  // Qs = Q * scale * log2(e)
+  src.load(k, 1, 1.f, g, tg);
+  src.load(v, 2, 1.f, g, tg);
+  src.load(go, 3, 1.f, g, tg);
   float lse2[4];
 #pragma unroll
-  for (int rb = 0; rb < 4; ++rb)
-    lse2[rb] = (8 * rb + g < S) ? __ldg(lse + grow[rb] * heads + h) * NRL_LOG2E : 0.f;
+  for (int rb = 0; rb < 4; ++rb) lse2[rb] = (8 * rb + g < S) ? src.lse2(lse, grow[rb], heads, h, 8 * rb + g) : 0.f;
 
   float s[2][4][4], dp[2][4][4];
 #pragma unroll
@@ -396,6 +427,44 @@ attn_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o
       if (g_lo) g_lo[gr * p3 + c] = __float2bfloat16_rn(0.f);
     }
   }
+}
+
+// ---- direct kernels: one warp = one item, operands straight from global memory -------------------
+template <int DH>
+__global__ void __launch_bounds__(128)
+attn_fwd_mma_kernel(const float* __restrict__ qkv, int E, int ldq, int heads, int S, long long seq_stride,
+                    int NB, long long batch_stride, float scale, __nv_bfloat16* __restrict__ o_hi,
+                    __nv_bfloat16* __restrict__ o_lo, int ep, float* __restrict__ lse) {
+  const int lane = threadIdx.x & 31;
+  const long long item = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (item >= (long long)NB * heads) return;
+  const int b = (int)(item / heads), h = (int)(item % heads);
+  const float* base = qkv + (long long)b * batch_stride * ldq + h * DH;
+  GmemSrc<DH> src;
+  src.S = S;
+#pragma unroll
+  for (int m = 0; m < 3; ++m) { src.base[m] = base + m * E; src.stride[m] = seq_stride * ldq; }
+  attn_fwd_item<DH>(src, E, heads, S, seq_stride, batch_stride, scale, b, h, o_hi, o_lo, ep, lse, lane);
+}
+
+template <int DH>
+__global__ void __launch_bounds__(128, 3)
+attn_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o, long long ld_do,
+                    const float* __restrict__ lse, int E, int ldq, int heads, int S, long long seq_stride,
+                    int NB, long long batch_stride, float scale, __nv_bfloat16* __restrict__ g_hi,
+                    __nv_bfloat16* __restrict__ g_lo, int p3) {
+  const int lane = threadIdx.x & 31;
+  const long long item = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (item >= (long long)NB * heads) return;
+  const int b = (int)(item / heads), h = (int)(item % heads);
+  const float* base = qkv + (long long)b * batch_stride * ldq + h * DH;
+  GmemSrc<DH> src;
+  src.S = S;
+#pragma unroll
+  for (int m = 0; m < 3; ++m) { src.base[m] = base + m * E; src.stride[m] = seq_stride * ldq; }
+  src.base[3] = d_o + (long long)b * batch_stride * ld_do + h * DH;
+  src.stride[3] = seq_stride * ld_do;
+  attn_bwd_item<DH>(src, lse, E, heads, S, seq_stride, batch_stride, scale, b, h, g_hi, g_lo, p3, lane);
 }
 
 }  // namespace nrl

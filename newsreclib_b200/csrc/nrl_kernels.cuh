@@ -1074,12 +1074,24 @@ pool_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ Y,
   float dq_acc[2] = {0.f, 0.f}, db_acc[2] = {0.f, 0.f};  // qp <= 2 * blockDim (Q <= 256... host checks)
   for (long long g = blockIdx.x; g < G; g += gridDim.x) {
     const long long r0 = g * L;
-    // dw_t = dOut . Y_t  (one warp per row, coalesced over E)
-    for (int t = warp; t < L; t += nw) {
-      float acc = 0.f;
-      for (int c = lane; c < E; c += 32) acc += d_out[g * E + c] * Y[(r0 + t) * E + c];
-      acc = warp_sum(acc);
-      if (lane == 0) s_ds[t] = acc;
+    // dw_t = dOut . Y_t  (one warp per row, coalesced over E; two rows in flight per warp)
+    for (int t = warp; t < L; t += 2 * nw) {
+      const int t2 = t + nw;
+      const bool two = t2 < L;
+      const float* y0 = Y + (r0 + t) * E;
+      const float* y1 = Y + (r0 + (two ? t2 : t)) * E;
+      float acc0 = 0.f, acc1 = 0.f;
+      for (int c = lane; c < E; c += 32) {
+        const float dv = __ldg(d_out + g * E + c);
+        acc0 += dv * __ldg(y0 + c);
+        acc1 += dv * __ldg(y1 + c);
+      }
+      acc0 = warp_sum(acc0);
+      acc1 = warp_sum(acc1);
+      if (lane == 0) {
+        s_ds[t] = acc0;
+        if (two) s_ds[t2] = acc1;
+      }
     }
     __syncthreads();
     float part = 0.f;
@@ -1092,21 +1104,30 @@ pool_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ Y,
         for (int c = threadIdx.x; c < E; c += blockDim.x)
           dY1[(r0 + t) * E + c] = w[r0 + t] * d_out[g * E + c];
     }
-    // single pass over A: dApre (split planes), and the dq / db partial sums of this thread's columns
+    // single pass over A: dApre (split planes), and the dq / db partial sums of this thread's columns;
+    // rows are walked six at a time so that six independent loads are in flight per thread
     int slot = 0;
     for (int j = threadIdx.x; j < qp; j += blockDim.x, ++slot) {
       const bool in = j < Q;
       const float qj = in ? qvec[j] : 0.f;
       float aq = 0.f, ab = 0.f;
-      for (int t = 0; t < L; ++t) {
-        const float a = in ? A[(r0 + t) * Q + j] : 0.f;
-        const float v = s_ds[t] * qj * (1.f - a * a);
-        __nv_bfloat16 hh, ll;
-        split_bf16(v, hh, ll);
-        da_hi[(r0 + t) * qp + j] = hh;
-        if (da_lo) da_lo[(r0 + t) * qp + j] = ll;
-        aq += s_ds[t] * a;
-        ab += v;
+      for (int t0 = 0; t0 < L; t0 += 6) {
+        float a[6];
+#pragma unroll
+        for (int u = 0; u < 6; ++u) a[u] = (in && t0 + u < L) ? __ldg(A + (r0 + t0 + u) * Q + j) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 6; ++u) {
+          if (t0 + u < L) {
+            const float sd = s_ds[t0 + u];
+            const float v = sd * qj * (1.f - a[u] * a[u]);
+            __nv_bfloat16 hh, ll;
+            split_bf16(v, hh, ll);
+            da_hi[(r0 + t0 + u) * qp + j] = hh;
+            if (da_lo) da_lo[(r0 + t0 + u) * qp + j] = ll;
+            aq += sd * a[u];
+            ab += v;
+          }
+        }
       }
       dq_acc[slot] += aq;
       db_acc[slot] += ab;
