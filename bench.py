@@ -250,12 +250,14 @@ def main():
 
     # ---- timed region B: same steps with per-launch events -> roofline of the dominant kernel
     roof = None
+    prof_steps = min(args.steps, 10)
+    torch.cuda.synchronize()
     if rank == 0:
-        torch.cuda.synchronize()
         lib.nrl_profile_start(torch.cuda.current_stream().cuda_stream)
-        prof_steps = min(args.steps, 10)
-        for i in range(prof_steps):
-            step_dev(i)
+    for i in range(prof_steps):  # every rank steps (the steps contain the gradient all-reduce); rank 0 records
+        step_dev(i)
+    torch.cuda.synchronize()
+    if rank == 0:
         import ctypes as C
         maxrec, stride = 200 * prof_steps, 48
         names = C.create_string_buffer(maxrec * stride)
