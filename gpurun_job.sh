@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-timeout 180 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 30 --warmup 5 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err
-cat gpurun_out/bench_n2.json | cut -c1-1500; tail -3 gpurun_out/bench_n2.err | cut -c1-300
+timeout 900 python -m pytest tests -m gpu -q --timeout 240 2>&1 | tail -25
+timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench_x.json; python -c "import json; d=json.load(open('gpurun_out/bench_x.json')); print(round(d['ms_per_step'],3), round(d['roofline']['kernel_ms_per_step'],3), d['roofline']['top_kernels_ms_per_step'])"

@@ -183,6 +183,13 @@ int nrl_to_dense_fwd(const float* x, const int* off, int B, int M, int E, float*
                      void* stream);
 int nrl_to_dense_bwd(const float* d_dense, const int* off, int B, int M, int E, float* dx,
                      void* stream);
+/* ---- device-side collate / cache lookup: out[i, :] = table[idx[i], :] ------------------------
+ * Replaces the per-row pandas .loc + F.pad + vstack of DatasetCollate._tokenize_df
+ * (data/components/rec_dataset.py:170-178,189-285) once the news table is pre-tokenised and
+ * resident in HBM, and gathers cached news vectors in the evaluation path.  Rows are row_bytes
+ * bytes (multiple of 4); idx [n] int64 must lie in [0, n_table_rows). */
+int nrl_gather_rows(const void* table, long long n_table_rows, int row_bytes, const long long* idx,
+                    long long n, void* out, void* stream);
 /* late fusion, nrms_module.py:243-248 */
 int nrl_late_fusion_fwd(const float* hist_vec, const int* off, int B, int E, float* user,
                         void* stream);

@@ -86,6 +86,7 @@ SIGNATURES = {
     "nrl_segment_offsets": (_I, [_VP, _LL, _I, _VP, _VP]),
     "nrl_to_dense_fwd": (_I, [_VP, _VP, _I, _I, _I, _VP, _VP]),
     "nrl_to_dense_bwd": (_I, [_VP, _VP, _I, _I, _I, _VP, _VP]),
+    "nrl_gather_rows": (_I, [_VP, _LL, _I, _VP, _LL, _VP, _VP]),
     "nrl_late_fusion_fwd": (_I, [_VP, _VP, _I, _I, _VP, _VP]),
     "nrl_late_fusion_bwd": (_I, [_VP, _VP, _I, _I, _VP, _VP]),
     "nrl_score_fwd": (_I, [_VP, _VP, _VP, _I, _I, _I, _VP, _VP]),

@@ -997,6 +997,26 @@ int nrl_to_dense_bwd(const float* d_dense, const int* off, int B, int M, int E, 
   return NRL_OK;
 }
 
+int nrl_gather_rows(const void* table, long long n_table_rows, int row_bytes, const long long* idx,
+                    long long n, void* out, void* stream) {
+  if (!table || !idx || !out || n_table_rows <= 0 || n <= 0 || row_bytes <= 0 || (row_bytes & 3))
+    return fail(NRL_ERR_INVALID_ARG, "nrl_gather_rows: bad argument (row_bytes must be a positive multiple of 4)");
+  TRY(device_init());
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool w8 = (row_bytes & 7) == 0 && ((reinterpret_cast<uintptr_t>(table) | reinterpret_cast<uintptr_t>(out)) & 7) == 0;
+  if (w8) {
+    const int words = row_bytes / 8;
+    gather_rows_kernel<unsigned long long><<<grid_for(n * words, 256, 16 * g_dev.sm_count), 256, 0, st>>>(
+        static_cast<const unsigned long long*>(table), words, idx, n, static_cast<unsigned long long*>(out));
+  } else {
+    const int words = row_bytes / 4;
+    gather_rows_kernel<unsigned int><<<grid_for(n * words, 256, 16 * g_dev.sm_count), 256, 0, st>>>(
+        static_cast<const unsigned int*>(table), words, idx, n, static_cast<unsigned int*>(out));
+  }
+  LAUNCH_CHECK("gather_rows");
+  return NRL_OK;
+}
+
 int nrl_late_fusion_fwd(const float* hist_vec, const int* off, int B, int E, float* user, void* stream) {
   if (!hist_vec || !off || !user || B <= 0 || E <= 0) return fail(NRL_ERR_INVALID_ARG, "nrl_late_fusion_fwd: bad argument");
   late_fusion_fwd_kernel<<<B, 128, 0, static_cast<cudaStream_t>(stream)>>>(hist_vec, off, B, E, user);

@@ -91,12 +91,14 @@ __device__ __forceinline__ GemmTile gemm_tile(const GemmParams& p, int tile, int
     n_blk = tile % n_tiles;
     m_blk = tile / n_tiles;
     ks = 0;
-  } else {  // n-major: all tiles of one n-block first (equal-cost tiles are handed out together)
-    const int per_n = m_tiles * p.k_splits;
-    n_blk = tile / per_n;
-    const int r = tile % per_n;
-    m_blk = r % m_tiles;
-    ks = r / m_tiles;
+  } else {  // k-split major, then m-block, n-block fastest: the CTAs of one wave share their A rows
+            // (the n-tiles of one (m-block, k-range) run side by side) and their B rows (all m-blocks
+            // of a k-range) while those are still in L2 -- each operand leaves DRAM once
+    const int per_ks = m_tiles * n_tiles;
+    ks = tile / per_ks;
+    const int r = tile % per_ks;
+    m_blk = r / n_tiles;
+    n_blk = r % n_tiles;
   }
   const int kb_per = (kb_total + p.k_splits - 1) / p.k_splits;
   t.m0 = m_blk * GEMM_BM;

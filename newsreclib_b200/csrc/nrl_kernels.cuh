@@ -1046,7 +1046,16 @@ pool_fwd_kernel(const float* __restrict__ score, const float* __restrict__ Y, in
     __syncthreads();
     for (int c = threadIdx.x; c < E; c += blockDim.x) {
       float acc = 0.f;
-      for (int t = 0; t < L; ++t) acc += sw[t] * Y[(r0 + t) * E + c];
+      const float* yc = Y + r0 * E + c;
+      int t = 0;
+      for (; t + 8 <= L; t += 8) {  // eight independent loads in flight per thread
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(yc + (long long)(t + u) * E);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += sw[t + u] * v[u];
+      }
+      for (; t < L; ++t) acc += sw[t] * __ldg(yc + (long long)t * E);
       out[g * E + c] = acc;
     }
     __syncthreads();
@@ -1371,6 +1380,22 @@ __global__ void dropout_mask_kernel(unsigned char* __restrict__ keep, long long 
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
     keep[i] = drop_keep(seed, site, (unsigned long long)i, thr) ? 1 : 0;
+}
+
+// Row gather out[i, :] = table[idx[i], :] over rows of `words` W-byte words (W = 8 for token-id /
+// label rows, 4 for fp32 rows): the device-side collate (DatasetCollate._tokenize_df,
+// rec_dataset.py:189-285, over a news table already resident in HBM) and the news-vector cache
+// lookup of the evaluation path.  Consecutive threads copy consecutive words: coalesced both ways.
+template <typename Wd>
+__global__ void gather_rows_kernel(const Wd* __restrict__ table, int words, const long long* __restrict__ idx,
+                                   long long n, Wd* __restrict__ out) {
+  const long long total = n * words;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / words;
+    const int w = (int)(i - r * words);
+    out[i] = __ldg(table + idx[r] * words + w);
+  }
 }
 
 // out[i] = hi[i] + lo[i]  (test helper: read back a split-plane GEMM sink)

@@ -45,6 +45,40 @@ class TwoTowerRecommender(AbstractRecommneder):
             user_vector = ops.LateFusionFn.apply(hist_news_vector, off_h, B)
         return DotProduct.ragged(user_vector, cand_news_vector, off_c, B, Cmax)
 
+    # ------------------------------------------------------------------ evaluation with cached news vectors
+    # validation / test re-encode every candidate of every impression
+    # (nrms_module.py:398-535); a news vector only depends on the news (the text encoders attend
+    # within one title and pad tokens are unmasked), so in eval mode the table is encoded ONCE and
+    # an impression batch becomes two row gathers + the user encoder + the scorer.
+    @torch.no_grad()
+    def encode_news_table(self, news: Dict[str, torch.Tensor], chunk: int = 16384) -> torch.Tensor:
+        """Eval-mode news vectors ``[num_news, D]`` for a whole news table (dict of per-news columns)."""
+        from ..components.encoders.news.text import PLM
+        if any(isinstance(m, PLM) for m in self.news_encoder.modules()):
+            raise NotImplementedError("the PLM head attends ACROSS the news of a call (text.py:96): its vectors "
+                                      "depend on the batch composition and cannot be cached per news")
+        was_training = self.training
+        self.eval()
+        n = next(iter(news.values())).shape[0]
+        out = [self.news_encoder({k: v[i:i + chunk].contiguous() for k, v in news.items()}) for i in range(0, n, chunk)]
+        self.train(was_training)
+        return torch.cat(out, dim=0)
+
+    @torch.no_grad()
+    def forward_cached(self, news_vectors: torch.Tensor, hist_rows: torch.Tensor, batch_hist: torch.Tensor,
+                       cand_rows: torch.Tensor, batch_cand: torch.Tensor, B: int) -> torch.Tensor:
+        """Scores ``[B, Cmax]`` from cached news vectors; equals ``forward`` in eval mode."""
+        off_h, off_c = ops.segment_offsets(batch_hist, B), ops.segment_offsets(batch_cand, B)
+        widths = torch.stack([(off_h[1:] - off_h[:-1]).max(), (off_c[1:] - off_c[:-1]).max()]).tolist()
+        Hmax, Cmax = int(widths[0]), int(widths[1])
+        hist = ops.gather_rows(news_vectors, hist_rows)
+        cand = ops.gather_rows(news_vectors, cand_rows)
+        if not self.late_fusion:
+            user = self.user_encoder(ops.ToDenseFn.apply(hist, off_h, B, Hmax))
+        else:
+            user = ops.LateFusionFn.apply(hist, off_h, B)
+        return DotProduct.ragged(user, cand, off_c, B, Cmax)
+
     # ------------------------------------------------------------------ model_step (nrms_module.py:260-362)
     def model_step(self, batch: RecommendationBatch) -> Tuple[torch.Tensor, ...]:
         layout = self._layout(batch)

@@ -113,6 +113,22 @@ def segment_offsets(seg: torch.Tensor, B: int) -> torch.Tensor:
     return off
 
 
+def gather_rows(table: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """``table[idx]`` along dim 0 (``nrl_gather_rows``): token-id / scalar / news-vector rows."""
+    lib = _lib.load()
+    if not table.is_cuda or not table.is_contiguous():
+        raise RuntimeError("table must be a contiguous CUDA tensor (newsreclib_b200 has no CPU path)")
+    idx = _chk(idx.contiguous(), torch.int64, "idx")
+    row_bytes = table[0].numel() * table.element_size() if table.dim() > 1 else table.element_size()
+    if row_bytes % 4:
+        raise RuntimeError("row size must be a multiple of 4 bytes")
+    out = torch.empty((idx.numel(),) + tuple(table.shape[1:]), dtype=table.dtype, device=table.device)
+    if idx.numel():
+        _lib.check(lib.nrl_gather_rows(_p(table), table.shape[0], row_bytes, _p(idx), idx.numel(), _p(out), _stream()),
+                   "nrl_gather_rows")
+    return out
+
+
 def adam_step(p, g, m, v, step: int, lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0) -> None:
     lib = _lib.load()
     for t, n in ((p, "p"), (g, "g"), (m, "m"), (v, "v")):
