@@ -43,6 +43,15 @@ def peaks():
     return 6650.0, 1590.0, 1400.0, "fallback"
 
 
+def gemm_traffic_per_launch():
+    """DRAM bytes per GEMM launch from the committed ncu --set full capture (None if absent)."""
+    p = os.path.join(ROOT, "profiles", "r01e_gemm_traffic.json")
+    try:
+        return json.load(open(p))["dram_bytes_per_launch_avg"]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 # ----------------------------------------------------------------------------------------
 # clocks sampler (nvidia-smi during the timed region)
 # ----------------------------------------------------------------------------------------
@@ -276,10 +285,13 @@ def main():
         achieved = flops_step / (gemm_ms / 1e3) / 1e12
         step_prof_ms = sum(t for t, c in agg.values()) / prof_steps
         top = sorted(((t / prof_steps, nm, c // prof_steps) for nm, (t, c) in agg.items()), reverse=True)[:8]
-        roof = {"bound": "tensor", "kernel": "nrl_gemm_tc_kernel (all 18 tcgen05 GEMM launches of a step)",
+        roof = {"bound": "tensor", "kernel": "nrl_gemm_tc2_kernel / nrl_gemm_tc_kernel (all 18 tcgen05 GEMM launches of a step)",
                 "achieved": achieved, "peak": tf_sust, "unit": "TFLOP/s", "frac": achieved / tf_sust,
                 "peak_source": f"{src} bf16 dense, sustained (kernel timed inside a long step)",
-                "traffic": None, "algorithmic_gflop_per_step": flops_step / 1e9,
+                "traffic": gemm_traffic_per_launch(), "traffic_unit": "bytes of DRAM traffic per GEMM launch "
+                "(ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the step's 18 launches; "
+                "profiles/r01e_gemm_traffic.json)",
+                "algorithmic_gflop_per_step": flops_step / 1e9,
                 "issued_passes": 3 if prec == ops.PREC_BF16X3 else 1,
                 "kernel_ms_per_step": gemm_ms, "launches_per_step": gemm_launches,
                 "share_of_step": gemm_ms / step_prof_ms,
