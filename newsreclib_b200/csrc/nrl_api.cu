@@ -259,9 +259,9 @@ static int make_tmap_planes(CUtensorMap* m, const bf16* base, unsigned long long
   return NRL_OK;
 }
 
-// staging buffers per epilogue warp (NRL_GEMM_EPI_BUFS=4: experiment with deeper TMA-store pipelining)
+// staging buffers per epilogue warp: 8 warps x 1 buffer = the smem of the old 4 x 2 (NRL_GEMM_EPI_BUFS=2: experiment)
 static int epi_bufs_cfg() {
-  static const int v = [] { const char* e = getenv("NRL_GEMM_EPI_BUFS"); return (e && atoi(e) == 4) ? 4 : 2; }();
+  static const int v = [] { const char* e = getenv("NRL_GEMM_EPI_BUFS"); return (e && atoi(e) == 2) ? 2 : 1; }();
   return v;
 }
 
@@ -290,17 +290,17 @@ static int launch_gemm(const Ctx& c, GemmParams& p, const CUtensorMap& ta, const
     p.epi.ones_col = sk.ones_col;
   }
   p.epi_buf_bytes = (sk.f32 && sk.sp) ? 8192 : 4096;
-  p.epi_bufs = p.pair ? epi_bufs_cfg() : 2;
+  p.epi_bufs = epi_bufs_cfg();
   static const int dbg = [] { const char* e = getenv("NRL_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
   p.debug = dbg;
   if (p.pair) {  // CTA pairs (cta_group::2): each CTA stages its 128 rows of A and half of the B tile
     const int stage_bytes2 = p.planes * (GEMM_A_BYTES + p.BN / 2 * 128);
-    int stages2 = (GEMM_SMEM_LIMIT - 1024 - GEMM_BAR_BYTES - 4 * p.epi_bufs * p.epi_buf_bytes) / stage_bytes2;
+    int stages2 = (GEMM_SMEM_LIMIT - 1024 - GEMM_BAR_BYTES - GEMM_EPI_WARPS * p.epi_bufs * p.epi_buf_bytes) / stage_bytes2;
     if (stages2 > GEMM_MAX_STAGES) stages2 = GEMM_MAX_STAGES;
     if (stages2 < 2) return fail(NRL_ERR_UNSUPPORTED, "pair GEMM tile does not fit shared memory");
     p.stages = stages2;
     p.tiles_per_unit = (p.n_extent + p.BN - 1) / p.BN;
-    const int smem2 = 1024 + stages2 * stage_bytes2 + 4 * p.epi_bufs * p.epi_buf_bytes + GEMM_BAR_BYTES;
+    const int smem2 = 1024 + stages2 * stage_bytes2 + GEMM_EPI_WARPS * p.epi_bufs * p.epi_buf_bytes + GEMM_BAR_BYTES;
     const int m_pairs = (p.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
     const int clusters = m_pairs < g_dev.sm_count / 2 ? m_pairs : g_dev.sm_count / 2;
     nrl_gemm_tc2_kernel<<<2 * clusters, GEMM_THREADS, smem2, c.stream>>>(ta, tb, tout, tsp, p);
@@ -308,11 +308,11 @@ static int launch_gemm(const Ctx& c, GemmParams& p, const CUtensorMap& ta, const
     return NRL_OK;
   }
   const int stage_bytes = p.planes * (GEMM_A_BYTES + (p.mn_major ? (p.BN + 63) / 64 * 8192 : p.BN * 128));
-  int stages = (GEMM_SMEM_LIMIT - 1024 - GEMM_BAR_BYTES - 4 * p.epi_bufs * p.epi_buf_bytes) / stage_bytes;
+  int stages = (GEMM_SMEM_LIMIT - 1024 - GEMM_BAR_BYTES - GEMM_EPI_WARPS * p.epi_bufs * p.epi_buf_bytes) / stage_bytes;
   if (stages > GEMM_MAX_STAGES) stages = GEMM_MAX_STAGES;
   if (stages < 2) return fail(NRL_ERR_UNSUPPORTED, "GEMM tile does not fit shared memory");
   p.stages = stages;
-  const int smem = 1024 + stages * stage_bytes + 4 * p.epi_bufs * p.epi_buf_bytes + GEMM_BAR_BYTES;
+  const int smem = 1024 + stages * stage_bytes + GEMM_EPI_WARPS * p.epi_bufs * p.epi_buf_bytes + GEMM_BAR_BYTES;
   const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM, n_tiles = (p.n_extent + p.BN - 1) / p.BN;
   const int tiles = m_tiles * n_tiles * p.k_splits;
   // unit = whole m-block when there are enough m-blocks to fill the machine twice over
@@ -330,7 +330,7 @@ static void set_segs(const Ctx& c, GemmParams& p) { p.planes = c.two_planes() ? 
 // narrow enough that at least two pipeline stages fit beside the epilogue staging buffers
 static int balanced_bn(int n_extent, int planes, bool both_sinks, int mn_major, bool single_tile = false,
                        bool pair = false) {
-  const int avail = GEMM_SMEM_LIMIT - 1024 - GEMM_BAR_BYTES - 4 * (pair ? epi_bufs_cfg() : 2) * (both_sinks ? 8192 : 4096);
+  const int avail = GEMM_SMEM_LIMIT - 1024 - GEMM_BAR_BYTES - GEMM_EPI_WARPS * epi_bufs_cfg() * (both_sinks ? 8192 : 4096);
   static const int bn_max = [] { const char* e = getenv("NRL_GEMM_BN_MAX"); return e ? atoi(e) : 256; }();
   const int cap = single_tile ? 256 : bn_max;
   for (int nt = (n_extent + cap - 1) / cap;; ++nt) {
@@ -356,6 +356,7 @@ static int gemm_nt(const Ctx& c, const bf16* A, long long M, int a_pitch, const 
   p.pair = (pair_on && (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM) >= g_dev.sm_count / 2) ? 1 : 0;
   p.BN = balanced_bn(p.n_extent, p.planes, sk.f32 && sk.sp, 0, epi.score != nullptr, p.pair != 0);
   if (epi.score && p.BN < N) return fail(NRL_ERR_UNSUPPORTED, "score fusion needs a single n-tile (N <= 256)");
+  if (epi.score) CUDA_TRY(cudaMemsetAsync(epi.score, 0, (size_t)M * sizeof(float), c.stream));
   p.k_splits = 1;
   p.epi = epi;
   CUtensorMap ta, tb;

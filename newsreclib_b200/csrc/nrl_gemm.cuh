@@ -16,8 +16,8 @@
 //                          over ROWS of both (weight-gradient GEMMs dW = dOut^T * In), with
 //                          split-K across CTAs and a TMA reduce-add (fp32) epilogue.
 //
-// Roles per CTA (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue.  N-stage smem ring (TMA <-> MMA), 2-stage TMEM accumulator ring
+// Roles per CTA (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..9 = epilogue (two per TMEM lane quarter, alternate 32-column chunks).  N-stage smem ring (TMA <-> MMA), 2-stage TMEM accumulator ring
 // (MMA <-> epilogue) so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
 // Epilogue: each warp owns 32 accumulator rows (its TMEM lane quarter) and walks the tile in
@@ -41,7 +41,8 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;  // bf16 elements per k-block = one 128-byte swizzle span
 constexpr int GEMM_MAX_STAGES = 6;
 constexpr int GEMM_A_BYTES = GEMM_BM * 128;  // 16 KB
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_EPI_WARPS = 8;  // two per TMEM lane quarter: they take alternate 32-column chunks
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 constexpr int GEMM_BAR_BYTES = 256;
 constexpr int GEMM_SMEM_LIMIT = 227 * 1024;
 constexpr int GEMM_TMEM_COLS = 512;
@@ -72,7 +73,7 @@ struct GemmParams {
   int k_splits;
   int stages;
   int epi_buf_bytes;   // staging bytes per epilogue warp per buffer (4096 or 8192)
-  int epi_bufs;        // staging buffers per epilogue warp (2 or 4): TMA stores in flight per warp
+  int epi_bufs;        // staging buffers per epilogue warp (1 or 2): TMA stores in flight per warp
   int tiles_per_unit;  // n_tiles (unit = m-block) or 1
   int pair;            // 1: nrl_gemm_tc2_kernel (CTA pairs, cta_group::2)
   int debug;           // timing experiments only (NRL_GEMM_DEBUG): 1 = no TMA stores, 2 = no epilogue work
@@ -109,22 +110,28 @@ __device__ __forceinline__ GemmTile gemm_tile(const GemmParams& p, int tile, int
   return t;
 }
 
-// keep-bits of 32 consecutive elements starting at flat index e0 (bit i = element e0 + i)
+// keep-bits of 32 consecutive elements starting at flat index e0 (bit i = element e0 + i).
+// Element e uses Philox group e >> 3, 16-bit slot e & 7 (nrl_ptx.cuh); 32 elements span four or
+// five groups depending on the alignment of e0.
+__device__ __forceinline__ uint32_t philox_keep8(const Philox4& r, uint32_t thr) {
+  // bit s = (slot s of the group is kept), slots in element order: x.lo, x.hi, y.lo, y.hi, ...
+  uint32_t b = 0;
+  b |= ((r.x & 0xFFFFu) >= thr) ? 1u : 0u;   b |= ((r.x >> 16) >= thr) ? 2u : 0u;
+  b |= ((r.y & 0xFFFFu) >= thr) ? 4u : 0u;   b |= ((r.y >> 16) >= thr) ? 8u : 0u;
+  b |= ((r.z & 0xFFFFu) >= thr) ? 16u : 0u;  b |= ((r.z >> 16) >= thr) ? 32u : 0u;
+  b |= ((r.w & 0xFFFFu) >= thr) ? 64u : 0u;  b |= ((r.w >> 16) >= thr) ? 128u : 0u;
+  return b;
+}
 __device__ __forceinline__ uint32_t drop_keep_bits32(unsigned long long seed, uint32_t site,
                                                      unsigned long long e0, uint32_t thr) {
-  uint32_t bits = 0;
-  unsigned long long g = e0 >> 3;
-  int slot = (int)(e0 & 7ull);
-  Philox4 r = philox4x32_10(seed, g, site);
+  const unsigned long long g0 = e0 >> 3;
+  const int sh = (int)(e0 & 7ull);
+  unsigned long long bits = 0;  // keep bits of groups g0 .. g0 + 4 (40 slots), slot 0 of g0 at bit 0
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    if (philox_u16(r, slot) >= thr) bits |= (1u << i);
-    if (++slot == 8 && i != 31) {
-      slot = 0;
-      r = philox4x32_10(seed, ++g, site);
-    }
-  }
-  return bits;
+  for (int k = 0; k < 4; ++k)
+    bits |= (unsigned long long)philox_keep8(philox4x32_10(seed, g0 + k, site), thr) << (8 * k);
+  if (sh) bits |= (unsigned long long)philox_keep8(philox4x32_10(seed, g0 + 4, site), thr) << 32;
+  return (uint32_t)(bits >> sh);
 }
 
 // Epilogue of one accumulator tile for one epilogue warp (its 32-row TMEM lane quarter): walks
@@ -133,7 +140,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const CU
                                                    const CUtensorMap* tmSpP, const GemmTile& t,
                                                    uint32_t t_row, int quarter, int lane,
                                                    uint32_t my_stage, uint32_t sp_off,
-                                                   uint32_t& chunk_ctr, bool one) {
+                                                   uint32_t& chunk_ctr, bool one, int half) {
     const GemmEpi& e = p.epi;
     const CUtensorMap& tmOut = *tmOutP;
     const CUtensorMap& tmSp = *tmSpP;
@@ -148,7 +155,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const CU
       addw = __ldg(e.add_w + row);
       addv = e.add_vec + (long long)(row / e.add_L) * e.ld_addvec;
     }
-    for (int c = 0; c < t.n_cur; c += 32) {
+    for (int c = 32 * half; c < t.n_cur; c += 32 * (GEMM_EPI_WARPS / 4)) {
       const int col_base = t.n0 + c;
       float v[32];
       if (c + 16 < t.n_cur) {
@@ -214,7 +221,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const CU
         const uint32_t buf = my_stage + (chunk_ctr & (uint32_t)(p.epi_bufs - 1)) * (uint32_t)p.epi_buf_bytes;
         ++chunk_ctr;
         if (one) {  // the store that last read this buffer is done
-          if (p.epi_bufs == 4) bulk_wait_read<3>(); else bulk_wait_read<1>();
+          if (p.epi_bufs == 1) bulk_wait_read<0>(); else bulk_wait_read<1>();
         }
         __syncwarp();
         if (e.f32_sink) {  // [32 rows][32 fp32], 128-byte rows, SWIZZLE_128B
@@ -263,7 +270,9 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const CU
         }
       }
     }
-    if (e.score && row_ok) e.score[row] = score_acc;
+    // two warps own a row (alternate chunks): each adds its partial into the zeroed score buffer
+    // (exactly two addends onto 0: the result does not depend on the order)
+    if (e.score && row_ok) atomicAdd(e.score + row, score_acc);
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -276,7 +285,7 @@ nrl_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const uint32_t b_bytes = p.mn_major ? b_boxes * 8192u : (uint32_t)p.BN * 128u;
   const uint32_t stage_bytes = (uint32_t)p.planes * (GEMM_A_BYTES + b_bytes);
   const uint32_t epi_base = smem_base + (uint32_t)p.stages * stage_bytes;
-  const uint32_t bar_base = epi_base + 4u * (uint32_t)p.epi_bufs * (uint32_t)p.epi_buf_bytes;
+  const uint32_t bar_base = epi_base + (uint32_t)GEMM_EPI_WARPS * (uint32_t)p.epi_bufs * (uint32_t)p.epi_buf_bytes;
   // barrier layout (8 B each): full[S], empty[S], tmem_full[2], tmem_empty[2], then tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (GEMM_MAX_STAGES + s); };
@@ -305,7 +314,7 @@ nrl_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);
+      mbar_init(tempty_bar(s), GEMM_EPI_WARPS);
     }
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
@@ -419,7 +428,7 @@ nrl_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
         const uint32_t t_row = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(quarter * 32) << 16);
-        gemm_epilogue_tile(p, &tmOut, &tmSp, t, t_row, quarter, lane, my_stage, sp_off, chunk_ctr, one);
+        gemm_epilogue_tile(p, &tmOut, &tmSp, t, t_row, quarter, lane, my_stage, sp_off, chunk_ctr, one, (warp - 2) >> 2);
         tc_fence_before();
         __syncwarp();
         if (one) mbar_arrive(tempty_bar(acc));
@@ -463,7 +472,7 @@ nrl_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t b_bytes = half_n * 128u;
   const uint32_t stage_bytes = (uint32_t)p.planes * (GEMM_A_BYTES + b_bytes);
   const uint32_t epi_base = smem_base + (uint32_t)p.stages * stage_bytes;
-  const uint32_t bar_base = epi_base + 4u * (uint32_t)p.epi_bufs * (uint32_t)p.epi_buf_bytes;
+  const uint32_t bar_base = epi_base + (uint32_t)GEMM_EPI_WARPS * (uint32_t)p.epi_bufs * (uint32_t)p.epi_buf_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (GEMM_MAX_STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * GEMM_MAX_STAGES + s); };
@@ -491,7 +500,7 @@ nrl_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 8);
+      mbar_init(tempty_bar(s), 2 * GEMM_EPI_WARPS);
     }
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
@@ -603,7 +612,7 @@ nrl_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait_cluster(tfull_bar(acc), acc_phase);
         tc_fence_after();
         const uint32_t t_row = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(quarter * 32) << 16);
-        gemm_epilogue_tile(p, &tmOut, &tmSp, t, t_row, quarter, lane, my_stage, sp_off, chunk_ctr, one);
+        gemm_epilogue_tile(p, &tmOut, &tmSp, t, t_row, quarter, lane, my_stage, sp_off, chunk_ctr, one, (warp - 2) >> 2);
         tc_fence_before();
         __syncwarp();
         if (one) {
