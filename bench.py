@@ -284,7 +284,7 @@ def main():
         hbm, tf_burst, tf_sust, src = peaks()
         achieved = flops_step / (gemm_ms / 1e3) / 1e12
         step_prof_ms = sum(t for t, c in agg.values()) / prof_steps
-        top = sorted(((t / prof_steps, nm, c // prof_steps) for nm, (t, c) in agg.items()), reverse=True)[:8]
+        top = sorted(((t / prof_steps, nm, c // prof_steps) for nm, (t, c) in agg.items()), reverse=True)[:14]
         roof = {"bound": "tensor", "kernel": "nrl_gemm_tc2_kernel / nrl_gemm_tc_kernel (all 18 tcgen05 GEMM launches of a step)",
                 "achieved": achieved, "peak": tf_sust, "unit": "TFLOP/s", "frac": achieved / tf_sust,
                 "peak_source": f"{src} bf16 dense, sustained (kernel timed inside a long step)",

@@ -294,7 +294,8 @@ static int launch_gemm(const Ctx& c, GemmParams& p, const CUtensorMap& ta, const
   static const int dbg = [] { const char* e = getenv("NRL_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
   p.debug = dbg;
   if (p.pair) {  // CTA pairs (cta_group::2): each CTA stages its 128 rows of A and half of the B tile
-    const int stage_bytes2 = p.planes * (GEMM_A_BYTES + p.BN / 2 * 128);
+    const int half_b = p.mn_major ? (p.BN / 2 + 63) / 64 * 8192 : p.BN / 2 * 128;
+    const int stage_bytes2 = p.planes * (GEMM_A_BYTES + half_b);
     int stages2 = (GEMM_SMEM_LIMIT - 1024 - GEMM_BAR_BYTES - GEMM_EPI_WARPS * p.epi_bufs * p.epi_buf_bytes) / stage_bytes2;
     if (stages2 > GEMM_MAX_STAGES) stages2 = GEMM_MAX_STAGES;
     if (stages2 < 2) return fail(NRL_ERR_UNSUPPORTED, "pair GEMM tile does not fit shared memory");
@@ -302,7 +303,8 @@ static int launch_gemm(const Ctx& c, GemmParams& p, const CUtensorMap& ta, const
     p.tiles_per_unit = (p.n_extent + p.BN - 1) / p.BN;
     const int smem2 = 1024 + stages2 * stage_bytes2 + GEMM_EPI_WARPS * p.epi_bufs * p.epi_buf_bytes + GEMM_BAR_BYTES;
     const int m_pairs = (p.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
-    const int clusters = m_pairs < g_dev.sm_count / 2 ? m_pairs : g_dev.sm_count / 2;
+    const int units = m_pairs * p.k_splits;
+    const int clusters = units < g_dev.sm_count / 2 ? units : g_dev.sm_count / 2;
     nrl_gemm_tc2_kernel<<<2 * clusters, GEMM_THREADS, smem2, c.stream>>>(ta, tb, tout, tsp, p);
     LAUNCH_CHECK(name);
     return NRL_OK;
@@ -377,10 +379,20 @@ static int gemm_tn(const Ctx& c, const bf16* A, int M, int a_pitch, const bf16* 
   p.n_extent = N;
   p.mn_major = 1;
   set_segs(c, p);
-  p.BN = balanced_bn(N, p.planes, false, 1);
-  const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM, n_tiles = (N + p.BN - 1) / p.BN;
   const int kb_total = (int)((R + GEMM_BK - 1) / GEMM_BK);
-  int ks = g_dev.sm_count / m_tiles;  // every n-block's tiles fill the machine once
+  // CTA pairs when the 256-row pairs waste no more MMA rows than the 128-row tiles would (M = 900, 200,
+  // 400 ...; not M = 300) -- doubles the operand reuse per byte pulled from L2
+  static const bool pair_on = [] { const char* e = getenv("NRL_GEMM_PAIR"); return !(e && e[0] == '0'); }();
+  const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM, m_pairs = (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+  p.pair = (pair_on && 2 * m_pairs == m_tiles && kb_total >= g_dev.sm_count) ? 1 : 0;
+  int ks;
+  if (p.pair) {
+    p.BN = N > 128 ? 256 : 128;  // each CTA's half is whole 64-column boxes (the last tile may be narrower)
+    ks = (g_dev.sm_count / 2) / m_pairs;
+  } else {
+    p.BN = balanced_bn(N, p.planes, false, 1);
+    ks = g_dev.sm_count / m_tiles;  // every n-block's tiles fill the machine once
+  }
   if (ks < 1) ks = 1;
   if (ks > kb_total) ks = kb_total;
   // no empty splits: shrink until every split owns at least one k-block
@@ -394,7 +406,6 @@ static int gemm_tn(const Ctx& c, const bf16* A, int M, int a_pitch, const bf16* 
   CUtensorMap ta, tb;
   TRY(make_tmap(&ta, A, a_pitch, R, a_pitch, 64, 64));
   TRY(make_tmap(&tb, B, b_pitch, R, b_pitch, 64, 64));
-  (void)n_tiles;
   return launch_gemm(c, p, ta, tb, sk, name);
 }
 

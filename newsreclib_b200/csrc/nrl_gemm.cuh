@@ -460,7 +460,8 @@ nrl_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 //   producer, expect_tx of both CTAs' bytes) + the TMA bytes of both CTAs; empty[s] / tmem_full[a]
 //   -- one multicast tcgen05.commit arrival in each CTA; tmem_empty[a] -- leader only, 8 arrivals
 //   (4 epilogue warps of each CTA, the peer's through mapa).
-// Work unit = one 256-row block with all its n-tiles; no split-K (weight gradients stay 1-CTA).
+// Work unit = (k-split, 256-row block) with all its n-tiles.  Both operand layouts: K-major "NT" (row
+// streaming GEMMs) and MN-major "TN" with split-K (weight gradients whose M fills the row pairs).
 // ------------------------------------------------------------------------------------------
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 nrl_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -468,8 +469,9 @@ nrl_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t half_n = (uint32_t)p.BN / 2u;  // B rows held by each CTA (multiple of 8)
-  const uint32_t b_bytes = half_n * 128u;
+  const uint32_t half_n = (uint32_t)p.BN / 2u;  // B rows (NT) / columns (TN) held by each CTA
+  // NT: half_n K-major rows of 128 B; TN: 64-column boxes of 8 KB ([64 k-rows][64 columns])
+  const uint32_t b_bytes = p.mn_major ? ((half_n + 63u) / 64u) * 8192u : half_n * 128u;
   const uint32_t stage_bytes = (uint32_t)p.planes * (GEMM_A_BYTES + b_bytes);
   const uint32_t epi_base = smem_base + (uint32_t)p.stages * stage_bytes;
   const uint32_t bar_base = epi_base + (uint32_t)GEMM_EPI_WARPS * (uint32_t)p.epi_bufs * (uint32_t)p.epi_buf_bytes;
@@ -479,9 +481,7 @@ nrl_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * GEMM_MAX_STAGES + 2 + s); };
   const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * GEMM_MAX_STAGES + 4);
 
-  // warp-uniform warp index and ONE elected lane per warp: inside `if (one)` the compiler knows a
-  // single thread is active, so TMA / tcgen05 operands go straight to uniform registers (with
-  // `lane == 0` it emits a vote loop around every UTMALDG / UTCHMMA / UTMASTG)
+  // warp-uniform warp index and ONE elected lane per warp (see nrl_gemm_tc_kernel)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const bool one = elect_one();
@@ -492,6 +492,8 @@ nrl_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int m_pairs = (p.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
   const int n_tiles = (p.n_extent + p.BN - 1) / p.BN;
   const int kb_total = (p.K + GEMM_BK - 1) / GEMM_BK;
+  const int kb_per = (kb_total + p.k_splits - 1) / p.k_splits;
+  const int num_units = m_pairs * p.k_splits;  // unit = (k-split, row pair), all its n-tiles
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -520,11 +522,12 @@ nrl_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   auto tile_of = [&](int unit, int j) {
     GemmTile t;
-    t.m0 = unit * 2 * GEMM_BM + (int)rank * GEMM_BM;  // this CTA's 128 rows
+    const int ks = unit / m_pairs, mp = unit - ks * m_pairs;
+    t.m0 = mp * 2 * GEMM_BM + (int)rank * GEMM_BM;  // this CTA's 128 rows
     t.n0 = j * p.BN;
     t.n_cur = min(p.BN, (p.n_extent - t.n0 + 15) & ~15);
-    t.kb0 = 0;
-    t.kb1 = kb_total;
+    t.kb0 = ks * kb_per;
+    t.kb1 = min(kb_total, t.kb0 + kb_per);
     return t;
   };
 
@@ -533,19 +536,29 @@ nrl_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (one) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int unit = cluster_id; unit < m_pairs; unit += num_clusters) {
+      for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
         for (int j = 0; j < n_tiles; ++j) {
           const GemmTile t = tile_of(unit, j);
-          const int b_row0 = t.n0 + (int)rank * (t.n_cur / 2);  // my half of the n_cur weight rows
-          for (int kb = 0; kb < kb_total; ++kb) {
+          const int b0 = t.n0 + (int)rank * (t.n_cur / 2);  // my half of the n_cur weight rows / columns
+          const int nb = (t.n_cur / 2 + 63) / 64;           // TN: 64-column boxes of my half
+          const uint32_t tx = p.mn_major ? (uint32_t)p.planes * (GEMM_A_BYTES + (uint32_t)nb * 8192u) : stage_bytes;
+          for (int kb = t.kb0; kb < t.kb1; ++kb) {
             mbar_wait_cluster(empty_bar(stage), phase ^ 1u);
             const uint32_t lead_full = mapa_shared(full_bar(stage), 0);
-            if (leader) mbar_expect_tx(full_bar(stage), 2u * stage_bytes);
+            if (leader) mbar_expect_tx(full_bar(stage), 2u * tx);
             const uint32_t a_dst = smem_base + stage * stage_bytes;
             const uint32_t b_dst = a_dst + (uint32_t)p.planes * GEMM_A_BYTES;
             for (int pl = 0; pl < p.planes; ++pl) {
-              tma_load_3d_pair(a_dst + pl * GEMM_A_BYTES, &tmA, lead_full, kb * GEMM_BK, t.m0, pl);
-              tma_load_3d_pair(b_dst + pl * b_bytes, &tmB, lead_full, kb * GEMM_BK, b_row0, pl);
+              if (!p.mn_major) {
+                tma_load_3d_pair(a_dst + pl * GEMM_A_BYTES, &tmA, lead_full, kb * GEMM_BK, t.m0, pl);
+                tma_load_3d_pair(b_dst + pl * b_bytes, &tmB, lead_full, kb * GEMM_BK, b0, pl);
+              } else {
+                for (int q = 0; q < 2; ++q)
+                  tma_load_3d_pair(a_dst + pl * GEMM_A_BYTES + q * 8192, &tmA, lead_full, t.m0 + q * 64,
+                                   kb * GEMM_BK, pl);
+                for (int q = 0; q < nb; ++q)
+                  tma_load_3d_pair(b_dst + pl * b_bytes + q * 8192, &tmB, lead_full, b0 + q * 64, kb * GEMM_BK, pl);
+              }
             }
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
@@ -559,27 +572,28 @@ nrl_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int unit = cluster_id; unit < m_pairs; unit += num_clusters) {
+      for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
         for (int j = 0; j < n_tiles; ++j) {
           const GemmTile t = tile_of(unit, j);
-          const uint32_t idesc = umma_idesc_bf16(2 * GEMM_BM, t.n_cur, 0, 0);
+          const uint32_t idesc = umma_idesc_bf16(2 * GEMM_BM, t.n_cur, p.mn_major, p.mn_major);
           mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
           uint32_t accumulate = 0;
-          for (int kb = 0; kb < kb_total; ++kb) {
+          for (int kb = t.kb0; kb < t.kb1; ++kb) {
             mbar_wait_cluster(full_bar(stage), phase);
             tc_fence_after();
             const uint32_t a_src = smem_base + stage * stage_bytes;
             const uint32_t b_src = a_src + (uint32_t)p.planes * GEMM_A_BYTES;
             const int nks = min(GEMM_BK / 16, (p.K - kb * GEMM_BK + 15) / 16);
             for (int k = 0; k < nks; ++k) {
-              const uint32_t koff = k * 32;
-              const uint64_t a_hi = umma_desc_sw128(a_src + koff, 16, 1024);
-              const uint64_t b_hi = umma_desc_sw128(b_src + koff, 16, 1024);
+              const uint32_t koff = p.mn_major ? k * 2048 : k * 32;
+              const uint32_t lbo = p.mn_major ? 8192 : 16;
+              const uint64_t a_hi = umma_desc_sw128(a_src + koff, lbo, 1024);
+              const uint64_t b_hi = umma_desc_sw128(b_src + koff, lbo, 1024);
               if (p.planes == 2) {
-                const uint64_t a_lo = umma_desc_sw128(a_src + GEMM_A_BYTES + koff, 16, 1024);
-                const uint64_t b_lo = umma_desc_sw128(b_src + b_bytes + koff, 16, 1024);
+                const uint64_t a_lo = umma_desc_sw128(a_src + GEMM_A_BYTES + koff, lbo, 1024);
+                const uint64_t b_lo = umma_desc_sw128(b_src + b_bytes + koff, lbo, 1024);
                 umma_bf16_pair(d_tmem, a_lo, b_hi, idesc, accumulate);
                 umma_bf16_pair(d_tmem, a_hi, b_lo, idesc, 1);
                 umma_bf16_pair(d_tmem, a_hi, b_hi, idesc, 1);
@@ -598,7 +612,7 @@ nrl_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else {
-    // ===================== epilogue warps (2..5), both CTAs =====================
+    // ===================== epilogue warps (2..9), both CTAs =====================
     const GemmEpi& e = p.epi;
     const int quarter = warp & 3;
     const uint32_t my_stage = epi_base + (uint32_t)(warp - 2) * (uint32_t)p.epi_bufs * (uint32_t)p.epi_buf_bytes;
@@ -606,7 +620,7 @@ nrl_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t chunk_ctr = 0;
-    for (int unit = cluster_id; unit < m_pairs; unit += num_clusters) {
+    for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
       for (int j = 0; j < n_tiles; ++j) {
         const GemmTile t = tile_of(unit, j);
         mbar_wait_cluster(tfull_bar(acc), acc_phase);

@@ -1341,19 +1341,46 @@ __global__ void emb_grad_kernel(const long long* __restrict__ ids, long long R,
   }
 }
 
-// torch.optim.Adam (no weight decay / amsgrad), dense over n elements.
+// torch.optim.Adam (no weight decay / amsgrad), dense over n elements; 128-bit accesses over the
+// 16-byte-aligned body (the flat parameter buffers are), scalar tail.
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float lr, float b1, float b2,
                             float eps, float bc1, float sqrt_bc2, float g_scale) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
+  const float lr_bc1 = lr / bc1;
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long nth = (long long)gridDim.x * blockDim.x;
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) |
+                     reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  const long long n4 = vec ? n / 4 : 0;
+  for (long long i = tid; i < n4; i += nth) {
+    float4 p4 = reinterpret_cast<float4*>(p)[i];
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(g) + i);
+    float4 m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i];
+    {  // sqrt(v) / sqrt_bc2 is kept as a division (torch's formula), not a reciprocal multiply
+      float* pp = &p4.x; const float* gg = &g4.x; float* mm = &m4.x; float* vv = &v4.x;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float gi = gg[k] * g_scale;
+        const float mi = b1 * mm[k] + (1.f - b1) * gi;
+        const float vi = b2 * vv[k] + (1.f - b2) * gi * gi;
+        mm[k] = mi;
+        vv[k] = vi;
+        const float denom = sqrtf(vi) / sqrt_bc2 + eps;
+        pp[k] -= lr_bc1 * (mi / denom);
+      }
+    }
+    reinterpret_cast<float4*>(p)[i] = p4;
+    reinterpret_cast<float4*>(m)[i] = m4;
+    reinterpret_cast<float4*>(v)[i] = v4;
+  }
+  for (long long i = 4 * n4 + tid; i < n; i += nth) {
     const float gi = g[i] * g_scale;
     const float mi = b1 * m[i] + (1.f - b1) * gi;
     const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
     m[i] = mi;
     v[i] = vi;
     const float denom = sqrtf(vi) / sqrt_bc2 + eps;
-    p[i] -= (lr / bc1) * (mi / denom);
+    p[i] -= lr_bc1 * (mi / denom);
   }
 }
 

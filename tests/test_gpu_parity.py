@@ -52,6 +52,22 @@ def test_gemm_nt_cta_pair(shape):
     assert torch.all(out[:, N] == 1.0) and torch.all(out[:, N + 1:] == 0.0)
 
 
+@pytest.mark.parametrize("shape", [(900, 304, 20000), (200, 304, 12000), (400, 912, 10048), (256, 100, 9500)])
+def test_gemm_tn_cta_pair(shape):
+    """Weight-gradient (MN-major, split-K) GEMMs whose M fills whole 256-row pairs run on the CTA-pair kernel:
+    BN = 256 / 128 tiles with a narrower last tile (304 = 256 + 48), TMA reduce-add of the k-split partials."""
+    from newsreclib_b200 import ops
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M * 5 + N)
+    A = torch.randn(K, M, generator=g).cuda()
+    B = torch.randn(K, N, generator=g).cuda()
+    ref = (A.double().t() @ B.double())
+    D3 = ops.gemm_test(A, B, True, ops.PREC_BF16X3)
+    D1 = ops.gemm_test(A, B, True, ops.PREC_BF16)
+    torch.cuda.synchronize()
+    assert rel_err(D3, ref) < 3e-5 and rel_err(D1, ref) < 2e-2
+
+
 @pytest.mark.parametrize("shape", [(128, 16, 16), (300, 208, 304), (1000, 300, 304), (4000, 900, 304)])
 def test_gemm_plane_sink(shape):
     """The bf16 hi/lo plane sink (TMA store of a [2, 32, 32] box): values, ones column, zero pad."""
