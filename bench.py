@@ -173,8 +173,11 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--vocab", type=int, default=VOCAB, help="70000 = MINDsmall-shape (headline), 130000 = MINDlarge-shape")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    globals()["VOCAB"] = args.vocab
+    globals()["WORKLOAD"] = WORKLOAD.replace("V=70000", f"V={args.vocab}")
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -305,6 +308,11 @@ def main():
     h2d = (nh + nc) * L * 8 + (nh + nc) * 8 + nc * 4
     d2h = B * Cmax * 4 + 4
 
+    # ---- timed region D: eval forward only (scores + loss, no backward / Adam), device-resident inputs
+    for i in range(2):
+        trainer.eval_forward(dev_batches[i % n_ring], B, Hmax, Cmax)
+    ms_eval = timed_region(lambda i: trainer.eval_forward(dev_batches[i % n_ring], B, Hmax, Cmax), args.steps) / args.steps
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         bs, timed, threads = cpu_train_steps(B, 4, 1, budget_s=25.0)
@@ -326,6 +334,7 @@ def main():
                        "precision": args.precision},
             "e2e": {"value": e2e_val, "unit": "impressions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e},
+            "eval_forward": {"value": world * B / (ms_eval / 1e3), "unit": "impressions/s", "ms_per_step": ms_eval},
             "gpu_launches": int(launches),
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         }

@@ -291,8 +291,6 @@ static int launch_gemm(const Ctx& c, GemmParams& p, const CUtensorMap& ta, const
   }
   p.epi_buf_bytes = (sk.f32 && sk.sp) ? 8192 : 4096;
   p.epi_bufs = epi_bufs_cfg();
-  static const int dbg = [] { const char* e = getenv("NRL_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
-  p.debug = dbg;
   if (p.pair) {  // CTA pairs (cta_group::2): each CTA stages its 128 rows of A and half of the B tile
     const int half_b = p.mn_major ? (p.BN / 2 + 63) / 64 * 8192 : p.BN / 2 * 128;
     const int stage_bytes2 = p.planes * (GEMM_A_BYTES + half_b);

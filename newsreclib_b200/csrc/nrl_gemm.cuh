@@ -76,7 +76,6 @@ struct GemmParams {
   int epi_bufs;        // staging buffers per epilogue warp (1 or 2): TMA stores in flight per warp
   int tiles_per_unit;  // n_tiles (unit = m-block) or 1
   int pair;            // 1: nrl_gemm_tc2_kernel (CTA pairs, cta_group::2)
-  int debug;           // timing experiments only (NRL_GEMM_DEBUG): 1 = no TMA stores, 2 = no epilogue work
   GemmEpi epi;
 };
 
@@ -144,7 +143,6 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const CU
     const GemmEpi& e = p.epi;
     const CUtensorMap& tmOut = *tmOutP;
     const CUtensorMap& tmSp = *tmSpP;
-    if (p.debug & 2) return;
     const int row_base = t.m0 + quarter * 32;
     const int row = row_base + lane;
     const bool row_ok = row < p.M;
@@ -262,7 +260,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const CU
         }
         fence_proxy_async();
         __syncwarp();
-        if (one && !(p.debug & 1)) {
+        if (one) {
           if (e.f32_sink == 1 && col_base < e.f32_cols) tma_store_2d(&tmOut, buf, col_base, row_base);
           else if (e.f32_sink == 2 && col_base < e.f32_cols) tma_reduce_add_2d(&tmOut, buf, col_base, row_base);
           if (e.sp_sink && col_base < e.sp_cols) tma_store_3d(&tmSp, buf + sp_off, col_base, row_base, 0);

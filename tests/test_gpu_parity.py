@@ -145,6 +145,20 @@ def test_nrms_step_against_oracle(hist, cand, B):
              grad_tolerances(params, batch, 15, GRAD_TOL, rg))
 
 
+@pytest.mark.parametrize("B,max_hist,hist,cand,L", [(1, 1, "fixed", "train", 30), (2, 3, "ragged", "eval", 5),
+                                                     (40, 4, "ragged", "train", 9), (3, 50, "fixed", "eval", 30)])
+def test_nrms_step_edge_shapes(B, max_hist, hist, cand, L):
+    """Edge cases: a single impression (the batch-axis user attention degenerates to S = 1), one-news
+    histories, very short titles, B > 32 (tile attention kernel for the user encoder), long candidate lists."""
+    V = 400
+    params = make_nrms_params(V, seed=B * 7 + L)
+    batch = make_batch(B, V, hist=hist, cand=cand, seed=B + L, max_hist=max_hist, max_title_len=L)
+    scores, loss, grads = gpu_run(params, batch, 15)
+    rs, rl, rg = oracle_run(params, batch, 15)
+    _compare(scores, loss, grads, rs, rl, rg, f"edge B={B} hist<={max_hist} L={L}",
+             grad_tolerances(params, batch, 15, GRAD_TOL, rg))
+
+
 def test_nrms_step_bf16_mode():
     from newsreclib_b200 import ops
     V = 2000
