@@ -300,6 +300,30 @@ def main():
                 "share_of_step": gemm_ms / step_prof_ms,
                 "top_kernels_ms_per_step": [[nm, round(t, 4), c] for t, nm, c in top]}
 
+    # HBM-bound kernels: algorithmic bytes per step (per token row of the title block /
+    # user block; Adam per parameter) over the live per-launch durations of region B
+    hbm_kernels = None
+    if rank == 0:
+        rows = (nh + nc) * L + B * Hmax
+        n_params = sum(v.numel() for v in params.values())
+        mw_bytes = 4 * ((E + 31) // 32)
+        algo = {
+            "gather_split": ((nh + nc) * L) * (8 + 4 * E + mw_bytes + 2 * 2 * (E + 4)),
+            "attn_fwd": rows * (3 * 4 * E + 2 * 2 * (E + 4) + 4 * H),
+            "attn_bwd": rows * (3 * 4 * E + 4 * E + 4 * H + 2 * 2 * (3 * E + 12)),
+            "pool_fwd": rows * (4 * E + 8) + (nh + nc + B) * 4 * E,
+            "pool_bwd": rows * (4 * E + 4 * Q + 4 + 2 * 2 * ((Q + 15) // 16 * 16)) + (nh + nc + B) * 4 * E,
+            "emb_grad": ((nh + nc) * L) * (4 * E + 8 + 2 * 4 * E),
+            "adam": n_params * 28,
+        }
+        hbm_kernels = []
+        for nm, nbytes in algo.items():
+            if nm in agg:
+                ms = agg[nm][0] / prof_steps
+                gbs = nbytes / (ms / 1e3) / 1e9
+                hbm_kernels.append({"kernel": nm, "ms_per_step": round(ms, 4), "algorithmic_mbytes": round(nbytes / 1e6, 1),
+                                    "achieved_gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / hbm, 3)})
+
     # ---- timed region C: end to end through the C ABI with host buffers -------------------
     for i in range(2):
         step_host(i)
@@ -336,7 +360,7 @@ def main():
                     "ms_per_step": ms_e2e},
             "eval_forward": {"value": world * B / (ms_eval / 1e3), "unit": "impressions/s", "ms_per_step": ms_eval},
             "gpu_launches": int(launches),
-            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "clocks": clocks, "roofline": roof, "hbm_kernels": hbm_kernels, "cpu_baseline": cpu,
         }
         print(json.dumps(out), flush=True)
     if world > 1:

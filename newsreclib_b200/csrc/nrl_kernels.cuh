@@ -428,11 +428,27 @@ attn_fwd_tile_kernel(const float* __restrict__ qkv, int E, int ldq, int heads, i
     const int P = 3 * W;         // smem row pitch
     const int segv = W / 4;      // float4 per segment
     __syncthreads();
-    for (int i = threadIdx.x; i < S * 3 * segv; i += blockDim.x) {
-      const int srow = i / (3 * segv), rem = i % (3 * segv), seg = rem / segv, c4 = rem % segv;
-      const long long grow = (long long)srow * seq_stride + (long long)b * batch_stride;
-      reinterpret_cast<float4*>(tile + (long long)srow * P + seg * W)[c4] =
-          __ldg(reinterpret_cast<const float4*>(qkv + grow * ld + seg * E + h0 * DH) + c4);
+    {  // stage the tile with four independent 16-byte loads in flight per thread (the loop is
+       // latency-bound otherwise: one DRAM round trip per iteration)
+      const int total = S * 3 * segv;
+      for (int i0 = threadIdx.x; i0 < total; i0 += 4 * blockDim.x) {
+        float4 v[4];
+        int dst[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * blockDim.x;
+          dst[u] = -1;
+          if (i < total) {
+            const int srow = i / (3 * segv), rem = i % (3 * segv), seg = rem / segv, c4 = rem % segv;
+            const long long grow = (long long)srow * seq_stride + (long long)b * batch_stride;
+            v[u] = __ldg(reinterpret_cast<const float4*>(qkv + grow * ld + seg * E + h0 * DH) + c4);
+            dst[u] = srow * P + seg * W + 4 * c4;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (dst[u] >= 0) *reinterpret_cast<float4*>(tile + dst[u]) = v[u];
+      }
     }
     __syncthreads();
     for (int it = warp; it < nh * qchunks; it += nwarps) {
@@ -450,24 +466,26 @@ attn_fwd_tile_kernel(const float* __restrict__ qkv, int E, int ldq, int heads, i
       float m = -INFINITY;
       for (int u = 0; u < S; ++u) {
         const float* kr = tile + (long long)u * P + W + hl * DH;
-        float acc = 0.f;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // four independent FMA chains
 #pragma unroll
         for (int d = 0; d < DH; d += 4) {
           float4 k4 = *reinterpret_cast<const float4*>(kr + d);
-          acc += q[d] * k4.x + q[d + 1] * k4.y + q[d + 2] * k4.z + q[d + 3] * k4.w;
+          a0 += q[d] * k4.x; a1 += q[d + 1] * k4.y; a2 += q[d + 2] * k4.z; a3 += q[d + 3] * k4.w;
         }
+        const float acc = (a0 + a1) + (a2 + a3);
         m = fmaxf(m, acc);
       }
       float l = 0.f;
       for (int u = 0; u < S; ++u) {
         const float* kr = tile + (long long)u * P + W + hl * DH;
         const float* vr = kr + W;
-        float acc = 0.f;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // four independent FMA chains
 #pragma unroll
         for (int d = 0; d < DH; d += 4) {
           float4 k4 = *reinterpret_cast<const float4*>(kr + d);
-          acc += q[d] * k4.x + q[d + 1] * k4.y + q[d + 2] * k4.z + q[d + 3] * k4.w;
+          a0 += q[d] * k4.x; a1 += q[d + 1] * k4.y; a2 += q[d + 2] * k4.z; a3 += q[d + 3] * k4.w;
         }
+        const float acc = (a0 + a1) + (a2 + a3);
         const float pu = expf(acc - m);
         l += pu;
 #pragma unroll
@@ -531,12 +549,28 @@ attn_bwd_tile_kernel(const float* __restrict__ qkv, const float* __restrict__ d_
     float* s_lse = tile + (long long)S * P;   // [S][nh]
     float* s_dd = s_lse + S * nh;             // [S][nh]
     __syncthreads();
-    for (int i = threadIdx.x; i < S * 4 * segv; i += blockDim.x) {
-      const int srow = i / (4 * segv), rem = i % (4 * segv), seg = rem / segv, c4 = rem % segv;
-      const long long grow = (long long)srow * seq_stride + (long long)b * batch_stride;
-      const float4* src = seg < 3 ? reinterpret_cast<const float4*>(qkv + grow * ld + seg * E + h0 * DH)
-                                  : reinterpret_cast<const float4*>(d_o + grow * ld_do + h0 * DH);
-      reinterpret_cast<float4*>(tile + (long long)srow * P + seg * W)[c4] = __ldg(src + c4);
+    {  // four independent 16-byte loads in flight per thread
+      const int total = S * 4 * segv;
+      for (int i0 = threadIdx.x; i0 < total; i0 += 4 * blockDim.x) {
+        float4 v[4];
+        int dst[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * blockDim.x;
+          dst[u] = -1;
+          if (i < total) {
+            const int srow = i / (4 * segv), rem = i % (4 * segv), seg = rem / segv, c4 = rem % segv;
+            const long long grow = (long long)srow * seq_stride + (long long)b * batch_stride;
+            const float4* src = seg < 3 ? reinterpret_cast<const float4*>(qkv + grow * ld + seg * E + h0 * DH)
+                                        : reinterpret_cast<const float4*>(d_o + grow * ld_do + h0 * DH);
+            v[u] = __ldg(src + c4);
+            dst[u] = srow * P + seg * W + 4 * c4;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (dst[u] >= 0) *reinterpret_cast<float4*>(tile + dst[u]) = v[u];
+      }
     }
     for (int i = threadIdx.x; i < S * nh; i += blockDim.x) {
       const int srow = i / nh, hl = i % nh;
@@ -563,26 +597,28 @@ attn_bwd_tile_kernel(const float* __restrict__ qkv, const float* __restrict__ d_
       float dd = 0.f;
       for (int u = 0; u < S; ++u) {
         const float* kr = tile + (long long)u * P + W + hl * DH;
-        float sc = 0.f, dp = 0.f;
+        float s0 = 0.f, s1 = 0.f, p0 = 0.f, p1 = 0.f;  // independent FMA chains
 #pragma unroll
         for (int d = 0; d < DH; d += 4) {
           float4 k4 = *reinterpret_cast<const float4*>(kr + d);
           float4 v4 = *reinterpret_cast<const float4*>(kr + W + d);
-          sc += q[d] * k4.x + q[d + 1] * k4.y + q[d + 2] * k4.z + q[d + 3] * k4.w;
-          dp += go[d] * v4.x + go[d + 1] * v4.y + go[d + 2] * v4.z + go[d + 3] * v4.w;
+          s0 += q[d] * k4.x + q[d + 1] * k4.y; s1 += q[d + 2] * k4.z + q[d + 3] * k4.w;
+          p0 += go[d] * v4.x + go[d + 1] * v4.y; p1 += go[d + 2] * v4.z + go[d + 3] * v4.w;
         }
+        const float sc = s0 + s1, dp = p0 + p1;
         dd += expf(sc - my_lse) * dp;
       }
       for (int u = 0; u < S; ++u) {
         const float* kr = tile + (long long)u * P + W + hl * DH;
-        float sc = 0.f, dp = 0.f;
+        float s0 = 0.f, s1 = 0.f, p0 = 0.f, p1 = 0.f;  // independent FMA chains
 #pragma unroll
         for (int d = 0; d < DH; d += 4) {
           float4 k4 = *reinterpret_cast<const float4*>(kr + d);
           float4 v4 = *reinterpret_cast<const float4*>(kr + W + d);
-          sc += q[d] * k4.x + q[d + 1] * k4.y + q[d + 2] * k4.z + q[d + 3] * k4.w;
-          dp += go[d] * v4.x + go[d + 1] * v4.y + go[d + 2] * v4.z + go[d + 3] * v4.w;
+          s0 += q[d] * k4.x + q[d + 1] * k4.y; s1 += q[d + 2] * k4.z + q[d + 3] * k4.w;
+          p0 += go[d] * v4.x + go[d + 1] * v4.y; p1 += go[d + 2] * v4.z + go[d + 3] * v4.w;
         }
+        const float sc = s0 + s1, dp = p0 + p1;
         const float ds = expf(sc - my_lse) * (dp - dd);
 #pragma unroll
         for (int d = 0; d < DH; d += 4) {
@@ -616,14 +652,15 @@ attn_bwd_tile_kernel(const float* __restrict__ qkv, const float* __restrict__ d_
       }
       for (int t = 0; t < S; ++t) {
         const float* qr = tile + (long long)t * P + hl * DH;
-        float sc = 0.f, dp = 0.f;
+        float s0 = 0.f, s1 = 0.f, p0 = 0.f, p1 = 0.f;
 #pragma unroll
         for (int d = 0; d < DH; d += 4) {
           float4 q4 = *reinterpret_cast<const float4*>(qr + d);
           float4 g4 = *reinterpret_cast<const float4*>(qr + 3 * W + d);
-          sc += q4.x * kk[d] + q4.y * kk[d + 1] + q4.z * kk[d + 2] + q4.w * kk[d + 3];
-          dp += g4.x * vv[d] + g4.y * vv[d + 1] + g4.z * vv[d + 2] + g4.w * vv[d + 3];
+          s0 += q4.x * kk[d] + q4.y * kk[d + 1]; s1 += q4.z * kk[d + 2] + q4.w * kk[d + 3];
+          p0 += g4.x * vv[d] + g4.y * vv[d + 1]; p1 += g4.z * vv[d + 2] + g4.w * vv[d + 3];
         }
+        const float sc = s0 + s1, dp = p0 + p1;
         const float pr = expf(sc * scale - s_lse[t * nh + hl]);
         const float ds = pr * (dp - s_dd[t * nh + hl]) * scale;
 #pragma unroll
