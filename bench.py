@@ -164,6 +164,93 @@ GEMM_FLOPS = {  # algorithmic (unpadded, single-pass) flops per row of the block
 }
 
 
+def main_naml(args, rank, local_rank, world):
+    """Secondary line: NAML (title + abstract + category views, CNN text encoder; BASELINE.json configs[4]
+    shape at MINDsmall vocabulary) trained through the drop-in NAMLModule + ModuleTrainer."""
+    import functools
+    import torch.distributed as dist
+    from newsreclib_b200 import _lib
+    from newsreclib_b200.models.general_rec.naml_module import NAMLModule
+    from newsreclib_b200.synthetic import make_naml_params
+    from newsreclib_b200.trainer import ModuleTrainer
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: newsreclib_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    B, F_, W, CE, LA = args.batch, 400, 3, 100, 50
+    params = make_naml_params(VOCAB, E, F_, W, Q, CE, 19, seed=1234)
+    outputs = {k: ["preds", "targets", "cand_news_size"] for k in ("train", "val", "test")}
+    m = NAMLModule(
+        dataset_attributes=["title", "abstract", "category", "subcategory"], attributes2encode=["title", "abstract", "category"],
+        outputs=outputs, dual_loss_training=False, dual_loss_coef=None, loss="cross_entropy_loss", late_fusion=False,
+        temperature=None, use_plm=False, pretrained_embeddings_path=None, plm_model=None, frozen_layers=None,
+        text_embed_dim=E, num_heads=H, num_filters=F_, window_size=W, query_dim=Q, categ_embed_dim=CE,
+        dropout_probability=DROPOUT, top_k_list=[5, 10], num_categ_classes=18, num_sent_classes=3, save_recs=False,
+        recs_fpath=None, optimizer=functools.partial(torch.optim.Adam, lr=1e-4), scheduler=None,
+        pretrained_embeddings=params["news_encoder.text_encoders.title.embedding_layer.weight"])
+    full = dict(params)
+    for k in list(params):
+        if ".text_encoders.title." in k:
+            full[k.replace(".title.", ".abstract.")] = params[k]
+    m.load_state_dict(full)
+    m = m.to(dev)
+    tr = ModuleTrainer(m, lr=1e-4)
+
+    def to_dev(hb):
+        return {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else {kk: vv.to(dev, non_blocking=True) for kk, vv in v.items()})
+                for k, v in hb.items()}
+    host = [make_batch(B, VOCAB, hist="fixed", max_hist=HIST, cand="train", seed=1234 + rank * 100 + i, max_title_len=L,
+                       abstract_len=LA) for i in range(4)]
+    host = [{k: (v.pin_memory() if torch.is_tensor(v) else {kk: vv.pin_memory() for kk, vv in v.items()}) for k, v in hb.items()}
+            for hb in host]
+    devb = [to_dev(hb) for hb in host]
+
+    def timed(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+    for i in range(args.warmup):
+        tr.train_step(devb[i % 4])
+    l0 = lib.nrl_launch_count()
+    ms = timed(lambda i: tr.train_step(devb[i % 4]), args.steps) / args.steps
+    launches = lib.nrl_launch_count() - l0
+    ms_e2e = timed(lambda i: float(tr.train_step(to_dev(host[i % 4]))), args.steps) / args.steps
+    if rank == 0:
+        nh, nc = B * HIST, B * CAND
+        h2d = sum(v.numel() * v.element_size() if torch.is_tensor(v) else sum(x.numel() * x.element_size() for x in v.values())
+                  for v in host[0].values())
+        print(json.dumps({
+            "metric": "impressions/sec", "value": world * B / (ms / 1e3), "unit": "impressions/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "fp32 via bf16x3 split on tcgen05 (fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": f"NAML train step through NAMLModule + ModuleTrainer (fwd + CE + autograd bwd + Adam): B={B}/GPU, "
+                                   f"hist {HIST}, {CAND} candidates, title {L} + abstract {LA} tokens + category, E={E}, "
+                                   f"F={F_}, w={W}, Q={Q}, V={VOCAB}, dropout {DROPOUT}", "global_batch": world * B,
+                       "parallelism": f"dp{world}", "news_per_step": nh + nc},
+            "e2e": {"value": world * B / (ms_e2e / 1e3), "unit": "impressions/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
+            "gpu_launches": int(launches)}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -173,6 +260,8 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--model", default="nrms", choices=["nrms", "naml"],
+                    help="nrms = the headline (BASELINE.json configs[1]); naml = configs[4] shape through NAMLModule")
     ap.add_argument("--vocab", type=int, default=VOCAB, help="70000 = MINDsmall-shape (headline), 130000 = MINDlarge-shape")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -185,6 +274,9 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args, rank)
         return
+
+    if args.model == "naml":
+        return main_naml(args, rank, local_rank, world)
 
     import torch.distributed as dist
     from newsreclib_b200 import _lib, ops

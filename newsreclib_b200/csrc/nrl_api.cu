@@ -612,7 +612,7 @@ static int block_forward(const Ctx& c, const Dims& d, BlockWs& w, long long R, c
     sk.f32 = w.a; sk.ld_f32 = d.Q; sk.f32_cols = d.Q;
     TRY(gemm_nt(c, w.yp, R, d.Ep, w.wadd_f, d.Q, d.Ep, d.Ep, e, sk, "gemm additive"));
   }
-  pool_fwd_kernel<<<grid_for(G, 1, 1 << 20), 128, L * sizeof(float), c.stream>>>(w.s, w.y, d.E, L, G, w.w, out_vec);
+  pool_fwd_kernel<<<dim3((unsigned)grid_for(G, 1, 1 << 20), (unsigned)((d.E + 511) / 512)), 128, L * sizeof(float), c.stream>>>(w.s, w.y, d.E, L, G, w.w, out_vec);
   LAUNCH_CHECK("pool_fwd");
   return NRL_OK;
 }
@@ -945,7 +945,7 @@ int nrl_additive_fwd(const float* x, long long G, int L, int D, int Q, const flo
   Sinks sk;
   sk.f32 = w.a; sk.ld_f32 = Q; sk.f32_cols = Q;
   TRY(gemm_nt(c, w.xp, R, Dp, w.wf, Q, Dp, Dp, e, sk, "gemm additive"));
-  pool_fwd_kernel<<<grid_for(G, 1, 1 << 20), 128, L * sizeof(float), c.stream>>>(w.s, x, D, L, G, w.w, out);
+  pool_fwd_kernel<<<dim3((unsigned)grid_for(G, 1, 1 << 20), (unsigned)((D + 511) / 512)), 128, L * sizeof(float), c.stream>>>(w.s, x, D, L, G, w.w, out);
   LAUNCH_CHECK("pool_fwd");
   return NRL_OK;
 }
@@ -1388,7 +1388,7 @@ int nrl_cnn_encoder_fwd(const long long* ids, long long n_news, int L, const flo
     sk.f32 = w.a; sk.ld_f32 = d.Q; sk.f32_cols = d.Q;
     TRY(gemm_nt(c, w.yp, R, d.Fp, w.wadd_f, d.Q, d.Fp, d.Fp, e, sk, "gemm additive"));
   }
-  pool_fwd_kernel<<<grid_for(n_news, 1, 1 << 20), 128, L * sizeof(float), c.stream>>>(w.s, w.y, d.F, L, n_news,
+  pool_fwd_kernel<<<dim3((unsigned)grid_for(n_news, 1, 1 << 20), (unsigned)((d.F + 511) / 512)), 128, L * sizeof(float), c.stream>>>(w.s, w.y, d.F, L, n_news,
                                                                                        w.w, out);
   LAUNCH_CHECK("pool_fwd");
   return NRL_OK;

@@ -1062,38 +1062,71 @@ pool_fwd_kernel(const float* __restrict__ score, const float* __restrict__ Y, in
                 long long G, float* __restrict__ w_out, float* __restrict__ out) {
   extern __shared__ float sw[];  // L weights
   __shared__ float red[33];
+  // blockIdx.y = block of 4 * blockDim columns (every CTA recomputes the L softmax weights: cheap)
+  const int c0 = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
+  const bool vec4 = (E & 3) == 0;
   for (long long g = blockIdx.x; g < G; g += gridDim.x) {
     const long long r0 = g * L;
-    float mx = -INFINITY;
-    for (int t = threadIdx.x; t < L; t += blockDim.x) mx = fmaxf(mx, score[r0 + t]);
-    mx = block_max(mx, red);
-    float sum = 0.f;
-    for (int t = threadIdx.x; t < L; t += blockDim.x) {
-      float e = expf(score[r0 + t] - mx);
-      sw[t] = e;
-      sum += e;
-    }
-    sum = block_sum(sum, red);
-    const float inv = 1.f / sum;
-    for (int t = threadIdx.x; t < L; t += blockDim.x) {
-      float w = sw[t] * inv;
-      sw[t] = w;
-      w_out[r0 + t] = w;
+    if (L <= 32) {  // one warp, no block-wide reductions
+      if (threadIdx.x < 32) {
+        const int t = threadIdx.x;
+        const float sc = t < L ? score[r0 + t] : -INFINITY;
+        const float mx = warp_max(sc);
+        const float e = t < L ? expf(sc - mx) : 0.f;
+        const float sum = warp_sum(e);
+        if (t < L) {
+          const float w = e * (1.f / sum);
+          sw[t] = w;
+          if (blockIdx.y == 0) w_out[r0 + t] = w;
+        }
+      }
+    } else {
+      float mx = -INFINITY;
+      for (int t = threadIdx.x; t < L; t += blockDim.x) mx = fmaxf(mx, score[r0 + t]);
+      mx = block_max(mx, red);
+      float sum = 0.f;
+      for (int t = threadIdx.x; t < L; t += blockDim.x) {
+        float e = expf(score[r0 + t] - mx);
+        sw[t] = e;
+        sum += e;
+      }
+      sum = block_sum(sum, red);
+      const float inv = 1.f / sum;
+      for (int t = threadIdx.x; t < L; t += blockDim.x) {
+        float w = sw[t] * inv;
+        sw[t] = w;
+        if (blockIdx.y == 0) w_out[r0 + t] = w;
+      }
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < E; c += blockDim.x) {
-      float acc = 0.f;
-      const float* yc = Y + r0 * E + c;
-      int t = 0;
-      for (; t + 8 <= L; t += 8) {  // eight independent loads in flight per thread
-        float v[8];
+    if (vec4) {  // four columns per thread, eight independent 16-byte loads in flight
+      if (c0 < E) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* yc = Y + r0 * E + c0;
+        int t = 0;
+        for (; t + 8 <= L; t += 8) {
+          float4 v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = __ldg(yc + (long long)(t + u) * E);
+          for (int u = 0; u < 8; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(yc + (long long)(t + u) * E));
 #pragma unroll
-        for (int u = 0; u < 8; ++u) acc += sw[t + u] * v[u];
+          for (int u = 0; u < 8; ++u) {
+            const float wt = sw[t + u];
+            acc.x += wt * v[u].x; acc.y += wt * v[u].y; acc.z += wt * v[u].z; acc.w += wt * v[u].w;
+          }
+        }
+        for (; t < L; ++t) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(yc + (long long)t * E));
+          const float wt = sw[t];
+          acc.x += wt * v.x; acc.y += wt * v.y; acc.z += wt * v.z; acc.w += wt * v.w;
+        }
+        *reinterpret_cast<float4*>(out + g * E + c0) = acc;
       }
-      for (; t < L; ++t) acc += sw[t] * __ldg(yc + (long long)t * E);
-      out[g * E + c] = acc;
+    } else {
+      for (int c = c0; c < min(E, c0 + 4); ++c) {
+        float acc = 0.f;
+        for (int t = 0; t < L; ++t) acc += sw[t] * __ldg(Y + (r0 + t) * E + c);
+        out[g * E + c] = acc;
+      }
     }
     __syncthreads();
   }

@@ -157,3 +157,49 @@ class NRMSTrainer:
             batch, self.table, self.news_block, self.user_block, self.dims, B=B, Hmax=Hmax, Cmax=Cmax,
             late_fusion=self.late_fusion, dropout_p=0.0, training=False, ws=self.ws, precision=self.precision)
         return scores, loss
+
+
+class ModuleTrainer:
+    """Training loop body for any of the drop-in LightningModule mirrors (``NRMSModule``, ``NAMLModule``)
+    without Lightning: ``model_step`` (sm_100a forward + loss), autograd backward through the
+    ``torch.autograd.Function``s of ``ops.py``, then ONE gradient all-reduce and ONE ``nrl_adam_step`` over
+    flat buffers the module's parameters and ``.grad``s are re-pointed into (what Lightning's DDP +
+    ``torch.optim.Adam`` do for the reference, ``configs/model/naml.yaml:56-59``)."""
+
+    def __init__(self, module: torch.nn.Module, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
+                 process_group=None) -> None:
+        _lib.load()
+        self.module = module
+        uniq, seen = [], set()
+        for p in module.parameters():
+            if p.requires_grad and id(p) not in seen:
+                seen.add(id(p)); uniq.append(p)
+        if not uniq or not uniq[0].is_cuda:
+            raise RuntimeError("ModuleTrainer needs a module on a CUDA device (newsreclib_b200 has no CPU path)")
+        total, offs = 0, []
+        for p in uniq:
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4
+        dev = uniq[0].device
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros_like(self.flat)
+        self.m, self.v = torch.zeros_like(self.flat), torch.zeros_like(self.flat)
+        for p, o in zip(uniq, offs):
+            n = p.numel()
+            self.flat[o:o + n].copy_(p.data.reshape(-1))
+            p.data = self.flat[o:o + n].view_as(p)
+            p.grad = self.grad[o:o + n].view_as(p)  # autograd accumulates in place into the flat buffer
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.exchange = GradExchange(process_group)
+        self.step_count = 0
+
+    def train_step(self, batch) -> torch.Tensor:
+        self.module.train()
+        self.grad.zero_()
+        loss = self.module.model_step(batch)[0]
+        loss.backward()
+        scale = self.exchange.all_reduce(self.grad)
+        self.step_count += 1
+        ops.adam_step(self.flat, self.grad, self.m, self.v, self.step_count, self.lr, self.betas[0], self.betas[1],
+                      self.eps, grad_scale=scale)
+        return loss.detach()

@@ -355,3 +355,32 @@ def test_nrms_plm_module_forward():
     loss.backward()
     got = [n for n, q in mc.named_parameters() if q.grad is not None]
     assert any("plm_model" in n for n in got) and any("multihead_attention" in n for n in got)
+
+
+def test_module_trainer_matches_torch_adam_on_naml():
+    """ModuleTrainer (flat buffers + nrl_adam_step) follows torch.optim.Adam on the same NAML module."""
+    from newsreclib_b200.trainer import ModuleTrainer
+    V = 600
+    d = dict(V=V, E=300, F=400, W=3, Q=200, CE=100, C=19, B=6)
+    params = make_naml_params(V, seed=12)
+    batch = make_batch(6, V, hist="ragged", max_hist=6, cand="train", seed=12, abstract_len=50)
+    b = naml_dev_batch(batch)
+    ma = make_naml_module(params, d, p=0.0).cuda()
+    mb = make_naml_module(params, d, p=0.0).cuda()
+    tr = ModuleTrainer(ma, lr=1e-3)
+    opt = torch.optim.Adam(mb.parameters(), lr=1e-3)
+    for step in range(3):
+        la = tr.train_step(b)
+        opt.zero_grad()
+        lb = mb.training_step(b, step)
+        lb.backward()
+        opt.step()
+        assert rel_err(la, lb.detach()) <= 1e-5
+    # Adam's step is lr * m / (sqrt(v) + eps) ~ +-lr wherever |g| >> eps, so elements whose gradient is ~0
+    # (sign decided by the last bits of a split-K reduction) may legitimately differ by O(lr) between two
+    # runs; everything else agrees to fp32 noise
+    sa, sb = ma.state_dict(), mb.state_dict()
+    for k in sa:
+        diff = (sa[k] - sb[k]).abs()
+        assert float(diff.max()) <= 3 * 2e-3 + 1e-6, k                      # never more than the 3 steps' worth
+        assert float((diff > 1e-5).float().mean()) <= 0.02, k                # and only on a sliver of elements
