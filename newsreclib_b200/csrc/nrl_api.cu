@@ -259,12 +259,6 @@ static int make_tmap_planes(CUtensorMap* m, const bf16* base, unsigned long long
   return NRL_OK;
 }
 
-// staging buffers per epilogue warp: 8 warps x 1 buffer = the smem of the old 4 x 2 (NRL_GEMM_EPI_BUFS=2: experiment)
-static int epi_bufs_cfg() {
-  static const int v = [] { const char* e = getenv("NRL_GEMM_EPI_BUFS"); return (e && atoi(e) == 2) ? 2 : 1; }();
-  return v;
-}
-
 // Host-side description of where a GEMM's result goes (turned into tensor maps + GemmEpi).
 struct Sinks {
   float* f32 = nullptr; long long ld_f32 = 0; int f32_cols = 0; bool reduce = false;  // fp32 [M, f32_cols]
@@ -290,7 +284,7 @@ static int launch_gemm(const Ctx& c, GemmParams& p, const CUtensorMap& ta, const
     p.epi.ones_col = sk.ones_col;
   }
   p.epi_buf_bytes = (sk.f32 && sk.sp) ? 8192 : 4096;
-  p.epi_bufs = epi_bufs_cfg();
+  p.epi_bufs = 1;
   if (p.pair) {  // CTA pairs (cta_group::2): each CTA stages its 128 rows of A and half of the B tile
     const int half_b = p.mn_major ? (p.BN / 2 + 63) / 64 * 8192 : p.BN / 2 * 128;
     const int stage_bytes2 = p.planes * (GEMM_A_BYTES + half_b);
@@ -330,7 +324,7 @@ static void set_segs(const Ctx& c, GemmParams& p) { p.planes = c.two_planes() ? 
 // narrow enough that at least two pipeline stages fit beside the epilogue staging buffers
 static int balanced_bn(int n_extent, int planes, bool both_sinks, int mn_major, bool single_tile = false,
                        bool pair = false) {
-  const int avail = GEMM_SMEM_LIMIT - 1024 - GEMM_BAR_BYTES - GEMM_EPI_WARPS * epi_bufs_cfg() * (both_sinks ? 8192 : 4096);
+  const int avail = GEMM_SMEM_LIMIT - 1024 - GEMM_BAR_BYTES - GEMM_EPI_WARPS * 1 * (both_sinks ? 8192 : 4096);
   static const int bn_max = [] { const char* e = getenv("NRL_GEMM_BN_MAX"); return e ? atoi(e) : 256; }();
   const int cap = single_tile ? 256 : bn_max;
   for (int nt = (n_extent + cap - 1) / cap;; ++nt) {

@@ -541,7 +541,7 @@ nrl_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int nb = (t.n_cur / 2 + 63) / 64;           // TN: 64-column boxes of my half
           const uint32_t tx = p.mn_major ? (uint32_t)p.planes * (GEMM_A_BYTES + (uint32_t)nb * 8192u) : stage_bytes;
           for (int kb = t.kb0; kb < t.kb1; ++kb) {
-            mbar_wait_cluster(empty_bar(stage), phase ^ 1u);
+            mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t lead_full = mapa_shared(full_bar(stage), 0);
             if (leader) mbar_expect_tx(full_bar(stage), 2u * tx);
             const uint32_t a_dst = smem_base + stage * stage_bytes;
@@ -574,12 +574,12 @@ nrl_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int j = 0; j < n_tiles; ++j) {
           const GemmTile t = tile_of(unit, j);
           const uint32_t idesc = umma_idesc_bf16(2 * GEMM_BM, t.n_cur, p.mn_major, p.mn_major);
-          mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u);
+          mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
           uint32_t accumulate = 0;
           for (int kb = t.kb0; kb < t.kb1; ++kb) {
-            mbar_wait_cluster(full_bar(stage), phase);
+            mbar_wait(full_bar(stage), phase);
             tc_fence_after();
             const uint32_t a_src = smem_base + stage * stage_bytes;
             const uint32_t b_src = a_src + (uint32_t)p.planes * GEMM_A_BYTES;
@@ -621,7 +621,7 @@ nrl_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
       for (int j = 0; j < n_tiles; ++j) {
         const GemmTile t = tile_of(unit, j);
-        mbar_wait_cluster(tfull_bar(acc), acc_phase);
+        mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
         const uint32_t t_row = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(quarter * 32) << 16);
         gemm_epilogue_tile(p, &tmOut, &tmSp, t, t_row, quarter, lane, my_stage, sp_off, chunk_ctr, one, (warp - 2) >> 2);

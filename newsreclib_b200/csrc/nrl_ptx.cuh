@@ -211,18 +211,10 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-// wait with cluster-scope acquire (the barrier is signalled by the peer CTA / by multicast commits)
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred P;\n\t"
-      "WAIT_LOOP_C:\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%0], %1;\n\t"
-      "@P bra DONE_C;\n\t"
-      "bra WAIT_LOOP_C;\n\t"
-      "DONE_C:\n\t}\n" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
+// NOTE: the pair kernel waits with the plain CTA-scope mbar_wait even on barriers signalled from the
+// peer CTA (TMA complete_tx, multicast tcgen05.commit, remote arrive): what those barriers order is
+// async-proxy shared memory and TMEM, guarded by the tcgen05 fences -- an `.acquire.cluster` wait makes
+// ptxas emit CCTL.IVALL + MEMBAR (an L1 flush) after every wait, which cost 13 % of the epilogue warps.
 // TMA load whose completion bytes are signalled on an mbarrier that may live in the PEER CTA of the
 // pair (the leader's "full" barrier): dst is this CTA's shared memory, bar a shared::cluster address.
 __device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* m, uint32_t cluster_bar,
