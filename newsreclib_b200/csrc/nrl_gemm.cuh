@@ -43,7 +43,7 @@ constexpr int GEMM_MAX_STAGES = 6;
 constexpr int GEMM_A_BYTES = GEMM_BM * 128;  // 16 KB
 constexpr int GEMM_EPI_WARPS = 8;  // two per TMEM lane quarter: they take alternate 32-column chunks
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
-constexpr int GEMM_BAR_BYTES = 256;
+constexpr int GEMM_BAR_BYTES = 256 + 1024;  // mbarriers + TMEM pointer, then the additive query vector (<= 256 floats)
 constexpr int GEMM_SMEM_LIMIT = 227 * 1024;
 constexpr int GEMM_TMEM_COLS = 512;
 
@@ -139,7 +139,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const CU
                                                    const CUtensorMap* tmSpP, const GemmTile& t,
                                                    uint32_t t_row, int quarter, int lane,
                                                    uint32_t my_stage, uint32_t sp_off,
-                                                   uint32_t& chunk_ctr, bool one, int half) {
+                                                   uint32_t& chunk_ctr, bool one, int half, uint32_t qv_smem) {
     const GemmEpi& e = p.epi;
     const CUtensorMap& tmOut = *tmOutP;
     const CUtensorMap& tmSp = *tmSpP;
@@ -324,6 +324,9 @@ nrl_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     tmem_alloc(tmem_ptr_addr, GEMM_TMEM_COLS);
     tmem_relinquish();
   }
+  if (p.epi.qvec)
+    for (int i = threadIdx.x; i < p.N && i < 256; i += blockDim.x)
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(bar_base + 256u + 4u * (uint32_t)i), "f"(__ldg(p.epi.qvec + i)) : "memory");
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -426,7 +429,7 @@ nrl_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
         const uint32_t t_row = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(quarter * 32) << 16);
-        gemm_epilogue_tile(p, &tmOut, &tmSp, t, t_row, quarter, lane, my_stage, sp_off, chunk_ctr, one, (warp - 2) >> 2);
+        gemm_epilogue_tile(p, &tmOut, &tmSp, t, t_row, quarter, lane, my_stage, sp_off, chunk_ctr, one, (warp - 2) >> 2, bar_base + 256u);
         tc_fence_before();
         __syncwarp();
         if (one) mbar_arrive(tempty_bar(acc));
@@ -512,6 +515,9 @@ nrl_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tmem_alloc_pair(tmem_ptr_addr, GEMM_TMEM_COLS);
     tmem_relinquish_pair();
   }
+  if (p.epi.qvec)
+    for (int i = threadIdx.x; i < p.N && i < 256; i += blockDim.x)
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(bar_base + 256u + 4u * (uint32_t)i), "f"(__ldg(p.epi.qvec + i)) : "memory");
   tc_fence_before();
   cluster_sync_all();  // barriers of BOTH CTAs are initialised before anybody signals them
   tc_fence_after();
@@ -624,7 +630,7 @@ nrl_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
         const uint32_t t_row = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(quarter * 32) << 16);
-        gemm_epilogue_tile(p, &tmOut, &tmSp, t, t_row, quarter, lane, my_stage, sp_off, chunk_ctr, one, (warp - 2) >> 2);
+        gemm_epilogue_tile(p, &tmOut, &tmSp, t, t_row, quarter, lane, my_stage, sp_off, chunk_ctr, one, (warp - 2) >> 2, bar_base + 256u);
         tc_fence_before();
         __syncwarp();
         if (one) {
