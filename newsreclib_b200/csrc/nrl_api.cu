@@ -473,6 +473,12 @@ static void launch_attn_fwd(const Ctx& c, const Dims& d, const AttnGeom& g, cons
         w.qkv, d.E, d.LDQ, d.H, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH), w.o, lo, d.Ep, w.lse);
     return;
   }
+  if (g.S <= 64 && !attn_force_simt()) {  // two 32-key blocks per warp (the NRMS user encoder, S = B = 64)
+    const long long warps = 2ll * g.NB * d.H;
+    attn_fwd_mma64_kernel<DH><<<(unsigned)((warps + 3) / 4), 128, 0, c.stream>>>(
+        w.qkv, d.E, d.LDQ, d.H, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH), w.o, lo, d.Ep, w.lse);
+    return;
+  }
   if (g.S <= 32) {  // register-resident SIMT path (NRL_ATTN_SIMT=1: A/B comparison only)
     const int hg = attn_head_group(d.H), groups = (d.H + hg - 1) / hg;
     const size_t smem = (size_t)g.S * attn_pitch(3 * hg * DH) * sizeof(float);
@@ -509,6 +515,12 @@ static void launch_attn_bwd(const Ctx& c, const Dims& d, const AttnGeom& g, cons
     attn_bwd_mma_kernel<DH><<<(unsigned)((items + 3) / 4), 128, 0, c.stream>>>(
         w.qkv, w.d_o, d.E, w.lse, d.E, d.LDQ, d.H, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH),
         w.dqkv, lo, d.P3);
+    return;
+  }
+  if (g.S <= 64 && !attn_force_simt()) {
+    attn_bwd_mma64_kernel<DH><<<(unsigned)((long long)g.NB * d.H), 128, 0, c.stream>>>(
+        w.qkv, w.d_o, d.E, w.o, c.two_planes() ? w.o + R * d.Ep : nullptr, d.Ep, w.lse, d.E, d.LDQ, d.H, g.S,
+        g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH), w.dqkv, lo, d.P3);
     return;
   }
   if (g.S <= 32) {

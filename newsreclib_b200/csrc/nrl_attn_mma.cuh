@@ -467,4 +467,274 @@ attn_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o
   attn_bwd_item<DH>(src, lse, E, heads, S, seq_stride, batch_stride, scale, b, h, g_hi, g_lo, p3, lane);
 }
 
+// ------------------------------------------------------------------------------------------------
+// 32 < S <= 64 (the NRMS user encoder: the reference attends across the B = 64 impressions of the
+// batch at every history position): the same register-fragment scheme on 32 x 32 blocks.
+//   forward : one warp per (item, 32-query block); both key blocks' scores live in registers.
+//   backward: four warps per item -- two own a query block (dQ, summed over the key blocks), two own
+//             a key block (dK, dV, summed over the query blocks).  D_t = sum_d dO[t, d] O[t, d] comes
+//             from the saved O planes, so every (query block, key block) pair is independent.
+// ------------------------------------------------------------------------------------------------
+template <int DH>
+__global__ void __launch_bounds__(128)
+attn_fwd_mma64_kernel(const float* __restrict__ qkv, int E, int ldq, int heads, int S, long long seq_stride,
+                      int NB, long long batch_stride, float scale, __nv_bfloat16* __restrict__ o_hi,
+                      __nv_bfloat16* __restrict__ o_lo, int ep, float* __restrict__ lse) {
+  constexpr int KS = (DH + 15) / 16, ND = (DH + 7) / 8;
+  const int lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
+  const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long item = wid >> 1;
+  const int qb = (int)(wid & 1);
+  if (item >= (long long)NB * heads) return;
+  const int b = (int)(item / heads), h = (int)(item % heads);
+  const bool three = o_lo != nullptr;
+  const float* base = qkv + (long long)b * batch_stride * ldq + h * DH;
+  const long long rstride = seq_stride * ldq;
+  const int Sq = min(32, S - 32 * qb);
+  if (Sq <= 0) return;
+  Blk q;
+  load_blocks<DH>(q, base + 32ll * qb * rstride, rstride, Sq, scale * NRL_LOG2E, g, tg);
+  float s[2][2][4][4];  // [key block][i][j][c]
+#pragma unroll
+  for (int kb = 0; kb < 2; ++kb) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) s[kb][i][j][c] = 0.f;
+    Blk k;
+    load_blocks<DH>(k, base + E + 32ll * kb * rstride, rstride, S - 32 * kb, 1.f, g, tg);
+    mma_nt<KS, 4>(s[kb], q, k, three);
+  }
+  float inv_l[4], row_lse[4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float m = -INFINITY;
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int col = 32 * kb + 8 * j + 2 * tg + c;
+            if (col >= S) s[kb][i][j][2 * half + c] = -INFINITY;
+            m = fmaxf(m, s[kb][i][j][2 * half + c]);
+          }
+      m = quad_max(m);
+      float l = 0.f;
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const float p = ex2_approx(s[kb][i][j][2 * half + c] - m);
+            s[kb][i][j][2 * half + c] = p;
+            l += p;
+          }
+      l = quad_sum(l);
+      inv_l[2 * i + half] = 1.f / l;
+      row_lse[2 * i + half] = m * NRL_LN2 + logf(l);
+    }
+  float o[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) o[i][j][c] = 0.f;
+#pragma unroll
+  for (int kb = 0; kb < 2; ++kb) {
+    Blk p, v;
+    acc_to_blocks(p, s[kb]);
+    load_blocks<DH>(v, base + 2 * E + 32ll * kb * rstride, rstride, S - 32 * kb, 1.f, g, tg);
+    mma_nn<ND>(o, p, v, three);
+  }
+  long long grow[4];
+#pragma unroll
+  for (int rb = 0; rb < 4; ++rb)
+    grow[rb] = (long long)(32 * qb + 8 * rb + g) * seq_stride + (long long)b * batch_stride;
+  store_acc_split<DH, ND>(o, inv_l[0], inv_l[1], inv_l[2], inv_l[3], o_hi, o_lo, ep, grow, Sq, h * DH, g, tg);
+  if (tg == 0) {
+#pragma unroll
+    for (int rb = 0; rb < 4; ++rb)
+      if (8 * rb + g < Sq) lse[grow[rb] * heads + h] = row_lse[rb];
+  }
+  if (h == 0) {
+    const int npad = ep - E;
+    for (int i = lane; i < Sq * npad; i += 32) {
+      const int srow = 32 * qb + i / npad, c = E + i % npad;
+      const long long gr = (long long)srow * seq_stride + (long long)b * batch_stride;
+      o_hi[gr * ep + c] = __float2bfloat16_rn(c == E ? 1.f : 0.f);
+      if (o_lo) o_lo[gr * ep + c] = __float2bfloat16_rn(0.f);
+    }
+  }
+}
+
+// D_t = sum_d dO[t, d] * O[t, d] for the 32 query rows starting at row0 (rows 8 rb + g of the block),
+// O = hi + lo of the saved planes.  Result replicated over the quad.
+template <int DH>
+__device__ __forceinline__ void attn_row_D(float (&D)[4], const float* __restrict__ d_o, long long ld_do,
+                                           const __nv_bfloat16* __restrict__ o_hi,
+                                           const __nv_bfloat16* __restrict__ o_lo, int ep, int h, int row0, int Sq,
+                                           long long seq_stride, long long batch_stride, int b, int g, int tg) {
+#pragma unroll
+  for (int rb = 0; rb < 4; ++rb) {
+    float acc = 0.f;
+    if (8 * rb + g < Sq) {
+      const long long grow = (long long)(row0 + 8 * rb + g) * seq_stride + (long long)b * batch_stride;
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) {
+        const int c = 8 * cb + 2 * tg;
+        if (8 * cb < DH && c < DH) {
+          const float2 dv = __ldg(reinterpret_cast<const float2*>(d_o + grow * ld_do + h * DH + c));
+          const __nv_bfloat162 oh = *reinterpret_cast<const __nv_bfloat162*>(o_hi + grow * ep + h * DH + c);
+          float2 ov = __bfloat1622float2(oh);
+          if (o_lo) {
+            const float2 ol = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(o_lo + grow * ep + h * DH + c));
+            ov.x += ol.x; ov.y += ol.y;
+          }
+          acc += dv.x * ov.x + dv.y * ov.y;
+        }
+      }
+    }
+    D[rb] = quad_sum(acc);
+  }
+}
+
+// P and dS of one (query block, key block) pair: s, dp in -> p (in s), ds (in dp).
+__device__ __forceinline__ void attn_p_ds(float (&s)[2][4][4], float (&dp)[2][4][4], const float (&lse2)[4],
+                                          const float (&D)[4], int Sq, int Sk, int g, int tg) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int rb = 2 * i + half;
+      const bool rok = 8 * rb + g < Sq;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int col = 8 * j + 2 * tg + c;
+          const float p = (rok && col < Sk) ? ex2_approx(s[i][j][2 * half + c] - lse2[rb]) : 0.f;
+          s[i][j][2 * half + c] = p;
+          dp[i][j][2 * half + c] = p * (dp[i][j][2 * half + c] - D[rb]);
+        }
+    }
+}
+
+template <int DH>
+__global__ void __launch_bounds__(128, 2)
+attn_bwd_mma64_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o, long long ld_do,
+                      const __nv_bfloat16* __restrict__ o_hi, const __nv_bfloat16* __restrict__ o_lo, int ep,
+                      const float* __restrict__ lse, int E, int ldq, int heads, int S, long long seq_stride,
+                      int NB, long long batch_stride, float scale, __nv_bfloat16* __restrict__ g_hi,
+                      __nv_bfloat16* __restrict__ g_lo, int p3) {
+  constexpr int KS = (DH + 15) / 16, ND = (DH + 7) / 8;
+  const int lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3, role = threadIdx.x >> 5;
+  const long long item = blockIdx.x;  // one CTA (4 warps) per (batch item, head)
+  if (item >= (long long)NB * heads) return;
+  const int b = (int)(item / heads), h = (int)(item % heads);
+  const bool three = g_lo != nullptr;
+  const float* base = qkv + (long long)b * batch_stride * ldq + h * DH;
+  const float* dbase = d_o + (long long)b * batch_stride * ld_do + h * DH;
+  const long long rstride = seq_stride * ldq, dstride = seq_stride * ld_do;
+  const int mine = role & 1;          // the block this warp owns (query block for roles 0/1, key block for 2/3)
+  const int Sm = min(32, S - 32 * mine);
+  if (Sm <= 0) return;
+  long long grow[4];
+#pragma unroll
+  for (int rb = 0; rb < 4; ++rb)
+    grow[rb] = (long long)(32 * mine + 8 * rb + g) * seq_stride + (long long)b * batch_stride;
+  float acc[2][4][4], acc2[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { acc[i][j][c] = 0.f; acc2[i][j][c] = 0.f; }
+
+  if (role < 2) {
+    // ---- query block `mine`: dQ = scale * sum_kb dS[mine][kb] K[kb] ----
+    Blk q, go;
+    load_blocks<DH>(q, base + 32ll * mine * rstride, rstride, Sm, scale * NRL_LOG2E, g, tg);
+    load_blocks<DH>(go, dbase + 32ll * mine * dstride, dstride, Sm, 1.f, g, tg);
+    float lse2[4], D[4];
+#pragma unroll
+    for (int rb = 0; rb < 4; ++rb) lse2[rb] = (8 * rb + g < Sm) ? __ldg(lse + grow[rb] * heads + h) * NRL_LOG2E : 0.f;
+    attn_row_D<DH>(D, d_o, ld_do, o_hi, o_lo, ep, h, 32 * mine, Sm, seq_stride, batch_stride, b, g, tg);
+#pragma unroll
+    for (int kb = 0; kb < 2; ++kb) {
+      const int Sk = min(32, S - 32 * kb);
+      if (Sk <= 0) continue;
+      Blk k, v;
+      load_blocks<DH>(k, base + E + 32ll * kb * rstride, rstride, Sk, 1.f, g, tg);
+      load_blocks<DH>(v, base + 2 * E + 32ll * kb * rstride, rstride, Sk, 1.f, g, tg);
+      float s[2][4][4], dp[2][4][4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { s[i][j][c] = 0.f; dp[i][j][c] = 0.f; }
+      mma_nt<KS, 4>(s, q, k, three);
+      mma_nt<KS, 4>(dp, go, v, three);
+      attn_p_ds(s, dp, lse2, D, Sm, Sk, g, tg);
+      Blk ds;
+      acc_to_blocks(ds, dp);
+      mma_nn<ND>(acc, ds, k, three);
+    }
+    store_acc_split<DH, ND>(acc, scale, scale, scale, scale, g_hi, g_lo, p3, grow, Sm, h * DH, g, tg);
+    if (h == 0 && p3 > 3 * E) {
+      const int npad = p3 - 3 * E;
+      for (int i = lane; i < Sm * npad; i += 32) {
+        const int srow = 32 * mine + i / npad, c = 3 * E + i % npad;
+        const long long gr = (long long)srow * seq_stride + (long long)b * batch_stride;
+        g_hi[gr * p3 + c] = __float2bfloat16_rn(0.f);
+        if (g_lo) g_lo[gr * p3 + c] = __float2bfloat16_rn(0.f);
+      }
+    }
+  } else {
+    // ---- key block `mine`: dK = ln2 * sum_qb dS[qb][mine]^T Qs[qb],  dV = sum_qb P[qb][mine]^T dO[qb] ----
+    Blk k, v;
+    load_blocks<DH>(k, base + E + 32ll * mine * rstride, rstride, Sm, 1.f, g, tg);
+    load_blocks<DH>(v, base + 2 * E + 32ll * mine * rstride, rstride, Sm, 1.f, g, tg);
+#pragma unroll
+    for (int qb = 0; qb < 2; ++qb) {
+      const int Sq = min(32, S - 32 * qb);
+      if (Sq <= 0) continue;
+      Blk q, go;
+      load_blocks<DH>(q, base + 32ll * qb * rstride, rstride, Sq, scale * NRL_LOG2E, g, tg);
+      load_blocks<DH>(go, dbase + 32ll * qb * dstride, dstride, Sq, 1.f, g, tg);
+      float lse2[4], D[4];
+#pragma unroll
+      for (int rb = 0; rb < 4; ++rb) {
+        const long long gr = (long long)(32 * qb + 8 * rb + g) * seq_stride + (long long)b * batch_stride;
+        lse2[rb] = (8 * rb + g < Sq) ? __ldg(lse + gr * heads + h) * NRL_LOG2E : 0.f;
+      }
+      attn_row_D<DH>(D, d_o, ld_do, o_hi, o_lo, ep, h, 32 * qb, Sq, seq_stride, batch_stride, b, g, tg);
+      float s[2][4][4], dp[2][4][4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { s[i][j][c] = 0.f; dp[i][j][c] = 0.f; }
+      mma_nt<KS, 4>(s, q, k, three);
+      mma_nt<KS, 4>(dp, go, v, three);
+      attn_p_ds(s, dp, lse2, D, Sq, Sm, g, tg);
+      Blk pb, ds;
+      acc_to_blocks(pb, s);
+      acc_to_blocks(ds, dp);
+      mma_tn<ND>(acc, ds, q, three);    // dK
+      mma_tn<ND>(acc2, pb, go, three);  // dV
+    }
+    store_acc_split<DH, ND>(acc, NRL_LN2, NRL_LN2, NRL_LN2, NRL_LN2, g_hi, g_lo, p3, grow, Sm, E + h * DH, g, tg);
+    store_acc_split<DH, ND>(acc2, 1.f, 1.f, 1.f, 1.f, g_hi, g_lo, p3, grow, Sm, 2 * E + h * DH, g, tg);
+  }
+}
+
 }  // namespace nrl
