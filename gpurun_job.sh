@@ -1,7 +1,4 @@
 mkdir -p gpurun_out
-timeout 600 python bench.py --steps 50 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err
-cat gpurun_out/bench.json | cut -c1-200
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_ncu.log 2>&1
-timeout 900 ncu --set full --clock-control none -k regex:nrl_gemm -s 54 -c 18 -o gpurun_out/prof_gemm_r01f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/prof_gemm.log 2>&1
-timeout 200 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2>/dev/null; cut -c1-200 gpurun_out/bench_ref.json
-du -sh gpurun_out
+timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -x --timeout 100 -k "gemm" 2>&1 | tail -4
+timeout 900 python -m pytest tests -m gpu -q --timeout 240 2>&1 | tail -2
+timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench_x.json; python -c "import json; d=json.load(open('gpurun_out/bench_x.json')); print(round(d['ms_per_step'],3), round(d['roofline']['kernel_ms_per_step'],3), [x for x in d['roofline']['top_kernels_ms_per_step'] if x[0].startswith('gemm')])"

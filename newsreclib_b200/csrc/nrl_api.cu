@@ -286,7 +286,8 @@ static int launch_gemm(const Ctx& c, GemmParams& p, const CUtensorMap& ta, const
   p.epi_buf_bytes = (sk.f32 && sk.sp) ? 8192 : 4096;
   p.epi_bufs = 1;
   if (p.pair) {  // CTA pairs (cta_group::2): each CTA stages its 128 rows of A and half of the B tile
-    const int half_b = p.mn_major ? (p.BN / 2 + 63) / 64 * 8192 : p.BN / 2 * 128;
+    int half_b = p.mn_major ? (p.BN / 2 + 63) / 64 * 8192 : p.BN / 2 * 128;
+    if (p.fuse_n) half_b += (((p.n_extent - p.BN + 15) & ~15) / 2 + 63) / 64 * 8192;  // boxes of the second n-tile
     const int stage_bytes2 = p.planes * (GEMM_A_BYTES + half_b);
     int stages2 = (GEMM_SMEM_LIMIT - 1024 - GEMM_BAR_BYTES - GEMM_EPI_WARPS * p.epi_bufs * p.epi_buf_bytes) / stage_bytes2;
     if (stages2 > GEMM_MAX_STAGES) stages2 = GEMM_MAX_STAGES;
@@ -380,6 +381,9 @@ static int gemm_tn(const Ctx& c, const bf16* A, int M, int a_pitch, const bf16* 
   int ks;
   if (p.pair) {
     p.BN = N > 128 ? 256 : 128;  // each CTA's half is whole 64-column boxes (the last tile may be narrower)
+    // N = BN + a narrow rest (304 = 256 + 48): both n-tiles accumulate in one k-loop (two TMEM regions), so the
+    // A operand -- the big one, [R, M] -- is streamed from DRAM once instead of once per n-tile
+    p.fuse_n = (N > p.BN && N <= 2 * p.BN && p.BN == 256) ? 1 : 0;
     ks = (g_dev.sm_count / 2) / m_pairs;
   } else {
     p.BN = balanced_bn(N, p.planes, false, 1);

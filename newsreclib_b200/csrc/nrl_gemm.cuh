@@ -76,6 +76,7 @@ struct GemmParams {
   int epi_bufs;        // staging buffers per epilogue warp (1 or 2): TMA stores in flight per warp
   int tiles_per_unit;  // n_tiles (unit = m-block) or 1
   int pair;            // 1: nrl_gemm_tc2_kernel (CTA pairs, cta_group::2)
+  int fuse_n;          // pair + MN-major: both n-tiles accumulate in ONE k-loop (A is streamed once)
   GemmEpi epi;
 };
 
@@ -472,7 +473,10 @@ nrl_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t half_n = (uint32_t)p.BN / 2u;  // B rows (NT) / columns (TN) held by each CTA
   // NT: half_n K-major rows of 128 B; TN: 64-column boxes of 8 KB ([64 k-rows][64 columns])
-  const uint32_t b_bytes = p.mn_major ? ((half_n + 63u) / 64u) * 8192u : half_n * 128u;
+  // fused n-tiles (weight gradients with N = BN + a narrow second tile): boxes of tile 0 then tile 1
+  const int n1_cur = p.fuse_n ? ((p.n_extent - p.BN + 15) & ~15) : 0;  // width of the second tile
+  const uint32_t nb0 = (half_n + 63u) / 64u, nb1 = p.fuse_n ? ((uint32_t)n1_cur / 2u + 63u) / 64u : 0u;
+  const uint32_t b_bytes = p.mn_major ? (nb0 + nb1) * 8192u : half_n * 128u;
   const uint32_t stage_bytes = (uint32_t)p.planes * (GEMM_A_BYTES + b_bytes);
   const uint32_t epi_base = smem_base + (uint32_t)p.stages * stage_bytes;
   const uint32_t bar_base = epi_base + (uint32_t)GEMM_EPI_WARPS * (uint32_t)p.epi_bufs * (uint32_t)p.epi_buf_bytes;
@@ -491,7 +495,7 @@ nrl_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
 
   const int m_pairs = (p.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
-  const int n_tiles = (p.n_extent + p.BN - 1) / p.BN;
+  const int n_tiles = p.fuse_n ? 1 : (p.n_extent + p.BN - 1) / p.BN;  // passes over K per unit
   const int kb_total = (p.K + GEMM_BK - 1) / GEMM_BK;
   const int kb_per = (kb_total + p.k_splits - 1) / p.k_splits;
   const int num_units = m_pairs * p.k_splits;  // unit = (k-split, row pair), all its n-tiles
@@ -545,7 +549,7 @@ nrl_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const GemmTile t = tile_of(unit, j);
           const int b0 = t.n0 + (int)rank * (t.n_cur / 2);  // my half of the n_cur weight rows / columns
           const int nb = (t.n_cur / 2 + 63) / 64;           // TN: 64-column boxes of my half
-          const uint32_t tx = p.mn_major ? (uint32_t)p.planes * (GEMM_A_BYTES + (uint32_t)nb * 8192u) : stage_bytes;
+          const uint32_t tx = p.mn_major ? (uint32_t)p.planes * (GEMM_A_BYTES + ((uint32_t)nb + nb1) * 8192u) : stage_bytes;
           for (int kb = t.kb0; kb < t.kb1; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t lead_full = mapa_shared(full_bar(stage), 0);
@@ -562,6 +566,9 @@ nrl_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                    kb * GEMM_BK, pl);
                 for (int q = 0; q < nb; ++q)
                   tma_load_3d_pair(b_dst + pl * b_bytes + q * 8192, &tmB, lead_full, b0 + q * 64, kb * GEMM_BK, pl);
+                for (int q = 0; q < (int)nb1; ++q)  // my half of the fused second n-tile
+                  tma_load_3d_pair(b_dst + pl * b_bytes + (nb + q) * 8192, &tmB, lead_full,
+                                   p.BN + (int)rank * (n1_cur / 2) + q * 64, kb * GEMM_BK, pl);
               }
             }
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -580,6 +587,7 @@ nrl_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int j = 0; j < n_tiles; ++j) {
           const GemmTile t = tile_of(unit, j);
           const uint32_t idesc = umma_idesc_bf16(2 * GEMM_BM, t.n_cur, p.mn_major, p.mn_major);
+          const uint32_t idesc1 = umma_idesc_bf16(2 * GEMM_BM, p.fuse_n ? n1_cur : 16, p.mn_major, p.mn_major);
           mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
@@ -601,8 +609,19 @@ nrl_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 umma_bf16_pair(d_tmem, a_lo, b_hi, idesc, accumulate);
                 umma_bf16_pair(d_tmem, a_hi, b_lo, idesc, 1);
                 umma_bf16_pair(d_tmem, a_hi, b_hi, idesc, 1);
+                if (p.fuse_n) {  // second n-tile from the same A k-block, accumulator columns 256..
+                  const uint64_t c_hi = umma_desc_sw128(b_src + nb0 * 8192u + koff, lbo, 1024);
+                  const uint64_t c_lo = umma_desc_sw128(b_src + b_bytes + nb0 * 8192u + koff, lbo, 1024);
+                  umma_bf16_pair(d_tmem + 256u, a_lo, c_hi, idesc1, accumulate);
+                  umma_bf16_pair(d_tmem + 256u, a_hi, c_lo, idesc1, 1);
+                  umma_bf16_pair(d_tmem + 256u, a_hi, c_hi, idesc1, 1);
+                }
               } else {
                 umma_bf16_pair(d_tmem, a_hi, b_hi, idesc, accumulate);
+                if (p.fuse_n) {
+                  const uint64_t c_hi = umma_desc_sw128(b_src + nb0 * 8192u + koff, lbo, 1024);
+                  umma_bf16_pair(d_tmem + 256u, a_hi, c_hi, idesc1, accumulate);
+                }
               }
               accumulate = 1;
             }
@@ -610,8 +629,12 @@ nrl_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
           umma_commit_pair(tfull_bar(acc));  // accumulator halves ready in both CTAs
-          acc ^= 1;
-          if (acc == 0) acc_phase ^= 1u;
+          if (p.fuse_n) {
+            acc_phase ^= 1u;  // one accumulator set (buffer 0), a new phase per unit
+          } else {
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+          }
         }
       }
     }
@@ -631,14 +654,25 @@ nrl_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tc_fence_after();
         const uint32_t t_row = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(quarter * 32) << 16);
         gemm_epilogue_tile(p, &tmOut, &tmSp, t, t_row, quarter, lane, my_stage, sp_off, chunk_ctr, one, (warp - 2) >> 2, bar_base + 256u);
+        if (p.fuse_n) {  // the second n-tile's accumulator sits 256 columns further
+          GemmTile t1 = t;
+          t1.n0 = p.BN;
+          t1.n_cur = n1_cur;
+          gemm_epilogue_tile(p, &tmOut, &tmSp, t1, t_row + 256u, quarter, lane, my_stage, sp_off, chunk_ctr, one,
+                             (warp - 2) >> 2, bar_base + 256u);
+        }
         tc_fence_before();
         __syncwarp();
         if (one) {
           if (leader) mbar_arrive(tempty_bar(acc));
           else mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
         }
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
+        if (p.fuse_n) {
+          acc_phase ^= 1u;
+        } else {
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1u;
+        }
       }
     }
     if (one) bulk_wait<0>();
