@@ -68,6 +68,31 @@ def test_two_rank_exchange_matches_single_process_mean_gradient():
     assert torch.allclose(out[0], fp.flat, rtol=0, atol=1e-6)
 
 
+def _chunk_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.arange(1003, dtype=torch.float32) * (rank + 1)
+    ex = GradExchange()
+    seen = []
+    for sl, work in ex.all_reduce_chunks(g, chunk_elems=256):   # 4 chunks, the last one ragged
+        assert work is not None and sl.start % 4 == 0
+        seen.append((sl.start, sl.stop))
+    out[rank] = (g.clone(), seen)
+    dist.destroy_process_group()
+
+
+def test_chunked_exchange_covers_the_buffer_in_order():
+    """all_reduce_chunks (Adam of chunk i overlaps the all-reduce of chunks i+1..) reduces every element once."""
+    world, port = 2, _free_port()
+    out = mp.Manager().dict()
+    mp.spawn(_chunk_worker, args=(world, port, out), nprocs=world, join=True)
+    g0, seen = out[0]
+    assert torch.equal(g0, torch.arange(1003, dtype=torch.float32) * 3) and torch.equal(g0, out[1][0])
+    assert seen == [(0, 256), (256, 512), (512, 768), (768, 1003)]
+    one = list(GradExchange().all_reduce_chunks(torch.zeros(10)))  # world 1: a single slice, no communication
+    assert len(one) == 1 and one[0][1] is None and (one[0][0].start, one[0][0].stop) == (0, 10)
+
+
 def test_flat_layout_and_seeds():
     params = make_nrms_params(V, E, H, Q, seed=1)
     fp = FlatParams(params, KEYS, "cpu")
