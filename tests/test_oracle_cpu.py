@@ -181,3 +181,19 @@ def test_product_path_refuses_cpu_tensors():
     from newsreclib_b200 import ops
     with pytest.raises(RuntimeError, match="CUDA tensor"):
         ops.gemm_test(torch.zeros(4, 16), torch.zeros(4, 16), False)
+
+
+def test_hydra_model_configs_match_module_constructors():
+    """configs/model/{nrms,naml}_b200.yaml carry exactly the constructor kwargs of the drop-in modules
+    (the reference's configs/model/{nrms,naml}.yaml keys) and point _target_ at them."""
+    import importlib
+    import inspect
+    import yaml
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for name in ("nrms_b200", "naml_b200"):
+        cfg = yaml.safe_load(open(os.path.join(root, "configs", "model", name + ".yaml")))
+        mod, cls = cfg.pop("_target_").rsplit(".", 1)
+        klass = getattr(importlib.import_module(mod), cls)
+        params = inspect.signature(klass.__init__).parameters
+        required = {k for k, v in params.items() if k != "self" and v.default is inspect.Parameter.empty}
+        assert required == set(cfg), (name, required ^ set(cfg))
