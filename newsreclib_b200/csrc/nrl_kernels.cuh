@@ -1153,23 +1153,26 @@ pool_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ Y,
   float dq_acc[2] = {0.f, 0.f}, db_acc[2] = {0.f, 0.f};  // qp <= 2 * blockDim (Q <= 256... host checks)
   for (long long g = blockIdx.x; g < G; g += gridDim.x) {
     const long long r0 = g * L;
-    // dw_t = dOut . Y_t  (one warp per row, coalesced over E; two rows in flight per warp)
-    for (int t = warp; t < L; t += 2 * nw) {
-      const int t2 = t + nw;
-      const bool two = t2 < L;
-      const float* y0 = Y + (r0 + t) * E;
-      const float* y1 = Y + (r0 + (two ? t2 : t)) * E;
-      float acc0 = 0.f, acc1 = 0.f;
+    // dw_t = dOut . Y_t  (one warp per row, coalesced over E; four rows in flight per warp)
+    for (int t = warp; t < L; t += 4 * nw) {
+      const float* yr[4];
+      bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        ok[u] = t + u * nw < L;
+        yr[u] = Y + (r0 + (ok[u] ? t + u * nw : t)) * E;
+      }
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
       for (int c = lane; c < E; c += 32) {
         const float dv = __ldg(d_out + g * E + c);
-        acc0 += dv * __ldg(y0 + c);
-        acc1 += dv * __ldg(y1 + c);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] += dv * __ldg(yr[u] + c);
       }
-      acc0 = warp_sum(acc0);
-      acc1 = warp_sum(acc1);
-      if (lane == 0) {
-        s_ds[t] = acc0;
-        if (two) s_ds[t2] = acc1;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float a = warp_sum(acc[u]);
+        if (lane == 0 && ok[u]) s_ds[t + u * nw] = a;
       }
     }
     __syncthreads();
@@ -1184,18 +1187,18 @@ pool_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ Y,
           dY1[(r0 + t) * E + c] = w[r0 + t] * d_out[g * E + c];
     }
     // single pass over A: dApre (split planes), and the dq / db partial sums of this thread's columns;
-    // rows are walked six at a time so that six independent loads are in flight per thread
+    // rows are walked ten at a time so that ten independent loads are in flight per thread
     int slot = 0;
     for (int j = threadIdx.x; j < qp; j += blockDim.x, ++slot) {
       const bool in = j < Q;
       const float qj = in ? qvec[j] : 0.f;
       float aq = 0.f, ab = 0.f;
-      for (int t0 = 0; t0 < L; t0 += 6) {
-        float a[6];
+      for (int t0 = 0; t0 < L; t0 += 10) {
+        float a[10];
 #pragma unroll
-        for (int u = 0; u < 6; ++u) a[u] = (in && t0 + u < L) ? __ldg(A + (r0 + t0 + u) * Q + j) : 0.f;
+        for (int u = 0; u < 10; ++u) a[u] = (in && t0 + u < L) ? __ldg(A + (r0 + t0 + u) * Q + j) : 0.f;
 #pragma unroll
-        for (int u = 0; u < 6; ++u) {
+        for (int u = 0; u < 10; ++u) {
           if (t0 + u < L) {
             const float sd = s_ds[t0 + u];
             const float v = sd * qj * (1.f - a[u] * a[u]);
