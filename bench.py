@@ -180,6 +180,8 @@ def main_naml(args, rank, local_rank, world):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     B, F_, W, CE, LA = args.batch, 400, 3, 100, 50
