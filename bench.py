@@ -253,6 +253,56 @@ def main_naml(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def make_trainer(NRMSTrainer, params, dev, prec, world, mode):
+    """Trainer + the name of the gradient exchange it uses.  One GPU: no exchange.  `auto`: the fused peer-memory
+    kernel if every rank can map its peers AND two probe steps leave bit-identical replicas with no barrier
+    timeout; otherwise NCCL all-reduce + dense Adam.  All ranks take the same branch (the verdict is all-reduced)."""
+    import torch.distributed as dist
+    if world == 1 or mode == "nccl":
+        return NRMSTrainer(params, H, device=dev, dropout_p=DROPOUT, precision=prec, exchange="nccl"), \
+            ("none (1 GPU)" if world == 1 else "nccl all-reduce + dense Adam")
+    def all_ok(ok):
+        t = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+    why, tr = "", None
+    try:
+        tr = NRMSTrainer(params, H, device=dev, dropout_p=DROPOUT, precision=prec, exchange="peer")
+        ok = True
+    except Exception as e:  # e.g. no peer access / IPC not permitted on this box
+        ok, why = False, f"{type(e).__name__}: {e}"
+    if all_ok(ok):
+        # probe: two tiny steps, then the replicas must be the same bits on every rank and no barrier may have timed out
+        rank = dist.get_rank()
+        hb = make_batch(4, VOCAB, hist="fixed", max_hist=6, cand="train", seed=4321 + rank, max_title_len=L)
+        b = {"x_hist": {"title": hb["x_hist"]["title"].to(dev)}, "x_cand": {"title": hb["x_cand"]["title"].to(dev)},
+             "batch_hist": hb["batch_hist"].to(dev), "batch_cand": hb["batch_cand"].to(dev), "labels": hb["labels"].to(dev)}
+        keep = tr.flat.clone()
+        for _ in range(2):
+            tr.train_step(b, 4, 6, CAND)
+        status = tr.peer_block.status()
+        lo, hi = tr.flat.clone(), tr.flat.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        ok = status == 0 and torch.equal(lo, hi) and not torch.equal(tr.flat, keep)
+        if all_ok(ok):
+            tr.flat.copy_(keep)  # back to the initial replica; the exchange epoch keeps counting
+            tr.m.zero_()
+            tr.v.zero_()
+            tr.step_count = 0
+            torch.cuda.synchronize()
+            dist.barrier()
+            return tr, "peer (nrl_exchange_adam_step: reduce-scatter + sharded Adam + all-gather in one kernel over NVLink peer memory)"
+        why = f"probe failed on some rank (here: status {status})"
+    if mode == "peer":
+        raise SystemExit(f"--exchange peer: {why or 'a peer rank failed'}")
+    if tr is not None and tr.peer_block is not None:
+        dist.barrier()
+        tr.peer_block.close()
+    return NRMSTrainer(params, H, device=dev, dropout_p=DROPOUT, precision=prec, exchange="nccl"), \
+        f"nccl all-reduce + dense Adam (peer exchange unavailable: {why or 'a peer rank failed'})"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -264,6 +314,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--model", default="nrms", choices=["nrms", "naml"],
                     help="nrms = the headline (BASELINE.json configs[1]); naml = configs[4] shape through NAMLModule")
+    ap.add_argument("--exchange", default=os.environ.get("NRL_EXCHANGE", "auto"), choices=["auto", "nccl", "peer"],
+                    help="N > 1: nccl = all-reduce + dense Adam; peer = nrl_exchange_adam_step over NVLink peer memory; "
+                         "auto = peer if its self-check passes on this box, else nccl (the line says which)")
     ap.add_argument("--vocab", type=int, default=VOCAB, help="70000 = MINDsmall-shape (headline), 130000 = MINDlarge-shape")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -298,7 +351,7 @@ def main():
 
     B = args.batch
     params = make_nrms_params(VOCAB, E, H, Q, seed=1234)  # same init on every rank (DDP replica)
-    trainer = NRMSTrainer(params, H, device=dev, dropout_p=DROPOUT, precision=prec)
+    trainer, exchange_used = make_trainer(NRMSTrainer, params, dev, prec, world, args.exchange)
     # a ring of distinct batches per rank so consecutive steps never see the same ids
     n_ring = 4
     host_batches, dev_batches = [], []
@@ -441,6 +494,8 @@ def main():
                "sample": f"{len(timed)} train steps of {bs} impressions on the host CPU (oracle port of the reference modules, fp32)",
                "ms_per_step": cms}
 
+    if trainer.peer_block is not None and trainer.peer_block.status() != 0:
+        raise SystemExit(f"rank {rank}: a peer-exchange barrier timed out (code {trainer.peer_block.status()}): numbers invalid")
     if rank == 0:
         out = {
             "metric": "impressions/sec", "value": value, "unit": "impressions/s", "n_gpus": world,
@@ -449,6 +504,7 @@ def main():
             "dtype": "fp32 via bf16x3 split on tcgen05 (fp32 accumulate)" if prec == ops.PREC_BF16X3 else "bf16 (fp32 accumulate)",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": f"dp{world}",
+                       "exchange": exchange_used,
                        "l2": "inputs rotate over 4 distinct batches; each step streams ~2 GB of activations "
                              "(>> 126 MB L2), so no step starts with a warm L2",
                        "precision": args.precision},

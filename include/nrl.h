@@ -218,6 +218,45 @@ int nrl_adam_step(float* p, const float* g, float* m, float* v, long long n, flo
                   float beta1, float beta2, float eps, long long step, float grad_scale,
                   void* stream);
 
+/* ---- the gradient exchange of data-parallel training fused with the optimizer step ----------
+ * Replaces, for world_size > 1, what Lightning DDP + torch.optim.Adam do for the reference after
+ * every backward pass (configs/trainer/ddp.yaml, configs/model/nrms.yaml:49-52; gradient mean
+ * over the ranks, then Adam on every replica) with ONE kernel per rank over NVLink peer memory:
+ * reduce-scatter of the flat gradient buffers by peer loads, Adam on the owned 1/world slice,
+ * all-gather of the new parameters by peer stores, bracketed by flag barriers in peer memory.
+ *
+ * These are the only entry points that allocate: peer-mapped memory has to come from cudaMalloc
+ * (IPC handles), so the flat parameter / gradient buffers of a rank live in one nrl_peer_alloc
+ * block that the caller lays out and frees.  Every rank allocates, exchanges the 64-byte handles
+ * out of band (torch.distributed.all_gather_object in newsreclib_b200/exchange.py) and opens its
+ * peers' blocks with its own device current. */
+#define NRL_MAX_RANKS 16
+#define NRL_FLAG_BYTES 512      /* per-rank flag block: zero once, 8-byte aligned, peer-mapped */
+#define NRL_IPC_HANDLE_BYTES 64
+typedef struct {
+  int world, rank;
+  float* params[NRL_MAX_RANKS];              /* flat parameter buffer of every rank ([rank] is local) */
+  const float* grads[NRL_MAX_RANKS];         /* flat gradient buffer of every rank */
+  unsigned long long* flags[NRL_MAX_RANKS];  /* flag block of every rank */
+} nrl_peer_set;
+int nrl_peer_alloc(size_t bytes, void** dev_ptr, unsigned char* handle /* [NRL_IPC_HANDLE_BYTES] */);
+int nrl_peer_free(void* dev_ptr);
+int nrl_peer_open(const unsigned char* handle, void** dev_ptr);
+int nrl_peer_close(void* dev_ptr);
+/* One exchange + Adam step over n elements (n % 4 == 0, all buffers 16-byte aligned).  m / v are
+ * LOCAL and indexed like the parameters; only the owned slice is read and written.  `epoch` must
+ * be the same on all ranks and grow by at least 1 per call (the trainer passes its step count);
+ * grad_scale = 1 / world gives DDP's mean.  max_ctas <= 0: 4 CTAs per SM.  timeout_ns == 0: 5 s.
+ * All ranks must call it for the same epoch; no other cross-rank wait may sit between. */
+int nrl_exchange_adam_step(const nrl_peer_set* peers, float* m, float* v, long long n, float lr,
+                           float beta1, float beta2, float eps, long long step,
+                           unsigned long long epoch, float grad_scale, int max_ctas,
+                           unsigned long long timeout_ns, void* stream);
+/* Synchronises `stream` and returns the flag block's error word (0 = every barrier completed,
+ * 1 / 2 = a ready / done wait timed out: a peer never arrived). */
+int nrl_exchange_status(const unsigned long long* flags_local, unsigned long long* error_host,
+                        void* stream);
+
 /* ---- NRMSModule.forward + model_step loss + backward, nrms_module.py:230-255,277,288 ------
  * One call = one pass of the hot path over one batch.  All inputs are device pointers.
  *   hist_ids [N_h, L], cand_ids [N_c, L], seg_hist [N_h], seg_cand [N_c] (sorted), labels [N_c]

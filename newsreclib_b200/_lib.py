@@ -49,6 +49,18 @@ class CnnDims(C.Structure):
     _fields_ = [("embed_dim", C.c_int), ("num_filters", C.c_int), ("window", C.c_int), ("query_dim", C.c_int)]
 
 
+MAX_RANKS = 16
+FLAG_BYTES = 512
+IPC_HANDLE_BYTES = 64
+
+
+class PeerSet(C.Structure):
+    """``nrl_peer_set``: the peer-mapped flat parameter / gradient buffers and flag blocks of every rank."""
+
+    _fields_ = [("world", C.c_int), ("rank", C.c_int), ("params", C.c_void_p * MAX_RANKS),
+                ("grads", C.c_void_p * MAX_RANKS), ("flags", C.c_void_p * MAX_RANKS)]
+
+
 class Dims(C.Structure):
     _fields_ = [("embed_dim", C.c_int), ("num_heads", C.c_int), ("query_dim", C.c_int)]
 
@@ -94,6 +106,12 @@ SIGNATURES = {
     "nrl_ce_soft_fwd": (_I, [_VP, _VP, _VP, _I, _I, _VP, _VP, _VP, _VP]),
     "nrl_ce_soft_bwd": (_I, [_VP, _VP, _VP, _I, _I, _VP, _F, _VP, _VP]),
     "nrl_adam_step": (_I, [_VP, _VP, _VP, _VP, _LL, _F, _F, _F, _F, _LL, _F, _VP]),
+    "nrl_peer_alloc": (_I, [_SZ, C.POINTER(C.c_void_p), C.c_char_p]),
+    "nrl_peer_free": (_I, [_VP]),
+    "nrl_peer_open": (_I, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "nrl_peer_close": (_I, [_VP]),
+    "nrl_exchange_adam_step": (_I, [C.POINTER(PeerSet), _VP, _VP, _LL, _F, _F, _F, _F, _LL, _ULL, _F, _I, _ULL, _VP]),
+    "nrl_exchange_status": (_I, [_VP, C.POINTER(_ULL), _VP]),
     "nrl_nrms_ws_bytes": (_SZ, [_LL, _LL, _I, _I, _I, _I, Dims]),
     "nrl_nrms_step": (_I, [_VP, _VP, _VP, _VP, _VP, _LL, _LL, _I, _I, _I, _I, _VP, _LL, _BP, _BP, Dims,
                            _I, _F, _I, _ULL, _VP, _VP, _I, _BP, _BP, _VP, _VP, _SZ, _I, _VP]),

@@ -19,6 +19,7 @@
 #include "nrl_kernels.cuh"
 #include "nrl_attn_mma.cuh"
 #include "nrl_naml.cuh"
+#include "nrl_exchange.cuh"
 
 using namespace nrl;
 typedef __nv_bfloat16 bf16;
@@ -1099,6 +1100,99 @@ int nrl_adam_step(float* p, const float* g, float* m, float* v, long long n, flo
   adam_kernel<<<grid_for(n, 256 * 4, 8 * g_dev.sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       p, g, m, v, n, lr, beta1, beta2, eps, (float)bc1, (float)std::sqrt(bc2), grad_scale);
   LAUNCH_CHECK("adam");
+  return NRL_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// peer-memory gradient exchange fused with Adam (nrl_exchange.cuh)
+// ----------------------------------------------------------------------------------------
+static_assert(sizeof(nrl_peer_set) == sizeof(PeerSet), "nrl_peer_set and PeerSet must have one layout");
+static_assert(NRL_MAX_RANKS == XCHG_MAX_RANKS && NRL_FLAG_BYTES == XCHG_FLAG_WORDS * 8, "flag block layout");
+static_assert(NRL_IPC_HANDLE_BYTES == sizeof(cudaIpcMemHandle_t), "IPC handle size");
+
+int nrl_peer_alloc(size_t bytes, void** dev_ptr, unsigned char* handle) {
+  if (!dev_ptr || !handle || bytes == 0) return fail(NRL_ERR_INVALID_ARG, "nrl_peer_alloc: bad argument");
+  void* p = nullptr;
+  CUDA_TRY(cudaMalloc(&p, bytes));
+  cudaError_t e = cudaMemset(p, 0, bytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return fail(NRL_ERR_CUDA, "nrl_peer_alloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
+  }
+  std::memcpy(handle, &h, sizeof(h));
+  *dev_ptr = p;
+  return NRL_OK;
+}
+int nrl_peer_free(void* dev_ptr) {
+  if (!dev_ptr) return NRL_OK;
+  CUDA_TRY(cudaFree(dev_ptr));
+  return NRL_OK;
+}
+int nrl_peer_open(const unsigned char* handle, void** dev_ptr) {
+  if (!handle || !dev_ptr) return fail(NRL_ERR_INVALID_ARG, "nrl_peer_open: bad argument");
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, sizeof(h));
+  // opened with the CALLER's device current: the driver maps the exporting GPU's allocation and enables
+  // peer access from this device to it
+  CUDA_TRY(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return NRL_OK;
+}
+int nrl_peer_close(void* dev_ptr) {
+  if (!dev_ptr) return NRL_OK;
+  CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr));
+  return NRL_OK;
+}
+
+int nrl_exchange_adam_step(const nrl_peer_set* peers, float* m, float* v, long long n, float lr, float beta1,
+                           float beta2, float eps, long long step, unsigned long long epoch, float grad_scale,
+                           int max_ctas, unsigned long long timeout_ns, void* stream) {
+  if (!peers || !m || !v || n <= 0 || step <= 0 || epoch == 0)
+    return fail(NRL_ERR_INVALID_ARG, "nrl_exchange_adam_step: bad argument");
+  if (peers->world < 1 || peers->world > NRL_MAX_RANKS || peers->rank < 0 || peers->rank >= peers->world)
+    return fail(NRL_ERR_INVALID_ARG, "nrl_exchange_adam_step: world %d rank %d", peers->world, peers->rank);
+  if (n % 4) return fail(NRL_ERR_INVALID_ARG, "nrl_exchange_adam_step: n = %lld is not a multiple of 4", n);
+  uintptr_t align = reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v);
+  for (int r = 0; r < peers->world; ++r) {
+    if (!peers->params[r] || !peers->grads[r] || !peers->flags[r])
+      return fail(NRL_ERR_INVALID_ARG, "nrl_exchange_adam_step: rank %d has a null buffer", r);
+    align |= reinterpret_cast<uintptr_t>(peers->params[r]) | reinterpret_cast<uintptr_t>(peers->grads[r]);
+    if (reinterpret_cast<uintptr_t>(peers->flags[r]) & 7)
+      return fail(NRL_ERR_INVALID_ARG, "nrl_exchange_adam_step: flag block of rank %d is not 8-byte aligned", r);
+  }
+  if (align & 15) return fail(NRL_ERR_INVALID_ARG, "nrl_exchange_adam_step: buffers must be 16-byte aligned");
+  TRY(device_init());
+  PeerSet ps;
+  std::memcpy(&ps, peers, sizeof(ps));
+  const double bc1 = 1.0 - std::pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - std::pow((double)beta2, (double)step);
+  const long long n4 = n / 4, per = (n4 + ps.world - 1) / ps.world;
+  int cap = max_ctas > 0 ? max_ctas : 4 * g_dev.sm_count;
+  const int grid = grid_for(per, 256, cap);
+  if (timeout_ns == 0) timeout_ns = 5000000000ull;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define XCHG_LAUNCH(W)                                                                                  \
+  exchange_adam_kernel<W><<<grid, 256, 0, st>>>(ps, m, v, n4, epoch, timeout_ns, lr, beta1, beta2, eps, \
+                                                (float)bc1, (float)std::sqrt(bc2), grad_scale)
+  switch (ps.world) {
+    case 1: XCHG_LAUNCH(1); break;
+    case 2: XCHG_LAUNCH(2); break;
+    case 4: XCHG_LAUNCH(4); break;
+    case 8: XCHG_LAUNCH(8); break;
+    default: XCHG_LAUNCH(0); break;
+  }
+#undef XCHG_LAUNCH
+  LAUNCH_CHECK("exchange_adam");
+  return NRL_OK;
+}
+
+int nrl_exchange_status(const unsigned long long* flags_local, unsigned long long* error_host, void* stream) {
+  if (!flags_local || !error_host) return fail(NRL_ERR_INVALID_ARG, "nrl_exchange_status: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaMemcpyAsync(error_host, flags_local + XCHG_ERR, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
   return NRL_OK;
 }
 

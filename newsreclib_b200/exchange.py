@@ -1,0 +1,134 @@
+"""Peer-memory gradient exchange fused with the Adam step (``nrl_exchange_adam_step``).
+
+What Lightning DDP + ``torch.optim.Adam`` do for the reference after every backward pass
+(``configs/trainer/ddp.yaml``, ``configs/model/nrms.yaml:49-52``: gradient mean over the ranks, then
+Adam on every replica) is ONE kernel per rank here: the flat parameter and gradient buffers of a
+rank live in a ``cudaMalloc`` block that every peer maps over NVLink (CUDA IPC); a rank sums the
+gradients of its 1/world slice by peer loads, runs Adam on that slice and stores the new values
+into every replica; flag barriers in the same peer memory bracket the kernel.  ``torch.distributed``
+is used once, at construction, to pass the 64-byte IPC handles around.
+
+``slice_bounds`` is the ownership rule of the kernel restated for the host (tests, checkpoint code
+that wants to gather the sharded Adam moments).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import _lib
+
+
+def slice_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Element range ``[lo, hi)`` of the flat buffers that ``rank`` owns (16-byte granules, the last
+    ranks may own less or nothing)."""
+    if n % 4:
+        raise ValueError(f"flat buffer length {n} is not a multiple of 4")
+    n4 = n // 4
+    per = (n4 + world - 1) // world
+    lo = min(n4, rank * per)
+    hi = min(n4, lo + per)
+    return 4 * lo, 4 * hi
+
+
+class _DevMem:
+    """``__cuda_array_interface__`` view of raw device memory so that torch can alias it."""
+
+    def __init__(self, ptr: int, nelem: int, typestr: str) -> None:
+        self.__cuda_array_interface__ = {"shape": (nelem,), "typestr": typestr, "data": (ptr, False),
+                                         "version": 3, "strides": None}
+
+
+class PeerBlock:
+    """One rank's peer-mapped block: ``[ params n f32 | grads n f32 | flag block ]`` and the same
+    blocks of all peers opened through their IPC handles."""
+
+    def __init__(self, n: int, device: torch.device, process_group=None) -> None:
+        lib = _lib.load()
+        dist = torch.distributed
+        on = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(process_group) if on else 1
+        self.rank = dist.get_rank(process_group) if on else 0
+        if self.world > _lib.MAX_RANKS:
+            raise ValueError(f"peer exchange is built for <= {_lib.MAX_RANKS} ranks, got {self.world}")
+        if n % 4:
+            raise ValueError("flat buffer length must be a multiple of 4 (16-byte slices)")
+        self.n, self.device = n, torch.device(device)
+        self._lib = lib
+        self._flag_off = 8 * n
+        nbytes = 8 * n + _lib.FLAG_BYTES
+        base, handle = C.c_void_p(), C.create_string_buffer(_lib.IPC_HANDLE_BYTES)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.nrl_peer_alloc(nbytes, C.byref(base), handle), "nrl_peer_alloc")
+        self.base = int(base.value)
+        self.flat = torch.as_tensor(_DevMem(self.base, n, "<f4"), device=self.device)
+        self.grad = torch.as_tensor(_DevMem(self.base + 4 * n, n, "<f4"), device=self.device)
+        self._opened: List[int] = []
+        bases = [0] * self.world
+        bases[self.rank] = self.base
+        if self.world > 1:
+            handles: List[Optional[bytes]] = [None] * self.world
+            dist.all_gather_object(handles, handle.raw, group=process_group)
+            with torch.cuda.device(self.device):
+                for r, h in enumerate(handles):
+                    if r == self.rank:
+                        continue
+                    ptr = C.c_void_p()
+                    _lib.check(lib.nrl_peer_open(h, C.byref(ptr)), f"nrl_peer_open(rank {r})")
+                    bases[r] = int(ptr.value)
+                    self._opened.append(bases[r])
+            dist.barrier(group=process_group)  # every block is zeroed and mapped before anyone signals
+        self.peer_set = peer_set(self.world, self.rank, [b for b in bases], [b + 4 * n for b in bases],
+                                 [b + self._flag_off for b in bases])
+
+    @property
+    def flags_ptr(self) -> int:
+        return self.base + self._flag_off
+
+    def status(self) -> int:
+        """Synchronise the current stream and return the flag block's error word (0 = ok)."""
+        err = C.c_ulonglong(0)
+        _lib.check(self._lib.nrl_exchange_status(self.flags_ptr, C.byref(err),
+                                                 torch.cuda.current_stream(self.device).cuda_stream),
+                   "nrl_exchange_status")
+        return int(err.value)
+
+    def close(self) -> None:
+        """Unmap the peers' blocks and free the local one (call on every rank, after a barrier)."""
+        if self.base == 0:
+            return
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            for ptr in self._opened:
+                self._lib.nrl_peer_close(ptr)
+            self._opened = []
+            self.flat = self.grad = None
+            self._lib.nrl_peer_free(self.base)
+        self.base = 0
+
+
+def peer_set(world: int, rank: int, params: List[int], grads: List[int], flags: List[int]) -> "_lib.PeerSet":
+    ps = _lib.PeerSet()
+    ps.world, ps.rank = int(world), int(rank)
+    for r in range(world):
+        ps.params[r], ps.grads[r], ps.flags[r] = params[r], grads[r], flags[r]
+    return ps
+
+
+def exchange_adam_step(ps: "_lib.PeerSet", m: torch.Tensor, v: torch.Tensor, n: int, step: int, *, lr=1e-4,
+                       beta1=0.9, beta2=0.999, eps=1e-8, grad_scale: Optional[float] = None, epoch: Optional[int] = None,
+                       max_ctas: int = 0, timeout_s: float = 5.0, stream: Optional[int] = None) -> None:
+    """Enqueue one fused exchange + Adam step (see ``include/nrl.h``)."""
+    lib = _lib.load()
+    for t, name in ((m, "m"), (v, "v")):
+        if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or t.numel() < n:
+            raise RuntimeError(f"exchange_adam_step: {name} must be a contiguous fp32 CUDA tensor of >= {n} elements")
+    if grad_scale is None:
+        grad_scale = 1.0 / ps.world
+    if stream is None:
+        stream = torch.cuda.current_stream(m.device).cuda_stream
+    _lib.check(lib.nrl_exchange_adam_step(C.byref(ps), m.data_ptr(), v.data_ptr(), n, lr, beta1, beta2, eps, step,
+                                          int(epoch if epoch is not None else step), grad_scale, int(max_ctas),
+                                          int(timeout_s * 1e9), stream), "nrl_exchange_adam_step")

@@ -8,6 +8,10 @@ the Adam moments.  A step is three library calls on the current CUDA stream:
     [-> one NCCL all-reduce of the flat gradient buffer when world_size > 1]
     ->  nrl_adam_step (dense Adam over the flat buffer, torch.optim.Adam semantics)
 
+or, with ``exchange="peer"``, the last two lines are ONE kernel over NVLink peer memory
+(``nrl_exchange_adam_step``: reduce-scatter by peer loads, Adam on the owned slice, all-gather by
+peer stores; ``exchange.py``).
+
 The path shards by impression batch (each rank runs its own ``batch_size`` impressions, as
 Lightning DDP does for the reference, ``configs/trainer/ddp.yaml``); the only exchange is the
 gradient all-reduce, averaged by ``grad_scale = 1 / world_size`` inside the Adam kernel.
@@ -32,7 +36,10 @@ class FlatParams:
     device, so the world_size-2 gloo tests exercise it on CPU).  Every tensor starts on a
     16-byte boundary (the table gradient uses 128-bit atomics)."""
 
-    def __init__(self, params: Dict[str, torch.Tensor], keys, device) -> None:
+    def __init__(self, params: Dict[str, torch.Tensor], keys, device, buffers=None) -> None:
+        """``buffers(total) -> (flat, grad)`` lets the caller place the parameter and gradient buffers
+        (zeroed, ``total`` fp32 each) in memory of its choice -- the peer-mapped block of
+        ``exchange.PeerBlock`` for the fused NVLink exchange; default: ordinary torch tensors."""
         self.keys = list(keys)
         shapes = [tuple(params[k].shape) for k in self.keys]
         sizes = [params[k].numel() for k in self.keys]
@@ -40,10 +47,15 @@ class FlatParams:
         for n in sizes:
             self.offsets.append(total)
             total += (n + 3) // 4 * 4
-        self.flat = torch.zeros(total, dtype=torch.float32, device=device)
-        self.grad = torch.zeros_like(self.flat)
-        self.m = torch.zeros_like(self.flat)
-        self.v = torch.zeros_like(self.flat)
+        if buffers is None:
+            self.flat = torch.zeros(total, dtype=torch.float32, device=device)
+            self.grad = torch.zeros_like(self.flat)
+        else:
+            self.flat, self.grad = buffers(total)
+            if self.flat.numel() != total or self.grad.numel() != total:
+                raise ValueError("FlatParams: buffers() must return two tensors of `total` elements")
+        self.m = torch.zeros(total, dtype=torch.float32, device=device)
+        self.v = torch.zeros_like(self.m)
         self.params, self.grads = {}, {}
         for k, o, n, shp in zip(self.keys, self.offsets, sizes, shapes):
             self.params[k] = self.flat[o:o + n].view(shp)
@@ -104,12 +116,27 @@ class NRMSTrainer:
     def __init__(self, params: Dict[str, torch.Tensor], num_heads: int, *, device="cuda",
                  dropout_p: float = 0.2, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
                  precision: int = ops.PREC_BF16X3, late_fusion: bool = False, seed: int = 1234,
-                 process_group=None) -> None:
+                 process_group=None, exchange: Optional[str] = None) -> None:
+        """``exchange``: how the ranks' gradients meet the optimizer when world_size > 1 --
+        ``"nccl"`` (one NCCL all-reduce of the flat gradient buffer, then dense Adam on every rank) or
+        ``"peer"`` (``nrl_exchange_adam_step``: reduce-scatter + sharded Adam + all-gather as one kernel
+        over NVLink peer memory, ``exchange.py``).  Default: ``$NRL_EXCHANGE`` or ``"nccl"``."""
         _lib.load()
         self.device = torch.device(device)
         self.keys = [TITLE + "embedding_layer.weight"] + [TITLE + k for k in ops.BLOCK_KEYS] + \
                     [USER + k for k in ops.BLOCK_KEYS]
-        self.fp = FlatParams(params, self.keys, self.device)
+        self.exchange_mode = (exchange or os.environ.get("NRL_EXCHANGE", "nccl")).lower()
+        if self.exchange_mode not in ("nccl", "peer"):
+            raise ValueError(f"exchange must be 'nccl' or 'peer', got {self.exchange_mode!r}")
+        self.peer_block = None
+        buffers = None
+        if self.exchange_mode == "peer":
+            from .exchange import PeerBlock
+
+            def buffers(total):
+                self.peer_block = PeerBlock(total, self.device, process_group)
+                return self.peer_block.flat, self.peer_block.grad
+        self.fp = FlatParams(params, self.keys, self.device, buffers)
         self.flat, self.grad, self.m, self.v = self.fp.flat, self.fp.grad, self.fp.m, self.fp.v
         self.params, self.grads = self.fp.params, self.fp.grads
         self.table = self.params[self.keys[0]]
@@ -123,6 +150,7 @@ class NRMSTrainer:
         self.dropout_p, self.lr, self.betas, self.eps = dropout_p, lr, betas, eps
         self.precision, self.late_fusion, self.seed = precision, late_fusion, seed
         self.step_count = 0
+        self.exchange_epoch = 0
         self.ws: Optional[torch.Tensor] = None
         self.exchange = GradExchange(process_group)
         self.world = self.exchange.world
@@ -138,6 +166,13 @@ class NRMSTrainer:
     def _finish(self) -> None:
         scale = 1.0 / self.world
         self.step_count += 1
+        if self.peer_block is not None:
+            from .exchange import exchange_adam_step
+            self.exchange_epoch += 1  # barrier epoch: never reset, also when step_count is
+            exchange_adam_step(self.peer_block.peer_set, self.m, self.v, self.flat.numel(), self.step_count,
+                               lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, grad_scale=scale,
+                               epoch=self.exchange_epoch)
+            return
         # Adam on chunk i overlaps the all-reduce of chunks i+1.. (one chunk = everything when world == 1)
         for sl, _ in self.exchange.all_reduce_chunks(self.grad):
             ops.adam_step(self.flat[sl], self.grad[sl], self.m[sl], self.v[sl], self.step_count, self.lr,

@@ -1,0 +1,169 @@
+"""The fused gradient exchange + Adam kernel (``nrl_exchange_adam_step``, csrc/nrl_exchange.cuh).
+
+What it replaces for the reference: Lightning DDP's gradient mean over the ranks followed by
+``torch.optim.Adam`` on every replica (configs/trainer/ddp.yaml, configs/model/nrms.yaml:49-52).  The
+checker is ``oracle.nrms_oracle.adam_step`` (the restated torch Adam) applied to the rank-ordered sum of
+the gradients.  Single-GPU tests run several "virtual ranks" of one process concurrently on separate
+streams (the kernel only sees pointers: peer blocks, flag blocks); the real two-process / two-GPU
+run is ``test_two_gpu_processes`` (skipped on a one-GPU box)."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+pytestmark = pytest.mark.gpu
+
+LR, B1, B2, EPS = 1e-3, 0.9, 0.999, 1e-8
+
+
+def _expected(p0, grads, steps, world):
+    """Rank-ordered gradient sum -> mean -> torch.optim.Adam semantics, in float64-free fp32 torch ops."""
+    from oracle.nrms_oracle import adam_step
+
+    p = p0.clone()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for s in range(1, steps + 1):
+        g = grads[s - 1][0].clone()
+        for r in range(1, world):
+            g = g + grads[s - 1][r]
+        adam_step(p, g * (1.0 / world), m, v, s, lr=LR, beta1=B1, beta2=B2, eps=EPS)
+    return p
+
+
+def _mostly_close(a, b, tol, frac=1e-4):
+    """Adam divides by sqrt(v): an element whose gradient is pure rounding noise (terms that cancel) can move by
+    +-lr in either run, so runs that sum gradients in a different order (float atomics, rank order) are compared
+    on all but a vanishing fraction of the elements."""
+    return float(((a - b).abs() > tol).float().mean()) < frac
+
+
+def test_world1_matches_adam_kernel():
+    from newsreclib_b200 import _lib, ops
+    from newsreclib_b200.exchange import exchange_adam_step, peer_set
+
+    dev = torch.device("cuda:0")
+    n = 4 * 100_003
+    g = torch.Generator(device="cpu").manual_seed(5)
+    p0 = torch.randn(n, generator=g).to(dev)
+    grad = torch.randn(n, generator=g).to(dev)
+    pa, ma, va = p0.clone(), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    pb, mb, vb = p0.clone(), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    flags = torch.zeros(_lib.FLAG_BYTES // 8, dtype=torch.int64, device=dev)
+    ps = peer_set(1, 0, [pb.data_ptr()], [grad.data_ptr()], [flags.data_ptr()])
+    for step in (1, 2, 3):
+        ops.adam_step(pa, grad, ma, va, step, LR, B1, B2, EPS, grad_scale=0.5)
+        exchange_adam_step(ps, mb, vb, n, step, lr=LR, beta1=B1, beta2=B2, eps=EPS, grad_scale=0.5)
+    torch.cuda.synchronize()
+    assert int(flags[32]) == 0
+    # same expression, same order of operations: the two kernels agree to the last bit or the last ulp
+    assert torch.allclose(pa, pb, rtol=1e-6, atol=1e-7)
+    assert torch.allclose(ma, mb, rtol=1e-6, atol=1e-9) and torch.allclose(va, vb, rtol=1e-6, atol=1e-12)
+
+
+@pytest.mark.parametrize("world,n", [(2, 4 * 65_537), (4, 4 * 50_001), (3, 4 * 1_001), (8, 4 * 9_999), (5, 8)])
+def test_virtual_ranks_on_one_gpu(world, n):
+    """`world` ranks of one process, one stream each, 8 CTAs per rank so that all are co-resident and the flag
+    barriers can complete.  Every replica must end with the same bits, equal to Adam on the mean gradient."""
+    from newsreclib_b200 import _lib
+    from newsreclib_b200.exchange import exchange_adam_step, peer_set, slice_bounds
+
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device="cpu").manual_seed(100 + world)
+    steps = 3
+    p0 = torch.randn(n, generator=gen)
+    grads = [[torch.randn(n, generator=gen) * (0.1 + r) for r in range(world)] for _ in range(steps)]
+    params = [p0.clone().to(dev) for _ in range(world)]
+    gbuf = [torch.zeros(n, device=dev) for _ in range(world)]
+    ms = [torch.zeros(n, device=dev) for _ in range(world)]
+    vs = [torch.zeros(n, device=dev) for _ in range(world)]
+    flags = [torch.zeros(_lib.FLAG_BYTES // 8, dtype=torch.int64, device=dev) for _ in range(world)]
+    sets = [peer_set(world, r, [t.data_ptr() for t in params], [t.data_ptr() for t in gbuf],
+                     [t.data_ptr() for t in flags]) for r in range(world)]
+    gdev = [[g.to(dev) for g in per_rank] for per_rank in grads]  # uploaded before any rank starts to wait
+    streams = [torch.cuda.Stream(device=dev) for _ in range(world)]
+    torch.cuda.synchronize()
+    for s in range(1, steps + 1):
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                # a rank's gradients are final when ITS stream reaches the exchange (what backward guarantees);
+                # the done barrier of the previous step is what allows them to be overwritten here
+                gbuf[r].copy_(gdev[s - 1][r], non_blocking=True)
+                exchange_adam_step(sets[r], ms[r], vs[r], n, s, lr=LR, beta1=B1, beta2=B2, eps=EPS, max_ctas=8,
+                                   timeout_s=3.0, stream=streams[r].cuda_stream)
+    torch.cuda.synchronize()
+    for r in range(world):
+        assert int(flags[r][32]) == 0, f"rank {r}: barrier timed out (code {int(flags[r][32])})"
+    want = _expected(p0, grads, steps, world)
+    for r in range(1, world):
+        assert torch.equal(params[0], params[r]), f"replica {r} differs from replica 0"
+    got = params[0].cpu()
+    assert torch.allclose(got, want, rtol=2e-6, atol=1e-7), float((got - want).abs().max())
+    # Adam moments are sharded: rank r's are non-zero only on the slice it owns
+    for r in range(world):
+        lo, hi = slice_bounds(n, world, r)
+        outside = torch.cat([ms[r][:lo], ms[r][hi:]])
+        assert not bool(outside.any())
+        if hi > lo:
+            assert bool(ms[r][lo:hi].any())
+
+
+def test_bad_arguments_are_loud():
+    from newsreclib_b200 import _lib
+    from newsreclib_b200.exchange import exchange_adam_step, peer_set
+
+    dev = torch.device("cuda:0")
+    t = torch.zeros(64, device=dev)
+    flags = torch.zeros(64, dtype=torch.int64, device=dev)
+    ps = peer_set(1, 0, [t.data_ptr()], [t.data_ptr()], [flags.data_ptr()])
+    with pytest.raises(RuntimeError, match="multiple of 4"):
+        exchange_adam_step(ps, t, t, 62, 1)
+    with pytest.raises(RuntimeError, match="16-byte"):
+        exchange_adam_step(peer_set(1, 0, [t.data_ptr() + 4], [t.data_ptr()], [flags.data_ptr()]), t, t, 8, 1)
+    bad = _lib.PeerSet()
+    bad.world, bad.rank = 3, 5
+    with pytest.raises(RuntimeError, match="world 3 rank 5"):
+        exchange_adam_step(bad, t, t, 8, 1)
+
+
+def test_trainer_peer_mode_single_rank_matches_default():
+    """NRMSTrainer(exchange="peer") places the flat parameter / gradient buffers in an nrl_peer_alloc block
+    (aliased by torch through __cuda_array_interface__); at world_size 1 a step must equal the default trainer's."""
+    from newsreclib_b200.synthetic import make_batch, make_nrms_params
+    from newsreclib_b200.trainer import NRMSTrainer
+
+    dev = torch.device("cuda:0")
+    params = make_nrms_params(500, 300, 15, 200, seed=3)
+    hb = make_batch(4, 500, hist="ragged", max_hist=10, cand="train", seed=9, max_title_len=30)
+    batch = {"x_hist": {"title": hb["x_hist"]["title"].to(dev)}, "x_cand": {"title": hb["x_cand"]["title"].to(dev)},
+             "batch_hist": hb["batch_hist"].to(dev), "batch_cand": hb["batch_cand"].to(dev), "labels": hb["labels"].to(dev)}
+    Hmax = int(torch.bincount(hb["batch_hist"]).max())
+    Cmax = int(torch.bincount(hb["batch_cand"]).max())
+    a = NRMSTrainer(params, 15, device=dev, dropout_p=0.0, exchange="nccl")
+    b = NRMSTrainer(params, 15, device=dev, dropout_p=0.0, exchange="peer")
+    assert b.peer_block is not None and b.flat.data_ptr() == b.peer_block.base
+    flat0 = a.flat.clone()
+    assert torch.equal(flat0, b.flat)
+    for _ in range(3):
+        sa, la = a.train_step(batch, 4, Hmax, Cmax)
+        sb, lb = b.train_step(batch, 4, Hmax, Cmax)
+        # the embedding-gradient scatter uses float atomics: two runs agree to rounding, not to the bit
+        assert torch.allclose(sa, sb, rtol=1e-4, atol=1e-5) and torch.allclose(la, lb, rtol=1e-4, atol=1e-6)
+    assert b.peer_block.status() == 0
+    assert _mostly_close(a.flat, b.flat, 1e-6)
+    assert float((a.flat - flat0).abs().max()) > 0  # it trained
+    b.peer_block.close()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_two_gpu_processes():
+    """Two processes, two GPUs, CUDA-IPC peer blocks: peer-mode training steps against NCCL all-reduce + Adam."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29631", os.path.join(ROOT, "tests", "multi_gpu_worker.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "MULTI_GPU_OK" in out.stdout, out.stdout[-3000:]
