@@ -1,4 +1,4 @@
-"""Worker of tests/test_gpu_exchange.py::test_two_gpu_processes (launched with torchrun, one rank per GPU).
+"""Worker of tests/test_gpu_peer_exchange.py::test_two_gpu_processes (launched with torchrun, one rank per GPU).
 
 Trains the NRMS step for a few steps twice from the same initial parameters and the same per-rank batches and
 dropout seeds: once with the NCCL all-reduce + dense Adam exchange, once with the fused peer-memory kernel
