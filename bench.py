@@ -326,6 +326,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        # rank 0's stdout carries ONE JSON line: NCCL writes its version banner to fd 1 whatever NCCL_DEBUG says,
+        # so fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved descriptor
+        sys.stdout.flush()
+        real_stdout = os.dup(1)
+        os.dup2(2, 1)
+        sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if args.impl == "reference":
         run_reference_arm(args, rank)
         return

@@ -35,11 +35,14 @@ def _expected(p0, grads, steps, world):
     return p
 
 
-def _mostly_close(a, b, tol, frac=1e-4):
-    """Adam divides by sqrt(v): an element whose gradient is pure rounding noise (terms that cancel) can move by
-    +-lr in either run, so runs that sum gradients in a different order (float atomics, rank order) are compared
-    on all but a vanishing fraction of the elements."""
-    return float(((a - b).abs() > tol).float().mean()) < frac
+def _mostly_close(a, b, tol, frac=2e-3):
+    """Adam divides by sqrt(v), so an element whose gradient is pure rounding noise moves by +-lr in either of two
+    runs that sum gradients in a different order (float atomics, rank order).  The NRMS path has ~600 such
+    elements by construction -- the key third of both in_proj_bias vectors: softmax is invariant to a constant
+    key shift, so that gradient is mathematically zero -- hence: all but a small fraction of the elements within
+    `tol`, and the median difference far below it."""
+    d = (a - b).abs()
+    return float((d > tol).float().mean()) < frac and float(d.median()) < 0.1 * tol
 
 
 def test_world1_matches_adam_kernel():
