@@ -480,6 +480,23 @@ def main():
                 hbm_kernels.append({"kernel": nm, "ms_per_step": round(ms, 4), "algorithmic_mbytes": round(nbytes / 1e6, 1),
                                     "achieved_gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / hbm, 3)})
 
+    # the fused exchange kernel (N > 1, --exchange peer): bytes that cross NVLink per rank and step, per direction
+    # (gradients of the owned slice pulled from W-1 peers; new parameters of the owned slice pushed to W-1 peers;
+    # a rank also serves the same amounts to its peers), over the live launch duration -- which includes waiting
+    # for the slowest rank's backward pass at the ready barrier
+    exchange_info = None
+    try:
+        if rank == 0 and world > 1 and "exchange_adam" in agg:
+            n_flat = trainer.flat.numel()
+            ms_x = agg["exchange_adam"][0] / prof_steps
+            link = 4.0 * n_flat * (world - 1) / world
+            exchange_info = {"kernel": "exchange_adam", "ms_per_step": round(ms_x, 4),
+                             "nvlink_mbytes_in": round(link / 1e6, 1), "nvlink_mbytes_out": round(link / 1e6, 1),
+                             "achieved_gbs_per_direction": round(link / (ms_x / 1e3) / 1e9, 1),
+                             "adam_elements_per_rank": n_flat // world}
+    except Exception as e:  # never lose the line over a diagnostic
+        exchange_info = {"error": repr(e)}
+
     # ---- timed region C: end to end through the C ABI with host buffers -------------------
     for i in range(2):
         step_host(i)
@@ -519,7 +536,8 @@ def main():
                     "ms_per_step": ms_e2e},
             "eval_forward": {"value": world * B / (ms_eval / 1e3), "unit": "impressions/s", "ms_per_step": ms_eval},
             "gpu_launches": int(launches),
-            "clocks": clocks, "roofline": roof, "hbm_kernels": hbm_kernels, "cpu_baseline": cpu,
+            "clocks": clocks, "roofline": roof, "hbm_kernels": hbm_kernels, "exchange": exchange_info,
+            "cpu_baseline": cpu,
         }
         print(json.dumps(out), flush=True)
     if world > 1:
