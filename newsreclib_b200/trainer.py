@@ -105,6 +105,14 @@ class GradExchange:
             work.wait()  # the current stream waits for this chunk only
             yield sl, work
 
+    def gather_sharded(self, t: torch.Tensor) -> torch.Tensor:
+        """Full copy of a tensor that every rank holds only on the slice it owns and as zeros elsewhere (the Adam
+        moments under the fused peer exchange, ``exchange.slice_bounds``): the sum over the ranks."""
+        out = t.detach().clone()
+        if self.world > 1:
+            torch.distributed.all_reduce(out, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+        return out
+
     @staticmethod
     def rank_seed(base_seed: int, rank: int, step: int) -> int:
         """Dropout seed of (rank, step): ranks must not share masks (they see different
@@ -161,6 +169,15 @@ class NRMSTrainer:
     def state_dict(self) -> Dict[str, torch.Tensor]:
         """Reference-named parameters (loadable into the reference's NRMSModule)."""
         return {k: v.detach().clone() for k, v in self.params.items()}
+
+    def gather_moments(self):
+        """Full Adam moments ``(exp_avg, exp_avg_sq)`` as flat tensors in ``FlatParams`` order, on every rank (for an
+        optimizer checkpoint).  With the fused peer exchange a rank updates only the slice it owns
+        (``exchange.slice_bounds``) and the rest stays zero, so the full state is the sum over the ranks; with the
+        NCCL exchange every rank already holds it."""
+        if self.peer_block is None:
+            return self.m.detach().clone(), self.v.detach().clone()
+        return self.exchange.gather_sharded(self.m), self.exchange.gather_sharded(self.v)
 
     # ------------------------------------------------------------------ steps
     def _finish(self) -> None:

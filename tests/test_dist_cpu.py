@@ -3,6 +3,8 @@ exchange step of the path (gradient all-reduce + 1/world averaging folded into A
 per-rank dropout seeds.  The arithmetic on each rank is done by the oracle (this is a test of
 the plumbing around the kernels, which is device-agnostic)."""
 import os
+
+import pytest
 import socket
 
 import torch
@@ -104,3 +106,64 @@ def test_flat_layout_and_seeds():
     assert GradExchange().world == 1 and GradExchange().all_reduce(fp.grad) == 1.0
     seeds = {GradExchange.rank_seed(1234, r, s) for r in range(8) for s in range(1000)}
     assert len(seeds) == 8000
+
+
+def _sharded_worker(rank, world, port, out):
+    """CPU restatement of what nrl_exchange_adam_step does on a rank (csrc/nrl_exchange.cuh): rank-ordered sum of the
+    ranks' gradients on the OWNED slice, Adam there, new parameters to every replica; moments stay sharded."""
+    from newsreclib_b200.exchange import slice_bounds
+    from oracle import nrms_oracle as O
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 4 * 257
+    gen = torch.Generator().manual_seed(7)
+    p = torch.randn(n, generator=gen)
+    m, v = torch.zeros(n), torch.zeros(n)
+    lo, hi = slice_bounds(n, world, rank)
+    for step in (1, 2, 3):
+        grads = [torch.randn(n, generator=gen) * (r + 1) for r in range(world)]   # every rank can see every gradient here
+        g = grads[0][lo:hi].clone()
+        for r in range(1, world):
+            g += grads[r][lo:hi]
+        O.adam_step(p[lo:hi], g * (1.0 / world), m[lo:hi], v[lo:hi], step, eps=EPS)
+        new = torch.zeros(n)
+        new[lo:hi] = p[lo:hi]
+        dist.all_reduce(new)                                  # "peer stores": every replica receives every owned slice
+        p.copy_(new)
+    ex = GradExchange()
+    out[rank] = (p.clone(), ex.gather_sharded(m), ex.gather_sharded(v), m.clone())
+    dist.destroy_process_group()
+
+
+def test_sharded_exchange_equals_all_reduce_plus_dense_adam():
+    from newsreclib_b200.exchange import slice_bounds
+    from oracle import nrms_oracle as O
+    world, port = 2, _free_port()
+    out = mp.Manager().dict()
+    mp.spawn(_sharded_worker, args=(world, port, out), nprocs=world, join=True)
+    n = 4 * 257
+    gen = torch.Generator().manual_seed(7)
+    p = torch.randn(n, generator=gen)
+    m, v = torch.zeros(n), torch.zeros(n)
+    for step in (1, 2, 3):
+        grads = [torch.randn(n, generator=gen) * (r + 1) for r in range(world)]
+        O.adam_step(p, (grads[0] + grads[1]) * 0.5, m, v, step, eps=EPS)
+    for rank in range(world):
+        pr, mr, vr, m_local = out[rank]
+        assert torch.equal(pr, p) and torch.equal(mr, m) and torch.equal(vr, v)   # same elementwise arithmetic: same bits
+        lo, hi = slice_bounds(n, world, rank)
+        assert not bool(m_local[:lo].any()) and not bool(m_local[hi:].any()) and bool(m_local[lo:hi].any())
+
+
+def test_slice_ownership_partitions_the_flat_buffer():
+    from newsreclib_b200.exchange import slice_bounds
+    for n in (4, 8, 12, 4 * 1001, 4 * 21_843_200 // 4):
+        for world in (1, 2, 3, 4, 5, 8, 16):
+            edges = [slice_bounds(n, world, r) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(edges, edges[1:]))            # contiguous, disjoint, in rank order
+            assert all(lo % 4 == 0 and hi % 4 == 0 and lo <= hi for lo, hi in edges)  # 16-byte granules
+            sizes = [hi - lo for lo, hi in edges]
+            assert max(sizes) - min(s for s in sizes if s) <= 4 * ((n // 4 + world - 1) // world)  # at most one granule row
+    with pytest.raises(ValueError):
+        slice_bounds(10, 2, 0)
