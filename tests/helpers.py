@@ -114,3 +114,37 @@ def grad_tolerances(params, batch, H, base_tol, ref_grads=None, **kw):
     if ref_grads is None:
         _, _, ref_grads = oracle_run(params, batch, H, **kw)
     return {k: max(base_tol, 4.0 * rel_err(ref_grads[k], g64[k])) for k in ref_grads}
+
+
+def load_collate_golden():
+    """``tests/golden/collate_ref.npz`` (minted by ``oracle/make_collate_golden.py`` from the reference's own
+    ``DatasetCollate``): returns (news columns as lists, {split: (samples, reference batch dict)}, (L_title, L_abs))."""
+    g = dict(np.load(os.path.join(GOLD, "collate_ref.npz")))
+    L_title, L_abs = int(g["meta"][0]), int(g["meta"][1])
+    news = {}
+    for k in ("nid", "category_class", "subcategory_class", "sentiment_class", "sentiment_score"):
+        news[k] = g[f"news.{k}"].tolist()
+    for k in ("tokenized_title", "tokenized_abstract"):
+        flat, lens = g[f"news.{k}.flat"], g[f"news.{k}.len"]
+        cuts = np.concatenate([[0], np.cumsum(lens)])
+        news[k] = [flat[a:b].tolist() for a, b in zip(cuts[:-1], cuts[1:])]
+    splits = {}
+    for split in ("test", "train"):
+        def ragged(name, lens):
+            cuts = np.concatenate([[0], np.cumsum(g[f"{split}.{lens}"])])
+            return [g[f"{split}.{name}"][a:b] for a, b in zip(cuts[:-1], cuts[1:])]
+        hist, cand = ragged("hist_rows", "hist_len"), ragged("cand_rows", "cand_len")
+        labels = ragged("labels", "cand_len")
+        samples = [(g[f"{split}.user_ids"][i:i + 1], g[f"{split}.user_idx"][i:i + 1], hist[i], cand[i], labels[i])
+                   for i in range(len(hist))]
+        ref = {}
+        for k, v in g.items():
+            if k.startswith(f"{split}.batch."):
+                name = k[len(f"{split}.batch."):]
+                if "." in name:
+                    side, col = name.split(".", 1)
+                    ref.setdefault(side, {})[col] = torch.from_numpy(v)
+                else:
+                    ref[name] = torch.from_numpy(v)
+        splits[split] = (samples, ref)
+    return news, splits, (L_title, L_abs)

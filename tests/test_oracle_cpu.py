@@ -197,3 +197,47 @@ def test_hydra_model_configs_match_module_constructors():
         params = inspect.signature(klass.__init__).parameters
         required = {k for k, v in params.items() if k != "self" and v.default is inspect.Parameter.empty}
         assert required == set(cfg), (name, required ^ set(cfg))
+
+
+@pytest.mark.parametrize("split", ["test", "train"])
+def test_collate_oracle_matches_reference_collate_golden(split):
+    """collate_ref.npz holds the output of the reference's OWN DatasetCollate.__call__ (rec_dataset.py:148-293) on
+    impressions produced by its own Dataset classes (test split; train split with 4:1 negative sampling under a fixed
+    numpy seed): the restatement must reproduce every tensor bit for bit, dtype included."""
+    from helpers import load_collate_golden
+    from oracle import collate_oracle as CO
+    news, splits, (lt, la) = load_collate_golden()
+    samples, ref = splits[split]
+    got = CO.collate(news, samples, lt, la)
+    assert set(got) == set(ref)
+    for k, v in ref.items():
+        if isinstance(v, dict):
+            assert set(got[k]) == set(v)
+            for c, t in v.items():
+                assert got[k][c].dtype == t.dtype and torch.equal(got[k][c], t), (k, c)
+        else:
+            assert got[k].dtype == v.dtype and torch.equal(got[k], v), k
+    assert ref["x_hist"]["title"].shape[1] == lt and ref["x_hist"]["abstract"].shape[1] == la
+    assert int(torch.bincount(ref["batch_hist"]).max()) <= 50          # max_history_len applied by the Dataset
+    if split == "train":                                               # 1 positive : 4 negatives per positive
+        B = int(ref["batch_cand"].max()) + 1
+        for b in range(B):
+            y = ref["labels"][ref["batch_cand"] == b]
+            assert int((y == 0).sum()) == 4 * int((y == 1).sum())
+
+
+def test_device_table_padding_matches_reference_collate_golden():
+    """Host half of the device-side collate (f2): the table padded ONCE with pad_token_lists and indexed by row equals
+    what the reference pads per batch (its negative F.pad truncates long titles; empty titles become all-zero rows)."""
+    from helpers import load_collate_golden
+    from newsreclib_b200.data.components.device_collate import pad_token_lists
+    news, splits, (lt, la) = load_collate_golden()
+    title, abstract = pad_token_lists(news["tokenized_title"], lt), pad_token_lists(news["tokenized_abstract"], la)
+    assert title.dtype == np.int64 and title.shape == (len(news["nid"]), lt)
+    for split, (samples, ref) in splits.items():
+        hist = np.concatenate([s[2] for s in samples])
+        cand = np.concatenate([s[3] for s in samples])
+        assert np.array_equal(title[hist], ref["x_hist"]["title"].numpy())
+        assert np.array_equal(title[cand], ref["x_cand"]["title"].numpy())
+        assert np.array_equal(abstract[hist], ref["x_hist"]["abstract"].numpy())
+        assert np.array_equal(np.asarray(news["nid"])[cand], ref["x_cand"]["news_ids"].numpy())
