@@ -1,10 +1,17 @@
 """CPU restatement of the reference collate for pre-tokenised (non-PLM) news -- TEST INFRASTRUCTURE,
-imported only by ``tests/``.  ``newsreclib/data/components/rec_dataset.py`` itself cannot be imported in
-this image (``omegaconf`` / ``hydra`` / ``pandas``-side deps of its base class are missing), so
-``DatasetCollate.__call__`` (``:148-168``), ``_tokenize_embeddings`` (``:170-178``, the very same
-``F.pad`` call), the scalar columns of ``_tokenize_df`` (``:189-285``) and ``_make_batch_asignees``
-(``:289-293``) are restated line by line over plain Python lists.  Parity unpinned by reference tests
-(its only test needs network downloads and does not parse)."""
+imported only by ``tests/`` and ``oracle/make_collate_golden.py``.
+
+``DatasetCollate.__call__`` (``newsreclib/data/components/rec_dataset.py:148-168``), ``_tokenize_embeddings``
+(``:170-178``, the very same ``F.pad`` call), the scalar columns of ``_tokenize_df`` (``:189-285``) and
+``_make_batch_asignees`` (``:289-293``) restated over plain Python lists (table-row indices instead of pandas
+``.loc`` on news ids).
+
+Pinned: ``oracle/make_collate_golden.py`` loads the reference's ``rec_dataset.py`` UNMODIFIED (only the
+``mind_dataframe`` base-class import, which drags in ``omegaconf`` / ``hydra``, is satisfied by a stand-in), runs
+its own ``RecommendationDatasetTest`` / ``RecommendationDatasetTrain`` + ``DatasetCollate`` on a synthetic news
+table, asserts that this restatement reproduces every tensor bit for bit, and stores inputs and reference outputs
+in ``tests/golden/collate_ref.npz`` (checked by ``tests/test_oracle_cpu.py`` and, for the device-side collate,
+``tests/test_gpu_pipeline.py``).  The reference's own tests hold no vectors for this path."""
 from typing import Dict, List, Sequence
 
 import numpy as np

@@ -1,0 +1,191 @@
+"""Pin the oracle's glue against the reference's OWN ``NRMSModule`` (``forward`` + ``model_step``) and mint
+``tests/golden/nrms_module_ref_*.npz``.
+
+Runs ONLY in the build container (imports the unmodified reference from ``/root/reference``).
+``newsreclib/models/general_rec/nrms_module.py`` needs ``lightning``, ``torchmetrics``, ``torch_geometric`` and (through
+``newsreclib.models.components.losses``) ``pytorch_metric_learning``; none is installed and none takes part in the
+arithmetic of ``forward`` / ``model_step`` except ``torch_geometric.utils.to_dense_batch``.  The imports are satisfied
+with stand-ins:
+
+* ``lightning.LightningModule`` -> ``torch.nn.Module`` + ``save_hyperparameters`` (constructor arguments -> ``self.hparams``)
+  and a ``device`` property;
+* ``torchmetrics`` metric classes, ``newsreclib.metrics.*`` and ``SupConLoss`` -> inert objects (built in ``__init__``,
+  never called by ``forward`` / ``model_step`` with the cross-entropy loss);
+* ``torch_geometric.utils.to_dense_batch`` -> ``oracle.nrms_oracle.to_dense_batch``, the restatement of the published
+  PyG 2.3.0 algorithm -- third-party, absent, "parity unpinned" for that one function.
+
+``nrms_module.py`` and ``abstract_recommender.py`` themselves are loaded UNMODIFIED, so the scores, the loss and the
+11-tuple below come out of the reference's own ``NRMSModule.forward`` (``:230-255``) and ``model_step`` (``:260-362``).
+The script asserts that ``oracle/nrms_oracle.py`` reproduces them and stores batch, reference outputs and gradients.
+
+Usage:  python oracle/make_module_golden.py
+"""
+from __future__ import annotations
+
+import functools
+import inspect
+import os
+import sys
+import tempfile
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+
+from oracle import nrms_oracle as O  # noqa: E402
+
+
+# ------------------------------------------------------------------------------- stand-ins for absent packages
+class _HParams(dict):
+    __getattr__ = dict.__getitem__
+
+
+class LightningModule(torch.nn.Module):
+    def save_hyperparameters(self, *args, **kwargs):
+        hp = _HParams()
+        frame = inspect.currentframe().f_back
+        while frame is not None:  # every __init__ of the class chain that is on the stack contributes its arguments
+            if frame.f_code.co_name == "__init__" and frame.f_locals.get("self") is self:
+                for k, v in frame.f_locals.items():
+                    if k not in ("self", "__class__", "args", "kwargs"):
+                        hp.setdefault(k, v)
+            frame = frame.f_back
+        self.hparams = hp
+
+    @property
+    def device(self):
+        return next(self.parameters()).device if any(True for _ in self.parameters()) else torch.device("cpu")
+
+    def log(self, *a, **k):
+        pass
+
+    def log_dict(self, *a, **k):
+        pass
+
+
+class _Inert(torch.nn.Module):
+    def __init__(self, *a, **k):
+        super().__init__()
+
+    def clone(self, prefix=None):
+        return _Inert()
+
+    def add_metrics(self, *a, **k):
+        pass
+
+    def reset(self):
+        pass
+
+
+def _module(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+_module("lightning", LightningModule=LightningModule)
+_module("torch_geometric")
+_module("torch_geometric.utils", to_dense_batch=O.to_dense_batch)
+_module("torchmetrics", MetricCollection=_Inert, MeanMetric=_Inert, MinMetric=_Inert)
+_module("torchmetrics.classification", AUROC=_Inert)
+_module("torchmetrics.retrieval", RetrievalMRR=_Inert, RetrievalNormalizedDCG=_Inert)
+_module("newsreclib.metrics.diversity", Diversity=_Inert)
+_module("newsreclib.metrics.personalization", Personalization=_Inert)
+_module("newsreclib.models.components.losses", SupConLoss=_Inert)
+
+from newsreclib.models.general_rec.nrms_module import NRMSModule  # noqa: E402  (the reference's own file)
+
+from newsreclib_b200.synthetic import make_batch, make_nrms_params  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+OUTPUTS = {"train": ["preds", "targets", "cand_news_size"], "val": ["preds", "targets", "cand_news_size"],
+           "test": ["preds", "targets", "cand_news_size", "hist_news_size", "user_ids", "cand_news_ids"]}
+TITLE = "news_encoder.text_encoders.title."
+GRAD_STRIDE = 37
+
+
+def build_reference(params, late_fusion, tmpdir):
+    emb = os.path.join(tmpdir, "emb.npy")
+    np.save(emb, params[TITLE + "embedding_layer.weight"].numpy())
+    m = NRMSModule(
+        dataset_attributes=["title", "category"], attributes2encode=["title"], outputs=OUTPUTS,
+        dual_loss_training=False, dual_loss_coef=None, loss="cross_entropy_loss", late_fusion=late_fusion,
+        temperature=None, use_plm=False, pretrained_embeddings_path=emb, plm_model=None, frozen_layers=None,
+        embed_dim=300, num_heads=15, query_dim=200, dropout_probability=0.2, top_k_list=[5, 10],
+        num_categ_classes=18, num_sent_classes=3, save_recs=False, recs_fpath=None,
+        optimizer=functools.partial(torch.optim.Adam, lr=1e-4), scheduler=None)
+    own = {k: v for k, v in params.items() if k in m.state_dict()}
+    missing = m.load_state_dict(own, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return m.eval()
+
+
+def rel(a, b):
+    a, b = a.detach(), b.detach()
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+def mint(name, V, B, max_hist, seed, late_fusion):
+    params = make_nrms_params(V, seed=seed)
+    batch = make_batch(B, V, hist="ragged", cand="train" if not late_fusion else "eval", seed=seed, max_hist=max_hist)
+    with tempfile.TemporaryDirectory() as tmp:
+        m = build_reference(params, late_fusion, tmp)
+    scores = m(batch)                                   # NRMSModule.forward, nrms_module.py:230-255
+    out = m.model_step(batch)                           # nrms_module.py:260-362
+    assert len(out) == 11
+    loss = out[0]
+    loss.backward()
+    grads = {k: (p.grad.clone() if p.grad is not None else torch.zeros_like(p)) for k, p in m.named_parameters()}
+    # the oracle's restatement of the same glue
+    ps = {k: v.clone().requires_grad_(True) for k, v in params.items() if k in grads}
+    o_scores = O.nrms_forward(batch, ps, 15, late_fusion=late_fusion)
+    o_loss = O.nrms_loss(batch, o_scores)
+    o_loss.backward()
+    assert o_scores.shape == scores.shape and rel(o_scores, scores) < 2e-6, rel(o_scores, scores)
+    assert rel(o_loss, loss) < 2e-6
+    # arbiter for the gradients: the same oracle in float64.  A few gradients (the additive-attention bias: sum_t ds_t = 0
+    # per softmax group) cancel to ~1e-5 of their terms, so two fp32 evaluations agree only to their own noise there.
+    p64 = {k: v.double().clone().requires_grad_(True) for k, v in params.items() if k in grads}
+    b64 = dict(batch)
+    b64["labels"] = batch["labels"].double()
+    O.nrms_loss(b64, O.nrms_forward(b64, p64, 15, late_fusion=late_fusion)).backward()
+    for k, g in grads.items():
+        og = ps[k].grad.clone() if ps[k].grad is not None else torch.zeros_like(ps[k])
+        g64 = p64[k].grad.clone() if p64[k].grad is not None else torch.zeros_like(p64[k])
+        if k == TITLE + "embedding_layer.weight":
+            og[0] = 0  # nn.Embedding(padding_idx=0) never accumulates into row 0 (text.py:215-217), as helpers.oracle_run does
+            g64[0] = 0
+            assert float(g[0].abs().max()) == 0.0
+        if float(g64.abs().max()) < 1e-9:
+            continue  # mathematically zero (the key bias of in_proj_bias): both fp32 runs hold rounding noise
+        ref_noise = rel(g, g64)
+        assert ref_noise <= 2e-3, (k, ref_noise)                           # the reference agrees with the fp64 oracle
+        assert rel(og, g64) <= max(2e-5, 4.0 * ref_noise) + 1e-12, (k, rel(og, g64), ref_noise)
+    names = ["loss", "preds", "targets", "cand_news_size", "hist_news_size", "target_categories", "target_sentiments",
+             "hist_categories", "hist_sentiments", "user_ids", "cand_news_ids"]
+    rec = {"meta": np.array([300, 15, 200, V, B, max_hist, seed, 30, int(late_fusion)]), "scores": scores.detach().numpy()}
+    for n, t in zip(names, out):
+        rec["out/" + n] = t.detach().numpy()
+    for k, g in grads.items():  # small tensors whole, big ones as every GRAD_STRIDE-th element (fixtures stay small)
+        rec["grad/" + k] = (g if g.numel() <= 5000 else g.reshape(-1)[::GRAD_STRIDE]).numpy()
+    for side in ("x_hist", "x_cand"):
+        for k, v in batch[side].items():
+            rec[f"batch/{side}/{k}"] = v.numpy()
+    for k in ("batch_hist", "batch_cand", "labels", "user_ids", "user_idx"):
+        rec["batch/" + k] = batch[k].numpy()
+    rec["param_checksum"] = np.array([float(v.double().sum()) for v in params.values()])
+    path = os.path.join(GOLD, name + ".npz")
+    np.savez_compressed(path, **rec)
+    print(f"[{name}] reference NRMSModule.forward/model_step == oracle: scores rel {rel(o_scores, scores):.1e}, "
+          f"loss rel {rel(o_loss, loss):.1e}; wrote {os.path.getsize(path)} bytes")
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    mint("nrms_module_ref", V=500, B=6, max_hist=9, seed=31, late_fusion=False)
+    mint("nrms_module_ref_late_fusion", V=400, B=5, max_hist=7, seed=32, late_fusion=True)

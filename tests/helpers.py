@@ -148,3 +148,36 @@ def load_collate_golden():
                     ref[name] = torch.from_numpy(v)
         splits[split] = (samples, ref)
     return news, splits, (L_title, L_abs)
+
+
+MODULE_OUT = ["loss", "preds", "targets", "cand_news_size", "hist_news_size", "target_categories", "target_sentiments",
+              "hist_categories", "hist_sentiments", "user_ids", "cand_news_ids"]
+GRAD_STRIDE = 37  # oracle/make_module_golden.py stores big gradients as every 37th element
+
+
+def load_module_golden(name):
+    """``tests/golden/nrms_module_ref*.npz``: batch + outputs of the reference's OWN ``NRMSModule.forward`` /
+    ``model_step`` (minted by ``oracle/make_module_golden.py``).  Returns (params, batch, reference dict, meta)."""
+    g = dict(np.load(os.path.join(GOLD, name + ".npz")))
+    E, H, Q, V, B, max_hist, seed, L, late = [int(x) for x in g["meta"]]
+    params = make_nrms_params(V, E, H, Q, seed=seed)
+    chk = np.array([float(v.double().sum()) for v in params.values()])
+    assert np.allclose(chk, g["param_checksum"], rtol=1e-9), "seeded parameter generator drifted"
+    batch = {"x_hist": {}, "x_cand": {}}
+    for k, v in g.items():
+        if k.startswith("batch/"):
+            parts = k.split("/")
+            if len(parts) == 3:
+                batch[parts[1]][parts[2]] = torch.from_numpy(v)
+            else:
+                batch[parts[1]] = torch.from_numpy(v)
+    ref = {"scores": torch.from_numpy(g["scores"]),
+           "out": {n: torch.from_numpy(np.asarray(g["out/" + n])) for n in MODULE_OUT},
+           "grad": {k[len("grad/"):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("grad/")}}
+    return params, batch, ref, dict(E=E, H=H, Q=Q, V=V, B=B, L=L, late_fusion=bool(late))
+
+
+def grad_sample(g):
+    """The part of a gradient tensor the module fixtures store."""
+    g = g.detach().cpu()
+    return g if g.numel() <= 5000 else g.reshape(-1)[::GRAD_STRIDE]

@@ -241,3 +241,36 @@ def test_device_table_padding_matches_reference_collate_golden():
         assert np.array_equal(title[cand], ref["x_cand"]["title"].numpy())
         assert np.array_equal(abstract[hist], ref["x_hist"]["abstract"].numpy())
         assert np.array_equal(np.asarray(news["nid"])[cand], ref["x_cand"]["news_ids"].numpy())
+
+
+@pytest.mark.parametrize("name", ["nrms_module_ref", "nrms_module_ref_late_fusion"])
+def test_oracle_matches_reference_nrms_module_golden(name):
+    """The fixtures hold what the reference's OWN NRMSModule.forward (nrms_module.py:230-255) and model_step (:260-362)
+    returned (oracle/make_module_golden.py; only to_dense_batch is the restated PyG function): the oracle's glue must
+    reproduce scores, loss and gradients, and the 11-tuple must be what the GPU module's vectorised model_step assumes."""
+    from helpers import grad_sample, load_module_golden
+    params, batch, ref, meta = load_module_golden(name)
+    lf = meta["late_fusion"]
+    use = {k: v for k, v in params.items() if not (lf and k.startswith(USER))}
+    scores, loss, grads = oracle_run(use, batch, meta["H"], late_fusion=lf)
+    assert scores.shape == ref["scores"].shape and rel_err(scores, ref["scores"]) <= 2e-6
+    assert rel_err(loss, ref["out"]["loss"]) <= 2e-6
+    tols = grad_tolerances(use, batch, meta["H"], 2e-5, grads, late_fusion=lf)
+    for k, g in ref["grad"].items():
+        if float(g.abs().max()) < 1e-9:
+            continue  # mathematically zero gradient (key bias): rounding noise on both sides
+        assert rel_err(grad_sample(grads[k]), g) <= tols[k], k
+    # model_step's outputs in terms of the ragged batch (what two_tower.TwoTowerRecommender.model_step returns directly)
+    out = ref["out"]
+    B = meta["B"]
+    sizes_c, sizes_h = torch.bincount(batch["batch_cand"], minlength=B), torch.bincount(batch["batch_hist"], minlength=B)
+    assert torch.equal(out["cand_news_size"], sizes_c) and torch.equal(out["hist_news_size"], sizes_h)
+    mask = torch.arange(ref["scores"].shape[1])[None, :] < sizes_c[:, None]
+    assert torch.equal(out["preds"], ref["scores"][mask])                  # masked dense order == ragged order
+    assert torch.equal(out["targets"], batch["labels"])
+    assert torch.equal(out["target_categories"], batch["x_cand"]["category"])
+    assert torch.equal(out["target_sentiments"], batch["x_cand"]["sentiment"])
+    assert torch.equal(out["hist_categories"], batch["x_hist"]["category"])
+    assert torch.equal(out["hist_sentiments"], batch["x_hist"]["sentiment"])
+    assert torch.equal(out["user_ids"], batch["user_ids"]) and torch.equal(out["cand_news_ids"], batch["x_cand"]["news_ids"])
+    assert bool((ref["scores"][~mask] == 0).all())                          # padded slots score exactly 0.0
