@@ -185,7 +185,55 @@ def mint(name, V, B, max_hist, seed, late_fusion):
           f"loss rel {rel(o_loss, loss):.1e}; wrote {os.path.getsize(path)} bytes")
 
 
+def naml_check(name="naml_mind"):
+    """The NAML fixtures (``oracle/make_golden.py::naml_step_case``) were minted from the reference's component modules
+    glued by a restatement of ``NAMLModule.forward``.  Here the reference's OWN ``NAMLModule`` (``naml_module.py``,
+    loaded unmodified under the stand-ins above) runs ``forward`` / ``model_step`` on the very inputs of such a fixture and
+    must reproduce its scores and loss; the module-level outputs go to ``tests/golden/naml_module_ref.npz``."""
+    from newsreclib.models.general_rec.naml_module import NAMLModule
+    from newsreclib_b200.synthetic import make_naml_params
+    g = dict(np.load(os.path.join(GOLD, name + ".npz")))
+    V, E, F_, W, Q, CE, C, B, max_hist, seed, L, LA = [int(x) for x in g["meta"]]
+    params = make_naml_params(V, E, F_, W, Q, CE, C, seed=seed)
+    assert np.allclose(np.array([float(v.double().sum()) for v in params.values()]), g["param_checksum"], rtol=1e-9)
+    batch = {"batch_hist": torch.from_numpy(g["batch_hist"]), "batch_cand": torch.from_numpy(g["batch_cand"]),
+             "labels": torch.from_numpy(g["labels"]), "x_hist": {}, "x_cand": {},
+             "user_ids": torch.arange(B) + 7, "user_idx": torch.arange(B)}
+    for side in ("hist", "cand"):
+        n = g[f"{side}_title"].shape[0]
+        for attr in ("title", "abstract", "category"):
+            batch["x_" + side][attr] = torch.from_numpy(g[f"{side}_{attr}"])
+        batch["x_" + side]["sentiment"] = torch.ones(n, dtype=torch.long)
+        batch["x_" + side]["news_ids"] = torch.arange(n)
+    with tempfile.TemporaryDirectory() as tmp:
+        emb = os.path.join(tmp, "emb.npy")
+        np.save(emb, params["news_encoder.text_encoders.title.embedding_layer.weight"].numpy())
+        m = NAMLModule(
+            dataset_attributes=["title", "abstract", "category"], attributes2encode=["title", "abstract", "category"],
+            outputs=OUTPUTS, dual_loss_training=False, dual_loss_coef=None, loss="cross_entropy_loss", late_fusion=False,
+            temperature=None, use_plm=False, pretrained_embeddings_path=emb, plm_model=None, frozen_layers=None,
+            text_embed_dim=E, num_heads=15, num_filters=F_, window_size=W, query_dim=Q, categ_embed_dim=CE,
+            dropout_probability=0.2, top_k_list=[5, 10], num_categ_classes=C - 1, num_sent_classes=3, save_recs=False,
+            recs_fpath=None, optimizer=functools.partial(torch.optim.Adam, lr=1e-4), scheduler=None)
+    full = dict(params)
+    for k in list(params):
+        if ".text_encoders.title." in k:
+            full[k.replace(".title.", ".abstract.")] = params[k]
+    res = m.load_state_dict(full, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    m.eval()
+    scores = m(batch)
+    out = m.model_step(batch)
+    assert rel(scores, torch.from_numpy(g["scores"])) < 1e-6 and rel(out[0], torch.from_numpy(g["loss"])) < 1e-6
+    np.savez_compressed(os.path.join(GOLD, "naml_module_ref.npz"), source=np.array(name), scores=scores.detach().numpy(),
+                        loss=out[0].detach().numpy(), preds=out[1].detach().numpy(), targets=out[2].numpy(),
+                        cand_news_size=out[3].numpy(), hist_news_size=out[4].numpy())
+    print(f"[naml_module_ref] reference NAMLModule.forward/model_step reproduces {name}.npz: scores rel "
+          f"{rel(scores, torch.from_numpy(g['scores'])):.1e}, loss rel {rel(out[0], torch.from_numpy(g['loss'])):.1e}")
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     mint("nrms_module_ref", V=500, B=6, max_hist=9, seed=31, late_fusion=False)
     mint("nrms_module_ref_late_fusion", V=400, B=5, max_hist=7, seed=32, late_fusion=True)
+    naml_check()

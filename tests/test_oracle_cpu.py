@@ -274,3 +274,17 @@ def test_oracle_matches_reference_nrms_module_golden(name):
     assert torch.equal(out["hist_sentiments"], batch["x_hist"]["sentiment"])
     assert torch.equal(out["user_ids"], batch["user_ids"]) and torch.equal(out["cand_news_ids"], batch["x_cand"]["news_ids"])
     assert bool((ref["scores"][~mask] == 0).all())                          # padded slots score exactly 0.0
+
+
+def test_naml_fixture_is_what_the_reference_naml_module_returns():
+    """naml_module_ref.npz = outputs of the reference's OWN NAMLModule.forward / model_step (naml_module.py:261-286 and
+    model_step; oracle/make_module_golden.py) on the inputs of naml_mind.npz: the fixture the NAML parity tests use
+    (minted from the reference's component modules + restated glue) must agree with it."""
+    r = dict(np.load(os.path.join(GOLD, "naml_module_ref.npz")))
+    g = dict(np.load(os.path.join(GOLD, str(r["source"]) + ".npz")))
+    assert r["scores"].shape == g["scores"].shape and rel_err(r["scores"], g["scores"]) < 1e-6
+    assert rel_err(r["loss"], g["loss"]) < 1e-6
+    sizes = np.bincount(g["batch_cand"])
+    mask = np.arange(r["scores"].shape[1])[None, :] < sizes[:, None]
+    assert np.array_equal(r["preds"], r["scores"][mask]) and np.array_equal(r["targets"], g["labels"])
+    assert np.array_equal(r["cand_news_size"], sizes) and np.array_equal(r["hist_news_size"], np.bincount(g["batch_hist"]))
