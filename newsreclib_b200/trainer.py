@@ -159,6 +159,7 @@ class NRMSTrainer:
         self.precision, self.late_fusion, self.seed = precision, late_fusion, seed
         self.step_count = 0
         self.exchange_epoch = 0
+        self.exchange_ctas = int(os.environ.get("NRL_EXCHANGE_CTAS", "0"))  # grid of the fused exchange; 0 = 4 per SM
         self.ws: Optional[torch.Tensor] = None
         self.exchange = GradExchange(process_group)
         self.world = self.exchange.world
@@ -188,7 +189,7 @@ class NRMSTrainer:
             self.exchange_epoch += 1  # barrier epoch: never reset, also when step_count is
             exchange_adam_step(self.peer_block.peer_set, self.m, self.v, self.flat.numel(), self.step_count,
                                lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, grad_scale=scale,
-                               epoch=self.exchange_epoch)
+                               epoch=self.exchange_epoch, max_ctas=self.exchange_ctas)
             return
         # Adam on chunk i overlaps the all-reduce of chunks i+1.. (one chunk = everything when world == 1)
         for sl, _ in self.exchange.all_reduce_chunks(self.grad):
