@@ -132,7 +132,7 @@ def rel(a, b):
 
 def mint(name, V, B, max_hist, seed, late_fusion):
     params = make_nrms_params(V, seed=seed)
-    batch = make_batch(B, V, hist="ragged", cand="train" if not late_fusion else "eval", seed=seed, max_hist=max_hist)
+    batch = make_batch(B, V, hist="ragged", cand="train", seed=seed, max_hist=max_hist)
     with tempfile.TemporaryDirectory() as tmp:
         m = build_reference(params, late_fusion, tmp)
     scores = m(batch)                                   # NRMSModule.forward, nrms_module.py:230-255
