@@ -296,8 +296,8 @@ def make_trainer(NRMSTrainer, params, dev, prec, world, mode):
         why = f"probe failed on some rank (here: status {status})"
     if mode == "peer":
         raise SystemExit(f"--exchange peer: {why or 'a peer rank failed'}")
+    dist.barrier()  # every rank, whether or not its own construction succeeded
     if tr is not None and tr.peer_block is not None:
-        dist.barrier()
         tr.peer_block.close()
     return NRMSTrainer(params, H, device=dev, dropout_p=DROPOUT, precision=prec, exchange="nccl"), \
         f"nccl all-reduce + dense Adam (peer exchange unavailable: {why or 'a peer rank failed'})"

@@ -45,8 +45,15 @@ class PeerBlock:
     """One rank's peer-mapped block: ``[ params n f32 | grads n f32 | flag block ]`` and the same
     blocks of all peers opened through their IPC handles."""
 
-    def __init__(self, n: int, device: torch.device, process_group=None) -> None:
-        lib = _lib.load()
+    # two seams for the world_size-2 gloo tests of the construction protocol (tests/test_dist_cpu.py)
+    def _device_ctx(self):
+        return torch.cuda.device(self.device)
+
+    def _alias(self, ptr: int, nelem: int) -> torch.Tensor:
+        return torch.as_tensor(_DevMem(ptr, nelem, "<f4"), device=self.device)
+
+    def __init__(self, n: int, device: torch.device, process_group=None, lib=None) -> None:
+        lib = lib or _lib.load()
         dist = torch.distributed
         on = dist.is_available() and dist.is_initialized()
         self.world = dist.get_world_size(process_group) if on else 1
@@ -60,26 +67,45 @@ class PeerBlock:
         self._flag_off = 8 * n
         nbytes = 8 * n + _lib.FLAG_BYTES
         base, handle = C.c_void_p(), C.create_string_buffer(_lib.IPC_HANDLE_BYTES)
-        with torch.cuda.device(self.device):
-            _lib.check(lib.nrl_peer_alloc(nbytes, C.byref(base), handle), "nrl_peer_alloc")
-        self.base = int(base.value)
-        self.flat = torch.as_tensor(_DevMem(self.base, n, "<f4"), device=self.device)
-        self.grad = torch.as_tensor(_DevMem(self.base + 4 * n, n, "<f4"), device=self.device)
-        self._opened: List[int] = []
+        self.base, self._opened = 0, []
+        # A rank that fails (no peer access, IPC not permitted, out of memory) must not leave the others waiting in a
+        # collective: every rank goes through the same two object all-gathers, then all raise or none does.
+        err: Optional[str] = None
+        try:
+            with self._device_ctx():
+                _lib.check(lib.nrl_peer_alloc(nbytes, C.byref(base), handle), "nrl_peer_alloc")
+            self.base = int(base.value)
+        except Exception as e:  # noqa: BLE001
+            err = f"rank {self.rank}: {e}"
         bases = [0] * self.world
         bases[self.rank] = self.base
         if self.world > 1:
             handles: List[Optional[bytes]] = [None] * self.world
-            dist.all_gather_object(handles, handle.raw, group=process_group)
-            with torch.cuda.device(self.device):
-                for r, h in enumerate(handles):
-                    if r == self.rank:
-                        continue
-                    ptr = C.c_void_p()
-                    _lib.check(lib.nrl_peer_open(h, C.byref(ptr)), f"nrl_peer_open(rank {r})")
-                    bases[r] = int(ptr.value)
-                    self._opened.append(bases[r])
+            dist.all_gather_object(handles, handle.raw if err is None else None, group=process_group)
+            if err is None and all(h is not None for h in handles):
+                try:
+                    with self._device_ctx():
+                        for r, h in enumerate(handles):
+                            if r == self.rank:
+                                continue
+                            ptr = C.c_void_p()
+                            _lib.check(lib.nrl_peer_open(h, C.byref(ptr)), f"nrl_peer_open(rank {r})")
+                            bases[r] = int(ptr.value)
+                            self._opened.append(bases[r])
+                except Exception as e:  # noqa: BLE001
+                    err = f"rank {self.rank}: {e}"
+            errs: List[Optional[str]] = [None] * self.world
+            dist.all_gather_object(errs, err, group=process_group)
+            failed = [e for e in errs if e is not None] or \
+                     ([f"rank {r}: allocation failed" for r, h in enumerate(handles) if h is None])
+            if failed:
+                self.close()
+                raise RuntimeError("peer exchange unavailable: " + "; ".join(failed))
             dist.barrier(group=process_group)  # every block is zeroed and mapped before anyone signals
+        elif err is not None:
+            raise RuntimeError("peer exchange unavailable: " + err)
+        self.flat = self._alias(self.base, n)
+        self.grad = self._alias(self.base + 4 * n, n)
         self.peer_set = peer_set(self.world, self.rank, [b for b in bases], [b + 4 * n for b in bases],
                                  [b + self._flag_off for b in bases])
 
@@ -97,15 +123,15 @@ class PeerBlock:
 
     def close(self) -> None:
         """Unmap the peers' blocks and free the local one (call on every rank, after a barrier)."""
-        if self.base == 0:
-            return
-        with torch.cuda.device(self.device):
-            torch.cuda.synchronize(self.device)
+        with self._device_ctx():
+            if (self.base or self._opened) and self.device.type == "cuda":
+                torch.cuda.synchronize(self.device)
             for ptr in self._opened:
                 self._lib.nrl_peer_close(ptr)
             self._opened = []
             self.flat = self.grad = None
-            self._lib.nrl_peer_free(self.base)
+            if self.base:
+                self._lib.nrl_peer_free(self.base)
         self.base = 0
 
 

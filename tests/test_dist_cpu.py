@@ -167,3 +167,89 @@ def test_slice_ownership_partitions_the_flat_buffer():
             assert max(sizes) - min(s for s in sizes if s) <= 4 * ((n // 4 + world - 1) // world)  # at most one granule row
     with pytest.raises(ValueError):
         slice_bounds(10, 2, 0)
+
+
+class _FakeLib:
+    """Stands in for the C ABI's peer-memory calls: hands out fake base addresses, optionally fails one call."""
+
+    def __init__(self, rank, fail_alloc_on=None, fail_open_on=None):
+        self.rank, self.fail_alloc_on, self.fail_open_on = rank, fail_alloc_on, fail_open_on
+        self.closed, self.freed = [], []
+
+    def nrl_peer_alloc(self, nbytes, base_ref, handle):
+        if self.rank == self.fail_alloc_on:
+            return -3
+        base_ref._obj.value = 0x10000000 * (self.rank + 1)
+        handle.raw = bytes([self.rank + 1]) * 64
+        return 0
+
+    def nrl_peer_open(self, handle, ptr_ref):
+        if self.rank == self.fail_open_on:
+            return -3
+        ptr_ref._obj.value = 0x10000000 * handle[0] + 0x1000        # "mapped" address of the exporting rank's block
+        return 0
+
+    def nrl_peer_close(self, ptr):
+        self.closed.append(ptr)
+        return 0
+
+    def nrl_peer_free(self, ptr):
+        self.freed.append(ptr)
+        return 0
+
+
+def _peer_block_worker(rank, world, port, out, fail_alloc_on, fail_open_on):
+    import contextlib
+    from newsreclib_b200.exchange import PeerBlock
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class HostPeerBlock(PeerBlock):          # the two seams: no CUDA device context, no aliasing of fake addresses
+        def _device_ctx(self):
+            return contextlib.nullcontext()
+
+        def _alias(self, ptr, nelem):
+            return torch.zeros(nelem)
+
+    lib = _FakeLib(rank, fail_alloc_on, fail_open_on)
+    n = 64
+    try:
+        pb = HostPeerBlock(n, torch.device("cpu"), lib=lib)
+        ps = pb.peer_set
+        out[rank] = ("ok", [int(ps.params[r] or 0) for r in range(world)], [int(ps.grads[r] or 0) for r in range(world)],
+                     [int(ps.flags[r] or 0) for r in range(world)], int(ps.world), int(ps.rank))
+        dist.barrier()
+        pb.close()
+        assert lib.freed == [0x10000000 * (rank + 1)] and len(lib.closed) == world - 1
+    except RuntimeError as e:
+        out[rank] = ("error", str(e), list(lib.freed), list(lib.closed))
+    dist.barrier()                           # nobody is left behind in a collective, whichever rank failed
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fail_alloc_on,fail_open_on", [(None, None), (1, None), (None, 0)])
+def test_peer_block_construction_protocol(fail_alloc_on, fail_open_on):
+    """PeerBlock's handle exchange on two gloo ranks with the C ABI's peer calls faked: on success every rank holds
+    every rank's block addresses in the layout [params | grads | flags]; when ONE rank cannot allocate or map, ALL ranks
+    raise the same error (no rank is left waiting in a collective) and what was allocated / mapped is released."""
+    world, port = 2, _free_port()
+    out = mp.Manager().dict()
+    mp.spawn(_peer_block_worker, args=(world, port, out, fail_alloc_on, fail_open_on), nprocs=world, join=True)
+    n = 64
+    if fail_alloc_on is None and fail_open_on is None:
+        for rank in range(world):
+            status, params, grads, flags, w, r = out[rank]
+            assert status == "ok" and (w, r) == (world, rank)
+            for peer in range(world):
+                base = 0x10000000 * (peer + 1) + (0 if peer == rank else 0x1000)
+                assert (params[peer], grads[peer], flags[peer]) == (base, base + 4 * n, base + 8 * n)
+    else:
+        bad = fail_alloc_on if fail_alloc_on is not None else fail_open_on
+        for rank in range(world):
+            status, msg, freed, closed = out[rank]
+            assert status == "error" and "peer exchange unavailable" in msg and f"rank {bad}" in msg
+            if fail_alloc_on is None:
+                assert freed == [0x10000000 * (rank + 1)]                   # own block released on every rank
+                assert len(closed) == (0 if rank == bad else world - 1)      # the healthy rank unmaps what it mapped
+            else:
+                assert freed == ([] if rank == bad else [0x10000000 * (rank + 1)]) and closed == []
