@@ -288,3 +288,31 @@ def test_naml_fixture_is_what_the_reference_naml_module_returns():
     mask = np.arange(r["scores"].shape[1])[None, :] < sizes[:, None]
     assert np.array_equal(r["preds"], r["scores"][mask]) and np.array_equal(r["targets"], g["labels"])
     assert np.array_equal(r["cand_news_size"], sizes) and np.array_equal(r["hist_news_size"], np.bincount(g["batch_hist"]))
+
+
+def test_to_dense_batch_property_against_naive_loop():
+    """PyG is absent (parity unpinned for this one third-party function), so the restatement is checked against the
+    definition itself: item i of segment b lands at [b, rank of i within b], everything else is zero / False; segments
+    may be empty, x may be 1-D (labels, nrms_module.py:277) or carry trailing dims."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.lists(st.integers(0, 6), min_size=1, max_size=9), st.sampled_from([(), (3,), (2, 2)]))
+    def check(counts, trailing):
+        if sum(counts) == 0 or counts[-1] == 0:
+            counts = counts + [1]                      # B = batch.max() + 1: the last segment is never empty
+        batch = torch.repeat_interleave(torch.arange(len(counts)), torch.tensor(counts))
+        x = torch.arange(1, batch.numel() * int(np.prod(trailing, dtype=np.int64)) + 1, dtype=torch.float32)
+        x = x.reshape((batch.numel(),) + trailing)
+        dense, mask = O.to_dense_batch(x, batch)
+        B, M = len(counts), max(counts)
+        assert dense.shape == (B, M) + trailing and mask.shape == (B, M)
+        want, wmask, i = torch.zeros((B, M) + trailing), torch.zeros(B, M, dtype=torch.bool), 0
+        for b, c in enumerate(counts):
+            for j in range(c):
+                want[b, j], wmask[b, j] = x[i], True
+                i += 1
+        assert torch.equal(dense, want) and torch.equal(mask, wmask)
+        assert torch.equal(dense[mask], x)             # masked dense order == ragged order (what model_step relies on)
+
+    check()
