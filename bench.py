@@ -267,7 +267,7 @@ def make_trainer(NRMSTrainer, params, dev, prec, world, mode):
         return bool(t.item())
     why, tr = "", None
     try:
-        tr = NRMSTrainer(params, H, device=dev, dropout_p=DROPOUT, precision=prec, exchange="peer")
+        tr = NRMSTrainer(params, H, device=dev, dropout_p=DROPOUT, precision=prec, exchange="peer", exchange_timeout_s=5.0)
         ok = True
     except Exception as e:  # e.g. no peer access / IPC not permitted on this box
         ok, why = False, f"{type(e).__name__}: {e}"

@@ -124,11 +124,14 @@ class NRMSTrainer:
     def __init__(self, params: Dict[str, torch.Tensor], num_heads: int, *, device="cuda",
                  dropout_p: float = 0.2, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
                  precision: int = ops.PREC_BF16X3, late_fusion: bool = False, seed: int = 1234,
-                 process_group=None, exchange: Optional[str] = None) -> None:
+                 process_group=None, exchange: Optional[str] = None, exchange_timeout_s: float = 30.0) -> None:
         """``exchange``: how the ranks' gradients meet the optimizer when world_size > 1 --
         ``"nccl"`` (one NCCL all-reduce of the flat gradient buffer, then dense Adam on every rank) or
         ``"peer"`` (``nrl_exchange_adam_step``: reduce-scatter + sharded Adam + all-gather as one kernel
-        over NVLink peer memory, ``exchange.py``).  Default: ``$NRL_EXCHANGE`` or ``"nccl"``."""
+        over NVLink peer memory, ``exchange.py``).  Default: ``$NRL_EXCHANGE`` or ``"nccl"``.
+        ``exchange_timeout_s``: how long a rank's fused exchange kernel waits for a peer before it gives up (a dead
+        peer must not hang the GPU); raise it if one rank may legitimately stall for longer between two steps
+        (checkpointing on rank 0, a slow data loader)."""
         _lib.load()
         self.device = torch.device(device)
         self.keys = [TITLE + "embedding_layer.weight"] + [TITLE + k for k in ops.BLOCK_KEYS] + \
@@ -160,6 +163,7 @@ class NRMSTrainer:
         self.step_count = 0
         self.exchange_epoch = 0
         self.exchange_ctas = int(os.environ.get("NRL_EXCHANGE_CTAS", "0"))  # grid of the fused exchange; 0 = 4 per SM
+        self.exchange_timeout_s = float(exchange_timeout_s)
         self.ws: Optional[torch.Tensor] = None
         self.exchange = GradExchange(process_group)
         self.world = self.exchange.world
@@ -189,7 +193,7 @@ class NRMSTrainer:
             self.exchange_epoch += 1  # barrier epoch: never reset, also when step_count is
             exchange_adam_step(self.peer_block.peer_set, self.m, self.v, self.flat.numel(), self.step_count,
                                lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, grad_scale=scale,
-                               epoch=self.exchange_epoch, max_ctas=self.exchange_ctas)
+                               epoch=self.exchange_epoch, max_ctas=self.exchange_ctas, timeout_s=self.exchange_timeout_s)
             return
         # Adam on chunk i overlaps the all-reduce of chunks i+1.. (one chunk = everything when world == 1)
         for sl, _ in self.exchange.all_reduce_chunks(self.grad):
