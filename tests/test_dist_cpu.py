@@ -253,3 +253,52 @@ def test_peer_block_construction_protocol(fail_alloc_on, fail_open_on):
                 assert len(closed) == (0 if rank == bad else world - 1)      # the healthy rank unmaps what it mapped
             else:
                 assert freed == ([] if rank == bad else [0x10000000 * (rank + 1)]) and closed == []
+
+
+def _make_trainer_worker(rank, world, port, scenario, out):
+    """bench.make_trainer(--exchange auto) with a fake trainer class: which exchange do the ranks end up with when the
+    peer path is unavailable on ONE rank, times out in the probe on one rank, or leaves different replicas?"""
+    import bench
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class FakePeer:
+        def __init__(self, status):
+            self._status, self.closed = status, False
+
+        def status(self):
+            return self._status
+
+        def close(self):
+            self.closed = True
+
+    class FakeTrainer:
+        def __init__(self, params, H, device=None, dropout_p=0.0, precision=0, exchange="nccl", exchange_timeout_s=30.0):
+            self.mode = exchange
+            if exchange == "peer" and scenario == "ctor_fails_on_rank1" and rank == 1:
+                raise RuntimeError("peer exchange unavailable: rank 1: no IPC")
+            self.flat, self.m, self.v, self.step_count = torch.zeros(16), torch.ones(16), torch.ones(16), 0
+            self.peer_block = None
+            if exchange == "peer":
+                self.peer_block = FakePeer(1 if (scenario == "probe_times_out_on_rank0" and rank == 0) else 0)
+
+        def train_step(self, b, B, Hmax, Cmax):
+            self.step_count += 1
+            self.flat += 2.0 if (scenario == "replicas_differ" and rank == 1) else 1.0
+
+    tr, used = bench.make_trainer(FakeTrainer, {}, torch.device("cpu"), 0, world, "auto")
+    out[rank] = (tr.mode, used)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("scenario", ["ctor_fails_on_rank1", "probe_times_out_on_rank0", "replicas_differ"])
+def test_bench_auto_exchange_falls_back_on_every_rank(scenario):
+    """N > 1, --exchange auto: if the fused peer exchange cannot be set up or fails its probe on ANY rank, EVERY rank
+    must end up on the NCCL exchange (and say why) -- a split decision would deadlock the first step."""
+    world, port = 2, _free_port()
+    out = mp.Manager().dict()
+    mp.spawn(_make_trainer_worker, args=(world, port, scenario, out), nprocs=world, join=True)
+    for rank in range(world):
+        mode, used = out[rank]
+        assert mode == "nccl" and used.startswith("nccl all-reduce + dense Adam (peer exchange unavailable")
