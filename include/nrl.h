@@ -10,6 +10,8 @@
  * Conventions
  *   - plain pointers + sizes, no torch types; all pointers are DEVICE pointers unless the
  *     name ends in _host; caller owns every buffer, nothing is allocated or freed here
+ *     (one exception: nrl_peer_alloc / nrl_peer_free, because peer-mapped memory must come
+ *     from cudaMalloc -- see the gradient-exchange section)
  *   - all launches go to the cudaStream_t passed as `stream` (void* to keep this header C)
  *   - return 0 on success, negative nrl_status on failure; nrl_last_error() gives the text
  *   - float = fp32, ids / segment ids = int64 (what the reference collate emits,
