@@ -11,7 +11,7 @@ Pinned: ``oracle/make_collate_golden.py`` loads the reference's ``rec_dataset.py
 its own ``RecommendationDatasetTest`` / ``RecommendationDatasetTrain`` + ``DatasetCollate`` on a synthetic news
 table, asserts that this restatement reproduces every tensor bit for bit, and stores inputs and reference outputs
 in ``tests/golden/collate_ref.npz`` (checked by ``tests/test_oracle_cpu.py`` and, for the device-side collate,
-``tests/test_gpu_pipeline.py``).  The reference's own tests hold no vectors for this path."""
+``tests/test_gpu_reference_goldens.py``).  The reference's own tests hold no vectors for this path."""
 from typing import Dict, List, Sequence
 
 import numpy as np

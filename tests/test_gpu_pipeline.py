@@ -96,24 +96,3 @@ def test_cached_news_vectors_eval_path_matches_forward():
     mask = torch.arange(got.shape[1], device="cuda")[None, :] < sizes.cuda()[:, None]
     met = ranking_metrics(got[mask], b["labels"], sizes.cuda(), [5, 10])
     assert 0.0 <= float(met["auc"]) <= 1.0 and 0.0 < float(met["mrr"]) <= 1.0
-
-
-@pytest.mark.parametrize("split", ["test", "train"])
-def test_device_collate_matches_reference_collate_golden(split):
-    """DeviceCollate against the output of the reference's OWN DatasetCollate (tests/golden/collate_ref.npz, minted by
-    oracle/make_collate_golden.py): every tensor of the RecommendationBatch bit for bit, dtype included."""
-    from helpers import load_collate_golden
-    from newsreclib_b200.data.components.device_collate import DeviceCollate, DeviceNewsTable
-    news, splits, (lt, la) = load_collate_golden()
-    samples, ref = splits[split]
-    table = DeviceNewsTable.from_token_lists(
-        news["nid"], news["tokenized_title"], news["category_class"], news["subcategory_class"], lt,
-        news["tokenized_abstract"], la, news["sentiment_class"], news["sentiment_score"])
-    got = DeviceCollate(table)(samples)
-    for k, v in ref.items():
-        if isinstance(v, dict):
-            assert set(got[k]) == set(v)
-            for c, t in v.items():
-                assert got[k][c].dtype == t.dtype and torch.equal(got[k][c].cpu(), t), (k, c)
-        else:
-            assert got[k].dtype == v.dtype and torch.equal(got[k].cpu(), v), k
