@@ -97,16 +97,65 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------
-# CPU arm: the oracle (a port of the reference's torch modules) on the host cores
+# CPU arm: the UNMODIFIED reference on the host cores (baseline/_ref, installed by baseline/install_ref.py);
+# the oracle port only if that install is absent
 # ----------------------------------------------------------------------------------------
-def cpu_train_steps(batch_size: int, steps: int, warmup: int, budget_s: float):
-    """Reference CPU path: oracle forward in train mode (fresh Bernoulli masks per step, as
-    nn.Dropout draws them), CE, autograd backward, torch.optim.Adam(lr=1e-4) over all
-    parameters incl. the dense embedding table (configs/model/nrms.yaml:49-52)."""
+def run_config(world: int, batch: int):
+    """The `config` object of the JSON line -- the same in both arms (the workload, not the implementation)."""
+    return {"workload": WORKLOAD, "global_batch": world * batch, "batch_per_gpu": batch, "parallelism": f"dp{world}",
+            "l2": "inputs rotate over 4 distinct batches; each step streams ~2 GB of activations "
+                  "(>> 126 MB L2), so no step starts with a warm L2"}
+
+
+def _reference_stepper(threads: int):
+    """One train step of the reference's own code: `NRMSModule.model_step` (nrms_module.py:260-362: forward :230-255,
+    to_dense_batch, CrossEntropyLoss, the per-row output collection) -> `loss.backward()` -> the optimizer built by the
+    reference's `configure_optimizers` (abstract_recommender.py:89-108) from `torch.optim.Adam(lr=1e-4)`
+    (configs/model/nrms.yaml:49-52), train mode (dropout 0.2), fp32.  The module files are loaded unmodified from
+    baseline/_ref under the stand-ins of oracle/ref_standins.py (lightning / torchmetrics / torch_geometric are absent;
+    `to_dense_batch` is the restated PyG 2.3.0 function)."""
+    import functools
+    import tempfile
+    import numpy as np
+    from oracle import ref_standins
+
+    ref_standins.install(ref_standins.BASELINE_REF if os.path.isdir(os.path.join(ref_standins.BASELINE_REF, "newsreclib"))
+                         else None)
+    from newsreclib.models.general_rec.nrms_module import NRMSModule
+
+    params = make_nrms_params(VOCAB, E, H, Q, seed=1234)
+    outputs = {k: ["preds", "targets", "cand_news_size"] for k in ("train", "val", "test")}
+    with tempfile.TemporaryDirectory() as tmp:
+        emb = os.path.join(tmp, "emb.npy")
+        np.save(emb, params["news_encoder.text_encoders.title.embedding_layer.weight"].numpy())
+        m = NRMSModule(
+            dataset_attributes=["title", "category"], attributes2encode=["title"], outputs=outputs,
+            dual_loss_training=False, dual_loss_coef=None, loss="cross_entropy_loss", late_fusion=False,
+            temperature=None, use_plm=False, pretrained_embeddings_path=emb, plm_model=None, frozen_layers=None,
+            embed_dim=E, num_heads=H, query_dim=Q, dropout_probability=DROPOUT, top_k_list=[5, 10],
+            num_categ_classes=18, num_sent_classes=3, save_recs=False, recs_fpath=None,
+            optimizer=functools.partial(torch.optim.Adam, lr=1e-4), scheduler=None)
+    res = m.load_state_dict({k: v for k, v in params.items() if k in m.state_dict()}, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    m.train()
+    opt = m.configure_optimizers()["optimizer"]
+
+    def one(bs, seed):
+        batch = make_batch(bs, VOCAB, hist="fixed", max_hist=HIST, cand="train", seed=seed, max_title_len=L)
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        loss = m.model_step(batch)[0]
+        loss.backward()
+        opt.step()
+        return time.perf_counter() - t0
+    return one, "reference"
+
+
+def _port_stepper(threads: int):
+    """Fallback when baseline/_ref is absent: the oracle port of the same modules (oracle/nrms_oracle.py), train mode
+    with fresh Bernoulli masks, CE, autograd backward, torch.optim.Adam over all parameters incl. the dense table."""
     from oracle import nrms_oracle as O
 
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
     params = {k: v.clone().requires_grad_(True) for k, v in make_nrms_params(VOCAB, E, H, Q, seed=1234).items()}
     opt = torch.optim.Adam(list(params.values()), lr=1e-4)
 
@@ -124,7 +173,20 @@ def cpu_train_steps(batch_size: int, steps: int, warmup: int, budget_s: float):
         params["news_encoder.text_encoders.title.embedding_layer.weight"].grad[0] = 0  # padding_idx
         opt.step()
         return time.perf_counter() - t0
+    return one, "port"
 
+
+def cpu_train_steps(batch_size: int, steps: int, warmup: int, budget_s: float):
+    """The reference's CPU path on all host threads; returns (impressions per step, timed step seconds, threads,
+    kind).  The sample is bounded: if `steps + warmup` full batches would exceed `budget_s`, every step processes
+    fewer impressions of the same shape."""
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    try:
+        one, kind = _reference_stepper(threads)
+    except ImportError as e:
+        print(f"[bench] reference install unavailable ({e}); timing the oracle port instead", file=sys.stderr)
+        one, kind = _port_stepper(threads)
     bs = batch_size
     t_first = one(bs, 0)
     total = steps + warmup
@@ -132,22 +194,28 @@ def cpu_train_steps(batch_size: int, steps: int, warmup: int, budget_s: float):
         bs = max(4, int(batch_size * budget_s / (t_first * total)))
     times = [one(bs, 1 + i) for i in range(total)]
     timed = times[warmup:] if len(times) > warmup else times
-    return bs, timed, threads
+    return bs, timed, threads, kind
 
 
-def run_reference_arm(args, rank: int):
+CPU_KIND_TEXT = {"reference": "the reference's own NRMSModule.model_step + backward + its configure_optimizers Adam "
+                              "(unmodified files from baseline/_ref)",
+                 "port": "oracle port of the reference modules"}
+
+
+def run_reference_arm(args, rank: int, world: int):
     if rank != 0:
         return
-    bs, timed, threads = cpu_train_steps(args.batch, args.steps, args.warmup, budget_s=150.0)
+    bs, timed, threads, kind = cpu_train_steps(args.batch, args.steps, args.warmup, budget_s=150.0)
     ms = 1e3 * sum(timed) / len(timed)
     val = bs / (ms / 1e3)
-    sample = f"{len(timed)} train steps of {bs} impressions (same shape as the GPU workload), fp32, {threads} threads"
+    sample = (f"{len(timed)} train steps of {bs} impressions (same shape as the GPU workload) on the host CPU, fp32, "
+              f"{threads} threads: {CPU_KIND_TEXT[kind]}")
     print(json.dumps({
         "impl": "reference", "metric": "impressions/sec", "value": val, "unit": "impressions/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_step": bs, "host": "CPU oracle port of the reference modules"},
-        "cpu_baseline": {"value": val, "unit": "impressions/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": run_config(world, args.batch),
+        "cpu_baseline": {"value": val, "unit": "impressions/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "impressions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }), flush=True)
@@ -334,7 +402,7 @@ def main():
         os.dup2(2, 1)
         sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if args.impl == "reference":
-        run_reference_arm(args, rank)
+        run_reference_arm(args, rank, world)
         return
 
     if args.model == "naml":
@@ -512,10 +580,11 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        bs, timed, threads = cpu_train_steps(B, 4, 1, budget_s=25.0)
+        bs, timed, threads, kind = cpu_train_steps(B, 6, 1, budget_s=25.0)
         cms = 1e3 * sum(timed) / len(timed)
-        cpu = {"value": bs / (cms / 1e3), "unit": "impressions/s", "cores": threads, "kind": "port",
-               "sample": f"{len(timed)} train steps of {bs} impressions on the host CPU (oracle port of the reference modules, fp32)",
+        cpu = {"value": bs / (cms / 1e3), "unit": "impressions/s", "cores": threads, "kind": kind,
+               "sample": f"{len(timed)} train steps of {bs} impressions on the host CPU, fp32, {threads} threads: "
+                         f"{CPU_KIND_TEXT[kind]}",
                "ms_per_step": cms}
 
     if trainer.peer_block is not None and trainer.peer_block.status() != 0:
@@ -527,11 +596,8 @@ def main():
             "scaling": "weak", "vs_baseline": None,
             "dtype": "fp32 via bf16x3 split on tcgen05 (fp32 accumulate)" if prec == ops.PREC_BF16X3 else "bf16 (fp32 accumulate)",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": f"dp{world}",
-                       "exchange": exchange_used,
-                       "l2": "inputs rotate over 4 distinct batches; each step streams ~2 GB of activations "
-                             "(>> 126 MB L2), so no step starts with a warm L2",
-                       "precision": args.precision},
+            "config": run_config(world, B),
+            "impl_detail": {"exchange": exchange_used, "precision": args.precision},
             "e2e": {"value": e2e_val, "unit": "impressions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e},
             "eval_forward": {"value": world * B / (ms_eval / 1e3), "unit": "impressions/s", "ms_per_step": ms_eval},

@@ -33,6 +33,7 @@ from newsreclib.data.components.rec_dataset import (  # noqa: E402
     DatasetCollate, RecommendationDatasetTest, RecommendationDatasetTrain)
 
 from oracle import collate_oracle as CO  # noqa: E402
+from oracle._golden_io import save as golden_save  # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden")
 L_TITLE, L_ABS = 30, 50
@@ -119,8 +120,8 @@ def main():
         print(f"[{split}] reference DatasetCollate == collate_oracle.collate on {len(items)} impressions, "
               f"{len(out[f'{split}.hist_rows'])} history rows, {len(out[f'{split}.cand_rows'])} candidates")
     path = os.path.join(GOLD, "collate_ref.npz")
-    np.savez_compressed(path, **out)
-    print("wrote", path, os.path.getsize(path), "bytes")
+    golden_save(path, **out)
+    print("wrote" if "--check" not in sys.argv else "checked", path, os.path.getsize(path), "bytes")
 
 
 if __name__ == "__main__":

@@ -11,7 +11,8 @@ Runs ONLY in the build container (it imports the unmodified reference from
 4. asserts agreement (fp32 noise floor) and writes inputs/outputs/gradients to
    ``tests/golden/*.npz``.
 
-Usage:  python oracle/make_golden.py
+Usage:  python oracle/make_golden.py            (mint)
+        python oracle/make_golden.py --check    (re-run the recipe and compare with the committed fixtures)
 """
 from __future__ import annotations
 
@@ -34,6 +35,7 @@ from newsreclib.models.components.layers.click_predictor import DotProduct  # no
 
 from newsreclib_b200.synthetic import make_batch, make_nrms_params  # noqa: E402
 from oracle import nrms_oracle as O  # noqa: E402
+from oracle._golden_io import save as golden_save  # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden")
 
@@ -97,9 +99,19 @@ def nrms_case(name, E, H, Q, V, B, max_hist, hist, cand, seed, store_params, max
     for k in ("hist", "cand", "user", "scores", "loss"):
         r = rel(orc[k], ref[k]); worst = max(worst, r)
         assert r < 2e-5, (name, k, r)
+    # arbiter for the gradients: the same oracle in float64.  A few gradients (the additive-attention bias:
+    # sum_t ds_t = 0 per softmax group) cancel to ~1e-5 of their terms, so two fp32 evaluations -- the reference's
+    # and the restatement's -- agree only to their own rounding noise there (which also depends on the thread count).
+    g64 = oracle_nrms({k: v.double() for k, v in params.items()},
+                      dict(batch, labels=batch["labels"].double()), H)["grads"]
     for k, g in ref["grads"].items():
-        r = rel(orc["grads"][k], g); worst = max(worst, r)
-        assert r < 2e-4, (name, "grad", k, r)
+        if float(g64[k].abs().max()) < 1e-9:
+            continue  # mathematically zero (the key bias of in_proj_bias): both fp32 runs hold rounding noise
+        ref_noise = rel(g, g64[k].float())
+        assert ref_noise <= 2e-3, (name, "grad", k, ref_noise)              # the reference agrees with the fp64 oracle
+        r = rel(orc["grads"][k], g64[k].float())
+        assert r <= max(2e-5, 4.0 * ref_noise), (name, "grad", k, r, ref_noise)
+        worst = max(worst, rel(orc["grads"][k], g))
     assert float(ref["grads"]["news_encoder.text_encoders.title.embedding_layer.weight"][0].abs().max()) == 0.0
     out = {
         "meta": np.array([E, H, Q, V, B, max_hist, seed, max_title_len], dtype=np.int64),
@@ -122,7 +134,7 @@ def nrms_case(name, E, H, Q, V, B, max_hist, hist, cand, seed, store_params, max
     if store_params:
         for k, v in params.items():
             out["param/" + k] = v.numpy()
-    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    golden_save(os.path.join(GOLD, name + ".npz"), **out)
     print(f"{name}: oracle vs reference max rel {worst:.2e}; loss {float(ref['loss']):.6f}; "
           f"N_h={batch['batch_hist'].numel()} N_c={batch['batch_cand'].numel()}")
 
@@ -142,7 +154,7 @@ def coupling_case():
     assert rel(o, u) < 1e-5 and rel(o2, u2) < 1e-5
     delta = float((u2[0] - u[0]).abs().max())
     assert delta > 1e-3
-    np.savez_compressed(os.path.join(GOLD, "user_coupling.npz"), h=h.numpy(), h2=h2.numpy(),
+    golden_save(os.path.join(GOLD, "user_coupling.npz"), h=h.numpy(), h2=h2.numpy(),
                         u=u.numpy(), u2=u2.numpy(), meta=np.array([E, H, Q]),
                         **{"param/" + k: v.numpy() for k, v in p.items()})
     print(f"user_coupling: delta on user 0 = {delta:.4f}")
@@ -187,7 +199,7 @@ def naml_case():
         up = {k: v for k, v in user.state_dict().items()}
         r2 = rel(O.naml_user_encoder(h, up), uref)
         assert r2 < 2e-5, r2
-    np.savez_compressed(
+    golden_save(
         os.path.join(GOLD, "naml_news.npz"), title=x["title"].numpy(), abstract=x["abstract"].numpy(),
         category=x["category"].numpy(), news_vec=vec.numpy(), user_in=h.numpy(), user_vec=uref.numpy(),
         meta=np.array([V, E, F_, W, Q, C, CE]),
@@ -266,7 +278,7 @@ def naml_step_case(name, V, E, F_, W, Q, CE, B, max_hist, seed, store_params, L=
     if store_params:
         for k, v in params.items():
             out["param/" + k] = v.numpy()
-    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    golden_save(os.path.join(GOLD, name + ".npz"), **out)
     print(f"{name}: oracle vs reference max rel {worst:.2e}; loss {float(loss):.6f}; "
           f"N_h={batch['batch_hist'].numel()} N_c={batch['batch_cand'].numel()}")
 
@@ -317,7 +329,7 @@ def plm_head_case(name, hidden, tf_heads, head_heads, Q, N, T, seed):
         assert r < 5e-4, (k, r)
     r = rel(xo.grad, x.grad); worst = max(worst, r)
     assert r < 5e-4, r
-    np.savez_compressed(
+    golden_save(
         os.path.join(GOLD, name + ".npz"), meta=np.array([hidden, head_heads, Q, N, T]), x=states.numpy(),
         w=w.numpy(), out=out.detach().numpy(), dx=x.grad.numpy(), oracle_vs_reference_maxrel=np.array(worst),
         **{"param/" + k: v.numpy() for k, v in head.items()}, **{"grad/" + k: v.numpy() for k, v in rgrads.items()})
@@ -327,7 +339,7 @@ def plm_head_case(name, hidden, tf_heads, head_heads, Q, N, T, seed):
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(4)
-    only = set(sys.argv[1:])
+    only = set(a for a in sys.argv[1:] if not a.startswith("--"))
     if only:  # mint selected fixtures without touching the committed ones
         if "naml_tiny" in only:
             naml_step_case("naml_tiny", V=60, E=32, F_=48, W=3, Q=24, CE=20, B=3, max_hist=5, seed=5,

@@ -5,7 +5,7 @@ Runs ONLY in the build container (imports the unmodified reference from ``/root/
 ``newsreclib/models/general_rec/nrms_module.py`` needs ``lightning``, ``torchmetrics``, ``torch_geometric`` and (through
 ``newsreclib.models.components.losses``) ``pytorch_metric_learning``; none is installed and none takes part in the
 arithmetic of ``forward`` / ``model_step`` except ``torch_geometric.utils.to_dense_batch``.  The imports are satisfied
-with stand-ins:
+with stand-ins (``oracle/ref_standins.py``):
 
 * ``lightning.LightningModule`` -> ``torch.nn.Module`` + ``save_hyperparameters`` (constructor arguments -> ``self.hparams``)
   and a ``device`` property;
@@ -18,16 +18,14 @@ with stand-ins:
 11-tuple below come out of the reference's own ``NRMSModule.forward`` (``:230-255``) and ``model_step`` (``:260-362``).
 The script asserts that ``oracle/nrms_oracle.py`` reproduces them and stores batch, reference outputs and gradients.
 
-Usage:  python oracle/make_module_golden.py
+Usage:  python oracle/make_module_golden.py [--check]
 """
 from __future__ import annotations
 
 import functools
-import inspect
 import os
 import sys
 import tempfile
-import types
 
 import numpy as np
 import torch
@@ -37,66 +35,13 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, "/root/reference")
 
 from oracle import nrms_oracle as O  # noqa: E402
+from oracle._golden_io import save as golden_save  # noqa: E402
 
 
-# ------------------------------------------------------------------------------- stand-ins for absent packages
-class _HParams(dict):
-    __getattr__ = dict.__getitem__
+# stand-ins for the absent packages (shared with bench.py's reference arm): oracle/ref_standins.py
+from oracle import ref_standins  # noqa: E402
 
-
-class LightningModule(torch.nn.Module):
-    def save_hyperparameters(self, *args, **kwargs):
-        hp = _HParams()
-        frame = inspect.currentframe().f_back
-        while frame is not None:  # every __init__ of the class chain that is on the stack contributes its arguments
-            if frame.f_code.co_name == "__init__" and frame.f_locals.get("self") is self:
-                for k, v in frame.f_locals.items():
-                    if k not in ("self", "__class__", "args", "kwargs"):
-                        hp.setdefault(k, v)
-            frame = frame.f_back
-        self.hparams = hp
-
-    @property
-    def device(self):
-        return next(self.parameters()).device if any(True for _ in self.parameters()) else torch.device("cpu")
-
-    def log(self, *a, **k):
-        pass
-
-    def log_dict(self, *a, **k):
-        pass
-
-
-class _Inert(torch.nn.Module):
-    def __init__(self, *a, **k):
-        super().__init__()
-
-    def clone(self, prefix=None):
-        return _Inert()
-
-    def add_metrics(self, *a, **k):
-        pass
-
-    def reset(self):
-        pass
-
-
-def _module(name, **attrs):
-    m = types.ModuleType(name)
-    m.__dict__.update(attrs)
-    sys.modules[name] = m
-    return m
-
-
-_module("lightning", LightningModule=LightningModule)
-_module("torch_geometric")
-_module("torch_geometric.utils", to_dense_batch=O.to_dense_batch)
-_module("torchmetrics", MetricCollection=_Inert, MeanMetric=_Inert, MinMetric=_Inert)
-_module("torchmetrics.classification", AUROC=_Inert)
-_module("torchmetrics.retrieval", RetrievalMRR=_Inert, RetrievalNormalizedDCG=_Inert)
-_module("newsreclib.metrics.diversity", Diversity=_Inert)
-_module("newsreclib.metrics.personalization", Personalization=_Inert)
-_module("newsreclib.models.components.losses", SupConLoss=_Inert)
+ref_standins.install("/root/reference")
 
 from newsreclib.models.general_rec.nrms_module import NRMSModule  # noqa: E402  (the reference's own file)
 
@@ -180,9 +125,9 @@ def mint(name, V, B, max_hist, seed, late_fusion):
         rec["batch/" + k] = batch[k].numpy()
     rec["param_checksum"] = np.array([float(v.double().sum()) for v in params.values()])
     path = os.path.join(GOLD, name + ".npz")
-    np.savez_compressed(path, **rec)
+    golden_save(path, **rec)
     print(f"[{name}] reference NRMSModule.forward/model_step == oracle: scores rel {rel(o_scores, scores):.1e}, "
-          f"loss rel {rel(o_loss, loss):.1e}; wrote {os.path.getsize(path)} bytes")
+          f"loss rel {rel(o_loss, loss):.1e}; {os.path.getsize(path)} bytes")
 
 
 def naml_check(name="naml_mind"):
@@ -225,7 +170,7 @@ def naml_check(name="naml_mind"):
     scores = m(batch)
     out = m.model_step(batch)
     assert rel(scores, torch.from_numpy(g["scores"])) < 1e-6 and rel(out[0], torch.from_numpy(g["loss"])) < 1e-6
-    np.savez_compressed(os.path.join(GOLD, "naml_module_ref.npz"), source=np.array(name), scores=scores.detach().numpy(),
+    golden_save(os.path.join(GOLD, "naml_module_ref.npz"), source=np.array(name), scores=scores.detach().numpy(),
                         loss=out[0].detach().numpy(), preds=out[1].detach().numpy(), targets=out[2].numpy(),
                         cand_news_size=out[3].numpy(), hist_news_size=out[4].numpy())
     print(f"[naml_module_ref] reference NAMLModule.forward/model_step reproduces {name}.npz: scores rel "
