@@ -220,6 +220,30 @@ int nrl_adam_step(float* p, const float* g, float* m, float* v, long long n, flo
                   float beta1, float beta2, float eps, long long step, float grad_scale,
                   void* stream);
 
+/* Same step fused with optimizer.zero_grad(): every gradient element is overwritten with 0 once it has been
+ * consumed (the gradient buffers of this library accumulate, so they must be clean before the next backward
+ * pass; this saves the separate memset of the 87 MB flat gradient buffer). */
+int nrl_adam_step_zero_grad(float* p, float* g, float* m, float* v, long long n, float lr,
+                            float beta1, float beta2, float eps, long long step, float grad_scale,
+                            void* stream);
+
+/* ---- nn.Embedding.forward alone, encoders/news/text.py:215-217 (construction), :224 (call) --------
+ * ids [n] int64 -> out_f32 [n, E] (bit-exact copies of the table rows; row 0 is a real row, only its
+ * gradient is zeroed) and / or the bf16 hi / lo split planes out_hi / out_lo [n, Ep], Ep = round_up(E + 1, 16),
+ * with 1.0 in column E and zeros after (the A-operand layout of the in-projection GEMM).  Any output may be
+ * NULL (at least one of out_f32 / out_hi must be given). */
+int nrl_embedding_gather(const long long* ids, long long n, const float* table, long long V1, int E,
+                         float* out_f32, void* out_hi, void* out_lo, void* stream);
+
+/* ---- device-side input checks -----------------------------------------------------------------------
+ * nn.Embedding raises on an id outside the table and to_dense_batch assumes sorted segment ids in [0, B).
+ * The kernels here cannot raise: they never touch memory outside the caller's buffers (an offending id reads
+ * row 0 / is skipped), record the first violation in a sticky device word, and the host asks for it:
+ * synchronises `stream`, writes 0 or the code to *code_host (1 token id out of [0, V1), 2 bad segment ids,
+ * 3 a segment longer than Hmax / Cmax, 4 row index out of range), clears the word, and sets nrl_last_error().
+ * nrl_nrms_step_host checks it itself (it synchronises anyway) and returns NRL_ERR_INVALID_ARG. */
+int nrl_device_status(int* code_host, void* stream);
+
 /* ---- the gradient exchange of data-parallel training fused with the optimizer step ----------
  * Replaces, for world_size > 1, what Lightning DDP + torch.optim.Adam do for the reference after
  * every backward pass (configs/trainer/ddp.yaml, configs/model/nrms.yaml:49-52; gradient mean

@@ -106,6 +106,9 @@ SIGNATURES = {
     "nrl_ce_soft_fwd": (_I, [_VP, _VP, _VP, _I, _I, _VP, _VP, _VP, _VP]),
     "nrl_ce_soft_bwd": (_I, [_VP, _VP, _VP, _I, _I, _VP, _F, _VP, _VP]),
     "nrl_adam_step": (_I, [_VP, _VP, _VP, _VP, _LL, _F, _F, _F, _F, _LL, _F, _VP]),
+    "nrl_adam_step_zero_grad": (_I, [_VP, _VP, _VP, _VP, _LL, _F, _F, _F, _F, _LL, _F, _VP]),
+    "nrl_embedding_gather": (_I, [_VP, _LL, _VP, _LL, _I, _VP, _VP, _VP, _VP]),
+    "nrl_device_status": (_I, [C.POINTER(C.c_int), _VP]),
     "nrl_peer_alloc": (_I, [_SZ, C.POINTER(C.c_void_p), C.c_char_p]),
     "nrl_peer_free": (_I, [_VP]),
     "nrl_peer_open": (_I, [C.c_char_p, C.POINTER(C.c_void_p)]),

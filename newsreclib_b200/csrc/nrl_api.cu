@@ -695,7 +695,7 @@ static int check_common(const void* ws, size_t ws_bytes, size_t need) {
 // news encoder
 // ----------------------------------------------------------------------------------------
 static int news_fwd_impl(const Ctx& c, const Dims& d, BlockWs& w, const long long* ids,
-                         long long n_news, int L, const float* table,
+                         long long n_news, int L, const float* table, long long V1,
                          const nrl_block_params* prm, const DropCfg& drop, float* out) {
   const long long R = n_news * L;
   TRY(pack_weights(c, d, prm, w));
@@ -705,20 +705,20 @@ static int news_fwd_impl(const Ctx& c, const Dims& d, BlockWs& w, const long lon
     LAUNCH_CHECK("dropout_words");
   }
   gather_split_kernel<<<grid_for(R, 8, 1 << 20), 256, 0, c.stream>>>(
-      ids, R, table, d.E, d.Ep, w.x, c.two_planes() ? w.x + R * d.Ep : nullptr, nullptr,
+      ids, R, table, V1, d.E, d.Ep, w.x, c.two_planes() ? w.x + R * d.Ep : nullptr, nullptr,
       drop.on ? w.mask0 : nullptr, d.MW, drop.scale);
   LAUNCH_CHECK("gather_split");
   AttnGeom ag{L, 1, (int)n_news, L};
   return block_forward(c, d, w, R, ag, n_news, L, prm, drop, out);
 }
 static int news_bwd_impl(const Ctx& c, const Dims& d, BlockWs& w, const long long* ids,
-                         long long n_news, int L, const nrl_block_params* prm, const DropCfg& drop,
+                         long long n_news, int L, long long V1, const nrl_block_params* prm, const DropCfg& drop,
                          const float* d_out, nrl_block_grads* g, float* d_table) {
   const long long R = n_news * L;
   AttnGeom ag{L, 1, (int)n_news, L};
   TRY(block_backward(c, d, w, R, ag, n_news, L, prm, drop, drop, d_out, g));
   if (d_table) {
-    emb_grad_kernel<<<grid_for(R, 8, 1 << 20), 256, 0, c.stream>>>(ids, R, w.dx, d.E, d_table);
+    emb_grad_kernel<<<grid_for(R, 8, 1 << 20), 256, 0, c.stream>>>(ids, R, V1, w.dx, d.E, d_table);
     LAUNCH_CHECK("emb_grad");
   }
   return NRL_OK;
@@ -779,7 +779,7 @@ int nrl_news_encoder_fwd(const long long* ids, long long n_news, int L, const fl
   Bump b(ws);
   BlockWs w;
   carve_block(b, n_news * L, d, w);
-  return news_fwd_impl(c, d, w, ids, n_news, L, table, params, make_drop(dropout_p, training, seed), out);
+  return news_fwd_impl(c, d, w, ids, n_news, L, table, V1, params, make_drop(dropout_p, training, seed), out);
 }
 
 int nrl_news_encoder_bwd(const long long* ids, long long n_news, int L, long long V1,
@@ -789,16 +789,15 @@ int nrl_news_encoder_bwd(const long long* ids, long long n_news, int L, long lon
                          int precision, void* stream) {
   Dims d;
   TRY(make_dims(dims, d));
-  if (!ids || !params || !d_out || !grads || n_news <= 0 || L <= 0)
+  if (!ids || !params || !d_out || !grads || n_news <= 0 || L <= 0 || V1 <= 0)
     return fail(NRL_ERR_INVALID_ARG, "nrl_news_encoder_bwd: null pointer or empty input");
-  (void)V1;
   TRY(device_init());
   TRY(check_common(ws, ws_bytes, nrl_news_encoder_ws_bytes(n_news, L, dims)));
   Ctx c{static_cast<cudaStream_t>(stream), precision};
   Bump b(ws);
   BlockWs w;
   carve_block(b, n_news * L, d, w);
-  return news_bwd_impl(c, d, w, ids, n_news, L, params, make_drop(dropout_p, training, seed), d_out,
+  return news_bwd_impl(c, d, w, ids, n_news, L, V1, params, make_drop(dropout_p, training, seed), d_out,
                        grads, d_table);
 }
 
@@ -834,7 +833,7 @@ static int mhsa_pool_fwd(const Ctx& c, const Dims& d, const float* x, int B, int
   }
   // dense rows -> (dropout site 0) -> split planes: the gather kernel with the identity index
   gather_split_kernel<<<grid_for(R, 8, 1 << 20), 256, 0, c.stream>>>(
-      nullptr, R, x, d.E, d.Ep, w.x, c.two_planes() ? w.x + R * d.Ep : nullptr, nullptr,
+      nullptr, R, x, R, d.E, d.Ep, w.x, c.two_planes() ? w.x + R * d.Ep : nullptr, nullptr,
       drop.on ? w.mask0 : nullptr, d.MW, drop.scale);
   LAUNCH_CHECK("split_rows");
   return block_forward(c, d, w, R, user_geom(B, Hmax, axis), B, Hmax, params, drop, out);
@@ -997,7 +996,7 @@ int nrl_additive_bwd(const float* x, long long G, int L, int D, int Q, const flo
 // ----------------------------------------------------------------------------------------
 int nrl_segment_offsets(const long long* seg, long long n, int B, int* off, void* stream) {
   if (!seg || !off || n < 0 || B <= 0) return fail(NRL_ERR_INVALID_ARG, "nrl_segment_offsets: bad argument");
-  segment_offsets_kernel<<<(B + 1 + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(seg, n, B, off);
+  segment_offsets_kernel<<<(B + 1 + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(seg, n, B, off, 0);
   LAUNCH_CHECK("segment_offsets");
   return NRL_OK;
 }
@@ -1028,11 +1027,11 @@ int nrl_gather_rows(const void* table, long long n_table_rows, int row_bytes, co
   if (w8) {
     const int words = row_bytes / 8;
     gather_rows_kernel<unsigned long long><<<grid_for(n * words, 256, 16 * g_dev.sm_count), 256, 0, st>>>(
-        static_cast<const unsigned long long*>(table), words, idx, n, static_cast<unsigned long long*>(out));
+        static_cast<const unsigned long long*>(table), n_table_rows, words, idx, n, static_cast<unsigned long long*>(out));
   } else {
     const int words = row_bytes / 4;
     gather_rows_kernel<unsigned int><<<grid_for(n * words, 256, 16 * g_dev.sm_count), 256, 0, st>>>(
-        static_cast<const unsigned int*>(table), words, idx, n, static_cast<unsigned int*>(out));
+        static_cast<const unsigned int*>(table), n_table_rows, words, idx, n, static_cast<unsigned int*>(out));
   }
   LAUNCH_CHECK("gather_rows");
   return NRL_OK;
@@ -1091,15 +1090,54 @@ int nrl_ce_soft_bwd(const float* scores, const float* labels, const int* cand_of
   return NRL_OK;
 }
 
-int nrl_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
-                  float beta2, float eps, long long step, float grad_scale, void* stream) {
+static int adam_impl(float* p, float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                     float eps, long long step, float grad_scale, int zero_grad, void* stream) {
   if (!p || !g || !m || !v || n <= 0 || step <= 0) return fail(NRL_ERR_INVALID_ARG, "nrl_adam_step: bad argument");
   const double bc1 = 1.0 - std::pow((double)beta1, (double)step);
   const double bc2 = 1.0 - std::pow((double)beta2, (double)step);
   TRY(device_init());
   adam_kernel<<<grid_for(n, 256 * 4, 8 * g_dev.sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      p, g, m, v, n, lr, beta1, beta2, eps, (float)bc1, (float)std::sqrt(bc2), grad_scale);
+      p, g, m, v, n, lr, beta1, beta2, eps, (float)bc1, (float)std::sqrt(bc2), grad_scale, zero_grad);
   LAUNCH_CHECK("adam");
+  return NRL_OK;
+}
+int nrl_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                  float beta2, float eps, long long step, float grad_scale, void* stream) {
+  return adam_impl(p, const_cast<float*>(g), m, v, n, lr, beta1, beta2, eps, step, grad_scale, 0, stream);
+}
+int nrl_adam_step_zero_grad(float* p, float* g, float* m, float* v, long long n, float lr, float beta1,
+                            float beta2, float eps, long long step, float grad_scale, void* stream) {
+  return adam_impl(p, g, m, v, n, lr, beta1, beta2, eps, step, grad_scale, 1, stream);
+}
+
+int nrl_device_status(int* code_host, void* stream) {
+  if (!code_host) return fail(NRL_ERR_INVALID_ARG, "nrl_device_status: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned int code = 0;
+  const unsigned int zero = 0;
+  CUDA_TRY(cudaMemcpyFromSymbolAsync(&code, g_dev_error, sizeof(code), 0, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (code) CUDA_TRY(cudaMemcpyToSymbolAsync(g_dev_error, &zero, sizeof(zero), 0, cudaMemcpyHostToDevice, st));
+  *code_host = (int)code;
+  if (code) {
+    static const char* what[] = {"", "a token id lies outside [0, V1) (nn.Embedding would raise)",
+                                 "segment ids are not sorted ids in [0, B)",
+                                 "a segment is longer than the dense width passed as Hmax / Cmax",
+                                 "a row index lies outside the table"};
+    fail(NRL_ERR_INVALID_ARG, "device-side input check %u: %s", code, code < 5 ? what[code] : "?");
+  }
+  return NRL_OK;
+}
+
+int nrl_embedding_gather(const long long* ids, long long n, const float* table, long long V1, int E,
+                         float* out_f32, void* out_hi, void* out_lo, void* stream) {
+  if (!ids || !table || n <= 0 || V1 <= 0 || E <= 0 || (!out_f32 && !out_hi))
+    return fail(NRL_ERR_INVALID_ARG, "nrl_embedding_gather: bad argument");
+  TRY(device_init());
+  gather_split_kernel<<<grid_for(n, 8, 1 << 20), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      ids, n, table, V1, E, round_up(E + 1, 16), static_cast<bf16*>(out_hi), static_cast<bf16*>(out_lo), out_f32,
+      nullptr, 0, 1.f);
+  LAUNCH_CHECK("gather_split");
   return NRL_OK;
 }
 
@@ -1248,20 +1286,20 @@ size_t nrl_nrms_ws_bytes(long long n_hist, long long n_cand, int L, int B, int H
 static int nrms_impl(const Ctx& c, const Dims& d, NrmsWs& w, const long long* hist_ids,
                      const long long* cand_ids, const long long* seg_hist, const long long* seg_cand,
                      const float* labels, long long nh, long long nc, int L, int B, int Hmax, int Cmax,
-                     const float* table, const nrl_block_params* np, const nrl_block_params* up,
+                     const float* table, long long V1, const nrl_block_params* np, const nrl_block_params* up,
                      int late_fusion, const DropCfg& drop, float* scores, float* loss, int do_backward,
                      nrl_block_grads* ng, nrl_block_grads* ug, float* d_table) {
   const long long N = nh + nc;
-  segment_offsets_kernel<<<(B + 1 + 127) / 128, 128, 0, c.stream>>>(seg_hist, nh, B, w.hist_off);
+  segment_offsets_kernel<<<(B + 1 + 127) / 128, 128, 0, c.stream>>>(seg_hist, nh, B, w.hist_off, Hmax);
   LAUNCH_CHECK("segment_offsets(hist)");
-  segment_offsets_kernel<<<(B + 1 + 127) / 128, 128, 0, c.stream>>>(seg_cand, nc, B, w.cand_off);
+  segment_offsets_kernel<<<(B + 1 + 127) / 128, 128, 0, c.stream>>>(seg_cand, nc, B, w.cand_off, Cmax);
   LAUNCH_CHECK("segment_offsets(cand)");
   if (hist_ids != w.ids)
     CUDA_TRY(cudaMemcpyAsync(w.ids, hist_ids, (size_t)nh * L * sizeof(long long), cudaMemcpyDeviceToDevice, c.stream));
   if (cand_ids != w.ids + nh * L)
     CUDA_TRY(cudaMemcpyAsync(w.ids + nh * L, cand_ids, (size_t)nc * L * sizeof(long long), cudaMemcpyDeviceToDevice, c.stream));
   // history and candidate titles share the news encoder: one pass over all N news
-  TRY(news_fwd_impl(c, d, w.news, w.ids, N, L, table, np, drop, w.news_vec));
+  TRY(news_fwd_impl(c, d, w.news, w.ids, N, L, table, V1, np, drop, w.news_vec));
   const float* cand_vec = w.news_vec + nh * d.E;
   const long long Ru = (long long)B * Hmax;
   DropCfg nodrop = make_drop(0.f, 0, 0);
@@ -1291,6 +1329,9 @@ static int nrms_impl(const Ctx& c, const Dims& d, NrmsWs& w, const long long* hi
   if (!ng || (!late_fusion && !ug)) return fail(NRL_ERR_INVALID_ARG, "backward requested without gradient buffers");
   ce_bwd_kernel<<<(B + 3) / 4, 128, 0, c.stream>>>(scores, labels, w.cand_off, B, Cmax, nullptr, 1.0f, w.d_scores);
   LAUNCH_CHECK("ce_bwd");
+  // every row is overwritten below for well-formed segment ids; rows of malformed input (flagged by the device-side
+  // checks) must not carry stale workspace bytes into the table gradient
+  CUDA_TRY(cudaMemsetAsync(w.d_news, 0, (size_t)N * d.E * sizeof(float), c.stream));
   score_bwd_kernel<<<B, 128, 0, c.stream>>>(w.d_scores, w.user_vec, cand_vec, w.cand_off, B, Cmax, d.E,
                                             w.d_user, w.d_news + nh * d.E);
   LAUNCH_CHECK("score_bwd");
@@ -1303,7 +1344,7 @@ static int nrms_impl(const Ctx& c, const Dims& d, NrmsWs& w, const long long* hi
     late_fusion_bwd_kernel<<<B, 128, 0, c.stream>>>(w.d_user, w.hist_off, B, d.E, w.d_news);
     LAUNCH_CHECK("late_fusion_bwd");
   }
-  return news_bwd_impl(c, d, w.news, w.ids, N, L, np, drop, w.d_news, ng, d_table);
+  return news_bwd_impl(c, d, w.news, w.ids, N, L, V1, np, drop, w.d_news, ng, d_table);
 }
 
 static int nrms_check(long long nh, long long nc, int L, int B, int Hmax, int Cmax, const float* table,
@@ -1336,7 +1377,7 @@ int nrl_nrms_step(const long long* hist_ids, const long long* cand_ids, const lo
   NrmsWs w;
   carve_nrms(b, n_hist, n_cand, L, B, Hmax, Cmax, d, w);
   return nrms_impl(c, d, w, hist_ids, cand_ids, seg_hist, seg_cand, labels, n_hist, n_cand, L, B, Hmax,
-                   Cmax, table, news_params, user_params, late_fusion,
+                   Cmax, table, V1, news_params, user_params, late_fusion,
                    make_drop(dropout_p, training, seed), scores, loss, do_backward, news_grads,
                    user_grads, d_table);
 }
@@ -1369,12 +1410,21 @@ int nrl_nrms_step_host(const long long* hist_ids_host, const long long* cand_ids
   if (labels_host)
     CUDA_TRY(cudaMemcpyAsync(w.labels, labels_host, (size_t)n_cand * sizeof(float), cudaMemcpyHostToDevice, c.stream));
   TRY(nrms_impl(c, d, w, w.ids, w.ids + n_hist * L, w.seg_h, w.seg_c, w.labels, n_hist, n_cand, L, B, Hmax,
-                Cmax, table, news_params, user_params, late_fusion, make_drop(dropout_p, training, seed),
+                Cmax, table, V1, news_params, user_params, late_fusion, make_drop(dropout_p, training, seed),
                 w.scores_dev, loss_host ? w.loss_dev : nullptr, do_backward, news_grads, user_grads, d_table));
   CUDA_TRY(cudaMemcpyAsync(scores_host, w.scores_dev, (size_t)B * Cmax * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
   if (loss_host)
     CUDA_TRY(cudaMemcpyAsync(loss_host, w.loss_dev, sizeof(float), cudaMemcpyDeviceToHost, c.stream));
   CUDA_TRY(cudaStreamSynchronize(c.stream));
+  {  // the stream is idle: surface a device-side input violation (bad token / segment ids) of this step
+    unsigned int code = 0;
+    CUDA_TRY(cudaMemcpyFromSymbol(&code, g_dev_error, sizeof(code)));
+    if (code) {
+      int dummy = 0;
+      nrl_device_status(&dummy, stream);  // formats the message and clears the flag
+      return NRL_ERR_INVALID_ARG;
+    }
+  }
   return NRL_OK;
 }
 
@@ -1473,7 +1523,7 @@ int nrl_cnn_encoder_fwd(const long long* ids, long long n_news, int L, const flo
     LAUNCH_CHECK("dropout_words(1)");
   }
   gather_im2col_kernel<<<grid_for(R, 8, 1 << 20), 256, 0, c.stream>>>(
-      ids, n_news, L, table, d.E, d.W, d.Kp, w.A, tp ? w.A + R * d.Kp : nullptr,
+      ids, n_news, L, table, V1, d.E, d.W, d.Kp, w.A, tp ? w.A + R * d.Kp : nullptr,
       drop.on ? w.mask0 : nullptr, d.MW0, drop.scale);
   LAUNCH_CHECK("gather_im2col");
   {  // Y = dropout1(relu(A Wc^T + bc)): fp32 + split planes (ones column at F)
@@ -1505,9 +1555,8 @@ int nrl_cnn_encoder_bwd(const long long* ids, long long n_news, int L, long long
                         int precision, void* stream) {
   CnnDims d;
   TRY(make_cnn_dims(dims, d));
-  if (!ids || !prm || !d_out || !g || n_news <= 0 || L <= 0)
+  if (!ids || !prm || !d_out || !g || n_news <= 0 || L <= 0 || V1 <= 0)
     return fail(NRL_ERR_INVALID_ARG, "nrl_cnn_encoder_bwd: null pointer or empty input");
-  (void)V1;
   TRY(device_init());
   TRY(check_common(ws, ws_bytes, nrl_cnn_encoder_ws_bytes(n_news, L, dims)));
   Ctx c{static_cast<cudaStream_t>(stream), precision};
@@ -1541,7 +1590,7 @@ int nrl_cnn_encoder_bwd(const long long* ids, long long n_news, int L, long long
     sk.f32 = w.dA; sk.ld_f32 = d.Kc; sk.f32_cols = d.Kc;
     TRY(gemm_nt(c, w.dyp, R, d.Fp, w.wconv_t, d.Kc, d.Fp, d.Fp, e, sk, "gemm conv dgrad"));
     col2im_emb_grad_kernel<<<grid_for(R, 8, 1 << 20), 256, 0, c.stream>>>(
-        ids, n_news, L, w.dA, d.Kc, d.E, d.W, drop.on ? w.mask0 : nullptr, d.MW0, drop.scale, d_table);
+        ids, n_news, L, V1, w.dA, d.Kc, d.E, d.W, drop.on ? w.mask0 : nullptr, d.MW0, drop.scale, d_table);
     LAUNCH_CHECK("col2im_emb_grad");
   }
   return NRL_OK;
@@ -1594,7 +1643,7 @@ int nrl_linear_encoder_fwd(const long long* ids, long long n, const float* table
     LAUNCH_CHECK("dropout_words(0)");
   }
   gather_split_kernel<<<grid_for(n, 8, 1 << 20), 256, 0, c.stream>>>(
-      ids, n, table, CE, Ep, w.x, tp ? w.x + n * Ep : nullptr, nullptr, drop.on ? w.mask0 : nullptr, MW,
+      ids, n, table, V1, CE, Ep, w.x, tp ? w.x + n * Ep : nullptr, nullptr, drop.on ? w.mask0 : nullptr, MW,
       drop.scale);
   LAUNCH_CHECK("gather_split");
   GemmEpi e = epi_none();
@@ -1611,7 +1660,7 @@ int nrl_linear_encoder_bwd(const long long* ids, long long n, long long V1, int 
                            size_t ws_bytes, int precision, void* stream) {
   if (!ids || !weight || !out || !d_out || !g_weight || !g_bias || n <= 0 || CE <= 0 || O <= 0 || (CE & 3) || (O & 3))
     return fail(NRL_ERR_INVALID_ARG, "nrl_linear_encoder_bwd: bad argument");
-  (void)V1;
+  if (V1 <= 0) return fail(NRL_ERR_INVALID_ARG, "nrl_linear_encoder_bwd: V1 must be positive");
   TRY(device_init());
   TRY(check_common(ws, ws_bytes, nrl_linear_encoder_ws_bytes(n, CE, O)));
   Ctx c{static_cast<cudaStream_t>(stream), precision};
@@ -1631,7 +1680,7 @@ int nrl_linear_encoder_bwd(const long long* ids, long long n, long long V1, int 
     Sinks sk;
     sk.f32 = w.dx; sk.ld_f32 = CE; sk.f32_cols = CE;
     TRY(gemm_nt(c, w.dpre, n, Op, w.wt, CE, Op, Op, e, sk, "gemm linear dgrad"));
-    emb_grad_kernel<<<grid_for(n, 8, 1 << 20), 256, 0, c.stream>>>(ids, n, w.dx, CE, d_table);
+    emb_grad_kernel<<<grid_for(n, 8, 1 << 20), 256, 0, c.stream>>>(ids, n, V1, w.dx, CE, d_table);
     LAUNCH_CHECK("emb_grad");
   }
   return NRL_OK;

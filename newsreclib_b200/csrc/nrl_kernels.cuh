@@ -8,6 +8,14 @@
 
 namespace nrl {
 
+// Sticky device-side input-validation flag (what nn.Embedding's index check is for the reference: an id
+// outside the table raises there).  Kernels that index with caller-provided ids / segment ids record the FIRST
+// violation here and neutralise the access (id 0 / skipped row) instead of touching memory out of bounds; the host
+// reads and clears it with nrl_device_status().
+enum { DEV_ERR_TOKEN_ID = 1, DEV_ERR_SEGMENT_ID = 2, DEV_ERR_SEGMENT_LEN = 3, DEV_ERR_ROW_INDEX = 4 };
+__device__ unsigned int g_dev_error = 0;
+__device__ __forceinline__ void dev_error(unsigned int code) { atomicCAS(&g_dev_error, 0u, code); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -85,7 +93,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ W, const float* __r
 // One warp per token row; rows of the table are 16-byte aligned when E % 4 == 0.
 // ------------------------------------------------------------------------------------
 __global__ void gather_split_kernel(const long long* __restrict__ ids, long long R,
-                                    const float* __restrict__ table, int E, int ep,
+                                    const float* __restrict__ table, long long V1, int E, int ep,
                                     __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                     float* __restrict__ x_f32, const uint32_t* __restrict__ drop_words,
                                     int drop_mw, float drop_scale) {
@@ -93,7 +101,11 @@ __global__ void gather_split_kernel(const long long* __restrict__ ids, long long
   const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long r = warp0; r < R; r += nwarps) {
-    const long long id = ids ? ids[r] : r;  // ids == nullptr: dense rows (identity gather)
+    long long id = ids ? ids[r] : r;  // ids == nullptr: dense rows (identity gather)
+    if (id < 0 || id >= V1) {           // nn.Embedding raises here; row 0 is read instead and the flag is set
+      if (lane == 0) dev_error(DEV_ERR_TOKEN_ID);
+      id = 0;
+    }
     const float* src = table + id * E;
     for (int c = lane * 4; c < ep; c += 128) {
       float v[4];
@@ -121,7 +133,8 @@ __global__ void gather_split_kernel(const long long* __restrict__ ids, long long
 #pragma unroll
       for (int i = 0; i < 4; ++i) split_bf16(v[i], h[i], l[i]);
       const long long off = r * ep + c;  // ep % 8 == 0 and c % 4 == 0 -> 8-byte aligned
-      *reinterpret_cast<uint2*>(hi + off) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+      if (hi)
+        *reinterpret_cast<uint2*>(hi + off) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
       if (lo)
         *reinterpret_cast<uint2*>(lo + off) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
     }
@@ -1228,8 +1241,10 @@ pool_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ Y,
 // segment ids.  Dense rows beyond a segment's length are zero (their ones column stays 1:
 // padded history rows still receive the in-projection bias, as in the reference).
 // ------------------------------------------------------------------------------------
+// max_count > 0: a segment longer than the dense width the caller announced (Hmax / Cmax), or ids outside
+// [0, B) (off[B] != n, seg[0] < 0), set the device error flag -- the dense kernels clip such rows.
 __global__ void segment_offsets_kernel(const long long* __restrict__ seg, long long n, int B,
-                                       int* __restrict__ off) {
+                                       int* __restrict__ off, int max_count) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b > B) return;
   long long lo = 0, hi = n;  // first index with seg[i] >= b
@@ -1238,6 +1253,18 @@ __global__ void segment_offsets_kernel(const long long* __restrict__ seg, long l
     if (seg[mid] < b) lo = mid + 1; else hi = mid;
   }
   off[b] = (int)lo;
+  if (max_count > 0) {
+    if (b == B && lo != n) dev_error(DEV_ERR_SEGMENT_ID);
+    if (b == 0 && (lo != 0 || (n > 0 && seg[0] < 0))) dev_error(DEV_ERR_SEGMENT_ID);
+    if (b < B) {
+      long long l2 = lo, h2 = n;  // first index with seg[i] >= b + 1
+      while (l2 < h2) {
+        long long mid = (l2 + h2) >> 1;
+        if (seg[mid] < b + 1) l2 = mid + 1; else h2 = mid;
+      }
+      if (l2 - lo > max_count) dev_error(DEV_ERR_SEGMENT_LEN);
+    }
+  }
 }
 
 __global__ void dense_scatter_kernel(const float* __restrict__ x, const int* __restrict__ off,
@@ -1264,7 +1291,7 @@ __global__ void dense_scatter_kernel(const float* __restrict__ x, const int* __r
 __global__ void dense_gather_kernel(const float* __restrict__ d_dense, const int* __restrict__ off,
                                     int B, int M, int E, float* __restrict__ dx) {
   for (int b = blockIdx.y; b < B; b += gridDim.y) {
-    const int cnt = off[b + 1] - off[b];
+    const int cnt = min(off[b + 1] - off[b], M);  // longer segments were flagged by segment_offsets_kernel
     for (int j = blockIdx.x; j < cnt; j += gridDim.x)
       for (int c = threadIdx.x; c < E; c += blockDim.x)
         dx[(long long)(off[b] + j) * E + c] = d_dense[((long long)b * M + j) * E + c];
@@ -1317,7 +1344,7 @@ __global__ void score_bwd_kernel(const float* __restrict__ d_scores, const float
                                  const float* __restrict__ cand, const int* __restrict__ off, int B,
                                  int C, int E, float* __restrict__ d_user, float* __restrict__ d_cand) {
   const int b = blockIdx.x;
-  const int cnt = off[b + 1] - off[b];
+  const int cnt = min(off[b + 1] - off[b], C);
   for (int i = threadIdx.x; i < E; i += blockDim.x) {
     const float u = user[(long long)b * E + i];
     float acc = 0.f;
@@ -1393,7 +1420,7 @@ __global__ void ce_bwd_kernel(const float* __restrict__ scores, const float* __r
 // padding_idx row is skipped so its gradient stays exactly zero, text.py:215-217).
 // One warp per token row, 128-bit vector atomics.
 // ------------------------------------------------------------------------------------
-__global__ void emb_grad_kernel(const long long* __restrict__ ids, long long R,
+__global__ void emb_grad_kernel(const long long* __restrict__ ids, long long R, long long V1,
                                 const float* __restrict__ dX, int E, float* __restrict__ d_table) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
@@ -1401,6 +1428,10 @@ __global__ void emb_grad_kernel(const long long* __restrict__ ids, long long R,
   for (long long r = warp0; r < R; r += nwarps) {
     const long long id = ids[r];
     if (id == 0) continue;
+    if (id < 0 || id >= V1) {  // never write outside the table: flag and skip
+      if (lane == 0) dev_error(DEV_ERR_TOKEN_ID);
+      continue;
+    }
     const float* src = dX + r * E;
     float* dst = d_table + id * E;
     if ((E & 3) == 0) {
@@ -1416,9 +1447,11 @@ __global__ void emb_grad_kernel(const long long* __restrict__ ids, long long R,
 
 // torch.optim.Adam (no weight decay / amsgrad), dense over n elements; 128-bit accesses over the
 // 16-byte-aligned body (the flat parameter buffers are), scalar tail.
-__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+// zero_grad != 0: the gradient element is overwritten with 0 after it has been consumed (optimizer.zero_grad()
+// folded into the step: the buffers accumulate, so they must be clean before the next backward pass).
+__global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float lr, float b1, float b2,
-                            float eps, float bc1, float sqrt_bc2, float g_scale) {
+                            float eps, float bc1, float sqrt_bc2, float g_scale, int zero_grad) {
   const float lr_bc1 = lr / bc1;
   const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long nth = (long long)gridDim.x * blockDim.x;
@@ -1427,7 +1460,8 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   const long long n4 = vec ? n / 4 : 0;
   for (long long i = tid; i < n4; i += nth) {
     float4 p4 = reinterpret_cast<float4*>(p)[i];
-    const float4 g4 = __ldg(reinterpret_cast<const float4*>(g) + i);
+    const float4 g4 = reinterpret_cast<const float4*>(g)[i];
+    if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i];
     {  // sqrt(v) / sqrt_bc2 is kept as a division (torch's formula), not a reciprocal multiply
       float* pp = &p4.x; const float* gg = &g4.x; float* mm = &m4.x; float* vv = &v4.x;
@@ -1448,6 +1482,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
   for (long long i = 4 * n4 + tid; i < n; i += nth) {
     const float gi = g[i] * g_scale;
+    if (zero_grad) g[i] = 0.f;
     const float mi = b1 * m[i] + (1.f - b1) * gi;
     const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
     m[i] = mi;
@@ -1487,14 +1522,19 @@ __global__ void dropout_mask_kernel(unsigned char* __restrict__ keep, long long 
 // rec_dataset.py:189-285, over a news table already resident in HBM) and the news-vector cache
 // lookup of the evaluation path.  Consecutive threads copy consecutive words: coalesced both ways.
 template <typename Wd>
-__global__ void gather_rows_kernel(const Wd* __restrict__ table, int words, const long long* __restrict__ idx,
-                                   long long n, Wd* __restrict__ out) {
+__global__ void gather_rows_kernel(const Wd* __restrict__ table, long long n_rows, int words,
+                                   const long long* __restrict__ idx, long long n, Wd* __restrict__ out) {
   const long long total = n * words;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / words;
     const int w = (int)(i - r * words);
-    out[i] = __ldg(table + idx[r] * words + w);
+    long long src = idx[r];
+    if (src < 0 || src >= n_rows) {  // flagged; row 0 is copied instead of reading out of bounds
+      if (w == 0) dev_error(DEV_ERR_ROW_INDEX);
+      src = 0;
+    }
+    out[i] = __ldg(table + src * words + w);
   }
 }
 

@@ -13,7 +13,7 @@ namespace nrl {
 // with x(n, t') = 0 outside [0, L) (the conv's zero padding along the token axis).
 // One warp per output row; the keep-bit words belong to the SOURCE token row.
 __global__ void gather_im2col_kernel(const long long* __restrict__ ids, long long N, int L,
-                                     const float* __restrict__ table, int E, int win, int kp,
+                                     const float* __restrict__ table, long long V1, int E, int win, int kp,
                                      __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                      const uint32_t* __restrict__ drop_words, int drop_mw,
                                      float drop_scale) {
@@ -31,7 +31,12 @@ __global__ void gather_im2col_kernel(const long long* __restrict__ ids, long lon
       const int ts = t + j - pad;
       const bool in = ts >= 0 && ts < L;
       const long long rs = n * L + ts;
-      const float* src = in ? table + ids[rs] * E : nullptr;
+      long long id = in ? ids[rs] : 0;
+      if (id < 0 || id >= V1) {  // flagged; row 0 is read instead (nn.Embedding raises here)
+        if (lane == 0) dev_error(DEV_ERR_TOKEN_ID);
+        id = 0;
+      }
+      const float* src = in ? table + id * E : nullptr;
       for (int c = lane * 4; c < E; c += 128) {  // E % 4 == 0 (host checks)
         float v[4] = {0.f, 0.f, 0.f, 0.f};
         if (in) {
@@ -62,7 +67,7 @@ __global__ void gather_im2col_kernel(const long long* __restrict__ ids, long lon
 // Transpose of the above fused with the embedding-gradient scatter:
 //   dx(n, t') = dropout0'( sum_j dA[(n, t' - j + pad)][j*E : (j+1)*E] ),   d_table[id(n, t')] += dx
 // (row 0 of the table = padding_idx is skipped, text.py:151-153).  One warp per source token.
-__global__ void col2im_emb_grad_kernel(const long long* __restrict__ ids, long long N, int L,
+__global__ void col2im_emb_grad_kernel(const long long* __restrict__ ids, long long N, int L, long long V1,
                                        const float* __restrict__ dA, long long ld_da, int E, int win,
                                        const uint32_t* __restrict__ drop_words, int drop_mw,
                                        float drop_scale, float* __restrict__ d_table) {
@@ -74,6 +79,10 @@ __global__ void col2im_emb_grad_kernel(const long long* __restrict__ ids, long l
   for (long long rs = warp0; rs < R; rs += nwarps) {
     const long long id = ids[rs];
     if (id == 0) continue;
+    if (id < 0 || id >= V1) {  // never write outside the table: flag and skip
+      if (lane == 0) dev_error(DEV_ERR_TOKEN_ID);
+      continue;
+    }
     const long long n = rs / L;
     const int ts = (int)(rs - n * L);
     float* dst = d_table + id * E;

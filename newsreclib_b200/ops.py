@@ -129,12 +129,44 @@ def gather_rows(table: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def adam_step(p, g, m, v, step: int, lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0) -> None:
+def adam_step(p, g, m, v, step: int, lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0,
+              zero_grad: bool = False) -> None:
+    """``torch.optim.Adam.step`` over flat buffers; ``zero_grad=True`` also clears ``g`` in the same pass."""
     lib = _lib.load()
     for t, n in ((p, "p"), (g, "g"), (m, "m"), (v, "v")):
         _chk(t, torch.float32, n)
-    _lib.check(lib.nrl_adam_step(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, step,
-                                 grad_scale, _stream()), "nrl_adam_step")
+    fn = lib.nrl_adam_step_zero_grad if zero_grad else lib.nrl_adam_step
+    _lib.check(fn(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, step, grad_scale, _stream()),
+               "nrl_adam_step")
+
+
+def embedding_gather(ids: torch.Tensor, table: torch.Tensor, want_planes: bool = False):
+    """``nn.Embedding.forward`` (``text.py:224``): ``table[ids]`` as fp32 ``[n, E]`` and, optionally, the bf16 hi / lo
+    split planes ``[n, Ep]`` the in-projection GEMM consumes (``nrl_embedding_gather``)."""
+    lib = _lib.load()
+    ids = _chk(ids.contiguous(), torch.int64, "ids")
+    _chk(table, torch.float32, "embedding table")
+    n, E = ids.numel(), table.shape[1]
+    Ep = (E + 1 + 15) // 16 * 16
+    out = torch.empty(n, E, dtype=torch.float32, device=table.device)
+    hi = lo = None
+    if want_planes:
+        hi = torch.empty(n, Ep, dtype=torch.bfloat16, device=table.device)
+        lo = torch.empty(n, Ep, dtype=torch.bfloat16, device=table.device)
+    _lib.check(lib.nrl_embedding_gather(_p(ids), n, _p(table), table.shape[0], E, _p(out), _p(hi), _p(lo), _stream()),
+               "nrl_embedding_gather")
+    return (out, hi, lo) if want_planes else out
+
+
+def device_status(raise_on_error: bool = True) -> int:
+    """Synchronise the current stream and return (and clear) the device-side input-check word: 0, or the code of the
+    first violation (token id outside the table, malformed segment ids ...) -- ``nrl_device_status``."""
+    lib = _lib.load()
+    code = C.c_int(0)
+    _lib.check(lib.nrl_device_status(C.byref(code), _stream()), "nrl_device_status")
+    if code.value and raise_on_error:
+        raise RuntimeError("newsreclib_b200: " + lib.nrl_last_error().decode("utf-8", "replace"))
+    return int(code.value)
 
 
 def nrms_step(batch: Dict, table: torch.Tensor, news_block, user_block, dims: Dims, *, B: int,

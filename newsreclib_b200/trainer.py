@@ -4,9 +4,10 @@
 in the reference's ``state_dict`` order and names), one flat gradient buffer and
 the Adam moments.  A step is three library calls on the current CUDA stream:
 
-    zero grads (one memset)  ->  nrl_nrms_step (forward + CE + backward, ~45 kernels)
+    nrl_nrms_step (forward + CE + backward, ~45 kernels)
     [-> one NCCL all-reduce of the flat gradient buffer when world_size > 1]
-    ->  nrl_adam_step (dense Adam over the flat buffer, torch.optim.Adam semantics)
+    ->  nrl_adam_step_zero_grad (dense Adam over the flat buffer, torch.optim.Adam semantics, which also
+        clears the gradient buffer for the next step: optimizer.zero_grad() costs no extra pass)
 
 or, with ``exchange="peer"``, the last two lines are ONE kernel over NVLink peer memory
 (``nrl_exchange_adam_step``: reduce-scatter by peer loads, Adam on the owned slice, all-gather by
@@ -124,14 +125,18 @@ class NRMSTrainer:
     def __init__(self, params: Dict[str, torch.Tensor], num_heads: int, *, device="cuda",
                  dropout_p: float = 0.2, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
                  precision: int = ops.PREC_BF16X3, late_fusion: bool = False, seed: int = 1234,
-                 process_group=None, exchange: Optional[str] = None, exchange_timeout_s: float = 30.0) -> None:
+                 process_group=None, exchange: Optional[str] = None, exchange_timeout_s: float = 30.0,
+                 status_every: int = 64) -> None:
         """``exchange``: how the ranks' gradients meet the optimizer when world_size > 1 --
         ``"nccl"`` (one NCCL all-reduce of the flat gradient buffer, then dense Adam on every rank) or
         ``"peer"`` (``nrl_exchange_adam_step``: reduce-scatter + sharded Adam + all-gather as one kernel
         over NVLink peer memory, ``exchange.py``).  Default: ``$NRL_EXCHANGE`` or ``"nccl"``.
         ``exchange_timeout_s``: how long a rank's fused exchange kernel waits for a peer before it gives up (a dead
         peer must not hang the GPU); raise it if one rank may legitimately stall for longer between two steps
-        (checkpointing on rank 0, a slow data loader)."""
+        (checkpointing on rank 0, a slow data loader).
+        ``status_every``: every that many steps (and in ``state_dict`` / ``gather_moments``) the stream is synchronised
+        and the library's sticky error words are read -- a timed-out peer barrier or an out-of-range token / segment
+        id raises ``RuntimeError`` here instead of silently training on (0 = only at checkpoints)."""
         _lib.load()
         self.device = torch.device(device)
         self.keys = [TITLE + "embedding_layer.weight"] + [TITLE + k for k in ops.BLOCK_KEYS] + \
@@ -170,9 +175,31 @@ class NRMSTrainer:
         on = torch.distributed.is_available() and torch.distributed.is_initialized()
         self.rank = torch.distributed.get_rank(process_group) if on else 0
         self._structs = None
+        self.status_every = int(status_every)
+        self._grads_clean = True  # the gradient buffers are zero (fresh, or cleared by the fused Adam step)
+        if self.world > 1:
+            # what Lightning DDP does for the reference at construction: every replica starts from rank 0's values
+            # (ranks built from different seeds / checkpoints would otherwise average gradients of different weights)
+            torch.distributed.broadcast(self.flat, src=torch.distributed.get_global_rank(process_group, 0)
+                                        if process_group is not None else 0, group=process_group)
+
+    def check_status(self) -> None:
+        """Synchronise the stream and raise if a peer-exchange barrier timed out (the replica of that step may be
+        partially updated: restore from the last checkpoint) or a device-side input check fired."""
+        if self.peer_block is not None:
+            code = self.peer_block.status()
+            if code:
+                raise RuntimeError(f"rank {self.rank}: peer-exchange barrier timed out (code {code}: "
+                                   f"{'ready' if code == 1 else 'done'} wait; a peer never arrived within "
+                                   f"{self.exchange_timeout_s:.0f} s). Parameters after step {self.step_count} are not "
+                                   "trustworthy; restore the last checkpoint on all ranks.")
+        if self.device.type == "cuda":
+            with torch.cuda.device(self.device):
+                ops.device_status(raise_on_error=True)
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
         """Reference-named parameters (loadable into the reference's NRMSModule)."""
+        self.check_status()
         return {k: v.detach().clone() for k, v in self.params.items()}
 
     def gather_moments(self):
@@ -180,6 +207,7 @@ class NRMSTrainer:
         optimizer checkpoint).  With the fused peer exchange a rank updates only the slice it owns
         (``exchange.slice_bounds``) and the rest stays zero, so the full state is the sum over the ranks; with the
         NCCL exchange every rank already holds it."""
+        self.check_status()
         if self.peer_block is None:
             return self.m.detach().clone(), self.v.detach().clone()
         return self.exchange.gather_sharded(self.m), self.exchange.gather_sharded(self.v)
@@ -194,15 +222,25 @@ class NRMSTrainer:
             exchange_adam_step(self.peer_block.peer_set, self.m, self.v, self.flat.numel(), self.step_count,
                                lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, grad_scale=scale,
                                epoch=self.exchange_epoch, max_ctas=self.exchange_ctas, timeout_s=self.exchange_timeout_s)
-            return
-        # Adam on chunk i overlaps the all-reduce of chunks i+1.. (one chunk = everything when world == 1)
-        for sl, _ in self.exchange.all_reduce_chunks(self.grad):
-            ops.adam_step(self.flat[sl], self.grad[sl], self.m[sl], self.v[sl], self.step_count, self.lr,
-                          self.betas[0], self.betas[1], self.eps, grad_scale=scale)
+            self._grads_clean = False  # peers read this rank's gradients until the kernel's done barrier
+        else:
+            # Adam on chunk i overlaps the all-reduce of chunks i+1.. (one chunk = everything when world == 1);
+            # the same pass clears the gradient slice it has consumed
+            for sl, _ in self.exchange.all_reduce_chunks(self.grad):
+                ops.adam_step(self.flat[sl], self.grad[sl], self.m[sl], self.v[sl], self.step_count, self.lr,
+                              self.betas[0], self.betas[1], self.eps, grad_scale=scale, zero_grad=True)
+            self._grads_clean = True
+        if self.status_every > 0 and self.step_count % self.status_every == 0:
+            self.check_status()
+
+    def _zero_grads(self) -> None:
+        if not self._grads_clean:
+            self.grad.zero_()
+        self._grads_clean = False
 
     def train_step(self, batch: Dict, B: int, Hmax: int, Cmax: int, training: bool = True):
         """Device-resident batch -> (scores [B, Cmax], loss [1]) device tensors; no host sync."""
-        self.grad.zero_()
+        self._zero_grads()
         scores, loss, self.ws = ops.nrms_step(
             batch, self.table, self.news_block, self.user_block, self.dims, B=B, Hmax=Hmax, Cmax=Cmax,
             late_fusion=self.late_fusion, dropout_p=self.dropout_p, training=training,
@@ -222,7 +260,7 @@ class NRMSTrainer:
         need = lib.nrl_nrms_ws_bytes(nh, nc, L, B, Hmax, Cmax, self.dims)
         if self.ws is None or self.ws.numel() < need:
             self.ws = ops.workspace(need, self.device)
-        self.grad.zero_()
+        self._zero_grads()
         nb, ub = ops.block_struct(self.news_block), ops.block_struct(self.user_block)
         ng, ug = ops.block_struct(self.grad_pack[0]), ops.block_struct(self.grad_pack[1])
         _lib.check(lib.nrl_nrms_step_host(
@@ -275,14 +313,16 @@ class ModuleTrainer:
         self.lr, self.betas, self.eps = lr, betas, eps
         self.exchange = GradExchange(process_group)
         self.step_count = 0
+        if self.exchange.world > 1:  # Lightning DDP broadcasts rank 0's parameters at construction
+            torch.distributed.broadcast(self.flat, src=torch.distributed.get_global_rank(process_group, 0)
+                                        if process_group is not None else 0, group=process_group)
 
     def train_step(self, batch) -> torch.Tensor:
         self.module.train()
-        self.grad.zero_()
-        loss = self.module.model_step(batch)[0]
+        loss = self.module.model_step(batch)[0]  # gradient buffers are clean: zeroed at construction / by the Adam pass
         loss.backward()
         scale = self.exchange.all_reduce(self.grad)
         self.step_count += 1
         ops.adam_step(self.flat, self.grad, self.m, self.v, self.step_count, self.lr, self.betas[0], self.betas[1],
-                      self.eps, grad_scale=scale)
+                      self.eps, grad_scale=scale, zero_grad=True)
         return loss.detach()

@@ -116,6 +116,22 @@ def grad_tolerances(params, batch, H, base_tol, ref_grads=None, **kw):
     return {k: max(base_tol, 4.0 * rel_err(ref_grads[k], g64[k])) for k in ref_grads}
 
 
+def report_step(tag, scores, loss, grads, ref_scores, ref_loss, ref_grads, tols, logit_tol, loss_tol):
+    """Compare one step with the oracle, PRINT every tensor's error next to the tolerance applied, then assert."""
+    es, el = rel_err(scores, ref_scores), rel_err(loss, ref_loss)
+    print(f"{tag}: logits rel {es:.2e} (tol {logit_tol:.0e})  loss rel {el:.2e} (tol {loss_tol:.0e})")
+    rows, worst = [], 0.0
+    for k, g in ref_grads.items():
+        e, t = rel_err(grads[k], g), tols[k]
+        rows.append((k, e, t))
+        worst = max(worst, e / t)
+        print(f"  grad {k:<66s} err {e:.2e}  tol {t:.2e}")
+    print(f"{tag}: worst gradient error / tolerance {worst:.2f}")
+    assert es <= logit_tol and el <= loss_tol, (tag, es, el)
+    for k, e, t in rows:
+        assert e <= t, (tag, k, e, t)
+
+
 def load_collate_golden():
     """``tests/golden/collate_ref.npz`` (minted by ``oracle/make_collate_golden.py`` from the reference's own
     ``DatasetCollate``): returns (news columns as lists, {split: (samples, reference batch dict)}, (L_title, L_abs))."""

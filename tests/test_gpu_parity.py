@@ -108,10 +108,12 @@ def _compare(scores, loss, grads, ref_scores, ref_loss, ref_grads, tag, tols=Non
     if grads is not None:
         worst = 0.0
         for k, g in ref_grads.items():
-            e = rel_err(grads[k], g)
-            worst = max(worst, e)
-            assert e <= (tols[k] if tols else GRAD_TOL), (tag, k, e)
-        print(f"{tag}: worst grad rel {worst:.2e}")
+            e, t = rel_err(grads[k], g), (tols[k] if tols else GRAD_TOL)
+            if t > GRAD_TOL:  # a bar relaxed to the fp32 oracle's own noise is always shown
+                print(f"  grad {k}: err {e:.2e} tol {t:.2e} (4 x oracle-vs-fp64 noise)")
+            worst = max(worst, e / t)
+            assert e <= t, (tag, k, e, t)
+        print(f"{tag}: worst gradient error / tolerance {worst:.2f}")
 
 
 @pytest.mark.parametrize("name", ["nrms_tiny", "nrms_mind", "nrms_b8"])
