@@ -244,6 +244,24 @@ static int make_tmap_f32(CUtensorMap* m, const float* base, unsigned long long c
                 (int)r, cols, rows, ld);
   return NRL_OK;
 }
+// fp32 operand boxes of the staged attention kernels: element (col, s, b) lives at
+// base + (s * seq_stride + b * batch_stride) * ld + col; box = [1][S][box_cols], no swizzle.
+static int make_tmap_attn(CUtensorMap* m, const float* base, unsigned long long cols, unsigned long long ld,
+                          unsigned long long S, long long seq_stride, unsigned long long NB, long long batch_stride,
+                          unsigned box_cols) {
+  cuuint64_t gdim[3] = {cols, S, NB};
+  cuuint64_t gstr[2] = {(cuuint64_t)seq_stride * ld * sizeof(float), (cuuint64_t)batch_stride * ld * sizeof(float)};
+  cuuint32_t box[3] = {box_cols, (cuuint32_t)S, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_dev.encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(NRL_ERR_CUDA, "cuTensorMapEncodeTiled(attention operand) failed (%d): cols=%llu ld=%llu S=%llu NB=%llu",
+                (int)r, cols, ld, S, NB);
+  return NRL_OK;
+}
+
 // split-plane bf16 sink [planes][rows][pitch]: 32 x 32 x planes boxes, SWIZZLE_64B staging
 static int make_tmap_planes(CUtensorMap* m, const bf16* base, unsigned long long cols,
                             unsigned long long rows, unsigned long long pitch, int planes) {
@@ -286,6 +304,8 @@ static int launch_gemm(const Ctx& c, GemmParams& p, const CUtensorMap& ta, const
   }
   p.epi_buf_bytes = (sk.f32 && sk.sp) ? 8192 : 4096;
   p.epi_bufs = 1;
+  static const int epi_dbg = [] { const char* e = getenv("NRL_EPI_DEBUG"); return e ? atoi(e) : 0; }();
+  p.dbg = epi_dbg;  // timing experiments only: results are wrong when != 0
   if (p.pair) {  // CTA pairs (cta_group::2): each CTA stages its 128 rows of A and half of the B tile
     int half_b = p.mn_major ? (p.BN / 2 + 63) / 64 * 8192 : p.BN / 2 * 128;
     if (p.fuse_n) half_b += (((p.n_extent - p.BN + 15) & ~15) / 2 + 63) / 64 * 8192;  // boxes of the second n-tile
@@ -416,17 +436,22 @@ static GemmEpi epi_none() {
 // ----------------------------------------------------------------------------------------
 // small launch helpers
 // ----------------------------------------------------------------------------------------
-static int pack_weights(const Ctx& c, const Dims& d, const nrl_block_params* p, BlockWs& w) {
-  const int tp = c.two_planes() ? 1 : 0;
-  pack_weight_kernel<<<grid_for(3ll * d.E * d.Ep + (long long)d.E * d.P3, 256, 4096), 256, 0, c.stream>>>(
-      p->in_proj_weight, p->in_proj_bias, 3 * d.E, d.E, d.Ep, d.P3, w.win_f, w.win_t, tp);
-  LAUNCH_CHECK("pack_weight(in_proj)");
-  pack_weight_kernel<<<grid_for(2ll * d.E * d.Ep, 256, 4096), 256, 0, c.stream>>>(
-      p->out_proj_weight, p->out_proj_bias, d.E, d.E, d.Ep, d.Ep, w.wout_f, w.wout_t, tp);
-  LAUNCH_CHECK("pack_weight(out_proj)");
-  pack_weight_kernel<<<grid_for((long long)d.Q * d.Ep + (long long)d.E * d.Qp, 256, 4096), 256, 0, c.stream>>>(
-      p->add_weight, p->add_bias, d.Q, d.E, d.Ep, d.Qp, w.wadd_f, w.wadd_t, tp);
-  LAUNCH_CHECK("pack_weight(additive)");
+static void pack_jobs(const Dims& d, const nrl_block_params* p, BlockWs& w, PackJob* j) {
+  j[0] = PackJob{p->in_proj_weight, p->in_proj_bias, 3 * d.E, d.E, d.Ep, d.P3, w.win_f, w.win_t};
+  j[1] = PackJob{p->out_proj_weight, p->out_proj_bias, d.E, d.E, d.Ep, d.Ep, w.wout_f, w.wout_t};
+  j[2] = PackJob{p->add_weight, p->add_bias, d.Q, d.E, d.Ep, d.Qp, w.wadd_f, w.wadd_t};
+}
+// bf16 hi / lo operand copies of the weights of one block (p2 == nullptr) or two blocks, ONE launch
+static int pack_weights(const Ctx& c, const Dims& d, const nrl_block_params* p, BlockWs& w,
+                        const nrl_block_params* p2 = nullptr, BlockWs* w2 = nullptr) {
+  PackJobs jobs;
+  memset(&jobs, 0, sizeof(jobs));
+  pack_jobs(d, p, w, jobs.j);
+  if (p2) pack_jobs(d, p2, *w2, jobs.j + 3);
+  const long long biggest = 3ll * d.E * d.Ep + (long long)d.E * d.P3;
+  pack_weights_multi_kernel<<<dim3((unsigned)grid_for(biggest, 256, 1024), p2 ? 6 : 3), 256, 0, c.stream>>>(
+      jobs, c.two_planes() ? 1 : 0);
+  LAUNCH_CHECK("pack_weights");
   return NRL_OK;
 }
 
@@ -438,6 +463,20 @@ constexpr int ATTN_FWD_SMEM_BUDGET = 110 * 1024;
 constexpr int ATTN_BWD_SMEM_BUDGET = 100 * 1024;
 
 constexpr int ATTN_S32_SMEM_BUDGET = 96 * 1024;
+constexpr int ATTN_TMA_SMEM_MAX = 112 * 1024;  // two stages of four [32][168] fp32 boxes + barriers
+
+// NRL_ATTN_TMA=0 keeps the direct (operands straight from global memory) S <= 32 kernels: A/B runs
+static bool attn_use_tma() {
+  static const bool v = [] { const char* e = getenv("NRL_ATTN_TMA"); return !(e && e[0] == '0'); }();
+  return v;
+}
+// shared memory of the staged kernels (nt = 3 forward, 4 backward), 0 if the shape does not qualify
+static int attn_tma_smem(int nt, int hg, int DH, int S, int E, int ld_other) {
+  const int pitch = attn_tma_pitch(hg * DH);
+  if (pitch > 256 || S > 32 || (E & 3) || (ld_other & 3) || ((hg * DH) & 3)) return 0;
+  const int bytes = 256 + 2 * nt * attn_tma_tile_bytes(S, pitch);
+  return bytes <= ATTN_TMA_SMEM_MAX ? bytes : 0;
+}
 
 // NRL_ATTN_SIMT=1 routes S <= 32 attention to the older fp32 SIMT kernels (profiling A/B only)
 static bool attn_force_simt() {
@@ -452,6 +491,10 @@ static int attn_set_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(attn_bwd_tile_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 ATTN_BWD_SMEM_BUDGET));
   if constexpr (DH <= 32) {
+    CUDA_TRY(cudaFuncSetAttribute(attn_fwd_tma_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  ATTN_TMA_SMEM_MAX));
+    CUDA_TRY(cudaFuncSetAttribute(attn_bwd_tma_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  ATTN_TMA_SMEM_MAX));
     CUDA_TRY(cudaFuncSetAttribute(attn_fwd_s32_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   ATTN_S32_SMEM_BUDGET));
     CUDA_TRY(cudaFuncSetAttribute(attn_bwd_s32_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -472,6 +515,18 @@ template <int DH>
 static void launch_attn_fwd(const Ctx& c, const Dims& d, const AttnGeom& g, const BlockWs& w, long long R) {
   bf16* lo = c.two_planes() ? w.o + R * d.Ep : nullptr;
   if constexpr (DH <= 32) {
+  if (g.S <= 32 && !attn_force_simt() && attn_use_tma()) {  // staged: operands through TMA into shared memory
+    const int hg = attn_head_group(d.H), groups = (d.H + hg - 1) / hg;
+    const int smem = attn_tma_smem(3, hg, DH, g.S, d.E, d.LDQ);
+    CUtensorMap tq;
+    if (smem && make_tmap_attn(&tq, w.qkv, d.LDQ, d.LDQ, g.S, g.seq_stride, g.NB, g.batch_stride,
+                               attn_tma_pitch(hg * DH)) == NRL_OK) {
+      const long long items = (long long)g.NB * groups;
+      attn_fwd_tma_kernel<DH><<<grid_for(items, 1, 3 * g_dev.sm_count), 32 * hg, smem, c.stream>>>(
+          tq, d.E, d.H, hg, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH), w.o, lo, d.Ep, w.lse);
+      return;
+    }
+  }
   if (g.S <= 32 && !attn_force_simt()) {  // warp-level tensor-core path (title tokens)
     const long long items = (long long)g.NB * d.H;
     attn_fwd_mma_kernel<DH><<<(unsigned)((items + 3) / 4), 128, 0, c.stream>>>(
@@ -515,6 +570,19 @@ template <int DH>
 static void launch_attn_bwd(const Ctx& c, const Dims& d, const AttnGeom& g, const BlockWs& w, long long R) {
   bf16* lo = c.two_planes() ? w.dqkv + R * d.P3 : nullptr;
   if constexpr (DH <= 32) {
+  if (g.S <= 32 && !attn_force_simt() && attn_use_tma()) {
+    const int hg = attn_head_group(d.H), groups = (d.H + hg - 1) / hg;
+    const int smem = attn_tma_smem(4, hg, DH, g.S, d.E, d.E);
+    CUtensorMap tq, tdo;
+    if (smem &&
+        make_tmap_attn(&tq, w.qkv, d.LDQ, d.LDQ, g.S, g.seq_stride, g.NB, g.batch_stride, attn_tma_pitch(hg * DH)) == NRL_OK &&
+        make_tmap_attn(&tdo, w.d_o, d.E, d.E, g.S, g.seq_stride, g.NB, g.batch_stride, attn_tma_pitch(hg * DH)) == NRL_OK) {
+      const long long items = (long long)g.NB * groups;
+      attn_bwd_tma_kernel<DH><<<grid_for(items, 1, 2 * g_dev.sm_count), 32 * hg, smem, c.stream>>>(
+          tq, tdo, w.lse, d.E, d.H, hg, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH), w.dqkv, lo, d.P3);
+      return;
+    }
+  }
   if (g.S <= 32 && !attn_force_simt()) {
     const long long items = (long long)g.NB * d.H;
     attn_bwd_mma_kernel<DH><<<(unsigned)((items + 3) / 4), 128, 0, c.stream>>>(
@@ -696,9 +764,9 @@ static int check_common(const void* ws, size_t ws_bytes, size_t need) {
 // ----------------------------------------------------------------------------------------
 static int news_fwd_impl(const Ctx& c, const Dims& d, BlockWs& w, const long long* ids,
                          long long n_news, int L, const float* table, long long V1,
-                         const nrl_block_params* prm, const DropCfg& drop, float* out) {
+                         const nrl_block_params* prm, const DropCfg& drop, float* out, bool packed = false) {
   const long long R = n_news * L;
-  TRY(pack_weights(c, d, prm, w));
+  if (!packed) TRY(pack_weights(c, d, prm, w));
   if (drop.on) {
     dropout_words_kernel<<<grid_for(2 * R * d.MW, 256, 16 * g_dev.sm_count), 256, 0, c.stream>>>(
         drop.seed, drop.thr, R, d.E, d.MW, w.mask0, w.mask1);
@@ -1290,21 +1358,21 @@ static int nrms_impl(const Ctx& c, const Dims& d, NrmsWs& w, const long long* hi
                      int late_fusion, const DropCfg& drop, float* scores, float* loss, int do_backward,
                      nrl_block_grads* ng, nrl_block_grads* ug, float* d_table) {
   const long long N = nh + nc;
-  segment_offsets_kernel<<<(B + 1 + 127) / 128, 128, 0, c.stream>>>(seg_hist, nh, B, w.hist_off, Hmax);
-  LAUNCH_CHECK("segment_offsets(hist)");
-  segment_offsets_kernel<<<(B + 1 + 127) / 128, 128, 0, c.stream>>>(seg_cand, nc, B, w.cand_off, Cmax);
-  LAUNCH_CHECK("segment_offsets(cand)");
+  segment_offsets2_kernel<<<dim3((B + 1 + 127) / 128, 2), 128, 0, c.stream>>>(seg_hist, nh, w.hist_off, Hmax, seg_cand, nc,
+                                                                               w.cand_off, Cmax, B);
+  LAUNCH_CHECK("segment_offsets");
   if (hist_ids != w.ids)
     CUDA_TRY(cudaMemcpyAsync(w.ids, hist_ids, (size_t)nh * L * sizeof(long long), cudaMemcpyDeviceToDevice, c.stream));
   if (cand_ids != w.ids + nh * L)
     CUDA_TRY(cudaMemcpyAsync(w.ids + nh * L, cand_ids, (size_t)nc * L * sizeof(long long), cudaMemcpyDeviceToDevice, c.stream));
   // history and candidate titles share the news encoder: one pass over all N news
-  TRY(news_fwd_impl(c, d, w.news, w.ids, N, L, table, V1, np, drop, w.news_vec));
+  // the operand copies of BOTH blocks' weights in one launch (the user block is packed while nothing depends on it)
+  TRY(pack_weights(c, d, np, w.news, late_fusion ? nullptr : up, late_fusion ? nullptr : &w.user));
+  TRY(news_fwd_impl(c, d, w.news, w.ids, N, L, table, V1, np, drop, w.news_vec, true));
   const float* cand_vec = w.news_vec + nh * d.E;
   const long long Ru = (long long)B * Hmax;
   DropCfg nodrop = make_drop(0.f, 0, 0);
   if (!late_fusion) {
-    TRY(pack_weights(c, d, up, w.user));
     dense_scatter_kernel<<<grid_for(Ru, 1, 1 << 20), 128, 0, c.stream>>>(
         w.news_vec, w.hist_off, B, Hmax, d.E, d.Ep, nullptr, w.user.x,
         c.two_planes() ? w.user.x + Ru * d.Ep : nullptr);
@@ -1314,27 +1382,19 @@ static int nrms_impl(const Ctx& c, const Dims& d, NrmsWs& w, const long long* hi
     late_fusion_fwd_kernel<<<B, 128, 0, c.stream>>>(w.news_vec, w.hist_off, B, d.E, w.user_vec);
     LAUNCH_CHECK("late_fusion_fwd");
   }
-  {
-    const long long warps = (long long)B * Cmax;
-    score_fwd_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, c.stream>>>(w.user_vec, cand_vec, w.cand_off, B,
-                                                                        Cmax, d.E, scores);
-    LAUNCH_CHECK("score_fwd");
-  }
-  if (loss) {
-    CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(float), c.stream));
-    ce_fwd_kernel<<<(B + 3) / 4, 128, 0, c.stream>>>(scores, labels, w.cand_off, B, Cmax, nullptr, loss, nullptr);
-    LAUNCH_CHECK("ce_fwd");
-  }
+  if (do_backward && (!ng || (!late_fusion && !ug)))
+    return fail(NRL_ERR_INVALID_ARG, "backward requested without gradient buffers");
+  if (loss) CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(float), c.stream));
+  if (do_backward)
+    // every row is overwritten below for well-formed segment ids; rows of malformed input (flagged by the device-side
+    // checks) must not carry stale workspace bytes into the table gradient
+    CUDA_TRY(cudaMemsetAsync(w.d_news, 0, (size_t)N * d.E * sizeof(float), c.stream));
+  // scorer + soft-target CE (+ their backward) in one launch: CTA b owns impression b
+  score_loss_kernel<<<B, 128, 2 * (size_t)Cmax * sizeof(float), c.stream>>>(
+      w.user_vec, cand_vec, labels, w.cand_off, B, Cmax, d.E, scores, loss, do_backward ? w.d_scores : nullptr,
+      w.d_user, w.d_news + nh * d.E);
+  LAUNCH_CHECK("score_loss");
   if (!do_backward) return NRL_OK;
-  if (!ng || (!late_fusion && !ug)) return fail(NRL_ERR_INVALID_ARG, "backward requested without gradient buffers");
-  ce_bwd_kernel<<<(B + 3) / 4, 128, 0, c.stream>>>(scores, labels, w.cand_off, B, Cmax, nullptr, 1.0f, w.d_scores);
-  LAUNCH_CHECK("ce_bwd");
-  // every row is overwritten below for well-formed segment ids; rows of malformed input (flagged by the device-side
-  // checks) must not carry stale workspace bytes into the table gradient
-  CUDA_TRY(cudaMemsetAsync(w.d_news, 0, (size_t)N * d.E * sizeof(float), c.stream));
-  score_bwd_kernel<<<B, 128, 0, c.stream>>>(w.d_scores, w.user_vec, cand_vec, w.cand_off, B, Cmax, d.E,
-                                            w.d_user, w.d_news + nh * d.E);
-  LAUNCH_CHECK("score_bwd");
   if (!late_fusion) {
     TRY(block_backward(c, d, w.user, Ru, user_geom(B, Hmax, 0), B, Hmax, up, nodrop, nodrop, w.d_user, ug));
     dim3 grid(Hmax, B < 65535 ? B : 65535);

@@ -240,6 +240,7 @@ __device__ __forceinline__ void store_acc_split(const float (&c)[2][4][4], float
 // Global: matrix m of the item lives at base[m] + r * stride[m] (fp32 rows); rows >= S read as 0.
 template <int DH>
 struct GmemSrc {
+  static constexpr bool kReload = false;
   const float* base[4];
   long long stride[4];
   int S;
@@ -251,11 +252,16 @@ struct GmemSrc {
   }
 };
 // ---- one (batch item, head) problem, forward ----------------------------------------------------
-template <int DH, class Src>
+struct NoRelease {
+  __device__ __forceinline__ void operator()() const {}
+};
+// `release()` is called once, right after the last operand fragment has been read from `src` (the staged kernels
+// hand the shared-memory stage back to the TMA producer there).
+template <int DH, class Src, class Release = NoRelease>
 __device__ __forceinline__ void attn_fwd_item(const Src& src, int E, int heads, int S, long long seq_stride,
                                               long long batch_stride, float scale, int b, int h,
                                               __nv_bfloat16* __restrict__ o_hi, __nv_bfloat16* __restrict__ o_lo,
-                                              int ep, float* __restrict__ lse, int lane) {
+                                              int ep, float* __restrict__ lse, int lane, Release release = Release()) {
   constexpr int KS = (DH + 15) / 16;  // k-steps over the head dim
   constexpr int ND = (DH + 7) / 8;    // 8-column blocks of the head dim
   const int g = lane >> 2, tg = lane & 3;
@@ -305,6 +311,7 @@ __device__ __forceinline__ void attn_fwd_item(const Src& src, int E, int heads, 
   acc_to_blocks(p, s);
   Blk v;
   src.load(v, 2, 1.f, g, tg);
+  release();
   float o[2][4][4];
 #pragma unroll
   for (int i = 0; i < 2; ++i)
@@ -337,11 +344,12 @@ __device__ __forceinline__ void attn_fwd_item(const Src& src, int E, int heads, 
 // ---- one (batch item, head) problem, backward ---------------------------------------------------
 // P is recomputed from Q, K and the saved log-sum-exp; D = rowsum(P * dP).  Writes dQ | dK | dV as
 // split planes [2][R][p3].
-template <int DH, class Src>
+template <int DH, class Src, class Release = NoRelease>
 __device__ __forceinline__ void attn_bwd_item(const Src& src, const float* __restrict__ lse, int E, int heads,
                                               int S, long long seq_stride, long long batch_stride, float scale,
                                               int b, int h, __nv_bfloat16* __restrict__ g_hi,
-                                              __nv_bfloat16* __restrict__ g_lo, int p3, int lane) {
+                                              __nv_bfloat16* __restrict__ g_lo, int p3, int lane,
+                                              Release release = Release()) {
   constexpr int KS = (DH + 15) / 16;
   constexpr int ND = (DH + 7) / 8;
   const int g = lane >> 2, tg = lane & 3;
@@ -350,15 +358,16 @@ __device__ __forceinline__ void attn_bwd_item(const Src& src, const float* __res
 #pragma unroll
   for (int rb = 0; rb < 4; ++rb) grow[rb] = (long long)(8 * rb + g) * seq_stride + (long long)b * batch_stride;
 
+  // Src::kReload (operands staged in shared memory): fragments are re-read where they are needed again instead
+  // of being kept in registers across the whole item (four operand blocks = 128 registers), and the stage is
+  // released at the end; otherwise (operands in global memory) everything is loaded once, up front.
+  constexpr bool kReload = Src::kReload;
   Blk q, k, v, go;
   src.load(q, 0, scale * NRL_LOG2E, g, tg);  // Qs = Q * scale * log2(e)
   src.load(k, 1, 1.f, g, tg);
-  src.load(v, 2, 1.f, g, tg);
-  src.load(go, 3, 1.f, g, tg);
   float lse2[4];
 #pragma unroll
   for (int rb = 0; rb < 4; ++rb) lse2[rb] = (8 * rb + g < S) ? src.lse2(lse, grow[rb], heads, h, 8 * rb + g) : 0.f;
-
   float s[2][4][4], dp[2][4][4];
 #pragma unroll
   for (int i = 0; i < 2; ++i)
@@ -366,7 +375,16 @@ __device__ __forceinline__ void attn_bwd_item(const Src& src, const float* __res
     for (int j = 0; j < 4; ++j)
 #pragma unroll
       for (int c = 0; c < 4; ++c) { s[i][j][c] = 0.f; dp[i][j][c] = 0.f; }
+  if (!kReload) {
+    src.load(v, 2, 1.f, g, tg);
+    src.load(go, 3, 1.f, g, tg);
+    release();
+  }
   mma_nt<KS, 4>(s, q, k, three);    // S (log2 domain)  [t][u]
+  if (kReload) {
+    src.load(v, 2, 1.f, g, tg);
+    src.load(go, 3, 1.f, g, tg);
+  }
   mma_nt<KS, 4>(dp, go, v, three);  // dP = dO V^T      [t][u]
 
   // P = 2^(S - lse2), D_t = sum_u P dP, dS = P (dP - D)   (natural-domain gradient of the scaled scores)
@@ -408,13 +426,19 @@ __device__ __forceinline__ void attn_bwd_item(const Src& src, const float* __res
   };
   // dQ = scale * dS K
   zero();
+  if (kReload) src.load(k, 1, 1.f, g, tg);
   mma_nn<ND>(acc, ds, k, three);
   store_acc_split<DH, ND>(acc, scale, scale, scale, scale, g_hi, g_lo, p3, grow, S, h * DH, g, tg);
   // dK = scale * dS^T Q = ln2 * dS^T Qs ;  dV = P^T dO
   zero();
+  if (kReload) src.load(q, 0, scale * NRL_LOG2E, g, tg);
   mma_tn<ND>(acc, ds, q, three);
   store_acc_split<DH, ND>(acc, NRL_LN2, NRL_LN2, NRL_LN2, NRL_LN2, g_hi, g_lo, p3, grow, S, E + h * DH, g, tg);
   zero();
+  if (kReload) {
+    src.load(go, 3, 1.f, g, tg);
+    release();
+  }
   mma_tn<ND>(acc, pb, go, three);
   store_acc_split<DH, ND>(acc, 1.f, 1.f, 1.f, 1.f, g_hi, g_lo, p3, grow, S, 2 * E + h * DH, g, tg);
 
@@ -465,6 +489,189 @@ attn_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o
   src.base[3] = d_o + (long long)b * batch_stride * ld_do + h * DH;
   src.stride[3] = seq_stride * ld_do;
   attn_bwd_item<DH>(src, lse, E, heads, S, seq_stride, batch_stride, scale, b, h, g_hi, g_lo, p3, lane);
+}
+
+// ---- staged kernels: operands arrive in shared memory through TMA ------------------------------------
+// The direct kernels above read four 30 x 20 fp32 slices per warp as 80-byte row segments and wait for them
+// (ncu: 40 % of the stall samples are long-scoreboard, 18 % of the instructions are address arithmetic).  Here
+// a CTA owns one (batch item, group of HG heads) at a time: ONE elected thread asks the TMA unit for the
+// [S rows] x [HG * DH columns] boxes of Q, K, V (and dO) -- whole 400-byte row segments, full DRAM bursts --
+// of the item AFTER the next while the HG warps (one head each) compute the current one from shared memory;
+// two stages, one mbarrier each.  The geometry (which rows form a sequence) lives in the tensor map, so the
+// same kernel serves the title encoder (sequence = the tokens of a title) and any other (seq_stride,
+// batch_stride) layout with S <= 32.
+//   box = [S][pitch] fp32 with pitch = HG * DH rounded up so that pitch % 32 == 8: the 64-bit fragment loads
+//   of a half-warp (rows g = 0..3, columns 2 tg) then hit 32 distinct banks.  The extra columns are the next
+//   head group's (or zero fill past the tensor edge) and are never used.
+struct SmemSrc {
+  static constexpr bool kReload = true;
+  const float* tile[4];  // shared-memory boxes of this stage: Q, K, V, dO
+  int pitch, col0, S;    // col0 = (head within the group) * DH
+  template <int DH>
+  __device__ __forceinline__ void load_t(Blk& m, int which, float mul, int g, int tg) const {
+    const float* base = tile[which] + col0;
+#pragma unroll
+    for (int rb = 0; rb < 4; ++rb) {
+      const int r = 8 * rb + g;
+      const bool rok = r < S;
+      const float* rp = base + (rok ? r : 0) * pitch;
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) {
+        if (8 * cb >= DH) {
+          m.h[rb][cb] = 0u; m.l[rb][cb] = 0u;
+          continue;
+        }
+        const int c = 8 * cb + 2 * tg;
+        float2 v = make_float2(0.f, 0.f);
+        if (rok && c < DH) v = *reinterpret_cast<const float2*>(rp + c);
+        split_pack2(v.x * mul, v.y * mul, m.h[rb][cb], m.l[rb][cb]);
+      }
+    }
+  }
+};
+template <int DH>
+struct SmemSrcT : SmemSrc {
+  __device__ __forceinline__ void load(Blk& m, int which, float mul, int g, int tg) const {
+    this->template load_t<DH>(m, which, mul, g, tg);
+  }
+  __device__ __forceinline__ float lse2(const float* lse, long long grow, int heads, int h, int /*r*/) const {
+    return __ldg(lse + grow * heads + h) * NRL_LOG2E;
+  }
+};
+
+constexpr int ATTN_TMA_MAX_HG = 5;
+__host__ __device__ constexpr int attn_tma_pitch(int cols) {  // smallest p >= cols with p % 32 == 8
+  return cols + ((8 - cols % 32) + 32) % 32;
+}
+__host__ __device__ constexpr int attn_tma_tile_bytes(int S, int pitch) {  // TMA destinations are 128-byte aligned
+  return (S * pitch * 4 + 127) / 128 * 128;
+}
+
+// NT = number of operand tensors per item (3 forward: Q K V; 4 backward: + dO).
+// Items: b-major, head group fastest; item -> (b = item / groups, grp = item % groups).
+template <int NT>
+struct AttnStage {
+  uint32_t smem_base, full_bar;  // shared-space addresses
+  int tile_bytes;
+  __device__ __forceinline__ uint32_t tile(int stage, int t) const {
+    return smem_base + (uint32_t)((stage * NT + t) * tile_bytes);
+  }
+  // issued by ONE thread
+  __device__ __forceinline__ void issue(int stage, const CUtensorMap* tmQKV, const CUtensorMap* tmDO, long long item,
+                                        int groups, int hg, int DH, int E) const {
+    const int b = (int)(item / groups), grp = (int)(item % groups);
+    const uint32_t bar = full_bar + 8u * (uint32_t)stage;
+    mbar_expect_tx(bar, (uint32_t)(NT * tile_bytes_payload));
+#pragma unroll
+    for (int t = 0; t < 3; ++t) tma_load_3d(tile(stage, t), tmQKV, bar, t * E + grp * hg * DH, 0, b);
+    if (NT == 4) tma_load_3d(tile(stage, 3), tmDO, bar, grp * hg * DH, 0, b);
+  }
+  int tile_bytes_payload;  // S * pitch * 4 (what one box transfers)
+};
+
+template <int DH>
+__global__ void __launch_bounds__(32 * ATTN_TMA_MAX_HG, 3)
+attn_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmQKV, int E, int heads, int hg, int S, long long seq_stride,
+                    int NB, long long batch_stride, float scale, __nv_bfloat16* __restrict__ o_hi,
+                    __nv_bfloat16* __restrict__ o_lo, int ep, float* __restrict__ lse) {
+  extern __shared__ uint8_t attn_smem_raw[];
+  const uint32_t base = (smem_u32(attn_smem_raw) + 127u) & ~127u;
+  const int pitch = attn_tma_pitch(hg * DH);
+  AttnStage<3> st;
+  st.tile_bytes = attn_tma_tile_bytes(S, pitch);
+  st.tile_bytes_payload = S * pitch * 4;
+  st.full_bar = base;
+  st.smem_base = base + 128u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int groups = (heads + hg - 1) / hg;
+  const long long items = (long long)NB * groups;
+  if (threadIdx.x == 0) {
+    mbar_init(st.full_bar, 1);
+    mbar_init(st.full_bar + 8u, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmQKV);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if ((long long)blockIdx.x < items) st.issue(0, &tmQKV, nullptr, blockIdx.x, groups, hg, DH, E);
+    if ((long long)blockIdx.x + gridDim.x < items) st.issue(1, &tmQKV, nullptr, (long long)blockIdx.x + gridDim.x, groups, hg, DH, E);
+  }
+  const uint8_t* gen = attn_smem_raw + (st.smem_base - smem_u32(attn_smem_raw));
+  int i = 0;
+  for (long long item = blockIdx.x; item < items; item += gridDim.x, ++i) {
+    const int stage = i & 1;
+    mbar_wait(st.full_bar + 8u * (uint32_t)stage, (uint32_t)((i >> 1) & 1));
+    const int b = (int)(item / groups), grp = (int)(item % groups);
+    const int h = grp * hg + warp;
+    SmemSrcT<DH> src;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) src.tile[t] = reinterpret_cast<const float*>(gen + (size_t)(stage * 3 + t) * st.tile_bytes);
+    src.tile[3] = nullptr;
+    src.pitch = pitch; src.col0 = warp * DH; src.S = S;
+    const long long nxt = item + 2ll * gridDim.x;
+    auto release = [&]() {
+      __syncthreads();  // every warp has its fragments in registers: the stage may be overwritten
+      if (threadIdx.x == 0 && nxt < items) st.issue(stage, &tmQKV, nullptr, nxt, groups, hg, DH, E);
+    };
+    if (warp < hg && h < heads) {
+      attn_fwd_item<DH>(src, E, heads, S, seq_stride, batch_stride, scale, b, h, o_hi, o_lo, ep, lse, lane, release);
+    } else {
+      release();
+    }
+  }
+}
+
+template <int DH>
+__global__ void __launch_bounds__(32 * ATTN_TMA_MAX_HG, 2)
+attn_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                    const float* __restrict__ lse, int E, int heads, int hg, int S, long long seq_stride, int NB,
+                    long long batch_stride, float scale, __nv_bfloat16* __restrict__ g_hi,
+                    __nv_bfloat16* __restrict__ g_lo, int p3) {
+  extern __shared__ uint8_t attn_smem_raw[];
+  const uint32_t base = (smem_u32(attn_smem_raw) + 127u) & ~127u;
+  const int pitch = attn_tma_pitch(hg * DH);
+  AttnStage<4> st;
+  st.tile_bytes = attn_tma_tile_bytes(S, pitch);
+  st.tile_bytes_payload = S * pitch * 4;
+  st.full_bar = base;
+  st.smem_base = base + 128u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int groups = (heads + hg - 1) / hg;
+  const long long items = (long long)NB * groups;
+  if (threadIdx.x == 0) {
+    mbar_init(st.full_bar, 1);
+    mbar_init(st.full_bar + 8u, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmDO);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if ((long long)blockIdx.x < items) st.issue(0, &tmQKV, &tmDO, blockIdx.x, groups, hg, DH, E);
+    if ((long long)blockIdx.x + gridDim.x < items) st.issue(1, &tmQKV, &tmDO, (long long)blockIdx.x + gridDim.x, groups, hg, DH, E);
+  }
+  const uint8_t* gen = attn_smem_raw + (st.smem_base - smem_u32(attn_smem_raw));
+  int i = 0;
+  for (long long item = blockIdx.x; item < items; item += gridDim.x, ++i) {
+    const int stage = i & 1;
+    mbar_wait(st.full_bar + 8u * (uint32_t)stage, (uint32_t)((i >> 1) & 1));
+    const int b = (int)(item / groups), grp = (int)(item % groups);
+    const int h = grp * hg + warp;
+    SmemSrcT<DH> src;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) src.tile[t] = reinterpret_cast<const float*>(gen + (size_t)(stage * 4 + t) * st.tile_bytes);
+    src.pitch = pitch; src.col0 = warp * DH; src.S = S;
+    const long long nxt = item + 2ll * gridDim.x;
+    auto release = [&]() {
+      __syncthreads();
+      if (threadIdx.x == 0 && nxt < items) st.issue(stage, &tmQKV, &tmDO, nxt, groups, hg, DH, E);
+    };
+    if (warp < hg && h < heads) {
+      attn_bwd_item<DH>(src, lse, E, heads, S, seq_stride, batch_stride, scale, b, h, g_hi, g_lo, p3, lane, release);
+    } else {
+      release();
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -88,6 +88,41 @@ __global__ void pack_weight_kernel(const float* __restrict__ W, const float* __r
   }
 }
 
+// All weight matrices of one or two MHSA + additive blocks in ONE launch (blockIdx.y = job): the step is a chain of
+// ~45 dependent launches, and six 4-microsecond packing kernels are 1 % of it.
+struct PackJob {
+  const float* W; const float* bias;
+  int n_out, k_in, kp, np;
+  __nv_bfloat16 *wf, *wt;
+};
+struct PackJobs {
+  PackJob j[6];
+};
+__global__ void pack_weights_multi_kernel(const PackJobs jobs, int two_planes) {
+  const PackJob& q = jobs.j[blockIdx.y];
+  const long long nf = (long long)q.n_out * q.kp, nt = (long long)q.k_in * q.np;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nf + nt;
+       i += (long long)gridDim.x * blockDim.x) {
+    float x;
+    __nv_bfloat16* dst;
+    long long plane_stride, off;
+    if (i < nf) {
+      int n = (int)(i / q.kp), k = (int)(i % q.kp);
+      x = k < q.k_in ? q.W[(long long)n * q.k_in + k] : (k == q.k_in && q.bias ? q.bias[n] : 0.f);
+      dst = q.wf; plane_stride = nf; off = i;
+    } else {
+      long long j = i - nf;
+      int k = (int)(j / q.np), n = (int)(j % q.np);
+      x = n < q.n_out ? q.W[(long long)n * q.k_in + k] : 0.f;
+      dst = q.wt; plane_stride = nt; off = j;
+    }
+    __nv_bfloat16 h, l;
+    split_bf16(x, h, l);
+    dst[off] = h;
+    if (two_planes) dst[plane_stride + off] = l;
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // a2/a3: embedding gather (+ dropout site 0) -> split planes [2][R][ep], ones column at E.
 // One warp per token row; rows of the table are 16-byte aligned when E % 4 == 0.
@@ -1220,7 +1255,11 @@ pool_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ Y,
             da_hi[(r0 + t0 + u) * qp + j] = hh;
             if (da_lo) da_lo[(r0 + t0 + u) * qp + j] = ll;
             aq += sd * a[u];
-            ab += v;
+            // db_j = sum_r ds_r q_j (1 - a_rj^2) = -q_j sum_r ds_r a_rj^2: sum_t ds_t = 0 within every softmax
+            // group EXACTLY (ds_t = w_t (dw_t - sum_u w_u dw_u), sum_t w_t = 1), so the "1" part only contributes
+            // its own fp32 rounding noise -- which dominates this gradient when the rows of a group resemble each
+            // other (a_rj^2 nearly constant over r: the result is then a second cancellation on top of the first)
+            ab -= sd * qj * (a[u] * a[u]);
           }
         }
       }
@@ -1265,6 +1304,37 @@ __global__ void segment_offsets_kernel(const long long* __restrict__ seg, long l
       if (l2 - lo > max_count) dev_error(DEV_ERR_SEGMENT_LEN);
     }
   }
+}
+
+// history and candidate offsets of one batch in one launch (blockIdx.y = 0 / 1)
+__device__ __forceinline__ void segment_offsets_body(const long long* __restrict__ seg, long long n, int B,
+                                                     int* __restrict__ off, int max_count, int b) {
+  if (b > B) return;
+  long long lo = 0, hi = n;
+  while (lo < hi) {
+    long long mid = (lo + hi) >> 1;
+    if (seg[mid] < b) lo = mid + 1; else hi = mid;
+  }
+  off[b] = (int)lo;
+  if (max_count > 0) {
+    if (b == B && lo != n) dev_error(DEV_ERR_SEGMENT_ID);
+    if (b == 0 && (lo != 0 || (n > 0 && seg[0] < 0))) dev_error(DEV_ERR_SEGMENT_ID);
+    if (b < B) {
+      long long l2 = lo, h2 = n;
+      while (l2 < h2) {
+        long long mid = (l2 + h2) >> 1;
+        if (seg[mid] < b + 1) l2 = mid + 1; else h2 = mid;
+      }
+      if (l2 - lo > max_count) dev_error(DEV_ERR_SEGMENT_LEN);
+    }
+  }
+}
+__global__ void segment_offsets2_kernel(const long long* __restrict__ seg0, long long n0, int* __restrict__ off0,
+                                        int max0, const long long* __restrict__ seg1, long long n1,
+                                        int* __restrict__ off1, int max1, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (blockIdx.y == 0) segment_offsets_body(seg0, n0, B, off0, max0, b);
+  else segment_offsets_body(seg1, n1, B, off1, max1, b);
 }
 
 __global__ void dense_scatter_kernel(const float* __restrict__ x, const int* __restrict__ off,
@@ -1415,6 +1485,75 @@ __global__ void ce_bwd_kernel(const float* __restrict__ scores, const float* __r
   }
 }
 
+// a11 + a12 (+ their backward) in ONE launch for the fused step: CTA b scores impression b's candidates, takes the
+// soft-target CE of the padded row and, when d_scores is given, goes straight on to d_scores, d_user and d_cand --
+// the four kernels above are each a few microseconds of launch latency on a dependent chain.  Same arithmetic, same
+// order of operations per row as score_fwd / ce_fwd / ce_bwd / score_bwd.  Dynamic smem: 2 * C floats.
+__global__ void __launch_bounds__(128)
+score_loss_kernel(const float* __restrict__ user, const float* __restrict__ cand, const float* __restrict__ labels,
+                  const int* __restrict__ off, int B, int C, int E, float* __restrict__ scores,
+                  float* __restrict__ loss_mean, float* __restrict__ d_scores, float* __restrict__ d_user,
+                  float* __restrict__ d_cand) {
+  extern __shared__ float sl_smem[];
+  float* s_sc = sl_smem;       // [C] scores of this row
+  float* s_ds = sl_smem + C;   // [C] d loss / d scores
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int cnt = min(off[b + 1] - off[b], C);
+  const float* u = user + (long long)b * E;
+  for (int c = warp; c < C; c += nw) {
+    float acc = 0.f;
+    if (c < cnt) {
+      const float* n = cand + (long long)(off[b] + c) * E;
+      for (int i = lane; i < E; i += 32) acc += u[i] * n[i];
+      acc = warp_sum(acc);
+    }
+    if (lane == 0) {
+      s_sc[c] = acc;
+      scores[(long long)b * C + c] = acc;
+    }
+  }
+  __syncthreads();
+  if (!loss_mean && !d_scores) return;
+  if (warp == 0) {
+    float mx = -INFINITY;
+    for (int c = lane; c < C; c += 32) mx = fmaxf(mx, s_sc[c]);
+    mx = warp_max(mx);
+    float se = 0.f, sy = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      se += expf(s_sc[c] - mx);
+      sy += c < cnt ? labels[off[b] + c] : 0.f;
+    }
+    se = warp_sum(se);
+    sy = warp_sum(sy);
+    const float lz = mx + logf(se);
+    float acc = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float y = c < cnt ? labels[off[b] + c] : 0.f;
+      acc += y * (lz - s_sc[c]);
+      if (d_scores) {
+        const float pr = expf(s_sc[c] - mx) / se;
+        const float ds = (pr * sy - y) / (float)B;
+        s_ds[c] = ds;
+        d_scores[(long long)b * C + c] = ds;
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0 && loss_mean) atomicAdd(loss_mean, acc / (float)B);
+  }
+  if (!d_scores) return;
+  __syncthreads();
+  for (int i = threadIdx.x; i < E; i += blockDim.x) {
+    const float ui = u[i];
+    float acc = 0.f;
+    for (int c = 0; c < cnt; ++c) {
+      const float ds = s_ds[c];
+      acc += ds * cand[(long long)(off[b] + c) * E + i];
+      d_cand[(long long)(off[b] + c) * E + i] = ds * ui;
+    }
+    d_user[(long long)b * E + i] = acc;
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // Embedding gradient: d_table[ids[r]] += dX[r]  (dense [V1, E] table gradient, row 0 = the
 // padding_idx row is skipped so its gradient stays exactly zero, text.py:215-217).
@@ -1461,7 +1600,6 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float*
   for (long long i = tid; i < n4; i += nth) {
     float4 p4 = reinterpret_cast<float4*>(p)[i];
     const float4 g4 = reinterpret_cast<const float4*>(g)[i];
-    if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i];
     {  // sqrt(v) / sqrt_bc2 is kept as a division (torch's formula), not a reciprocal multiply
       float* pp = &p4.x; const float* gg = &g4.x; float* mm = &m4.x; float* vv = &v4.x;
@@ -1479,6 +1617,8 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float*
     reinterpret_cast<float4*>(p)[i] = p4;
     reinterpret_cast<float4*>(m)[i] = m4;
     reinterpret_cast<float4*>(v)[i] = v4;
+    // after every load of the iteration has been issued: a store in between serialises the loads behind it
+    if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (long long i = 4 * n4 + tid; i < n; i += nth) {
     const float gi = g[i] * g_scale;

@@ -34,6 +34,11 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// arrive WITHOUT release semantics: no MEMBAR in front of it.  For barriers that hand over TMEM (tcgen05.ld results
+// already in registers, ordered by tcgen05.fence::before_thread_sync), not generic-proxy memory.
+__device__ __forceinline__ void mbar_arrive_relaxed(uint32_t bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
@@ -211,6 +216,9 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // NOTE: the pair kernel waits with the plain CTA-scope mbar_wait even on barriers signalled from the
 // peer CTA (TMA complete_tx, multicast tcgen05.commit, remote arrive): what those barriers order is
 // async-proxy shared memory and TMEM, guarded by the tcgen05 fences -- an `.acquire.cluster` wait makes
@@ -254,13 +262,16 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
 }
 
 // ------------------------------------------------------------------ dropout RNG
-// Philox4x32-10 keyed by the 64-bit seed; counter = (group index lo, hi, site, 0).  One call
+// Philox4x32 (PHILOX_ROUNDS rounds) keyed by the 64-bit seed; counter = (group index lo, hi, site, 0).  One call
 // yields 128 bits = eight 16-bit uniforms; element e of a site uses group e>>3, slot e&7 and
 // is KEPT iff its uniform >= round(p * 65536).  The same function regenerates the mask in
 // the backward pass, so no mask is ever stored.
 struct Philox4 {
   uint32_t x, y, z, w;
 };
+// Philox4x32 with 7 rounds (the smallest round count of the Random123 family that passes BigCrush; the default
+// 10 adds safety margin a dropout mask does not need): the keep-bit kernels are ALU-bound on exactly these rounds.
+constexpr int PHILOX_ROUNDS = 7;
 __host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) {
 #ifdef __CUDA_ARCH__
   return __umulhi(a, b);
@@ -268,13 +279,13 @@ __host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) {
   return static_cast<uint32_t>((static_cast<uint64_t>(a) * b) >> 32);
 #endif
 }
-__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint64_t seed, uint64_t group,
+__host__ __device__ __forceinline__ Philox4 philox4x32(uint64_t seed, uint64_t group,
                                                           uint32_t site) {
   uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
   uint32_t c0 = static_cast<uint32_t>(group), c1 = static_cast<uint32_t>(group >> 32), c2 = site,
            c3 = 0;
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < PHILOX_ROUNDS; ++r) {
     uint32_t h0 = mulhi32(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
     uint32_t h1 = mulhi32(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
     uint32_t n0 = h1 ^ c1 ^ k0, n1 = l1, n2 = h0 ^ c3 ^ k1, n3 = l0;
@@ -293,7 +304,7 @@ __host__ __device__ __forceinline__ uint32_t drop_threshold(float p) {
 // keep-flag of a single element (generic, slow path)
 __host__ __device__ __forceinline__ bool drop_keep(uint64_t seed, uint32_t site, uint64_t e,
                                                    uint32_t thr) {
-  Philox4 r = philox4x32_10(seed, e >> 3, site);
+  Philox4 r = philox4x32(seed, e >> 3, site);
   return philox_u16(r, static_cast<int>(e & 7)) >= thr;
 }
 
