@@ -346,13 +346,28 @@ def make_trainer(NRMSTrainer, params, dev, prec, world, mode):
         b = {"x_hist": {"title": hb["x_hist"]["title"].to(dev)}, "x_cand": {"title": hb["x_cand"]["title"].to(dev)},
              "batch_hist": hb["batch_hist"].to(dev), "batch_cand": hb["batch_cand"].to(dev), "labels": hb["labels"].to(dev)}
         keep = tr.flat.clone()
-        for _ in range(2):
-            tr.train_step(b, 4, 6, CAND)
+        # probe step 1: forward + backward into the (clean) gradient buffer, keep a copy of THIS rank's gradients,
+        # then the fused exchange; the result must equal torch.optim.Adam on the NCCL-averaged gradients
+        from newsreclib_b200 import ops as _ops
+        _ops.nrms_step(b, tr.table, tr.news_block, tr.user_block, tr.dims, B=4, Hmax=6, Cmax=CAND, dropout_p=DROPOUT,
+                       training=True, seed=99 + rank, grads=tr.grad_pack, precision=prec)
+        g_sum = tr.grad.clone()
+        tr._grads_clean = False
+        tr._finish()
+        dist.all_reduce(g_sum, op=dist.ReduceOp.SUM)
+        p_ref, m_ref, v_ref = keep.clone(), torch.zeros_like(keep), torch.zeros_like(keep)
+        _ops.adam_step(p_ref, g_sum, m_ref, v_ref, 1, tr.lr, tr.betas[0], tr.betas[1], tr.eps, grad_scale=1.0 / world)
+        # a parameter whose gradient is pure rounding noise (the key third of in_proj_bias: mathematically zero) moves by
+        # +-lr in either summation order; everything else agrees to fp32 rounding
+        d = (p_ref - tr.flat).abs()
+        adam_ok = float((d > 1e-6).float().mean()) < 2e-3 and float(d.median()) < 1e-7
+        cleared = not bool(tr.grad.any())
+        tr.train_step(b, 4, 6, CAND)  # probe step 2 through the public call
         status = tr.peer_block.status()
         lo, hi = tr.flat.clone(), tr.flat.clone()
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-        ok = status == 0 and torch.equal(lo, hi) and not torch.equal(tr.flat, keep)
+        ok = status == 0 and adam_ok and cleared and torch.equal(lo, hi) and not torch.equal(tr.flat, keep)
         if all_ok(ok):
             tr.flat.copy_(keep)  # back to the initial replica; the exchange epoch keeps counting
             tr.m.zero_()
@@ -360,8 +375,10 @@ def make_trainer(NRMSTrainer, params, dev, prec, world, mode):
             tr.step_count = 0
             torch.cuda.synchronize()
             dist.barrier()
-            return tr, "peer (nrl_exchange_adam_step: reduce-scatter + sharded Adam + all-gather in one kernel over NVLink peer memory)"
-        why = f"probe failed on some rank (here: status {status})"
+            return tr, ("peer (nrl_exchange_adam_step: row-sparse reduce-scatter + sharded Adam + all-gather + zero_grad in one "
+                        "kernel over NVLink peer memory; probe: equals Adam on the NCCL-averaged gradients, replicas bit-identical)")
+        why = (f"probe failed on some rank (here: status {status}, equals NCCL-mean Adam {adam_ok}, gradients cleared "
+               f"{cleared})")
     if mode == "peer":
         raise SystemExit(f"--exchange peer: {why or 'a peer rank failed'}")
     dist.barrier()  # every rank, whether or not its own construction succeeded
@@ -557,10 +574,20 @@ def main():
         if rank == 0 and world > 1 and "exchange_adam" in agg:
             n_flat = trainer.flat.numel()
             ms_x = agg["exchange_adam"][0] / prof_steps
-            link = 4.0 * n_flat * (world - 1) / world
+            dense = 4.0 * n_flat * (world - 1) / world      # new parameters of the owned slice to W-1 peers (and received)
+            # gradients: only the table rows a rank touched cross the links (plus the dense non-embedding parameters)
+            touched = sum(int(torch.unique(torch.cat([hb["x_hist"]["title"].reshape(-1), hb["x_cand"]["title"].reshape(-1)])).numel())
+                          for hb in host_batches) / len(host_batches)
+            n_table = trainer.table.numel()
+            grads = 4.0 * ((n_flat - n_table) + touched * E) * (world - 1) / world
             exchange_info = {"kernel": "exchange_adam", "ms_per_step": round(ms_x, 4),
-                             "nvlink_mbytes_in": round(link / 1e6, 1), "nvlink_mbytes_out": round(link / 1e6, 1),
-                             "achieved_gbs_per_direction": round(link / (ms_x / 1e3) / 1e9, 1),
+                             "nvlink_mbytes_params_per_direction": round(dense / 1e6, 1),
+                             "nvlink_mbytes_grads_per_direction": round(grads / 1e6, 1),
+                             "nvlink_mbytes_grads_if_dense": round(dense / 1e6, 1),
+                             "table_rows_touched_per_rank": round(touched), "table_rows": int(trainer.table.shape[0]),
+                             "achieved_gbs_per_direction": round((dense + grads) / (ms_x / 1e3) / 1e9, 1),
+                             "note": "kernel time includes the local non-zero-row scan (84 MB of HBM reads), the wait for the "
+                                     "slowest rank at the ready barrier and the sharded Adam",
                              "adam_elements_per_rank": n_flat // world}
     except Exception as e:  # never lose the line over a diagnostic
         exchange_info = {"error": repr(e)}

@@ -262,8 +262,10 @@ int nrl_device_status(int* code_host, void* stream);
 typedef struct {
   int world, rank;
   float* params[NRL_MAX_RANKS];              /* flat parameter buffer of every rank ([rank] is local) */
-  const float* grads[NRL_MAX_RANKS];         /* flat gradient buffer of every rank */
+  float* grads[NRL_MAX_RANKS];               /* flat gradient buffer of every rank (cleared by the owner of a slice) */
   unsigned long long* flags[NRL_MAX_RANKS];  /* flag block of every rank */
+  unsigned int* bitmaps[NRL_MAX_RANKS];      /* row-bitmap area of every rank: world x ((sparse_rows + 31) / 32) u32,
+                                                zero once, peer-mapped; NULL when sparse_rows == 0 */
 } nrl_peer_set;
 int nrl_peer_alloc(size_t bytes, void** dev_ptr, unsigned char* handle /* [NRL_IPC_HANDLE_BYTES] */);
 int nrl_peer_free(void* dev_ptr);
@@ -272,12 +274,21 @@ int nrl_peer_close(void* dev_ptr);
 /* One exchange + Adam step over n elements (n % 4 == 0, all buffers 16-byte aligned).  m / v are
  * LOCAL and indexed like the parameters; only the owned slice is read and written.  `epoch` must
  * be the same on all ranks and grow by at least 1 per call (the trainer passes its step count);
- * grad_scale = 1 / world gives DDP's mean.  max_ctas <= 0: 4 CTAs per SM.  timeout_ns == 0: 5 s.
- * All ranks must call it for the same epoch; no other cross-rank wait may sit between. */
+ * grad_scale = 1 / world gives DDP's mean.  max_ctas <= 0: 4 CTAs per SM (never more than fit the
+ * device at once: the grid waits for itself).  timeout_ns == 0: 5 s.
+ * sparse_rows > 0: the first sparse_rows * row_elems elements are a row-sparse gradient (the dense
+ * [V+1, E] embedding gradient, of which a step touches a fraction): each rank publishes which of its rows are
+ * non-zero and all-zero rows never cross the links; the result is bit-identical to the dense exchange.
+ * zero_grads != 0: every gradient element, on every rank, is zero when the kernel ends
+ * (optimizer.zero_grad() folded in: the owner of a slice clears what it has consumed).
+ * A timed-out ready barrier leaves parameters and moments of this rank's slice untouched (one decision
+ * per kernel, not per CTA).  All ranks must call it for the same epoch; no other cross-rank wait may sit
+ * between. */
 int nrl_exchange_adam_step(const nrl_peer_set* peers, float* m, float* v, long long n, float lr,
                            float beta1, float beta2, float eps, long long step,
                            unsigned long long epoch, float grad_scale, int max_ctas,
-                           unsigned long long timeout_ns, void* stream);
+                           unsigned long long timeout_ns, long long sparse_rows, int row_elems,
+                           int zero_grads, void* stream);
 /* Synchronises `stream` and returns the flag block's error word (0 = every barrier completed,
  * 1 / 2 = a ready / done wait timed out: a peer never arrived). */
 int nrl_exchange_status(const unsigned long long* flags_local, unsigned long long* error_host,

@@ -58,7 +58,8 @@ class PeerSet(C.Structure):
     """``nrl_peer_set``: the peer-mapped flat parameter / gradient buffers and flag blocks of every rank."""
 
     _fields_ = [("world", C.c_int), ("rank", C.c_int), ("params", C.c_void_p * MAX_RANKS),
-                ("grads", C.c_void_p * MAX_RANKS), ("flags", C.c_void_p * MAX_RANKS)]
+                ("grads", C.c_void_p * MAX_RANKS), ("flags", C.c_void_p * MAX_RANKS),
+                ("bitmaps", C.c_void_p * MAX_RANKS)]
 
 
 class Dims(C.Structure):
@@ -113,7 +114,8 @@ SIGNATURES = {
     "nrl_peer_free": (_I, [_VP]),
     "nrl_peer_open": (_I, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "nrl_peer_close": (_I, [_VP]),
-    "nrl_exchange_adam_step": (_I, [C.POINTER(PeerSet), _VP, _VP, _LL, _F, _F, _F, _F, _LL, _ULL, _F, _I, _ULL, _VP]),
+    "nrl_exchange_adam_step": (_I, [C.POINTER(PeerSet), _VP, _VP, _LL, _F, _F, _F, _F, _LL, _ULL, _F, _I, _ULL, _LL, _I, _I,
+                                    _VP]),
     "nrl_exchange_status": (_I, [_VP, C.POINTER(_ULL), _VP]),
     "nrl_nrms_ws_bytes": (_SZ, [_LL, _LL, _I, _I, _I, _I, Dims]),
     "nrl_nrms_step": (_I, [_VP, _VP, _VP, _VP, _VP, _LL, _LL, _I, _I, _I, _I, _VP, _LL, _BP, _BP, Dims,

@@ -465,10 +465,13 @@ constexpr int ATTN_BWD_SMEM_BUDGET = 100 * 1024;
 constexpr int ATTN_S32_SMEM_BUDGET = 96 * 1024;
 constexpr int ATTN_TMA_SMEM_MAX = 112 * 1024;  // two stages of four [32][168] fp32 boxes + barriers
 
-// NRL_ATTN_TMA=0 keeps the direct (operands straight from global memory) S <= 32 kernels: A/B runs
-static bool attn_use_tma() {
-  static const bool v = [] { const char* e = getenv("NRL_ATTN_TMA"); return !(e && e[0] == '0'); }();
-  return v;
+// Which S <= 32 kernels take their operands through TMA-staged shared memory.  Measured on B200 at the bench size
+// (profiles/r02_attention.md): forward 0.170 ms staged vs 0.174 direct; backward 0.444 staged vs 0.422 direct (its
+// 168 registers allow only 2 CTAs of 5 warps beside the two 50 KB stages).  Default: forward staged, backward direct.
+// NRL_ATTN_TMA=0 none, =1 both (A/B runs).
+static bool attn_use_tma(bool backward) {
+  static const int v = [] { const char* e = getenv("NRL_ATTN_TMA"); return e ? atoi(e) : -1; }();
+  return v < 0 ? !backward : v != 0;
 }
 // shared memory of the staged kernels (nt = 3 forward, 4 backward), 0 if the shape does not qualify
 static int attn_tma_smem(int nt, int hg, int DH, int S, int E, int ld_other) {
@@ -515,7 +518,7 @@ template <int DH>
 static void launch_attn_fwd(const Ctx& c, const Dims& d, const AttnGeom& g, const BlockWs& w, long long R) {
   bf16* lo = c.two_planes() ? w.o + R * d.Ep : nullptr;
   if constexpr (DH <= 32) {
-  if (g.S <= 32 && !attn_force_simt() && attn_use_tma()) {  // staged: operands through TMA into shared memory
+  if (g.S <= 32 && !attn_force_simt() && attn_use_tma(false)) {  // staged: operands through TMA into shared memory
     const int hg = attn_head_group(d.H), groups = (d.H + hg - 1) / hg;
     const int smem = attn_tma_smem(3, hg, DH, g.S, d.E, d.LDQ);
     CUtensorMap tq;
@@ -570,7 +573,7 @@ template <int DH>
 static void launch_attn_bwd(const Ctx& c, const Dims& d, const AttnGeom& g, const BlockWs& w, long long R) {
   bf16* lo = c.two_planes() ? w.dqkv + R * d.P3 : nullptr;
   if constexpr (DH <= 32) {
-  if (g.S <= 32 && !attn_force_simt() && attn_use_tma()) {
+  if (g.S <= 32 && !attn_force_simt() && attn_use_tma(true)) {
     const int hg = attn_head_group(d.H), groups = (d.H + hg - 1) / hg;
     const int smem = attn_tma_smem(4, hg, DH, g.S, d.E, d.E);
     CUtensorMap tq, tdo;
@@ -1254,7 +1257,8 @@ int nrl_peer_close(void* dev_ptr) {
 
 int nrl_exchange_adam_step(const nrl_peer_set* peers, float* m, float* v, long long n, float lr, float beta1,
                            float beta2, float eps, long long step, unsigned long long epoch, float grad_scale,
-                           int max_ctas, unsigned long long timeout_ns, void* stream) {
+                           int max_ctas, unsigned long long timeout_ns, long long sparse_rows, int row_elems,
+                           int zero_grads, void* stream) {
   if (!peers || !m || !v || n <= 0 || step <= 0 || epoch == 0)
     return fail(NRL_ERR_INVALID_ARG, "nrl_exchange_adam_step: bad argument");
   if (peers->world < 1 || peers->world > NRL_MAX_RANKS || peers->rank < 0 || peers->rank >= peers->world)
@@ -1269,19 +1273,39 @@ int nrl_exchange_adam_step(const nrl_peer_set* peers, float* m, float* v, long l
       return fail(NRL_ERR_INVALID_ARG, "nrl_exchange_adam_step: flag block of rank %d is not 8-byte aligned", r);
   }
   if (align & 15) return fail(NRL_ERR_INVALID_ARG, "nrl_exchange_adam_step: buffers must be 16-byte aligned");
+  SparseCfg sp;
+  sp.rows = 0; sp.row_f4 = 1; sp.bm_words = 0; sp.zero_grads = zero_grads ? 1 : 0;
+  if (sparse_rows > 0 && peers->world > 1) {
+    if (row_elems <= 0 || (row_elems & 3) || sparse_rows * row_elems > n)
+      return fail(NRL_ERR_INVALID_ARG, "nrl_exchange_adam_step: sparse region %lld rows x %d elements does not fit n = %lld "
+                  "(row_elems must be a positive multiple of 4)", sparse_rows, row_elems, n);
+    for (int r = 0; r < peers->world; ++r)
+      if (!peers->bitmaps[r] || (reinterpret_cast<uintptr_t>(peers->bitmaps[r]) & 3))
+        return fail(NRL_ERR_INVALID_ARG, "nrl_exchange_adam_step: rank %d has no row-bitmap area", r);
+    sp.rows = sparse_rows; sp.row_f4 = row_elems / 4; sp.bm_words = (int)((sparse_rows + 31) / 32);
+  }
   TRY(device_init());
   PeerSet ps;
   std::memcpy(&ps, peers, sizeof(ps));
   const double bc1 = 1.0 - std::pow((double)beta1, (double)step);
   const double bc2 = 1.0 - std::pow((double)beta2, (double)step);
   const long long n4 = n / 4, per = (n4 + ps.world - 1) / ps.world;
-  int cap = max_ctas > 0 ? max_ctas : 4 * g_dev.sm_count;
-  const int grid = grid_for(per, 256, cap);
   if (timeout_ns == 0) timeout_ns = 5000000000ull;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define XCHG_LAUNCH(W)                                                                                  \
-  exchange_adam_kernel<W><<<grid, 256, 0, st>>>(ps, m, v, n4, epoch, timeout_ns, lr, beta1, beta2, eps, \
-                                                (float)bc1, (float)std::sqrt(bc2), grad_scale)
+  // every CTA waits for a decision that needs ALL CTAs of the grid to have passed step 0: the grid must be
+  // co-resident (never more CTAs than the device can hold at once)
+#define XCHG_LAUNCH(W)                                                                                       \
+  do {                                                                                                       \
+    int occ = 0;                                                                                             \
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, exchange_adam_kernel<W>, 256, 0));          \
+    if (occ < 1) return fail(NRL_ERR_CUDA, "exchange kernel does not fit an SM");                            \
+    int cap = max_ctas > 0 ? max_ctas : 4 * g_dev.sm_count;                                                  \
+    if (cap > occ * g_dev.sm_count) cap = occ * g_dev.sm_count;                                              \
+    long long work = per > (long long)sp.bm_words * 32 ? per : (long long)sp.bm_words * 32;                  \
+    const int grid = grid_for(work, 256, cap);                                                               \
+    exchange_adam_kernel<W><<<grid, 256, 0, st>>>(ps, m, v, n4, epoch, timeout_ns, lr, beta1, beta2, eps,    \
+                                                  (float)bc1, (float)std::sqrt(bc2), grad_scale, sp);        \
+  } while (0)
   switch (ps.world) {
     case 1: XCHG_LAUNCH(1); break;
     case 2: XCHG_LAUNCH(2); break;

@@ -4,8 +4,10 @@ What Lightning DDP + ``torch.optim.Adam`` do for the reference after every backw
 (``configs/trainer/ddp.yaml``, ``configs/model/nrms.yaml:49-52``: gradient mean over the ranks, then
 Adam on every replica) is ONE kernel per rank here: the flat parameter and gradient buffers of a
 rank live in a ``cudaMalloc`` block that every peer maps over NVLink (CUDA IPC); a rank sums the
-gradients of its 1/world slice by peer loads, runs Adam on that slice and stores the new values
-into every replica; flag barriers in the same peer memory bracket the kernel.  ``torch.distributed``
+gradients of its 1/world slice by peer loads, runs Adam on that slice, stores the new values
+into every replica and clears the gradients it has consumed; flag barriers in the same peer memory bracket the
+kernel.  The embedding-table part of the gradient is row-sparse (a step touches a fraction of the vocabulary):
+every rank publishes one bit per row and all-zero rows never cross the links.  ``torch.distributed``
 is used once, at construction, to pass the 64-byte IPC handles around.
 
 ``slice_bounds`` is the ownership rule of the kernel restated for the host (tests, checkpoint code
@@ -42,8 +44,10 @@ class _DevMem:
 
 
 class PeerBlock:
-    """One rank's peer-mapped block: ``[ params n f32 | grads n f32 | flag block ]`` and the same
-    blocks of all peers opened through their IPC handles."""
+    """One rank's peer-mapped block: ``[ params n f32 | grads n f32 | flag block | row bitmaps ]`` and the same
+    blocks of all peers opened through their IPC handles.  ``sparse_rows`` > 0 declares the first
+    ``sparse_rows * row_elems`` elements a row-sparse gradient (the embedding table) and reserves
+    ``world x ceil(sparse_rows / 32)`` u32 words of bitmap area."""
 
     # two seams for the world_size-2 gloo tests of the construction protocol (tests/test_dist_cpu.py)
     def _device_ctx(self):
@@ -52,7 +56,8 @@ class PeerBlock:
     def _alias(self, ptr: int, nelem: int) -> torch.Tensor:
         return torch.as_tensor(_DevMem(ptr, nelem, "<f4"), device=self.device)
 
-    def __init__(self, n: int, device: torch.device, process_group=None, lib=None) -> None:
+    def __init__(self, n: int, device: torch.device, process_group=None, lib=None, sparse_rows: int = 0,
+                 row_elems: int = 0) -> None:
         lib = lib or _lib.load()
         dist = torch.distributed
         on = dist.is_available() and dist.is_initialized()
@@ -65,7 +70,12 @@ class PeerBlock:
         self.n, self.device = n, torch.device(device)
         self._lib = lib
         self._flag_off = 8 * n
-        nbytes = 8 * n + _lib.FLAG_BYTES
+        if sparse_rows and (row_elems <= 0 or row_elems % 4 or sparse_rows * row_elems > n):
+            raise ValueError("sparse region must be sparse_rows rows of row_elems (multiple of 4) elements inside n")
+        self.sparse_rows, self.row_elems = int(sparse_rows), int(row_elems)
+        self.bm_words = (self.sparse_rows + 31) // 32
+        self._bm_off = self._flag_off + _lib.FLAG_BYTES
+        nbytes = self._bm_off + (4 * self.world * self.bm_words + 15) // 16 * 16
         base, handle = C.c_void_p(), C.create_string_buffer(_lib.IPC_HANDLE_BYTES)
         self.base, self._opened = 0, []
         # A rank that fails (no peer access, IPC not permitted, out of memory) must not leave the others waiting in a
@@ -107,7 +117,8 @@ class PeerBlock:
         self.flat = self._alias(self.base, n)
         self.grad = self._alias(self.base + 4 * n, n)
         self.peer_set = peer_set(self.world, self.rank, [b for b in bases], [b + 4 * n for b in bases],
-                                 [b + self._flag_off for b in bases])
+                                 [b + self._flag_off for b in bases],
+                                 [b + self._bm_off for b in bases] if self.sparse_rows else None)
 
     @property
     def flags_ptr(self) -> int:
@@ -135,18 +146,23 @@ class PeerBlock:
         self.base = 0
 
 
-def peer_set(world: int, rank: int, params: List[int], grads: List[int], flags: List[int]) -> "_lib.PeerSet":
+def peer_set(world: int, rank: int, params: List[int], grads: List[int], flags: List[int],
+             bitmaps: Optional[List[int]] = None) -> "_lib.PeerSet":
     ps = _lib.PeerSet()
     ps.world, ps.rank = int(world), int(rank)
     for r in range(world):
         ps.params[r], ps.grads[r], ps.flags[r] = params[r], grads[r], flags[r]
+        if bitmaps is not None:
+            ps.bitmaps[r] = bitmaps[r]
     return ps
 
 
 def exchange_adam_step(ps: "_lib.PeerSet", m: torch.Tensor, v: torch.Tensor, n: int, step: int, *, lr=1e-4,
                        beta1=0.9, beta2=0.999, eps=1e-8, grad_scale: Optional[float] = None, epoch: Optional[int] = None,
-                       max_ctas: int = 0, timeout_s: float = 5.0, stream: Optional[int] = None) -> None:
-    """Enqueue one fused exchange + Adam step (see ``include/nrl.h``)."""
+                       max_ctas: int = 0, timeout_s: float = 5.0, stream: Optional[int] = None, sparse_rows: int = 0,
+                       row_elems: int = 0, zero_grads: bool = False) -> None:
+    """Enqueue one fused exchange + Adam step (see ``include/nrl.h``).  ``sparse_rows`` / ``row_elems``: the leading
+    row-sparse region (needs ``ps.bitmaps``); ``zero_grads``: leave every gradient buffer cleared."""
     lib = _lib.load()
     for t, name in ((m, "m"), (v, "v")):
         if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or t.numel() < n:
@@ -157,4 +173,5 @@ def exchange_adam_step(ps: "_lib.PeerSet", m: torch.Tensor, v: torch.Tensor, n: 
         stream = torch.cuda.current_stream(m.device).cuda_stream
     _lib.check(lib.nrl_exchange_adam_step(C.byref(ps), m.data_ptr(), v.data_ptr(), n, lr, beta1, beta2, eps, step,
                                           int(epoch if epoch is not None else step), grad_scale, int(max_ctas),
-                                          int(timeout_s * 1e9), stream), "nrl_exchange_adam_step")
+                                          int(timeout_s * 1e9), int(sparse_rows), int(row_elems), int(zero_grads),
+                                          stream), "nrl_exchange_adam_step")

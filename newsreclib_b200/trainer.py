@@ -150,7 +150,11 @@ class NRMSTrainer:
             from .exchange import PeerBlock
 
             def buffers(total):
-                self.peer_block = PeerBlock(total, self.device, process_group)
+                # the embedding table leads the flat buffer: its gradient is row-sparse (a step touches the tokens
+                # of its batch), so the exchange moves only the rows a rank actually touched
+                table = params[self.keys[0]]
+                rows, width = (table.shape[0], table.shape[1]) if table.shape[1] % 4 == 0 else (0, 0)
+                self.peer_block = PeerBlock(total, self.device, process_group, sparse_rows=rows, row_elems=width)
                 return self.peer_block.flat, self.peer_block.grad
         self.fp = FlatParams(params, self.keys, self.device, buffers)
         self.flat, self.grad, self.m, self.v = self.fp.flat, self.fp.grad, self.fp.m, self.fp.v
@@ -221,8 +225,10 @@ class NRMSTrainer:
             self.exchange_epoch += 1  # barrier epoch: never reset, also when step_count is
             exchange_adam_step(self.peer_block.peer_set, self.m, self.v, self.flat.numel(), self.step_count,
                                lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, grad_scale=scale,
-                               epoch=self.exchange_epoch, max_ctas=self.exchange_ctas, timeout_s=self.exchange_timeout_s)
-            self._grads_clean = False  # peers read this rank's gradients until the kernel's done barrier
+                               epoch=self.exchange_epoch, max_ctas=self.exchange_ctas, timeout_s=self.exchange_timeout_s,
+                               sparse_rows=self.peer_block.sparse_rows, row_elems=self.peer_block.row_elems,
+                               zero_grads=True)
+            self._grads_clean = True  # every owner cleared what it consumed, on every rank, before the done barrier
         else:
             # Adam on chunk i overlaps the all-reduce of chunks i+1.. (one chunk = everything when world == 1);
             # the same pass clears the gradient slice it has consumed

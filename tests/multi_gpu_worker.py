@@ -42,6 +42,7 @@ def main() -> None:
         torch.cuda.synchronize()
         if mode == "peer":
             assert tr.peer_block.status() == 0, f"rank {rank}: barrier timeout code {tr.peer_block.status()}"
+            assert not bool(tr.grad.any()), f"rank {rank}: the exchange did not leave the gradient buffer cleared"
         flat = tr.flat.clone()
         gathered = [torch.empty_like(flat) for _ in range(world)]
         dist.all_gather(gathered, flat)

@@ -115,6 +115,77 @@ def test_virtual_ranks_on_one_gpu(world, n):
             assert bool(ms[r][lo:hi].any())
 
 
+@pytest.mark.parametrize("world,rows,width,tail", [(2, 1000, 300, 4 * 211), (4, 777, 300, 4 * 1000), (8, 2500, 64, 8),
+                                                   (3, 95, 300, 4 * 50)])
+def test_virtual_ranks_row_sparse_region(world, rows, width, tail):
+    """The embedding-table part of the gradient is row-sparse: every rank publishes one bit per row of ITS gradient,
+    all-zero rows are never pulled, and the owner clears what it consumed (zero_grads).  The result must be the very
+    bits of the dense exchange (skipped addends are zeros), every replica identical, every gradient buffer zero."""
+    from newsreclib_b200 import _lib
+    from newsreclib_b200.exchange import exchange_adam_step, peer_set
+
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device="cpu").manual_seed(7 * world + rows)
+    n = rows * width + tail
+    steps = 3
+    p0 = torch.randn(n, generator=gen)
+    grads = []
+    for _ in range(steps):
+        per_rank = []
+        for r in range(world):
+            g = torch.zeros(n)
+            touched = torch.rand(rows, generator=gen) < 0.15            # a step touches a fraction of the vocabulary
+            touched[0] = False                                          # padding_idx row: never any gradient
+            tab = torch.randn(rows, width, generator=gen) * touched[:, None]
+            g[:rows * width] = tab.reshape(-1)
+            g[rows * width:] = torch.randn(tail, generator=gen)         # the dense (non-embedding) parameters
+            per_rank.append(g * (0.1 + r))
+        grads.append(per_rank)
+    bm_words = (rows + 31) // 32
+
+    def run(sparse):
+        params = [p0.clone().to(dev) for _ in range(world)]
+        gbuf = [torch.zeros(n, device=dev) for _ in range(world)]
+        ms = [torch.zeros(n, device=dev) for _ in range(world)]
+        vs = [torch.zeros(n, device=dev) for _ in range(world)]
+        flags = [torch.zeros(_lib.FLAG_BYTES // 8, dtype=torch.int64, device=dev) for _ in range(world)]
+        bms = [torch.zeros(world * bm_words, dtype=torch.int32, device=dev) for _ in range(world)]
+        sets = [peer_set(world, r, [t.data_ptr() for t in params], [t.data_ptr() for t in gbuf],
+                         [t.data_ptr() for t in flags], [t.data_ptr() for t in bms]) for r in range(world)]
+        gdev = [[g.to(dev) for g in per_rank] for per_rank in grads]
+        streams = [torch.cuda.Stream(device=dev) for _ in range(world)]
+        torch.cuda.synchronize()
+        for s in range(1, steps + 1):
+            for r in range(world):
+                with torch.cuda.stream(streams[r]):
+                    if sparse:  # gradients ACCUMULATE into the buffer the previous exchange left cleared
+                        gbuf[r].add_(gdev[s - 1][r])
+                    else:
+                        gbuf[r].copy_(gdev[s - 1][r], non_blocking=True)
+                    exchange_adam_step(sets[r], ms[r], vs[r], n, s, lr=LR, beta1=B1, beta2=B2, eps=EPS, max_ctas=8,
+                                       timeout_s=3.0, stream=streams[r].cuda_stream, sparse_rows=rows if sparse else 0,
+                                       row_elems=width if sparse else 0, zero_grads=sparse)
+        torch.cuda.synchronize()
+        for r in range(world):
+            assert int(flags[r][32]) == 0, f"rank {r}: barrier timed out (code {int(flags[r][32])})"
+        return params, gbuf, bms
+
+    dense, _, _ = run(False)
+    sparse, gbuf, bms = run(True)
+    for r in range(world):
+        assert torch.equal(sparse[r], dense[0]), f"replica {r}: sparse exchange differs from the dense one"
+        assert not bool(gbuf[r].any()), f"rank {r}: gradient buffer not cleared"
+    want = _expected(p0, grads, steps, world)
+    assert torch.allclose(sparse[0].cpu(), want, rtol=2e-6, atol=1e-7)
+    # the published bits of the last step = non-zero rows of each rank's last gradient, in every rank's copy
+    for src in range(world):
+        nz = (grads[-1][src][:rows * width].reshape(rows, width) != 0).any(dim=1)
+        for dst in range(world):
+            words = bms[dst][src * bm_words:(src + 1) * bm_words].cpu().numpy().view("uint32")
+            bits = torch.tensor([(int(words[i >> 5]) >> (i & 31)) & 1 for i in range(rows)], dtype=torch.bool)
+            assert torch.equal(bits, nz), (src, dst)
+
+
 def test_bad_arguments_are_loud():
     from newsreclib_b200 import _lib
     from newsreclib_b200.exchange import exchange_adam_step, peer_set
