@@ -321,6 +321,188 @@ def main_naml(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------
+# the other BASELINE.json configurations, as extra keys of the one JSON line (the headline stays configs[1])
+# ----------------------------------------------------------------------------------------
+def _timed_steps(fn, steps, warmup, dev, world):
+    import torch.distributed as dist
+    for i in range(warmup):
+        fn(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms) / steps
+
+
+def _dev_batch(hb, dev):
+    return {k: (v.to(dev) if torch.is_tensor(v) else {kk: vv.to(dev) for kk, vv in v.items()}) for k, v in hb.items()}
+
+
+def _module_kwargs(outputs):
+    import functools
+    return dict(outputs=outputs, dual_loss_training=False, dual_loss_coef=None, loss="cross_entropy_loss", late_fusion=False,
+                temperature=None, dropout_probability=DROPOUT, top_k_list=[5, 10], num_categ_classes=18, num_sent_classes=3,
+                save_recs=False, recs_fpath=None, optimizer=functools.partial(torch.optim.Adam, lr=1e-4), scheduler=None)
+
+
+def extra_configs(args, dev, rank, world, exchange_mode, steps=15, warmup=3):
+    """Secondary measurements, each a short timed loop of full training steps on synthetic data of the named shape
+    (device-resident inputs, max over ranks).  Every entry is independent and guarded: a failure is reported in place and
+    never costs the headline."""
+    from newsreclib_b200 import ops
+    from newsreclib_b200.trainer import ModuleTrainer, NRMSTrainer
+    B = args.batch
+    peer = exchange_mode.startswith("peer")
+    outputs = {k: ["preds", "targets", "cand_news_size"] for k in ("train", "val", "test")}
+    out = {}
+
+    def entry(name, fn):
+        try:
+            torch.cuda.synchronize()
+            out[name] = fn()
+        except Exception as e:  # noqa: BLE001
+            out[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        torch.cuda.empty_cache()
+
+    def imps(ms, per_gpu):
+        return {"value": world * per_gpu / (ms / 1e3), "unit": "impressions/s", "ms_per_step": ms}
+
+    # -- configs[2]: NRMS MINDlarge-shape (V = 130 000), single-pass bf16, the fused step
+    def nrms_large_bf16():
+        V = 130000
+        tr = NRMSTrainer(make_nrms_params(V, E, H, Q, seed=1234), H, device=dev, dropout_p=DROPOUT, precision=ops.PREC_BF16,
+                         exchange="peer" if peer else "nccl", exchange_timeout_s=5.0, status_every=0)
+        bs = [_dev_batch(make_batch(B, V, hist="fixed", max_hist=HIST, cand="train", seed=500 + rank * 100 + i, max_title_len=L), dev)
+              for i in range(4)]
+        bs = [{"x_hist": {"title": b["x_hist"]["title"]}, "x_cand": {"title": b["x_cand"]["title"]}, "batch_hist": b["batch_hist"],
+               "batch_cand": b["batch_cand"], "labels": b["labels"]} for b in bs]
+        ms = _timed_steps(lambda i: tr.train_step(bs[i % 4], B, HIST, CAND), steps, warmup, dev, world)
+        tr.check_status()
+        r = imps(ms, B)
+        r.update(workload=f"BASELINE configs[2]: NRMS train step, MINDlarge-shape V={V}, B={B}/GPU, hist {HIST}, {CAND} candidates, "
+                          f"single-pass bf16 (fp32 accumulate), {'peer exchange' if peer else 'no exchange' if world == 1 else 'nccl'}")
+        if tr.peer_block is not None:
+            torch.distributed.barrier()
+            tr.peer_block.close()
+        return r
+    entry("nrms_mindlarge_bf16", nrms_large_bf16)
+
+    # -- configs[4]: NAML (title + abstract + category), MINDlarge-shape, through the drop-in NAMLModule
+    def naml():
+        from newsreclib_b200.models.general_rec.naml_module import NAMLModule
+        from newsreclib_b200.synthetic import make_naml_params
+        V, F_, W, CE, LA = 130000, 400, 3, 100, 50
+        params = make_naml_params(V, E, F_, W, Q, CE, 19, seed=1234)
+        m = NAMLModule(dataset_attributes=["title", "abstract", "category", "subcategory"],
+                       attributes2encode=["title", "abstract", "category"], use_plm=False, pretrained_embeddings_path=None,
+                       plm_model=None, frozen_layers=None, text_embed_dim=E, num_heads=H, num_filters=F_, window_size=W,
+                       query_dim=Q, categ_embed_dim=CE,
+                       pretrained_embeddings=params["news_encoder.text_encoders.title.embedding_layer.weight"],
+                       **_module_kwargs(outputs))
+        full = dict(params)
+        for k in list(params):
+            if ".text_encoders.title." in k:
+                full[k.replace(".title.", ".abstract.")] = params[k]
+        m.load_state_dict(full)
+        tr = ModuleTrainer(m.to(dev), lr=1e-4, exchange="peer" if peer else "nccl", exchange_timeout_s=5.0)
+        bs = [_dev_batch(make_batch(B, V, hist="fixed", max_hist=HIST, cand="train", seed=700 + rank * 100 + i, max_title_len=L,
+                                    abstract_len=LA), dev) for i in range(4)]
+        ms = _timed_steps(lambda i: tr.train_step(bs[i % 4]), steps, warmup, dev, world)
+        tr.check_status()
+        r = imps(ms, B)
+        r.update(workload=f"BASELINE configs[4]: NAML train step through NAMLModule + ModuleTrainer (autograd over the sm_100a "
+                          f"ops), MINDlarge-shape V={V}, B={B}/GPU, title {L} + abstract {LA} tokens + category, F={F_}, w={W}")
+        if tr.peer_block is not None:
+            torch.distributed.barrier()
+            tr.peer_block.close()
+        return r
+    entry("naml_mindlarge", naml)
+
+    # -- the drop-in path a Lightning user gets: NRMSModule.model_step + autograd + an optimizer
+    def nrms_module():
+        from newsreclib_b200.models.general_rec.nrms_module import NRMSModule
+        params = make_nrms_params(VOCAB, E, H, Q, seed=1234)
+
+        def build():
+            m = NRMSModule(dataset_attributes=["title", "category"], attributes2encode=["title"], use_plm=False,
+                           pretrained_embeddings_path=None, plm_model=None, frozen_layers=None, embed_dim=E, num_heads=H,
+                           query_dim=Q, pretrained_embeddings=params["news_encoder.text_encoders.title.embedding_layer.weight"],
+                           **_module_kwargs(outputs))
+            m.load_state_dict({k: v for k, v in params.items() if k in m.state_dict()})
+            return m.to(dev).train()
+        bs = [_dev_batch(make_batch(B, VOCAB, hist="fixed", max_hist=HIST, cand="train", seed=900 + rank * 100 + i,
+                                    max_title_len=L), dev) for i in range(4)]
+        tr = ModuleTrainer(build(), lr=1e-4, exchange="peer" if peer else "nccl", exchange_timeout_s=5.0)
+        ms = _timed_steps(lambda i: tr.train_step(bs[i % 4]), steps, warmup, dev, world)
+        tr.check_status()
+        r = imps(ms, B)
+        r.update(workload="NRMSModule.model_step + autograd backward + ModuleTrainer (flat fused Adam): the drop-in module path, "
+                          "headline workload")
+        if tr.peer_block is not None:
+            torch.distributed.barrier()
+            tr.peer_block.close()
+        if world == 1:  # stock torch.optim.Adam from the module's own configure_optimizers (what Lightning would call)
+            m = build()
+            opt = m.configure_optimizers()["optimizer"]
+
+            def step(i):
+                opt.zero_grad(set_to_none=True)
+                m.training_step(bs[i % 4], i).backward()
+                opt.step()
+            ms2 = _timed_steps(step, steps, warmup, dev, world)
+            r["with_torch_optim_adam"] = imps(ms2, B)
+        return r
+    entry("nrms_module_dropin", nrms_module)
+
+    # -- configs[3]: NRMS-PLM, roberta-base-shaped news encoder (random init), layers 0-7 frozen, B = 8 per GPU.
+    # The transformer is the third-party HF module on torch; only the MHSA + additive head is this library's code.
+    def nrms_plm():
+        import numpy as np
+        from transformers import RobertaConfig, RobertaModel
+        from newsreclib_b200.models.general_rec.nrms_module import NRMSModule
+        Bp, Ep, Hp = 8, 768, 16
+        torch.manual_seed(1234)
+        plm = RobertaModel(RobertaConfig(vocab_size=50265, max_position_embeddings=514, type_vocab_size=1), add_pooling_layer=False)
+        m = NRMSModule(dataset_attributes=["title", "category"], attributes2encode=["title"], use_plm=True,
+                       pretrained_embeddings_path=None, plm_model=plm, frozen_layers=list(range(8)), embed_dim=Ep, num_heads=Hp,
+                       query_dim=Q, **_module_kwargs(outputs))
+        tr = ModuleTrainer(m.to(dev), lr=1e-5, exchange="nccl")
+        rng = np.random.default_rng(1234 + rank)
+
+        def plm_news(n):
+            lens = np.clip(rng.poisson(16, n), 6, 96)
+            T = int(lens.max())
+            ids = rng.integers(3, 50265, (n, T))
+            mask = np.arange(T)[None, :] < lens[:, None]
+            ids[~mask] = 1
+            return {"input_ids": torch.from_numpy(ids).to(dev), "attention_mask": torch.from_numpy(mask.astype(np.int64)).to(dev)}
+        bs = []
+        for i in range(2):
+            hb = make_batch(Bp, 1000, hist="fixed", max_hist=HIST, cand="train", seed=40 + rank * 10 + i, max_title_len=L)
+            b = _dev_batch(hb, dev)
+            b["x_hist"]["title"], b["x_cand"]["title"] = plm_news(Bp * HIST), plm_news(Bp * CAND)
+            bs.append(b)
+        ms = _timed_steps(lambda i: tr.train_step(bs[i % 2]), 5, 2, dev, world)
+        r = imps(ms, Bp)
+        r.update(workload=f"BASELINE configs[3]: NRMS-PLM train step, roberta-base-shaped encoder (random init, layers 0-7 frozen, "
+                          f"fp32 HF/torch transformer = third-party code) + sm_100a MHSA/additive head (768-d, 16 heads), B={Bp}/GPU, "
+                          f"{HIST} + {CAND} news per impression, titles padded to the longest (<= 96 tokens), nccl exchange")
+        return r
+    entry("nrms_plm_roberta_base", nrms_plm)
+    return out
+
+
 def make_trainer(NRMSTrainer, params, dev, prec, world, mode):
     """Trainer + the name of the gradient exchange it uses.  One GPU: no exchange.  `auto`: the fused peer-memory
     kernel if every rank can map its peers AND two probe steps leave bit-identical replicas with no barrier
@@ -346,22 +528,9 @@ def make_trainer(NRMSTrainer, params, dev, prec, world, mode):
         b = {"x_hist": {"title": hb["x_hist"]["title"].to(dev)}, "x_cand": {"title": hb["x_cand"]["title"].to(dev)},
              "batch_hist": hb["batch_hist"].to(dev), "batch_cand": hb["batch_cand"].to(dev), "labels": hb["labels"].to(dev)}
         keep = tr.flat.clone()
-        # probe step 1: forward + backward into the (clean) gradient buffer, keep a copy of THIS rank's gradients,
-        # then the fused exchange; the result must equal torch.optim.Adam on the NCCL-averaged gradients
-        from newsreclib_b200 import ops as _ops
-        _ops.nrms_step(b, tr.table, tr.news_block, tr.user_block, tr.dims, B=4, Hmax=6, Cmax=CAND, dropout_p=DROPOUT,
-                       training=True, seed=99 + rank, grads=tr.grad_pack, precision=prec)
-        g_sum = tr.grad.clone()
-        tr._grads_clean = False
-        tr._finish()
-        dist.all_reduce(g_sum, op=dist.ReduceOp.SUM)
-        p_ref, m_ref, v_ref = keep.clone(), torch.zeros_like(keep), torch.zeros_like(keep)
-        _ops.adam_step(p_ref, g_sum, m_ref, v_ref, 1, tr.lr, tr.betas[0], tr.betas[1], tr.eps, grad_scale=1.0 / world)
-        # a parameter whose gradient is pure rounding noise (the key third of in_proj_bias: mathematically zero) moves by
-        # +-lr in either summation order; everything else agrees to fp32 rounding
-        d = (p_ref - tr.flat).abs()
-        adam_ok = float((d > 1e-6).float().mean()) < 2e-3 and float(d.median()) < 1e-7
-        cleared = not bool(tr.grad.any())
+        # probe step 1: a training step whose fused exchange is checked against torch.optim.Adam on the NCCL-averaged
+        # gradients of the same backward pass (NRMSTrainer.probe_exchange)
+        adam_ok, cleared = tr.probe_exchange(b, 4, 6, CAND)
         tr.train_step(b, 4, 6, CAND)  # probe step 2 through the public call
         status = tr.peer_block.status()
         lo, hi = tr.flat.clone(), tr.flat.clone()
@@ -403,6 +572,7 @@ def main():
                     help="N > 1: nccl = all-reduce + dense Adam; peer = nrl_exchange_adam_step over NVLink peer memory; "
                          "auto = peer if its self-check passes on this box, else nccl (the line says which)")
     ap.add_argument("--vocab", type=int, default=VOCAB, help="70000 = MINDsmall-shape (headline), 130000 = MINDlarge-shape")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (configs key)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     globals()["VOCAB"] = args.vocab
@@ -616,6 +786,9 @@ def main():
 
     if trainer.peer_block is not None and trainer.peer_block.status() != 0:
         raise SystemExit(f"rank {rank}: a peer-exchange barrier timed out (code {trainer.peer_block.status()}): numbers invalid")
+    extras = None
+    if not args.no_extras:
+        extras = extra_configs(args, dev, rank, world, exchange_used)
     if rank == 0:
         out = {
             "metric": "impressions/sec", "value": value, "unit": "impressions/s", "n_gpus": world,
@@ -631,6 +804,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks, "roofline": roof, "hbm_kernels": hbm_kernels, "exchange": exchange_info,
             "cpu_baseline": cpu,
+            "configs": extras,
         }
         print(json.dumps(out), flush=True)
     if world > 1:

@@ -254,6 +254,32 @@ class NRMSTrainer:
         self._finish()
         return scores, loss
 
+    def probe_exchange(self, batch: Dict, B: int, Hmax: int, Cmax: int):
+        """One training step that ALSO checks the exchange against the library path it replaces: forward + backward into
+        the (clean) gradient buffer, a copy of this rank's gradients is summed with NCCL and fed to a dense Adam step on a
+        copy of the parameters, then the configured exchange runs.  Returns ``(equals, cleared)``: the updated replica
+        equals Adam on the averaged gradients (a parameter whose gradient is pure rounding noise -- the key third of
+        ``in_proj_bias`` is mathematically zero -- moves by +-lr in either summation order; everything else must agree to
+        fp32 rounding), and the gradient buffer was left cleared.  Collective: call on every rank."""
+        keep = self.flat.clone()
+        m0, v0, step0 = self.m.clone(), self.v.clone(), self.step_count
+        self._zero_grads()
+        _, _, self.ws = ops.nrms_step(batch, self.table, self.news_block, self.user_block, self.dims, B=B, Hmax=Hmax, Cmax=Cmax,
+                                      late_fusion=self.late_fusion, dropout_p=self.dropout_p, training=True,
+                                      seed=GradExchange.rank_seed(self.seed, self.rank, self.step_count),
+                                      grads=self.grad_pack, ws=self.ws, precision=self.precision)
+        g_sum = self.grad.clone()
+        self._finish()
+        if self.world > 1:
+            torch.distributed.all_reduce(g_sum, op=torch.distributed.ReduceOp.SUM, group=self.exchange.pg)
+        if self.peer_block is not None:  # moments are sharded: the reference copy needs the full ones of the start state
+            m0, v0 = self.exchange.gather_sharded(m0), self.exchange.gather_sharded(v0)
+        ops.adam_step(keep, g_sum, m0, v0, step0 + 1, self.lr, self.betas[0], self.betas[1], self.eps,
+                      grad_scale=1.0 / self.world)
+        d = (keep - self.flat).abs()
+        equals = float((d > 1e-6).float().mean()) < 2e-3 and float(d.median()) < 1e-7
+        return equals, not bool(self.grad.any())
+
     def train_step_host(self, hb: Dict, B: int, Hmax: int, Cmax: int, scores_host: torch.Tensor,
                         loss_host: torch.Tensor, training: bool = True) -> None:
         """End-to-end step from HOST buffers (``nrl_nrms_step_host``): ids / segment ids / labels
@@ -294,7 +320,11 @@ class ModuleTrainer:
     ``torch.optim.Adam`` do for the reference, ``configs/model/naml.yaml:56-59``)."""
 
     def __init__(self, module: torch.nn.Module, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
-                 process_group=None) -> None:
+                 process_group=None, exchange: Optional[str] = None, exchange_timeout_s: float = 30.0) -> None:
+        """``exchange``: ``"nccl"`` (one all-reduce of the flat gradient buffer + dense Adam on every rank) or ``"peer"``
+        (``nrl_exchange_adam_step`` over NVLink peer memory, as in ``NRMSTrainer``); default ``$NRL_EXCHANGE`` or
+        ``"nccl"``.  The largest ``nn.Embedding`` table leads the flat buffer so that the peer exchange can treat its
+        gradient as row-sparse."""
         _lib.load()
         self.module = module
         uniq, seen = [], set()
@@ -303,32 +333,63 @@ class ModuleTrainer:
                 seen.add(id(p)); uniq.append(p)
         if not uniq or not uniq[0].is_cuda:
             raise RuntimeError("ModuleTrainer needs a module on a CUDA device (newsreclib_b200 has no CPU path)")
+        tables = [m.weight for m in module.modules() if isinstance(m, torch.nn.Embedding) and m.weight.requires_grad
+                  and m.weight.dim() == 2 and m.weight.shape[1] % 4 == 0]
+        table = max(tables, key=lambda t: t.numel()) if tables else None
+        if table is not None:
+            uniq = [table] + [p for p in uniq if p is not table]
         total, offs = 0, []
         for p in uniq:
             offs.append(total)
             total += (p.numel() + 3) // 4 * 4
         dev = uniq[0].device
-        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.grad = torch.zeros_like(self.flat)
-        self.m, self.v = torch.zeros_like(self.flat), torch.zeros_like(self.flat)
+        self.exchange = GradExchange(process_group)
+        self.world = self.exchange.world
+        self.exchange_mode = (exchange or os.environ.get("NRL_EXCHANGE", "nccl")).lower()
+        if self.exchange_mode not in ("nccl", "peer"):
+            raise ValueError(f"exchange must be 'nccl' or 'peer', got {self.exchange_mode!r}")
+        self.peer_block = None
+        if self.exchange_mode == "peer":
+            from .exchange import PeerBlock
+            rows, width = (table.shape[0], table.shape[1]) if table is not None else (0, 0)
+            self.peer_block = PeerBlock(total, dev, process_group, sparse_rows=rows, row_elems=width)
+            self.flat, self.grad = self.peer_block.flat, self.peer_block.grad
+        else:
+            self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+            self.grad = torch.zeros_like(self.flat)
+        self.m, self.v = torch.zeros(total, dtype=torch.float32, device=dev), torch.zeros(total, dtype=torch.float32, device=dev)
         for p, o in zip(uniq, offs):
             n = p.numel()
             self.flat[o:o + n].copy_(p.data.reshape(-1))
             p.data = self.flat[o:o + n].view_as(p)
             p.grad = self.grad[o:o + n].view_as(p)  # autograd accumulates in place into the flat buffer
         self.lr, self.betas, self.eps = lr, betas, eps
-        self.exchange = GradExchange(process_group)
         self.step_count = 0
-        if self.exchange.world > 1:  # Lightning DDP broadcasts rank 0's parameters at construction
+        self.exchange_epoch = 0
+        self.exchange_timeout_s = float(exchange_timeout_s)
+        if self.world > 1:  # Lightning DDP broadcasts rank 0's parameters at construction
             torch.distributed.broadcast(self.flat, src=torch.distributed.get_global_rank(process_group, 0)
                                         if process_group is not None else 0, group=process_group)
+
+    def check_status(self) -> None:
+        if self.peer_block is not None and self.peer_block.status():
+            raise RuntimeError(f"peer-exchange barrier timed out (code {self.peer_block.status()}); restore the last checkpoint")
+        ops.device_status(raise_on_error=True)
 
     def train_step(self, batch) -> torch.Tensor:
         self.module.train()
         loss = self.module.model_step(batch)[0]  # gradient buffers are clean: zeroed at construction / by the Adam pass
         loss.backward()
-        scale = self.exchange.all_reduce(self.grad)
         self.step_count += 1
-        ops.adam_step(self.flat, self.grad, self.m, self.v, self.step_count, self.lr, self.betas[0], self.betas[1],
-                      self.eps, grad_scale=scale, zero_grad=True)
+        if self.peer_block is not None:
+            from .exchange import exchange_adam_step
+            self.exchange_epoch += 1
+            exchange_adam_step(self.peer_block.peer_set, self.m, self.v, self.flat.numel(), self.step_count, lr=self.lr,
+                               beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, grad_scale=1.0 / self.world,
+                               epoch=self.exchange_epoch, timeout_s=self.exchange_timeout_s,
+                               sparse_rows=self.peer_block.sparse_rows, row_elems=self.peer_block.row_elems, zero_grads=True)
+        else:
+            scale = self.exchange.all_reduce(self.grad)
+            ops.adam_step(self.flat, self.grad, self.m, self.v, self.step_count, self.lr, self.betas[0], self.betas[1],
+                          self.eps, grad_scale=scale, zero_grad=True)
         return loss.detach()

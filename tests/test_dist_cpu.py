@@ -286,6 +286,10 @@ def _make_trainer_worker(rank, world, port, scenario, out):
             self.step_count += 1
             self.flat += 2.0 if (scenario == "replicas_differ" and rank == 1) else 1.0
 
+        def probe_exchange(self, b, B, Hmax, Cmax):
+            self.train_step(b, B, Hmax, Cmax)
+            return True, True
+
     tr, used = bench.make_trainer(FakeTrainer, {}, torch.device("cpu"), 0, world, "auto")
     out[rank] = (tr.mode, used)
     dist.barrier()
