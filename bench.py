@@ -758,7 +758,8 @@ def main():
                              "achieved_gbs_per_direction": round((dense + grads) / (ms_x / 1e3) / 1e9, 1),
                              "note": "kernel time includes the local non-zero-row scan (84 MB of HBM reads), the wait for the "
                                      "slowest rank at the ready barrier and the sharded Adam",
-                             "adam_elements_per_rank": n_flat // world}
+                             "adam_elements_per_rank": n_flat // world,
+                             "timeline_us_last_step_rank0": trainer.peer_block.timeline_us()}
     except Exception as e:  # never lose the line over a diagnostic
         exchange_info = {"error": repr(e)}
 

@@ -37,6 +37,7 @@
 //   [33]        cta counter  local: CTAs of the running kernel that have finished their slice
 //   [34]        scan counter local: CTAs of the running kernel that have finished step 0
 //   [35]        go           local: epoch of the last step whose ready barrier completed
+//   [40 .. 45)  timeline     local: %globaltimer of the last launch (start, scan done, go, slice done, done barrier)
 // Waits poll with ld.acquire.sys and give up after `timeout_ns` (a peer that died must not hang the
 // GPU); the host reads the error word with nrl_exchange_status.  Once the error word is set, later
 // launches on this rank return immediately.
@@ -47,6 +48,8 @@ namespace nrl {
 
 constexpr int XCHG_MAX_RANKS = 16;
 constexpr int XCHG_READY = 0, XCHG_DONE = 16, XCHG_ERR = 32, XCHG_CTAS = 33, XCHG_SCAN = 34, XCHG_GO = 35,
+              XCHG_T0 = 40,  // [40..45): %globaltimer (ns) of the last launch: first CTA in, row scan finished, go, slice
+                             // finished by the last CTA, done barrier passed -- a timeline the host can read
               XCHG_FLAG_WORDS = 64;
 
 struct PeerSet {
@@ -138,28 +141,34 @@ exchange_adam_kernel(PeerSet ps, float* __restrict__ m, float* __restrict__ v, l
   __syncthreads();
   if (!s_flag) return;
   __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) my_flags[XCHG_T0] = globaltimer_ns();
 
-  // ---- 0. which rows of MY table gradient are non-zero: one word = 32 rows per warp, published to every rank
+  // ---- 0. which rows of MY table gradient are non-zero: 16 rows (half a bitmap word) per warp, eight rows' loads in
+  // flight per lane, published to every rank as one 16-bit store each
   if (sparse) {
     const int lane = threadIdx.x & 31;
     const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const float4* g_loc = reinterpret_cast<const float4*>(ps.grads[rank]);
-    for (long long word = gw; word < sp.bm_words; word += nwarps) {
+    const long long halves = 2ll * sp.bm_words;
+    for (long long hw = gw; hw < halves; hw += nwarps) {
       unsigned int bits = 0;
-      for (int r0 = 0; r0 < 32; r0 += 4) {  // four rows' loads in flight
-        bool any[4] = {false, false, false, false};
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const long long row = word * 32 + r0 + u;
+      for (int r0 = 0; r0 < 16; r0 += 8) {
+        bool any[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          any[u] = false;
+          const long long row = hw * 16 + r0 + u;
           if (row < sp.rows)
             for (int c = lane; c < sp.row_f4; c += 32) any[u] |= f4_nonzero(g_loc[row * sp.row_f4 + c]);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < 8; ++u)
           if (__any_sync(0xffffffffu, any[u])) bits |= 1u << (r0 + u);
       }
-      if (lane < world) ps.bitmaps[lane][(long long)rank * sp.bm_words + word] = bits;
+      if (lane < world)  // little-endian: half `hw & 1` of word `hw >> 1`
+        reinterpret_cast<unsigned short*>(ps.bitmaps[lane] + (long long)rank * sp.bm_words)[hw] = (unsigned short)bits;
     }
   }
 
@@ -176,6 +185,7 @@ exchange_adam_kernel(PeerSet ps, float* __restrict__ m, float* __restrict__ v, l
     __shared__ int s_ok;
     if (threadIdx.x == 0) {
       my_flags[XCHG_SCAN] = 0ull;
+      my_flags[XCHG_T0 + 1] = globaltimer_ns();
       s_ok = 1;
     }
     __syncthreads();
@@ -185,6 +195,7 @@ exchange_adam_kernel(PeerSet ps, float* __restrict__ m, float* __restrict__ v, l
     }
     __syncthreads();
     if (threadIdx.x == 0) {
+      my_flags[XCHG_T0 + 2] = globaltimer_ns();
       if (s_ok) st_release_sys_u64(my_flags + XCHG_GO, epoch);  // local word: the other CTAs poll it
       else atomicCAS(my_flags + XCHG_ERR, 0ull, 1ull);
     }
@@ -295,12 +306,17 @@ exchange_adam_kernel(PeerSet ps, float* __restrict__ m, float* __restrict__ v, l
   __syncthreads();
   if (s_flag) {
     __threadfence_system();  // acquire side of the counter: every CTA's stores precede the signal
-    if (threadIdx.x == 0) my_flags[XCHG_CTAS] = 0ull;  // next launch starts from zero
+    if (threadIdx.x == 0) {
+      my_flags[XCHG_CTAS] = 0ull;  // next launch starts from zero
+      my_flags[XCHG_T0 + 3] = globaltimer_ns();
+    }
     if (threadIdx.x < world && threadIdx.x != rank) {
       st_release_sys_u64(ps.flags[threadIdx.x] + XCHG_DONE + rank, epoch);
       if (!wait_flag(my_flags + XCHG_DONE + threadIdx.x, epoch, timeout_ns))
         atomicCAS(my_flags + XCHG_ERR, 0ull, 2ull);
     }
+    __syncthreads();
+    if (threadIdx.x == 0) my_flags[XCHG_T0 + 4] = globaltimer_ns();
   }
 }
 

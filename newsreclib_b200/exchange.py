@@ -132,6 +132,15 @@ class PeerBlock:
                    "nrl_exchange_status")
         return int(err.value)
 
+    def timeline_us(self):
+        """Phases of the LAST exchange kernel of this rank in microseconds (device ``%globaltimer``): row scan, wait for
+        the slowest rank (ready barrier), owned slice (pull + Adam + push + clear), done barrier.  Synchronises."""
+        torch.cuda.synchronize(self.device)
+        words = torch.as_tensor(_DevMem(self.flags_ptr, _lib.FLAG_BYTES // 8, "<i8"), device=self.device)[40:45].tolist()
+        t0, t1, t2, t3, t4 = words
+        return {"scan": (t1 - t0) / 1e3, "ready_wait": (t2 - t1) / 1e3, "slice": (t3 - t2) / 1e3, "done_wait": (t4 - t3) / 1e3,
+                "total": (t4 - t0) / 1e3}
+
     def close(self) -> None:
         """Unmap the peers' blocks and free the local one (call on every rank, after a barrier)."""
         with self._device_ctx():
