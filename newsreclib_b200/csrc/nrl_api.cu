@@ -1301,7 +1301,7 @@ int nrl_exchange_adam_step(const nrl_peer_set* peers, float* m, float* v, long l
     if (occ < 1) return fail(NRL_ERR_CUDA, "exchange kernel does not fit an SM");                            \
     int cap = max_ctas > 0 ? max_ctas : 4 * g_dev.sm_count;                                                  \
     if (cap > occ * g_dev.sm_count) cap = occ * g_dev.sm_count;                                              \
-    long long work = per > (long long)sp.bm_words * 64 * 32 ? per : (long long)sp.bm_words * 64 * 32;        \
+    long long work = per > (long long)sp.bm_words * 64 ? per : (long long)sp.bm_words * 64;                  \
     const int grid = grid_for(work, 256, cap);                                                               \
     exchange_adam_kernel<W><<<grid, 256, 0, st>>>(ps, m, v, n4, epoch, timeout_ns, lr, beta1, beta2, eps,    \
                                                   (float)bc1, (float)std::sqrt(bc2), grad_scale, sp);        \
