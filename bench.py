@@ -500,6 +500,67 @@ def extra_configs(args, dev, rank, world, exchange_mode, steps=15, warmup=3):
                           f"{HIST} + {CAND} news per impression, titles padded to the longest (<= 96 tokens), nccl exchange")
         return r
     entry("nrms_plm_roberta_base", nrms_plm)
+
+    # -- evaluation at MINDlarge-dev shape (whole impressions, candidate lists up to 300): news
+    # vectors encoded once per epoch for the news table, then an impression batch = two row gathers + user encoder +
+    # scorer + device metrics; the plain (re-encoding) eval forward of the same batches beside it
+    def eval_cached():
+        from newsreclib_b200.metrics import ranking_metrics
+        from newsreclib_b200.models.general_rec.nrms_module import NRMSModule
+        from newsreclib_b200.synthetic import make_titles
+        import numpy as np
+        V, M = 130000, 100000  # MINDlarge: ~130 k vocabulary rows, ~100 k news in the dev table
+        params = make_nrms_params(V, E, H, Q, seed=1234)
+        m = NRMSModule(dataset_attributes=["title", "category"], attributes2encode=["title"], use_plm=False,
+                       pretrained_embeddings_path=None, plm_model=None, frozen_layers=None, embed_dim=E, num_heads=H,
+                       query_dim=Q, pretrained_embeddings=params["news_encoder.text_encoders.title.embedding_layer.weight"],
+                       **_module_kwargs(outputs))
+        m.load_state_dict({k: v for k, v in params.items() if k in m.state_dict()})
+        m = m.to(dev).eval()
+        rng = np.random.default_rng(7 + rank)
+        titles = torch.from_numpy(make_titles(rng, M, V, L)).to(dev)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        vecs = m.encode_news_table({"title": titles})
+        e1.record()
+        torch.cuda.synchronize()
+        enc_ms = e0.elapsed_time(e1)
+        bs = []
+        for i in range(4):
+            hb = make_batch(B, V, hist="ragged", max_hist=HIST, cand="eval", seed=300 + rank * 100 + i, max_title_len=L)
+            nh, nc = hb["batch_hist"].numel(), hb["batch_cand"].numel()
+            hr, cr = torch.from_numpy(rng.integers(0, M, nh)).to(dev), torch.from_numpy(rng.integers(0, M, nc)).to(dev)
+            full = _dev_batch(hb, dev)
+            full["x_hist"]["title"], full["x_cand"]["title"] = titles[hr], titles[cr]
+            bs.append((hr, cr, full, torch.bincount(hb["batch_cand"], minlength=B).to(dev)))
+
+        def cached(i):
+            hr, cr, full, sizes = bs[i % 4]
+            sc = m.forward_cached(vecs, hr, full["batch_hist"], cr, full["batch_cand"], B)
+            mask = torch.arange(sc.shape[1], device=dev)[None, :] < sizes[:, None]
+            return ranking_metrics(sc[mask], full["labels"], sizes, [5, 10])
+
+        def plain(i):
+            with torch.no_grad():
+                return m(bs[i % 4][2])
+        def cached_scores_only(i):
+            hr, cr, full, sizes = bs[i % 4]
+            return m.forward_cached(vecs, hr, full["batch_hist"], cr, full["batch_cand"], B)
+        ms_c = _timed_steps(cached, steps, warmup, dev, world)
+        ms_s = _timed_steps(cached_scores_only, steps, warmup, dev, world)
+        ms_p = _timed_steps(plain, steps, warmup, dev, world)
+        cands = sum(int(b[1].numel()) for b in bs) / 4
+        r = imps(ms_c, B)
+        r.update(news_table_encode={"news": M, "ms": enc_ms, "news_per_s": M / (enc_ms / 1e3)},
+                 candidates_per_batch=cands, cached_scores_only=imps(ms_s, B), plain_eval_forward_scores_only=imps(ms_p, B),
+                 note="value = cached scores + AUC/MRR/nDCG@5,10 on device (torch sort / unique: not library kernels); "
+                      "cached_scores_only / plain_eval_forward_scores_only compare the two ways of producing the scores",
+                 workload=f"eval at MINDlarge-dev shape: B={B} whole impressions/GPU (ragged histories <= {HIST}, candidate lists "
+                          f"lognormal up to 300), scores from news vectors cached once per epoch + AUC/MRR/nDCG on device; "
+                          f"plain_eval_forward re-encodes every news of the batch")
+        return r
+    entry("eval_cached_mindlarge_dev", eval_cached)
     return out
 
 

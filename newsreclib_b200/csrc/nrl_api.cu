@@ -701,15 +701,61 @@ static int block_forward(const Ctx& c, const Dims& d, BlockWs& w, long long R, c
 
 // Backward of block_forward.  d_vec [G][E] -> w.dx [R][E] (gradient w.r.t. the block input,
 // dropout site 0 applied when drop0.on), parameter gradients accumulated into g.
+// The three weight-gradient GEMMs of a block depend on the data-gradient chain only through their operands
+// (dApre, dY, dQKV), and nothing in the backward pass consumes them: they run on a second, lower-priority stream so
+// that their CTAs fill the SMs the main chain leaves idle -- the partial last wave and the ramp of every persistent
+// GEMM, and the register-bound attention backward, which occupies a third of an SM's shared memory-free resources.
+// NRL_WGRAD_STREAM=0 keeps everything on the caller's stream (also forced while per-launch profiling is on, so that
+// every launch's duration is its own).
+struct SideStream {
+  cudaStream_t s = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  int dev = -1;
+};
+static SideStream g_side;
+static bool side_wanted() {
+  static const bool v = [] { const char* e = getenv("NRL_WGRAD_STREAM"); return !(e && e[0] == '0'); }();
+  return v && !g_prof.on;
+}
+static int side_init() {
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (g_side.s && g_side.dev == dev) return NRL_OK;
+  int lo = 0, hi = 0;
+  CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // lo = numerically greatest = lowest priority
+  CUDA_TRY(cudaStreamCreateWithPriority(&g_side.s, cudaStreamNonBlocking, lo));
+  for (int i = 0; i < 4; ++i) CUDA_TRY(cudaEventCreateWithFlags(&g_side.ev[i], cudaEventDisableTiming));
+  g_side.dev = dev;
+  return NRL_OK;
+}
+// side stream waits for everything issued on `main` so far
+static int side_follow(cudaStream_t main, int ev) {
+  CUDA_TRY(cudaEventRecord(g_side.ev[ev], main));
+  CUDA_TRY(cudaStreamWaitEvent(g_side.s, g_side.ev[ev], 0));
+  return NRL_OK;
+}
+
+// the caller's stream continues only when the weight gradients issued so far are complete
+static int side_join(cudaStream_t main) {
+  if (!g_side.s) return NRL_OK;
+  CUDA_TRY(cudaEventRecord(g_side.ev[3], g_side.s));
+  CUDA_TRY(cudaStreamWaitEvent(main, g_side.ev[3], 0));
+  return NRL_OK;
+}
+
 static int block_backward(const Ctx& c, const Dims& d, BlockWs& w, long long R, const AttnGeom& ag,
                           long long G, int L, const nrl_block_params* prm, const DropCfg& drop1,
-                          const DropCfg& drop0, const float* d_vec, nrl_block_grads* g) {
+                          const DropCfg& drop0, const float* d_vec, nrl_block_grads* g, bool join = true) {
   TRY(attn_attrs_init());
+  const bool side = side_wanted() && side_init() == NRL_OK;
+  Ctx cw = c;  // where the weight-gradient GEMMs go
+  if (side) cw.stream = g_side.s;
   bf16* lo_or_null_dap = c.two_planes() ? w.dap + R * d.Qp : nullptr;
   pool_bwd_kernel<<<grid_for(G, 1, 8 * g_dev.sm_count), 256, L * sizeof(float), c.stream>>>(
       d_vec, w.y, w.w, w.a, prm->add_query, d.E, d.Q, d.Qp, L, G, nullptr, w.dap, lo_or_null_dap,
       g->add_query, g->add_bias);
   LAUNCH_CHECK("pool_bwd");
+  if (side) TRY(side_follow(c.stream, 0));
   // dY = dropout1'( w_r * dVec[g] + dApre W_add )  -> split planes
   {
     GemmEpi e = epi_none();
@@ -719,9 +765,10 @@ static int block_backward(const Ctx& c, const Dims& d, BlockWs& w, long long R, 
     epi_dropout(e, drop1, w.mask1, d.MW);
     TRY(gemm_nt(c, w.dap, R, d.Qp, w.wadd_t, d.E, d.Qp, d.Qp, e, sk, "gemm additive dgrad"));
   }
+  if (side) TRY(side_follow(c.stream, 1));
   // dW_add, db_add
   // (db_add is summed in fp32 by pool_bwd)
-  TRY(gemm_tn(c, w.dap, d.Q, d.Qp, w.yp, d.Ep, d.Ep, R, g->add_weight, d.E, d.E, nullptr,
+  TRY(gemm_tn(cw, w.dap, d.Q, d.Qp, w.yp, d.Ep, d.Ep, R, g->add_weight, d.E, d.E, nullptr,
               "gemm additive wgrad"));
   // dO = dY W_out
   {
@@ -731,7 +778,7 @@ static int block_backward(const Ctx& c, const Dims& d, BlockWs& w, long long R, 
     TRY(gemm_nt(c, w.dyp, R, d.Ep, w.wout_t, d.E, d.Ep, d.Ep, e, sk, "gemm out_proj dgrad"));
   }
   // dW_out, db_out
-  TRY(gemm_tn(c, w.dyp, d.E, d.Ep, w.o, d.Ep, d.Ep, R, g->out_proj_weight, d.E, d.E, g->out_proj_bias,
+  TRY(gemm_tn(cw, w.dyp, d.E, d.Ep, w.o, d.Ep, d.Ep, R, g->out_proj_weight, d.E, d.E, g->out_proj_bias,
               "gemm out_proj wgrad"));
   if (d.DH == 16) launch_attn_bwd<16>(c, d, ag, w, R);
   else if (d.DH == 20) launch_attn_bwd<20>(c, d, ag, w, R);
@@ -739,6 +786,7 @@ static int block_backward(const Ctx& c, const Dims& d, BlockWs& w, long long R, 
   else if (d.DH == 48) launch_attn_bwd<48>(c, d, ag, w, R);
   else launch_attn_bwd<64>(c, d, ag, w, R);
   LAUNCH_CHECK("attn_bwd");
+  if (side) TRY(side_follow(c.stream, 2));
   // dX = dropout0'( dQKV W_in )
   {
     GemmEpi e = epi_none();
@@ -748,8 +796,9 @@ static int block_backward(const Ctx& c, const Dims& d, BlockWs& w, long long R, 
     TRY(gemm_nt(c, w.dqkv, R, d.P3, w.win_t, d.E, d.P3, d.P3, e, sk, "gemm in_proj dgrad"));
   }
   // dW_in, db_in
-  TRY(gemm_tn(c, w.dqkv, 3 * d.E, d.P3, w.x, d.Ep, d.Ep, R, g->in_proj_weight, d.E, d.E, g->in_proj_bias,
+  TRY(gemm_tn(cw, w.dqkv, 3 * d.E, d.P3, w.x, d.Ep, d.Ep, R, g->in_proj_weight, d.E, d.E, g->in_proj_bias,
               "gemm in_proj wgrad"));
+  if (side && join) TRY(side_join(c.stream));
   return NRL_OK;
 }
 
@@ -787,12 +836,13 @@ static int news_bwd_impl(const Ctx& c, const Dims& d, BlockWs& w, const long lon
                          const float* d_out, nrl_block_grads* g, float* d_table) {
   const long long R = n_news * L;
   AttnGeom ag{L, 1, (int)n_news, L};
-  TRY(block_backward(c, d, w, R, ag, n_news, L, prm, drop, drop, d_out, g));
+  // the weight-gradient stream is joined after the embedding-gradient scatter (they are independent)
+  TRY(block_backward(c, d, w, R, ag, n_news, L, prm, drop, drop, d_out, g, false));
   if (d_table) {
     emb_grad_kernel<<<grid_for(R, 8, 1 << 20), 256, 0, c.stream>>>(ids, R, V1, w.dx, d.E, d_table);
     LAUNCH_CHECK("emb_grad");
   }
-  return NRL_OK;
+  return side_join(c.stream);
 }
 
 extern "C" {
@@ -1420,7 +1470,7 @@ static int nrms_impl(const Ctx& c, const Dims& d, NrmsWs& w, const long long* hi
   LAUNCH_CHECK("score_loss");
   if (!do_backward) return NRL_OK;
   if (!late_fusion) {
-    TRY(block_backward(c, d, w.user, Ru, user_geom(B, Hmax, 0), B, Hmax, up, nodrop, nodrop, w.d_user, ug));
+    TRY(block_backward(c, d, w.user, Ru, user_geom(B, Hmax, 0), B, Hmax, up, nodrop, nodrop, w.d_user, ug, false));
     dim3 grid(Hmax, B < 65535 ? B : 65535);
     dense_gather_kernel<<<grid, 128, 0, c.stream>>>(w.user.dx, w.hist_off, B, Hmax, d.E, w.d_news);
     LAUNCH_CHECK("dense_gather");

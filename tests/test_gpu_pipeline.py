@@ -96,3 +96,48 @@ def test_cached_news_vectors_eval_path_matches_forward():
     mask = torch.arange(got.shape[1], device="cuda")[None, :] < sizes.cuda()[:, None]
     met = ranking_metrics(got[mask], b["labels"], sizes.cuda(), [5, 10])
     assert 0.0 <= float(met["auc"]) <= 1.0 and 0.0 < float(met["mrr"]) <= 1.0
+
+
+def test_cached_eval_path_full_impression_size_vs_oracle():
+    """SURVEY section 8 f4 at evaluation size: 64 whole impressions (candidate lists up to 300, histories up to 50) scored
+    from news vectors encoded ONCE for the news table, against the CPU oracle's eval forward on the gathered titles
+    (logit bar 1e-4), padded slots exactly 0.0, and the device ranking metrics against their definitions on the CPU."""
+    from test_gpu_modules import full_batch, make_module
+    from test_gpu_fullsize import _eval_batch_with_long_impression
+    from newsreclib_b200.metrics import ranking_metrics
+    from oracle import nrms_oracle as O
+    V, M, B = 70000, 6000, 64
+    params = make_nrms_params(V, seed=44)
+    rng = np.random.default_rng(44)
+    titles = torch.from_numpy(make_titles(rng, M, V, 30))
+    m = make_module(params).cuda().eval()
+    m.load_state_dict(params)
+    vecs = m.encode_news_table({"title": titles.cuda()})
+    batch = _eval_batch_with_long_impression(B, V, 300, seed=45)
+    nh, nc = batch["batch_hist"].numel(), batch["batch_cand"].numel()
+    hist_rows = torch.from_numpy(rng.integers(0, M, nh)); cand_rows = torch.from_numpy(rng.integers(0, M, nc))
+    batch["x_hist"]["title"] = titles[hist_rows]; batch["x_cand"]["title"] = titles[cand_rows]
+    got = m.forward_cached(vecs, hist_rows.cuda(), batch["batch_hist"].cuda(), cand_rows.cuda(), batch["batch_cand"].cuda(), B)
+    with torch.no_grad():
+        ref = O.nrms_forward(batch, params, 15)
+    assert got.shape == ref.shape == (B, 300)
+    e = rel_err(got, ref)
+    print(f"cached eval path, B=64 Cmax=300: logits rel {e:.2e} (tol 1e-4)")
+    assert e <= 1e-4
+    sizes = torch.bincount(batch["batch_cand"], minlength=B)
+    for b in range(B):
+        assert torch.all(got[b, sizes[b]:] == 0)
+    mask = torch.arange(300)[None, :] < sizes[:, None]
+    met = ranking_metrics(got[mask.cuda()], batch["labels"].cuda(), sizes.cuda(), [5, 10])
+    # the same definitions, impression by impression, on the oracle's scores
+    mrr, nd5 = [], []
+    off = np.concatenate([[0], np.cumsum(sizes.numpy())])
+    for b in range(B):
+        sc, y = ref[b, :sizes[b]].numpy(), batch["labels"][off[b]:off[b + 1]].numpy()
+        order = np.argsort(-sc, kind="stable")
+        ys = y[order]
+        mrr.append(1.0 / (np.argmax(ys > 0) + 1) if ys.sum() > 0 else 0.0)
+        disc = 1.0 / np.log2(np.arange(2, len(ys) + 2))
+        idcg = (np.sort(y)[::-1][:5] * disc[:5]).sum()
+        nd5.append((ys[:5] * disc[:5]).sum() / idcg if idcg > 0 else 0.0)
+    assert abs(float(met["mrr"]) - np.mean(mrr)) < 2e-3 and abs(float(met["ndcg@5"]) - np.mean(nd5)) < 2e-3
