@@ -588,9 +588,17 @@ static void launch_attn_bwd(const Ctx& c, const Dims& d, const AttnGeom& g, cons
   }
   if (g.S <= 32 && !attn_force_simt()) {
     const long long items = (long long)g.NB * d.H;
-    attn_bwd_mma_kernel<DH><<<(unsigned)((items + 3) / 4), 128, 0, c.stream>>>(
-        w.qkv, w.d_o, d.E, w.lse, d.E, d.LDQ, d.H, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH),
-        w.dqkv, lo, d.P3);
+    // NRL_ATTN_BWD_VARIANT (A/B runs): 0 = fragments held in registers (168 registers, 3 CTAs / SM), 1 = fragments
+    // re-read when needed again (default), 2 = re-read + register budget of 4 CTAs / SM
+    static const int variant = [] { const char* e = getenv("NRL_ATTN_BWD_VARIANT"); return e ? atoi(e) : 1; }();
+#define NRL_ATTN_BWD_LAUNCH(RELOAD, MINB)                                                                            \
+    attn_bwd_mma_kernel<DH, RELOAD, MINB><<<(unsigned)((items + 3) / 4), 128, 0, c.stream>>>(                        \
+        w.qkv, w.d_o, d.E, w.lse, d.E, d.LDQ, d.H, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH), w.dqkv, lo, \
+        d.P3)
+    if (variant == 0) NRL_ATTN_BWD_LAUNCH(false, 3);
+    else if (variant == 2) NRL_ATTN_BWD_LAUNCH(true, 4);
+    else NRL_ATTN_BWD_LAUNCH(true, 3);
+#undef NRL_ATTN_BWD_LAUNCH
     return;
   }
   if (g.S <= 64 && !attn_force_simt()) {

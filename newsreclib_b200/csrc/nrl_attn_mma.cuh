@@ -31,6 +31,21 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
+// same with C = 0: the first product of an accumulator tile needs no zeroed registers
+__device__ __forceinline__ void mma_16816_z(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                            uint32_t b0, uint32_t b1) {
+  asm(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, "
+      "{%8, %9}, {%10, %10, %10, %10};"
+      : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(0.f));
+}
+template <bool Z>
+__device__ __forceinline__ void mma_16816_t(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                            uint32_t b0, uint32_t b1) {
+  if (Z) mma_16816_z(c, a0, a1, a2, a3, b0, b1);
+  else mma_16816(c, a0, a1, a2, a3, b0, b1);
+}
 __device__ __forceinline__ uint32_t movm_t(uint32_t x) {
   uint32_t y;
   asm("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(y) : "r"(x));
@@ -79,10 +94,19 @@ __device__ __forceinline__ void load_blocks(Blk& m, const float* __restrict__ ba
 // three on the same tile.
 // c[i][j] += sum over k-steps  A(i, kk) * B(j, kk)   with A blocks a[2i + ..][2kk + ..] (row layout,
 // M x K) and B given as the row-layout blocks of the [N x K] operand b[j][2kk + ..] ("NT" product).
-template <int KSTEPS, int NT>
+// INIT: the accumulator tiles c[i][j], j < NT, are (re)initialised by the first product (no zeroing needed; the
+// hi*hi pass goes first then, so that the same instruction initialises in both precisions).
+template <int KSTEPS, int NT, bool INIT = false>
 __device__ __forceinline__ void mma_nt(float (&c)[2][4][4], const Blk& a, const Blk& b, bool three) {
 #pragma unroll
   for (int kk = 0; kk < KSTEPS; ++kk) {
+    if (INIT && kk == 0) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+          mma_16816_z(c[i][j], a.h[2 * i][0], a.h[2 * i + 1][0], a.h[2 * i][1], a.h[2 * i + 1][1], b.h[j][0], b.h[j][1]);
+    }
     if (three) {
 #pragma unroll
       for (int i = 0; i < 2; ++i)
@@ -97,17 +121,19 @@ __device__ __forceinline__ void mma_nt(float (&c)[2][4][4], const Blk& a, const 
           mma_16816(c[i][j], a.h[2 * i][2 * kk], a.h[2 * i + 1][2 * kk], a.h[2 * i][2 * kk + 1],
                     a.h[2 * i + 1][2 * kk + 1], b.l[j][2 * kk], b.l[j][2 * kk + 1]);
     }
+    if (!(INIT && kk == 0)) {
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+      for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int j = 0; j < NT; ++j)
-        mma_16816(c[i][j], a.h[2 * i][2 * kk], a.h[2 * i + 1][2 * kk], a.h[2 * i][2 * kk + 1],
-                  a.h[2 * i + 1][2 * kk + 1], b.h[j][2 * kk], b.h[j][2 * kk + 1]);
+        for (int j = 0; j < NT; ++j)
+          mma_16816(c[i][j], a.h[2 * i][2 * kk], a.h[2 * i + 1][2 * kk], a.h[2 * i][2 * kk + 1],
+                    a.h[2 * i + 1][2 * kk + 1], b.h[j][2 * kk], b.h[j][2 * kk + 1]);
+    }
   }
 }
 // c[i][j] += A(i, kk) * B(kk, j) with B given as row-layout blocks of the [K x N] operand
 // b[2kk + ..][j] ("NN" product: the B fragments are the movmatrix transposes of those blocks).
-template <int NT>
+template <int NT, bool INIT = false>
 __device__ __forceinline__ void mma_nn(float (&c)[2][4][4], const Blk& a, const Blk& b, bool three) {
 #pragma unroll
   for (int kk = 0; kk < 2; ++kk) {
@@ -116,6 +142,13 @@ __device__ __forceinline__ void mma_nn(float (&c)[2][4][4], const Blk& a, const 
     for (int j = 0; j < NT; ++j) {
       bh[j][0] = movm_t(b.h[2 * kk][j]); bh[j][1] = movm_t(b.h[2 * kk + 1][j]);
       bl[j][0] = three ? movm_t(b.l[2 * kk][j]) : 0u; bl[j][1] = three ? movm_t(b.l[2 * kk + 1][j]) : 0u;
+    }
+    if (INIT && kk == 0) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+          mma_16816_z(c[i][j], a.h[2 * i][0], a.h[2 * i + 1][0], a.h[2 * i][1], a.h[2 * i + 1][1], bh[j][0], bh[j][1]);
     }
     if (three) {
 #pragma unroll
@@ -131,18 +164,20 @@ __device__ __forceinline__ void mma_nn(float (&c)[2][4][4], const Blk& a, const 
           mma_16816(c[i][j], a.h[2 * i][2 * kk], a.h[2 * i + 1][2 * kk], a.h[2 * i][2 * kk + 1],
                     a.h[2 * i + 1][2 * kk + 1], bl[j][0], bl[j][1]);
     }
+    if (!(INIT && kk == 0)) {
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+      for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int j = 0; j < NT; ++j)
-        mma_16816(c[i][j], a.h[2 * i][2 * kk], a.h[2 * i + 1][2 * kk], a.h[2 * i][2 * kk + 1],
-                  a.h[2 * i + 1][2 * kk + 1], bh[j][0], bh[j][1]);
+        for (int j = 0; j < NT; ++j)
+          mma_16816(c[i][j], a.h[2 * i][2 * kk], a.h[2 * i + 1][2 * kk], a.h[2 * i][2 * kk + 1],
+                    a.h[2 * i + 1][2 * kk + 1], bh[j][0], bh[j][1]);
+    }
   }
 }
 // c[i][j] += sum_t X[t][16 i + ..] * Y[t][8 j + ..]  ("TN" product, reduction over the ROWS of both
 // operands): A fragments are movmatrix transposes of X's blocks, B fragments those of Y's blocks,
 // formed just in time so that no transposed copy of X stays live.
-template <int NT>
+template <int NT, bool INIT = false>
 __device__ __forceinline__ void mma_tn(float (&c)[2][4][4], const Blk& x, const Blk& y, bool three) {
 #pragma unroll
   for (int kk = 0; kk < 2; ++kk) {
@@ -164,6 +199,12 @@ __device__ __forceinline__ void mma_tn(float (&c)[2][4][4], const Blk& x, const 
         al[i][2] = movm_t(x.l[2 * kk + 1][2 * i]); al[i][3] = movm_t(x.l[2 * kk + 1][2 * i + 1]);
       }
     }
+    if (INIT && kk == 0) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) mma_16816_z(c[i][j], ah[i][0], ah[i][1], ah[i][2], ah[i][3], bh[j][0], bh[j][1]);
+    }
     if (three) {
 #pragma unroll
       for (int i = 0; i < 2; ++i)
@@ -174,10 +215,12 @@ __device__ __forceinline__ void mma_tn(float (&c)[2][4][4], const Blk& x, const 
 #pragma unroll
         for (int j = 0; j < NT; ++j) mma_16816(c[i][j], ah[i][0], ah[i][1], ah[i][2], ah[i][3], bl[j][0], bl[j][1]);
     }
+    if (!(INIT && kk == 0)) {
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+      for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int j = 0; j < NT; ++j) mma_16816(c[i][j], ah[i][0], ah[i][1], ah[i][2], ah[i][3], bh[j][0], bh[j][1]);
+        for (int j = 0; j < NT; ++j) mma_16816(c[i][j], ah[i][0], ah[i][1], ah[i][2], ah[i][3], bh[j][0], bh[j][1]);
+    }
   }
 }
 // Accumulator tile set c[2][4][4] (rows 16 i + g (+8), cols 8 j + 2 tg (+1)) -> row-layout blocks.
@@ -238,9 +281,9 @@ __device__ __forceinline__ void store_acc_split(const float (&c)[2][4][4], float
 
 // ---- operand sources ------------------------------------------------------------------------
 // Global: matrix m of the item lives at base[m] + r * stride[m] (fp32 rows); rows >= S read as 0.
-template <int DH>
+template <int DH, bool RELOAD = false>
 struct GmemSrc {
-  static constexpr bool kReload = false;
+  static constexpr bool kReload = RELOAD;  // re-read operand fragments (L1 / L2 hits) instead of keeping them live
   const float* base[4];
   long long stride[4];
   int S;
@@ -270,13 +313,7 @@ __device__ __forceinline__ void attn_fwd_item(const Src& src, int E, int heads, 
   src.load(q, 0, scale * NRL_LOG2E, g, tg);
   src.load(k, 1, 1.f, g, tg);
   float s[2][4][4];
-#pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) s[i][j][c] = 0.f;
-  mma_nt<KS, 4>(s, q, k, three);
+  mma_nt<KS, 4, true>(s, q, k, three);
 
   // softmax over the key axis (columns); rows 8 rb + g, rb = 2 i + half
   float inv_l[4], row_lse[4];
@@ -313,13 +350,7 @@ __device__ __forceinline__ void attn_fwd_item(const Src& src, int E, int heads, 
   src.load(v, 2, 1.f, g, tg);
   release();
   float o[2][4][4];
-#pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) o[i][j][c] = 0.f;
-  mma_nn<ND>(o, p, v, three);
+  mma_nn<ND, true>(o, p, v, three);
 
   long long grow[4];
 #pragma unroll
@@ -369,23 +400,17 @@ __device__ __forceinline__ void attn_bwd_item(const Src& src, const float* __res
 #pragma unroll
   for (int rb = 0; rb < 4; ++rb) lse2[rb] = (8 * rb + g < S) ? src.lse2(lse, grow[rb], heads, h, 8 * rb + g) : 0.f;
   float s[2][4][4], dp[2][4][4];
-#pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) { s[i][j][c] = 0.f; dp[i][j][c] = 0.f; }
   if (!kReload) {
     src.load(v, 2, 1.f, g, tg);
     src.load(go, 3, 1.f, g, tg);
     release();
   }
-  mma_nt<KS, 4>(s, q, k, three);    // S (log2 domain)  [t][u]
+  mma_nt<KS, 4, true>(s, q, k, three);    // S (log2 domain)  [t][u]
   if (kReload) {
     src.load(v, 2, 1.f, g, tg);
     src.load(go, 3, 1.f, g, tg);
   }
-  mma_nt<KS, 4>(dp, go, v, three);  // dP = dO V^T      [t][u]
+  mma_nt<KS, 4, true>(dp, go, v, three);  // dP = dO V^T      [t][u]
 
   // P = 2^(S - lse2), D_t = sum_u P dP, dS = P (dP - D)   (natural-domain gradient of the scaled scores)
 #pragma unroll
@@ -416,30 +441,19 @@ __device__ __forceinline__ void attn_bwd_item(const Src& src, const float* __res
   acc_to_blocks(ds, dp);
 
   float acc[2][4][4];
-  auto zero = [&]() {
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.f;
-  };
   // dQ = scale * dS K
-  zero();
   if (kReload) src.load(k, 1, 1.f, g, tg);
-  mma_nn<ND>(acc, ds, k, three);
+  mma_nn<ND, true>(acc, ds, k, three);
   store_acc_split<DH, ND>(acc, scale, scale, scale, scale, g_hi, g_lo, p3, grow, S, h * DH, g, tg);
   // dK = scale * dS^T Q = ln2 * dS^T Qs ;  dV = P^T dO
-  zero();
   if (kReload) src.load(q, 0, scale * NRL_LOG2E, g, tg);
-  mma_tn<ND>(acc, ds, q, three);
+  mma_tn<ND, true>(acc, ds, q, three);
   store_acc_split<DH, ND>(acc, NRL_LN2, NRL_LN2, NRL_LN2, NRL_LN2, g_hi, g_lo, p3, grow, S, E + h * DH, g, tg);
-  zero();
   if (kReload) {
     src.load(go, 3, 1.f, g, tg);
     release();
   }
-  mma_tn<ND>(acc, pb, go, three);
+  mma_tn<ND, true>(acc, pb, go, three);
   store_acc_split<DH, ND>(acc, 1.f, 1.f, 1.f, 1.f, g_hi, g_lo, p3, grow, S, 2 * E + h * DH, g, tg);
 
   if (h == 0 && p3 > 3 * E) {
@@ -471,8 +485,10 @@ attn_fwd_mma_kernel(const float* __restrict__ qkv, int E, int ldq, int heads, in
   attn_fwd_item<DH>(src, E, heads, S, seq_stride, batch_stride, scale, b, h, o_hi, o_lo, ep, lse, lane);
 }
 
-template <int DH>
-__global__ void __launch_bounds__(128, 3)
+// RELOAD: operand fragments are re-read from global memory (L1 / L2 hits) where they are needed again instead of being
+// held in registers across the item; MINB: CTAs per SM the register budget is cut for.
+template <int DH, bool RELOAD = false, int MINB = 3>
+__global__ void __launch_bounds__(128, MINB)
 attn_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o, long long ld_do,
                     const float* __restrict__ lse, int E, int ldq, int heads, int S, long long seq_stride,
                     int NB, long long batch_stride, float scale, __nv_bfloat16* __restrict__ g_hi,
@@ -482,7 +498,7 @@ attn_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o
   if (item >= (long long)NB * heads) return;
   const int b = (int)(item / heads), h = (int)(item % heads);
   const float* base = qkv + (long long)b * batch_stride * ldq + h * DH;
-  GmemSrc<DH> src;
+  GmemSrc<DH, RELOAD> src;
   src.S = S;
 #pragma unroll
   for (int m = 0; m < 3; ++m) { src.base[m] = base + m * E; src.stride[m] = seq_stride * ldq; }
