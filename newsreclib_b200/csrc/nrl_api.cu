@@ -304,6 +304,15 @@ static int launch_gemm(const Ctx& c, GemmParams& p, const CUtensorMap& ta, const
   }
   p.epi_buf_bytes = (sk.f32 && sk.sp) ? 8192 : 4096;
   p.epi_bufs = 1;
+  // register-direct fp32 sink (NRL_EPI_DIRECT=1).  Measured on B200 (profiles/r02_gemm_epilogue.md): the same time as
+  // the TMA-store epilogue (in-proj 0.181 ms either way) -- what the epilogue costs is the output's trip through L2, which
+  // these GEMMs already saturate with operand fills, not the way the bytes leave the SM.  Kept as an option: it needs no
+  // staging buffers, which an operand-stationary main loop could use.
+  static const bool direct_on = [] { const char* e = getenv("NRL_EPI_DIRECT"); return e && e[0] == '1'; }();
+  const GemmEpi& ee = p.epi;
+  p.direct = (direct_on && sk.f32 && !sk.reduce && !sk.sp && !ee.add_w && !ee.relu && !ee.pos_mask && !ee.qvec && !ee.gb &&
+              !(sk.f32_cols & 1) && !(sk.ld_f32 & 1) && !(reinterpret_cast<uintptr_t>(sk.f32) & 7)) ? 1 : 0;
+  p.out = sk.f32; p.ld_out = sk.ld_f32;
   static const int epi_dbg = [] { const char* e = getenv("NRL_EPI_DEBUG"); return e ? atoi(e) : 0; }();
   p.dbg = epi_dbg;  // timing experiments only: results are wrong when != 0
   if (p.pair) {  // CTA pairs (cta_group::2): each CTA stages its 128 rows of A and half of the B tile

@@ -77,6 +77,10 @@ struct GemmParams {
   int tiles_per_unit;  // n_tiles (unit = m-block) or 1
   int pair;            // 1: nrl_gemm_tc2_kernel (CTA pairs, cta_group::2)
   int fuse_n;          // pair + MN-major: both n-tiles accumulate in ONE k-loop (A is streamed once)
+  int direct;          // fp32 sink written straight from registers (16x256b TMEM loads, 8-byte global stores): plain or
+                       // dropout epilogues with an fp32 sink only
+  long long ld_out;    // row pitch (floats) of the fp32 sink for the direct path
+  float* out;          // its base
   int dbg;             // timing experiments only (NRL_EPI_DEBUG): low bits 1 no TMA stores, 2 no staging either, 3 no TMEM loads; bit 8: release (not relaxed) tmem-empty arrive
   GemmEpi epi;
 };
@@ -145,6 +149,43 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const CU
     const GemmEpi& e = p.epi;
     const CUtensorMap& tmOut = *tmOutP;
     const CUtensorMap& tmSp = *tmSpP;
+    if (p.direct) {
+      // ---- register-direct fp32 sink: no shared-memory staging, no TMA store (the staging buffer's turn-around --
+      // waiting for the TMA unit to have read it, behind the producer's loads -- was 16 % of the epilogue warps' time,
+      // and its reads and writes share the shared-memory port with the MMA operands)
+      const int g = lane >> 2, tq = lane & 3;
+      const int row0 = t.m0 + quarter * 32;
+      if (row0 >= p.M) return;
+      for (int c = 32 * half; c < t.n_cur; c += 32 * (GEMM_EPI_WARPS / 4)) {
+        const int col_base = t.n0 + c;
+        uint32_t r[2][16];
+        tmem_ld_16x256b_x4(t_row + (uint32_t)c, r[0]);
+        tmem_ld_16x256b_x4(t_row + (16u << 16) + (uint32_t)c, r[1]);
+        tmem_wait_ld();
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb)
+#pragma unroll
+          for (int h8 = 0; h8 < 2; ++h8) {
+            const int row = row0 + 16 * hb + 8 * h8 + g;
+            if (row >= p.M) continue;
+            uint32_t bits = 0xffffffffu;
+            if (e.drop_words) bits = __ldg(e.drop_words + (long long)row * e.drop_mw + (col_base >> 5));
+            float* orow = p.out + (long long)row * p.ld_out + col_base + 2 * tq;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (col_base + 8 * j + 2 * tq >= e.f32_cols) continue;
+              float v0 = __uint_as_float(r[hb][4 * j + 2 * h8]), v1 = __uint_as_float(r[hb][4 * j + 2 * h8 + 1]);
+              if (e.drop_words) {
+                const uint32_t b2 = bits >> (8 * j + 2 * tq);
+                v0 = (b2 & 1u) ? v0 * e.drop_scale : 0.f;
+                v1 = (b2 & 2u) ? v1 * e.drop_scale : 0.f;
+              }
+              *reinterpret_cast<float2*>(orow + 8 * j) = make_float2(v0, v1);
+            }
+          }
+      }
+      return;
+    }
     const int row_base = t.m0 + quarter * 32;
     const int row = row_base + lane;
     const bool row_ok = row < p.M;

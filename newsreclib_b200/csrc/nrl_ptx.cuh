@@ -171,6 +171,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 16 lanes x 32 consecutive fp32 columns, the m16n8 accumulator-fragment layout (measured, experiments/ldtm_layout.cu):
+// thread t gets r[4 j + 0, 1] = (lane taddr.lane + t / 4,     columns 8 j + 2 (t % 4), + 1)
+//               r[4 j + 2, 3] = (lane taddr.lane + t / 4 + 8, same columns),  j = 0..3.
+// Four adjacent threads hold 32 contiguous bytes of a row: full-sector global stores straight from registers.
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // UMMA shared-memory matrix descriptor (sm_100 format): start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout type [61,64) (2 = SWIZZLE_128B).
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo_bytes,
