@@ -45,7 +45,7 @@ def peaks():
 
 def gemm_traffic_per_launch():
     """DRAM bytes per GEMM launch from the committed ncu --set full capture (None if absent)."""
-    p = os.path.join(ROOT, "profiles", "r01f_gemm_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")
     try:
         return json.load(open(p))["dram_bytes_per_launch_avg"]
     except (OSError, KeyError, ValueError):
@@ -765,7 +765,7 @@ def main():
                 "peak_source": f"{src} bf16 dense, sustained (kernel timed inside a long step)",
                 "traffic": gemm_traffic_per_launch(), "traffic_unit": "bytes of DRAM traffic per GEMM launch "
                 "(ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the step's 18 launches; "
-                "profiles/r01f_gemm_traffic.json)",
+                "profiles/r02_gemm_traffic.json)",
                 "algorithmic_gflop_per_step": flops_step / 1e9,
                 "issued_passes": 3 if prec == ops.PREC_BF16X3 else 1,
                 "kernel_ms_per_step": gemm_ms, "launches_per_step": gemm_launches,

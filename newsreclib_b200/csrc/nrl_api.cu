@@ -116,6 +116,8 @@ static int device_init() {
                                 GEMM_SMEM_LIMIT));
   CUDA_TRY(cudaFuncSetAttribute(nrl_gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 GEMM_SMEM_LIMIT));
+  CUDA_TRY(cudaFuncSetAttribute(nrl_gemm_tc2a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                GEMM_SMEM_LIMIT));
   g_dev.ok = true;
   return NRL_OK;
 }
@@ -315,6 +317,22 @@ static int launch_gemm(const Ctx& c, GemmParams& p, const CUtensorMap& ta, const
   p.out = sk.f32; p.ld_out = sk.ld_f32;
   static const int epi_dbg = [] { const char* e = getenv("NRL_EPI_DEBUG"); return e ? atoi(e) : 0; }();
   p.dbg = epi_dbg;  // timing experiments only: results are wrong when != 0
+  if (p.astat) {  // A-stationary pair kernel: the unit's A panel resident, B halves through a ring, register-direct epilogue
+    const int kb_total = (p.K + GEMM_BK - 1) / GEMM_BK;
+    const int a_bytes = kb_total * p.planes * GEMM_A_BYTES;
+    const int b_stage = p.planes * (p.BN / 2) * 128;
+    int bst = (GEMM_SMEM_LIMIT - 1024 - GEMM_BAR_BYTES - a_bytes) / b_stage;
+    if (bst > GEMM_B_STAGES_MAX) bst = GEMM_B_STAGES_MAX;
+    if (bst < 2) return fail(NRL_ERR_UNSUPPORTED, "A-stationary GEMM does not fit shared memory");
+    p.direct = 1;
+    p.stages = bst;
+    const int smem3 = 1024 + a_bytes + bst * b_stage + GEMM_BAR_BYTES;
+    const int m_pairs = (p.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+    const int clusters = m_pairs < g_dev.sm_count / 2 ? m_pairs : g_dev.sm_count / 2;
+    nrl_gemm_tc2a_kernel<<<2 * clusters, GEMM_THREADS, smem3, c.stream>>>(ta, tb, tout, tsp, p);
+    LAUNCH_CHECK(name);
+    return NRL_OK;
+  }
   if (p.pair) {  // CTA pairs (cta_group::2): each CTA stages its 128 rows of A and half of the B tile
     int half_b = p.mn_major ? (p.BN / 2 + 63) / 64 * 8192 : p.BN / 2 * 128;
     if (p.fuse_n) half_b += (((p.n_extent - p.BN + 15) & ~15) / 2 + 63) / 64 * 8192;  // boxes of the second n-tile
@@ -380,6 +398,23 @@ static int gemm_nt(const Ctx& c, const bf16* A, long long M, int a_pitch, const 
   static const bool pair_on = [] { const char* e = getenv("NRL_GEMM_PAIR"); return !(e && e[0] == '0'); }();
   p.pair = (pair_on && (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM) >= g_dev.sm_count / 2) ? 1 : 0;
   p.BN = balanced_bn(p.n_extent, p.planes, sk.f32 && sk.sp, 0, epi.score != nullptr, p.pair != 0);
+  // A-stationary pair kernel (nrl_gemm_tc2a_kernel) for plain / dropout fp32-sink GEMMs whose A panel fits: the n-tile is
+  // narrowed until THREE B stages fit beside the panel (measured: 240-wide tiles with a 2-deep ring 0.183 ms, 160-wide
+  // with a 3-deep ring 0.175 ms for the in-projection, against 0.189 ms for the streaming kernel; NRL_GEMM_ASTAT=0: off)
+  static const bool astat_on = [] { const char* e = getenv("NRL_GEMM_ASTAT"); return !(e && e[0] == '0'); }();
+  p.astat = 0;
+  if (p.pair && astat_on && sk.f32 && !sk.reduce && !sk.sp && !epi.add_w && !epi.relu && !epi.pos_mask && !epi.qvec &&
+      !epi.gb && !(sk.f32_cols & 1) && !(sk.ld_f32 & 1) && !(reinterpret_cast<uintptr_t>(sk.f32) & 7)) {
+    const int kb_total = (K + GEMM_BK - 1) / GEMM_BK;
+    const int avail = GEMM_SMEM_LIMIT - 1024 - GEMM_BAR_BYTES - kb_total * p.planes * GEMM_A_BYTES;
+    int bn = avail > 0 ? (avail / (3 * p.planes * 64)) & ~31 : 0;
+    if (bn > 256) bn = 256;
+    if (kb_total <= GEMM_A_SLOTS && bn >= 64 && p.n_extent > bn) {
+      const int nt = (p.n_extent + bn - 1) / bn;
+      p.BN = round_up((p.n_extent + nt - 1) / nt, 32);
+      p.astat = 1;
+    }
+  }
   if (epi.score && p.BN < N) return fail(NRL_ERR_UNSUPPORTED, "score fusion needs a single n-tile (N <= 256)");
   if (epi.score) CUDA_TRY(cudaMemsetAsync(epi.score, 0, (size_t)M * sizeof(float), c.stream));
   p.k_splits = 1;

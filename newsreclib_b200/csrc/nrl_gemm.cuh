@@ -77,6 +77,7 @@ struct GemmParams {
   int tiles_per_unit;  // n_tiles (unit = m-block) or 1
   int pair;            // 1: nrl_gemm_tc2_kernel (CTA pairs, cta_group::2)
   int fuse_n;          // pair + MN-major: both n-tiles accumulate in ONE k-loop (A is streamed once)
+  int astat;           // nrl_gemm_tc2a_kernel: A panel of a unit resident in shared memory
   int direct;          // fp32 sink written straight from registers (16x256b TMEM loads, 8-byte global stores): plain or
                        // dropout epilogues with an fp32 sink only
   long long ld_out;    // row pitch (floats) of the fp32 sink for the direct path
@@ -739,6 +740,199 @@ nrl_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   tc_fence_before();
   cluster_sync_all();  // the leader's MMAs read the peer's shared memory: nobody leaves early
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, GEMM_TMEM_COLS);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// A-stationary CTA-pair NT GEMM ("tc2a").  The pair kernel above re-streams the A panel of a 256-row unit once per
+// n-tile (in-projection: 4 x) and its main loop is bound by the L2 -> SM fill rate: 62 KB per k-block and SM against
+// 1440 clocks of MMA is 43 B / clk / SM = the ~6.3 KB / clk the chip's L2 delivers, so the tensor pipe idles 40 % of
+// the time (ncu, profiles/r02_ncu_gemm.md).  Here the A panel of a unit -- all k-blocks, both planes, 160 KB at
+// K = 304 -- stays in shared memory while the n-tiles of the unit stream only their B halves through a small ring:
+// fill traffic of the in-projection drops from 2.3 MB to 1.4 MB per unit.  The room comes from the register-direct
+// epilogue (no staging buffers).  A slot kb of the NEXT unit is reloaded as soon as the LAST n-tile of the current unit
+// has consumed it (per-k-block full / empty barriers), so the pipeline never drains between units.
+//   barriers: a_full[kb] / b_full[s] (leader only, expect_tx of both CTAs' bytes), a_empty[kb] / b_empty[s] / tmem_full[a]
+//   (multicast tcgen05.commit, one arrival per CTA), tmem_empty[a] (leader only, 16 arrivals).
+// Requirements (host checks): K-major operands, k_splits == 1, fp32 sink with a plain or dropout epilogue (direct path),
+// ceil(K / 64) <= GEMM_A_SLOTS.
+// ------------------------------------------------------------------------------------------
+constexpr int GEMM_A_SLOTS = 8;
+constexpr int GEMM_B_STAGES_MAX = 4;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+nrl_gemm_tc2a_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmSp,
+                     const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int kb_total = (p.K + GEMM_BK - 1) / GEMM_BK;
+  const uint32_t half_n = (uint32_t)p.BN / 2u;
+  const uint32_t a_slot_bytes = (uint32_t)p.planes * GEMM_A_BYTES;
+  const uint32_t b_bytes = half_n * 128u;                         // one plane of this CTA's half of a B k-block
+  const uint32_t b_stage_bytes = (uint32_t)p.planes * b_bytes;
+  const uint32_t b_base = smem_base + (uint32_t)kb_total * a_slot_bytes;
+  const uint32_t bar_base = b_base + (uint32_t)p.stages * b_stage_bytes;
+  auto a_full = [&](int kb) { return bar_base + 8u * kb; };
+  auto a_empty = [&](int kb) { return bar_base + 8u * (GEMM_A_SLOTS + kb); };
+  auto b_full = [&](int s) { return bar_base + 8u * (2 * GEMM_A_SLOTS + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (2 * GEMM_A_SLOTS + GEMM_B_STAGES_MAX + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * GEMM_A_SLOTS + 2 * GEMM_B_STAGES_MAX + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * GEMM_A_SLOTS + 2 * GEMM_B_STAGES_MAX + 2 + s); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * GEMM_A_SLOTS + 2 * GEMM_B_STAGES_MAX + 4);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const bool one = elect_one();
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int m_pairs = (p.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+  const int n_tiles = (p.n_extent + p.BN - 1) / p.BN;
+  const int num_units = m_pairs;
+
+  if (threadIdx.x == 0) {
+    for (int kb = 0; kb < kb_total; ++kb) {
+      mbar_init(a_full(kb), 1);
+      mbar_init(a_empty(kb), 1);
+    }
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(b_full(s), 1);
+      mbar_init(b_empty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 2 * GEMM_EPI_WARPS);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_ptr_addr, GEMM_TMEM_COLS);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+
+  auto tile_of = [&](int unit, int j) {
+    GemmTile t;
+    t.m0 = unit * 2 * GEMM_BM + (int)rank * GEMM_BM;
+    t.n0 = j * p.BN;
+    t.n_cur = min(p.BN, (p.n_extent - t.n0 + 15) & ~15);
+    t.kb0 = 0;
+    t.kb1 = kb_total;
+    return t;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (one) {
+      int bs = 0;
+      uint32_t bphase = 0, uiter = 0;
+      for (int unit = cluster_id; unit < num_units; unit += num_clusters, ++uiter) {
+        const uint32_t aph = uiter & 1u;
+        for (int j = 0; j < n_tiles; ++j) {
+          const GemmTile t = tile_of(unit, j);
+          const int b0 = t.n0 + (int)rank * (t.n_cur / 2);
+          for (int kb = 0; kb < kb_total; ++kb) {
+            if (j == 0) {  // this unit's A k-block: its slot is free once the previous unit's last n-tile has used it
+              mbar_wait(a_empty(kb), aph ^ 1u);
+              const uint32_t lead = mapa_shared(a_full(kb), 0);
+              if (leader) mbar_expect_tx(a_full(kb), 2u * a_slot_bytes);
+              for (int pl = 0; pl < p.planes; ++pl)
+                tma_load_3d_pair(smem_base + (uint32_t)kb * a_slot_bytes + (uint32_t)pl * GEMM_A_BYTES, &tmA, lead,
+                                 kb * GEMM_BK, t.m0, pl);
+            }
+            mbar_wait(b_empty(bs), bphase ^ 1u);
+            const uint32_t leadb = mapa_shared(b_full(bs), 0);
+            if (leader) mbar_expect_tx(b_full(bs), 2u * b_stage_bytes);
+            for (int pl = 0; pl < p.planes; ++pl)
+              tma_load_3d_pair(b_base + (uint32_t)bs * b_stage_bytes + (uint32_t)pl * b_bytes, &tmB, leadb, kb * GEMM_BK, b0, pl);
+            if (++bs == p.stages) { bs = 0; bphase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (one && leader) {
+      int bs = 0, acc = 0;
+      uint32_t bphase = 0, acc_phase = 0, uiter = 0;
+      for (int unit = cluster_id; unit < num_units; unit += num_clusters, ++uiter) {
+        const uint32_t aph = uiter & 1u;
+        for (int j = 0; j < n_tiles; ++j) {
+          const GemmTile t = tile_of(unit, j);
+          const uint32_t idesc = umma_idesc_bf16(2 * GEMM_BM, t.n_cur, 0, 0);
+          mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+          uint32_t accumulate = 0;
+          for (int kb = 0; kb < kb_total; ++kb) {
+            if (j == 0) mbar_wait(a_full(kb), aph);
+            mbar_wait(b_full(bs), bphase);
+            tc_fence_after();
+            const uint32_t a_src = smem_base + (uint32_t)kb * a_slot_bytes;
+            const uint32_t b_src = b_base + (uint32_t)bs * b_stage_bytes;
+            const int nks = min(GEMM_BK / 16, (p.K - kb * GEMM_BK + 15) / 16);
+            for (int k = 0; k < nks; ++k) {
+              const uint32_t koff = k * 32;
+              const uint64_t a_hi = umma_desc_sw128(a_src + koff, 16, 1024);
+              const uint64_t b_hi = umma_desc_sw128(b_src + koff, 16, 1024);
+              if (p.planes == 2) {
+                const uint64_t a_lo = umma_desc_sw128(a_src + GEMM_A_BYTES + koff, 16, 1024);
+                const uint64_t b_lo = umma_desc_sw128(b_src + b_bytes + koff, 16, 1024);
+                umma_bf16_pair(d_tmem, a_lo, b_hi, idesc, accumulate);
+                umma_bf16_pair(d_tmem, a_hi, b_lo, idesc, 1);
+                umma_bf16_pair(d_tmem, a_hi, b_hi, idesc, 1);
+              } else {
+                umma_bf16_pair(d_tmem, a_hi, b_hi, idesc, accumulate);
+              }
+              accumulate = 1;
+            }
+            umma_commit_pair(b_empty(bs));
+            if (j == n_tiles - 1) umma_commit_pair(a_empty(kb));  // the unit is done with this A k-block
+            if (++bs == p.stages) { bs = 0; bphase ^= 1u; }
+          }
+          umma_commit_pair(tfull_bar(acc));
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..9), both CTAs: register-direct fp32 sink =====================
+    const int quarter = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0, chunk_ctr = 0;
+    for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
+      for (int j = 0; j < n_tiles; ++j) {
+        const GemmTile t = tile_of(unit, j);
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(quarter * 32) << 16);
+        gemm_epilogue_tile(p, &tmOut, &tmSp, t, t_row, quarter, lane, 0u, 0u, chunk_ctr, one, (warp - 2) >> 2, 0u);
+        tc_fence_before();
+        __syncwarp();
+        if (one) {
+          if (leader) mbar_arrive_relaxed(tempty_bar(acc));
+          else mbar_arrive_cluster_relaxed(mapa_shared(tempty_bar(acc), 0));
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc_pair(tmem_base, GEMM_TMEM_COLS);

@@ -19,7 +19,11 @@ def load(path):
 
 
 def one_step(seq):
+    """The launches between two consecutive adam_kernel launches; a capture of exactly one profiled step
+    (profiles/ncu_step.py: cudaProfilerStart/Stop around one step) is taken whole."""
     ad = [i for i, s in enumerate(seq) if "adam_kernel" in s[1]]
+    if len(ad) < 3:
+        return seq
     return seq[ad[-3] + 1: ad[-2] + 1]
 
 
