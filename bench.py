@@ -466,38 +466,56 @@ def extra_configs(args, dev, rank, world, exchange_mode, steps=15, warmup=3):
     entry("nrms_module_dropin", nrms_module)
 
     # -- configs[3]: NRMS-PLM, roberta-base-shaped news encoder (random init), layers 0-7 frozen, B = 8 per GPU.
-    # The transformer is the third-party HF module on torch; only the MHSA + additive head is this library's code.
+    # transformer_impl="native": embeddings + 12 layers on the sm_100a encoder + the MHSA / additive
+    # head; the HF torch module on the same weights and batches beside it ("with_hf_transformer").
     def nrms_plm():
         import numpy as np
         from transformers import RobertaConfig, RobertaModel
         from newsreclib_b200.models.general_rec.nrms_module import NRMSModule
         Bp, Ep, Hp = 8, 768, 16
-        torch.manual_seed(1234)
-        plm = RobertaModel(RobertaConfig(vocab_size=50265, max_position_embeddings=514, type_vocab_size=1), add_pooling_layer=False)
-        m = NRMSModule(dataset_attributes=["title", "category"], attributes2encode=["title"], use_plm=True,
-                       pretrained_embeddings_path=None, plm_model=plm, frozen_layers=list(range(8)), embed_dim=Ep, num_heads=Hp,
-                       query_dim=Q, **_module_kwargs(outputs))
-        tr = ModuleTrainer(m.to(dev), lr=1e-5, exchange="nccl")
-        rng = np.random.default_rng(1234 + rank)
 
-        def plm_news(n):
-            lens = np.clip(rng.poisson(16, n), 6, 96)
-            T = int(lens.max())
-            ids = rng.integers(3, 50265, (n, T))
-            mask = np.arange(T)[None, :] < lens[:, None]
-            ids[~mask] = 1
-            return {"input_ids": torch.from_numpy(ids).to(dev), "attention_mask": torch.from_numpy(mask.astype(np.int64)).to(dev)}
-        bs = []
-        for i in range(2):
-            hb = make_batch(Bp, 1000, hist="fixed", max_hist=HIST, cand="train", seed=40 + rank * 10 + i, max_title_len=L)
-            b = _dev_batch(hb, dev)
-            b["x_hist"]["title"], b["x_cand"]["title"] = plm_news(Bp * HIST), plm_news(Bp * CAND)
-            bs.append(b)
-        ms = _timed_steps(lambda i: tr.train_step(bs[i % 2]), 5, 2, dev, world)
-        r = imps(ms, Bp)
-        r.update(workload=f"BASELINE configs[3]: NRMS-PLM train step, roberta-base-shaped encoder (random init, layers 0-7 frozen, "
-                          f"fp32 HF/torch transformer = third-party code) + sm_100a MHSA/additive head (768-d, 16 heads), B={Bp}/GPU, "
-                          f"{HIST} + {CAND} news per impression, titles padded to the longest (<= 96 tokens), nccl exchange")
+        def run(impl, max_len, precision=None):
+            torch.manual_seed(1234)
+            plm = RobertaModel(RobertaConfig(vocab_size=50265, max_position_embeddings=514, type_vocab_size=1),
+                               add_pooling_layer=False)
+            m = NRMSModule(dataset_attributes=["title", "category"], attributes2encode=["title"], use_plm=True,
+                           pretrained_embeddings_path=None, plm_model=plm, frozen_layers=list(range(8)), embed_dim=Ep,
+                           num_heads=Hp, query_dim=Q, transformer_impl=impl, **_module_kwargs(outputs))
+            if precision is not None:
+                m.news_encoder.text_encoders["title"].precision = precision
+            tr = ModuleTrainer(m.to(dev), lr=1e-5, exchange="nccl")
+            rng = np.random.default_rng(1234 + rank)
+
+            def plm_news(n):
+                lens = np.clip(rng.poisson(16, n), 6, max_len)
+                lens[0] = max_len if max_len == 96 else lens[0]  # tokenizer(padding=True): the batch is padded to its longest
+                T = int(lens.max())
+                ids = rng.integers(3, 50265, (n, T))
+                mask = np.arange(T)[None, :] < lens[:, None]
+                ids[~mask] = 1
+                return {"input_ids": torch.from_numpy(ids).to(dev), "attention_mask": torch.from_numpy(mask.astype(np.int64)).to(dev)}
+            bs = []
+            for i in range(2):
+                hb = make_batch(Bp, 1000, hist="fixed", max_hist=HIST, cand="train", seed=40 + rank * 10 + i, max_title_len=L)
+                b = _dev_batch(hb, dev)
+                b["x_hist"]["title"], b["x_cand"]["title"] = plm_news(Bp * HIST), plm_news(Bp * CAND)
+                bs.append(b)
+            ms = _timed_steps(lambda i: tr.train_step(bs[i % 2]), 5, 2, dev, world)
+            r = imps(ms, Bp)
+            r["tokens_per_title_padded"] = [int(b["x_hist"]["title"]["input_ids"].shape[1]) for b in bs]
+            del tr, m, plm, bs
+            torch.cuda.empty_cache()
+            return r
+        r = run("native", 40)
+        r.update(workload=f"BASELINE configs[3]: NRMS-PLM train step, roberta-base-shaped encoder (random init, layers 0-7 "
+                          f"frozen, embeddings + layers 8-11 trained): transformer on the sm_100a encoder (bf16x3 tcgen05 GEMMs, "
+                          f"tensor-core attention, fp32-equivalent) + sm_100a MHSA/additive head (768-d, 16 heads), B={Bp}/GPU, "
+                          f"{HIST} + {CAND} news per impression, titles of 6-40 tokens padded to the longest of the batch, all "
+                          f"three dropouts on, nccl exchange")
+        r["with_hf_transformer"] = run("hf", 40)
+        r["titles_padded_to_96_tokens"] = {"native": run("native", 96), "hf": run("hf", 96)}
+        from newsreclib_b200 import ops as _ops
+        r["native_bf16_single_pass"] = run("native", 40, _ops.PREC_BF16)
         return r
     entry("nrms_plm_roberta_base", nrms_plm)
 

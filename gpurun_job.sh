@@ -1,6 +1,9 @@
-# the standard GPU job of this repo: parity tests, smoke, headline bench (run with: gpurun -- 'bash gpurun_job.sh')
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q --timeout 600 -x 2>&1 | tail -15 > gpurun_out/pytest_gpu.log; cat gpurun_out/pytest_gpu.log
-python -c "from __graft_entry__ import smoke; smoke()" 2>&1 | tail -1
-timeout 600 python bench.py --steps 50 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err
-cut -c1-400 gpurun_out/bench.json
+timeout 900 python -m pytest tests/test_gpu_tfm.py -m gpu -q --timeout 600 -s 2>&1 | grep -v "^$" | tail -60 > gpurun_out/r02f_pytest_tfm.log; grep "tfm\]\|passed\|failed" gpurun_out/r02f_pytest_tfm.log
+timeout 1200 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_f3.json 2> gpurun_out/bench_f3.err; tail -3 gpurun_out/bench_f3.err
+python - <<'PY'
+import json
+j=json.loads(open("gpurun_out/bench_f3.json").read())
+print(j["ms_per_step"], j["value"])
+print(json.dumps(j["configs"].get("nrms_plm_roberta_base"), indent=1))
+PY

@@ -325,6 +325,87 @@ int nrl_nrms_step_host(const long long* hist_ids_host, const long long* cand_ids
                        int do_backward, nrl_block_grads* news_grads, nrl_block_grads* user_grads,
                        float* d_table, void* ws, size_t ws_bytes, int precision, void* stream);
 
+/* ---- PLM news encoder internals ---------------------------------------
+ * The transformer inside PLM.forward (encoders/news/text.py:67-73 constructor / freezing, :92
+ * `self.plm_model(**text)[0]`): a HF RobertaModel / BertModel-shaped post-LN encoder -- embeddings
+ * (word + position + token type -> LayerNorm -> dropout) and `num_layers` layers of
+ *   h1 = LN(x + drop(MHSA(x) W_ao + b)),   h2 = LN(h1 + drop(gelu(h1 W_i + b) W_o + b)),
+ * key-padding mask from attention_mask, exact (erf) GELU, head dim 64, T <= 128 tokens.
+ * The third-party algorithm restated here is transformers' modeling_roberta.py (pinned by the
+ * reference at transformers 4.x; identical maths in the 5.5 of this image, which is what the
+ * golden vectors under tests/golden/tfm_*.npz were minted with).  state_dict names in comments
+ * are relative to `plm_model.` (embeddings.*) and `plm_model.encoder.layer.<i>.` (layers).
+ * A layer whose nrl_tfm_layer_grads is all NULL is FROZEN (text.py:70-73): only the data gradient
+ * passes through it. */
+typedef struct {
+  const float* word;   /* embeddings.word_embeddings.weight        [vocab, D]   (row pad_idx never updated) */
+  const float* pos;    /* embeddings.position_embeddings.weight    [max_pos, D] (row pad_idx never updated) */
+  const float* type0;  /* embeddings.token_type_embeddings.weight  row 0 [D]    (token_type_ids are all 0) */
+  const float* ln_g;   /* embeddings.LayerNorm.weight [D] */
+  const float* ln_b;   /* embeddings.LayerNorm.bias   [D] */
+} nrl_tfm_embed_params;
+typedef struct {
+  float *word, *pos, *type0, *ln_g, *ln_b;
+} nrl_tfm_embed_grads;
+typedef struct {
+  const float *q_w, *q_b;     /* attention.self.query.{weight,bias}   [D, D], [D] */
+  const float *k_w, *k_b;     /* attention.self.key.*                               */
+  const float *v_w, *v_b;     /* attention.self.value.*                             */
+  const float *ao_w, *ao_b;   /* attention.output.dense.*             [D, D], [D] */
+  const float *ln1_g, *ln1_b; /* attention.output.LayerNorm.*         [D]         */
+  const float *i_w, *i_b;     /* intermediate.dense.*                 [I, D], [I] */
+  const float *o_w, *o_b;     /* output.dense.*                       [D, I], [D] */
+  const float *ln2_g, *ln2_b; /* output.LayerNorm.*                   [D]         */
+} nrl_tfm_layer_params;
+typedef struct {
+  float *q_w, *q_b, *k_w, *k_b, *v_w, *v_b, *ao_w, *ao_b, *ln1_g, *ln1_b, *i_w, *i_b, *o_w, *o_b,
+      *ln2_g, *ln2_b;
+} nrl_tfm_layer_grads;
+typedef struct {
+  int hidden;        /* D: config.hidden_size (multiple of 64, <= 1024) */
+  int heads;         /* config.num_attention_heads; D / heads must be 64 */
+  int intermediate;  /* I: config.intermediate_size (multiple of 16) */
+  int num_layers;    /* layers handled by the call */
+  int vocab;         /* config.vocab_size */
+  int max_pos;       /* config.max_position_embeddings */
+  int pad_idx;       /* config.pad_token_id (RoBERTa position ids start at pad_idx + 1); < 0: positions 0..T-1 (BERT) */
+  float ln_eps;      /* config.layer_norm_eps */
+  float hidden_dropout; /* config.hidden_dropout_prob (embeddings, attention output, layer output) */
+  float attn_dropout;   /* config.attention_probs_dropout_prob */
+} nrl_tfm_dims;
+
+/* packed bf16 hi/lo GEMM operands of the layers' weights (forward + transposed copies).  They
+ * change only when the weights do: the caller re-packs layers [first, first + count) after an
+ * optimizer step (frozen layers: once).  `layers` points at the parameters of layer `first`. */
+size_t nrl_tfm_wpack_bytes(nrl_tfm_dims dims);
+int nrl_tfm_pack_weights(const nrl_tfm_layer_params* layers, int first, int count, nrl_tfm_dims dims,
+                         void* wpack, size_t wpack_bytes, int precision, void* stream);
+/* activations of all layers (kept for the backward pass) + backward scratch */
+size_t nrl_tfm_ws_bytes(long long N, int T, nrl_tfm_dims dims);
+/* input_ids / attention_mask: int64 [N, T] (the tokenizer output the reference collate emits,
+ * rec_dataset.py:181-183; attention_mask may be NULL = all ones).  out: last hidden state
+ * [N, T, D] fp32 (`self.plm_model(**text)[0]`).  training != 0 applies the three dropouts. */
+int nrl_tfm_encoder_fwd(const long long* input_ids, const long long* attention_mask, int N, int T,
+                        const nrl_tfm_embed_params* embed, const nrl_tfm_layer_params* layers,
+                        nrl_tfm_dims dims, int training, unsigned long long seed, const void* wpack,
+                        float* out, void* ws, size_t ws_bytes, int precision, void* stream);
+/* d_out [N, T, D] -> parameter gradients (+=).  embed_grads NULL: embeddings frozen.
+ * layer_grads[i] all-NULL: layer i frozen.  Same ids / mask / seed / ws as the forward call. */
+int nrl_tfm_encoder_bwd(const long long* input_ids, const long long* attention_mask, int N, int T,
+                        const nrl_tfm_embed_params* embed, const nrl_tfm_layer_params* layers,
+                        nrl_tfm_dims dims, int training, unsigned long long seed, const void* wpack,
+                        const float* d_out, const nrl_tfm_embed_grads* embed_grads,
+                        const nrl_tfm_layer_grads* layer_grads, void* ws, size_t ws_bytes,
+                        int precision, void* stream);
+/* keep-flags of the attention-probability dropout of (layer, title n, head h): keep [T][T] bytes
+ * (query-major), for tests that replay the kernel's own mask in the oracle */
+int nrl_tfm_attn_dropout_mask(unsigned char* keep, int layer, int n, int h, int heads, int T,
+                              unsigned long long seed, float p, void* stream);
+/* keep-flags of the hidden dropouts: site 0 = embeddings, 1 + 2 l = attention output of layer l,
+ * 2 + 2 l = layer output of layer l; keep [R = N T][D] bytes */
+int nrl_tfm_hidden_dropout_mask(unsigned char* keep, long long R, int D, int site,
+                                unsigned long long seed, float p, void* stream);
+
 /* ---- test / measurement helpers ----------------------------------------------------------- */
 /* keep[i] = 1 iff element i of dropout site `site` (0 = after the embedding, 1 = after the
  * MHSA) is kept for (seed, p): lets a test feed the very same mask to the CPU oracle. */

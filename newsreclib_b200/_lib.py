@@ -66,6 +66,29 @@ class Dims(C.Structure):
     _fields_ = [("embed_dim", C.c_int), ("num_heads", C.c_int), ("query_dim", C.c_int)]
 
 
+TFM_EMBED_FIELDS = ("word", "pos", "type0", "ln_g", "ln_b")
+TFM_LAYER_FIELDS = ("q_w", "q_b", "k_w", "k_b", "v_w", "v_b", "ao_w", "ao_b", "ln1_g", "ln1_b", "i_w", "i_b", "o_w",
+                    "o_b", "ln2_g", "ln2_b")
+
+
+class TfmEmbed(C.Structure):
+    """``nrl_tfm_embed_params`` / ``nrl_tfm_embed_grads`` (five float pointers)."""
+
+    _fields_ = [(n, C.c_void_p) for n in TFM_EMBED_FIELDS]
+
+
+class TfmLayer(C.Structure):
+    """``nrl_tfm_layer_params`` / ``nrl_tfm_layer_grads`` (sixteen float pointers)."""
+
+    _fields_ = [(n, C.c_void_p) for n in TFM_LAYER_FIELDS]
+
+
+class TfmDims(C.Structure):
+    _fields_ = [("hidden", C.c_int), ("heads", C.c_int), ("intermediate", C.c_int), ("num_layers", C.c_int),
+                ("vocab", C.c_int), ("max_pos", C.c_int), ("pad_idx", C.c_int), ("ln_eps", C.c_float),
+                ("hidden_dropout", C.c_float), ("attn_dropout", C.c_float)]
+
+
 PREC_BF16X3 = 0
 PREC_BF16 = 1
 
@@ -122,6 +145,13 @@ SIGNATURES = {
                            _I, _F, _I, _ULL, _VP, _VP, _I, _BP, _BP, _VP, _VP, _SZ, _I, _VP]),
     "nrl_nrms_step_host": (_I, [_VP, _VP, _VP, _VP, _VP, _LL, _LL, _I, _I, _I, _I, _VP, _LL, _BP, _BP, Dims,
                                 _I, _F, _I, _ULL, _VP, _VP, _I, _BP, _BP, _VP, _VP, _SZ, _I, _VP]),
+    "nrl_tfm_wpack_bytes": (_SZ, [TfmDims]),
+    "nrl_tfm_pack_weights": (_I, [_VP, _I, _I, TfmDims, _VP, _SZ, _I, _VP]),
+    "nrl_tfm_ws_bytes": (_SZ, [_LL, _I, TfmDims]),
+    "nrl_tfm_encoder_fwd": (_I, [_VP, _VP, _I, _I, _VP, _VP, TfmDims, _I, _ULL, _VP, _VP, _VP, _SZ, _I, _VP]),
+    "nrl_tfm_encoder_bwd": (_I, [_VP, _VP, _I, _I, _VP, _VP, TfmDims, _I, _ULL, _VP, _VP, _VP, _VP, _VP, _SZ, _I, _VP]),
+    "nrl_tfm_attn_dropout_mask": (_I, [_VP, _I, _I, _I, _I, _I, _ULL, _F, _VP]),
+    "nrl_tfm_hidden_dropout_mask": (_I, [_VP, _LL, _I, _I, _ULL, _F, _VP]),
     "nrl_dropout_mask": (_I, [_VP, _LL, _ULL, _I, _F, _VP]),
     "nrl_gemm_test_ws_bytes": (_SZ, [_I, _I, _I]),
     "nrl_gemm_test": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _VP, _SZ, _VP]),

@@ -20,6 +20,7 @@
 #include "nrl_attn_mma.cuh"
 #include "nrl_naml.cuh"
 #include "nrl_exchange.cuh"
+#include "nrl_tfm.cuh"
 
 using namespace nrl;
 typedef __nv_bfloat16 bf16;
@@ -312,7 +313,8 @@ static int launch_gemm(const Ctx& c, GemmParams& p, const CUtensorMap& ta, const
   // staging buffers, which an operand-stationary main loop could use.
   static const bool direct_on = [] { const char* e = getenv("NRL_EPI_DIRECT"); return e && e[0] == '1'; }();
   const GemmEpi& ee = p.epi;
-  p.direct = (direct_on && sk.f32 && !sk.reduce && !sk.sp && !ee.add_w && !ee.relu && !ee.pos_mask && !ee.qvec && !ee.gb &&
+  p.direct = (direct_on && sk.f32 && !sk.reduce && !sk.sp && !ee.add_w && !ee.relu && !ee.pos_mask && !ee.qvec && !ee.gb && !ee.gelu &&
+              !ee.add_mat && !ee.gelu_pre &&
               !(sk.f32_cols & 1) && !(sk.ld_f32 & 1) && !(reinterpret_cast<uintptr_t>(sk.f32) & 7)) ? 1 : 0;
   p.out = sk.f32; p.ld_out = sk.ld_f32;
   static const int epi_dbg = [] { const char* e = getenv("NRL_EPI_DEBUG"); return e ? atoi(e) : 0; }();
@@ -404,7 +406,7 @@ static int gemm_nt(const Ctx& c, const bf16* A, long long M, int a_pitch, const 
   static const bool astat_on = [] { const char* e = getenv("NRL_GEMM_ASTAT"); return !(e && e[0] == '0'); }();
   p.astat = 0;
   if (p.pair && astat_on && sk.f32 && !sk.reduce && !sk.sp && !epi.add_w && !epi.relu && !epi.pos_mask && !epi.qvec &&
-      !epi.gb && !(sk.f32_cols & 1) && !(sk.ld_f32 & 1) && !(reinterpret_cast<uintptr_t>(sk.f32) & 7)) {
+      !epi.gb && !epi.gelu && !epi.add_mat && !epi.gelu_pre && !(sk.f32_cols & 1) && !(sk.ld_f32 & 1) && !(reinterpret_cast<uintptr_t>(sk.f32) & 7)) {
     const int kb_total = (K + GEMM_BK - 1) / GEMM_BK;
     const int avail = GEMM_SMEM_LIMIT - 1024 - GEMM_BAR_BYTES - kb_total * p.planes * GEMM_A_BYTES;
     int bn = avail > 0 ? (avail / (3 * p.planes * 64)) & ~31 : 0;
@@ -1957,5 +1959,7 @@ int nrl_gemm_test_planes(const float* A, const float* B, float* out, int M, int 
   LAUNCH_CHECK("planes_to_f32");
   return NRL_OK;
 }
+
+#include "nrl_tfm_api.cuh"
 
 }  // extern "C"

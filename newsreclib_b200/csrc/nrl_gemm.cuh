@@ -52,6 +52,10 @@ struct GemmEpi {
   // tanh + query dot ; sinks
   const float* add_w;   const float* add_vec; long long ld_addvec; int add_L;
   int relu;             // x = max(x, 0)  (CNN / category-encoder forward)
+  int gelu;             // the PLANE sink receives gelu(x) = 0.5 x (1 + erf(x / sqrt 2)) (HF "gelu"), the fp32 sink keeps
+                        // the pre-activation x (what the backward pass needs): transformer feed-forward
+  const float* add_mat; long long ld_addmat;  // x += add_mat[row, col] after dropout (residual connections)
+  const float* gelu_pre; long long ld_gelu;   // x *= gelu'(gelu_pre[row, col])  (feed-forward backward)
   const float* pos_mask; long long ld_pos;  // x = pos_mask[row, col] > 0 ? x : 0  (ReLU backward)
   const uint32_t* drop_words; int drop_mw; float drop_scale;  // keep-bit words [row][drop_mw], or null
   const float* qvec;    float* score;         // x = tanh(x); score[row] = sum_col x * qvec[col]
@@ -85,6 +89,12 @@ struct GemmParams {
   int dbg;             // timing experiments only (NRL_EPI_DEBUG): low bits 1 no TMA stores, 2 no staging either, 3 no TMEM loads; bit 8: release (not relaxed) tmem-empty arrive
   GemmEpi epi;
 };
+
+// exact (erf) GELU of torch / HF "gelu" and its derivative Phi(x) + x phi(x)
+__device__ __forceinline__ float gelu_fwd(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad(float x) {
+  return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
 
 struct GemmTile {
   int m0, n0, n_cur, kb0, kb1;
@@ -231,6 +241,27 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const CU
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = ((bits >> i) & 1u) ? v[i] * e.drop_scale : 0.f;
         }
+        if (e.add_mat && row_ok) {
+          const float* am = e.add_mat + (long long)row * e.ld_addmat + col_base;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if (col_base + 4 * q < p.N) {
+              const float4 a4 = __ldg(reinterpret_cast<const float4*>(am) + q);
+              v[4 * q] += a4.x; v[4 * q + 1] += a4.y; v[4 * q + 2] += a4.z; v[4 * q + 3] += a4.w;
+            }
+          }
+        }
+        if (e.gelu_pre && row_ok) {
+          const float* gp = e.gelu_pre + (long long)row * e.ld_gelu + col_base;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if (col_base + 4 * q < p.N) {
+              const float4 u4 = __ldg(reinterpret_cast<const float4*>(gp) + q);
+              v[4 * q] *= gelu_grad(u4.x); v[4 * q + 1] *= gelu_grad(u4.y);
+              v[4 * q + 2] *= gelu_grad(u4.z); v[4 * q + 3] *= gelu_grad(u4.w);
+            }
+          }
+        }
         if (e.pos_mask && row_ok) {
           const float* pm = e.pos_mask + (long long)row * e.ld_pos + col_base;
 #pragma unroll
@@ -286,6 +317,10 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const CU
           }
         }
         if (e.sp_sink) {  // [planes][32 rows][32 bf16], 64-byte rows, SWIZZLE_64B
+          if (e.gelu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_fwd(v[i]);
+          }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             uint32_t hw[4], lw[4];

@@ -72,15 +72,23 @@ class CNNAddAtt(nn.Module):
 
 class PLM(nn.Module):
     """PLM text encoder (reference ``text.py:15-109``), ``use_mhsa=True`` form used by NRMS-PLM /
-    NAML-PLM: the HF transformer (third-party, stays on torch) followed by the
-    sm_100a head -- dropout -> MHSA over dim 0 of ``[N, T, E]`` (the reference passes batch-first
-    states to a ``batch_first=False`` attention, ``text.py:96``, so attention runs across the N news
-    of the call at each token position; ``attention_axis="tokens"`` attends along the tokens
-    instead) -> dropout -> additive pooling over the T tokens (pad tokens included)."""
+    NAML-PLM: the transformer followed by the sm_100a head -- dropout -> MHSA over dim 0 of
+    ``[N, T, E]`` (the reference passes batch-first states to a ``batch_first=False`` attention,
+    ``text.py:96``, so attention runs across the N news of the call at each token position;
+    ``attention_axis="tokens"`` attends along the tokens instead) -> dropout -> additive pooling over
+    the T tokens (pad tokens included).
+
+    ``transformer_impl="native"`` (default): the HF ``RobertaModel`` is the PARAMETER
+    CONTAINER (``state_dict`` keys, ``from_pretrained`` checkpoints, the reference's name-based freezing
+    ``text.py:70-73`` all unchanged) and ``self.plm_model(**text)[0]`` (``text.py:92``) runs on the sm_100a
+    encoder (``ops.TfmEncoderFn``: embeddings, every layer's projections on tcgen05, key-padding-masked attention,
+    LayerNorm / GELU / the three dropouts, forward and backward).  Architectures the kernels do not cover
+    (anything but RoBERTa-style post-LN layers with head dim 64, erf-GELU, absolute positions, <= 128 tokens) raise;
+    ``transformer_impl="hf"`` keeps the third-party torch module on the path instead."""
 
     def __init__(self, plm_model, frozen_layers, embed_dim: int, use_mhsa: bool, apply_reduce_dim: bool,
                  reduced_embed_dim, num_heads, query_dim, dropout_probability: float,
-                 attention_axis: str = "reference") -> None:
+                 attention_axis: str = "reference", transformer_impl: str = "native") -> None:
         super().__init__()
         if not isinstance(plm_model, (str, nn.Module)):
             raise ValueError(f"Expected keyword argument `plm_model` to be a `str` but got {plm_model}")
@@ -110,6 +118,65 @@ class PLM(nn.Module):
         self.num_heads = num_heads
         self.attention_axis = attention_axis
         self.precision = ops.PREC_BF16X3
+        if transformer_impl not in ("native", "hf"):
+            raise ValueError(f"transformer_impl must be 'native' or 'hf', got {transformer_impl}")
+        self.transformer_impl = transformer_impl
+        self._tfm_state = None
+        if transformer_impl == "native":
+            self._tfm_state = self._native_state()
+
+    def _native_state(self) -> "ops.TfmState":
+        cfg = getattr(self.plm_model, "config", None)
+        why = None
+        if cfg is None or getattr(cfg, "model_type", None) not in ("roberta", "xlm-roberta"):
+            why = f"model_type {getattr(cfg, 'model_type', None)!r} (RoBERTa-style models only)"
+        elif cfg.hidden_size != 64 * cfg.num_attention_heads:
+            why = f"head dim {cfg.hidden_size // cfg.num_attention_heads} (64 only)"
+        elif cfg.hidden_act != "gelu":
+            why = f"hidden_act {cfg.hidden_act!r} (erf 'gelu' only)"
+        elif getattr(cfg, "position_embedding_type", "absolute") != "absolute":
+            why = "relative position embeddings"
+        elif cfg.hidden_size > 1024 or cfg.intermediate_size % 16:
+            why = f"hidden {cfg.hidden_size} / intermediate {cfg.intermediate_size}"
+        elif getattr(cfg, "is_decoder", False) or getattr(cfg, "add_cross_attention", False):
+            why = "decoder / cross-attention configuration"
+        if why is not None:
+            raise ValueError(f"the sm_100a transformer does not cover this PLM: {why}; pass transformer_impl='hf' to keep "
+                             f"the HF torch module on the path")
+        return ops.TfmState(cfg.hidden_size, cfg.num_attention_heads, cfg.intermediate_size, cfg.num_hidden_layers,
+                            cfg.vocab_size, cfg.max_position_embeddings, cfg.pad_token_id, cfg.layer_norm_eps,
+                            cfg.hidden_dropout_prob, cfg.attention_probs_dropout_prob)
+
+    def transformer_parameters(self):
+        """The tensors ``ops.TfmEncoderFn`` takes, in ``_lib.TFM_EMBED_FIELDS`` + per-layer ``TFM_LAYER_FIELDS`` order."""
+        m = self.plm_model
+        e = m.embeddings
+        ps = [e.word_embeddings.weight, e.position_embeddings.weight, e.token_type_embeddings.weight[0],
+              e.LayerNorm.weight, e.LayerNorm.bias]
+        for lyr in m.encoder.layer:
+            a, so = lyr.attention.self, lyr.attention.output
+            ps += [a.query.weight, a.query.bias, a.key.weight, a.key.bias, a.value.weight, a.value.bias,
+                   so.dense.weight, so.dense.bias, so.LayerNorm.weight, so.LayerNorm.bias,
+                   lyr.intermediate.dense.weight, lyr.intermediate.dense.bias,
+                   lyr.output.dense.weight, lyr.output.dense.bias, lyr.output.LayerNorm.weight, lyr.output.LayerNorm.bias]
+        return ps
+
+    def transformer(self, text) -> torch.Tensor:
+        """``self.plm_model(**text)[0]``: ``[N, T, D]`` last hidden states."""
+        if self.transformer_impl == "hf":
+            return self.plm_model(**text)[0]
+        extra = set(text.keys()) - {"input_ids", "attention_mask"}
+        if extra:
+            raise ValueError(f"the sm_100a transformer takes input_ids / attention_mask only, got {sorted(extra)} "
+                             f"(the reference tokenises with return_token_type_ids=False, rec_dataset.py:181)")
+        ids = text["input_ids"]
+        if ids.shape[1] > 128:
+            raise ValueError(f"{ids.shape[1]} tokens per text > 128: tokenise with max_length <= 128 or pass "
+                             f"transformer_impl='hf'")
+        training = self.plm_model.training
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if training else 0
+        return ops.TfmEncoderFn.apply(ids, text.get("attention_mask"), self._tfm_state, training, seed, self.precision,
+                                      *self.transformer_parameters())
 
     def head(self, states: torch.Tensor) -> torch.Tensor:
         """``[N, T, E]`` last hidden states -> ``[N, E]`` on the sm_100a path."""
@@ -123,5 +190,5 @@ class PLM(nn.Module):
 
     def forward(self, text) -> torch.Tensor:
         if self.use_mhsa:
-            return self.head(self.plm_model(**text)[0])
-        return self.plm_model(**text).last_hidden_state[:, 0, :]
+            return self.head(self.transformer(text))
+        return self.transformer(text)[:, 0, :]

@@ -48,6 +48,7 @@ class NAMLModule(TwoTowerRecommender):
         optimizer,
         scheduler,
         pretrained_embeddings: Optional[torch.Tensor] = None,
+        transformer_impl: str = "native",
     ) -> None:
         super().__init__(outputs=outputs, optimizer=optimizer, scheduler=scheduler)
         self.num_categ_classes = num_categ_classes + 1
@@ -78,7 +79,8 @@ class NAMLModule(TwoTowerRecommender):
             assert isinstance(plm_model, (str, torch.nn.Module))
             text_encoder = PLM(plm_model=plm_model, frozen_layers=frozen_layers, embed_dim=text_embed_dim,
                                use_mhsa=True, apply_reduce_dim=False, reduced_embed_dim=None, num_heads=num_heads,
-                               query_dim=query_dim, dropout_probability=dropout_probability)
+                               query_dim=query_dim, dropout_probability=dropout_probability,
+                               transformer_impl=transformer_impl)
             news_dim = text_embed_dim
         category_encoder = LinearEncoder(
             pretrained_embeddings=None, from_pretrained=False, freeze_pretrained_emb=False,

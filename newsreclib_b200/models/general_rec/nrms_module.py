@@ -44,6 +44,7 @@ class NRMSModule(TwoTowerRecommender):
         optimizer,
         scheduler,
         pretrained_embeddings: Optional[torch.Tensor] = None,
+        transformer_impl: str = "native",
     ) -> None:
         super().__init__(outputs=outputs, optimizer=optimizer, scheduler=scheduler)
         self.num_categ_classes = num_categ_classes + 1
@@ -64,7 +65,8 @@ class NRMSModule(TwoTowerRecommender):
             assert isinstance(plm_model, (str, torch.nn.Module))
             text_encoder = PLM(plm_model=plm_model, frozen_layers=frozen_layers, embed_dim=embed_dim,
                                use_mhsa=True, apply_reduce_dim=False, reduced_embed_dim=None,
-                               num_heads=num_heads, query_dim=query_dim, dropout_probability=dropout_probability)
+                               num_heads=num_heads, query_dim=query_dim, dropout_probability=dropout_probability,
+                               transformer_impl=transformer_impl)
         else:
             if pretrained_embeddings is None:
                 assert isinstance(pretrained_embeddings_path, str)

@@ -559,3 +559,141 @@ class PlmHeadFn(torch.autograd.Function):
                    "nrl_plm_head_bwd")
         ctx.ws = None
         return (d_x, *grads, None, None, None, None, None, None)
+
+
+# ----------------------------------------------------------------------------------------
+# PLM transformer: embeddings + encoder layers of a HF RobertaModel / BertModel
+# ----------------------------------------------------------------------------------------
+from ._lib import TFM_EMBED_FIELDS, TFM_LAYER_FIELDS, TfmDims, TfmEmbed, TfmLayer  # noqa: E402
+
+
+class TfmState:
+    """Per-module state of the sm_100a transformer: the ``nrl_tfm_dims`` and the packed bf16 hi/lo GEMM operands of
+    the layers' weights.  Frozen layers are packed once (re-packed if a tensor is replaced or modified through
+    torch); layers with a trainable parameter are re-packed at every forward call, because an optimizer that steps
+    through raw pointers (``nrl_adam_step`` on the flat buffer) does not bump torch's version counters."""
+
+    def __init__(self, hidden: int, heads: int, intermediate: int, num_layers: int, vocab: int, max_pos: int,
+                 pad_idx: int, ln_eps: float, hidden_dropout: float, attn_dropout: float):
+        self.dims = TfmDims(int(hidden), int(heads), int(intermediate), int(num_layers), int(vocab), int(max_pos),
+                            int(pad_idx), float(ln_eps), float(hidden_dropout), float(attn_dropout))
+        self.wpack: Optional[torch.Tensor] = None
+        self.packed_key = [None] * int(num_layers)
+        self.precision = None
+
+    def pack(self, layer_params, precision: int) -> torch.Tensor:
+        lib = _lib.load()
+        dev = layer_params[0][0].device
+        need = lib.nrl_tfm_wpack_bytes(self.dims)
+        if need == 0:
+            raise RuntimeError(f"nrl_tfm: unsupported transformer dims: {_lib.load().nrl_last_error().decode()}")
+        if self.wpack is None or self.wpack.device != dev or self.precision != precision:
+            self.wpack = workspace(need, dev)
+            self.packed_key = [None] * self.dims.num_layers
+            self.precision = precision
+        for l, ps in enumerate(layer_params):
+            weights = [ps[i] for i, n in enumerate(TFM_LAYER_FIELDS) if not n.startswith("ln")]
+            key = None if any(t.requires_grad for t in weights) else tuple((t.data_ptr(), t._version) for t in weights)
+            if key is not None and key == self.packed_key[l]:
+                continue
+            st = TfmLayer()
+            for n, t in zip(TFM_LAYER_FIELDS, ps):
+                setattr(st, n, _p(_chk(t, torch.float32, n)))
+            _lib.check(lib.nrl_tfm_pack_weights(C.byref(st), l, 1, self.dims, _p(self.wpack), self.wpack.numel(),
+                                                precision, _stream()), "nrl_tfm_pack_weights")
+            self.packed_key[l] = key
+        return self.wpack
+
+
+def _tfm_structs(params, n_layers):
+    emb = TfmEmbed()
+    for n, t in zip(TFM_EMBED_FIELDS, params[:5]):
+        setattr(emb, n, _p(t))
+    layers = (TfmLayer * n_layers)()
+    for l in range(n_layers):
+        for i, n in enumerate(TFM_LAYER_FIELDS):
+            setattr(layers[l], n, _p(params[5 + 16 * l + i]))
+    return emb, layers
+
+
+class TfmEncoderFn(torch.autograd.Function):
+    """``self.plm_model(**text)[0]`` of ``PLM.forward`` (``encoders/news/text.py:92``) for a RoBERTa / BERT-shaped
+    transformer: ``input_ids``, ``attention_mask`` int64 ``[N, T]`` -> last hidden state ``[N, T, D]``.
+    ``params``: the 5 embedding tensors (``TFM_EMBED_FIELDS`` order; ``type0`` = row 0 of the token-type table) then 16
+    tensors per layer (``TFM_LAYER_FIELDS`` order).  A layer with no trainable tensor is frozen (data gradient only);
+    mixed layers are refused by the library."""
+
+    @staticmethod
+    def forward(ctx, input_ids, attention_mask, state, training, seed, precision, *params):
+        lib = _lib.load()
+        ids = _chk(input_ids.contiguous(), torch.int64, "input_ids")
+        mask = None if attention_mask is None else _chk(attention_mask.contiguous(), torch.int64, "attention_mask")
+        N, T = ids.shape
+        dims = state.dims
+        L = dims.num_layers
+        if len(params) != 5 + 16 * L:
+            raise RuntimeError(f"TfmEncoderFn: expected {5 + 16 * L} parameter tensors, got {len(params)}")
+        params = [_chk(t.contiguous(), torch.float32, "transformer parameter") for t in params]
+        wpack = state.pack([params[5 + 16 * l: 21 + 16 * l] for l in range(L)], precision)
+        need = lib.nrl_tfm_ws_bytes(N, T, dims)
+        if need == 0:
+            raise RuntimeError("nrl_tfm: unsupported transformer dims")
+        ws = workspace(need, ids.device)
+        out = torch.empty(N, T, dims.hidden, dtype=torch.float32, device=ids.device)
+        emb, layers = _tfm_structs(params, L)
+        _lib.check(lib.nrl_tfm_encoder_fwd(_p(ids), _p(mask), N, T, C.byref(emb), layers, dims, int(training), int(seed),
+                                           _p(wpack), _p(out), _p(ws), ws.numel(), precision, _stream()),
+                   "nrl_tfm_encoder_fwd")
+        ctx.save_for_backward(ids, *params)
+        ctx.mask, ctx.ws, ctx.wpack, ctx.state = mask, ws, wpack, state
+        ctx.cfg = (N, T, int(training), int(seed), precision)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        ids, *params = ctx.saved_tensors
+        N, T, training, seed, precision = ctx.cfg
+        dims = ctx.state.dims
+        L = dims.num_layers
+        need = ctx.needs_input_grad[6:]
+        d_out = d_out.contiguous().float()
+        grads = [torch.zeros_like(t) if nd else None for t, nd in zip(params, need)]
+        emb, layers = _tfm_structs(params, L)
+        eg = None
+        if any(need[:5]):
+            if not all(need[:5]):
+                raise RuntimeError("TfmEncoderFn: the embeddings must be all trainable or all frozen")
+            eg = TfmEmbed()
+            for n, t in zip(TFM_EMBED_FIELDS, grads[:5]):
+                setattr(eg, n, _p(t))
+        lg = (TfmLayer * L)()
+        for l in range(L):
+            for i, n in enumerate(TFM_LAYER_FIELDS):
+                setattr(lg[l], n, _p(grads[5 + 16 * l + i]))
+        _lib.check(lib.nrl_tfm_encoder_bwd(_p(ids), _p(ctx.mask), N, T, C.byref(emb), layers, dims, training, seed,
+                                           _p(ctx.wpack), _p(d_out), C.byref(eg) if eg is not None else None, lg,
+                                           _p(ctx.ws), ctx.ws.numel(), precision, _stream()), "nrl_tfm_encoder_bwd")
+        ctx.ws = None
+        return (None, None, None, None, None, None, *grads)
+
+
+def tfm_hidden_dropout_mask(R: int, D: int, site: int, seed: int, p: float, device) -> torch.Tensor:
+    """keep flags ``[R, D]`` (bool) of hidden-dropout site ``site`` (0 embeddings, 1 + 2l attention output, 2 + 2l layer
+    output of layer l) that ``TfmEncoderFn`` uses for ``seed``: lets a test replay the kernel's masks in the oracle."""
+    keep = torch.empty(R, D, dtype=torch.uint8, device=device)
+    _lib.check(_lib.load().nrl_tfm_hidden_dropout_mask(_p(keep), R, D, int(site), int(seed), float(p), _stream()),
+               "nrl_tfm_hidden_dropout_mask")
+    return keep.bool()
+
+
+def tfm_attn_dropout_mask(layers: int, N: int, heads: int, T: int, seed: int, p: float, device) -> torch.Tensor:
+    """keep flags ``[layers, N, heads, T, T]`` (bool) of the attention-probability dropout."""
+    lib = _lib.load()
+    keep = torch.empty(layers, N, heads, T, T, dtype=torch.uint8, device=device)
+    for l in range(layers):
+        for n in range(N):
+            for h in range(heads):
+                _lib.check(lib.nrl_tfm_attn_dropout_mask(_p(keep[l, n, h]), l, n, h, heads, T, int(seed), float(p),
+                                                         _stream()), "nrl_tfm_attn_dropout_mask")
+    return keep.bool()

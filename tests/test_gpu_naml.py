@@ -310,7 +310,8 @@ def test_plm_head_dropout_and_token_axis():
 
 
 def test_nrms_plm_module_forward():
-    """NRMSModule(use_plm=True) around a tiny random RoBERTa: HF transformer on torch + the sm_100a head."""
+    """NRMSModule(use_plm=True, transformer_impl="hf") around a tiny random RoBERTa with head dim 48 (outside the sm_100a
+    transformer's coverage): HF transformer on torch + the sm_100a head.  The native transformer: tests/test_gpu_tfm.py."""
     from transformers import RobertaConfig, RobertaModel
     from newsreclib_b200.models.general_rec.nrms_module import NRMSModule
     torch.manual_seed(0)
@@ -323,7 +324,7 @@ def test_nrms_plm_module_forward():
         dual_loss_coef=None, loss="cross_entropy_loss", late_fusion=False, temperature=None, use_plm=True,
         pretrained_embeddings_path=None, plm_model=tf, frozen_layers=[0], embed_dim=hidden, num_heads=2,
         query_dim=40, dropout_probability=0.2, top_k_list=[5], num_categ_classes=18, num_sent_classes=3,
-        save_recs=False, recs_fpath=None, optimizer=None, scheduler=None)
+        save_recs=False, recs_fpath=None, optimizer=None, scheduler=None, transformer_impl="hf")  # head dim 48
     frozen = [n for n, q in m.named_parameters() if not q.requires_grad]
     assert frozen and all("layer.0." in n for n in frozen)
     B = 4

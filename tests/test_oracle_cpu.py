@@ -316,3 +316,55 @@ def test_to_dense_batch_property_against_naive_loop():
         assert torch.equal(dense[mask], x)             # masked dense order == ragged order (what model_step relies on)
 
     check()
+
+
+# ---- transformer restatement against the fixtures minted from HF RobertaModel -------------
+@pytest.mark.parametrize("name", ["tfm_tiny", "tfm_t40"])
+def test_tfm_oracle_matches_hf_golden(name):
+    from tfm_helpers import grad_errors, load_tfm_golden, oracle_tfm
+    g, cfg, params, rgrads = load_tfm_golden(name)
+    ids, att, w = torch.from_numpy(g["input_ids"]), torch.from_numpy(g["attention_mask"]), torch.from_numpy(g["w"])
+    out, grads = oracle_tfm(params, cfg, ids, att, w, frozen=cfg["frozen"])
+    assert rel_err(out, g["out"]) <= 5e-5
+    assert set(grads) == set(rgrads)  # the frozen layers get none, the embeddings do
+    errs = grad_errors(grads, rgrads)
+    assert max(errs.values()) <= 5e-4, max(errs.items(), key=lambda kv: kv[1])
+    # the padding rows of both embedding tables never receive a gradient (nn.Embedding(padding_idx=1))
+    assert float(grads["embeddings.word_embeddings.weight"][1].abs().max()) == 0.0
+    assert float(grads["embeddings.position_embeddings.weight"][1].abs().max()) == 0.0
+
+
+def test_tfm_oracle_position_ids_and_masking():
+    from oracle import tfm_oracle as TO
+    ids = torch.tensor([[0, 5, 6, 2, 1, 1], [0, 7, 2, 1, 1, 1]])
+    assert TO.position_ids(ids, 1).tolist() == [[2, 3, 4, 5, 1, 1], [2, 3, 4, 1, 1, 1]]
+    # a masked key has no influence on the valid positions
+    from tfm_helpers import random_tfm_params
+    P = random_tfm_params(64, 1, 128, 1, 20, 10, seed=0)
+    att = (ids != 1).long()
+    a = TO.encoder(ids, att, P, 1, 1)
+    ids2 = ids.clone(); ids2[0, 4] = 9  # change a masked position's token (position id changes too)
+    b = TO.encoder(ids2, att, P, 1, 1)
+    assert torch.allclose(a[0, :4], b[0, :4], atol=1e-6) and not torch.allclose(a[0, 4], b[0, 4], atol=1e-3)
+
+
+def test_plm_mirror_refuses_uncovered_transformers():
+    """transformer_impl='native' (the default) never falls back silently: an architecture outside the kernels' coverage
+    raises at construction and names the explicit opt-out."""
+    from transformers import RobertaConfig, RobertaModel
+    from newsreclib_b200.models.components.encoders.news.text import PLM
+    kw = dict(frozen_layers=[0], use_mhsa=True, apply_reduce_dim=False, reduced_embed_dim=None, num_heads=2, query_dim=8,
+              dropout_probability=0.2)
+    small = RobertaModel(RobertaConfig(vocab_size=30, hidden_size=96, num_hidden_layers=1, num_attention_heads=2,
+                                       intermediate_size=64, max_position_embeddings=20))
+    with pytest.raises(ValueError, match="transformer_impl='hf'"):
+        PLM(plm_model=small, embed_dim=96, **kw)
+    assert PLM(plm_model=small, embed_dim=96, transformer_impl="hf", **kw).transformer_impl == "hf"
+    ok = RobertaModel(RobertaConfig(vocab_size=30, hidden_size=128, num_hidden_layers=2, num_attention_heads=2,
+                                    intermediate_size=64, max_position_embeddings=20))
+    m = PLM(plm_model=ok, embed_dim=128, **kw)
+    ps = m.transformer_parameters()
+    assert len(ps) == 5 + 16 * 2 and ps[2].shape == (128,)
+    assert [p.requires_grad for p in ps[5:21]] == [False] * 16 and all(p.requires_grad for p in ps[21:])
+    with pytest.raises(RuntimeError, match="CUDA"):  # no CPU path
+        m({"input_ids": torch.zeros(2, 5, dtype=torch.long), "attention_mask": torch.ones(2, 5, dtype=torch.long)})
