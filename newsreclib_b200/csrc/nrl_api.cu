@@ -21,6 +21,7 @@
 #include "nrl_naml.cuh"
 #include "nrl_exchange.cuh"
 #include "nrl_tfm.cuh"
+#include "nrl_attn_flash.cuh"
 
 using namespace nrl;
 typedef __nv_bfloat16 bf16;
@@ -165,6 +166,7 @@ struct BlockWs {
   bf16* x;     // [2][R][Ep]   input planes (ones column at E)
   float* qkv;  // [R][3E]
   float* lse;  // [R][H]
+  float* delta;  // [R][H]      dO . O per row and head (backward of the long-sequence attention kernels)
   bf16* o;     // [2][R][Ep]
   float* y;    // [R][E]       MHSA output (after dropout site 1)
   bf16* yp;    // [2][R][Ep]
@@ -188,6 +190,7 @@ static void carve_block(Bump& b, long long R, const Dims& d, BlockWs& w) {
   w.x = b.take<bf16>(2ull * R * d.Ep);
   w.qkv = b.take<float>((size_t)R * d.LDQ);
   w.lse = b.take<float>((size_t)R * d.H);
+  w.delta = b.take<float>((size_t)R * d.H);
   w.o = b.take<bf16>(2ull * R * d.Ep);
   w.y = b.take<float>((size_t)R * d.E);
   w.yp = b.take<bf16>(2ull * R * d.Ep);
@@ -533,12 +536,25 @@ static bool attn_force_simt() {
   return v;
 }
 
+static bool attn_flash_on() {
+  static const bool v = [] { const char* e = getenv("NRL_ATTN_FLASH"); return !(e && e[0] == '0'); }();
+  return v;
+}
+
 template <int DH>
 static int attn_set_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(attn_fwd_tile_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 ATTN_FWD_SMEM_BUDGET));
   CUDA_TRY(cudaFuncSetAttribute(attn_bwd_tile_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 ATTN_BWD_SMEM_BUDGET));
+  if constexpr (DH == 48 || DH == 64) {
+    CUDA_TRY(cudaFuncSetAttribute(attn_fwd_flash_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  flash_fwd_smem<DH>()));
+    CUDA_TRY(cudaFuncSetAttribute(attn_bwd_flash_dq_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  flash_bwd_smem<DH>()));
+    CUDA_TRY(cudaFuncSetAttribute(attn_bwd_flash_dkv_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  flash_bwd_smem<DH>()));
+  }
   if constexpr (DH <= 32) {
     CUDA_TRY(cudaFuncSetAttribute(attn_fwd_tma_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   ATTN_TMA_SMEM_MAX));
@@ -597,6 +613,17 @@ static void launch_attn_fwd(const Ctx& c, const Dims& d, const AttnGeom& g, cons
       return;
     }
   }
+  }
+  if constexpr (DH == 48 || DH == 64) {
+    // long sequences / wide heads (the PLM head: attention across the N news of the call): flash-style tensor-core kernel
+    // (NRL_ATTN_FLASH=0: the fp32 SIMT kernels below, A/B runs)
+    if (g.S > 32 && attn_flash_on()) {
+      const int nqb = (g.S + 127) / 128;
+      attn_fwd_flash_kernel<DH><<<(unsigned)((long long)g.NB * d.H * nqb), 256, flash_fwd_smem<DH>(), c.stream>>>(
+          w.qkv, d.E, d.LDQ, d.H, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH), w.o, lo, d.Ep, w.lse,
+          c.two_planes() ? 1 : 0);
+      return;
+    }
   }
   const size_t per_head = (size_t)g.S * 3 * DH * sizeof(float);
   int hp = (int)(ATTN_FWD_SMEM_BUDGET / per_head);
@@ -663,6 +690,21 @@ static void launch_attn_bwd(const Ctx& c, const Dims& d, const AttnGeom& g, cons
       return;
     }
   }
+  }
+  if constexpr (DH == 48 || DH == 64) {
+    if (g.S > 32 && attn_flash_on()) {
+      const int nqb = (g.S + 127) / 128;
+      const unsigned grid = (unsigned)((long long)g.NB * d.H * nqb);
+      attn_delta_kernel<<<grid_for(R, 8, 8 * g_dev.sm_count), 256, 0, c.stream>>>(
+          w.d_o, d.E, w.o, c.two_planes() ? w.o + R * d.Ep : nullptr, d.Ep, R, d.H, DH, w.delta);
+      attn_bwd_flash_dq_kernel<DH><<<grid, 256, flash_bwd_smem<DH>(), c.stream>>>(
+          w.qkv, w.d_o, d.E, w.lse, w.delta, d.E, d.LDQ, d.H, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH),
+          w.dqkv, lo, d.P3, c.two_planes() ? 1 : 0);
+      attn_bwd_flash_dkv_kernel<DH><<<grid, 256, flash_bwd_smem<DH>(), c.stream>>>(
+          w.qkv, w.d_o, d.E, w.lse, w.delta, d.E, d.LDQ, d.H, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH),
+          w.dqkv, lo, d.P3, c.two_planes() ? 1 : 0);
+      return;
+    }
   }
   const size_t per_head = (size_t)g.S * (5 * DH + 2) * sizeof(float);
   int hp = (int)(ATTN_BWD_SMEM_BUDGET / per_head);

@@ -241,14 +241,25 @@ tfm_ln_bwd_kernel(const float* __restrict__ s, const float* __restrict__ dy, lon
         if (dt_lo) dt_lo[r * dtp + c] = __float2bfloat16_rn(0.f);
       }
   }
-  if (dgamma) {
+  if (dgamma) {  // warps -> shared-memory accumulators -> ONE global atomic per column per CTA (the launch is capped at
+                 // two CTAs per SM: thousands of warps adding into the same 2 D addresses serialise in L2)
+    extern __shared__ float ln_acc[];  // [2][D]
+    for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) ln_acc[i] = 0.f;
+    __syncthreads();
 #pragma unroll
     for (int i = 0; i < TFM_LN_CHUNKS; ++i) {
       const int c = lane * 4 + 128 * i;
       if (c < D) {
-        atomicAdd(reinterpret_cast<float4*>(dgamma + c), ag[i]);
-        atomicAdd(reinterpret_cast<float4*>(dbeta + c), ab[i]);
+        atomicAdd(ln_acc + c, ag[i].x); atomicAdd(ln_acc + c + 1, ag[i].y);
+        atomicAdd(ln_acc + c + 2, ag[i].z); atomicAdd(ln_acc + c + 3, ag[i].w);
+        atomicAdd(ln_acc + D + c, ab[i].x); atomicAdd(ln_acc + D + c + 1, ab[i].y);
+        atomicAdd(ln_acc + D + c + 2, ab[i].z); atomicAdd(ln_acc + D + c + 3, ab[i].w);
       }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+      atomicAdd(dgamma + i, ln_acc[i]);
+      atomicAdd(dbeta + i, ln_acc[D + i]);
     }
   }
 }

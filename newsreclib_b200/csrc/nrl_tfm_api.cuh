@@ -355,7 +355,7 @@ int nrl_tfm_encoder_bwd(const long long* input_ids, const long long* attention_m
     const unsigned long long lseed = tfm_layer_seed(seed, l);
     const bool need_dx = l > lowest || embed_grads;  // the data gradient below the lowest trainable layer is not needed
     // LN2 backward
-    tfm_ln_bwd_kernel<<<grid_for(R, 8, 8 * g_dev.sm_count), 256, 0, c.stream>>>(
+    tfm_ln_bwd_kernel<<<grid_for(R, 8, (g ? 2 : 8) * g_dev.sm_count), 256, g ? 2 * d.D * sizeof(float) : 0, c.stream>>>(
         y.s2, dy, R, d.D, p.ln2_g, d.eps, w.ds, w.dtp, dtp_lo, d.D, hdrop.on ? y.mask2 : nullptr, d.MW, hdrop.scale,
         g ? g->ln2_g : nullptr, g ? g->ln2_b : nullptr);
     LAUNCH_CHECK("tfm ln2_bwd");
@@ -376,7 +376,7 @@ int nrl_tfm_encoder_bwd(const long long* input_ids, const long long* attention_m
       TRY(gemm_nt(c, w.dup, R, d.I, pk.wi_t, d.D, d.I, d.I, e, sk, "tfm gemm ffn_in dgrad"));
     }
     // LN1 backward
-    tfm_ln_bwd_kernel<<<grid_for(R, 8, 8 * g_dev.sm_count), 256, 0, c.stream>>>(
+    tfm_ln_bwd_kernel<<<grid_for(R, 8, (g ? 2 : 8) * g_dev.sm_count), 256, g ? 2 * d.D * sizeof(float) : 0, c.stream>>>(
         y.s1, w.gb, R, d.D, p.ln1_g, d.eps, w.ds, w.dtp, dtp_lo, d.D, hdrop.on ? y.mask1 : nullptr, d.MW, hdrop.scale,
         g ? g->ln1_g : nullptr, g ? g->ln1_b : nullptr);
     LAUNCH_CHECK("tfm ln1_bwd");

@@ -173,6 +173,8 @@ def exchange_adam_step(ps: "_lib.PeerSet", m: torch.Tensor, v: torch.Tensor, n: 
     """Enqueue one fused exchange + Adam step (see ``include/nrl.h``).  ``sparse_rows`` / ``row_elems``: the leading
     row-sparse region (needs ``ps.bitmaps``); ``zero_grads``: leave every gradient buffer cleared."""
     lib = _lib.load()
+    from . import ops
+    ops.bump_weights_epoch()
     for t, name in ((m, "m"), (v, "v")):
         if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or t.numel() < n:
             raise RuntimeError(f"exchange_adam_step: {name} must be a contiguous fp32 CUDA tensor of >= {n} elements")

@@ -129,10 +129,26 @@ def gather_rows(table: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     return out
 
 
+_weights_epoch = 0
+
+
+def weights_epoch() -> int:
+    """Counts the parameter updates this library made through raw pointers (``nrl_adam_step``,
+    ``nrl_exchange_adam_step``): torch's version counters do not see those, so anything that caches a function of the
+    weights (``TfmState``'s packed GEMM operands) keys on this as well."""
+    return _weights_epoch
+
+
+def bump_weights_epoch() -> None:
+    global _weights_epoch
+    _weights_epoch += 1
+
+
 def adam_step(p, g, m, v, step: int, lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0,
               zero_grad: bool = False) -> None:
     """``torch.optim.Adam.step`` over flat buffers; ``zero_grad=True`` also clears ``g`` in the same pass."""
     lib = _lib.load()
+    bump_weights_epoch()
     for t, n in ((p, "p"), (g, "g"), (m, "m"), (v, "v")):
         _chk(t, torch.float32, n)
     fn = lib.nrl_adam_step_zero_grad if zero_grad else lib.nrl_adam_step
@@ -569,9 +585,10 @@ from ._lib import TFM_EMBED_FIELDS, TFM_LAYER_FIELDS, TfmDims, TfmEmbed, TfmLaye
 
 class TfmState:
     """Per-module state of the sm_100a transformer: the ``nrl_tfm_dims`` and the packed bf16 hi/lo GEMM operands of
-    the layers' weights.  Frozen layers are packed once (re-packed if a tensor is replaced or modified through
-    torch); layers with a trainable parameter are re-packed at every forward call, because an optimizer that steps
-    through raw pointers (``nrl_adam_step`` on the flat buffer) does not bump torch's version counters."""
+    the layers' weights.  A layer is re-packed when one of its tensors was replaced or modified through torch (data
+    pointer / version counter) or -- trainable layers only -- when this library stepped an optimizer through raw pointers
+    since (``weights_epoch()``: ``nrl_adam_step`` on a flat buffer does not bump torch's counters).  The two encoder calls
+    of a training step (history, candidates) therefore share one packing."""
 
     def __init__(self, hidden: int, heads: int, intermediate: int, num_layers: int, vocab: int, max_pos: int,
                  pad_idx: int, ln_eps: float, hidden_dropout: float, attn_dropout: float):
@@ -593,8 +610,9 @@ class TfmState:
             self.precision = precision
         for l, ps in enumerate(layer_params):
             weights = [ps[i] for i, n in enumerate(TFM_LAYER_FIELDS) if not n.startswith("ln")]
-            key = None if any(t.requires_grad for t in weights) else tuple((t.data_ptr(), t._version) for t in weights)
-            if key is not None and key == self.packed_key[l]:
+            key = (weights_epoch() if any(t.requires_grad for t in weights) else -1,
+                   tuple((t.data_ptr(), t._version) for t in weights))
+            if key == self.packed_key[l]:
                 continue
             st = TfmLayer()
             for n, t in zip(TFM_LAYER_FIELDS, ps):

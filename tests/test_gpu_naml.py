@@ -309,6 +309,47 @@ def test_plm_head_dropout_and_token_axis():
     assert rel_err(out_tok, ref_tok) <= 1e-4
 
 
+@pytest.mark.parametrize("hidden,heads,N,T,axis", [(768, 16, 400, 6, 0), (128, 2, 200, 5, 0), (768, 16, 9, 96, 1),
+                                                   (768, 16, 130, 3, 0)])
+def test_plm_head_long_sequences_vs_oracle(hidden, heads, N, T, axis):
+    """The PLM head at the sequence lengths the reference's batch-axis attention produces (S = N = the 400 clicked news
+    of 8 impressions; head dims 48 and 64; S not a multiple of the 64-key / 128-query blocks) and along 96 tokens:
+    the flash-style tensor-core attention kernels (nrl_attn_flash.cuh), forward and backward, against the oracle."""
+    from newsreclib_b200 import ops
+    g = torch.Generator().manual_seed(N + T)
+    Q = 40
+    order = ["multihead_attention.in_proj_weight", "multihead_attention.in_proj_bias",
+             "multihead_attention.out_proj.weight", "multihead_attention.out_proj.bias",
+             "additive_attention.linear.weight", "additive_attention.linear.bias", "additive_attention.query"]
+    shapes = [(3 * hidden, hidden), (3 * hidden,), (hidden, hidden), (hidden,), (Q, hidden), (Q,), (Q,)]
+    p = {k: torch.randn(*sh, generator=g) * (0.08 if len(sh) == 2 else 0.1) for k, sh in zip(order, shapes)}
+    x = torch.randn(N, T, hidden, generator=g)
+    wgt = torch.randn(N, hidden, generator=g)
+    dev = [p[k].cuda().requires_grad_(True) for k in order]
+    xd = x.cuda().requires_grad_(True)
+    out = ops.PlmHeadFn.apply(xd, *dev, heads, axis, 0.0, False, 0, ops.PREC_BF16X3)
+    (out * wgt.cuda()).sum().backward()
+
+    def ref(leaves, dt):
+        if axis == 0:
+            o = O.plm_head(leaves["x"], leaves, heads)
+        else:
+            y = O.mha_seq_first(leaves["x"].permute(1, 0, 2), *[leaves[k] for k in order[:4]], heads).permute(1, 0, 2)
+            o = O.additive_attention(y, leaves[order[4]], leaves[order[5]], leaves[order[6]])
+        ref.out = o.detach() if dt == torch.float32 else ref.out
+        return (o * wgt.to(dt)).sum()
+    ref.out = None
+    rg, tol = oracle_grads(ref, {"x": x, **p})
+    e = rel_err(out, ref.out)
+    errs = {"x": rel_err(xd.grad, rg["x"]) / tol["x"]}
+    errs.update({k: rel_err(v.grad, rg[k]) / tol[k] for k, v in zip(order, dev)})
+    worst = max(errs, key=errs.get)
+    print(f"[plm head] E={hidden} heads={heads} N={N} T={T} axis={axis}: out rel {e:.2e} (tol 1e-4); worst gradient error / "
+          f"tolerance {errs[worst]:.2f} ({worst}, tol {tol[worst]:.1e})")
+    assert e <= 1e-4
+    assert errs[worst] <= 1.0, (worst, errs[worst])
+
+
 def test_nrms_plm_module_forward():
     """NRMSModule(use_plm=True, transformer_impl="hf") around a tiny random RoBERTa with head dim 48 (outside the sm_100a
     transformer's coverage): HF transformer on torch + the sm_100a head.  The native transformer: tests/test_gpu_tfm.py."""
