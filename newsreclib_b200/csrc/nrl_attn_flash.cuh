@@ -42,22 +42,31 @@ __device__ __forceinline__ uint32_t fl_bn_addr(uint32_t base, int k0, int n0, in
   const int mi = lane >> 3;
   return base + (uint32_t)((k0 + (lane & 7) + 8 * (mi & 1)) * ROWB + (n0 + 8 * (mi >> 1)) * 2);
 }
-// stage `rows` sequence rows s0 .. of one (batch item, column offset) slice as hi / lo planes; rows >= S are zero
-template <int DH>
+// stage ROWS sequence rows s0 .. of one (batch item, column offset) slice as hi / lo planes; rows >= S are zero.  256
+// threads; every thread issues all its 16-byte loads before the first conversion (one trip to L2 / HBM per matrix).
+template <int DH, int ROWS>
 __device__ __forceinline__ void fl_stage(uint8_t* sm, uint32_t o_hi, uint32_t o_lo, const float* __restrict__ src,
-                                         long long ld, long long seq_stride, long long row_base, int s0, int rows, int S,
-                                         float mul) {
-  constexpr int C4 = DH / 4, ROWB = FlashCfg<DH>::ROWB;
-  for (int i = threadIdx.x; i < rows * C4; i += blockDim.x) {
-    const int r = i / C4, c = (i % C4) * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (s0 + r < S) v = __ldg(reinterpret_cast<const float4*>(src + ((long long)(s0 + r) * seq_stride + row_base) * ld + c));
-    uint32_t h0, l0, h1, l1;
-    split_pack2(v.x * mul, v.y * mul, h0, l0);
-    split_pack2(v.z * mul, v.w * mul, h1, l1);
-    const uint32_t off = (uint32_t)(r * ROWB + c * 2);
-    *reinterpret_cast<uint2*>(sm + o_hi + off) = make_uint2(h0, h1);
-    *reinterpret_cast<uint2*>(sm + o_lo + off) = make_uint2(l0, l1);
+                                         long long ld, long long seq_stride, long long row_base, int s0, int S, float mul) {
+  constexpr int C4 = DH / 4, ROWB = FlashCfg<DH>::ROWB, TOTAL = ROWS * C4, ITER = (TOTAL + 255) / 256;
+  float4 v[ITER];
+#pragma unroll
+  for (int it = 0; it < ITER; ++it) {
+    const int i = threadIdx.x + it * 256, r = i / C4, c = (i % C4) * 4;
+    v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < TOTAL && s0 + r < S)
+      v[it] = __ldg(reinterpret_cast<const float4*>(src + ((long long)(s0 + r) * seq_stride + row_base) * ld + c));
+  }
+#pragma unroll
+  for (int it = 0; it < ITER; ++it) {
+    const int i = threadIdx.x + it * 256, r = i / C4, c = (i % C4) * 4;
+    if (i < TOTAL) {
+      uint32_t h0, l0, h1, l1;
+      split_pack2(v[it].x * mul, v[it].y * mul, h0, l0);
+      split_pack2(v[it].z * mul, v[it].w * mul, h1, l1);
+      const uint32_t off = (uint32_t)(r * ROWB + c * 2);
+      *reinterpret_cast<uint2*>(sm + o_hi + off) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(sm + o_lo + off) = make_uint2(l0, l1);
+    }
   }
 }
 template <int DH>
@@ -81,7 +90,7 @@ attn_fwd_flash_kernel(const float* __restrict__ qkv, int E, int ldq, int heads, 
   const uint32_t oQh = 0, oQl = C::QB * ROWB, oKh = 2 * C::QB * ROWB, oKl = oKh + C::KB * ROWB, oVh = oKl + C::KB * ROWB,
                  oVl = oVh + C::KB * ROWB;
   const int q0 = qb * C::QB;
-  fl_stage<DH>(fsm, oQh, oQl, qkv + h * DH, ldq, seq_stride, row_base, q0, C::QB, S, scale * TFM_LOG2E);
+  fl_stage<DH, C::QB>(fsm, oQh, oQl, qkv + h * DH, ldq, seq_stride, row_base, q0, S, scale * TFM_LOG2E);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
   const int w0 = 16 * warp;
   const bool active = q0 + w0 < S;
@@ -92,8 +101,8 @@ attn_fwd_flash_kernel(const float* __restrict__ qkv, int E, int ldq, int heads, 
   for (int j = 0; j < C::DT; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
   for (int k0 = 0; k0 < S; k0 += C::KB) {
     __syncthreads();  // the previous block's K / V are no longer read (first pass: Q staged)
-    fl_stage<DH>(fsm, oKh, oKl, qkv + E + h * DH, ldq, seq_stride, row_base, k0, C::KB, S, 1.f);
-    fl_stage<DH>(fsm, oVh, oVl, qkv + 2 * E + h * DH, ldq, seq_stride, row_base, k0, C::KB, S, 1.f);
+    fl_stage<DH, C::KB>(fsm, oKh, oKl, qkv + E + h * DH, ldq, seq_stride, row_base, k0, S, 1.f);
+    fl_stage<DH, C::KB>(fsm, oVh, oVl, qkv + 2 * E + h * DH, ldq, seq_stride, row_base, k0, S, 1.f);
     __syncthreads();
     if (!active) continue;
     float s[8][4];
@@ -234,8 +243,8 @@ attn_bwd_flash_dq_kernel(const float* __restrict__ qkv, const float* __restrict_
   float* lse2 = reinterpret_cast<float*>(fsm + oVl + C::KB * ROWB);
   float* dd = lse2 + C::QB;
   const int q0 = qb * C::QB;
-  fl_stage<DH>(fsm, oQh, oQl, qkv + h * DH, ldq, seq_stride, row_base, q0, C::QB, S, scale * TFM_LOG2E);
-  fl_stage<DH>(fsm, oGh, oGl, d_o + h * DH, ld_do, seq_stride, row_base, q0, C::QB, S, 1.f);
+  fl_stage<DH, C::QB>(fsm, oQh, oQl, qkv + h * DH, ldq, seq_stride, row_base, q0, S, scale * TFM_LOG2E);
+  fl_stage<DH, C::QB>(fsm, oGh, oGl, d_o + h * DH, ld_do, seq_stride, row_base, q0, S, 1.f);
   fl_stage_rowstats(lse2, dd, lse, delta, heads, h, seq_stride, row_base, q0, C::QB, S);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
   const int w0 = 16 * warp;
@@ -246,8 +255,8 @@ attn_bwd_flash_dq_kernel(const float* __restrict__ qkv, const float* __restrict_
   for (int j = 0; j < C::DT; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.f;
   for (int k0 = 0; k0 < S; k0 += C::KB) {
     __syncthreads();
-    fl_stage<DH>(fsm, oKh, oKl, qkv + E + h * DH, ldq, seq_stride, row_base, k0, C::KB, S, 1.f);
-    fl_stage<DH>(fsm, oVh, oVl, qkv + 2 * E + h * DH, ldq, seq_stride, row_base, k0, C::KB, S, 1.f);
+    fl_stage<DH, C::KB>(fsm, oKh, oKl, qkv + E + h * DH, ldq, seq_stride, row_base, k0, S, 1.f);
+    fl_stage<DH, C::KB>(fsm, oVh, oVl, qkv + 2 * E + h * DH, ldq, seq_stride, row_base, k0, S, 1.f);
     __syncthreads();
     if (!active) continue;
     const float ls0 = lse2[w0 + g], ls1 = lse2[w0 + g + 8], d0 = dd[w0 + g], d1 = dd[w0 + g + 8];
@@ -345,8 +354,8 @@ attn_bwd_flash_dkv_kernel(const float* __restrict__ qkv, const float* __restrict
   float* lse2 = reinterpret_cast<float*>(fsm + oGl + C::KB * ROWB);
   float* dd = lse2 + C::QB;
   const int k0 = kb * C::QB;
-  fl_stage<DH>(fsm, oKh, oKl, qkv + E + h * DH, ldq, seq_stride, row_base, k0, C::QB, S, 1.f);
-  fl_stage<DH>(fsm, oVh, oVl, qkv + 2 * E + h * DH, ldq, seq_stride, row_base, k0, C::QB, S, 1.f);
+  fl_stage<DH, C::QB>(fsm, oKh, oKl, qkv + E + h * DH, ldq, seq_stride, row_base, k0, S, 1.f);
+  fl_stage<DH, C::QB>(fsm, oVh, oVl, qkv + 2 * E + h * DH, ldq, seq_stride, row_base, k0, S, 1.f);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
   const int w0 = 16 * warp;
   const bool active = k0 + w0 < S;
@@ -360,8 +369,8 @@ attn_bwd_flash_dkv_kernel(const float* __restrict__ qkv, const float* __restrict
   }
   for (int q0 = 0; q0 < S; q0 += C::KB) {
     __syncthreads();
-    fl_stage<DH>(fsm, oQh, oQl, qkv + h * DH, ldq, seq_stride, row_base, q0, C::KB, S, scale * TFM_LOG2E);
-    fl_stage<DH>(fsm, oGh, oGl, d_o + h * DH, ld_do, seq_stride, row_base, q0, C::KB, S, 1.f);
+    fl_stage<DH, C::KB>(fsm, oQh, oQl, qkv + h * DH, ldq, seq_stride, row_base, q0, S, scale * TFM_LOG2E);
+    fl_stage<DH, C::KB>(fsm, oGh, oGl, d_o + h * DH, ld_do, seq_stride, row_base, q0, S, 1.f);
     fl_stage_rowstats(lse2, dd, lse, delta, heads, h, seq_stride, row_base, q0, C::KB, S);
     __syncthreads();
     if (!active) continue;

@@ -170,8 +170,10 @@ tfm_ln_fwd_kernel(const float* __restrict__ s, long long R, int D, int dp, const
 //   ds_out  [R][D] fp32 (nullable): the gradient w.r.t. s -- the residual branch takes it as is;
 //   dt planes [R][dtp] (nullable): ds with the keep-bit words of the dropout that FOLLOWED the producing GEMM applied
 //           (the A operand of that GEMM's data- and weight-gradient products);
-//   dgamma / dbeta (nullable: frozen layer) accumulated with one atomic per warp per column.
-__global__ void __launch_bounds__(256)
+//   dgamma / dbeta (PG: the layer is trainable) accumulated per CTA, then one atomic per column.
+// 128-thread CTAs; the frozen-layer instance carries no accumulators (half the registers): 16 warps per SM against 12.
+template <bool PG>
+__global__ void __launch_bounds__(128, PG ? 3 : 4)
 tfm_ln_bwd_kernel(const float* __restrict__ s, const float* __restrict__ dy, long long R, int D,
                   const float* __restrict__ gamma, float eps, float* __restrict__ ds_out,
                   __nv_bfloat16* __restrict__ dt_hi, __nv_bfloat16* __restrict__ dt_lo, int dtp,
@@ -202,7 +204,7 @@ tfm_ln_bwd_kernel(const float* __restrict__ s, const float* __restrict__ dy, lon
         const float4 w4 = __ldg(reinterpret_cast<const float4*>(gamma + c));
         float4& x = row.v[i];
         x.x = (x.x - mean) * rstd; x.y = (x.y - mean) * rstd; x.z = (x.z - mean) * rstd; x.w = (x.w - mean) * rstd;
-        if (dgamma) {
+        if (PG) {
           ag[i].x += g[i].x * x.x; ag[i].y += g[i].y * x.y; ag[i].z += g[i].z * x.z; ag[i].w += g[i].w * x.w;
           ab[i].x += g[i].x; ab[i].y += g[i].y; ab[i].z += g[i].z; ab[i].w += g[i].w;
         }
@@ -241,7 +243,7 @@ tfm_ln_bwd_kernel(const float* __restrict__ s, const float* __restrict__ dy, lon
         if (dt_lo) dt_lo[r * dtp + c] = __float2bfloat16_rn(0.f);
       }
   }
-  if (dgamma) {  // warps -> shared-memory accumulators -> ONE global atomic per column per CTA (the launch is capped at
+  if (PG) {  // warps -> shared-memory accumulators -> ONE global atomic per column per CTA (the launch is capped at
                  // two CTAs per SM: thousands of warps adding into the same 2 D addresses serialise in L2)
     extern __shared__ float ln_acc[];  // [2][D]
     for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) ln_acc[i] = 0.f;
@@ -432,16 +434,27 @@ __device__ __forceinline__ void tfm_mma3(float (&c)[4], const uint32_t (&ah)[4],
   mma_16816(c, ah[0], ah[1], ah[2], ah[3], bh0, bh1);
 }
 
-// stage rows [0, S) x 64 columns of a row-major fp32 slice (pitch ld) as hi / lo planes, rows [S, SK) zero
+// stage rows [0, S) x 64 columns of a row-major fp32 slice (pitch ld) as hi / lo planes, rows [S, SK) zero.
+// NT = threads of the CTA (compile time): every thread issues ALL its 16-byte loads before the first conversion, so a
+// matrix costs one trip to L2 / HBM instead of one per loop iteration.
+template <int SK, int NT>
 __device__ __forceinline__ void tfm_stage(uint8_t* smem, uint32_t plane_hi, uint32_t plane_lo, const float* __restrict__ src,
-                                          long long ld, int S, int SK, float mul) {
-  for (int i = threadIdx.x; i < SK * 16; i += blockDim.x) {
-    const int t = i >> 4, c = (i & 15) * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (t < S) v = __ldg(reinterpret_cast<const float4*>(src + (long long)t * ld + c));
+                                          long long ld, int S, float mul) {
+  constexpr int ITER = SK * 16 / NT;
+  static_assert(ITER * NT == SK * 16, "thread count must divide the tile");
+  float4 v[ITER];
+#pragma unroll
+  for (int it = 0; it < ITER; ++it) {
+    const int i = threadIdx.x + it * NT, t = i >> 4, c = (i & 15) * 4;
+    v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < S) v[it] = __ldg(reinterpret_cast<const float4*>(src + (long long)t * ld + c));
+  }
+#pragma unroll
+  for (int it = 0; it < ITER; ++it) {
+    const int i = threadIdx.x + it * NT, t = i >> 4, c = (i & 15) * 4;
     uint32_t h0, l0, h1, l1;
-    split_pack2(v.x * mul, v.y * mul, h0, l0);
-    split_pack2(v.z * mul, v.w * mul, h1, l1);
+    split_pack2(v[it].x * mul, v[it].y * mul, h0, l0);
+    split_pack2(v[it].z * mul, v[it].w * mul, h1, l1);
     const uint32_t off = (uint32_t)(t * TFM_PLANE_ROW_BYTES + c * 2);
     *reinterpret_cast<uint2*>(smem + plane_hi + off) = make_uint2(h0, h1);
     *reinterpret_cast<uint2*>(smem + plane_lo + off) = make_uint2(l0, l1);
@@ -461,13 +474,15 @@ __host__ __device__ inline int tfm_attn_bwd_smem(int SK) {
   return 8 * SK * TFM_PLANE_ROW_BYTES + 2 * SK * 4 + SK + SK * (SK / 32) * 4 + 16;
 }
 
+// CTAs are launched with 64 * NK32 threads (two warps per 32 padded rows: warps beyond ceil(T / 16) only help staging);
+// the minimum-CTA hints keep 12 warps per SM resident for every size but the largest
 template <int NK32>  // padded key count SK = 32 * NK32 (<= 128)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(64 * NK32, NK32 == 1 ? 6 : NK32 == 2 ? 3 : NK32 == 3 ? 2 : 1)
 tfm_attn_fwd_kernel(const float* __restrict__ qkv, int ldq, int D, int H, int T, const unsigned char* __restrict__ kmask,
                     float scale, __nv_bfloat16* __restrict__ o_hi, __nv_bfloat16* __restrict__ o_lo, int dp,
                     float* __restrict__ lse, int three_i, int drop_on, uint32_t thr, float dscale,
                     unsigned long long seed, uint32_t site) {
-  constexpr int SK = 32 * NK32, NT = SK / 8;
+  constexpr int SK = 32 * NK32, NT = SK / 8, NTHR = 64 * NK32;
   extern __shared__ __align__(16) uint8_t tsm[];
   const bool three = three_i != 0;
   const int n = blockIdx.x / H, h = blockIdx.x % H;
@@ -477,9 +492,9 @@ tfm_attn_fwd_kernel(const float* __restrict__ qkv, int ldq, int D, int H, int T,
   unsigned char* km = tsm + 6 * plane;
   uint32_t* bits = reinterpret_cast<uint32_t*>(tsm + ((6 * plane + SK + 15) & ~15u));
   const float* base = qkv + (long long)n * T * ldq + h * TFM_DH;
-  tfm_stage(tsm, oQh, oQl, base, ldq, S, SK, scale * TFM_LOG2E);
-  tfm_stage(tsm, oKh, oKl, base + D, ldq, S, SK, 1.f);
-  tfm_stage(tsm, oVh, oVl, base + 2 * D, ldq, S, SK, 1.f);
+  tfm_stage<SK, NTHR>(tsm, oQh, oQl, base, ldq, S, scale * TFM_LOG2E);
+  tfm_stage<SK, NTHR>(tsm, oKh, oKl, base + D, ldq, S, 1.f);
+  tfm_stage<SK, NTHR>(tsm, oVh, oVl, base + 2 * D, ldq, S, 1.f);
   for (int u = threadIdx.x; u < SK; u += blockDim.x) km[u] = (u < S && kmask[(long long)n * T + u]) ? 1 : 0;
   if (drop_on) tfm_drop_bits(bits, SK, seed, site, (unsigned long long)blockIdx.x, thr);
   __syncthreads();
@@ -602,7 +617,7 @@ tfm_attn_fwd_kernel(const float* __restrict__ qkv, int ldq, int D, int H, int T,
 //   phase B (warp = 16 keys):    the same tiles transposed (K Q^T, V dO^T), dV = (M c P)^T dO, dK = dS^T Q / sqrt(d_h)
 // Both phases walk the other axis in blocks of 64 so that a warp never holds more than two 16 x 64 fp32 tiles.
 template <int NK32>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(64 * NK32, NK32 == 1 ? 6 : NK32 == 2 ? 3 : NK32 == 3 ? 2 : 1)
 tfm_attn_bwd_kernel(const float* __restrict__ qkv, int ldq, int D, int H, int T, const unsigned char* __restrict__ kmask,
                     float scale, const float* __restrict__ d_o, const __nv_bfloat16* __restrict__ o_hi,
                     const __nv_bfloat16* __restrict__ o_lo, int dp, const float* __restrict__ lse,
@@ -611,6 +626,7 @@ tfm_attn_bwd_kernel(const float* __restrict__ qkv, int ldq, int D, int H, int T,
   constexpr int SK = 32 * NK32;
   constexpr int BW = (NK32 & 1) ? 32 : 64;  // keys (phase A) / queries (phase B) per block
   constexpr int BT = BW / 8;                // 8-wide tiles per block
+  constexpr int NTHR = 64 * NK32;
   extern __shared__ __align__(16) uint8_t tsm[];
   const bool three = three_i != 0;
   const int n = blockIdx.x / H, h = blockIdx.x % H;
@@ -623,37 +639,44 @@ tfm_attn_bwd_kernel(const float* __restrict__ qkv, int ldq, int D, int H, int T,
   unsigned char* km = reinterpret_cast<unsigned char*>(dd + SK);
   uint32_t* bits = reinterpret_cast<uint32_t*>(tsm + ((8 * plane + 2 * SK * 4 + SK + 15) & ~15u));
   const float* base = qkv + (long long)n * T * ldq + h * TFM_DH;
-  tfm_stage(tsm, oQh, oQl, base, ldq, S, SK, scale * TFM_LOG2E);
-  tfm_stage(tsm, oKh, oKl, base + D, ldq, S, SK, 1.f);
-  tfm_stage(tsm, oVh, oVl, base + 2 * D, ldq, S, SK, 1.f);
-  // dO with D_t = dO_t . ctx_t on the way (16 consecutive lanes own a row)
-  for (int i = threadIdx.x; i < SK * 16; i += blockDim.x) {
-    const int t = i >> 4, c = (i & 15) * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    float part = 0.f;
-    if (t < S) {
-      const long long row = (long long)n * T + t;
-      v = __ldg(reinterpret_cast<const float4*>(d_o + row * D + h * TFM_DH + c));
-      const uint2 oh = *reinterpret_cast<const uint2*>(o_hi + row * dp + h * TFM_DH + c);
-      float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&oh.x));
-      float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&oh.y));
-      if (o_lo) {
-        const uint2 ol = *reinterpret_cast<const uint2*>(o_lo + row * dp + h * TFM_DH + c);
-        const float2 a2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ol.x));
-        const float2 b2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ol.y));
-        a.x += a2.x; a.y += a2.y; b.x += b2.x; b.y += b2.y;
+  tfm_stage<SK, NTHR>(tsm, oQh, oQl, base, ldq, S, scale * TFM_LOG2E);
+  tfm_stage<SK, NTHR>(tsm, oKh, oKl, base + D, ldq, S, 1.f);
+  tfm_stage<SK, NTHR>(tsm, oVh, oVl, base + 2 * D, ldq, S, 1.f);
+  {  // dO with D_t = dO_t . ctx_t on the way (16 consecutive lanes own a row); all loads issued before the first use
+    constexpr int ITER = SK * 16 / NTHR;
+    float4 v[ITER];
+    uint2 oh[ITER], ol[ITER];
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+      const int i = threadIdx.x + it * NTHR, t = i >> 4, c = (i & 15) * 4;
+      v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      oh[it] = ol[it] = make_uint2(0u, 0u);
+      if (t < S) {
+        const long long row = (long long)n * T + t;
+        v[it] = __ldg(reinterpret_cast<const float4*>(d_o + row * D + h * TFM_DH + c));
+        oh[it] = *reinterpret_cast<const uint2*>(o_hi + row * dp + h * TFM_DH + c);
+        if (o_lo) ol[it] = *reinterpret_cast<const uint2*>(o_lo + row * dp + h * TFM_DH + c);
       }
-      part = (v.x * a.x + v.y * a.y) + (v.z * b.x + v.w * b.y);
     }
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    if ((i & 15) == 0) dd[t] = part;
-    uint32_t h0, l0, h1, l1;
-    split_pack2(v.x, v.y, h0, l0);
-    split_pack2(v.z, v.w, h1, l1);
-    const uint32_t off = (uint32_t)(t * TFM_PLANE_ROW_BYTES + c * 2);
-    *reinterpret_cast<uint2*>(tsm + oGh + off) = make_uint2(h0, h1);
-    *reinterpret_cast<uint2*>(tsm + oGl + off) = make_uint2(l0, l1);
+    for (int it = 0; it < ITER; ++it) {
+      const int i = threadIdx.x + it * NTHR, t = i >> 4, c = (i & 15) * 4;
+      float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&oh[it].x));
+      float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&oh[it].y));
+      const float2 a2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ol[it].x));
+      const float2 b2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ol[it].y));
+      a.x += a2.x; a.y += a2.y; b.x += b2.x; b.y += b2.y;
+      float part = (v[it].x * a.x + v[it].y * a.y) + (v[it].z * b.x + v[it].w * b.y);
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      if ((i & 15) == 0) dd[t] = part;
+      uint32_t h0, l0, h1, l1;
+      split_pack2(v[it].x, v[it].y, h0, l0);
+      split_pack2(v[it].z, v[it].w, h1, l1);
+      const uint32_t off = (uint32_t)(t * TFM_PLANE_ROW_BYTES + c * 2);
+      *reinterpret_cast<uint2*>(tsm + oGh + off) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(tsm + oGl + off) = make_uint2(l0, l1);
+    }
   }
   for (int u = threadIdx.x; u < SK; u += blockDim.x) {
     km[u] = (u < S && kmask[(long long)n * T + u]) ? 1 : 0;

@@ -123,7 +123,7 @@ static int tfm_attn_attrs_init() {
 static int tfm_attn_fwd(const Ctx& c, const TfmDims& d, const TfmWs& w, const TfmLayerWs& y, int N, int T,
                         const DropCfg& adrop, unsigned long long lseed) {
   const long long R = (long long)N * T;
-  const int nk32 = (T + 31) / 32, SK = 32 * nk32, threads = 32 * ((T + 15) / 16);
+  const int nk32 = (T + 31) / 32, SK = 32 * nk32, threads = 64 * nk32;
   bf16* lo = c.two_planes() ? y.cp + R * d.Dp : nullptr;
   const float scale = 1.0f / sqrtf((float)TFM_DH);
 #define NRL_TFM_FWD(NK)                                                                                          \
@@ -141,7 +141,7 @@ static int tfm_attn_fwd(const Ctx& c, const TfmDims& d, const TfmWs& w, const Tf
 static int tfm_attn_bwd(const Ctx& c, const TfmDims& d, const TfmWs& w, const TfmLayerWs& y, int N, int T,
                         const DropCfg& adrop, unsigned long long lseed) {
   const long long R = (long long)N * T;
-  const int nk32 = (T + 31) / 32, SK = 32 * nk32, threads = 32 * ((T + 15) / 16);
+  const int nk32 = (T + 31) / 32, SK = 32 * nk32, threads = 64 * nk32;
   const bf16* olo = c.two_planes() ? y.cp + R * d.Dp : nullptr;
   bf16* glo = c.two_planes() ? w.dqkv + R * d.P3 : nullptr;
   const float scale = 1.0f / sqrtf((float)TFM_DH);
@@ -355,9 +355,14 @@ int nrl_tfm_encoder_bwd(const long long* input_ids, const long long* attention_m
     const unsigned long long lseed = tfm_layer_seed(seed, l);
     const bool need_dx = l > lowest || embed_grads;  // the data gradient below the lowest trainable layer is not needed
     // LN2 backward
-    tfm_ln_bwd_kernel<<<grid_for(R, 8, (g ? 2 : 8) * g_dev.sm_count), 256, g ? 2 * d.D * sizeof(float) : 0, c.stream>>>(
-        y.s2, dy, R, d.D, p.ln2_g, d.eps, w.ds, w.dtp, dtp_lo, d.D, hdrop.on ? y.mask2 : nullptr, d.MW, hdrop.scale,
-        g ? g->ln2_g : nullptr, g ? g->ln2_b : nullptr);
+    if (g)
+      tfm_ln_bwd_kernel<true><<<grid_for(R, 4, 6 * g_dev.sm_count), 128, 2 * d.D * sizeof(float), c.stream>>>(
+          y.s2, dy, R, d.D, p.ln2_g, d.eps, w.ds, w.dtp, dtp_lo, d.D, hdrop.on ? y.mask2 : nullptr, d.MW, hdrop.scale,
+          g->ln2_g, g->ln2_b);
+    else
+      tfm_ln_bwd_kernel<false><<<grid_for(R, 4, 16 * g_dev.sm_count), 128, 0, c.stream>>>(
+          y.s2, dy, R, d.D, p.ln2_g, d.eps, w.ds, w.dtp, dtp_lo, d.D, hdrop.on ? y.mask2 : nullptr, d.MW, hdrop.scale,
+          nullptr, nullptr);
     LAUNCH_CHECK("tfm ln2_bwd");
     if (g) TRY(gemm_tn(c, w.dtp, d.D, d.D, y.up, d.Ip, d.Ip, R, g->o_w, d.I, d.I, g->o_b, "tfm gemm ffn_out wgrad"));
     {  // dup = (dt2 Wo) * gelu'(u)
@@ -376,9 +381,14 @@ int nrl_tfm_encoder_bwd(const long long* input_ids, const long long* attention_m
       TRY(gemm_nt(c, w.dup, R, d.I, pk.wi_t, d.D, d.I, d.I, e, sk, "tfm gemm ffn_in dgrad"));
     }
     // LN1 backward
-    tfm_ln_bwd_kernel<<<grid_for(R, 8, (g ? 2 : 8) * g_dev.sm_count), 256, g ? 2 * d.D * sizeof(float) : 0, c.stream>>>(
-        y.s1, w.gb, R, d.D, p.ln1_g, d.eps, w.ds, w.dtp, dtp_lo, d.D, hdrop.on ? y.mask1 : nullptr, d.MW, hdrop.scale,
-        g ? g->ln1_g : nullptr, g ? g->ln1_b : nullptr);
+    if (g)
+      tfm_ln_bwd_kernel<true><<<grid_for(R, 4, 6 * g_dev.sm_count), 128, 2 * d.D * sizeof(float), c.stream>>>(
+          y.s1, w.gb, R, d.D, p.ln1_g, d.eps, w.ds, w.dtp, dtp_lo, d.D, hdrop.on ? y.mask1 : nullptr, d.MW, hdrop.scale,
+          g->ln1_g, g->ln1_b);
+    else
+      tfm_ln_bwd_kernel<false><<<grid_for(R, 4, 16 * g_dev.sm_count), 128, 0, c.stream>>>(
+          y.s1, w.gb, R, d.D, p.ln1_g, d.eps, w.ds, w.dtp, dtp_lo, d.D, hdrop.on ? y.mask1 : nullptr, d.MW, hdrop.scale,
+          nullptr, nullptr);
     LAUNCH_CHECK("tfm ln1_bwd");
     if (g) TRY(gemm_tn(c, w.dtp, d.D, d.D, y.cp, d.Dp, d.Dp, R, g->ao_w, d.D, d.D, g->ao_b, "tfm gemm attn_out wgrad"));
     {  // dO = dt1 Wao
