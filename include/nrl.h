@@ -330,7 +330,7 @@ int nrl_nrms_step_host(const long long* hist_ids_host, const long long* cand_ids
  * `self.plm_model(**text)[0]`): a HF RobertaModel / BertModel-shaped post-LN encoder -- embeddings
  * (word + position + token type -> LayerNorm -> dropout) and `num_layers` layers of
  *   h1 = LN(x + drop(MHSA(x) W_ao + b)),   h2 = LN(h1 + drop(gelu(h1 W_i + b) W_o + b)),
- * key-padding mask from attention_mask, exact (erf) GELU, head dim 64, T <= 128 tokens.
+ * key-padding mask from attention_mask, exact (erf) GELU, head dim 64, any T <= max_pos.
  * The third-party algorithm restated here is transformers' modeling_roberta.py (pinned by the
  * reference at transformers 4.x; identical maths in the 5.5 of this image, which is what the
  * golden vectors under tests/golden/tfm_*.npz were minted with).  state_dict names in comments

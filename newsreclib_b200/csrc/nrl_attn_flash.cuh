@@ -69,17 +69,31 @@ __device__ __forceinline__ void fl_stage(uint8_t* sm, uint32_t o_hi, uint32_t o_
     }
   }
 }
+// optional key-padding mask and attention-probability dropout (the PLM transformer at more than 128 tokens): per block,
+// 128 key-mask bytes and a 128 x 64 (64 x 128 in the dK/dV kernel) keep-bit tile = 256 words, drawn by the CTA's 256
+// threads with the element numbering of tfm_drop_bits (SP = S rounded up to 32), so that every kernel and
+// nrl_tfm_attn_dropout_mask see the same bits
+constexpr int FLASH_AUX_BYTES = 128 + 256 * 4;
+__device__ __forceinline__ void fl_drop_tile(uint32_t* bits, int words_per_row, unsigned long long item, int SP, int t0,
+                                             int u0, unsigned long long seed, uint32_t site, uint32_t thr) {
+  const int r = threadIdx.x / words_per_row, w = threadIdx.x % words_per_row;
+  bits[threadIdx.x] = drop_keep_bits32(seed, site, (item * (unsigned long long)SP + (unsigned long long)(t0 + r)) * SP +
+                                                       (unsigned long long)(u0 + 32 * w), thr);
+}
+
 template <int DH>
-__host__ __device__ constexpr int flash_fwd_smem() { return (2 * 128 + 4 * 64) * FlashCfg<DH>::ROWB + 16; }
+__host__ __device__ constexpr int flash_fwd_smem() { return (2 * 128 + 4 * 64) * FlashCfg<DH>::ROWB + 16 + FLASH_AUX_BYTES; }
 template <int DH>
-__host__ __device__ constexpr int flash_bwd_smem() { return (4 * 128 + 4 * 64) * FlashCfg<DH>::ROWB + 2 * 128 * 4 + 16; }
+__host__ __device__ constexpr int flash_bwd_smem() { return (4 * 128 + 4 * 64) * FlashCfg<DH>::ROWB + 2 * 128 * 4 + 16 + FLASH_AUX_BYTES; }
 
 // ---------------------------------------------------------------- forward
 template <int DH>
 __global__ void __launch_bounds__(256)
 attn_fwd_flash_kernel(const float* __restrict__ qkv, int E, int ldq, int heads, int S, long long seq_stride, int NB,
                       long long batch_stride, float scale, __nv_bfloat16* __restrict__ o_hi,
-                      __nv_bfloat16* __restrict__ o_lo, int ep, float* __restrict__ lse, int three_i) {
+                      __nv_bfloat16* __restrict__ o_lo, int ep, float* __restrict__ lse, int three_i,
+                      const unsigned char* __restrict__ kmask = nullptr, int drop_on = 0, uint32_t thr = 0,
+                      float dscale = 1.f, unsigned long long seed = 0, uint32_t site = 0) {
   using C = FlashCfg<DH>;
   constexpr int ROWB = C::ROWB;
   extern __shared__ __align__(16) uint8_t fsm[];
@@ -89,6 +103,10 @@ attn_fwd_flash_kernel(const float* __restrict__ qkv, int E, int ldq, int heads, 
   const long long row_base = (long long)b * batch_stride;
   const uint32_t oQh = 0, oQl = C::QB * ROWB, oKh = 2 * C::QB * ROWB, oKl = oKh + C::KB * ROWB, oVh = oKl + C::KB * ROWB,
                  oVl = oVh + C::KB * ROWB;
+  unsigned char* km = fsm + oVl + C::KB * ROWB;
+  uint32_t* bits = reinterpret_cast<uint32_t*>(km + 128);
+  const int SP = (S + 31) & ~31;
+  const unsigned long long item = (unsigned long long)b * heads + h;
   const int q0 = qb * C::QB;
   fl_stage<DH, C::QB>(fsm, oQh, oQl, qkv + h * DH, ldq, seq_stride, row_base, q0, S, scale * TFM_LOG2E);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
@@ -103,6 +121,8 @@ attn_fwd_flash_kernel(const float* __restrict__ qkv, int E, int ldq, int heads, 
     __syncthreads();  // the previous block's K / V are no longer read (first pass: Q staged)
     fl_stage<DH, C::KB>(fsm, oKh, oKl, qkv + E + h * DH, ldq, seq_stride, row_base, k0, S, 1.f);
     fl_stage<DH, C::KB>(fsm, oVh, oVl, qkv + 2 * E + h * DH, ldq, seq_stride, row_base, k0, S, 1.f);
+    if (threadIdx.x < C::KB) km[threadIdx.x] = (k0 + threadIdx.x < S && (!kmask || kmask[(long long)b * S + k0 + threadIdx.x])) ? 1 : 0;
+    if (drop_on) fl_drop_tile(bits, 2, item, SP, q0, k0, seed, site, thr);
     __syncthreads();
     if (!active) continue;
     float s[8][4];
@@ -122,19 +142,21 @@ attn_fwd_flash_kernel(const float* __restrict__ qkv, int E, int ldq, int heads, 
         tfm_mma3(s[2 * j2 + 1], ah, al, bh[2], bh[3], bl[2], bl[3], three);
       }
     }
-    // online softmax (log2 domain); keys >= S take no part
+    // online softmax (log2 domain); keys >= S and masked keys take no part
     float bm0 = -INFINITY, bm1 = -INFINITY;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int u = k0 + 8 * j + 2 * tg;
-      if (u >= S) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
-      if (u + 1 >= S) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+      const int u = 8 * j + 2 * tg;
+      if (!km[u]) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
+      if (!km[u + 1]) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
       bm0 = fmaxf(bm0, fmaxf(s[j][0], s[j][1]));
       bm1 = fmaxf(bm1, fmaxf(s[j][2], s[j][3]));
     }
     bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1)); bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
     bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1)); bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
-    const float n0 = fmaxf(m0, bm0), n1 = fmaxf(m1, bm1);  // finite: every block holds at least one key < S
+    float n0 = fmaxf(m0, bm0), n1 = fmaxf(m1, bm1);
+    if (n0 == -INFINITY) n0 = 0.f;  // nothing but masked keys so far: every p below is exp2(-inf) = 0
+    if (n1 == -INFINITY) n1 = 0.f;
     const float c0 = ex2_approx(m0 - n0), c1 = ex2_approx(m1 - n1);
     m0 = n0; m1 = n1;
     float ps0 = 0.f, ps1 = 0.f;
@@ -149,6 +171,17 @@ attn_fwd_flash_kernel(const float* __restrict__ qkv, int E, int ldq, int heads, 
     l0 = l0 * c0 + ps0; l1 = l1 * c1 + ps1;
 #pragma unroll
     for (int j = 0; j < C::DT; ++j) { o[j][0] *= c0; o[j][1] *= c0; o[j][2] *= c1; o[j][3] *= c1; }
+    if (drop_on) {  // dropped probabilities leave the PV product, not the normaliser
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int sh = 8 * (j & 3) + 2 * tg;
+        const uint32_t b0 = bits[(w0 + g) * 2 + (j >> 2)] >> sh, b1 = bits[(w0 + g + 8) * 2 + (j >> 2)] >> sh;
+        if (!(b0 & 1u)) s[j][0] = 0.f;
+        if (!(b0 & 2u)) s[j][1] = 0.f;
+        if (!(b1 & 1u)) s[j][2] = 0.f;
+        if (!(b1 & 2u)) s[j][3] = 0.f;
+      }
+    }
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {  // 64 keys = 4 k-steps
       uint32_t ah[4], al[4];
@@ -167,7 +200,8 @@ attn_fwd_flash_kernel(const float* __restrict__ qkv, int E, int ldq, int heads, 
     }
   }
   if (!active) return;
-  const float i0 = 1.f / l0, i1 = 1.f / l1;
+  const float keep_scale = drop_on ? dscale : 1.f;
+  const float i0 = l0 > 0.f ? keep_scale / l0 : 0.f, i1 = l1 > 0.f ? keep_scale / l1 : 0.f;
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     const int t = q0 + w0 + g + 8 * half;
@@ -182,7 +216,7 @@ attn_fwd_flash_kernel(const float* __restrict__ qkv, int E, int ldq, int heads, 
       *reinterpret_cast<uint32_t*>(o_hi + off) = hh;
       if (o_lo) *reinterpret_cast<uint32_t*>(o_lo + off) = ll;
     }
-    if (tg == 0) lse[grow * heads + h] = ((half ? m1 : m0) + log2f(half ? l1 : l0)) * TFM_LN2;
+    if (tg == 0) lse[grow * heads + h] = (half ? l1 : l0) > 0.f ? ((half ? m1 : m0) + log2f(half ? l1 : l0)) * TFM_LN2 : 0.f;
     if (h == 0)
       for (int c = E + tg; c < ep; c += 4) {
         o_hi[grow * ep + c] = __float2bfloat16_rn(c == E ? 1.f : 0.f);
@@ -230,7 +264,9 @@ __global__ void __launch_bounds__(256)
 attn_bwd_flash_dq_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o, long long ld_do,
                          const float* __restrict__ lse, const float* __restrict__ delta, int E, int ldq, int heads, int S,
                          long long seq_stride, int NB, long long batch_stride, float scale,
-                         __nv_bfloat16* __restrict__ g_hi, __nv_bfloat16* __restrict__ g_lo, int p3, int three_i) {
+                         __nv_bfloat16* __restrict__ g_hi, __nv_bfloat16* __restrict__ g_lo, int p3, int three_i,
+                         const unsigned char* __restrict__ kmask = nullptr, int drop_on = 0, uint32_t thr = 0,
+                         float dscale = 1.f, unsigned long long seed = 0, uint32_t site = 0) {
   using C = FlashCfg<DH>;
   constexpr int ROWB = C::ROWB;
   extern __shared__ __align__(16) uint8_t fsm[];
@@ -242,6 +278,11 @@ attn_bwd_flash_dq_kernel(const float* __restrict__ qkv, const float* __restrict_
                  oKl = oKh + C::KB * ROWB, oVh = oKl + C::KB * ROWB, oVl = oVh + C::KB * ROWB;
   float* lse2 = reinterpret_cast<float*>(fsm + oVl + C::KB * ROWB);
   float* dd = lse2 + C::QB;
+  unsigned char* km = reinterpret_cast<unsigned char*>(dd + C::QB);
+  uint32_t* bits = reinterpret_cast<uint32_t*>(km + 128);
+  const int SP = (S + 31) & ~31;
+  const unsigned long long item = (unsigned long long)b * heads + h;
+  const float c_keep = drop_on ? dscale : 1.f;
   const int q0 = qb * C::QB;
   fl_stage<DH, C::QB>(fsm, oQh, oQl, qkv + h * DH, ldq, seq_stride, row_base, q0, S, scale * TFM_LOG2E);
   fl_stage<DH, C::QB>(fsm, oGh, oGl, d_o + h * DH, ld_do, seq_stride, row_base, q0, S, 1.f);
@@ -257,6 +298,8 @@ attn_bwd_flash_dq_kernel(const float* __restrict__ qkv, const float* __restrict_
     __syncthreads();
     fl_stage<DH, C::KB>(fsm, oKh, oKl, qkv + E + h * DH, ldq, seq_stride, row_base, k0, S, 1.f);
     fl_stage<DH, C::KB>(fsm, oVh, oVl, qkv + 2 * E + h * DH, ldq, seq_stride, row_base, k0, S, 1.f);
+    if (threadIdx.x < C::KB) km[threadIdx.x] = (k0 + threadIdx.x < S && (!kmask || kmask[(long long)b * S + k0 + threadIdx.x])) ? 1 : 0;
+    if (drop_on) fl_drop_tile(bits, 2, item, SP, q0, k0, seed, site, thr);
     __syncthreads();
     if (!active) continue;
     const float ls0 = lse2[w0 + g], ls1 = lse2[w0 + g + 8], d0 = dd[w0 + g], d1 = dd[w0 + g + 8];
@@ -290,12 +333,21 @@ attn_bwd_flash_dq_kernel(const float* __restrict__ qkv, const float* __restrict_
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int u = k0 + 8 * j + 2 * tg;
-      const bool v0 = u < S, v1 = u + 1 < S;
+      const int u = 8 * j + 2 * tg;
+      const bool v0 = km[u] != 0, v1 = km[u + 1] != 0;
+      float k00 = c_keep, k01 = c_keep, k10 = c_keep, k11 = c_keep;
+      if (drop_on) {
+        const int sh = 8 * (j & 3) + 2 * tg;
+        const uint32_t b0 = bits[(w0 + g) * 2 + (j >> 2)] >> sh, b1 = bits[(w0 + g + 8) * 2 + (j >> 2)] >> sh;
+        if (!(b0 & 1u)) k00 = 0.f;
+        if (!(b0 & 2u)) k01 = 0.f;
+        if (!(b1 & 1u)) k10 = 0.f;
+        if (!(b1 & 2u)) k11 = 0.f;
+      }
       const float p00 = v0 ? ex2_approx(s[j][0] - ls0) : 0.f, p01 = v1 ? ex2_approx(s[j][1] - ls0) : 0.f;
       const float p10 = v0 ? ex2_approx(s[j][2] - ls1) : 0.f, p11 = v1 ? ex2_approx(s[j][3] - ls1) : 0.f;
-      s[j][0] = p00 * (dp[j][0] - d0); s[j][1] = p01 * (dp[j][1] - d0);
-      s[j][2] = p10 * (dp[j][2] - d1); s[j][3] = p11 * (dp[j][3] - d1);
+      s[j][0] = p00 * (k00 * dp[j][0] - d0); s[j][1] = p01 * (k01 * dp[j][1] - d0);
+      s[j][2] = p10 * (k10 * dp[j][2] - d1); s[j][3] = p11 * (k11 * dp[j][3] - d1);
     }
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
@@ -341,7 +393,9 @@ __global__ void __launch_bounds__(256)
 attn_bwd_flash_dkv_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o, long long ld_do,
                           const float* __restrict__ lse, const float* __restrict__ delta, int E, int ldq, int heads, int S,
                           long long seq_stride, int NB, long long batch_stride, float scale,
-                          __nv_bfloat16* __restrict__ g_hi, __nv_bfloat16* __restrict__ g_lo, int p3, int three_i) {
+                          __nv_bfloat16* __restrict__ g_hi, __nv_bfloat16* __restrict__ g_lo, int p3, int three_i,
+                          const unsigned char* __restrict__ kmask = nullptr, int drop_on = 0, uint32_t thr = 0,
+                          float dscale = 1.f, unsigned long long seed = 0, uint32_t site = 0) {
   using C = FlashCfg<DH>;
   constexpr int ROWB = C::ROWB;
   extern __shared__ __align__(16) uint8_t fsm[];
@@ -353,13 +407,18 @@ attn_bwd_flash_dkv_kernel(const float* __restrict__ qkv, const float* __restrict
                  oQl = oQh + C::KB * ROWB, oGh = oQl + C::KB * ROWB, oGl = oGh + C::KB * ROWB;
   float* lse2 = reinterpret_cast<float*>(fsm + oGl + C::KB * ROWB);
   float* dd = lse2 + C::QB;
+  uint32_t* bits = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(dd + C::QB) + 128);
+  const int SP = (S + 31) & ~31;
+  const unsigned long long item = (unsigned long long)b * heads + h;
+  const float c_keep = drop_on ? dscale : 1.f;
   const int k0 = kb * C::QB;
   fl_stage<DH, C::QB>(fsm, oKh, oKl, qkv + E + h * DH, ldq, seq_stride, row_base, k0, S, 1.f);
   fl_stage<DH, C::QB>(fsm, oVh, oVl, qkv + 2 * E + h * DH, ldq, seq_stride, row_base, k0, S, 1.f);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
   const int w0 = 16 * warp;
   const bool active = k0 + w0 < S;
-  const bool kv0 = k0 + w0 + g < S, kv1 = k0 + w0 + g + 8 < S;
+  const int u0 = k0 + w0 + g, u1 = u0 + 8;
+  const bool kv0 = u0 < S && (!kmask || kmask[(long long)b * S + u0]), kv1 = u1 < S && (!kmask || kmask[(long long)b * S + u1]);
   const uint32_t sb = smem_u32(fsm);
   float dk[C::DT][4], dv[C::DT][4];
 #pragma unroll
@@ -372,6 +431,7 @@ attn_bwd_flash_dkv_kernel(const float* __restrict__ qkv, const float* __restrict
     fl_stage<DH, C::KB>(fsm, oQh, oQl, qkv + h * DH, ldq, seq_stride, row_base, q0, S, scale * TFM_LOG2E);
     fl_stage<DH, C::KB>(fsm, oGh, oGl, d_o + h * DH, ld_do, seq_stride, row_base, q0, S, 1.f);
     fl_stage_rowstats(lse2, dd, lse, delta, heads, h, seq_stride, row_base, q0, C::KB, S);
+    if (drop_on) fl_drop_tile(bits, 4, item, SP, q0, k0, seed, site, thr);  // [64 queries][128 keys]
     __syncthreads();
     if (!active) continue;
     float st[8][4], dpt[8][4];
@@ -408,11 +468,17 @@ attn_bwd_flash_dkv_kernel(const float* __restrict__ qkv, const float* __restrict
       for (int e = 0; e < 2; ++e) {
         const int t = 8 * j + 2 * tg + e;  // query of the block (lse2 = +inf beyond S: P = 0)
         const float ls = lse2[t], dt = dd[t];
+        float kp0 = c_keep, kp1 = c_keep;
+        if (drop_on) {
+          const uint32_t wd = bits[t * 4 + ((w0 + g) >> 5)];  // keys w0 + g and + 8 share a word
+          if (!((wd >> ((w0 + g) & 31)) & 1u)) kp0 = 0.f;
+          if (!((wd >> ((w0 + g + 8) & 31)) & 1u)) kp1 = 0.f;
+        }
         const float p0 = kv0 ? ex2_approx(st[j][e] - ls) : 0.f, p1 = kv1 ? ex2_approx(st[j][2 + e] - ls) : 0.f;
-        st[j][e] = p0 * (dpt[j][e] - dt);
-        st[j][2 + e] = p1 * (dpt[j][2 + e] - dt);
-        dpt[j][e] = p0;
-        dpt[j][2 + e] = p1;
+        st[j][e] = p0 * (kp0 * dpt[j][e] - dt);
+        st[j][2 + e] = p1 * (kp1 * dpt[j][2 + e] - dt);
+        dpt[j][e] = p0 * kp0;
+        dpt[j][2 + e] = p1 * kp1;
       }
     }
 #pragma unroll

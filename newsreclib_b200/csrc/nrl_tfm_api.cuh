@@ -66,6 +66,7 @@ struct TfmWs {
   uint32_t *mask_e, *mask_e1;
   float *xa, *xb, *h1;       // fp32 residual stream (ping-pong) and the LN1 output of the current layer
   float *ga, *gb, *ds, *d_o;  // backward: layer gradient ping-pong, LN-backward residual branch, attention dO
+  float* delta;               // [R][H] dO . ctx per row and head (attention backward beyond 128 tokens)
   bf16 *dtp, *dup, *dqkv;     // backward GEMM operands
   std::vector<TfmLayerWs> layer;
 };
@@ -82,6 +83,7 @@ static void carve_tfm(Bump& b, long long N, int T, const TfmDims& d, TfmWs& w) {
   w.gb = b.take<float>((size_t)R * d.D);
   w.ds = b.take<float>((size_t)R * d.D);
   w.d_o = b.take<float>((size_t)R * d.D);
+  w.delta = b.take<float>((size_t)R * d.H);
   w.dtp = b.take<bf16>(2ull * R * d.D);
   w.dup = b.take<bf16>(2ull * R * d.I);
   w.dqkv = b.take<bf16>(2ull * R * d.P3);
@@ -116,6 +118,7 @@ static int tfm_attn_attrs_init() {
   CUDA_TRY(cudaFuncSetAttribute(tfm_attn_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tfm_attn_bwd_smem(64)));
   CUDA_TRY(cudaFuncSetAttribute(tfm_attn_bwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tfm_attn_bwd_smem(96)));
   CUDA_TRY(cudaFuncSetAttribute(tfm_attn_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tfm_attn_bwd_smem(128)));
+  TRY(attn_attrs_init());  // the flash kernels take over beyond 128 tokens
   done = true;
   return NRL_OK;
 }
@@ -126,6 +129,14 @@ static int tfm_attn_fwd(const Ctx& c, const TfmDims& d, const TfmWs& w, const Tf
   const int nk32 = (T + 31) / 32, SK = 32 * nk32, threads = 64 * nk32;
   bf16* lo = c.two_planes() ? y.cp + R * d.Dp : nullptr;
   const float scale = 1.0f / sqrtf((float)TFM_DH);
+  if (T > 128) {  // flash-style kernels (nrl_attn_flash.cuh) with the key-padding mask and the same dropout bits
+    const int nqb = (T + 127) / 128;
+    attn_fwd_flash_kernel<TFM_DH><<<(unsigned)((long long)N * d.H * nqb), 256, flash_fwd_smem<TFM_DH>(), c.stream>>>(
+        y.qkv, d.D, d.LDQ, d.H, T, 1, N, T, scale, y.cp, lo, d.Dp, y.lse, c.two_planes() ? 1 : 0, w.kmask, adrop.on,
+        adrop.thr, adrop.scale, lseed, 2u);
+    LAUNCH_CHECK("tfm attn_fwd (flash)");
+    return NRL_OK;
+  }
 #define NRL_TFM_FWD(NK)                                                                                          \
   tfm_attn_fwd_kernel<NK><<<(unsigned)(N * d.H), threads, tfm_attn_fwd_smem(SK), c.stream>>>(                    \
       y.qkv, d.LDQ, d.D, d.H, T, w.kmask, scale, y.cp, lo, d.Dp, y.lse, c.two_planes() ? 1 : 0, adrop.on, adrop.thr, \
@@ -145,6 +156,22 @@ static int tfm_attn_bwd(const Ctx& c, const TfmDims& d, const TfmWs& w, const Tf
   const bf16* olo = c.two_planes() ? y.cp + R * d.Dp : nullptr;
   bf16* glo = c.two_planes() ? w.dqkv + R * d.P3 : nullptr;
   const float scale = 1.0f / sqrtf((float)TFM_DH);
+  if (T > 128) {
+    const int nqb = (T + 127) / 128;
+    const unsigned grid = (unsigned)((long long)N * d.H * nqb);
+    attn_delta_kernel<<<grid_for(R, 8, 8 * g_dev.sm_count), 256, 0, c.stream>>>(w.d_o, d.D, y.cp, olo, d.Dp, R, d.H, TFM_DH,
+                                                                             w.delta);
+    LAUNCH_CHECK("tfm attn_delta");
+    attn_bwd_flash_dq_kernel<TFM_DH><<<grid, 256, flash_bwd_smem<TFM_DH>(), c.stream>>>(
+        y.qkv, w.d_o, d.D, y.lse, w.delta, d.D, d.LDQ, d.H, T, 1, N, T, scale, w.dqkv, glo, d.P3, c.two_planes() ? 1 : 0,
+        w.kmask, adrop.on, adrop.thr, adrop.scale, lseed, 2u);
+    LAUNCH_CHECK("tfm attn_bwd dq (flash)");
+    attn_bwd_flash_dkv_kernel<TFM_DH><<<grid, 256, flash_bwd_smem<TFM_DH>(), c.stream>>>(
+        y.qkv, w.d_o, d.D, y.lse, w.delta, d.D, d.LDQ, d.H, T, 1, N, T, scale, w.dqkv, glo, d.P3, c.two_planes() ? 1 : 0,
+        w.kmask, adrop.on, adrop.thr, adrop.scale, lseed, 2u);
+    LAUNCH_CHECK("tfm attn_bwd dkv (flash)");
+    return NRL_OK;
+  }
 #define NRL_TFM_BWD(NK)                                                                                          \
   tfm_attn_bwd_kernel<NK><<<(unsigned)(N * d.H), threads, tfm_attn_bwd_smem(SK), c.stream>>>(                    \
       y.qkv, d.LDQ, d.D, d.H, T, w.kmask, scale, w.d_o, y.cp, olo, d.Dp, y.lse, w.dqkv, glo, d.P3,               \
@@ -160,7 +187,7 @@ static int tfm_attn_bwd(const Ctx& c, const TfmDims& d, const TfmWs& w, const Tf
 
 static int tfm_check(const char* who, int N, int T, const TfmDims& d) {
   if (N <= 0 || T <= 0) return fail(NRL_ERR_INVALID_ARG, "%s: empty input", who);
-  if (T > 128) return fail(NRL_ERR_UNSUPPORTED, "%s: %d tokens per title > 128 (the staged attention tile)", who, T);
+  if (T > d.P) return fail(NRL_ERR_INVALID_ARG, "%s: %d tokens per text > max_position_embeddings %d", who, T, d.P);
   if (d.L <= 0) return fail(NRL_ERR_INVALID_ARG, "%s: num_layers must be positive", who);
   return NRL_OK;
 }
@@ -428,7 +455,7 @@ int nrl_tfm_encoder_bwd(const long long* input_ids, const long long* attention_m
 
 int nrl_tfm_attn_dropout_mask(unsigned char* keep, int layer, int n, int h, int heads, int T, unsigned long long seed,
                               float p, void* stream) {
-  if (!keep || layer < 0 || n < 0 || h < 0 || h >= heads || T <= 0 || T > 128 || p < 0.f || p >= 1.f)
+  if (!keep || layer < 0 || n < 0 || h < 0 || h >= heads || T <= 0 || p < 0.f || p >= 1.f)
     return fail(NRL_ERR_INVALID_ARG, "nrl_tfm_attn_dropout_mask: bad argument");
   const int SK = 32 * ((T + 31) / 32);
   tfm_attn_mask_kernel<<<grid_for((long long)T * T, 256, 64), 256, 0, static_cast<cudaStream_t>(stream)>>>(

@@ -83,7 +83,7 @@ class PLM(nn.Module):
     ``text.py:70-73`` all unchanged) and ``self.plm_model(**text)[0]`` (``text.py:92``) runs on the sm_100a
     encoder (``ops.TfmEncoderFn``: embeddings, every layer's projections on tcgen05, key-padding-masked attention,
     LayerNorm / GELU / the three dropouts, forward and backward).  Architectures the kernels do not cover
-    (anything but RoBERTa-style post-LN layers with head dim 64, erf-GELU, absolute positions, <= 128 tokens) raise;
+    (anything but RoBERTa-style post-LN layers with head dim 64, erf-GELU, absolute positions) raise;
     ``transformer_impl="hf"`` keeps the third-party torch module on the path instead."""
 
     def __init__(self, plm_model, frozen_layers, embed_dim: int, use_mhsa: bool, apply_reduce_dim: bool,
@@ -170,9 +170,6 @@ class PLM(nn.Module):
             raise ValueError(f"the sm_100a transformer takes input_ids / attention_mask only, got {sorted(extra)} "
                              f"(the reference tokenises with return_token_type_ids=False, rec_dataset.py:181)")
         ids = text["input_ids"]
-        if ids.shape[1] > 128:
-            raise ValueError(f"{ids.shape[1]} tokens per text > 128: tokenise with max_length <= 128 or pass "
-                             f"transformer_impl='hf'")
         training = self.plm_model.training
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if training else 0
         return ops.TfmEncoderFn.apply(ids, text.get("attention_mask"), self._tfm_state, training, seed, self.precision,

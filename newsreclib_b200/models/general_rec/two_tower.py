@@ -18,6 +18,25 @@ from ..components.layers.click_predictor import DotProduct
 
 class TwoTowerRecommender(AbstractRecommneder):
     late_fusion: bool = False
+    # the NRMS / NAML news encoders treat every news of a call independently (attention within one title, pooling per
+    # news), so ``news_encoder(x_hist)`` and ``news_encoder(x_cand)`` (nrms_module.py:231,235) give the same vectors
+    # as ONE call over the concatenated news: half the launches, twice the rows per GEMM, one embedding-gradient
+    # buffer in the backward pass.  Not valid for the PLM head (it attends across the news of a call), which keeps two.
+    merge_news_calls: bool = True
+
+    def _encode_hist_and_cand(self, x_hist, x_cand):
+        enc = self.news_encoder
+        if not hasattr(self, "_per_news_encoder"):
+            from ..components.encoders.news.text import PLM
+            self._per_news_encoder = not any(isinstance(m, PLM) for m in enc.modules())
+        keys = list(getattr(enc, "text_encoders", {}).keys()) + list(getattr(enc, "category_encoders", {}).keys())
+        if not (self.merge_news_calls and self._per_news_encoder and keys and all(
+                torch.is_tensor(x_hist.get(k)) and torch.is_tensor(x_cand.get(k)) and x_hist[k].shape[1:] == x_cand[k].shape[1:]
+                for k in keys)):
+            return enc(x_hist), enc(x_cand)
+        n_hist = x_hist[keys[0]].shape[0]
+        vec = enc({k: torch.cat([x_hist[k], x_cand[k]], dim=0) for k in keys})
+        return vec[:n_hist], vec[n_hist:]
 
     # ------------------------------------------------------------------ layout helpers
     @staticmethod
@@ -36,8 +55,7 @@ class TwoTowerRecommender(AbstractRecommneder):
 
     def _forward_with_layout(self, batch, layout) -> torch.Tensor:
         B, off_h, off_c, Hmax, Cmax = layout
-        hist_news_vector = self.news_encoder(batch["x_hist"])
-        cand_news_vector = self.news_encoder(batch["x_cand"])
+        hist_news_vector, cand_news_vector = self._encode_hist_and_cand(batch["x_hist"], batch["x_cand"])
         if not self.late_fusion:
             hist_agg = ops.ToDenseFn.apply(hist_news_vector, off_h, B, Hmax)
             user_vector = self.user_encoder(hist_agg)

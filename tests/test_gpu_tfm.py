@@ -108,6 +108,31 @@ def test_tfm_train_mode_replays_the_kernels_dropout_masks():
     assert rel_err(out2, out) > 1e-2  # another seed, another mask
 
 
+@pytest.mark.parametrize("N,T,train", [(5, 200, False), (3, 300, True), (2, 512, False)])
+def test_tfm_long_texts_flash_attention(N, T, train):
+    """More than 128 tokens per text (abstracts; the tokenizer truncates at 512): the flash-style attention kernels with
+    the key-padding mask (whole 64-key blocks of padding included) and, in train mode, the same Philox dropout bits."""
+    from newsreclib_b200 import ops
+    L, H, D = 1, 2, 128
+    ph, pa, seed = (0.1, 0.1, 4242) if train else (0.0, 0.0, 0)
+    cfg = dict(hidden=D, heads=H, inter=256, layers=L, vocab=80, max_pos=T + 4, eps=1e-5)
+    P = random_tfm_params(D, H, 256, L, 80, T + 4, seed=T)
+    ids, att = random_text(N, T, 80, seed=T, min_len=5)
+    w = torch.randn(N, T, D, generator=torch.Generator().manual_seed(3))
+    masks = None
+    if train:
+        R = N * T
+        masks = {"embed": ops.tfm_hidden_dropout_mask(R, D, 0, seed, ph, "cuda").view(N, T, D).cpu(),
+                 ("attn_out", 0): ops.tfm_hidden_dropout_mask(R, D, 1, seed, ph, "cuda").view(N, T, D).cpu(),
+                 ("out", 0): ops.tfm_hidden_dropout_mask(R, D, 2, seed, ph, "cuda").view(N, T, D).cpu(),
+                 ("attn", 0): ops.tfm_attn_dropout_mask(L, N, H, T, seed, pa, "cuda").cpu()[0]}
+    ro, rg = oracle_tfm(P, cfg, ids, att, w, masks=masks, p_hidden=ph, p_attn=pa)
+    out, grads = gpu_tfm(P, cfg, ids, att, w, training=train, seed=seed, p_hidden=ph, p_attn=pa)
+    e, errs = rel_err(out, ro), grad_errors(grads, rg)
+    _report(f"N={N} T={T} train={train} (flash attention)", e, errs)
+    assert e <= FWD_TOL and max(errs.values()) <= GRAD_TOL
+
+
 def test_tfm_bf16_single_pass():
     """NRL_PREC_BF16 (one bf16 plane, one MMA per product): the bf16 configuration's bar is 2e-2."""
     from newsreclib_b200 import ops
@@ -124,11 +149,13 @@ def test_tfm_bf16_single_pass():
 
 def test_tfm_refuses_what_it_does_not_cover():
     from newsreclib_b200 import ops
-    cfg = dict(hidden=128, heads=2, inter=256, layers=1, vocab=60, max_pos=200, eps=1e-5)
-    P = random_tfm_params(128, 2, 256, 1, 60, 200, seed=1)
+    cfg = dict(hidden=128, heads=2, inter=256, layers=1, vocab=60, max_pos=100, eps=1e-5)
+    P = random_tfm_params(128, 2, 256, 1, 60, 100, seed=1)
     ids, att = random_text(2, 130, 60, seed=1)
-    with pytest.raises(RuntimeError, match="128"):
+    with pytest.raises(RuntimeError, match="max_position_embeddings"):
         gpu_tfm(P, cfg, ids, att)
+    with pytest.raises(RuntimeError, match="head dim"):
+        gpu_tfm(random_tfm_params(96, 2, 256, 1, 60, 100, seed=1), dict(cfg, hidden=96), *random_text(2, 10, 60, seed=1))
     ids, att = random_text(2, 10, 60, seed=1)
     ids[0, 3] = 60  # out-of-range token id: flagged on the device, never read out of bounds
     with pytest.raises(RuntimeError):
