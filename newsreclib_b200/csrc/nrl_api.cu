@@ -349,7 +349,18 @@ static int launch_gemm(const Ctx& c, GemmParams& p, const CUtensorMap& ta, const
     p.tiles_per_unit = (p.n_extent + p.BN - 1) / p.BN;
     const int smem2 = 1024 + stages2 * stage_bytes2 + GEMM_EPI_WARPS * p.epi_bufs * p.epi_buf_bytes + GEMM_BAR_BYTES;
     const int m_pairs = (p.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
-    const int units = m_pairs * p.k_splits;
+    int units = m_pairs * p.k_splits;
+    {  // NT GEMMs: hand out single tiles instead of whole row pairs when that saves >= 4 % of the tile rounds (the row
+       // pairs of a wave share their B tiles either way; NRL_GEMM_FINE=0: always whole row pairs)
+      static const bool fine_on = [] { const char* e = getenv("NRL_GEMM_FINE"); return !(e && e[0] == '0'); }();
+      const int nt = p.tiles_per_unit, cl = g_dev.sm_count / 2;
+      const long long rounds_unit = (long long)((m_pairs + cl - 1) / cl) * nt;
+      const long long rounds_tile = ((long long)m_pairs * nt + cl - 1) / cl;
+      if (fine_on && !p.mn_major && !p.fuse_n && p.k_splits == 1 && nt > 1 && rounds_tile * 100 <= rounds_unit * 96) {
+        p.tiles_per_unit = 1;
+        units = m_pairs * nt;
+      }
+    }
     const int clusters = units < g_dev.sm_count / 2 ? units : g_dev.sm_count / 2;
     nrl_gemm_tc2_kernel<<<2 * clusters, GEMM_THREADS, smem2, c.stream>>>(ta, tb, tout, tsp, p);
     LAUNCH_CHECK(name);

@@ -609,7 +609,11 @@ nrl_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int n_tiles = p.fuse_n ? 1 : (p.n_extent + p.BN - 1) / p.BN;  // passes over K per unit
   const int kb_total = (p.K + GEMM_BK - 1) / GEMM_BK;
   const int kb_per = (kb_total + p.k_splits - 1) / p.k_splits;
-  const int num_units = m_pairs * p.k_splits;  // unit = (k-split, row pair), all its n-tiles
+  // unit = (k-split, row pair) with all its n-tiles, or -- tiles_per_unit == 1, NT GEMMs only -- ONE (row pair, n-tile):
+  // when the row pairs do not fill a whole number of waves (150 pairs on 74 clusters = 3 waves of 12-tile units, the
+  // last with 2 clusters busy) single tiles hand the remainder out evenly (1800 tiles = 25 rounds instead of 36)
+  const bool fine = p.tiles_per_unit == 1 && !p.fuse_n && p.k_splits == 1 && !p.mn_major;
+  const int num_units = fine ? m_pairs * n_tiles : m_pairs * p.k_splits;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -656,8 +660,9 @@ nrl_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
-        for (int j = 0; j < n_tiles; ++j) {
-          const GemmTile t = tile_of(unit, j);
+        const int ub = fine ? unit / n_tiles : unit, j0 = fine ? unit - ub * n_tiles : 0, j1 = fine ? j0 + 1 : n_tiles;
+        for (int j = j0; j < j1; ++j) {
+          const GemmTile t = tile_of(ub, j);
           const int b0 = t.n0 + (int)rank * (t.n_cur / 2);  // my half of the n_cur weight rows / columns
           const int nb = (t.n_cur / 2 + 63) / 64;           // TN: 64-column boxes of my half
           const uint32_t tx = p.mn_major ? (uint32_t)p.planes * (GEMM_A_BYTES + ((uint32_t)nb + nb1) * 8192u) : stage_bytes;
@@ -695,8 +700,9 @@ nrl_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
-        for (int j = 0; j < n_tiles; ++j) {
-          const GemmTile t = tile_of(unit, j);
+        const int ub = fine ? unit / n_tiles : unit, j0 = fine ? unit - ub * n_tiles : 0, j1 = fine ? j0 + 1 : n_tiles;
+        for (int j = j0; j < j1; ++j) {
+          const GemmTile t = tile_of(ub, j);
           const uint32_t idesc = umma_idesc_bf16(2 * GEMM_BM, t.n_cur, p.mn_major, p.mn_major);
           const uint32_t idesc1 = umma_idesc_bf16(2 * GEMM_BM, p.fuse_n ? n1_cur : 16, p.mn_major, p.mn_major);
           mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -759,8 +765,9 @@ nrl_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t acc_phase = 0;
     uint32_t chunk_ctr = 0;
     for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
-      for (int j = 0; j < n_tiles; ++j) {
-        const GemmTile t = tile_of(unit, j);
+      const int ub = fine ? unit / n_tiles : unit, j0 = fine ? unit - ub * n_tiles : 0, j1 = fine ? j0 + 1 : n_tiles;
+      for (int j = j0; j < j1; ++j) {
+        const GemmTile t = tile_of(ub, j);
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
         const uint32_t t_row = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(quarter * 32) << 16);
