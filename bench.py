@@ -503,6 +503,31 @@ def extra_configs(args, dev, rank, world, exchange_mode, steps=15, warmup=3):
             ms = _timed_steps(lambda i: tr.train_step(bs[i % 2]), 5, 2, dev, world)
             r = imps(ms, Bp)
             r["tokens_per_title_padded"] = [int(b["x_hist"]["title"]["input_ids"].shape[1]) for b in bs]
+            if impl == "native" and rank == 0 and world == 1:
+                # live per-launch times of one more step: the transformer's tcgen05 projections against the bf16 peak.
+                # Algorithmic FLOPs per token row and layer: 2 D (3D + D + 2I) forward, the same for the data gradients
+                # (every layer: the embeddings train), again for the weight gradients of the trainable layers 8-11.
+                import ctypes as C
+                from newsreclib_b200 import _lib
+                lib = _lib.load()
+                torch.cuda.synchronize()
+                lib.nrl_profile_start(torch.cuda.current_stream().cuda_stream)
+                tr.train_step(bs[0])
+                torch.cuda.synchronize()
+                names, msbuf = C.create_string_buffer(4000 * 48), (C.c_float * 4000)()
+                n = lib.nrl_profile_stop(names, 48, msbuf, 4000)
+                gemm_ms = sum(msbuf[i] for i in range(n) if names.raw[i * 48:(i + 1) * 48].split(b"\0")[0].startswith(b"tfm gemm"))
+                attn_ms = sum(msbuf[i] for i in range(n) if names.raw[i * 48:(i + 1) * 48].split(b"\0")[0].startswith(b"tfm attn"))
+                rows = sum(int(bs[0][k]["title"]["input_ids"].numel()) for k in ("x_hist", "x_cand"))
+                per_row = 2 * 768 * (3 * 768 + 768 + 2 * 3072)
+                flops = rows * per_row * (12 + 12 + 4)
+                _, _, tf_sust, src = peaks()
+                ach = flops / (gemm_ms / 1e3) / 1e12
+                r["roofline"] = {"bound": "tensor", "kernel": "nrl_gemm_tc_kernel / nrl_gemm_tc2_kernel (the transformer's projections of one step)",
+                                 "achieved": ach, "peak": tf_sust, "unit": "TFLOP/s", "frac": ach / tf_sust,
+                                 "peak_source": f"{src} bf16 dense, sustained", "issued_passes": 1 if precision is not None else 3,
+                                 "algorithmic_gflop_per_step": flops / 1e9, "kernel_ms_per_step": gemm_ms,
+                                 "token_rows": rows, "tfm_attention_ms_per_step": attn_ms}
             del tr, m, plm, bs
             torch.cuda.empty_cache()
             return r

@@ -380,17 +380,20 @@ typedef struct {
 size_t nrl_tfm_wpack_bytes(nrl_tfm_dims dims);
 int nrl_tfm_pack_weights(const nrl_tfm_layer_params* layers, int first, int count, nrl_tfm_dims dims,
                          void* wpack, size_t wpack_bytes, int precision, void* stream);
-/* activations of all layers (kept for the backward pass) + backward scratch */
-size_t nrl_tfm_ws_bytes(long long N, int T, nrl_tfm_dims dims);
+/* keep_activations != 0: activations of all layers (kept for the backward pass) + backward scratch;
+ * keep_activations == 0 (inference, no backward call will follow): one layer's worth, shared by all layers */
+size_t nrl_tfm_ws_bytes(long long N, int T, nrl_tfm_dims dims, int keep_activations);
 /* input_ids / attention_mask: int64 [N, T] (the tokenizer output the reference collate emits,
  * rec_dataset.py:181-183; attention_mask may be NULL = all ones).  out: last hidden state
  * [N, T, D] fp32 (`self.plm_model(**text)[0]`).  training != 0 applies the three dropouts. */
 int nrl_tfm_encoder_fwd(const long long* input_ids, const long long* attention_mask, int N, int T,
                         const nrl_tfm_embed_params* embed, const nrl_tfm_layer_params* layers,
                         nrl_tfm_dims dims, int training, unsigned long long seed, const void* wpack,
-                        float* out, void* ws, size_t ws_bytes, int precision, void* stream);
+                        float* out, int keep_activations, void* ws, size_t ws_bytes, int precision,
+                        void* stream);
 /* d_out [N, T, D] -> parameter gradients (+=).  embed_grads NULL: embeddings frozen.
- * layer_grads[i] all-NULL: layer i frozen.  Same ids / mask / seed / ws as the forward call. */
+ * layer_grads[i] all-NULL: layer i frozen.  Same ids / mask / seed / ws as the forward call, which
+ * must have been made with keep_activations != 0. */
 int nrl_tfm_encoder_bwd(const long long* input_ids, const long long* attention_mask, int N, int T,
                         const nrl_tfm_embed_params* embed, const nrl_tfm_layer_params* layers,
                         nrl_tfm_dims dims, int training, unsigned long long seed, const void* wpack,

@@ -147,8 +147,8 @@ SIGNATURES = {
                                 _I, _F, _I, _ULL, _VP, _VP, _I, _BP, _BP, _VP, _VP, _SZ, _I, _VP]),
     "nrl_tfm_wpack_bytes": (_SZ, [TfmDims]),
     "nrl_tfm_pack_weights": (_I, [_VP, _I, _I, TfmDims, _VP, _SZ, _I, _VP]),
-    "nrl_tfm_ws_bytes": (_SZ, [_LL, _I, TfmDims]),
-    "nrl_tfm_encoder_fwd": (_I, [_VP, _VP, _I, _I, _VP, _VP, TfmDims, _I, _ULL, _VP, _VP, _VP, _SZ, _I, _VP]),
+    "nrl_tfm_ws_bytes": (_SZ, [_LL, _I, TfmDims, _I]),
+    "nrl_tfm_encoder_fwd": (_I, [_VP, _VP, _I, _I, _VP, _VP, TfmDims, _I, _ULL, _VP, _VP, _I, _VP, _SZ, _I, _VP]),
     "nrl_tfm_encoder_bwd": (_I, [_VP, _VP, _I, _I, _VP, _VP, TfmDims, _I, _ULL, _VP, _VP, _VP, _VP, _VP, _SZ, _I, _VP]),
     "nrl_tfm_attn_dropout_mask": (_I, [_VP, _I, _I, _I, _I, _I, _ULL, _F, _VP]),
     "nrl_tfm_hidden_dropout_mask": (_I, [_VP, _LL, _I, _I, _ULL, _F, _VP]),

@@ -70,7 +70,10 @@ struct TfmWs {
   bf16 *dtp, *dup, *dqkv;     // backward GEMM operands
   std::vector<TfmLayerWs> layer;
 };
-static void carve_tfm(Bump& b, long long N, int T, const TfmDims& d, TfmWs& w) {
+// keep == false (inference: no backward pass will follow): every layer works in the SAME activation buffers -- each
+// is produced and consumed inside its layer, and LayerNorm 2 writes the next layer's input planes when the current
+// layer's are no longer read -- so the workspace does not grow with the number of layers
+static void carve_tfm(Bump& b, long long N, int T, const TfmDims& d, TfmWs& w, bool keep = true) {
   const long long R = N * T;
   w.pos = b.take<int>((size_t)R);
   w.kmask = b.take<unsigned char>((size_t)R);
@@ -90,6 +93,7 @@ static void carve_tfm(Bump& b, long long N, int T, const TfmDims& d, TfmWs& w) {
   w.layer.resize(d.L);
   for (int l = 0; l < d.L; ++l) {
     TfmLayerWs& y = w.layer[l];
+    if (!keep && l > 0) { y = w.layer[0]; continue; }
     y.xp = b.take<bf16>(2ull * R * d.Dp);
     y.qkv = b.take<float>((size_t)R * d.LDQ);
     y.lse = b.take<float>((size_t)R * d.H);
@@ -233,12 +237,12 @@ int nrl_tfm_pack_weights(const nrl_tfm_layer_params* layers, int first, int coun
   return NRL_OK;
 }
 
-size_t nrl_tfm_ws_bytes(long long N, int T, nrl_tfm_dims dims) {
+size_t nrl_tfm_ws_bytes(long long N, int T, nrl_tfm_dims dims, int keep_activations) {
   TfmDims d;
   if (make_tfm_dims(dims, d) != NRL_OK || N <= 0 || T <= 0) return 0;
   Bump b(nullptr);
   TfmWs w;
-  carve_tfm(b, N, T, d, w);
+  carve_tfm(b, N, T, d, w, keep_activations != 0);
   return b.off + 1024;
 }
 
@@ -252,8 +256,8 @@ static int tfm_dropout_words(const Ctx& c, const TfmDims& d, long long R, const 
 
 int nrl_tfm_encoder_fwd(const long long* input_ids, const long long* attention_mask, int N, int T,
                         const nrl_tfm_embed_params* embed, const nrl_tfm_layer_params* layers, nrl_tfm_dims dims,
-                        int training, unsigned long long seed, const void* wpack, float* out, void* ws,
-                        size_t ws_bytes, int precision, void* stream) {
+                        int training, unsigned long long seed, const void* wpack, float* out, int keep_activations,
+                        void* ws, size_t ws_bytes, int precision, void* stream) {
   TfmDims d;
   TRY(make_tfm_dims(dims, d));
   TRY(tfm_check("nrl_tfm_encoder_fwd", N, T, d));
@@ -261,13 +265,13 @@ int nrl_tfm_encoder_fwd(const long long* input_ids, const long long* attention_m
     return fail(NRL_ERR_INVALID_ARG, "nrl_tfm_encoder_fwd: null pointer");
   TRY(device_init());
   TRY(tfm_attn_attrs_init());
-  TRY(check_common(ws, ws_bytes, nrl_tfm_ws_bytes(N, T, dims)));
+  TRY(check_common(ws, ws_bytes, nrl_tfm_ws_bytes(N, T, dims, keep_activations)));
   if (reinterpret_cast<uintptr_t>(wpack) & 1023) return fail(NRL_ERR_INVALID_ARG, "wpack must be 1024-byte aligned");
   Ctx c{static_cast<cudaStream_t>(stream), precision};
   const long long R = (long long)N * T;
   Bump b(ws);
   TfmWs w;
-  carve_tfm(b, N, T, d, w);
+  carve_tfm(b, N, T, d, w, keep_activations != 0);
   Bump bp(const_cast<void*>(wpack));
   const DropCfg hdrop = make_drop(d.pdrop, training, seed), adrop = make_drop(d.padrop, training, seed);
   const bool two = c.two_planes();
@@ -349,7 +353,7 @@ int nrl_tfm_encoder_bwd(const long long* input_ids, const long long* attention_m
     return fail(NRL_ERR_INVALID_ARG, "nrl_tfm_encoder_bwd: null pointer");
   TRY(device_init());
   TRY(tfm_attn_attrs_init());
-  TRY(check_common(ws, ws_bytes, nrl_tfm_ws_bytes(N, T, dims)));
+  TRY(check_common(ws, ws_bytes, nrl_tfm_ws_bytes(N, T, dims, 1)));
   Ctx c{static_cast<cudaStream_t>(stream), precision};
   const long long R = (long long)N * T;
   Bump b(ws);

@@ -653,15 +653,19 @@ class TfmEncoderFn(torch.autograd.Function):
             raise RuntimeError(f"TfmEncoderFn: expected {5 + 16 * L} parameter tensors, got {len(params)}")
         params = [_chk(t.contiguous(), torch.float32, "transformer parameter") for t in params]
         wpack = state.pack([params[5 + 16 * l: 21 + 16 * l] for l in range(L)], precision)
-        need = lib.nrl_tfm_ws_bytes(N, T, dims)
+        # no gradient will be asked for (torch.no_grad(), or nothing trainable): the layers share one set of activations
+        keep = int(any(ctx.needs_input_grad[6:]))
+        need = lib.nrl_tfm_ws_bytes(N, T, dims, keep)
         if need == 0:
             raise RuntimeError("nrl_tfm: unsupported transformer dims")
         ws = workspace(need, ids.device)
         out = torch.empty(N, T, dims.hidden, dtype=torch.float32, device=ids.device)
         emb, layers = _tfm_structs(params, L)
         _lib.check(lib.nrl_tfm_encoder_fwd(_p(ids), _p(mask), N, T, C.byref(emb), layers, dims, int(training), int(seed),
-                                           _p(wpack), _p(out), _p(ws), ws.numel(), precision, _stream()),
+                                           _p(wpack), _p(out), keep, _p(ws), ws.numel(), precision, _stream()),
                    "nrl_tfm_encoder_fwd")
+        if not keep:
+            return out
         ctx.save_for_backward(ids, *params)
         ctx.mask, ctx.ws, ctx.wpack, ctx.state = mask, ws, wpack, state
         ctx.cfg = (N, T, int(training), int(seed), precision)

@@ -133,6 +133,26 @@ def test_tfm_long_texts_flash_attention(N, T, train):
     assert e <= FWD_TOL and max(errs.values()) <= GRAD_TOL
 
 
+def test_tfm_inference_shares_one_layer_of_activations():
+    """torch.no_grad(): the layers reuse ONE set of activation buffers (the workspace no longer grows with the depth);
+    the hidden states are bit-identical to those of the gradient-enabled call."""
+    from newsreclib_b200 import _lib, ops
+    from tfm_helpers import param_list
+    cfg = dict(hidden=128, heads=2, inter=256, layers=4, vocab=60, max_pos=40, eps=1e-5)
+    P = random_tfm_params(128, 2, 256, 4, 60, 40, seed=2)
+    ids, att = random_text(11, 33, 60, seed=2)
+    st = ops.TfmState(128, 2, 256, 4, 60, 40, 1, 1e-5, 0.0, 0.0)
+    leaves, _ = param_list(P, 4, "cuda")
+    a = ops.TfmEncoderFn.apply(ids.cuda(), att.cuda(), st, False, 0, ops.PREC_BF16X3, *leaves)
+    with torch.no_grad():
+        b = ops.TfmEncoderFn.apply(ids.cuda(), att.cuda(), st, False, 0, ops.PREC_BF16X3, *leaves)
+    assert a.requires_grad and not b.requires_grad and torch.equal(a.detach(), b)
+    lib = _lib.load()
+    keep, share = lib.nrl_tfm_ws_bytes(11, 33, st.dims, 1), lib.nrl_tfm_ws_bytes(11, 33, st.dims, 0)
+    one = lib.nrl_tfm_ws_bytes(11, 33, ops.TfmState(128, 2, 256, 1, 60, 40, 1, 1e-5, 0.0, 0.0).dims, 1)
+    assert share == one < keep
+
+
 def test_tfm_bf16_single_pass():
     """NRL_PREC_BF16 (one bf16 plane, one MMA per product): the bf16 configuration's bar is 2e-2."""
     from newsreclib_b200 import ops
