@@ -1,10 +1,4 @@
 mkdir -p gpurun_out
-timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 50 --warmup 5 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; tail -3 gpurun_out/bench_n2.err
-python - <<'PY'
-import json
-j=json.loads(open("gpurun_out/bench_n2.json").read().strip().splitlines()[-1])
-print(j["n_gpus"], j["ms_per_step"], j["value"], j["impl_detail"], j.get("exchange"))
-for k,v in j["configs"].items(): print(k, v.get("ms_per_step"), v.get("value"), v.get("error"))
-print(json.dumps(j["configs"]["nrms_plm_roberta_base"].get("roofline")))
-PY
-timeout 600 python -m pytest tests/test_gpu_peer_exchange.py -m gpu -q --timeout 500 2>&1 | tail -3
+timeout 900 python -m pytest tests/test_gpu_tfm.py tests/test_gpu_naml.py -m gpu -q --timeout 600 -s -k "module" 2>&1 | grep "tfm\]\|passed\|failed\|Error" | cut -c1-300
+timeout 600 python experiments/plm_profile.py 40 > gpurun_out/plm_profile_40.txt 2>&1; cat gpurun_out/plm_profile_40.txt | head -24
+timeout 600 python experiments/plm_profile.py 96 > gpurun_out/plm_profile_96.txt 2>&1; cat gpurun_out/plm_profile_96.txt | head -4

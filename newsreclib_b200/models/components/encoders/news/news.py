@@ -59,6 +59,23 @@ class NewsEncoder(nn.Module):
             vectors += [enc(news[name]) for name, enc in self.text_encoders.items()]
         if self.encode_category:
             vectors += [enc(news[name]) for name, enc in self.category_encoders.items()]
+        return self._combine(vectors)
+
+    def forward_pair(self, news_a: Dict[str, torch.Tensor], news_b: Dict[str, torch.Tensor]):
+        """``(self(news_a), self(news_b))``; text encoders that can share work between the two calls (the PLM: one pass
+        through the transformer, ``PLM.forward_pair``) do so, everything else is called twice."""
+        va, vb = [], []
+        if self.encode_text:
+            for name, enc in self.text_encoders.items():
+                a, b = enc.forward_pair(news_a[name], news_b[name]) if hasattr(enc, "forward_pair") else \
+                    (enc(news_a[name]), enc(news_b[name]))
+                va.append(a); vb.append(b)
+        if self.encode_category:
+            for name, enc in self.category_encoders.items():
+                va.append(enc(news_a[name])); vb.append(enc(news_b[name]))
+        return self._combine(va), self._combine(vb)
+
+    def _combine(self, vectors) -> torch.Tensor:
         if len(vectors) == 1:
             return vectors[0]
         if self.combine_type == "add_att":

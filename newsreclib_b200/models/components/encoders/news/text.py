@@ -175,6 +175,33 @@ class PLM(nn.Module):
         return ops.TfmEncoderFn.apply(ids, text.get("attention_mask"), self._tfm_state, training, seed, self.precision,
                                       *self.transformer_parameters())
 
+    def forward_pair(self, text_a, text_b):
+        """``(self(text_a), self(text_b))`` with ONE pass through the transformer: the hidden state of a token does not
+        depend on how much padding follows it (padding is masked out of every softmax and keeps position id
+        ``pad_token_id``), so the two calls of a training step (clicked history, candidates: ``nrms_module.py:231,235``)
+        run as one batch padded to the longer of the two, and each part is cut back to ITS OWN padded length before
+        the head -- which, as in the reference, does look at the padding positions and across the news of its call."""
+        if self.transformer_impl != "native" or not self.use_mhsa:
+            return self(text_a), self(text_b)
+        ia, ib = text_a["input_ids"], text_b["input_ids"]
+        ma, mb = text_a.get("attention_mask"), text_b.get("attention_mask")
+        ma = torch.ones_like(ia) if ma is None else ma
+        mb = torch.ones_like(ib) if mb is None else mb
+        Ta, Tb = ia.shape[1], ib.shape[1]
+        T = max(Ta, Tb)
+        pad = int(self.plm_model.config.pad_token_id)
+
+        def widen(ids, mask):
+            if ids.shape[1] == T:
+                return ids, mask
+            extra = T - ids.shape[1]
+            return (torch.nn.functional.pad(ids, (0, extra), value=pad), torch.nn.functional.pad(mask, (0, extra), value=0))
+        ia2, ma2 = widen(ia, ma)
+        ib2, mb2 = widen(ib, mb)
+        states = self.transformer({"input_ids": torch.cat([ia2, ib2], 0), "attention_mask": torch.cat([ma2, mb2], 0)})
+        na = ia.shape[0]
+        return self.head(states[:na, :Ta].contiguous()), self.head(states[na:, :Tb].contiguous())
+
     def head(self, states: torch.Tensor) -> torch.Tensor:
         """``[N, T, E]`` last hidden states -> ``[N, E]`` on the sm_100a path."""
         mha, add = self.multihead_attention, self.additive_attention

@@ -33,6 +33,8 @@ class TwoTowerRecommender(AbstractRecommneder):
         if not (self.merge_news_calls and self._per_news_encoder and keys and all(
                 torch.is_tensor(x_hist.get(k)) and torch.is_tensor(x_cand.get(k)) and x_hist[k].shape[1:] == x_cand[k].shape[1:]
                 for k in keys)):
+            if hasattr(enc, "forward_pair") and self.merge_news_calls:
+                return enc.forward_pair(x_hist, x_cand)  # PLM: one pass through the transformer, two through the head
             return enc(x_hist), enc(x_cand)
         n_hist = x_hist[keys[0]].shape[0]
         vec = enc({k: torch.cat([x_hist[k], x_cand[k]], dim=0) for k in keys})

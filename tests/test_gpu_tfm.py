@@ -240,3 +240,60 @@ def test_plm_module_native_transformer_vs_hf():
     # the fp32 reference's own error on them is ~1e-3), everything else is held to 2e-3 between the two implementations
     for v, k in sorted(((v, k) for k, v in errs.items()), reverse=True):
         assert v <= (6e-3 if k.endswith("additive_attention.linear.bias") else 2e-3), (k, v)
+
+
+def test_naml_plm_module_native_transformer_vs_hf():
+    """NAMLModule(use_plm=True): title (12 tokens) AND abstract (150 tokens: the flash attention path) through the one
+    shared PLM + category view, native transformer against the HF torch module on the same weights."""
+    from transformers import RobertaConfig, RobertaModel
+    from newsreclib_b200.models.general_rec.naml_module import NAMLModule
+    hidden, B = 128, 3
+    outputs = {"train": ["preds", "targets", "cand_news_size"], "val": ["preds", "targets", "cand_news_size"],
+               "test": ["preds", "targets", "cand_news_size"]}
+    cfg = RobertaConfig(vocab_size=120, hidden_size=hidden, num_hidden_layers=2, num_attention_heads=2,
+                        intermediate_size=256, max_position_embeddings=160, pad_token_id=1, type_vocab_size=1)
+
+    def build(impl):
+        torch.manual_seed(0)
+        tf = RobertaModel(cfg)
+        with torch.no_grad():
+            for p in tf.parameters():
+                p.mul_(3.0) if p.dim() > 1 else p.add_(0.05 * torch.randn_like(p))
+        m = NAMLModule(
+            dataset_attributes=["title", "abstract", "category", "subcategory"],
+            attributes2encode=["title", "abstract", "category"], outputs=outputs, dual_loss_training=False,
+            dual_loss_coef=None, loss="cross_entropy_loss", late_fusion=False, temperature=None, use_plm=True,
+            pretrained_embeddings_path=None, plm_model=tf, frozen_layers=[0], text_embed_dim=hidden, num_heads=2,
+            num_filters=None, window_size=None, query_dim=40, categ_embed_dim=20, dropout_probability=0.2,
+            top_k_list=[5], num_categ_classes=18, num_sent_classes=3, save_recs=False, recs_fpath=None, optimizer=None,
+            scheduler=None, transformer_impl=impl)
+        return m.cuda().eval()
+    hcnt, ccnt = [3, 4, 2], [5, 5, 5]
+    g = torch.Generator().manual_seed(1)
+
+    def text(n, T):
+        lens = torch.randint(4, T + 1, (n,), generator=g); lens[0] = T
+        att = (torch.arange(T)[None, :] < lens[:, None]).long()
+        ids = torch.where(att.bool(), torch.randint(3, 120, (n, T), generator=g), torch.ones(n, T, dtype=torch.long))
+        return {"input_ids": ids.cuda(), "attention_mask": att.cuda()}
+
+    def news(n):
+        return {"title": text(n, 12), "abstract": text(n, 150), "category": torch.randint(1, 19, (n,), generator=g).cuda()}
+    batch = {"x_hist": news(sum(hcnt)), "x_cand": news(sum(ccnt)),
+             "batch_hist": torch.repeat_interleave(torch.arange(B), torch.tensor(hcnt)).cuda(),
+             "batch_cand": torch.repeat_interleave(torch.arange(B), torch.tensor(ccnt)).cuda(),
+             "labels": torch.tensor([1., 0, 0, 0, 0] * B).cuda(), "user_idx": torch.arange(B).cuda()}
+    res = {}
+    for impl in ("native", "hf"):
+        m = build(impl)
+        loss = m.model_step(batch)[0]
+        loss.backward()
+        res[impl] = (m(batch).detach(), loss.detach(), {n: p.grad.detach().cpu() for n, p in m.named_parameters()
+                                                        if p.grad is not None})
+    assert rel_err(res["native"][0], res["hf"][0]) <= 2e-4 and rel_err(res["native"][1], res["hf"][1]) <= 2e-4
+    assert set(res["native"][2]) == set(res["hf"][2])
+    errs = grad_errors(res["native"][2], res["hf"][2])
+    print(f"[tfm] NAML-PLM module, native vs HF: scores {rel_err(res['native'][0], res['hf'][0]):.2e}, largest gradient "
+          f"differences {sorted(((round(v, 5), k) for k, v in errs.items()), reverse=True)[:3]}")
+    for k, v in errs.items():
+        assert v <= (6e-3 if k.endswith("additive_attention.linear.bias") else 2e-3), (k, v)
