@@ -25,33 +25,51 @@ struct TfmPackJob {
 struct TfmPackJobs {
   TfmPackJob j[6];
 };
-__global__ void tfm_pack_kernel(const TfmPackJobs jobs, int two_planes) {
+// blockIdx.y = job, blockIdx.z = 0: forward operand (coalesced both ways), 1: transposed operand through a 32 x 33
+// shared-memory tile (W is read along k, wt is written along n: both coalesced)
+__global__ void __launch_bounds__(256) tfm_pack_kernel(const TfmPackJobs jobs, int two_planes) {
   const TfmPackJob& q = jobs.j[blockIdx.y];
   if (!q.W) return;
-  const long long nf = (long long)q.n_out * q.kp;
+  const long long plane_f = (long long)q.n_total * q.kp, plane_t = (long long)q.k_in * q.np;
+  if (blockIdx.z == 0) {  // one output row per CTA pass: no per-element index divisions
+    for (int n = blockIdx.x; n < q.n_out; n += gridDim.x) {
+      const float* src = q.W + (long long)n * q.k_in;
+      const long long row = (long long)(q.n_off + n) * q.kp;
+      for (int k = threadIdx.x; k < q.kp; k += blockDim.x) {
+        const float x = k < q.k_in ? src[k] : (k == q.k_in && q.bias ? q.bias[n] : 0.f);
+        __nv_bfloat16 h, l;
+        split_bf16(x, h, l);
+        q.wf[row + k] = h;
+        if (two_planes) q.wf[plane_f + row + k] = l;
+      }
+    }
+    return;
+  }
+  __shared__ float tile[32][33];
   const bool last = q.n_off + q.n_out == q.n_total;
   const int tcols = last ? q.np - q.n_off : q.n_out;  // the last job also zeroes the pad columns of wt
-  const long long nt = (long long)q.k_in * tcols;
-  const long long plane_f = (long long)q.n_total * q.kp, plane_t = (long long)q.k_in * q.np;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nf + nt;
-       i += (long long)gridDim.x * blockDim.x) {
-    float x;
-    __nv_bfloat16* dst;
-    long long plane, off;
-    if (i < nf) {
-      const int n = (int)(i / q.kp), k = (int)(i % q.kp);
-      x = k < q.k_in ? q.W[(long long)n * q.k_in + k] : (k == q.k_in && q.bias ? q.bias[n] : 0.f);
-      dst = q.wf; plane = plane_f; off = (long long)(q.n_off + n) * q.kp + k;
-    } else {
-      const long long j = i - nf;
-      const int k = (int)(j / tcols), n = (int)(j % tcols);
-      x = n < q.n_out ? q.W[(long long)n * q.k_in + k] : 0.f;
-      dst = q.wt; plane = plane_t; off = (long long)k * q.np + q.n_off + n;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int kt = (q.k_in + 31) / 32, nt = (tcols + 31) / 32;
+  for (int t = blockIdx.x; t < kt * nt; t += gridDim.x) {
+    const int k0 = (t % kt) * 32, n0 = (t / kt) * 32;
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+      const int n = n0 + r, k = k0 + tx;
+      tile[r][tx] = (n < q.n_out && k < q.k_in) ? q.W[(long long)n * q.k_in + k] : 0.f;
     }
-    __nv_bfloat16 h, l;
-    split_bf16(x, h, l);
-    dst[off] = h;
-    if (two_planes) dst[plane + off] = l;
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+      const int k = k0 + r, n = n0 + tx;
+      if (k < q.k_in && n < tcols) {
+        __nv_bfloat16 h, l;
+        split_bf16(tile[tx][r], h, l);
+        const long long off = (long long)k * q.np + q.n_off + n;
+        q.wt[off] = h;
+        if (two_planes) q.wt[plane_t + off] = l;
+      }
+    }
   }
 }
 

@@ -230,7 +230,7 @@ int nrl_tfm_pack_weights(const nrl_tfm_layer_params* layers, int first, int coun
     jobs.j[5] = TfmPackJob{p.o_w, p.o_b, d.D, d.I, d.Ip, d.D, 0, d.D, w.wo_f, w.wo_t};
     for (int j = 0; j < 6; ++j)
       if (!jobs.j[j].W) return fail(NRL_ERR_INVALID_ARG, "nrl_tfm_pack_weights: NULL weight in layer %d", l);
-    tfm_pack_kernel<<<dim3((unsigned)grid_for((long long)d.I * (d.Dp + d.D), 256, 2048), 6), 256, 0, c.stream>>>(
+    tfm_pack_kernel<<<dim3((unsigned)grid_for((long long)d.I * d.Dp, 256 * 8, 1024), 6, 2), 256, 0, c.stream>>>(
         jobs, c.two_planes() ? 1 : 0);
     LAUNCH_CHECK("tfm pack_weights");
   }
