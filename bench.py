@@ -272,12 +272,13 @@ def main_naml(args, rank, local_rank, world):
     tr = ModuleTrainer(m, lr=1e-4)
 
     def to_dev(hb):
-        return {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else {kk: vv.to(dev, non_blocking=True) for kk, vv in v.items()})
+        return {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else
+                    {kk: vv.to(dev, non_blocking=True) for kk, vv in v.items()} if isinstance(v, dict) else v)
                 for k, v in hb.items()}
     host = [make_batch(B, VOCAB, hist="fixed", max_hist=HIST, cand="train", seed=1234 + rank * 100 + i, max_title_len=L,
                        abstract_len=LA) for i in range(4)]
-    host = [{k: (v.pin_memory() if torch.is_tensor(v) else {kk: vv.pin_memory() for kk, vv in v.items()}) for k, v in hb.items()}
-            for hb in host]
+    host = [{k: (v.pin_memory() if torch.is_tensor(v) else {kk: vv.pin_memory() for kk, vv in v.items()} if isinstance(v, dict) else v)
+             for k, v in hb.items()} for hb in host]
     devb = [to_dev(hb) for hb in host]
 
     def timed(fn, steps):
@@ -346,7 +347,8 @@ def _timed_steps(fn, steps, warmup, dev, world):
 
 
 def _dev_batch(hb, dev):
-    return {k: (v.to(dev) if torch.is_tensor(v) else {kk: vv.to(dev) for kk, vv in v.items()}) for k, v in hb.items()}
+    return {k: (v.to(dev) if torch.is_tensor(v) else {kk: vv.to(dev) for kk, vv in v.items()} if isinstance(v, dict) else v)
+            for k, v in hb.items()}
 
 
 def _module_kwargs(outputs):

@@ -5,7 +5,7 @@ from typing import Any, Dict, TypedDict
 import torch
 
 
-class RecommendationBatch(TypedDict):
+class RecommendationBatch(TypedDict, total=False):
     """Ragged PyG-style recommendation batch.
 
     batch_hist / batch_cand: sorted int64 segment ids (impression index of every history /
@@ -20,6 +20,8 @@ class RecommendationBatch(TypedDict):
     labels: torch.Tensor
     user_ids: torch.Tensor
     user_idx: torch.Tensor
+    # optional, not in the reference: (Hmax, Cmax) as host integers when the collate knows them (DeviceCollate)
+    dense_widths: tuple
 
 
 class NewsBatch(TypedDict):

@@ -90,7 +90,10 @@ class DeviceCollate:
         batch_cand = torch.from_numpy(np.repeat(np.arange(len(batch), dtype=np.int64), sizes_c)).to(dev)
         x_hist = self.table.gather(torch.from_numpy(hist_rows).to(dev))
         x_cand = self.table.gather(torch.from_numpy(cand_rows).to(dev))
+        # dense_widths: (Hmax, Cmax), known here on the host -- the modules then need no device sync to size the dense
+        # history / candidate tensors (the reference's to_dense_batch reads them back from the device)
         return RecommendationBatch(
+            dense_widths=(int(sizes_h.max()), int(sizes_c.max())),
             batch_hist=batch_hist, batch_cand=batch_cand, x_hist=x_hist, x_cand=x_cand,
             labels=torch.from_numpy(np.concatenate([np.asarray(l) for l in labels])).float().to(dev),
             user_ids=torch.from_numpy(np.concatenate([np.atleast_1d(u) for u in user_ids])).long().to(dev),

@@ -43,12 +43,16 @@ class TwoTowerRecommender(AbstractRecommneder):
     # ------------------------------------------------------------------ layout helpers
     @staticmethod
     def _layout(batch: RecommendationBatch):
-        """Offsets and dense widths of the ragged batch.  One host sync for (B, Hmax, Cmax), the
-        same information ``to_dense_batch`` fetches with ``batch.max()`` / ``num.max()``."""
+        """Offsets and dense widths of the ragged batch.  (B, Hmax, Cmax) are host integers: ``to_dense_batch`` fetches
+        them with a device sync (``batch.max()`` / ``num.max()``); a collate that already knows them on the host --
+        ``DeviceCollate``, the synthetic generator -- passes them as ``batch["dense_widths"] = (Hmax, Cmax)`` and the
+        step then has no sync at all, so the host keeps running ahead of the GPU."""
         seg_h, seg_c = batch["batch_hist"], batch["batch_cand"]
         B = int(batch["user_idx"].numel()) if "user_idx" in batch else int(seg_c[-1]) + 1
         off_h, off_c = ops.segment_offsets(seg_h, B), ops.segment_offsets(seg_c, B)
-        widths = torch.stack([(off_h[1:] - off_h[:-1]).max(), (off_c[1:] - off_c[:-1]).max()]).tolist()
+        widths = batch.get("dense_widths")
+        if widths is None:
+            widths = torch.stack([(off_h[1:] - off_h[:-1]).max(), (off_c[1:] - off_c[:-1]).max()]).tolist()
         return B, off_h, off_c, int(widths[0]), int(widths[1])
 
     # ------------------------------------------------------------------ forward (nrms_module.py:230-255)

@@ -80,6 +80,8 @@ def make_batch(
         "labels": torch.from_numpy(labels),
         "user_ids": torch.from_numpy(rng.integers(1, 10**6, batch_size).astype(np.int64)),
         "user_idx": torch.arange(batch_size, dtype=torch.int64),
+        # host-known dense widths (Hmax, Cmax): lets the drop-in modules skip the device sync of to_dense_batch
+        "dense_widths": (int(h.max()), int(c.max())),
     }
 
 

@@ -116,7 +116,7 @@ def _eval_batch_with_long_impression(B, V, cmax, seed):
     extra = cmax - int(cnt[-1])
     assert extra > 0
     rng = np.random.default_rng(seed + 1)
-    out = {k: (dict(v) if isinstance(v, dict) else v) for k, v in batch.items()}
+    out = {k: (dict(v) if isinstance(v, dict) else v) for k, v in batch.items() if k != "dense_widths"}  # widths change below
     out["x_cand"] = {"title": torch.cat([batch["x_cand"]["title"], torch.from_numpy(make_titles(rng, extra, V))])}
     out["x_hist"] = {"title": batch["x_hist"]["title"]}
     out["labels"] = torch.cat([batch["labels"], torch.zeros(extra)])

@@ -206,7 +206,8 @@ def make_naml_module(params, d, late_fusion=False, p=0.2):
 
 
 def naml_dev_batch(batch, dev="cuda"):
-    b = {k: (v.to(dev) if torch.is_tensor(v) else {kk: vv.to(dev) for kk, vv in v.items()}) for k, v in batch.items()}
+    b = {k: (v.to(dev) if torch.is_tensor(v) else {kk: vv.to(dev) for kk, vv in v.items()} if isinstance(v, dict) else v)
+         for k, v in batch.items()}
     return b
 
 
