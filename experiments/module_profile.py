@@ -20,15 +20,35 @@ def main():
     lib = _lib.load()
     outputs = {"train": ["preds", "targets", "cand_news_size"], "val": ["preds", "targets", "cand_news_size"],
                "test": ["preds", "targets", "cand_news_size"]}
-    params = make_nrms_params(VOCAB, E, H, Q, seed=1234)
-    m = NRMSModule(dataset_attributes=["title", "category"], attributes2encode=["title"], use_plm=False,
-                   pretrained_embeddings_path=None, plm_model=None, frozen_layers=None, embed_dim=E, num_heads=H,
-                   query_dim=Q, pretrained_embeddings=params["news_encoder.text_encoders.title.embedding_layer.weight"],
-                   **_module_kwargs(outputs))
-    m.load_state_dict({k: v for k, v in params.items() if k in m.state_dict()})
+    naml = len(sys.argv) > 1 and sys.argv[1] == "naml"
+    if naml:
+        from newsreclib_b200.models.general_rec.naml_module import NAMLModule
+        from newsreclib_b200.synthetic import make_naml_params
+        V, F_, W, CE, LA = 130000, 400, 3, 100, 50
+        params = make_naml_params(V, E, F_, W, Q, CE, 19, seed=1234)
+        m = NAMLModule(dataset_attributes=["title", "abstract", "category", "subcategory"],
+                       attributes2encode=["title", "abstract", "category"], use_plm=False, pretrained_embeddings_path=None,
+                       plm_model=None, frozen_layers=None, text_embed_dim=E, num_heads=H, num_filters=F_, window_size=W,
+                       query_dim=Q, categ_embed_dim=CE,
+                       pretrained_embeddings=params["news_encoder.text_encoders.title.embedding_layer.weight"],
+                       **_module_kwargs(outputs))
+        full = dict(params)
+        for k in list(params):
+            if ".text_encoders.title." in k:
+                full[k.replace(".title.", ".abstract.")] = params[k]
+        m.load_state_dict(full)
+        bs = [_dev_batch(make_batch(64, V, hist="fixed", max_hist=HIST, cand="train", seed=700 + i, max_title_len=L,
+                                    abstract_len=LA), dev) for i in range(4)]
+    else:
+        params = make_nrms_params(VOCAB, E, H, Q, seed=1234)
+        m = NRMSModule(dataset_attributes=["title", "category"], attributes2encode=["title"], use_plm=False,
+                       pretrained_embeddings_path=None, plm_model=None, frozen_layers=None, embed_dim=E, num_heads=H,
+                       query_dim=Q, pretrained_embeddings=params["news_encoder.text_encoders.title.embedding_layer.weight"],
+                       **_module_kwargs(outputs))
+        m.load_state_dict({k: v for k, v in params.items() if k in m.state_dict()})
+        bs = [_dev_batch(make_batch(64, VOCAB, hist="fixed", max_hist=HIST, cand="train", seed=900 + i, max_title_len=L), dev)
+              for i in range(4)]
     tr = ModuleTrainer(m.to(dev).train(), lr=1e-4, exchange="nccl")
-    bs = [_dev_batch(make_batch(64, VOCAB, hist="fixed", max_hist=HIST, cand="train", seed=900 + i, max_title_len=L), dev)
-          for i in range(4)]
     for i in range(5):
         tr.train_step(bs[i % 4])
     torch.cuda.synchronize()

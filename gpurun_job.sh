@@ -1,4 +1,10 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q --timeout 900 2>&1 | tail -3
-timeout 600 python experiments/module_profile.py > gpurun_out/module_profile.txt 2>&1; cat gpurun_out/module_profile.txt | head -12
-timeout 600 python experiments/plm_profile.py 40 2>&1 | grep "wall\|pack_weights\|ce_bwd"
+timeout 600 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --no-extras > gpurun_out/bench_q.json 2> gpurun_out/bench_q.err; tail -2 gpurun_out/bench_q.err
+python - <<'PY'
+import json
+j=json.loads(open("gpurun_out/bench_q.json").read())
+print(j["ms_per_step"], j["value"], j["e2e"]["value"])
+print([ (k["kernel"], k["ms_per_step"], round(k["frac_of_hbm_peak"],3)) for k in j["hbm_kernels"]])
+PY
+timeout 600 python experiments/module_profile.py naml 2>&1 | head -5
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fullsize.py tests/test_gpu_naml.py -m gpu -q --timeout 900 -x 2>&1 | tail -2

@@ -1199,9 +1199,17 @@ pool_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ Y,
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   // this thread owns columns j = tid, tid + blockDim, ... of the [*, qp] tanh matrix
   float dq_acc[2] = {0.f, 0.f}, db_acc[2] = {0.f, 0.f};  // qp <= 2 * blockDim (Q <= 256... host checks)
+  // 16-byte path: rows of Y / dOut / A and the plane rows start on 16 / 8-byte boundaries
+  const bool vec = !(E & 3) && !(Q & 3) && !(qp & 3) && !dY1 &&
+                   !((reinterpret_cast<uintptr_t>(Y) | reinterpret_cast<uintptr_t>(d_out) | reinterpret_cast<uintptr_t>(A) |
+                      reinterpret_cast<uintptr_t>(qvec)) & 15) &&
+                   !((reinterpret_cast<uintptr_t>(da_hi) | reinterpret_cast<uintptr_t>(da_lo)) & 7);
+  const int chunks = qp / 4, rgs = vec ? max(1, (int)blockDim.x / chunks) : 1;
+  float vq[4] = {0.f, 0.f, 0.f, 0.f}, vb[4] = {0.f, 0.f, 0.f, 0.f};
   for (long long g = blockIdx.x; g < G; g += gridDim.x) {
     const long long r0 = g * L;
-    // dw_t = dOut . Y_t  (one warp per row, coalesced over E; four rows in flight per warp)
+    // dw_t = dOut . Y_t  (one warp per row, coalesced over E; four rows in flight per warp; 16-byte loads when the
+    // rows allow it: a quarter of the load instructions -- the kernel was issue-bound on 4-byte accesses)
     for (int t = warp; t < L; t += 4 * nw) {
       const float* yr[4];
       bool ok[4];
@@ -1211,11 +1219,22 @@ pool_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ Y,
         yr[u] = Y + (r0 + (ok[u] ? t + u * nw : t)) * E;
       }
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 2
-      for (int c = lane; c < E; c += 32) {
-        const float dv = __ldg(d_out + g * E + c);
+      if (vec) {
+        for (int c = lane; c < E / 4; c += 32) {
+          const float4 dv = __ldg(reinterpret_cast<const float4*>(d_out + g * E) + c);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) acc[u] += dv * __ldg(yr[u] + c);
+          for (int u = 0; u < 4; ++u) {
+            const float4 y4 = __ldg(reinterpret_cast<const float4*>(yr[u]) + c);
+            acc[u] += (dv.x * y4.x + dv.y * y4.y) + (dv.z * y4.z + dv.w * y4.w);
+          }
+        }
+      } else {
+#pragma unroll 2
+        for (int c = lane; c < E; c += 32) {
+          const float dv = __ldg(d_out + g * E + c);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc[u] += dv * __ldg(yr[u] + c);
+        }
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -1234,39 +1253,97 @@ pool_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ Y,
         for (int c = threadIdx.x; c < E; c += blockDim.x)
           dY1[(r0 + t) * E + c] = w[r0 + t] * d_out[g * E + c];
     }
-    // single pass over A: dApre (split planes), and the dq / db partial sums of this thread's columns;
-    // rows are walked ten at a time so that ten independent loads are in flight per thread
-    int slot = 0;
-    for (int j = threadIdx.x; j < qp; j += blockDim.x, ++slot) {
-      const bool in = j < Q;
-      const float qj = in ? qvec[j] : 0.f;
-      float aq = 0.f, ab = 0.f;
-      for (int t0 = 0; t0 < L; t0 += 10) {
-        float a[10];
+    // single pass over A: dApre (split planes), and the dq / db partial sums of this thread's columns
+    if (vec) {
+      // thread = (4-column chunk, row group): 16-byte loads of A, 8-byte plane stores, four rows in flight
+      if ((int)threadIdx.x < rgs * chunks) {
+        const int ch = threadIdx.x % chunks, rg = threadIdx.x / chunks, j0 = 4 * ch;
+        const bool in = j0 < Q;  // Q % 4 == 0: a chunk is all data or all padding
+        const float4 q4 = in ? __ldg(reinterpret_cast<const float4*>(qvec + j0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float qv[4] = {q4.x, q4.y, q4.z, q4.w};
+        for (int t0 = rg; t0 < L; t0 += 4 * rgs) {
+          float4 a4[4];
 #pragma unroll
-        for (int u = 0; u < 10; ++u) a[u] = (in && t0 + u < L) ? __ldg(A + (r0 + t0 + u) * Q + j) : 0.f;
+          for (int u = 0; u < 4; ++u) {
+            const int t = t0 + u * rgs;
+            a4[u] = (in && t < L) ? __ldg(reinterpret_cast<const float4*>(A + (r0 + t) * Q + j0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
 #pragma unroll
-        for (int u = 0; u < 10; ++u) {
-          if (t0 + u < L) {
-            const float sd = s_ds[t0 + u];
-            const float v = sd * qj * (1.f - a[u] * a[u]);
-            __nv_bfloat16 hh, ll;
-            split_bf16(v, hh, ll);
-            da_hi[(r0 + t0 + u) * qp + j] = hh;
-            if (da_lo) da_lo[(r0 + t0 + u) * qp + j] = ll;
-            aq += sd * a[u];
-            // db_j = sum_r ds_r q_j (1 - a_rj^2) = -q_j sum_r ds_r a_rj^2: sum_t ds_t = 0 within every softmax
-            // group EXACTLY (ds_t = w_t (dw_t - sum_u w_u dw_u), sum_t w_t = 1), so the "1" part only contributes
-            // its own fp32 rounding noise -- which dominates this gradient when the rows of a group resemble each
-            // other (a_rj^2 nearly constant over r: the result is then a second cancellation on top of the first)
-            ab -= sd * qj * (a[u] * a[u]);
+          for (int u = 0; u < 4; ++u) {
+            const int t = t0 + u * rgs;
+            if (t < L) {
+              const float sd = s_ds[t];
+              const float av[4] = {a4[u].x, a4[u].y, a4[u].z, a4[u].w};
+              __nv_bfloat16 hh[4], ll[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float v = sd * qv[k] * (1.f - av[k] * av[k]);
+                split_bf16(v, hh[k], ll[k]);
+                vq[k] += sd * av[k];
+                vb[k] -= sd * qv[k] * (av[k] * av[k]);  // exact-cancellation form of db, see the scalar path below
+              }
+              const long long off = (r0 + t) * qp + j0;
+              *reinterpret_cast<uint2*>(da_hi + off) = make_uint2(pack_bf16x2(hh[0], hh[1]), pack_bf16x2(hh[2], hh[3]));
+              if (da_lo)
+                *reinterpret_cast<uint2*>(da_lo + off) = make_uint2(pack_bf16x2(ll[0], ll[1]), pack_bf16x2(ll[2], ll[3]));
+            }
           }
         }
       }
-      dq_acc[slot] += aq;
-      db_acc[slot] += ab;
+    } else {
+      int slot = 0;
+      for (int j = threadIdx.x; j < qp; j += blockDim.x, ++slot) {
+        const bool in = j < Q;
+        const float qj = in ? qvec[j] : 0.f;
+        float aq = 0.f, ab = 0.f;
+        for (int t0 = 0; t0 < L; t0 += 10) {
+          float a[10];
+#pragma unroll
+          for (int u = 0; u < 10; ++u) a[u] = (in && t0 + u < L) ? __ldg(A + (r0 + t0 + u) * Q + j) : 0.f;
+#pragma unroll
+          for (int u = 0; u < 10; ++u) {
+            if (t0 + u < L) {
+              const float sd = s_ds[t0 + u];
+              const float v = sd * qj * (1.f - a[u] * a[u]);
+              __nv_bfloat16 hh, ll;
+              split_bf16(v, hh, ll);
+              da_hi[(r0 + t0 + u) * qp + j] = hh;
+              if (da_lo) da_lo[(r0 + t0 + u) * qp + j] = ll;
+              aq += sd * a[u];
+              // db_j = sum_r ds_r q_j (1 - a_rj^2) = -q_j sum_r ds_r a_rj^2: sum_t ds_t = 0 within every softmax
+              // group EXACTLY (ds_t = w_t (dw_t - sum_u w_u dw_u), sum_t w_t = 1), so the "1" part only contributes
+              // its own fp32 rounding noise -- which dominates this gradient when the rows of a group resemble each
+              // other (a_rj^2 nearly constant over r: the result is then a second cancellation on top of the first)
+              ab -= sd * qj * (a[u] * a[u]);
+            }
+          }
+        }
+        dq_acc[slot] += aq;
+        db_acc[slot] += ab;
+      }
     }
     __syncthreads();
+  }
+  if (vec) {  // row groups -> shared memory -> ONE global atomic per column per CTA (as many as the scalar path issues)
+    __shared__ float s_acc[2][256];
+    for (int j = threadIdx.x; j < 2 * 256; j += blockDim.x) (&s_acc[0][0])[j] = 0.f;
+    __syncthreads();
+    if ((int)threadIdx.x < rgs * chunks) {
+      const int j0 = 4 * ((int)threadIdx.x % chunks);
+      if (j0 < Q) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          atomicAdd(&s_acc[0][j0 + k], vq[k]);
+          atomicAdd(&s_acc[1][j0 + k], vb[k]);
+        }
+      }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < Q; j += blockDim.x) {
+      atomicAdd(dq_accum + j, s_acc[0][j]);
+      atomicAdd(db_accum + j, s_acc[1][j]);
+    }
+    return;
   }
   int slot = 0;
   for (int j = threadIdx.x; j < Q; j += blockDim.x, ++slot) {
