@@ -22,6 +22,7 @@
 #include "nrl_exchange.cuh"
 #include "nrl_tfm.cuh"
 #include "nrl_attn_flash.cuh"
+#include "nrl_attn_title.cuh"
 
 using namespace nrl;
 typedef __nv_bfloat16 bf16;
@@ -519,6 +520,7 @@ struct AttnGeom {
   int S; long long seq_stride; int NB; long long batch_stride;
 };
 
+constexpr int ATTN_BWD_DEFAULT_VARIANT = 1;
 constexpr int ATTN_FWD_SMEM_BUDGET = 110 * 1024;
 constexpr int ATTN_BWD_SMEM_BUDGET = 100 * 1024;
 
@@ -567,6 +569,8 @@ static int attn_set_attrs() {
                                   flash_bwd_smem<DH>()));
   }
   if constexpr (DH <= 32) {
+    CUDA_TRY(cudaFuncSetAttribute(attn_bwd_ldsm_kernel<DH, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  3 * TitleCfg<DH>::HEAD_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(attn_fwd_tma_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   ATTN_TMA_SMEM_MAX));
     CUDA_TRY(cudaFuncSetAttribute(attn_bwd_tma_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -673,8 +677,17 @@ static void launch_attn_bwd(const Ctx& c, const Dims& d, const AttnGeom& g, cons
   if (g.S <= 32 && !attn_force_simt()) {
     const long long items = (long long)g.NB * d.H;
     // NRL_ATTN_BWD_VARIANT (A/B runs): 0 = fragments held in registers (168 registers, 3 CTAs / SM), 1 = fragments
-    // re-read when needed again (default), 2 = re-read + register budget of 4 CTAs / SM
-    static const int variant = [] { const char* e = getenv("NRL_ATTN_BWD_VARIANT"); return e ? atoi(e) : 1; }();
+    // re-read when needed again, 2 = re-read + register budget of 4 CTAs / SM, 3 = operands staged once per head as bf16
+    // hi / lo planes in shared memory + ldmatrix (nrl_attn_title.cuh)
+    static const int variant = [] { const char* e = getenv("NRL_ATTN_BWD_VARIANT"); return e ? atoi(e) : ATTN_BWD_DEFAULT_VARIANT; }();
+    if (variant == 3 && (DH % 4) == 0 && !(d.E & 3) && !(d.LDQ & 3)) {
+      constexpr int HG = 3;
+      const int groups = (d.H + HG - 1) / HG;
+      attn_bwd_ldsm_kernel<DH, HG><<<(unsigned)((long long)g.NB * groups), 64 * HG, HG * TitleCfg<DH>::HEAD_BYTES, c.stream>>>(
+          w.qkv, w.d_o, d.E, w.lse, d.E, d.LDQ, d.H, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH), w.dqkv, lo,
+          d.P3, c.two_planes() ? 1 : 0);
+      return;
+    }
 #define NRL_ATTN_BWD_LAUNCH(RELOAD, MINB)                                                                            \
     attn_bwd_mma_kernel<DH, RELOAD, MINB><<<(unsigned)((items + 3) / 4), 128, 0, c.stream>>>(                        \
         w.qkv, w.d_o, d.E, w.lse, d.E, d.LDQ, d.H, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH), w.dqkv, lo, \
