@@ -793,10 +793,12 @@ def main():
         msbuf = (C.c_float * maxrec)()
         n = lib.nrl_profile_stop(names, stride, msbuf, maxrec)
         agg = {}
+        per_launch = {}  # name -> durations in launch order (all profiled steps)
         for i in range(n):
             nm = names.raw[i * stride:(i + 1) * stride].split(b"\0")[0].decode()
             t, c = agg.get(nm, (0.0, 0))
             agg[nm] = (t + msbuf[i], c + 1)
+            per_launch.setdefault(nm, []).append(msbuf[i])
         rows_news, rows_user = (nh + nc) * L, B * Hmax
         gemm_ms = sum(t for nm, (t, c) in agg.items() if nm.startswith("gemm")) / prof_steps
         gemm_launches = sum(c for nm, (t, c) in agg.items() if nm.startswith("gemm")) / prof_steps
@@ -821,25 +823,39 @@ def main():
     # user block; Adam per parameter) over the live per-launch durations of region B
     hbm_kernels = None
     if rank == 0:
-        rows = (nh + nc) * L + B * Hmax
         n_params = sum(v.numel() for v in params.values())
         mw_bytes = 4 * ((E + 31) // 32)
-        algo = {
-            "gather_split": ((nh + nc) * L) * (8 + 4 * E + mw_bytes + 2 * 2 * (E + 4)),
-            "attn_fwd": rows * (3 * 4 * E + 2 * 2 * (E + 4) + 4 * H),
-            "attn_bwd": rows * (3 * 4 * E + 4 * E + 4 * H + 2 * 2 * (3 * E + 12)),
-            "pool_fwd": rows * (4 * E + 8) + (nh + nc + B) * 4 * E,
-            "pool_bwd": rows * (4 * E + 4 * Q + 4 + 2 * 2 * ((Q + 15) // 16 * 16)) + (nh + nc + B) * 4 * E,
-            "emb_grad": ((nh + nc) * L) * (4 * E + 8 + 2 * 4 * E),
-            "adam": n_params * 28,
-        }
+        Qp = (Q + 15) // 16 * 16
+        # bytes per token row of a MHSA + additive block (title block: (nh + nc) * L rows; user block: B * Hmax rows)
+        per_row = {"attn_fwd": 3 * 4 * E + 2 * 2 * (E + 4) + 4 * H,
+                   "attn_bwd": 3 * 4 * E + 4 * E + 4 * H + 2 * 2 * (3 * E + 12),
+                   "pool_fwd": 4 * E + 8, "pool_bwd": 4 * E + 4 * Q + 4 + 2 * 2 * Qp}
+        per_group = {"pool_fwd": 4 * E, "pool_bwd": 4 * E}
         hbm_kernels = []
-        for nm, nbytes in algo.items():
-            if nm in agg:
-                ms = agg[nm][0] / prof_steps
-                gbs = nbytes / (ms / 1e3) / 1e9
-                hbm_kernels.append({"kernel": nm, "ms_per_step": round(ms, 4), "algorithmic_mbytes": round(nbytes / 1e6, 1),
-                                    "achieved_gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / hbm, 3)})
+
+        def add(label, ms, nbytes, **extra):
+            gbs = nbytes / (ms / 1e3) / 1e9
+            hbm_kernels.append({"kernel": label, "ms_per_step": round(ms, 4), "algorithmic_mbytes": round(nbytes / 1e6, 1),
+                                "achieved_gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / hbm, 3), **extra})
+        if "gather_split" in agg:
+            add("gather_split", agg["gather_split"][0] / prof_steps, rows_news * (8 + 4 * E + mw_bytes + 2 * 2 * (E + 4)))
+        for nm in ("attn_fwd", "attn_bwd", "pool_fwd", "pool_bwd"):
+            # two launches per step: the title block ((nh + nc) * L = 105 600 rows) and the user block (B * Hmax = 3 200 rows:
+            # 33x less data, a latency-bound launch).  Launch order differs between forward and backward: the longer one of a
+            # step is the title block.
+            d = per_launch.get(nm, [])
+            k = len(d) // prof_steps
+            if k != 2:
+                continue
+            big = sum(max(d[i * k:(i + 1) * k]) for i in range(prof_steps)) / prof_steps
+            small = sum(min(d[i * k:(i + 1) * k]) for i in range(prof_steps)) / prof_steps
+            add(nm + " (title block)", big, rows_news * per_row[nm] + (nh + nc) * per_group.get(nm, 0))
+            add(nm + " (user block, 3 200 rows: latency-bound)", small, rows_user * per_row[nm] + B * per_group.get(nm, 0))
+        if "emb_grad" in agg:
+            add("emb_grad", agg["emb_grad"][0] / prof_steps, rows_news * (4 * E + 8 + 2 * 4 * E),
+                note="the read-modify-write of the table rows is served by L2 (ncu: DRAM 15 %): this is an L2-assisted figure")
+        if "adam" in agg:
+            add("adam", agg["adam"][0] / prof_steps, n_params * 28)
 
     # the fused exchange kernel (N > 1, --exchange peer): bytes that cross NVLink per rank and step, per direction
     # (gradients of the owned slice pulled from W-1 peers; new parameters of the owned slice pushed to W-1 peers;

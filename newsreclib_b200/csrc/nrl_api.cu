@@ -778,6 +778,31 @@ static int attn_attrs_init() {
   return NRL_OK;
 }
 
+// additive pooling forward: the TMA-staged kernel when the [L][E] tile of a group can be bulk-copied (16-byte rows, two
+// stages fit shared memory, enough groups to keep persistent CTAs busy), else the direct kernel.  NRL_POOL_TMA=0: direct.
+static int launch_pool_fwd(const Ctx& c, const float* score, const float* Y, int E, int L, long long G, float* w_out,
+                           float* out) {
+  static const bool tma_on = [] { const char* e = getenv("NRL_POOL_TMA"); return !(e && e[0] == '0'); }();
+  static bool attr_done = false;
+  const size_t smem = pool_fwd_tma_smem(E, L);
+  if (tma_on && !(E & 3) && L <= 64 && smem <= 200 * 1024 && G >= 4 * g_dev.sm_count &&
+      !(reinterpret_cast<uintptr_t>(Y) & 15) && !(reinterpret_cast<uintptr_t>(out) & 15)) {
+    if (!attr_done) {
+      CUDA_TRY(cudaFuncSetAttribute(pool_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_done = true;
+    }
+    const int per_sm = (int)((220 * 1024) / (smem + 1024));
+    const int ctas = g_dev.sm_count * (per_sm < 1 ? 1 : per_sm > 4 ? 4 : per_sm);
+    pool_fwd_tma_kernel<<<(unsigned)(G < ctas ? G : ctas), 128, smem, c.stream>>>(score, Y, E, L, G, w_out, out);
+    LAUNCH_CHECK("pool_fwd");
+    return NRL_OK;
+  }
+  pool_fwd_kernel<<<dim3((unsigned)grid_for(G, 1, 1 << 20), (unsigned)((E + 511) / 512)), 128, L * sizeof(float), c.stream>>>(
+      score, Y, E, L, G, w_out, out);
+  LAUNCH_CHECK("pool_fwd");
+  return NRL_OK;
+}
+
 // MHSA + additive pooling over R rows already staged in w.x (split planes).
 static int block_forward(const Ctx& c, const Dims& d, BlockWs& w, long long R, const AttnGeom& ag,
                          long long G, int L, const nrl_block_params* prm, const DropCfg& drop,
@@ -814,8 +839,7 @@ static int block_forward(const Ctx& c, const Dims& d, BlockWs& w, long long R, c
     sk.f32 = w.a; sk.ld_f32 = d.Q; sk.f32_cols = d.Q;
     TRY(gemm_nt(c, w.yp, R, d.Ep, w.wadd_f, d.Q, d.Ep, d.Ep, e, sk, "gemm additive"));
   }
-  pool_fwd_kernel<<<dim3((unsigned)grid_for(G, 1, 1 << 20), (unsigned)((d.E + 511) / 512)), 128, L * sizeof(float), c.stream>>>(w.s, w.y, d.E, L, G, w.w, out_vec);
-  LAUNCH_CHECK("pool_fwd");
+  TRY(launch_pool_fwd(c, w.s, w.y, d.E, L, G, w.w, out_vec));
   return NRL_OK;
 }
 
@@ -1196,8 +1220,7 @@ int nrl_additive_fwd(const float* x, long long G, int L, int D, int Q, const flo
   Sinks sk;
   sk.f32 = w.a; sk.ld_f32 = Q; sk.f32_cols = Q;
   TRY(gemm_nt(c, w.xp, R, Dp, w.wf, Q, Dp, Dp, e, sk, "gemm additive"));
-  pool_fwd_kernel<<<dim3((unsigned)grid_for(G, 1, 1 << 20), (unsigned)((D + 511) / 512)), 128, L * sizeof(float), c.stream>>>(w.s, x, D, L, G, w.w, out);
-  LAUNCH_CHECK("pool_fwd");
+  TRY(launch_pool_fwd(c, w.s, x, D, L, G, w.w, out));
   return NRL_OK;
 }
 
@@ -1796,10 +1819,7 @@ int nrl_cnn_encoder_fwd(const long long* ids, long long n_news, int L, const flo
     sk.f32 = w.a; sk.ld_f32 = d.Q; sk.f32_cols = d.Q;
     TRY(gemm_nt(c, w.yp, R, d.Fp, w.wadd_f, d.Q, d.Fp, d.Fp, e, sk, "gemm additive"));
   }
-  pool_fwd_kernel<<<dim3((unsigned)grid_for(n_news, 1, 1 << 20), (unsigned)((d.F + 511) / 512)), 128, L * sizeof(float), c.stream>>>(w.s, w.y, d.F, L, n_news,
-                                                                                       w.w, out);
-  LAUNCH_CHECK("pool_fwd");
-  return NRL_OK;
+  return launch_pool_fwd(c, w.s, w.y, d.F, L, n_news, w.w, out);
 }
 
 int nrl_cnn_encoder_bwd(const long long* ids, long long n_news, int L, long long V1,

@@ -1180,6 +1180,73 @@ pool_fwd_kernel(const float* __restrict__ score, const float* __restrict__ Y, in
   }
 }
 
+// The same pooling with the [L][E] tile of a group staged by the TMA unit: the rows of a group are contiguous, so ONE
+// cp.async.bulk (1-D bulk copy, completion on an mbarrier) brings the whole 36 KB tile into shared memory; persistent
+// CTAs, two stages: thread 0 asks for the tile of the CTA's NEXT group before the current one is reduced, warp 0 computes
+// the L <= 64 softmax weights meanwhile, then every thread reduces four columns out of shared memory (16-byte reads,
+// conflict-free) -- no global-load instructions, no address arithmetic, the copy engine keeps the HBM requests in flight.
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__global__ void __launch_bounds__(128)
+pool_fwd_tma_kernel(const float* __restrict__ score, const float* __restrict__ Y, int E, int L, long long G,
+                    float* __restrict__ w_out, float* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char psm[];
+  const uint32_t tile_bytes = (uint32_t)L * E * 4u;             // multiple of 16 (E % 4 == 0)
+  const uint32_t stage_bytes = (tile_bytes + 127u) & ~127u;
+  float* sw = reinterpret_cast<float*>(psm + 2 * stage_bytes);  // [64]
+  const uint32_t bar0 = smem_u32(psm + 2 * stage_bytes + 256);
+  const uint32_t base = smem_u32(psm);
+  if (threadIdx.x == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && (long long)blockIdx.x < G) {
+    mbar_expect_tx(bar0, tile_bytes);
+    bulk_load_1d(base, Y + (long long)blockIdx.x * L * E, tile_bytes, bar0);
+  }
+  int it = 0;
+  for (long long g = blockIdx.x; g < G; g += gridDim.x, ++it) {
+    const int st = it & 1;
+    const long long gn = g + gridDim.x;
+    if (threadIdx.x == 0 && gn < G) {  // stage st ^ 1 was released by the barrier that ended the previous iteration
+      mbar_expect_tx(bar0 + 8 * (st ^ 1), tile_bytes);
+      bulk_load_1d(base + (st ^ 1) * stage_bytes, Y + gn * L * E, tile_bytes, bar0 + 8 * (st ^ 1));
+    }
+    const long long r0 = g * L;
+    if (threadIdx.x < 32) {  // softmax over the L <= 64 scores of the group
+      const int t = threadIdx.x;
+      const float s0 = t < L ? score[r0 + t] : -INFINITY, s1 = t + 32 < L ? score[r0 + t + 32] : -INFINITY;
+      const float mx = warp_max(fmaxf(s0, s1));
+      const float e0 = t < L ? expf(s0 - mx) : 0.f, e1 = t + 32 < L ? expf(s1 - mx) : 0.f;
+      const float inv = 1.f / warp_sum(e0 + e1);
+      if (t < L) { sw[t] = e0 * inv; w_out[r0 + t] = e0 * inv; }
+      if (t + 32 < L) { sw[t + 32] = e1 * inv; w_out[r0 + t + 32] = e1 * inv; }
+    }
+    __syncthreads();
+    mbar_wait(bar0 + 8 * st, (uint32_t)(it >> 1) & 1u);
+    const float* tile = reinterpret_cast<const float*>(psm + st * stage_bytes);
+    for (int c = threadIdx.x * 4; c < E; c += blockDim.x * 4) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 5
+      for (int t = 0; t < L; ++t) {
+        const float4 v = *reinterpret_cast<const float4*>(tile + t * E + c);
+        const float wt = sw[t];
+        acc.x += wt * v.x; acc.y += wt * v.y; acc.z += wt * v.z; acc.w += wt * v.w;
+      }
+      *reinterpret_cast<float4*>(out + g * E + c) = acc;
+    }
+    __syncthreads();  // the tile and sw are free again
+  }
+}
+__host__ __device__ inline size_t pool_fwd_tma_smem(int E, int L) {
+  return 2 * (((size_t)L * E * 4 + 127) & ~(size_t)127) + 256 + 64;
+}
+
 // Backward of additive pooling (through softmax, the q-dot and tanh):
 //   dY1[r]   = w_r * dOut[g]                                  (fp32, later += dApre * W_add)
 //   dApre[r] = ds_r * q * (1 - A_r^2),  ds_r = w_r (dOut.Y_r - sum_u w_u dOut.Y_u)   (split planes)
