@@ -569,8 +569,10 @@ static int attn_set_attrs() {
                                   flash_bwd_smem<DH>()));
   }
   if constexpr (DH <= 32) {
-    CUDA_TRY(cudaFuncSetAttribute(attn_bwd_ldsm_kernel<DH, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_TRY(cudaFuncSetAttribute(attn_bwd_ldsm_kernel<DH, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   3 * TitleCfg<DH>::HEAD_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(attn_bwd_ldsm_kernel<DH, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  TitleCfg<DH, 2>::HEAD_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(attn_fwd_tma_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   ATTN_TMA_SMEM_MAX));
     CUDA_TRY(cudaFuncSetAttribute(attn_bwd_tma_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -683,7 +685,7 @@ static void launch_attn_bwd(const Ctx& c, const Dims& d, const AttnGeom& g, cons
     if (variant == 3 && (DH % 4) == 0 && !(d.E & 3) && !(d.LDQ & 3)) {
       constexpr int HG = 3;
       const int groups = (d.H + HG - 1) / HG;
-      attn_bwd_ldsm_kernel<DH, HG><<<(unsigned)((long long)g.NB * groups), 64 * HG, HG * TitleCfg<DH>::HEAD_BYTES, c.stream>>>(
+      attn_bwd_ldsm_kernel<DH, HG, 1><<<(unsigned)((long long)g.NB * groups), 64 * HG, HG * TitleCfg<DH>::HEAD_BYTES, c.stream>>>(
           w.qkv, w.d_o, d.E, w.lse, d.E, d.LDQ, d.H, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH), w.dqkv, lo,
           d.P3, c.two_planes() ? 1 : 0);
       return;
@@ -696,6 +698,16 @@ static void launch_attn_bwd(const Ctx& c, const Dims& d, const AttnGeom& g, cons
     else if (variant == 2) NRL_ATTN_BWD_LAUNCH(true, 4);
     else NRL_ATTN_BWD_LAUNCH(true, 3);
 #undef NRL_ATTN_BWD_LAUNCH
+    return;
+  }
+  // 32 < S <= 64 (the NRMS user encoder: S = B = 64 along the batch axis): operands staged once per (item, head) as
+  // bf16 hi / lo planes + ldmatrix, four warps of 16 rows (nrl_attn_title.cuh).  NRL_ATTN_BWD64=0: the register /
+  // movmatrix kernel below (250 registers, 61 us for 750 problems against ~15 us here)
+  static const bool ldsm64 = [] { const char* e = getenv("NRL_ATTN_BWD64"); return !(e && e[0] == '0'); }();
+  if (g.S <= 64 && !attn_force_simt() && ldsm64 && (DH % 4) == 0 && !(d.E & 3) && !(d.LDQ & 3)) {
+    attn_bwd_ldsm_kernel<DH, 1, 2><<<(unsigned)((long long)g.NB * d.H), 128, TitleCfg<DH, 2>::HEAD_BYTES, c.stream>>>(
+        w.qkv, w.d_o, d.E, w.lse, d.E, d.LDQ, d.H, g.S, g.seq_stride, g.NB, g.batch_stride, sqrtf(1.0f / DH), w.dqkv, lo,
+        d.P3, c.two_planes() ? 1 : 0);
     return;
   }
   if (g.S <= 64 && !attn_force_simt()) {

@@ -16,15 +16,18 @@
 
 namespace nrl {
 
-template <int DH>
+template <int DH, int NK32 = 1>  // sequence padded to SK = 32 * NK32 rows (S <= 32: titles; S <= 64: the NRMS user encoder)
 struct TitleCfg {
+  static constexpr int SK = 32 * NK32;
   static constexpr int DHP = (DH + 15) / 16 * 16;  // staged columns (zeros beyond DH)
   static constexpr int PITCH = DHP + 8;
   static constexpr int ROWB = PITCH * 2;
   static constexpr int KS = DHP / 16;
   static constexpr int DT = (DH + 7) / 8;          // 8-wide output tiles that hold real columns
-  static constexpr int PLANE = 32 * ROWB;
-  static constexpr int HEAD_BYTES = 8 * PLANE + 2 * 32 * 4;  // Q K V dO (hi, lo) + lse2[32] + dd[32]
+  static constexpr int NT = SK / 8;                // 8-wide tiles along the sequence
+  static constexpr int PLANE = SK * ROWB;
+  static constexpr int HEAD_BYTES = 8 * PLANE + 2 * SK * 4;  // Q K V dO (hi, lo) + lse2[SK] + dd[SK]
+  static constexpr int HEAD_THREADS = 32 * (SK / 16);        // one warp per 16 rows
 };
 template <int ROWB>
 __device__ __forceinline__ uint32_t tt_a_addr(uint32_t base, int row0, int k0, int lane) {
@@ -42,35 +45,35 @@ __device__ __forceinline__ uint32_t tt_bn_addr(uint32_t base, int k0, int n0, in
   return base + (uint32_t)((k0 + (lane & 7) + 8 * (mi & 1)) * ROWB + (n0 + 8 * (mi >> 1)) * 2);
 }
 
-template <int DH, int HG>
-__global__ void __launch_bounds__(64 * HG, 3)
+template <int DH, int HG, int NK32>
+__global__ void __launch_bounds__(64 * NK32 * HG, NK32 == 1 ? 3 : 2)
 attn_bwd_ldsm_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o, long long ld_do,
                      const float* __restrict__ lse, int E, int ldq, int heads, int S, long long seq_stride, int NB,
                      long long batch_stride, float scale, __nv_bfloat16* __restrict__ g_hi,
                      __nv_bfloat16* __restrict__ g_lo, int p3, int three_i) {
-  using C = TitleCfg<DH>;
-  constexpr int ROWB = C::ROWB, C4 = C::DHP / 4, R4 = DH / 4;
+  using C = TitleCfg<DH, NK32>;
+  constexpr int ROWB = C::ROWB, C4 = C::DHP / 4, R4 = DH / 4, SK = C::SK, NT = C::NT, HT = C::HEAD_THREADS;
   static_assert(DH % 4 == 0, "16-byte row segments");
   extern __shared__ __align__(16) uint8_t ttsm[];
   const bool three = three_i != 0;
   const int groups = (heads + HG - 1) / HG;
-  const int b = blockIdx.x / groups, hl = threadIdx.x >> 6, h = (blockIdx.x % groups) * HG + hl;
+  const int b = blockIdx.x / groups, hl = threadIdx.x / HT, h = (blockIdx.x % groups) * HG + hl;
   const bool head_ok = h < heads;
-  const int t2 = threadIdx.x & 63;  // thread within the head's two warps
+  const int t2 = threadIdx.x % HT;  // thread within the head's warps
   uint8_t* hs = ttsm + hl * C::HEAD_BYTES;
   float* lse2 = reinterpret_cast<float*>(hs + 8 * C::PLANE);
-  float* dd = lse2 + 32;
+  float* dd = lse2 + SK;
   const long long row_base = (long long)b * batch_stride;
   // ---- stage Q (pre-scaled), K, V, dO: 4 matrices x 32 rows x C4 chunks, two batches of loads in flight ----
   if (head_ok) {
-    constexpr int ITEMS = 4 * 32 * C4, ITER = ITEMS / 64, HALF = ITER / 2;
-    static_assert(ITER * 64 == ITEMS && HALF * 2 == ITER, "staging split");
+    constexpr int ITEMS = 4 * SK * C4, ITER = ITEMS / HT, HALF = ITER / 2;
+    static_assert(ITER * HT == ITEMS && HALF * 2 == ITER, "staging split");
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       float4 v[HALF];
 #pragma unroll
       for (int it = 0; it < HALF; ++it) {
-        const int i = t2 + (half * HALF + it) * 64, m = i / (32 * C4), r = (i / C4) % 32, c = i % C4;
+        const int i = t2 + (half * HALF + it) * HT, m = i / (SK * C4), r = (i / C4) % SK, c = i % C4;
         v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (r < S && c < R4) {
           const long long grow = (long long)r * seq_stride + row_base;
@@ -80,7 +83,7 @@ attn_bwd_ldsm_kernel(const float* __restrict__ qkv, const float* __restrict__ d_
       }
 #pragma unroll
       for (int it = 0; it < HALF; ++it) {
-        const int i = t2 + (half * HALF + it) * 64, m = i / (32 * C4), r = (i / C4) % 32, c = i % C4;
+        const int i = t2 + (half * HALF + it) * HT, m = i / (SK * C4), r = (i / C4) % SK, c = i % C4;
         const float mul = m == 0 ? scale * TFM_LOG2E : 1.f;
         uint32_t h0, l0, h1, l1;
         split_pack2(v[it].x * mul, v[it].y * mul, h0, l0);
@@ -90,14 +93,14 @@ attn_bwd_ldsm_kernel(const float* __restrict__ qkv, const float* __restrict__ d_
         *reinterpret_cast<uint2*>(hs + off + C::PLANE) = make_uint2(l0, l1);
       }
     }
-    if (t2 < 32) {
+    if (t2 < SK) {
       lse2[t2] = t2 < S ? lse[((long long)t2 * seq_stride + row_base) * heads + h] * TFM_LOG2E : INFINITY;
       dd[t2] = 0.f;  // rows of a warp that has nothing to do (S <= 16) are still read by phase B
     }
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
-  const int w0 = 16 * ((threadIdx.x >> 5) & 1);
+  const int w0 = 16 * (t2 >> 5);
   const bool active = head_ok && w0 < S;
   const uint32_t sb = smem_u32(hs);
   const uint32_t oQh = 0, oQl = C::PLANE, oKh = 2 * C::PLANE, oKl = 3 * C::PLANE, oVh = 4 * C::PLANE, oVl = 5 * C::PLANE,
@@ -105,9 +108,9 @@ attn_bwd_ldsm_kernel(const float* __restrict__ qkv, const float* __restrict__ d_
   const int r0 = w0 + g, r1 = r0 + 8;
   // =========================== phase A: D and dQ (rows = queries) ===========================
   if (active) {
-    float s[4][4], dp[4][4];
+    float s[NT][4], dp[NT][4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NT; ++j) {
       s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
       dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
     }
@@ -121,7 +124,7 @@ attn_bwd_ldsm_kernel(const float* __restrict__ qkv, const float* __restrict__ d_
         ldsm_x4(gl, tt_a_addr<ROWB>(sb + oGl, w0, 16 * kk, lane));
       }
 #pragma unroll
-      for (int j2 = 0; j2 < 2; ++j2) {
+      for (int j2 = 0; j2 < NT / 2; ++j2) {
         uint32_t bh[4], bl[4] = {0u, 0u, 0u, 0u};
         ldsm_x4(bh, tt_bt_addr<ROWB>(sb + oKh, 16 * j2, 16 * kk, lane));
         if (three) ldsm_x4(bl, tt_bt_addr<ROWB>(sb + oKl, 16 * j2, 16 * kk, lane));
@@ -136,7 +139,7 @@ attn_bwd_ldsm_kernel(const float* __restrict__ qkv, const float* __restrict__ d_
     const float ls0 = lse2[r0], ls1 = lse2[r1];
     float d0 = 0.f, d1 = 0.f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NT; ++j) {
       const int u = 8 * j + 2 * tg;
       s[j][0] = u < S ? ex2_approx(s[j][0] - ls0) : 0.f; s[j][1] = u + 1 < S ? ex2_approx(s[j][1] - ls0) : 0.f;
       s[j][2] = u < S ? ex2_approx(s[j][2] - ls1) : 0.f; s[j][3] = u + 1 < S ? ex2_approx(s[j][3] - ls1) : 0.f;
@@ -147,7 +150,7 @@ attn_bwd_ldsm_kernel(const float* __restrict__ qkv, const float* __restrict__ d_
     d1 += __shfl_xor_sync(0xffffffffu, d1, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
     if (tg == 0) { dd[r0] = d0; dd[r1] = d1; }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NT; ++j) {
       s[j][0] *= dp[j][0] - d0; s[j][1] *= dp[j][1] - d0;
       s[j][2] *= dp[j][2] - d1; s[j][3] *= dp[j][3] - d1;
     }
@@ -155,7 +158,7 @@ attn_bwd_ldsm_kernel(const float* __restrict__ qkv, const float* __restrict__ d_
 #pragma unroll
     for (int j = 0; j < C::DT; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.f;
 #pragma unroll
-    for (int kk = 0; kk < 2; ++kk) {  // 32 keys
+    for (int kk = 0; kk < NT / 2; ++kk) {  // all keys
       uint32_t ah[4], al[4];
       split_pack2(s[2 * kk][0], s[2 * kk][1], ah[0], al[0]);
       split_pack2(s[2 * kk][2], s[2 * kk][3], ah[1], al[1]);
@@ -192,12 +195,12 @@ attn_bwd_ldsm_kernel(const float* __restrict__ qkv, const float* __restrict__ d_
         }
     }
   }
-  __syncthreads();  // D of all 32 queries of the head is in shared memory
+  __syncthreads();  // D of all queries of the head is in shared memory
   // =========================== phase B: dK, dV (rows = keys) ===========================
   if (active) {
-    float st[4][4], dpt[4][4];
+    float st[NT][4], dpt[NT][4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NT; ++j) {
       st[j][0] = st[j][1] = st[j][2] = st[j][3] = 0.f;
       dpt[j][0] = dpt[j][1] = dpt[j][2] = dpt[j][3] = 0.f;
     }
@@ -211,7 +214,7 @@ attn_bwd_ldsm_kernel(const float* __restrict__ qkv, const float* __restrict__ d_
         ldsm_x4(vl, tt_a_addr<ROWB>(sb + oVl, w0, 16 * kk, lane));
       }
 #pragma unroll
-      for (int j2 = 0; j2 < 2; ++j2) {
+      for (int j2 = 0; j2 < NT / 2; ++j2) {
         uint32_t bh[4], bl[4] = {0u, 0u, 0u, 0u};
         ldsm_x4(bh, tt_bt_addr<ROWB>(sb + oQh, 16 * j2, 16 * kk, lane));
         if (three) ldsm_x4(bl, tt_bt_addr<ROWB>(sb + oQl, 16 * j2, 16 * kk, lane));
@@ -225,7 +228,7 @@ attn_bwd_ldsm_kernel(const float* __restrict__ qkv, const float* __restrict__ d_
     }
     const bool kv0 = r0 < S, kv1 = r1 < S;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NT; ++j) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int t = 8 * j + 2 * tg + e;  // query (lse2 = +inf beyond S: P = 0)
@@ -244,7 +247,7 @@ attn_bwd_ldsm_kernel(const float* __restrict__ qkv, const float* __restrict__ d_
       dv[j][0] = dv[j][1] = dv[j][2] = dv[j][3] = 0.f;
     }
 #pragma unroll
-    for (int kk = 0; kk < 2; ++kk) {  // 32 queries
+    for (int kk = 0; kk < NT / 2; ++kk) {  // all queries
       uint32_t sh_[4], sl_[4], ph[4], pl[4];
       split_pack2(st[2 * kk][0], st[2 * kk][1], sh_[0], sl_[0]);
       split_pack2(st[2 * kk][2], st[2 * kk][3], sh_[1], sl_[1]);
