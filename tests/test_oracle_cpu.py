@@ -368,3 +368,57 @@ def test_plm_mirror_refuses_uncovered_transformers():
     assert [p.requires_grad for p in ps[5:21]] == [False] * 16 and all(p.requires_grad for p in ps[21:])
     with pytest.raises(RuntimeError, match="CUDA"):  # no CPU path
         m({"input_ids": torch.zeros(2, 5, dtype=torch.long), "attention_mask": torch.ones(2, 5, dtype=torch.long)})
+
+
+def test_transformer_hidden_states_do_not_depend_on_trailing_padding():
+    """The claim PLM.forward_pair rests on (one transformer pass for history + candidates, each part cut back to its own
+    padded length): with the key-padding mask, a token's hidden state is the same whether its text is padded to 9 or to 14
+    positions -- checked on the real HF RobertaModel and on the restatement."""
+    from transformers import RobertaConfig, RobertaModel
+    from oracle import tfm_oracle as TO
+    torch.manual_seed(3)
+    tf = RobertaModel(RobertaConfig(vocab_size=50, hidden_size=64, num_hidden_layers=2, num_attention_heads=1,
+                                    intermediate_size=96, max_position_embeddings=20, pad_token_id=1, type_vocab_size=1),
+                      add_pooling_layer=False).eval()
+    ids = torch.tensor([[0, 7, 9, 12, 2, 1, 1, 1, 1], [0, 5, 6, 7, 8, 9, 10, 11, 2]])
+    att = (ids != 1).long()
+    wide_ids = torch.nn.functional.pad(ids, (0, 5), value=1)
+    wide_att = torch.nn.functional.pad(att, (0, 5), value=0)
+    with torch.no_grad():
+        a = tf(input_ids=ids, attention_mask=att)[0]
+        b = tf(input_ids=wide_ids, attention_mask=wide_att)[0][:, :9]
+    assert float((a - b).abs().max()) <= 2e-6  # padding positions included: they attend to the same valid keys
+    P = {k: v for k, v in tf.state_dict().items() if v.is_floating_point()}
+    eps = tf.config.layer_norm_eps
+    oa = TO.encoder(ids, att, P, 1, 2, eps=eps)
+    ob = TO.encoder(wide_ids, wide_att, P, 1, 2, eps=eps)[:, :9]
+    assert float((oa - ob).abs().max()) <= 2e-6 and float((oa - a).abs().max()) <= 2e-5
+
+
+def test_two_tower_merges_per_news_encoder_calls():
+    """TwoTowerRecommender._encode_hist_and_cand: ONE call of a per-news encoder over history + candidates gives the vectors
+    of the two separate calls (nrms_module.py:231,235); mismatching token widths fall back to two calls."""
+    from newsreclib_b200.models.general_rec.two_tower import TwoTowerRecommender
+
+    class ToyNews(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.text_encoders = torch.nn.ModuleDict({"title": torch.nn.Embedding(30, 8)})
+            self.calls = 0
+
+        def forward(self, news):
+            self.calls += 1
+            return self.text_encoders["title"](news["title"]).mean(dim=1)  # per-news: rows independent
+    m = TwoTowerRecommender.__new__(TwoTowerRecommender)
+    torch.nn.Module.__init__(m)
+    m.news_encoder = ToyNews()
+    h, c = {"title": torch.randint(0, 30, (7, 5))}, {"title": torch.randint(0, 30, (3, 5))}
+    vh, vc = m._encode_hist_and_cand(h, c)
+    assert m.news_encoder.calls == 1 and vh.shape == (7, 8) and vc.shape == (3, 8)
+    assert torch.equal(vh, m.news_encoder(h)) and torch.equal(vc, m.news_encoder(c))
+    m.news_encoder.calls = 0
+    m._encode_hist_and_cand(h, {"title": torch.randint(0, 30, (3, 6))})  # another padded width: two calls
+    assert m.news_encoder.calls == 2
+    m.merge_news_calls, m.news_encoder.calls = False, 0
+    m._encode_hist_and_cand(h, c)
+    assert m.news_encoder.calls == 2
