@@ -1,12 +1,7 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q --timeout 900 -x 2>&1 | tail -3
-for v in 0 1; do
-NRL_ATTN_BWD64=$v timeout 600 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --no-extras > gpurun_out/bench_u$v.json 2> gpurun_out/bench_u$v.err; tail -1 gpurun_out/bench_u$v.err
-python - $v <<'PY'
-import json,sys
-j=json.loads(open(f"gpurun_out/bench_u{sys.argv[1]}.json").read())
-print("ldsm64", sys.argv[1], j["ms_per_step"], j["value"])
-for k in j["hbm_kernels"]:
-    if "attn_bwd" in k["kernel"]: print("   ", k["kernel"], k["ms_per_step"], k["frac_of_hbm_peak"])
-PY
-done
+export PYTHONUNBUFFERED=1
+timeout 600 python -m pytest tests/test_gpu_tfm.py -m gpu -q --timeout 500 2>&1 | tail -2
+timeout 600 python experiments/plm_profile.py 40 2>&1 | grep "wall\|ln._bwd"
+timeout 600 python experiments/plm_profile.py 96 2>&1 | grep "wall\|ln._bwd"
+timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 --print-limit 20 python -m pytest tests -m gpu -q --timeout 1400 --deselect tests/test_gpu_peer_exchange.py > gpurun_out/r02_sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; grep "passed\|failed\|ERROR SUMMARY" gpurun_out/r02_sanitizer_memcheck.log
+timeout 1200 compute-sanitizer --tool racecheck --error-exitcode 9 --print-limit 20 python -m pytest tests/test_gpu_tfm.py tests/test_gpu_naml.py tests/test_gpu_parity.py -m gpu -q --timeout 1100 > gpurun_out/r02_sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?"; grep "passed\|failed\|RACECHECK SUMMARY" gpurun_out/r02_sanitizer_racecheck.log

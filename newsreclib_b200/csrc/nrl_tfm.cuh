@@ -212,9 +212,36 @@ tfm_ln_bwd_kernel(const float* __restrict__ s, const float* __restrict__ dy, lon
       row.v[i] = c < D ? *reinterpret_cast<const float4*>(s + r * D + c) : make_float4(0.f, 0.f, 0.f, 0.f);
       g[i] = c < D ? *reinterpret_cast<const float4*>(dy + r * D + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    float mean, rstd;
-    ln_stats(row, D, lane, mean, rstd, eps);
-    float sg = 0.f, sgx = 0.f;
+    // ONE pass, four sums reduced together (their shuffle chains interleave: one reduction latency instead of four
+    // dependent ones).  The row is shifted by its first element so that sum (x - k)^2 - (sum (x - k))^2 / D does not
+    // cancel when |mean| >> std;  sum g xhat = rstd (sum g x' - mean' sum g) with the same shifted values.
+    const float shift = __shfl_sync(0xffffffffu, row.v[0].x, 0);
+    float sx = 0.f, sxx = 0.f, sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int i = 0; i < TFM_LN_CHUNKS; ++i) {
+      const int c = lane * 4 + 128 * i;
+      if (c < D) {
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        float4& x = row.v[i];
+        x.x -= shift; x.y -= shift; x.z -= shift; x.w -= shift;
+        sx += (x.x + x.y) + (x.z + x.w);
+        sxx += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
+        const float4 gw = make_float4(g[i].x * w4.x, g[i].y * w4.y, g[i].z * w4.z, g[i].w * w4.w);
+        sg += (gw.x + gw.y) + (gw.z + gw.w);
+        sgx += (gw.x * x.x + gw.y * x.y) + (gw.z * x.z + gw.w * x.w);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sx += __shfl_xor_sync(0xffffffffu, sx, o);
+      sxx += __shfl_xor_sync(0xffffffffu, sxx, o);
+      sg += __shfl_xor_sync(0xffffffffu, sg, o);
+      sgx += __shfl_xor_sync(0xffffffffu, sgx, o);
+    }
+    const float inv_d = 1.f / (float)D;
+    const float mean = sx * inv_d;  // of the shifted row
+    const float rstd = rsqrtf(fmaxf(sxx * inv_d - mean * mean, 0.f) + eps);
+    const float mg = sg * inv_d, mgx = rstd * (sgx - mean * sg) * inv_d;
 #pragma unroll
     for (int i = 0; i < TFM_LN_CHUNKS; ++i) {
       const int c = lane * 4 + 128 * i;
@@ -227,11 +254,8 @@ tfm_ln_bwd_kernel(const float* __restrict__ s, const float* __restrict__ dy, lon
           ab[i].x += g[i].x; ab[i].y += g[i].y; ab[i].z += g[i].z; ab[i].w += g[i].w;
         }
         g[i].x *= w4.x; g[i].y *= w4.y; g[i].z *= w4.z; g[i].w *= w4.w;
-        sg += (g[i].x + g[i].y) + (g[i].z + g[i].w);
-        sgx += (g[i].x * x.x + g[i].y * x.y) + (g[i].z * x.z + g[i].w * x.w);
       }
     }
-    const float mg = warp_sum(sg) / (float)D, mgx = warp_sum(sgx) / (float)D;
 #pragma unroll
     for (int i = 0; i < TFM_LN_CHUNKS; ++i) {
       const int c = lane * 4 + 128 * i;
