@@ -327,7 +327,7 @@ int nrl_nrms_step_host(const long long* hist_ids_host, const long long* cand_ids
 
 /* ---- PLM news encoder internals ---------------------------------------
  * The transformer inside PLM.forward (encoders/news/text.py:67-73 constructor / freezing, :92
- * `self.plm_model(**text)[0]`): a HF RobertaModel / BertModel-shaped post-LN encoder -- embeddings
+ * `self.plm_model(**text)[0]`): a HF RobertaModel / BertModel post-LN encoder -- embeddings
  * (word + position + token type -> LayerNorm -> dropout) and `num_layers` layers of
  *   h1 = LN(x + drop(MHSA(x) W_ao + b)),   h2 = LN(h1 + drop(gelu(h1 W_i + b) W_o + b)),
  * key-padding mask from attention_mask, exact (erf) GELU, head dim 64, any T <= max_pos.
@@ -368,10 +368,13 @@ typedef struct {
   int num_layers;    /* layers handled by the call */
   int vocab;         /* config.vocab_size */
   int max_pos;       /* config.max_position_embeddings */
-  int pad_idx;       /* config.pad_token_id (RoBERTa position ids start at pad_idx + 1); < 0: positions 0..T-1 (BERT) */
+  int pad_idx;       /* config.pad_token_id: padding row of the word table (never updated) */
   float ln_eps;      /* config.layer_norm_eps */
   float hidden_dropout; /* config.hidden_dropout_prob (embeddings, attention output, layer output) */
   float attn_dropout;   /* config.attention_probs_dropout_prob */
+  int position_mode;    /* 0: RoBERTa (position ids = cumsum(ids != pad_idx) * (ids != pad_idx) + pad_idx, the position
+                           table's row pad_idx is a padding row); 1: BERT (position ids 0..T-1, no padding row in the
+                           position table).  pad_idx is the padding row of the WORD table in both modes. */
 } nrl_tfm_dims;
 
 /* packed bf16 hi/lo GEMM operands of the layers' weights (forward + transposed copies).  They

@@ -86,7 +86,7 @@ class TfmLayer(C.Structure):
 class TfmDims(C.Structure):
     _fields_ = [("hidden", C.c_int), ("heads", C.c_int), ("intermediate", C.c_int), ("num_layers", C.c_int),
                 ("vocab", C.c_int), ("max_pos", C.c_int), ("pad_idx", C.c_int), ("ln_eps", C.c_float),
-                ("hidden_dropout", C.c_float), ("attn_dropout", C.c_float)]
+                ("hidden_dropout", C.c_float), ("attn_dropout", C.c_float), ("position_mode", C.c_int)]
 
 
 PREC_BF16X3 = 0

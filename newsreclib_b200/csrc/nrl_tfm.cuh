@@ -358,12 +358,13 @@ tfm_embed_fwd_kernel(const long long* __restrict__ ids, const int* __restrict__ 
   }
 }
 // backward: g = dx0 (keep-bits applied) -> LN backward -> de; d_word[id] += de (padding_idx row skipped),
-// d_pos[pos] += de (its padding_idx row skipped), d_type[0] += sum de, dgamma / dbeta.
+// d_pos[pos] += de (RoBERTa: its padding_idx row skipped; BERT: pos_pad_idx = -1, every row), d_type[0] += sum de,
+// dgamma / dbeta.
 __global__ void __launch_bounds__(256)
 tfm_embed_bwd_kernel(const long long* __restrict__ ids, const int* __restrict__ pos, long long R,
                      const float* __restrict__ word, long long V, const float* __restrict__ pe, int P,
                      const float* __restrict__ type0, int D, const float* __restrict__ gamma, float eps,
-                     const uint32_t* __restrict__ words, int mw, float dscale, int pad_idx,
+                     const uint32_t* __restrict__ words, int mw, float dscale, int pad_idx, int pos_pad_idx,
                      const float* __restrict__ dx, float* __restrict__ d_word, float* __restrict__ d_pos,
                      float* __restrict__ d_type, float* __restrict__ dgamma, float* __restrict__ dbeta) {
   const int lane = threadIdx.x & 31;
@@ -411,7 +412,7 @@ tfm_embed_bwd_kernel(const long long* __restrict__ ids, const int* __restrict__ 
                                       rstd * (g[i].z - mg - x.z * mgx), rstd * (g[i].w - mg - x.w * mgx));
         at[i].x += de.x; at[i].y += de.y; at[i].z += de.z; at[i].w += de.w;
         if (ok && id != pad_idx) atomicAdd(reinterpret_cast<float4*>(d_word + id * D + c), de);
-        if (ok && p != pad_idx) atomicAdd(reinterpret_cast<float4*>(d_pos + (long long)p * D + c), de);
+        if (ok && p != pos_pad_idx) atomicAdd(reinterpret_cast<float4*>(d_pos + (long long)p * D + c), de);
       }
     }
   }

@@ -12,7 +12,7 @@
 //   x', xp' = LN2(s2)                    tfm_ln_fwd                 dWq/k/v += dqkv^T xp;  dx = dqkv Wqkv + ds1
 
 struct TfmDims {
-  int D, H, I, L, V, P, pad;
+  int D, H, I, L, V, P, pad, posmode;
   float eps, pdrop, padrop;
   int Dp, Ip, P3, LDQ, MW;
 };
@@ -27,6 +27,10 @@ static int make_tfm_dims(nrl_tfm_dims d, TfmDims& o) {
   if (d.hidden_dropout < 0.f || d.hidden_dropout >= 1.f || d.attn_dropout < 0.f || d.attn_dropout >= 1.f)
     return fail(NRL_ERR_INVALID_ARG, "dropout probabilities out of [0,1)");
   o.D = d.hidden; o.H = d.heads; o.I = d.intermediate; o.L = d.num_layers; o.V = d.vocab; o.P = d.max_pos;
+  if (d.position_mode != 0 && d.position_mode != 1)
+    return fail(NRL_ERR_INVALID_ARG, "position_mode must be 0 (RoBERTa) or 1 (BERT), got %d", d.position_mode);
+  if (d.pad_idx < 0 || d.pad_idx >= d.vocab) return fail(NRL_ERR_INVALID_ARG, "pad_idx %d outside the vocabulary", d.pad_idx);
+  o.posmode = d.position_mode;
   o.pad = d.pad_idx; o.eps = d.ln_eps; o.pdrop = d.hidden_dropout; o.padrop = d.attn_dropout;
   o.Dp = round_up(o.D + 1, 16);
   o.Ip = round_up(o.I + 1, 16);
@@ -275,8 +279,8 @@ int nrl_tfm_encoder_fwd(const long long* input_ids, const long long* attention_m
   Bump bp(const_cast<void*>(wpack));
   const DropCfg hdrop = make_drop(d.pdrop, training, seed), adrop = make_drop(d.padrop, training, seed);
   const bool two = c.two_planes();
-  tfm_prepare_kernel<<<grid_for(N, 8, 4 * g_dev.sm_count), 256, 0, c.stream>>>(input_ids, attention_mask, N, T, d.pad,
-                                                                            w.pos, w.kmask);
+  tfm_prepare_kernel<<<grid_for(N, 8, 4 * g_dev.sm_count), 256, 0, c.stream>>>(
+      input_ids, attention_mask, N, T, d.posmode == 0 ? d.pad : -1, w.pos, w.kmask);
   LAUNCH_CHECK("tfm prepare");
   if (hdrop.on) TRY(tfm_dropout_words(c, d, R, hdrop, seed, w.mask_e, w.mask_e1));
   float* x = w.xa;      // fp32 residual stream entering the layer
@@ -451,7 +455,8 @@ int nrl_tfm_encoder_bwd(const long long* input_ids, const long long* attention_m
       return fail(NRL_ERR_INVALID_ARG, "nrl_tfm_encoder_bwd: embeddings partly frozen (all 5 gradients or none)");
     tfm_embed_bwd_kernel<<<grid_for(R, 8, 8 * g_dev.sm_count), 256, 0, c.stream>>>(
         input_ids, w.pos, R, embed->word, d.V, embed->pos, d.P, embed->type0, d.D, embed->ln_g, d.eps,
-        hdrop.on ? w.mask_e : nullptr, d.MW, hdrop.scale, d.pad, dy, eg->word, eg->pos, eg->type0, eg->ln_g, eg->ln_b);
+        hdrop.on ? w.mask_e : nullptr, d.MW, hdrop.scale, d.pad, d.posmode == 0 ? d.pad : -1, dy, eg->word, eg->pos, eg->type0,
+        eg->ln_g, eg->ln_b);
     LAUNCH_CHECK("tfm embed_bwd");
   }
   return NRL_OK;

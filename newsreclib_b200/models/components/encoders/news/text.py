@@ -83,7 +83,7 @@ class PLM(nn.Module):
     ``text.py:70-73`` all unchanged) and ``self.plm_model(**text)[0]`` (``text.py:92``) runs on the sm_100a
     encoder (``ops.TfmEncoderFn``: embeddings, every layer's projections on tcgen05, key-padding-masked attention,
     LayerNorm / GELU / the three dropouts, forward and backward).  Architectures the kernels do not cover
-    (anything but RoBERTa-style post-LN layers with head dim 64, erf-GELU, absolute positions) raise;
+    (anything but RoBERTa / XLM-R / BERT post-LN layers with head dim 64, erf-GELU, absolute positions) raise;
     ``transformer_impl="hf"`` keeps the third-party torch module on the path instead."""
 
     def __init__(self, plm_model, frozen_layers, embed_dim: int, use_mhsa: bool, apply_reduce_dim: bool,
@@ -128,8 +128,8 @@ class PLM(nn.Module):
     def _native_state(self) -> "ops.TfmState":
         cfg = getattr(self.plm_model, "config", None)
         why = None
-        if cfg is None or getattr(cfg, "model_type", None) not in ("roberta", "xlm-roberta"):
-            why = f"model_type {getattr(cfg, 'model_type', None)!r} (RoBERTa-style models only)"
+        if cfg is None or getattr(cfg, "model_type", None) not in ("roberta", "xlm-roberta", "bert"):
+            why = f"model_type {getattr(cfg, 'model_type', None)!r} (RoBERTa / XLM-R / BERT only)"
         elif cfg.hidden_size != 64 * cfg.num_attention_heads:
             why = f"head dim {cfg.hidden_size // cfg.num_attention_heads} (64 only)"
         elif cfg.hidden_act != "gelu":
@@ -145,7 +145,8 @@ class PLM(nn.Module):
                              f"the HF torch module on the path")
         return ops.TfmState(cfg.hidden_size, cfg.num_attention_heads, cfg.intermediate_size, cfg.num_hidden_layers,
                             cfg.vocab_size, cfg.max_position_embeddings, cfg.pad_token_id, cfg.layer_norm_eps,
-                            cfg.hidden_dropout_prob, cfg.attention_probs_dropout_prob)
+                            cfg.hidden_dropout_prob, cfg.attention_probs_dropout_prob,
+                            position_mode=1 if cfg.model_type == "bert" else 0)
 
     def transformer_parameters(self):
         """The tensors ``ops.TfmEncoderFn`` takes, in ``_lib.TFM_EMBED_FIELDS`` + per-layer ``TFM_LAYER_FIELDS`` order."""

@@ -591,9 +591,10 @@ class TfmState:
     of a training step (history, candidates) therefore share one packing."""
 
     def __init__(self, hidden: int, heads: int, intermediate: int, num_layers: int, vocab: int, max_pos: int,
-                 pad_idx: int, ln_eps: float, hidden_dropout: float, attn_dropout: float):
+                 pad_idx: int, ln_eps: float, hidden_dropout: float, attn_dropout: float, position_mode: int = 0):
+        """``position_mode``: 0 = RoBERTa position ids (from the non-padding tokens), 1 = BERT (0..T-1)."""
         self.dims = TfmDims(int(hidden), int(heads), int(intermediate), int(num_layers), int(vocab), int(max_pos),
-                            int(pad_idx), float(ln_eps), float(hidden_dropout), float(attn_dropout))
+                            int(pad_idx), float(ln_eps), float(hidden_dropout), float(attn_dropout), int(position_mode))
         self.wpack: Optional[torch.Tensor] = None
         self.packed_key = [None] * int(num_layers)
         self.precision = None

@@ -32,9 +32,16 @@ def _drop(x, keep, p):
     return x * keep.to(x.dtype) / (1.0 - p)
 
 
-def embeddings(input_ids, P, pad_idx, eps, keep=None, p=0.0):
-    """RobertaEmbeddings.forward: (word + token_type[0]) + position -> LayerNorm -> dropout"""
+def embeddings(input_ids, P, pad_idx, eps, keep=None, p=0.0, bert=False):
+    """RobertaEmbeddings.forward: (word + token_type[0]) + position -> LayerNorm -> dropout.  ``bert=True``:
+    BertEmbeddings.forward (modeling_bert.py) -- position ids 0..T-1 and no padding row in the position table."""
     D = P["embeddings.word_embeddings.weight"].shape[1]
+    if bert:
+        e = F.embedding(input_ids, P["embeddings.word_embeddings.weight"], padding_idx=pad_idx)
+        e = e + P["embeddings.token_type_embeddings.weight"][0]
+        e = e + P["embeddings.position_embeddings.weight"][: input_ids.shape[1]][None]
+        e = F.layer_norm(e, (D,), P["embeddings.LayerNorm.weight"], P["embeddings.LayerNorm.bias"], eps)
+        return _drop(e, keep, p)
     # both tables are nn.Embedding(padding_idx=pad_token_id): row pad_idx is read but never receives a gradient
     e = F.embedding(input_ids, P["embeddings.word_embeddings.weight"], padding_idx=pad_idx)
     e = e + P["embeddings.token_type_embeddings.weight"][0]
@@ -67,11 +74,12 @@ def layer(x, key_mask, P, pre, heads, eps, masks=None, l=0, p_hidden=0.0, p_attn
     return F.layer_norm(t2 + h1, (D,), P[pre + "output.LayerNorm.weight"], P[pre + "output.LayerNorm.bias"], eps)
 
 
-def encoder(input_ids, attention_mask, P, heads, num_layers, pad_idx=1, eps=1e-5, masks=None, p_hidden=0.0, p_attn=0.0):
+def encoder(input_ids, attention_mask, P, heads, num_layers, pad_idx=1, eps=1e-5, masks=None, p_hidden=0.0, p_attn=0.0,
+            bert=False):
     """RobertaModel.forward(...)[0]: last hidden state [N, T, D].  ``masks``: {"embed": keep [N, T, D],
     ("attn_out", l) / ("out", l): keep [N, T, D], ("attn", l): keep [N, heads, T, T]} or None (eval)."""
     masks = masks or {}
-    x = embeddings(input_ids, P, pad_idx, eps, masks.get("embed"), p_hidden)
+    x = embeddings(input_ids, P, pad_idx, eps, masks.get("embed"), p_hidden, bert=bert)
     km = torch.ones_like(input_ids, dtype=torch.bool) if attention_mask is None else attention_mask.bool()
     for l in range(num_layers):
         x = layer(x, km, P, f"encoder.layer.{l}.", heads, eps, masks, l, p_hidden, p_attn)

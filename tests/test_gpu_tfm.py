@@ -21,7 +21,7 @@ def _report(tag, e_out, errs):
           f"{GRAD_TOL:.0e}); {len(errs)} gradient tensors" if k else f"[tfm] {tag}: hidden-state rel {e_out:.2e}")
 
 
-@pytest.mark.parametrize("name", ["tfm_tiny", "tfm_t40"])
+@pytest.mark.parametrize("name", ["tfm_tiny", "tfm_t40", "tfm_bert"])
 def test_tfm_matches_hf_golden(name):
     g, cfg, params, rgrads = load_tfm_golden(name)
     ids, att, w = torch.from_numpy(g["input_ids"]), torch.from_numpy(g["attention_mask"]), torch.from_numpy(g["w"])
@@ -32,8 +32,10 @@ def test_tfm_matches_hf_golden(name):
     assert e <= FWD_TOL
     assert set(grads) == set(rgrads)
     assert max(errs.values()) <= GRAD_TOL, max(errs.items(), key=lambda kv: kv[1])
-    assert float(grads["embeddings.word_embeddings.weight"][1].abs().max()) == 0.0  # padding_idx rows: exactly zero
-    assert float(grads["embeddings.position_embeddings.weight"][1].abs().max()) == 0.0
+    pad = 0 if cfg["bert"] else 1  # padding_idx rows: exactly zero (BERT: the word table only)
+    assert float(grads["embeddings.word_embeddings.weight"][pad].abs().max()) == 0.0
+    if not cfg["bert"]:
+        assert float(grads["embeddings.position_embeddings.weight"][1].abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("N,T,layers,frozen", [(24, 40, 2, (0,)), (10, 96, 2, ()), (6, 128, 1, ()), (33, 17, 3, (0, 1))])

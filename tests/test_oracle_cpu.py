@@ -319,7 +319,7 @@ def test_to_dense_batch_property_against_naive_loop():
 
 
 # ---- transformer restatement against the fixtures minted from HF RobertaModel -------------
-@pytest.mark.parametrize("name", ["tfm_tiny", "tfm_t40"])
+@pytest.mark.parametrize("name", ["tfm_tiny", "tfm_t40", "tfm_bert"])
 def test_tfm_oracle_matches_hf_golden(name):
     from tfm_helpers import grad_errors, load_tfm_golden, oracle_tfm
     g, cfg, params, rgrads = load_tfm_golden(name)
@@ -329,9 +329,14 @@ def test_tfm_oracle_matches_hf_golden(name):
     assert set(grads) == set(rgrads)  # the frozen layers get none, the embeddings do
     errs = grad_errors(grads, rgrads)
     assert max(errs.values()) <= 5e-4, max(errs.items(), key=lambda kv: kv[1])
-    # the padding rows of both embedding tables never receive a gradient (nn.Embedding(padding_idx=1))
-    assert float(grads["embeddings.word_embeddings.weight"][1].abs().max()) == 0.0
-    assert float(grads["embeddings.position_embeddings.weight"][1].abs().max()) == 0.0
+    # the padding rows never receive a gradient: RoBERTa nn.Embedding(padding_idx=1) for words AND positions; BERT
+    # padding_idx=0 for words only (its position table has no padding row)
+    pad = 0 if cfg["bert"] else 1
+    assert float(grads["embeddings.word_embeddings.weight"][pad].abs().max()) == 0.0
+    if not cfg["bert"]:
+        assert float(grads["embeddings.position_embeddings.weight"][1].abs().max()) == 0.0
+    else:
+        assert float(grads["embeddings.position_embeddings.weight"][0].abs().max()) > 0.0
 
 
 def test_tfm_oracle_position_ids_and_masking():

@@ -20,7 +20,7 @@ def load_tfm_golden(name):
     g = dict(np.load(os.path.join(GOLD, name + ".npz")))
     hidden, heads, inter, layers, vocab, N, T, max_pos = [int(x) for x in g["meta"]]
     cfg = dict(hidden=hidden, heads=heads, inter=inter, layers=layers, vocab=vocab, N=N, T=T, max_pos=max_pos,
-               eps=float(g["eps"]), frozen=[int(x) for x in g["frozen"]])
+               eps=float(g["eps"]), frozen=[int(x) for x in g["frozen"]], bert=bool(int(g["bert"])) if "bert" in g else False)
     params = {k[len("param/"):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("param/")}
     grads = {k[len("grad/"):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("grad/")}
     return g, cfg, params, grads
@@ -79,8 +79,9 @@ def gpu_tfm(P, cfg, ids, att, w=None, frozen=(), train_embed=True, training=Fals
             precision=None):
     """The CUDA path through ops.TfmEncoderFn -> the C ABI; returns out, {name: grad} (grads if w is given)."""
     from newsreclib_b200 import ops
-    st = ops.TfmState(cfg["hidden"], cfg["heads"], cfg["inter"], cfg["layers"], cfg["vocab"], cfg["max_pos"], 1,
-                      cfg["eps"], p_hidden, p_attn)
+    bert = bool(cfg.get("bert", False))
+    st = ops.TfmState(cfg["hidden"], cfg["heads"], cfg["inter"], cfg["layers"], cfg["vocab"], cfg["max_pos"], 0 if bert else 1,
+                      cfg["eps"], p_hidden, p_attn, position_mode=1 if bert else 0)
     leaves, names = param_list(P, cfg["layers"], "cuda", frozen, train_embed)
     out = ops.TfmEncoderFn.apply(ids.cuda(), None if att is None else att.cuda(), st, training, seed,
                                  ops.PREC_BF16X3 if precision is None else precision, *leaves)
@@ -103,8 +104,9 @@ def oracle_tfm(P, cfg, ids, att, w=None, frozen=(), train_embed=True, masks=None
         layer = int(k.split(".")[2]) if k.startswith("encoder.layer.") else -1
         rg = (layer >= 0 and layer not in frozen) or (layer < 0 and train_embed)
         Q[k] = v.detach().clone().to(dtype).requires_grad_(rg and w is not None)
-    out = TO.encoder(ids, att, Q, cfg["heads"], cfg["layers"], pad_idx=1, eps=cfg["eps"], masks=masks, p_hidden=p_hidden,
-                     p_attn=p_attn)
+    bert = bool(cfg.get("bert", False))
+    out = TO.encoder(ids, att, Q, cfg["heads"], cfg["layers"], pad_idx=0 if bert else 1, eps=cfg["eps"], masks=masks,
+                     p_hidden=p_hidden, p_attn=p_attn, bert=bert)
     grads = {}
     if w is not None:
         (out * w.to(dtype)).sum().backward()
