@@ -818,6 +818,37 @@ def main():
                 "kernel_ms_per_step": gemm_ms, "launches_per_step": gemm_launches,
                 "share_of_step": gemm_ms / step_prof_ms,
                 "top_kernels_ms_per_step": [[nm, round(t, 4), c] for t, nm, c in top]}
+        # every GEMM of the title block on its own (the longer of a name's two launches per step): algorithmic FLOP/s
+        # against the tensor peak (x issued passes = share of the pipe) AND algorithmic operand + result bytes against the
+        # HBM peak -- the 300-wide reductions of the out-projection / additive GEMMs sit left of the ridge
+        # (peak FLOP/s / peak B/s = 212 issued FLOP per byte): they are bound by their output bytes, not by the tensor pipe
+        planes = 2 if prec == ops.PREC_BF16X3 else 1
+        Ep_, Qp_, P3_, LDQ_ = (E + 1 + 15) // 16 * 16, (Q + 15) // 16 * 16, (3 * E + 15) // 16 * 16, (3 * E + 31) // 32 * 32
+        mwb = 4 * ((E + 31) // 32)
+        gemm_bytes = {"gemm in_proj": planes * 2 * Ep_ + 4 * LDQ_,
+                      "gemm out_proj": planes * 2 * Ep_ + 4 * E + planes * 2 * Ep_ + mwb,
+                      "gemm additive": planes * 2 * Ep_ + 4 * Q + 4,
+                      "gemm additive dgrad": planes * 2 * Qp_ + 4 + mwb + planes * 2 * Ep_,
+                      "gemm additive wgrad": planes * 2 * Qp_ + planes * 2 * Ep_,
+                      "gemm out_proj dgrad": planes * 2 * Ep_ + 4 * E,
+                      "gemm out_proj wgrad": planes * 2 * Ep_ + planes * 2 * Ep_,
+                      "gemm in_proj dgrad": planes * 2 * P3_ + 4 * E + mwb,
+                      "gemm in_proj wgrad": planes * 2 * P3_ + planes * 2 * Ep_}
+        per_gemm = []
+        for nm, f in GEMM_FLOPS.items():
+            d = per_launch.get(nm, [])
+            k = len(d) // prof_steps
+            if k < 1:
+                continue
+            ms = sum(max(d[i * k:(i + 1) * k]) for i in range(prof_steps)) / prof_steps
+            tf = rows_news * f() / (ms / 1e3) / 1e12
+            gbs = rows_news * gemm_bytes[nm] / (ms / 1e3) / 1e9
+            ft, fh = tf / tf_sust, gbs / hbm
+            per_gemm.append({"kernel": nm + " (title block)", "ms": round(ms, 4), "algorithmic_tflops": round(tf, 1),
+                             "frac_of_bf16_peak": round(ft, 3), "issued_frac": round(ft * roof["issued_passes"], 3),
+                             "algorithmic_gbs": round(gbs, 1), "frac_of_hbm_peak": round(fh, 3),
+                             "bound": "tensor" if ft * roof["issued_passes"] >= fh else "hbm"})
+        roof["per_gemm"] = per_gemm
 
     # HBM-bound kernels: algorithmic bytes per step (per token row of the title block /
     # user block; Adam per parameter) over the live per-launch durations of region B

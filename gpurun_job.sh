@@ -1,5 +1,13 @@
 mkdir -p gpurun_out
-timeout 900 ncu --profile-from-start off --set full --clock-control none -k regex:'pool|attn|gather|emb_grad|adam|dropout|dense|score|pack' -o /tmp/mem python profiles/ncu_step.py > gpurun_out/ncu_mem.log 2>&1; tail -2 gpurun_out/ncu_mem.log
-ncu -i /tmp/mem.ncu-rep --page raw --csv > gpurun_out/r02k_mem_raw.csv 2>/dev/null; wc -l gpurun_out/r02k_mem_raw.csv
-timeout 900 ncu --profile-from-start off --set full --clock-control none -k regex:'attn|pool' -o /tmp/head python profiles/ncu_plm_head.py > gpurun_out/ncu_head.log 2>&1; tail -2 gpurun_out/ncu_head.log
-ncu -i /tmp/head.ncu-rep --page raw --csv > gpurun_out/r02k_head_raw.csv 2>/dev/null; wc -l gpurun_out/r02k_head_raw.csv
+timeout 1500 python -m pytest tests -m gpu -q --timeout 900 2>&1 | tail -3 > gpurun_out/r02_final_pytest_gpu.log; cat gpurun_out/r02_final_pytest_gpu.log
+python __graft_entry__.py --smoke > gpurun_out/r02_final_smoke.log 2>&1; tail -2 gpurun_out/r02_final_smoke.log
+timeout 900 python bench.py --impl reference --steps 6 --warmup 3 > gpurun_out/r02_final_bench_reference_arm.json 2> gpurun_out/ref.err; tail -c 300 gpurun_out/r02_final_bench_reference_arm.json
+timeout 1200 python bench.py > gpurun_out/r02_final_bench.json 2> gpurun_out/r02_final_bench.err; tail -2 gpurun_out/r02_final_bench.err
+python - <<'PY'
+import json
+j=json.loads(open("gpurun_out/r02_final_bench.json").read())
+print(j["ms_per_step"], j["value"], j["e2e"]["value"], j["roofline"]["frac"], j["cpu_baseline"]["value"], j["gpu_launches"], j["clocks"])
+for k in j["roofline"]["per_gemm"]: print("  ", k)
+for k in j["hbm_kernels"]: print("  ", k["kernel"], k["ms_per_step"], k["frac_of_hbm_peak"])
+for k,v in j["configs"].items(): print(k, v.get("ms_per_step"), v.get("value"), v.get("error"))
+PY
