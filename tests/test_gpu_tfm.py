@@ -299,3 +299,32 @@ def test_naml_plm_module_native_transformer_vs_hf():
           f"differences {sorted(((round(v, 5), k) for k, v in errs.items()), reverse=True)[:3]}")
     for k, v in errs.items():
         assert v <= (6e-3 if k.endswith("additive_attention.linear.bias") else 2e-3), (k, v)
+
+
+def test_integration_md_transformer_stub_runs_as_written():
+    """The ctypes stub INTEGRATION.md shows for `PLM.forward` (text.py:92) is executed AS WRITTEN against the built
+    library and compared with the HF module it replaces."""
+    import ctypes as C
+    import re
+    from transformers import RobertaConfig, RobertaModel
+    from newsreclib_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    md = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = next(b for b in re.findall(r"```python\n(.*?)```", md, flags=re.S) if "def plm_last_hidden_state" in b)
+    ns = {"C": C, "torch": torch, "_nrl": C.CDLL(_lib.LIB_PATH)}
+    ns["_nrl"].nrl_last_error.restype = C.c_char_p
+    exec(block, ns)
+    torch.manual_seed(0)
+    tf = RobertaModel(RobertaConfig(vocab_size=90, hidden_size=128, num_hidden_layers=2, num_attention_heads=2,
+                                    intermediate_size=256, max_position_embeddings=24, pad_token_id=1, type_vocab_size=1),
+                      add_pooling_layer=False).cuda().eval()
+    ids, att = random_text(5, 17, 90, seed=3)
+    text = {"input_ids": ids.cuda(), "attention_mask": att.cuda()}
+
+    class Holder:
+        plm_model = tf
+    with torch.no_grad():
+        got = ns["plm_last_hidden_state"](Holder(), text)
+        ref = tf(**text)[0]
+    torch.cuda.synchronize()
+    assert rel_err(got, ref) <= 1e-4
