@@ -215,6 +215,23 @@ int nrl_ce_soft_fwd(const float* scores, const float* labels, const int* cand_of
 int nrl_ce_soft_bwd(const float* scores, const float* labels, const int* cand_off, int B,
                     int Cmax, const float* g_loss, float g_scale, float* d_scores, void* stream);
 
+/* ---- SupConLoss()(embeddings=scores, indices_tuple=...) , nrms_module.py:289-316 + components/losses.py:6-40 ----
+ * Supervised-contrastive loss over the dense [B, Cmax] score matrix (positives = real candidates with a non-zero
+ * label, negatives = real candidates with label 0, padded slots in neither set; per-row
+ * -mean_pos(log_softmax_kept(s / T)); mean over the rows whose loss is > 0 -- pytorch-metric-learning's
+ * AvgNonZeroReducer).  temperature: the reference always constructs SupConLoss() with its default 0.1
+ * (abstract_recommender.py:117-120).  row_loss [B] and stats [3] = {SupCon loss, rows counted, live flag} are saved for
+ * the backward.  ce_loss != NULL: `loss` = (1 - dual_loss_coef) * ce_loss[0] + dual_loss_coef * SupCon, the reference's
+ * dual loss (nrms_module.py:318-328); else `loss` = SupCon. */
+int nrl_supcon_fwd(const float* scores, const float* labels, const int* cand_off, int B, int Cmax,
+                   float temperature, const float* ce_loss, float dual_loss_coef, float* row_loss,
+                   float* loss, float* stats, void* stream);
+/* d_scores (+)= g_loss[0] * g_scale * dSupCon/dScores (g_loss may be NULL = 1; accumulate != 0 adds to d_scores, as
+ * the dual loss does after nrl_ce_soft_bwd) */
+int nrl_supcon_bwd(const float* scores, const float* labels, const int* cand_off, int B, int Cmax,
+                   float temperature, const float* row_loss, const float* stats, const float* g_loss,
+                   float g_scale, int accumulate, float* d_scores, void* stream);
+
 /* ---- torch.optim.Adam step (configs/model/nrms.yaml:49-52), dense over n elements --------- */
 int nrl_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr,
                   float beta1, float beta2, float eps, long long step, float grad_scale,

@@ -1366,6 +1366,28 @@ int nrl_ce_soft_bwd(const float* scores, const float* labels, const int* cand_of
   return NRL_OK;
 }
 
+int nrl_supcon_fwd(const float* scores, const float* labels, const int* cand_off, int B, int Cmax, float temperature,
+                   const float* ce_loss, float dual_loss_coef, float* row_loss, float* loss, float* stats,
+                   void* stream) {
+  if (!scores || !labels || !cand_off || !row_loss || !loss || !stats || B <= 0 || Cmax <= 0 || !(temperature > 0.f))
+    return fail(NRL_ERR_INVALID_ARG, "nrl_supcon_fwd: bad argument");
+  const int threads = B >= 32 ? 1024 : 32 * B;
+  supcon_fwd_kernel<<<1, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      scores, labels, cand_off, B, Cmax, 1.f / temperature, ce_loss, dual_loss_coef, row_loss, loss, stats);
+  LAUNCH_CHECK("supcon_fwd");
+  return NRL_OK;
+}
+int nrl_supcon_bwd(const float* scores, const float* labels, const int* cand_off, int B, int Cmax, float temperature,
+                   const float* row_loss, const float* stats, const float* g_loss, float g_scale, int accumulate,
+                   float* d_scores, void* stream) {
+  if (!scores || !labels || !cand_off || !row_loss || !stats || !d_scores || B <= 0 || Cmax <= 0 || !(temperature > 0.f))
+    return fail(NRL_ERR_INVALID_ARG, "nrl_supcon_bwd: bad argument");
+  supcon_bwd_kernel<<<(B + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      scores, labels, cand_off, B, Cmax, 1.f / temperature, row_loss, stats, g_loss, g_scale, accumulate, d_scores);
+  LAUNCH_CHECK("supcon_bwd");
+  return NRL_OK;
+}
+
 static int adam_impl(float* p, float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                      float eps, long long step, float grad_scale, int zero_grad, void* stream) {
   if (!p || !g || !m || !v || n <= 0 || step <= 0) return fail(NRL_ERR_INVALID_ARG, "nrl_adam_step: bad argument");

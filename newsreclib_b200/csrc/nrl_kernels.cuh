@@ -4,6 +4,8 @@
 // additive-attention pooling forward/backward, ragged<->dense, scorer, soft-target CE,
 // embedding-gradient scatter, Adam.
 #pragma once
+#include <cfloat>
+
 #include "nrl_ptx.cuh"
 
 namespace nrl {
@@ -1626,6 +1628,122 @@ __global__ void ce_bwd_kernel(const float* __restrict__ scores, const float* __r
     const float y = c < cnt ? labels[off[b] + c] : 0.f;
     const float pr = expf(scores[(long long)b * C + c] - mx) / se;
     d_scores[(long long)b * C + c] = g * (pr * sy - y);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// f4: supervised-contrastive loss over the dense score matrix (nrms_module.py:290-316 + components/losses.py:12-40 on
+// pytorch-metric-learning's SupConLoss; temperature is the constructor default 0.1, abstract_recommender.py:117-120).
+// Row b: positives = real slots with a non-zero label, negatives = real slots with label 0, padded slots in neither.
+//   x = s / T - max_c(s / T)   (maximum over ALL C slots, padded zeros included; detached)
+//   loss_b = -sum_pos (x - logsumexp_kept x) / (npos + FLT_MIN)
+// The batch loss is the mean over the rows with loss_b > 0 (AvgNonZeroReducer); zero when every index list of the
+// batch has at most one element, or there is no positive / no negative at all.  ONE CTA (the batch reduction is a
+// count of rows): warp w takes rows w, w + nwarps, ...   stats = {loss, rows counted, 1 if the batch loss is live}.
+// With `ce_loss` given the value written to `out_loss` is the dual loss (1 - coef) * CE + coef * SupCon
+// (nrms_module.py:326-328).
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ void supcon_row(const float* __restrict__ s, const float* __restrict__ y, int cnt, int C,
+                                           float inv_t, int lane, float& mx, float& lse, float& sum_pos, int& npos) {
+  mx = -INFINITY;
+  for (int c = lane; c < C; c += 32) mx = fmaxf(mx, s[c] * inv_t);
+  mx = warp_max(mx);
+  float m2 = -INFINITY;
+  for (int c = lane; c < cnt; c += 32) m2 = fmaxf(m2, s[c] * inv_t - mx);
+  m2 = warp_max(m2);
+  float se = 0.f;
+  sum_pos = 0.f;
+  npos = 0;
+  for (int c = lane; c < cnt; c += 32) {
+    const float x = s[c] * inv_t - mx;
+    se += expf(x - m2);
+    if (y[c] != 0.f) {
+      sum_pos += x;
+      ++npos;
+    }
+  }
+  se = warp_sum(se);
+  sum_pos = warp_sum(sum_pos);
+  npos = (int)warp_sum((float)npos);
+  lse = cnt > 0 ? m2 + logf(se) : 0.f;
+}
+
+__global__ void __launch_bounds__(1024)
+supcon_fwd_kernel(const float* __restrict__ scores, const float* __restrict__ labels, const int* __restrict__ off,
+                  int B, int C, float inv_t, const float* __restrict__ ce_loss, float coef,
+                  float* __restrict__ row_loss, float* __restrict__ out_loss, float* __restrict__ stats) {
+  __shared__ float s_sum[32], s_rows[32], s_pos[32], s_neg[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float sum = 0.f, rows = 0.f, tot_pos = 0.f, tot_neg = 0.f;
+  for (int b = warp; b < B; b += nw) {
+    const int cnt = min(off[b + 1] - off[b], C);
+    float mx, lse, sp;
+    int np;
+    supcon_row(scores + (long long)b * C, labels + off[b], cnt, C, inv_t, lane, mx, lse, sp, np);
+    // sum_pos (x - lse) = sum_pos x - npos * lse
+    const float l = -(sp - (float)np * lse) / ((float)np + FLT_MIN);
+    if (lane == 0) row_loss[b] = l;
+    if (l > 0.f) {
+      sum += l;
+      rows += 1.f;
+    }
+    tot_pos += (float)np;
+    tot_neg += (float)(cnt - np);
+  }
+  if (lane == 0) {
+    s_sum[warp] = sum;
+    s_rows[warp] = rows;
+    s_pos[warp] = tot_pos;
+    s_neg[warp] = tot_neg;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    sum = warp_sum(lane < nw ? s_sum[lane] : 0.f);
+    rows = warp_sum(lane < nw ? s_rows[lane] : 0.f);
+    tot_pos = warp_sum(lane < nw ? s_pos[lane] : 0.f);
+    tot_neg = warp_sum(lane < nw ? s_neg[lane] : 0.f);
+    if (lane == 0) {
+      const bool live = !(tot_pos <= 1.f && tot_neg <= 1.f) && tot_pos > 0.f && tot_neg > 0.f && rows > 0.f;
+      const float scl = live ? sum / rows : 0.f;
+      stats[0] = scl;
+      stats[1] = rows;
+      stats[2] = live ? 1.f : 0.f;
+      out_loss[0] = ce_loss ? (1.f - coef) * ce_loss[0] + coef * scl : scl;
+    }
+  }
+}
+// d s[b,c] = g / (rows * T) * (softmax_kept(x)[c] * npos / (npos + FLT_MIN) - [c positive] / (npos + FLT_MIN)) for the real
+// slots of the rows that were counted; everything else 0.  `accumulate` adds to d_scores (dual loss after ce_bwd).
+__global__ void supcon_bwd_kernel(const float* __restrict__ scores, const float* __restrict__ labels,
+                                  const int* __restrict__ off, int B, int C, float inv_t,
+                                  const float* __restrict__ row_loss, const float* __restrict__ stats,
+                                  const float* __restrict__ g_loss, float g_scale, int accumulate,
+                                  float* __restrict__ d_scores) {
+  const int lane = threadIdx.x & 31;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= B) return;
+  float* d = d_scores + (long long)b * C;
+  const bool counted = stats[2] != 0.f && row_loss[b] > 0.f;
+  if (!counted) {
+    if (!accumulate)
+      for (int c = lane; c < C; c += 32) d[c] = 0.f;
+    return;
+  }
+  const int cnt = min(off[b + 1] - off[b], C);
+  const float* s = scores + (long long)b * C;
+  const float* y = labels + off[b];
+  float mx, lse, sp;
+  int np;
+  supcon_row(s, y, cnt, C, inv_t, lane, mx, lse, sp, np);
+  const float g = (g_loss ? g_loss[0] : 1.f) * g_scale * inv_t / stats[1];
+  const float inv_np = 1.f / ((float)np + FLT_MIN);
+  for (int c = lane; c < C; c += 32) {
+    float v = 0.f;
+    if (c < cnt) {
+      const float pr = expf(s[c] * inv_t - mx - lse);
+      v = g * (pr * (float)np * inv_np - (y[c] != 0.f ? inv_np : 0.f));
+    }
+    d[c] = accumulate ? d[c] + v : v;
   }
 }
 

@@ -1,4 +1,5 @@
-"""Per-impression ranking metrics on device (AUC, MRR, nDCG@k) for the epoch-end hooks.
+"""Per-impression ranking metrics on device (AUC, MRR, nDCG@k) and the aspect-based diversity / personalization of the
+test epoch (``newsreclib/metrics/functional.py``) for the epoch-end hooks.
 
 The reference computes them with torchmetrics (``nrms_module.py:182-191``: ``AUROC(task="binary")`` over all
 candidates of the epoch, ``RetrievalMRR()`` and ``RetrievalNormalizedDCG(top_k=k)`` with ``indexes`` = the
@@ -63,4 +64,52 @@ def ranking_metrics(preds: torch.Tensor, targets: torch.Tensor, sizes: torch.Ten
         idcg = (ideal[:, :k] * disc[:, :k]).sum(1)
         out[f"ndcg@{k}"] = torch.where(idcg > 0, dcg / idcg.clamp_min(1e-12), torch.zeros_like(dcg)).mean()
     out["auc"] = binary_auroc(preds, targets)
+    return out
+
+
+def aspect_metrics(preds: torch.Tensor, sizes: torch.Tensor, cand_aspects: torch.Tensor, hist_aspects: torch.Tensor,
+                   hist_sizes: torch.Tensor, num_classes: int, top_k_list: List[int], name: str,
+                   per_impression: bool = False) -> Dict[str, torch.Tensor]:
+    """Aspect-based diversity ``D@k`` and personalization ``PS@k`` of the reference's test epoch
+    (``metrics/functional.py:8-49`` and ``:52-110`` through ``metrics/diversity.py`` / ``personalization.py``, logged at
+    ``nrms_module.py:494-522`` as ``{name}_div@k`` / ``{name}_pers@k`` with name = ``categ`` | ``sent``), for all
+    impressions at once:
+
+    * the k best-scored candidates of an impression -> histogram of their aspect ids over ``num_classes`` bins;
+    * diversity = entropy of that histogram (normalised to a distribution) / log(num_classes);
+    * personalization = generalised Jaccard ``sum(min) / sum(max)`` between that histogram and the histogram of the
+      aspects of the impression's clicked history;
+    * an impression whose candidate aspect ids sum to 0 counts 0.0 (``empty_target_action="neg"``,
+      ``metrics/base.py:160-170``); the result is the mean over all impressions.
+
+    preds / cand_aspects: concatenated per impression (``sizes``); hist_aspects likewise (``hist_sizes``).  One dense
+    sort and two scatter-adds; no loop over impressions."""
+    dev = preds.device
+    sizes, hist_sizes = sizes.to(dev).long(), hist_sizes.to(dev).long()
+    B, M = sizes.numel(), int(sizes.max())
+    valid = torch.arange(M, device=dev)[None, :] < sizes[:, None]
+    p = torch.full((B, M), float("-inf"), device=dev)
+    a = torch.zeros(B, M, dtype=torch.long, device=dev)
+    p[valid] = preds.float()
+    a[valid] = cand_aspects.to(dev).long()
+    order = p.argsort(dim=1, descending=True, stable=True)
+    a_sorted = a.gather(1, order)
+    has_target = a.sum(dim=1) != 0
+    hist_rows = torch.repeat_interleave(torch.arange(B, device=dev), hist_sizes)
+    hist_count = torch.zeros(B, num_classes, device=dev)
+    hist_count.index_put_((hist_rows, hist_aspects.to(dev).long()), torch.ones((), device=dev), accumulate=True)
+    log_c = torch.log(torch.tensor(float(num_classes), device=dev))
+    zero = torch.zeros(B, device=dev)
+    out = {}
+    for k in top_k_list:
+        kk = min(k, M)
+        take = valid[:, :kk].float()                     # ranks beyond the impression's own candidates do not count
+        count = torch.zeros(B, num_classes, device=dev).scatter_add_(1, a_sorted[:, :kk], take)
+        prob = count / count.sum(dim=1, keepdim=True).clamp_min(1.0)
+        ent = -(prob * torch.log(prob.clamp_min(torch.finfo(prob.dtype).tiny))).sum(dim=1)
+        div = torch.where(has_target, ent / log_c, zero)
+        jac = torch.minimum(count, hist_count).sum(dim=1) / torch.maximum(count, hist_count).sum(dim=1).clamp_min(1.0)
+        pers = torch.where(has_target, jac, zero)
+        out[f"{name}_div@{k}"] = div if per_impression else div.mean()
+        out[f"{name}_pers@{k}"] = pers if per_impression else pers.mean()
     return out

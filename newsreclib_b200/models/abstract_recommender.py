@@ -65,6 +65,23 @@ class CrossEntropySoft(nn.Module):
         return ops.CESoftFn.apply(scores, y_true.reshape(-1).float(), off)
 
 
+class SupConLoss(nn.Module):
+    """The reference's ``SupConLoss`` (``models/components/losses.py:6-40``, a pytorch-metric-learning subclass fed with
+    the score matrix and the positive / negative index tuples of ``nrms_module.py:290-307``) on the ragged layout:
+    positives are the real candidates with a non-zero label, negatives the real candidates with label 0.  The reference
+    always builds it with the default temperature (``abstract_recommender.py:117-120``)."""
+
+    def __init__(self, temperature: float = 0.1) -> None:
+        super().__init__()
+        self.temperature = temperature
+
+    def forward(self, scores: torch.Tensor, labels: torch.Tensor, cand_off: torch.Tensor) -> torch.Tensor:
+        from .. import ops
+        if self.temperature != ops.SupConFn.TEMPERATURE:
+            raise ValueError("the reference never passes a temperature to SupConLoss(): only the default 0.1 exists")
+        return ops.SupConFn.apply(scores, labels, cand_off, None)
+
+
 class AbstractRecommneder(_Base):  # sic: the reference's class name (abstract_recommender.py:14)
     def __init__(self, outputs: Dict[str, List[str]], optimizer, scheduler) -> None:
         super().__init__()
@@ -86,10 +103,52 @@ class AbstractRecommneder(_Base):  # sic: the reference's class name (abstract_r
         return torch.from_numpy(np.load(filepath)).float()
 
     def _get_loss(self, criterion: str) -> Union[Callable, Tuple[Callable, Callable]]:
+        # abstract_recommender.py:113-124
         if criterion == "cross_entropy_loss":
             return CrossEntropySoft()
-        raise ValueError(f"Loss not defined on the sm_100a path: {criterion} "
-                         "(the hot path implements cross_entropy_loss, configs/model/nrms.yaml:6)")
+        if criterion == "sup_con_loss":
+            return SupConLoss()
+        if criterion == "dual_loss":
+            return CrossEntropySoft(), SupConLoss()
+        raise ValueError(f"Loss not defined: {criterion}")
+
+    def _init_loss(self, loss: str, dual_loss_training: bool, dual_loss_coef) -> None:
+        """``nrms_module.py:113-119`` / ``naml_module.py`` (same lines)."""
+        self.loss_name, self.dual_loss_coef = loss, dual_loss_coef
+        if not dual_loss_training:
+            self.criterion = self._get_loss(loss)
+            if isinstance(self.criterion, tuple):
+                raise ValueError("loss='dual_loss' needs dual_loss_training=True (the reference would fail in model_step)")
+        else:
+            assert isinstance(dual_loss_coef, float)
+            assert loss == "dual_loss"
+            self.ce_criterion, self.scl_criterion = self._get_loss(loss)
+
+    def _loss(self, scores: torch.Tensor, labels: torch.Tensor, cand_off: torch.Tensor) -> torch.Tensor:
+        """``nrms_module.py:286-328`` on the ragged layout (labels ``[N_c]`` + candidate offsets)."""
+        from .. import ops
+        labels = labels.float().contiguous()
+        if self.loss_name == "cross_entropy_loss":
+            return ops.CESoftFn.apply(scores, labels, cand_off)
+        if self.loss_name == "sup_con_loss":
+            return self.criterion(scores, labels, cand_off)
+        return ops.SupConFn.apply(scores, labels, cand_off, float(self.dual_loss_coef))  # both kernels, one Function
+
+    def _get_recommendations(self, user_ids: torch.Tensor, news_ids: torch.Tensor, scores: torch.Tensor,
+                             cand_news_size: torch.Tensor) -> Dict[str, Dict[str, float]]:
+        """``abstract_recommender.py:150-181``: ``{"U<user id>": {"N<news id>": score, ...}, ...}`` -- one entry per user,
+        later impressions of the same user add to (and overwrite within) that user's dictionary."""
+        owner = torch.repeat_interleave(user_ids.detach().cpu(), cand_news_size.detach().cpu()).tolist()
+        recs: Dict[str, Dict[str, float]] = {}
+        for u, n, s in zip(owner, news_ids.detach().cpu().tolist(), scores.detach().cpu().tolist()):
+            recs.setdefault(f"U{u}", {})[f"N{n}"] = s
+        return recs
+
+    def _save_recommendations(self, recommendations: Dict[str, Dict[str, float]], fpath: str) -> None:
+        """``abstract_recommender.py:183-185``: one JSON file."""
+        import json
+        with open(fpath, "w") as f:
+            json.dump(recommendations, f)
 
     def _collect_model_outputs(self, vector: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
         # rows are concatenated in impression order: identical to boolean-mask indexing

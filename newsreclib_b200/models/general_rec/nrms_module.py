@@ -51,15 +51,8 @@ class NRMSModule(TwoTowerRecommender):
         self.num_sent_classes = num_sent_classes + 1
         if save_recs:
             assert isinstance(recs_fpath, str)
-            # the reference writes per-user recommendation lists and the diversity / personalization metrics in
-            # on_test_epoch_end (nrms_module.py:470-535): offline evaluation plumbing outside the hot path; refuse
-            # loudly instead of accepting the flag and silently not writing anything
-            raise NotImplementedError("save_recs=True (recommendation dumps + diversity / personalization metrics of the "
-                                      "reference's test epoch) is not implemented on the sm_100a path")
-        if dual_loss_training:
-            raise NotImplementedError("dual_loss_training (SupCon) is outside the hot path; "
-                                      "configs/model/nrms.yaml uses cross_entropy_loss")
-        self.criterion = self._get_loss(loss)
+        self.save_recs, self.recs_fpath = save_recs, recs_fpath
+        self._init_loss(loss, dual_loss_training, dual_loss_coef)
         if use_plm:
             # nrms_module.py:143-157: HF transformer + the MHSA / additive head (sm_100a)
             assert isinstance(plm_model, (str, torch.nn.Module))

@@ -11,7 +11,7 @@ import torch
 
 from ... import ops
 from ...data.components.batch import RecommendationBatch
-from ...metrics import ranking_metrics
+from ...metrics import aspect_metrics, ranking_metrics
 from ..abstract_recommender import AbstractRecommneder
 from ..components.layers.click_predictor import DotProduct
 
@@ -108,7 +108,7 @@ class TwoTowerRecommender(AbstractRecommneder):
         layout = self._layout(batch)
         B, off_h, off_c, Hmax, Cmax = layout
         scores = self._forward_with_layout(batch, layout)
-        loss = ops.CESoftFn.apply(scores, batch["labels"].float().contiguous(), off_c)
+        loss = self._loss(scores, batch["labels"], off_c)
         cand_news_size = (off_c[1:] - off_c[:-1]).long()
         hist_news_size = (off_h[1:] - off_h[:-1]).long()
         mask_cand = torch.arange(Cmax, device=scores.device)[None, :] < cand_news_size[:, None]
@@ -158,4 +158,29 @@ class TwoTowerRecommender(AbstractRecommneder):
         return loss
 
     def on_test_epoch_end(self):
-        return self._epoch_metrics(self.test_step_outputs, "test/")
+        """``nrms_module.py:470-535``: ranking metrics, aspect-based diversity / personalization over categories and
+        sentiments (when the test outputs carry them), and the recommendation dump of ``save_recs``."""
+        out = self.test_step_outputs
+        have = lambda *keys: all(k in out and len(out[k]) and torch.is_tensor(out[k][0]) for k in keys)
+        extra = {}
+        if have("preds", "cand_news_size", "hist_news_size"):
+            preds = self._gather_step_outputs(out, "preds")
+            sizes, hist_sizes = (self._gather_step_outputs(out, k) for k in ("cand_news_size", "hist_news_size"))
+            for name, cand_key, hist_key, classes in (("categ", "target_categories", "hist_categories", self.num_categ_classes),
+                                                      ("sent", "target_sentiments", "hist_sentiments", self.num_sent_classes)):
+                if have(cand_key, hist_key):
+                    m = aspect_metrics(preds, sizes, self._gather_step_outputs(out, cand_key),
+                                       self._gather_step_outputs(out, hist_key), hist_sizes, classes, self.top_k_list, name)
+                    extra.update({"test/" + k: v for k, v in m.items()})
+        if extra:
+            self.log_dict(extra, on_step=False, on_epoch=True, prog_bar=True, sync_dist=True)
+        if getattr(self, "save_recs", False):
+            if not have("user_ids", "cand_news_ids", "preds", "cand_news_size"):
+                raise ValueError("save_recs=True needs user_ids, cand_news_ids, preds and cand_news_size among the test outputs")
+            recs = self._get_recommendations(
+                user_ids=self._gather_step_outputs(out, "user_ids"), news_ids=self._gather_step_outputs(out, "cand_news_ids"),
+                scores=self._gather_step_outputs(out, "preds"), cand_news_size=self._gather_step_outputs(out, "cand_news_size"))
+            self._save_recommendations(recommendations=recs, fpath=self.recs_fpath)
+        m = self._epoch_metrics(out, "test/")
+        m.update(extra)
+        return m

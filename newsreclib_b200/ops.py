@@ -413,6 +413,50 @@ class CESoftFn(torch.autograd.Function):
         return d, None, None
 
 
+class SupConFn(torch.autograd.Function):
+    """``SupConLoss()`` on the score matrix (``nrms_module.py:289-316``, ``components/losses.py:6-40``) or, with
+    ``dual_loss_coef`` given, the dual loss ``(1 - coef) * CE + coef * SupCon`` (``nrms_module.py:318-328``)."""
+
+    TEMPERATURE = 0.1  # SupConLoss() default: the module's `temperature` hparam never reaches it (abstract_recommender.py:117-120)
+
+    @staticmethod
+    def forward(ctx, scores, labels, off, dual_loss_coef=None):
+        lib = _lib.load()
+        scores = _chk(scores.contiguous(), torch.float32, "scores")
+        labels = _chk(labels.contiguous(), torch.float32, "labels")
+        B, Cmax = scores.shape
+        buf = torch.empty(B + 4, dtype=torch.float32, device=scores.device)  # row losses, stats[3], CE
+        row, stats, ce = buf[:B], buf[B:B + 3], buf[B + 3:B + 4]
+        loss = torch.empty(1, dtype=torch.float32, device=scores.device)
+        if dual_loss_coef is not None:
+            _lib.check(lib.nrl_ce_soft_fwd(_p(scores), _p(labels), _p(off), B, Cmax, None, _p(ce), None, _stream()),
+                       "nrl_ce_soft_fwd")
+        _lib.check(lib.nrl_supcon_fwd(_p(scores), _p(labels), _p(off), B, Cmax, SupConFn.TEMPERATURE,
+                                      _p(ce) if dual_loss_coef is not None else None,
+                                      float(dual_loss_coef or 0.0), _p(row), _p(loss), _p(stats), _stream()),
+                   "nrl_supcon_fwd")
+        ctx.save_for_backward(scores, labels, off, buf)
+        ctx.coef = dual_loss_coef
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        scores, labels, off, buf = ctx.saved_tensors
+        B, Cmax = scores.shape
+        row, stats = buf[:B], buf[B:B + 3]
+        g = g.contiguous().float().reshape(1)
+        d = torch.empty_like(scores)
+        coef = ctx.coef
+        if coef is not None:
+            _lib.check(lib.nrl_ce_soft_bwd(_p(scores), _p(labels), _p(off), B, Cmax, _p(g), 1.0 - float(coef), _p(d),
+                                           _stream()), "nrl_ce_soft_bwd")
+        _lib.check(lib.nrl_supcon_bwd(_p(scores), _p(labels), _p(off), B, Cmax, SupConFn.TEMPERATURE, _p(row), _p(stats),
+                                      _p(g), 1.0 if coef is None else float(coef), 0 if coef is None else 1, _p(d),
+                                      _stream()), "nrl_supcon_bwd")
+        return d, None, None, None
+
+
 class AdditiveFn(torch.autograd.Function):
     """``AdditiveAttention.forward`` (``layers/attention.py:24-42``): x ``[G, L, D]`` -> ``[G, D]``."""
 

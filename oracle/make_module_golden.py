@@ -54,13 +54,14 @@ TITLE = "news_encoder.text_encoders.title."
 GRAD_STRIDE = 37
 
 
-def build_reference(params, late_fusion, tmpdir):
+def build_reference(params, late_fusion, tmpdir, loss="cross_entropy_loss", dual_loss_coef=None):
     emb = os.path.join(tmpdir, "emb.npy")
     np.save(emb, params[TITLE + "embedding_layer.weight"].numpy())
     m = NRMSModule(
         dataset_attributes=["title", "category"], attributes2encode=["title"], outputs=OUTPUTS,
-        dual_loss_training=False, dual_loss_coef=None, loss="cross_entropy_loss", late_fusion=late_fusion,
-        temperature=None, use_plm=False, pretrained_embeddings_path=emb, plm_model=None, frozen_layers=None,
+        dual_loss_training=loss == "dual_loss", dual_loss_coef=dual_loss_coef, loss=loss, late_fusion=late_fusion,
+        temperature=0.36 if loss != "cross_entropy_loss" else None,  # never reaches SupConLoss() (abstract_recommender.py:117-120)
+        use_plm=False, pretrained_embeddings_path=emb, plm_model=None, frozen_layers=None,
         embed_dim=300, num_heads=15, query_dim=200, dropout_probability=0.2, top_k_list=[5, 10],
         num_categ_classes=18, num_sent_classes=3, save_recs=False, recs_fpath=None,
         optimizer=functools.partial(torch.optim.Adam, lr=1e-4), scheduler=None)
@@ -75,11 +76,19 @@ def rel(a, b):
     return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
 
 
-def mint(name, V, B, max_hist, seed, late_fusion):
+def mint(name, V, B, max_hist, seed, late_fusion, criterion="cross_entropy_loss", dual_loss_coef=None, cand="train"):
     params = make_nrms_params(V, seed=seed)
-    batch = make_batch(B, V, hist="ragged", cand="train", seed=seed, max_hist=max_hist)
+    batch = make_batch(B, V, hist="ragged", cand=cand, seed=seed, max_hist=max_hist)
+    if criterion != "cross_entropy_loss":
+        # the SupCon index tuples (nrms_module.py:290-307) on rows the plain generator does not make: a row with
+        # several positives, a row with none (its loss is exactly 0 and AvgNonZeroReducer leaves it out), ragged
+        # candidate counts (padded slots are in neither the positive nor the negative set)
+        off = np.concatenate([[0], np.cumsum(np.bincount(batch["batch_cand"].numpy(), minlength=B))])
+        batch["labels"][off[1]:off[1] + 2] = 1.0
+        batch["labels"][off[1] + 2 + (off[2] - off[1] - 2) // 2] = 1.0
+        batch["labels"][off[2]:off[3]] = 0.0
     with tempfile.TemporaryDirectory() as tmp:
-        m = build_reference(params, late_fusion, tmp)
+        m = build_reference(params, late_fusion, tmp, criterion, dual_loss_coef)
     scores = m(batch)                                   # NRMSModule.forward, nrms_module.py:230-255
     out = m.model_step(batch)                           # nrms_module.py:260-362
     assert len(out) == 11
@@ -89,7 +98,7 @@ def mint(name, V, B, max_hist, seed, late_fusion):
     # the oracle's restatement of the same glue
     ps = {k: v.clone().requires_grad_(True) for k, v in params.items() if k in grads}
     o_scores = O.nrms_forward(batch, ps, 15, late_fusion=late_fusion)
-    o_loss = O.nrms_loss(batch, o_scores)
+    o_loss = O.nrms_loss(batch, o_scores, criterion, dual_loss_coef)
     o_loss.backward()
     assert o_scores.shape == scores.shape and rel(o_scores, scores) < 2e-6, rel(o_scores, scores)
     assert rel(o_loss, loss) < 2e-6
@@ -98,7 +107,7 @@ def mint(name, V, B, max_hist, seed, late_fusion):
     p64 = {k: v.double().clone().requires_grad_(True) for k, v in params.items() if k in grads}
     b64 = dict(batch)
     b64["labels"] = batch["labels"].double()
-    O.nrms_loss(b64, O.nrms_forward(b64, p64, 15, late_fusion=late_fusion)).backward()
+    O.nrms_loss(b64, O.nrms_forward(b64, p64, 15, late_fusion=late_fusion), criterion, dual_loss_coef).backward()
     for k, g in grads.items():
         og = ps[k].grad.clone() if ps[k].grad is not None else torch.zeros_like(ps[k])
         g64 = p64[k].grad.clone() if p64[k].grad is not None else torch.zeros_like(p64[k])
@@ -114,6 +123,19 @@ def mint(name, V, B, max_hist, seed, late_fusion):
     names = ["loss", "preds", "targets", "cand_news_size", "hist_news_size", "target_categories", "target_sentiments",
              "hist_categories", "hist_sentiments", "user_ids", "cand_news_ids"]
     rec = {"meta": np.array([300, 15, 200, V, B, max_hist, seed, 30, int(late_fusion)]), "scores": scores.detach().numpy()}
+    if criterion != "cross_entropy_loss":
+        rec["loss_name"] = np.array(criterion)
+        rec["dual_loss_coef"] = np.array(0.0 if dual_loss_coef is None else dual_loss_coef)
+        s_leaf = scores.detach().clone().requires_grad_(True)   # d loss / d scores of the reference's own criterion
+        O_y, O_mask = O.to_dense_batch(batch["labels"], batch["batch_cand"])
+        crit = (lambda s: m.criterion(embeddings=s, labels=None, indices_tuple=_indices(O_y, O_mask), ref_emb=None,
+                                      ref_labels=None)) if criterion == "sup_con_loss" else (
+            lambda s: (1 - dual_loss_coef) * m.ce_criterion(s, O_y) + dual_loss_coef * m.scl_criterion(
+                embeddings=s, labels=None, indices_tuple=_indices(O_y, O_mask), ref_emb=None, ref_labels=None))
+        l2 = crit(s_leaf)
+        assert rel(l2, out[0]) < 1e-6, (float(l2), float(out[0]))
+        l2.backward()
+        rec["d_scores"] = s_leaf.grad.numpy()
     for n, t in zip(names, out):
         rec["out/" + n] = t.detach().numpy()
     for k, g in grads.items():  # small tensors whole, big ones as every GRAD_STRIDE-th element (fixtures stay small)
@@ -128,6 +150,20 @@ def mint(name, V, B, max_hist, seed, late_fusion):
     golden_save(path, **rec)
     print(f"[{name}] reference NRMSModule.forward/model_step == oracle: scores rel {rel(o_scores, scores):.1e}, "
           f"loss rel {rel(o_loss, loss):.1e}; {os.path.getsize(path)} bytes")
+
+
+def _indices(y_true, mask_cand):
+    """The index tuples exactly as ``nrms_module.py:290-307`` builds them (used only to take d loss / d scores of the
+    reference's own criterion objects on the reference's own scores)."""
+    pos_idx = [torch.where(y_true[i])[0] for i in range(mask_cand.shape[0])]
+    pos_repeats = torch.tensor([len(pos_idx[i]) for i in range(len(pos_idx))])
+    q_p = torch.repeat_interleave(torch.arange(mask_cand.shape[0]), pos_repeats)
+    p = torch.cat(pos_idx)
+    neg_idx = [torch.where(~y_true[i].bool())[0][: len(torch.where(mask_cand[i])[0]) - pos_repeats[i]]
+               for i in range(mask_cand.shape[0])]
+    neg_repeats = torch.tensor([len(t) for t in neg_idx])
+    q_n = torch.repeat_interleave(torch.arange(mask_cand.shape[0]), neg_repeats)
+    return q_p, p, q_n, torch.cat(neg_idx)
 
 
 def naml_check(name="naml_mind"):
@@ -181,4 +217,8 @@ if __name__ == "__main__":
     torch.manual_seed(0)
     mint("nrms_module_ref", V=500, B=6, max_hist=9, seed=31, late_fusion=False)
     mint("nrms_module_ref_late_fusion", V=400, B=5, max_hist=7, seed=32, late_fusion=True)
+    # nrms_module.py:289-328 with the reference's own losses.py (over oracle/pml_standins.py)
+    mint("nrms_module_ref_supcon", V=400, B=6, max_hist=6, seed=33, late_fusion=False, criterion="sup_con_loss", cand="eval")
+    mint("nrms_module_ref_dual", V=400, B=6, max_hist=6, seed=34, late_fusion=False, criterion="dual_loss",
+         dual_loss_coef=0.3, cand="eval")
     naml_check()

@@ -217,10 +217,55 @@ def nrms_forward(
     return dot_product(u, cand_agg)  # :251-253
 
 
-def nrms_loss(batch: Dict, scores: Tensor) -> Tensor:
-    """``nrms_module.py:277,288``."""
-    y_true, _ = to_dense_batch(batch["labels"], batch["batch_cand"])
-    return ce_soft(scores, y_true)
+def sup_con_loss(scores: Tensor, y_true: Tensor, mask_cand: Tensor, temperature: float = 0.1) -> Tensor:
+    """Supervised-contrastive loss over the dense score matrix, ``nrms_module.py:290-316`` +
+    ``models/components/losses.py:12-40`` on top of pytorch-metric-learning 2.2.0 (``setup.py:26``; third-party, absent
+    from /root/reference and from this image: its pieces below are restated from the published source and are "parity
+    unpinned" by the reference -- ``oracle/make_module_golden.py`` runs the reference's OWN ``losses.py`` and
+    ``model_step`` over ``oracle/pml_standins.py`` and asserts this function reproduces them).
+
+    * index tuples (``nrms_module.py:291-307``): positives of row ``i`` = slots with a non-zero label; negatives = the
+      first ``count_i - npos_i`` slots whose label is zero -- real candidates come first in the dense row, so these are
+      exactly the real candidates with label 0; padded slots are in neither set;
+    * ``GenericPairLoss.compute_loss`` as overridden at ``losses.py:12-17``: zero loss when every index list has at most
+      one element; otherwise ``mat`` = the SCORES themselves (no distance), ``pos_mask[a1, p] = 1``,
+      ``neg_mask[a2, n] = 1`` (``mat_based_loss``);
+    * ``losses.py:19-40``: ``mat / temperature``, minus the detached row maximum (over ALL slots of the row, padded
+      zeros included), ``denominator = logsumexp`` over the kept (pos + neg) slots (``lmu.logsumexp``: the others are
+      filled with ``finfo.min``), ``-sum(pos * log_prob) / (npos + finfo.tiny)`` per row;
+    * reduction: ``SupConLoss.get_default_reducer() = AvgNonZeroReducer`` -- the mean over the rows whose loss is > 0
+      (rows without a positive give exactly 0 and are left out), zero when there is none.
+
+    ``abstract_recommender.py:117-120`` builds ``SupConLoss()`` with the DEFAULT temperature 0.1: the module's
+    ``temperature`` hyper-parameter never reaches it."""
+    pos = (y_true != 0) & mask_cand
+    neg = (y_true == 0) & mask_cand
+    n_pos, n_neg = int(pos.sum()), int(neg.sum())
+    if (n_pos <= 1 and n_neg <= 1) or n_pos == 0 or n_neg == 0:  # losses.py:14-15,20,40 -> zero_losses()
+        return (scores * 0).sum()
+    mat = scores / temperature
+    mat = mat - mat.max(dim=1, keepdim=True)[0].detach()
+    keep = pos | neg
+    denominator = torch.logsumexp(mat.masked_fill(~keep, torch.finfo(mat.dtype).min), dim=1, keepdim=True)
+    denominator = denominator.masked_fill(~keep.any(dim=1, keepdim=True), 0)
+    log_prob = mat - denominator
+    posf = pos.to(mat.dtype)
+    row = -(posf * log_prob).sum(dim=1) / (posf.sum(dim=1) + torch.finfo(mat.dtype).tiny)
+    sel = row > 0
+    return row[sel].mean() if bool(sel.any()) else (scores * 0).sum()
+
+
+def nrms_loss(batch: Dict, scores: Tensor, loss: str = "cross_entropy_loss",
+              dual_loss_coef: Optional[float] = None) -> Tensor:
+    """``nrms_module.py:277,286-328``: soft-target CE, SupCon, or their weighted average (``dual_loss``)."""
+    y_true, mask_cand = to_dense_batch(batch["labels"], batch["batch_cand"])
+    if loss == "cross_entropy_loss":
+        return ce_soft(scores, y_true)
+    scl = sup_con_loss(scores, y_true, mask_cand)
+    if loss == "sup_con_loss":
+        return scl
+    assert loss == "dual_loss" and dual_loss_coef is not None
+    return (1 - dual_loss_coef) * ce_soft(scores, y_true) + dual_loss_coef * scl
 
 
 # --------------------------------------------------------------------------------------

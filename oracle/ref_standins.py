@@ -11,8 +11,11 @@ can be installed (no network).  Only ONE of those imports takes part in the arit
 
 * ``lightning.LightningModule`` -> ``torch.nn.Module`` + ``save_hyperparameters`` (constructor arguments ->
   ``self.hparams``), a ``device`` property and no-op ``log`` / ``log_dict``;
-* ``torchmetrics`` metric classes, ``newsreclib.metrics.*`` and ``SupConLoss`` -> inert objects (constructed in
-  ``__init__``, never called by ``forward`` / ``model_step`` with the cross-entropy loss);
+* ``torchmetrics`` metric classes and ``newsreclib.metrics.*`` -> inert objects (constructed in ``__init__``, never
+  called by ``forward`` / ``model_step``);
+* ``pytorch_metric_learning`` -> ``oracle/pml_standins.py`` (restatement of the few published 2.2.0 pieces under the
+  reference's ``SupConLoss``), so the reference's own ``newsreclib/models/components/losses.py`` loads unmodified and
+  ``loss="sup_con_loss"`` / ``"dual_loss"`` run through the reference's own ``model_step`` (``nrms_module.py:290-328``);
 * ``torch_geometric.utils.to_dense_batch`` -> ``oracle.nrms_oracle.to_dense_batch``, the restatement of the published
   PyG 2.3.0 algorithm -- third-party, absent, "parity unpinned" for that one function.
 
@@ -108,5 +111,6 @@ def install(ref_root: str | None = None) -> str:
     _module("torchmetrics.retrieval", RetrievalMRR=Inert, RetrievalNormalizedDCG=Inert)
     _module("newsreclib.metrics.diversity", Diversity=Inert)
     _module("newsreclib.metrics.personalization", Personalization=Inert)
-    _module("newsreclib.models.components.losses", SupConLoss=Inert)
+    from oracle import pml_standins
+    pml_standins.install()  # the reference's own losses.py is imported on top of it
     return ref_root

@@ -53,13 +53,14 @@ def to_dev(batch, dev="cuda"):
     }
 
 
-def oracle_run(params, batch, H, masks=None, dropout_p=0.0, late_fusion=False, grad=True):
+def oracle_run(params, batch, H, masks=None, dropout_p=0.0, late_fusion=False, grad=True, loss_name="cross_entropy_loss",
+               dual_loss_coef=None):
     """Oracle forward (+ autograd backward) on CPU; returns scores, loss, grads."""
     from oracle import nrms_oracle as O
 
     ps = {k: v.clone().requires_grad_(grad) for k, v in params.items()}
     scores = O.nrms_forward(batch, ps, H, late_fusion=late_fusion, masks=masks, dropout_p=dropout_p)
-    loss = O.nrms_loss(batch, scores)
+    loss = O.nrms_loss(batch, scores, loss_name, dual_loss_coef)
     grads = None
     if grad:
         loss.backward()
@@ -190,6 +191,9 @@ def load_module_golden(name):
     ref = {"scores": torch.from_numpy(g["scores"]),
            "out": {n: torch.from_numpy(np.asarray(g["out/" + n])) for n in MODULE_OUT},
            "grad": {k[len("grad/"):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("grad/")}}
+    if "d_scores" in g:  # SupCon / dual-loss fixtures: the criterion's name, its coefficient, d loss / d scores
+        ref["loss_name"], ref["dual_loss_coef"] = str(g["loss_name"]), float(g["dual_loss_coef"])
+        ref["d_scores"] = torch.from_numpy(g["d_scores"])
     return params, batch, ref, dict(E=E, H=H, Q=Q, V=V, B=B, L=L, late_fusion=bool(late))
 
 

@@ -14,11 +14,11 @@ OUTPUTS = {"train": ["preds", "targets", "cand_news_size"], "val": ["preds", "ta
            "test": ["preds", "targets", "cand_news_size", "hist_news_size", "user_ids", "cand_news_ids"]}
 
 
-def make_module(params, late_fusion=False, p=0.2):
+def make_module(params, late_fusion=False, p=0.2, loss="cross_entropy_loss", dual_loss_coef=None):
     from newsreclib_b200.models.general_rec.nrms_module import NRMSModule
     m = NRMSModule(
         dataset_attributes=["title", "category"], attributes2encode=["title"], outputs=OUTPUTS,
-        dual_loss_training=False, dual_loss_coef=None, loss="cross_entropy_loss", late_fusion=late_fusion,
+        dual_loss_training=loss == "dual_loss", dual_loss_coef=dual_loss_coef, loss=loss, late_fusion=late_fusion,
         temperature=None, use_plm=False, pretrained_embeddings_path=None, plm_model=None, frozen_layers=None,
         embed_dim=300, num_heads=15, query_dim=200, dropout_probability=p, top_k_list=[5, 10],
         num_categ_classes=18, num_sent_classes=3, save_recs=False, recs_fpath=None,

@@ -57,3 +57,22 @@ def test_auroc_edge_cases():
     assert float(binary_auroc(torch.tensor([0.9, 0.1, 0.8, 0.2]), t)) == 0.0
     assert float(binary_auroc(torch.zeros(4), t)) == 0.5            # all tied: chance
     assert float(binary_auroc(torch.tensor([0.3, 0.7]), torch.zeros(2))) == 0.0   # no positive: defined as 0
+
+
+def test_aspect_metrics_match_reference_functional_golden():
+    """tests/golden/metrics_ref.npz = per-impression values of the reference's OWN diversity / personalization functions
+    (newsreclib/metrics/functional.py, oracle/make_metrics_golden.py), grouped as metrics/base.py:144-181 groups them."""
+    import os
+    from newsreclib_b200.metrics import aspect_metrics
+    g = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "metrics_ref.npz")))
+    t = lambda k: torch.from_numpy(g[k])
+    ncat, nsent = [int(x) for x in g["num_classes"]]
+    for name, cand, hist, nc in (("categ", "cat", "hcat", ncat), ("sent", "sent", "hsent", nsent)):
+        per = aspect_metrics(t("preds"), t("sizes"), t(cand), t(hist), t("hist_sizes"), nc, [5, 10], name, per_impression=True)
+        mean = aspect_metrics(t("preds"), t("sizes"), t(cand), t(hist), t("hist_sizes"), nc, [5, 10], name)
+        for k in (5, 10):
+            for kind in ("div", "pers"):
+                key = f"{name}_{kind}@{k}"
+                assert np.allclose(per[key].numpy(), g[key], atol=2e-6), key
+                assert float(mean[key]) == pytest.approx(float(g[key].mean()), abs=2e-6)
+    assert float(g["categ_div@5"][0]) == 0.0 and float(g["categ_pers@5"][0]) == 0.0   # the impression with aspect ids all 0

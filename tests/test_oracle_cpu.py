@@ -243,7 +243,8 @@ def test_device_table_padding_matches_reference_collate_golden():
         assert np.array_equal(np.asarray(news["nid"])[cand], ref["x_cand"]["news_ids"].numpy())
 
 
-@pytest.mark.parametrize("name", ["nrms_module_ref", "nrms_module_ref_late_fusion"])
+@pytest.mark.parametrize("name", ["nrms_module_ref", "nrms_module_ref_late_fusion", "nrms_module_ref_supcon",
+                                  "nrms_module_ref_dual"])
 def test_oracle_matches_reference_nrms_module_golden(name):
     """The fixtures hold what the reference's OWN NRMSModule.forward (nrms_module.py:230-255) and model_step (:260-362)
     returned (oracle/make_module_golden.py; only to_dense_batch is the restated PyG function): the oracle's glue must
@@ -252,10 +253,11 @@ def test_oracle_matches_reference_nrms_module_golden(name):
     params, batch, ref, meta = load_module_golden(name)
     lf = meta["late_fusion"]
     use = {k: v for k, v in params.items() if not (lf and k.startswith(USER))}
-    scores, loss, grads = oracle_run(use, batch, meta["H"], late_fusion=lf)
+    lk = dict(loss_name=ref.get("loss_name", "cross_entropy_loss"), dual_loss_coef=ref.get("dual_loss_coef"))
+    scores, loss, grads = oracle_run(use, batch, meta["H"], late_fusion=lf, **lk)
     assert scores.shape == ref["scores"].shape and rel_err(scores, ref["scores"]) <= 2e-6
     assert rel_err(loss, ref["out"]["loss"]) <= 2e-6
-    tols = grad_tolerances(use, batch, meta["H"], 2e-5, grads, late_fusion=lf)
+    tols = grad_tolerances(use, batch, meta["H"], 2e-5, grads, late_fusion=lf, **lk)
     for k, g in ref["grad"].items():
         if float(g.abs().max()) < 1e-9:
             continue  # mathematically zero gradient (key bias): rounding noise on both sides
@@ -274,6 +276,48 @@ def test_oracle_matches_reference_nrms_module_golden(name):
     assert torch.equal(out["hist_sentiments"], batch["x_hist"]["sentiment"])
     assert torch.equal(out["user_ids"], batch["user_ids"]) and torch.equal(out["cand_news_ids"], batch["x_cand"]["news_ids"])
     assert bool((ref["scores"][~mask] == 0).all())                          # padded slots score exactly 0.0
+
+
+@pytest.mark.parametrize("name", ["nrms_module_ref_supcon", "nrms_module_ref_dual"])
+def test_sup_con_oracle_matches_reference_criterion_golden(name):
+    """The SupCon / dual-loss fixtures hold the value and d loss / d scores of the reference's OWN criterion objects
+    (components/losses.py over oracle/pml_standins.py, index tuples of nrms_module.py:290-307) on the reference's own
+    scores: oracle.sup_con_loss must reproduce both from (scores, labels, segment ids) alone."""
+    from helpers import load_module_golden
+    _, batch, ref, meta = load_module_golden(name)
+    s = ref["scores"].clone().requires_grad_(True)
+    coef = ref["dual_loss_coef"] if ref["loss_name"] == "dual_loss" else None
+    loss = O.nrms_loss(batch, s, ref["loss_name"], coef)
+    loss.backward()
+    assert rel_err(loss.detach(), ref["out"]["loss"]) <= 1e-6
+    assert rel_err(s.grad, ref["d_scores"]) <= 1e-5
+    sizes = torch.bincount(batch["batch_cand"], minlength=meta["B"])
+    mask = torch.arange(s.shape[1])[None, :] < sizes[:, None]
+    assert len(set(sizes.tolist())) > 1                                     # ragged: padded slots exist
+    if ref["loss_name"] == "sup_con_loss":
+        assert bool((ref["d_scores"][~mask] == 0).all())                    # padded slots are in neither index set
+        y, _ = O.to_dense_batch(batch["labels"], batch["batch_cand"])
+        no_pos = y.sum(dim=1) == 0
+        assert bool(no_pos.any()) and bool((ref["d_scores"][no_pos] == 0).all())  # rows without a positive drop out
+
+
+def test_sup_con_oracle_zero_loss_cases():
+    """components/losses.py:14-15,20,40 -> zero_losses(): every index list has at most one element, or there is no
+    positive / no negative in the whole batch; and AvgNonZeroReducer with no row > 0."""
+    s = torch.randn(3, 4)
+    m = torch.tensor([[1, 1, 0, 0], [1, 0, 0, 0], [1, 1, 1, 0]], dtype=torch.bool)
+    assert float(O.sup_con_loss(s, torch.zeros(3, 4), m)) == 0.0                              # no positive at all
+    y = torch.tensor([[1., 1, 0, 0], [1, 0, 0, 0], [1, 1, 1, 0]])
+    assert float(O.sup_con_loss(s, y, m)) == 0.0                                              # no negative at all
+    m1 = torch.tensor([[1, 1, 0, 0], [0, 0, 0, 0], [0, 0, 0, 0]], dtype=torch.bool)
+    y1 = torch.tensor([[1., 0, 0, 0], [0, 0, 0, 0], [0, 0, 0, 0]])
+    assert float(O.sup_con_loss(s, y1, m1)) == 0.0                                            # one positive, one negative pair
+    y2 = torch.tensor([[1., 0, 0, 0], [0, 0, 0, 0], [0., 1, 0, 0]])
+    s2 = s.clone().requires_grad_(True)
+    l = O.sup_con_loss(s2, y2, m)
+    assert float(l) > 0
+    l.backward()
+    assert bool((s2.grad[1] == 0).all()) and bool((s2.grad[~m] == 0).all())
 
 
 def test_naml_fixture_is_what_the_reference_naml_module_returns():
