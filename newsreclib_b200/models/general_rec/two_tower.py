@@ -144,11 +144,22 @@ class TwoTowerRecommender(AbstractRecommneder):
     def validation_step(self, batch: RecommendationBatch, batch_idx: int):
         loss, preds, targets, cand_news_size, *_ = self.model_step(batch)
         self.log("val/loss", loss, on_step=False, on_epoch=True, prog_bar=True, sync_dist=True)
+        self._val_loss_sum = getattr(self, "_val_loss_sum", 0.0) + loss.detach()
+        self._val_loss_n = getattr(self, "_val_loss_n", 0) + 1
         self.val_step_outputs = self._collect_step_outputs(self.val_step_outputs, locals())
         return loss
 
     def on_validation_epoch_end(self):
-        return self._epoch_metrics(self.val_step_outputs, "val/")
+        m = self._epoch_metrics(self.val_step_outputs, "val/")
+        if getattr(self, "_val_loss_n", 0):
+            # nrms_module.py:412-424: the best (lowest) epoch-mean validation loss so far, logged as a plain value
+            epoch_loss = self._val_loss_sum / self._val_loss_n
+            best = getattr(self, "_val_loss_best", None)
+            self._val_loss_best = epoch_loss if best is None else torch.minimum(best, epoch_loss)
+            self._val_loss_sum, self._val_loss_n = 0.0, 0
+            self.log("val/loss_best", self._val_loss_best, sync_dist=True, prog_bar=True)
+            m["val/loss_best"] = self._val_loss_best
+        return m
 
     def test_step(self, batch: RecommendationBatch, batch_idx: int):
         (loss, preds, targets, cand_news_size, hist_news_size, target_categories, target_sentiments,

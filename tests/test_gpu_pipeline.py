@@ -141,3 +141,65 @@ def test_cached_eval_path_full_impression_size_vs_oracle():
         idcg = (np.sort(y)[::-1][:5] * disc[:5]).sum()
         nd5.append((ys[:5] * disc[:5]).sum() / idcg if idcg > 0 else 0.0)
     assert abs(float(met["mrr"]) - np.mean(mrr)) < 2e-3 and abs(float(met["ndcg@5"]) - np.mean(nd5)) < 2e-3
+
+
+def test_test_epoch_hooks_aspect_metrics_and_recommendation_dump(tmp_path):
+    """The reference's test stage (nrms_module.py:442-535): test_step over two batches, then on_test_epoch_end returns the
+    ranking metrics, categ/sent diversity and personalization @k (against a per-impression python loop over the module's
+    own scores) and, with save_recs=True, writes {"U<user>": {"N<news>": score}} (abstract_recommender.py:150-185)."""
+    import functools
+    import json
+    from helpers import TITLE
+    from test_gpu_modules import OUTPUTS, full_batch
+    from newsreclib_b200.models.general_rec.nrms_module import NRMSModule
+    from newsreclib_b200.synthetic import make_batch
+    V = 1500
+    params = make_nrms_params(V, seed=5)
+    outputs = dict(OUTPUTS)
+    outputs["test"] = OUTPUTS["test"] + ["target_categories", "target_sentiments", "hist_categories", "hist_sentiments"]
+    path = str(tmp_path / "recs.json")
+    m = NRMSModule(
+        dataset_attributes=["title", "category", "sentiment"], attributes2encode=["title"], outputs=outputs,
+        dual_loss_training=False, dual_loss_coef=None, loss="cross_entropy_loss", late_fusion=False, temperature=None,
+        use_plm=False, pretrained_embeddings_path=None, plm_model=None, frozen_layers=None, embed_dim=300, num_heads=15,
+        query_dim=200, dropout_probability=0.2, top_k_list=[5, 10], num_categ_classes=18, num_sent_classes=3,
+        save_recs=True, recs_fpath=path, optimizer=functools.partial(torch.optim.Adam, lr=1e-4), scheduler=None,
+        pretrained_embeddings=params[TITLE + "embedding_layer.weight"])
+    m.load_state_dict(params)
+    m = m.cuda().eval()
+    batches = [make_batch(7, V, hist="ragged", cand="eval", seed=s, max_hist=12) for s in (71, 72)]
+    with torch.no_grad():
+        for i, b in enumerate(batches):
+            m.test_step(full_batch(b), i)
+        scores = [m(full_batch(b)).cpu() for b in batches]
+    met = m.on_test_epoch_end()
+    for k in ("test/auc", "test/mrr", "test/ndcg@5", "test/categ_div@5", "test/categ_pers@10", "test/sent_div@10",
+              "test/sent_pers@5"):
+        assert k in met and 0.0 <= float(met[k]) <= 1.0, k
+    # per-impression loop over the same scores (definitions of metrics/functional.py:8-49,52-110)
+    div5, pers10, recs = [], [], {}
+    for b, sc in zip(batches, scores):
+        B = 7
+        cs, hs = torch.bincount(b["batch_cand"], minlength=B), torch.bincount(b["batch_hist"], minlength=B)
+        co, ho = np.concatenate([[0], np.cumsum(cs.numpy())]), np.concatenate([[0], np.cumsum(hs.numpy())])
+        for i in range(B):
+            s = sc[i, :cs[i]].numpy()
+            cat = b["x_cand"]["category"][co[i]:co[i + 1]].numpy()
+            order = np.argsort(-s, kind="stable")
+            c5 = np.bincount(cat[order][:5], minlength=19).astype(np.float64)
+            p = c5 / c5.sum()
+            div5.append(float(-(p[p > 0] * np.log(p[p > 0])).sum() / np.log(19)))
+            c10 = np.bincount(cat[order][:10], minlength=19)
+            h = np.bincount(b["x_hist"]["category"][ho[i]:ho[i + 1]].numpy(), minlength=19)
+            pers10.append(float(np.minimum(c10, h).sum() / np.maximum(c10, h).sum()))
+            d = recs.setdefault(f"U{int(b['user_ids'][i])}", {})
+            for n, v in zip(b["x_cand"]["news_ids"][co[i]:co[i + 1]].tolist(), s.tolist()):
+                d[f"N{n}"] = v
+    assert abs(float(met["test/categ_div@5"]) - np.mean(div5)) < 1e-5
+    assert abs(float(met["test/categ_pers@10"]) - np.mean(pers10)) < 1e-5
+    got = json.load(open(path))
+    assert set(got) == set(recs)
+    for u in recs:
+        assert set(got[u]) == set(recs[u])
+        assert max(abs(got[u][n] - recs[u][n]) for n in recs[u]) < 1e-5
+    assert all(len(v) == 0 for v in m.test_step_outputs.values())          # cleared for the next epoch
