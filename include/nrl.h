@@ -342,6 +342,28 @@ int nrl_nrms_step_host(const long long* hist_ids_host, const long long* cand_ids
                        int do_backward, nrl_block_grads* news_grads, nrl_block_grads* user_grads,
                        float* d_table, void* ws, size_t ws_bytes, int precision, void* stream);
 
+/* The same end-to-end call split in two, so that the host can queue more work behind the step before it waits for the
+ * step's results (a training loop queues the gradient exchange + optimizer step there: the wait for the loss and the
+ * host->device copies of the NEXT batch then overlap it):
+ *   begin: copies the host inputs on `copy_stream` (NULL = on `stream`; a different stream lets the copies overlap what
+ *          is still running on `stream`), makes `stream` wait for them, enqueues the step and the copies of scores /
+ *          loss (and, when status_host != NULL, of the device-side input-check word) back to the host; does not wait.
+ *          Host buffers should be pinned (pageable memory makes the copies synchronous).  *ticket identifies the step.
+ *   end:   waits until the results of that step are in scores_host / loss_host, releases the ticket, and returns
+ *          NRL_ERR_INVALID_ARG when *status_host reports a device-side input violation (nrl_device_status semantics).
+ * A workspace may carry ONE step at a time: call end() before the next begin() on the same `ws`. */
+int nrl_nrms_step_host_begin(const long long* hist_ids_host, const long long* cand_ids_host,
+                             const long long* seg_hist_host, const long long* seg_cand_host,
+                             const float* labels_host, long long n_hist, long long n_cand, int L, int B,
+                             int Hmax, int Cmax, const float* table, long long V1,
+                             const nrl_block_params* news_params, const nrl_block_params* user_params,
+                             nrl_dims dims, int late_fusion, float dropout_p, int training,
+                             unsigned long long seed, float* scores_host, float* loss_host,
+                             int do_backward, nrl_block_grads* news_grads, nrl_block_grads* user_grads,
+                             float* d_table, void* ws, size_t ws_bytes, int precision, void* copy_stream,
+                             unsigned int* status_host, void* stream, void** ticket);
+int nrl_nrms_step_host_end(void* ticket);
+
 /* ---- PLM news encoder internals ---------------------------------------
  * The transformer inside PLM.forward (encoders/news/text.py:67-73 constructor / freezing, :92
  * `self.plm_model(**text)[0]`): a HF RobertaModel / BertModel post-LN encoder -- embeddings

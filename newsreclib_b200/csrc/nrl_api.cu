@@ -1693,15 +1693,17 @@ int nrl_nrms_step(const long long* hist_ids, const long long* cand_ids, const lo
                    user_grads, d_table);
 }
 
-int nrl_nrms_step_host(const long long* hist_ids_host, const long long* cand_ids_host,
-                       const long long* seg_hist_host, const long long* seg_cand_host,
-                       const float* labels_host, long long n_hist, long long n_cand, int L, int B,
-                       int Hmax, int Cmax, const float* table, long long V1,
-                       const nrl_block_params* news_params, const nrl_block_params* user_params,
-                       nrl_dims dims, int late_fusion, float dropout_p, int training,
-                       unsigned long long seed, float* scores_host, float* loss_host, int do_backward,
-                       nrl_block_grads* news_grads, nrl_block_grads* user_grads, float* d_table,
-                       void* ws, size_t ws_bytes, int precision, void* stream) {
+// host buffers -> staging area of `ws` (on copy_stream when given), the step on `stream`, results -> host buffers.
+// Nothing here waits for the device.
+static int nrms_step_host_enqueue(const long long* hist_ids_host, const long long* cand_ids_host,
+                                  const long long* seg_hist_host, const long long* seg_cand_host,
+                                  const float* labels_host, long long n_hist, long long n_cand, int L, int B, int Hmax,
+                                  int Cmax, const float* table, long long V1, const nrl_block_params* news_params,
+                                  const nrl_block_params* user_params, nrl_dims dims, int late_fusion, float dropout_p,
+                                  int training, unsigned long long seed, float* scores_host, float* loss_host,
+                                  int do_backward, nrl_block_grads* news_grads, nrl_block_grads* user_grads,
+                                  float* d_table, void* ws, size_t ws_bytes, int precision, void* copy_stream,
+                                  unsigned int* status_host, void* stream) {
   Dims d;
   TRY(make_dims(dims, d));
   TRY(nrms_check(n_hist, n_cand, L, B, Hmax, Cmax, table, V1, news_params, user_params, late_fusion, dropout_p));
@@ -1711,22 +1713,50 @@ int nrl_nrms_step_host(const long long* hist_ids_host, const long long* cand_ids
   TRY(device_init());
   TRY(check_common(ws, ws_bytes, nrl_nrms_ws_bytes(n_hist, n_cand, L, B, Hmax, Cmax, dims)));
   Ctx c{static_cast<cudaStream_t>(stream), precision};
+  cudaStream_t cs = copy_stream ? static_cast<cudaStream_t>(copy_stream) : c.stream;
   Bump b(ws);
   NrmsWs w;
   carve_nrms(b, n_hist, n_cand, L, B, Hmax, Cmax, d, w);
-  CUDA_TRY(cudaMemcpyAsync(w.ids, hist_ids_host, (size_t)n_hist * L * sizeof(long long), cudaMemcpyHostToDevice, c.stream));
-  CUDA_TRY(cudaMemcpyAsync(w.ids + n_hist * L, cand_ids_host, (size_t)n_cand * L * sizeof(long long), cudaMemcpyHostToDevice, c.stream));
-  CUDA_TRY(cudaMemcpyAsync(w.seg_h, seg_hist_host, (size_t)n_hist * sizeof(long long), cudaMemcpyHostToDevice, c.stream));
-  CUDA_TRY(cudaMemcpyAsync(w.seg_c, seg_cand_host, (size_t)n_cand * sizeof(long long), cudaMemcpyHostToDevice, c.stream));
+  CUDA_TRY(cudaMemcpyAsync(w.ids, hist_ids_host, (size_t)n_hist * L * sizeof(long long), cudaMemcpyHostToDevice, cs));
+  CUDA_TRY(cudaMemcpyAsync(w.ids + n_hist * L, cand_ids_host, (size_t)n_cand * L * sizeof(long long), cudaMemcpyHostToDevice, cs));
+  CUDA_TRY(cudaMemcpyAsync(w.seg_h, seg_hist_host, (size_t)n_hist * sizeof(long long), cudaMemcpyHostToDevice, cs));
+  CUDA_TRY(cudaMemcpyAsync(w.seg_c, seg_cand_host, (size_t)n_cand * sizeof(long long), cudaMemcpyHostToDevice, cs));
   if (labels_host)
-    CUDA_TRY(cudaMemcpyAsync(w.labels, labels_host, (size_t)n_cand * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+    CUDA_TRY(cudaMemcpyAsync(w.labels, labels_host, (size_t)n_cand * sizeof(float), cudaMemcpyHostToDevice, cs));
+  if (cs != c.stream) {  // the step waits for its inputs; whatever else is queued on `stream` (the optimizer step of the
+                         // previous batch) overlaps the copies
+    cudaEvent_t copied;
+    CUDA_TRY(cudaEventCreateWithFlags(&copied, cudaEventDisableTiming));
+    cudaError_t e = cudaEventRecord(copied, cs);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(c.stream, copied, 0);
+    cudaEventDestroy(copied);  // released once the recorded work has completed
+    CUDA_TRY(e);
+  }
   TRY(nrms_impl(c, d, w, w.ids, w.ids + n_hist * L, w.seg_h, w.seg_c, w.labels, n_hist, n_cand, L, B, Hmax,
                 Cmax, table, V1, news_params, user_params, late_fusion, make_drop(dropout_p, training, seed),
                 w.scores_dev, loss_host ? w.loss_dev : nullptr, do_backward, news_grads, user_grads, d_table));
   CUDA_TRY(cudaMemcpyAsync(scores_host, w.scores_dev, (size_t)B * Cmax * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
   if (loss_host)
     CUDA_TRY(cudaMemcpyAsync(loss_host, w.loss_dev, sizeof(float), cudaMemcpyDeviceToHost, c.stream));
-  CUDA_TRY(cudaStreamSynchronize(c.stream));
+  if (status_host)
+    CUDA_TRY(cudaMemcpyFromSymbolAsync(status_host, g_dev_error, sizeof(unsigned int), 0, cudaMemcpyDeviceToHost, c.stream));
+  return NRL_OK;
+}
+
+int nrl_nrms_step_host(const long long* hist_ids_host, const long long* cand_ids_host,
+                       const long long* seg_hist_host, const long long* seg_cand_host,
+                       const float* labels_host, long long n_hist, long long n_cand, int L, int B,
+                       int Hmax, int Cmax, const float* table, long long V1,
+                       const nrl_block_params* news_params, const nrl_block_params* user_params,
+                       nrl_dims dims, int late_fusion, float dropout_p, int training,
+                       unsigned long long seed, float* scores_host, float* loss_host, int do_backward,
+                       nrl_block_grads* news_grads, nrl_block_grads* user_grads, float* d_table,
+                       void* ws, size_t ws_bytes, int precision, void* stream) {
+  TRY(nrms_step_host_enqueue(hist_ids_host, cand_ids_host, seg_hist_host, seg_cand_host, labels_host, n_hist, n_cand, L,
+                             B, Hmax, Cmax, table, V1, news_params, user_params, dims, late_fusion, dropout_p, training,
+                             seed, scores_host, loss_host, do_backward, news_grads, user_grads, d_table, ws, ws_bytes,
+                             precision, nullptr, nullptr, stream));
+  CUDA_TRY(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
   {  // the stream is idle: surface a device-side input violation (bad token / segment ids) of this step
     unsigned int code = 0;
     CUDA_TRY(cudaMemcpyFromSymbol(&code, g_dev_error, sizeof(code)));
@@ -1735,6 +1765,56 @@ int nrl_nrms_step_host(const long long* hist_ids_host, const long long* cand_ids
       nrl_device_status(&dummy, stream);  // formats the message and clears the flag
       return NRL_ERR_INVALID_ARG;
     }
+  }
+  return NRL_OK;
+}
+
+struct StepTicket {
+  cudaEvent_t ready;
+  unsigned int* status_host;
+  void* stream;
+};
+
+int nrl_nrms_step_host_begin(const long long* hist_ids_host, const long long* cand_ids_host,
+                             const long long* seg_hist_host, const long long* seg_cand_host,
+                             const float* labels_host, long long n_hist, long long n_cand, int L, int B,
+                             int Hmax, int Cmax, const float* table, long long V1,
+                             const nrl_block_params* news_params, const nrl_block_params* user_params,
+                             nrl_dims dims, int late_fusion, float dropout_p, int training,
+                             unsigned long long seed, float* scores_host, float* loss_host, int do_backward,
+                             nrl_block_grads* news_grads, nrl_block_grads* user_grads, float* d_table,
+                             void* ws, size_t ws_bytes, int precision, void* copy_stream,
+                             unsigned int* status_host, void* stream, void** ticket) {
+  if (!ticket) return fail(NRL_ERR_INVALID_ARG, "nrl_nrms_step_host_begin: null ticket pointer");
+  *ticket = nullptr;
+  TRY(nrms_step_host_enqueue(hist_ids_host, cand_ids_host, seg_hist_host, seg_cand_host, labels_host, n_hist, n_cand, L,
+                             B, Hmax, Cmax, table, V1, news_params, user_params, dims, late_fusion, dropout_p, training,
+                             seed, scores_host, loss_host, do_backward, news_grads, user_grads, d_table, ws, ws_bytes,
+                             precision, copy_stream, status_host, stream));
+  cudaEvent_t ready;
+  CUDA_TRY(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+  cudaError_t e = cudaEventRecord(ready, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) {
+    cudaEventDestroy(ready);
+    CUDA_TRY(e);
+  }
+  *ticket = new StepTicket{ready, status_host, stream};
+  return NRL_OK;
+}
+
+int nrl_nrms_step_host_end(void* ticket) {
+  if (!ticket) return fail(NRL_ERR_INVALID_ARG, "nrl_nrms_step_host_end: null ticket");
+  StepTicket* t = static_cast<StepTicket*>(ticket);
+  cudaError_t e = cudaEventSynchronize(t->ready);
+  cudaEventDestroy(t->ready);
+  unsigned int* status_host = t->status_host;
+  void* stream = t->stream;
+  delete t;
+  CUDA_TRY(e);
+  if (status_host && *status_host) {
+    int dummy = 0;
+    nrl_device_status(&dummy, stream);  // formats the message and clears the flag (synchronises: error path only)
+    return NRL_ERR_INVALID_ARG;
   }
   return NRL_OK;
 }

@@ -282,9 +282,12 @@ class NRMSTrainer:
 
     def train_step_host(self, hb: Dict, B: int, Hmax: int, Cmax: int, scores_host: torch.Tensor,
                         loss_host: torch.Tensor, training: bool = True) -> None:
-        """End-to-end step from HOST buffers (``nrl_nrms_step_host``): ids / segment ids / labels
-        are copied host->device, the step runs, scores and loss are copied back and the stream is
-        synchronised; then the gradient exchange and the Adam update are enqueued."""
+        """End-to-end step from HOST buffers: ``nrl_nrms_step_host_begin`` copies ids / segment ids / labels host->device
+        on a copy stream and enqueues the step and the copies of scores and loss back; the gradient exchange and the
+        Adam update are enqueued behind it; only then does ``nrl_nrms_step_host_end`` wait for THIS step's scores and
+        loss.  The optimizer step therefore runs while the host waits, returns and stages the next batch (whose copies
+        overlap it on the copy stream).  ``NRL_E2E_SPLIT=0`` selects the one-call ``nrl_nrms_step_host`` (copy, step,
+        copy back, synchronise, then the optimizer step)."""
         lib = _lib.load()
         hist_ids, cand_ids = hb["x_hist"]["title"], hb["x_cand"]["title"]
         nh, L = hist_ids.shape
@@ -295,14 +298,27 @@ class NRMSTrainer:
         self._zero_grads()
         nb, ub = ops.block_struct(self.news_block), ops.block_struct(self.user_block)
         ng, ug = ops.block_struct(self.grad_pack[0]), ops.block_struct(self.grad_pack[1])
-        _lib.check(lib.nrl_nrms_step_host(
-            hist_ids.data_ptr(), cand_ids.data_ptr(), hb["batch_hist"].data_ptr(), hb["batch_cand"].data_ptr(),
-            hb["labels"].data_ptr(), nh, nc, L, B, Hmax, Cmax, self.table.data_ptr(), self.table.shape[0],
-            C.byref(nb), C.byref(ub), self.dims, int(self.late_fusion), float(self.dropout_p), int(training),
-            GradExchange.rank_seed(self.seed, self.rank, self.step_count), scores_host.data_ptr(), loss_host.data_ptr(), 1, C.byref(ng),
-            C.byref(ug), self.grad_pack[2].data_ptr(), self.ws.data_ptr(), self.ws.numel(), self.precision,
-            torch.cuda.current_stream().cuda_stream), "nrl_nrms_step_host")
-        self._finish()
+        args = (hist_ids.data_ptr(), cand_ids.data_ptr(), hb["batch_hist"].data_ptr(), hb["batch_cand"].data_ptr(),
+                hb["labels"].data_ptr(), nh, nc, L, B, Hmax, Cmax, self.table.data_ptr(), self.table.shape[0],
+                C.byref(nb), C.byref(ub), self.dims, int(self.late_fusion), float(self.dropout_p), int(training),
+                GradExchange.rank_seed(self.seed, self.rank, self.step_count), scores_host.data_ptr(),
+                loss_host.data_ptr(), 1, C.byref(ng), C.byref(ug), self.grad_pack[2].data_ptr(), self.ws.data_ptr(),
+                self.ws.numel(), self.precision)
+        stream = torch.cuda.current_stream().cuda_stream
+        if os.environ.get("NRL_E2E_SPLIT", "1") == "0":
+            _lib.check(lib.nrl_nrms_step_host(*args, stream), "nrl_nrms_step_host")
+            self._finish()
+            return
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._status_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        ticket = C.c_void_p()
+        _lib.check(lib.nrl_nrms_step_host_begin(*args, self._copy_stream.cuda_stream, self._status_host.data_ptr(),
+                                                stream, C.byref(ticket)), "nrl_nrms_step_host_begin")
+        try:
+            self._finish()
+        finally:
+            _lib.check(lib.nrl_nrms_step_host_end(ticket), "nrl_nrms_step_host_end")
 
     @torch.no_grad()
     def eval_forward(self, batch: Dict, B: int, Hmax: int, Cmax: int):

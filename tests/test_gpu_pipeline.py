@@ -203,3 +203,43 @@ def test_test_epoch_hooks_aspect_metrics_and_recommendation_dump(tmp_path):
         assert set(got[u]) == set(recs[u])
         assert max(abs(got[u][n] - recs[u][n]) for n in recs[u]) < 1e-5
     assert all(len(v) == 0 for v in m.test_step_outputs.values())          # cleared for the next epoch
+
+
+@pytest.mark.parametrize("split", ["1", "0"])
+def test_train_step_from_host_buffers_matches_device_resident_step(split, monkeypatch):
+    """The end-to-end call (host buffers in, scores + loss out): nrl_nrms_step_host_begin / _end with the optimizer step
+    queued between them (NRL_E2E_SPLIT=1, the default) and the one-call nrl_nrms_step_host (=0) against the
+    device-resident train_step on the same seeds: scores, loss and the parameters after three steps; then a token id
+    outside the table must come back as an error from the SAME call (device-side check word copied with the results)."""
+    from helpers import batch_sizes, to_dev
+    from newsreclib_b200 import ops
+    from newsreclib_b200.synthetic import make_batch
+    from newsreclib_b200.trainer import NRMSTrainer
+    monkeypatch.setenv("NRL_E2E_SPLIT", split)
+    V = 3000
+    params = make_nrms_params(V, seed=8)
+    batches = [make_batch(9, V, hist="ragged", cand="train", seed=80 + i, max_hist=14) for i in range(3)]
+    t_dev = NRMSTrainer(params, 15, dropout_p=0.2, seed=5)
+    t_host = NRMSTrainer(params, 15, dropout_p=0.2, seed=5)
+    pin = lambda b: {k: ({c: t.pin_memory() for c, t in v.items()} if isinstance(v, dict) else v.pin_memory())
+                     for k, v in to_dev(b, "cpu").items()}
+    for b in batches:
+        B, Hmax, Cmax = batch_sizes(b)
+        s_ref, l_ref = t_dev.train_step(to_dev(b), B, Hmax, Cmax)
+        scores_host, loss_host = torch.empty(B, Cmax).pin_memory(), torch.empty(1).pin_memory()
+        t_host.train_step_host(pin(b), B, Hmax, Cmax, scores_host, loss_host)
+        # results are on the host when the call returns: no synchronize here on purpose
+        assert rel_err(scores_host, s_ref.cpu()) <= 1e-5 and rel_err(loss_host, l_ref.cpu()) <= 1e-5
+    torch.cuda.synchronize()
+    # the two replicas differ by the summation order of the gradient atomics; Adam turns a gradient that is pure rounding
+    # noise (mathematically zero: the key third of in_proj_bias) into a +-lr move, so the criterion is the one of
+    # NRMSTrainer.probe_exchange: nearly every element identical to fp32 rounding, none further apart than 3 steps of lr
+    d = (t_host.flat - t_dev.flat).abs()
+    assert float((d > 1e-6).float().mean()) < 2e-3 and float(d.median()) < 1e-7 and float(d.max()) <= 3.5e-4
+    assert t_host.step_count == 3 and ops.device_status(raise_on_error=False) == 0
+    bad = pin(batches[0])
+    bad["x_cand"]["title"][0, 0] = V + 11
+    B, Hmax, Cmax = batch_sizes(batches[0])
+    with pytest.raises(RuntimeError, match="token id"):
+        t_host.train_step_host(bad, B, Hmax, Cmax, torch.empty(B, Cmax).pin_memory(), torch.empty(1).pin_memory())
+    assert ops.device_status(raise_on_error=False) == 0                      # reported once, then clear
