@@ -449,11 +449,18 @@ def extra_configs(args, dev, rank, world, exchange_mode, steps=15, warmup=3):
         ms = _timed_steps(lambda i: tr.train_step(bs[i % 4]), steps, warmup, dev, world)
         tr.check_status()
         r = imps(ms, B)
-        r.update(workload="NRMSModule.model_step + autograd backward + ModuleTrainer (flat fused Adam): the drop-in module path, "
-                          "headline workload")
+        r.update(workload="NRMSModule.model_step (one autograd node on nrl_nrms_step / nrl_nrms_step_bwd) + loss.backward() + "
+                          "ModuleTrainer (flat fused Adam, gradients accumulated in place): the drop-in module path, headline "
+                          "workload")
         if tr.peer_block is not None:
             torch.distributed.barrier()
             tr.peer_block.close()
+        if world == 1:  # the same module on the per-op autograd.Functions (ten nodes per step), as before the fused node
+            m = build()
+            m.fused_model_step = False
+            tr2 = ModuleTrainer(m, lr=1e-4, exchange="nccl")
+            r["per_op_functions"] = imps(_timed_steps(lambda i: tr2.train_step(bs[i % 4]), steps, warmup, dev, world), B)
+            del tr2, m
         if world == 1:  # stock torch.optim.Adam from the module's own configure_optimizers (what Lightning would call)
             m = build()
             opt = m.configure_optimizers()["optimizer"]

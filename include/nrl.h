@@ -329,6 +329,18 @@ int nrl_nrms_step(const long long* hist_ids, const long long* cand_ids, const lo
                   float* loss, int do_backward, nrl_block_grads* news_grads,
                   nrl_block_grads* user_grads, float* d_table, void* ws, size_t ws_bytes,
                   int precision, void* stream);
+/* The backward half alone, for callers whose framework asks for gradients later than the forward pass (an autograd
+ * backward()): continues a forward-only nrl_nrms_step (do_backward = 0) that ran with the SAME sizes, parameters,
+ * dropout configuration and workspace -- `ws` still holds the news / user vectors, offsets, ids, packed weights,
+ * keep-bit words and saved activations of that pass and must not have been touched in between.  g_loss [1] (device,
+ * NULL = 1.0) is d(objective) / d(loss), folded into d loss / d scores.  Gradients are accumulated (+=) exactly as by
+ * nrl_nrms_step(do_backward = 1); the two calls together launch the same kernels as that one call (the scorer twice). */
+int nrl_nrms_step_bwd(const float* labels, const float* g_loss, long long n_hist, long long n_cand, int L,
+                      int B, int Hmax, int Cmax, long long V1, const nrl_block_params* news_params,
+                      const nrl_block_params* user_params, nrl_dims dims, int late_fusion,
+                      float dropout_p, int training, unsigned long long seed,
+                      nrl_block_grads* news_grads, nrl_block_grads* user_grads, float* d_table, void* ws,
+                      size_t ws_bytes, int precision, void* stream);
 /* Same pass with HOST input buffers (pinned or pageable): copies ids / segments / labels to the
  * device staging area inside `ws`, runs nrl_nrms_step, copies scores and loss back to
  * scores_host / loss_host and synchronises the stream.  This is the end-to-end call. */

@@ -147,6 +147,8 @@ SIGNATURES = {
                            _I, _F, _I, _ULL, _VP, _VP, _I, _BP, _BP, _VP, _VP, _SZ, _I, _VP]),
     "nrl_nrms_step_host": (_I, [_VP, _VP, _VP, _VP, _VP, _LL, _LL, _I, _I, _I, _I, _VP, _LL, _BP, _BP, Dims,
                                 _I, _F, _I, _ULL, _VP, _VP, _I, _BP, _BP, _VP, _VP, _SZ, _I, _VP]),
+    "nrl_nrms_step_bwd": (_I, [_VP, _VP, _LL, _LL, _I, _I, _I, _I, _LL, _BP, _BP, Dims, _I, _F, _I, _ULL, _BP, _BP, _VP,
+                               _VP, _SZ, _I, _VP]),
     "nrl_nrms_step_host_begin": (_I, [_VP, _VP, _VP, _VP, _VP, _LL, _LL, _I, _I, _I, _I, _VP, _LL, _BP, _BP, Dims,
                                       _I, _F, _I, _ULL, _VP, _VP, _I, _BP, _BP, _VP, _VP, _SZ, _I, _VP, _VP, _VP,
                                       C.POINTER(C.c_void_p)]),

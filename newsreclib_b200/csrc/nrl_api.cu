@@ -1602,6 +1602,11 @@ size_t nrl_nrms_ws_bytes(long long n_hist, long long n_cand, int L, int B, int H
   return b.off + 1024;
 }
 
+static int nrms_tail(const Ctx& c, const Dims& d, NrmsWs& w, const float* labels, long long nh, long long nc, int L,
+                     int B, int Hmax, int Cmax, long long V1, const nrl_block_params* np, const nrl_block_params* up,
+                     int late_fusion, const DropCfg& drop, float* scores, float* loss, const float* g_loss,
+                     int do_backward, nrl_block_grads* ng, nrl_block_grads* ug, float* d_table);
+
 static int nrms_impl(const Ctx& c, const Dims& d, NrmsWs& w, const long long* hist_ids,
                      const long long* cand_ids, const long long* seg_hist, const long long* seg_cand,
                      const float* labels, long long nh, long long nc, int L, int B, int Hmax, int Cmax,
@@ -1620,7 +1625,6 @@ static int nrms_impl(const Ctx& c, const Dims& d, NrmsWs& w, const long long* hi
   // the operand copies of BOTH blocks' weights in one launch (the user block is packed while nothing depends on it)
   TRY(pack_weights(c, d, np, w.news, late_fusion ? nullptr : up, late_fusion ? nullptr : &w.user));
   TRY(news_fwd_impl(c, d, w.news, w.ids, N, L, table, V1, np, drop, w.news_vec, true));
-  const float* cand_vec = w.news_vec + nh * d.E;
   const long long Ru = (long long)B * Hmax;
   DropCfg nodrop = make_drop(0.f, 0, 0);
   if (!late_fusion) {
@@ -1636,13 +1640,28 @@ static int nrms_impl(const Ctx& c, const Dims& d, NrmsWs& w, const long long* hi
   if (do_backward && (!ng || (!late_fusion && !ug)))
     return fail(NRL_ERR_INVALID_ARG, "backward requested without gradient buffers");
   if (loss) CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(float), c.stream));
+  return nrms_tail(c, d, w, labels, nh, nc, L, B, Hmax, Cmax, V1, np, up, late_fusion, drop, scores, loss, nullptr,
+                   do_backward, ng, ug, d_table);
+}
+
+// Scorer + soft-target CE and, when do_backward, everything behind them.  Runs on the state the forward half left in the
+// workspace (news / user vectors, offsets, ids, packed weights, keep-bit words, the blocks' saved activations), so it is
+// also the whole of nrl_nrms_step_bwd.  g_loss (device, may be NULL = 1) scales d loss / d scores.
+static int nrms_tail(const Ctx& c, const Dims& d, NrmsWs& w, const float* labels, long long nh, long long nc, int L,
+                     int B, int Hmax, int Cmax, long long V1, const nrl_block_params* np, const nrl_block_params* up,
+                     int late_fusion, const DropCfg& drop, float* scores, float* loss, const float* g_loss,
+                     int do_backward, nrl_block_grads* ng, nrl_block_grads* ug, float* d_table) {
+  const long long N = nh + nc;
+  const float* cand_vec = w.news_vec + nh * d.E;
+  const long long Ru = (long long)B * Hmax;
+  DropCfg nodrop = make_drop(0.f, 0, 0);
   if (do_backward)
     // every row is overwritten below for well-formed segment ids; rows of malformed input (flagged by the device-side
     // checks) must not carry stale workspace bytes into the table gradient
     CUDA_TRY(cudaMemsetAsync(w.d_news, 0, (size_t)N * d.E * sizeof(float), c.stream));
   // scorer + soft-target CE (+ their backward) in one launch: CTA b owns impression b
   score_loss_kernel<<<B, 128, 2 * (size_t)Cmax * sizeof(float), c.stream>>>(
-      w.user_vec, cand_vec, labels, w.cand_off, B, Cmax, d.E, scores, loss, do_backward ? w.d_scores : nullptr,
+      w.user_vec, cand_vec, labels, w.cand_off, B, Cmax, d.E, scores, loss, g_loss, do_backward ? w.d_scores : nullptr,
       w.d_user, w.d_news + nh * d.E);
   LAUNCH_CHECK("score_loss");
   if (!do_backward) return NRL_OK;
@@ -1691,6 +1710,29 @@ int nrl_nrms_step(const long long* hist_ids, const long long* cand_ids, const lo
                    Cmax, table, V1, news_params, user_params, late_fusion,
                    make_drop(dropout_p, training, seed), scores, loss, do_backward, news_grads,
                    user_grads, d_table);
+}
+
+int nrl_nrms_step_bwd(const float* labels, const float* g_loss, long long n_hist, long long n_cand, int L, int B, int Hmax,
+                      int Cmax, long long V1, const nrl_block_params* news_params, const nrl_block_params* user_params,
+                      nrl_dims dims, int late_fusion, float dropout_p, int training, unsigned long long seed,
+                      nrl_block_grads* news_grads, nrl_block_grads* user_grads, float* d_table, void* ws,
+                      size_t ws_bytes, int precision, void* stream) {
+  Dims d;
+  TRY(make_dims(dims, d));
+  if (n_hist <= 0 || n_cand <= 0 || L <= 0 || B <= 0 || Hmax <= 0 || Cmax <= 0 || V1 <= 0)
+    return fail(NRL_ERR_INVALID_ARG, "nrl_nrms_step_bwd: empty batch or non-positive size");
+  if (!labels || !news_params || !news_grads || (!late_fusion && (!user_params || !user_grads)))
+    return fail(NRL_ERR_INVALID_ARG, "nrl_nrms_step_bwd: null pointer");
+  if (dropout_p < 0.f || dropout_p >= 1.f) return fail(NRL_ERR_INVALID_ARG, "dropout_p out of [0,1)");
+  TRY(device_init());
+  TRY(check_common(ws, ws_bytes, nrl_nrms_ws_bytes(n_hist, n_cand, L, B, Hmax, Cmax, dims)));
+  Ctx c{static_cast<cudaStream_t>(stream), precision};
+  Bump b(ws);
+  NrmsWs w;
+  carve_nrms(b, n_hist, n_cand, L, B, Hmax, Cmax, d, w);
+  return nrms_tail(c, d, w, labels, n_hist, n_cand, L, B, Hmax, Cmax, V1, news_params, user_params, late_fusion,
+                   make_drop(dropout_p, training, seed), w.scores_dev, nullptr, g_loss, 1, news_grads, user_grads,
+                   d_table);
 }
 
 // host buffers -> staging area of `ws` (on copy_stream when given), the step on `stream`, results -> host buffers.

@@ -1754,8 +1754,8 @@ __global__ void supcon_bwd_kernel(const float* __restrict__ scores, const float*
 __global__ void __launch_bounds__(128)
 score_loss_kernel(const float* __restrict__ user, const float* __restrict__ cand, const float* __restrict__ labels,
                   const int* __restrict__ off, int B, int C, int E, float* __restrict__ scores,
-                  float* __restrict__ loss_mean, float* __restrict__ d_scores, float* __restrict__ d_user,
-                  float* __restrict__ d_cand) {
+                  float* __restrict__ loss_mean, const float* __restrict__ g_loss, float* __restrict__ d_scores,
+                  float* __restrict__ d_user, float* __restrict__ d_cand) {
   extern __shared__ float sl_smem[];
   float* s_sc = sl_smem;       // [C] scores of this row
   float* s_ds = sl_smem + C;   // [C] d loss / d scores
@@ -1794,7 +1794,8 @@ score_loss_kernel(const float* __restrict__ user, const float* __restrict__ cand
       acc += y * (lz - s_sc[c]);
       if (d_scores) {
         const float pr = expf(s_sc[c] - mx) / se;
-        const float ds = (pr * sy - y) / (float)B;
+        float ds = (pr * sy - y) / (float)B;
+        if (g_loss) ds *= g_loss[0];
         s_ds[c] = ds;
         d_scores[(long long)b * C + c] = ds;
       }

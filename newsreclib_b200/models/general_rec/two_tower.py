@@ -103,16 +103,28 @@ class TwoTowerRecommender(AbstractRecommneder):
             user = ops.LateFusionFn.apply(hist, off_h, B)
         return DotProduct.ragged(user, cand, off_c, B, Cmax)
 
+    def _fused_step_inputs(self, batch):
+        """Parameters + configuration of ``ops.NrmsStepFn`` when this module is the plain NRMS configuration it covers,
+        else ``None`` (subclasses that have a fused step override this)."""
+        return None
+
     # ------------------------------------------------------------------ model_step (nrms_module.py:260-362)
     def model_step(self, batch: RecommendationBatch) -> Tuple[torch.Tensor, ...]:
         layout = self._layout(batch)
         B, off_h, off_c, Hmax, Cmax = layout
-        scores = self._forward_with_layout(batch, layout)
-        loss = self._loss(scores, batch["labels"], off_c)
+        fused = self._fused_step_inputs(batch)
+        if fused is not None:
+            # NRMS + cross-entropy: the whole differentiable part as ONE autograd node on the fused C calls (ops.NrmsStepFn)
+            params, cfg = fused
+            scores, loss = ops.NrmsStepFn.apply(*params, batch["x_hist"]["title"], batch["x_cand"]["title"], batch["batch_hist"],
+                                                batch["batch_cand"], batch["labels"], (B, Hmax, Cmax) + cfg)
+        else:
+            scores = self._forward_with_layout(batch, layout)
+            loss = self._loss(scores, batch["labels"], off_c)
         cand_news_size = (off_c[1:] - off_c[:-1]).long()
         hist_news_size = (off_h[1:] - off_h[:-1]).long()
-        mask_cand = torch.arange(Cmax, device=scores.device)[None, :] < cand_news_size[:, None]
-        preds = self._collect_model_outputs(scores, mask_cand)
+        # scores[mask_cand] (abstract_recommender.py:126-130) in ragged order, without the host sync of boolean indexing
+        preds = ops.dense_to_ragged(scores, off_c, int(batch["labels"].numel()))
         targets = batch["labels"]                      # ragged order == masked dense order
         target_categories = batch["x_cand"].get("category")
         target_sentiments = batch["x_cand"].get("sentiment")

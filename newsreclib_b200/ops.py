@@ -233,6 +233,70 @@ def nrms_step(batch: Dict, table: torch.Tensor, news_block, user_block, dims: Di
 # ----------------------------------------------------------------------------------------
 # autograd functions used by the drop-in modules
 # ----------------------------------------------------------------------------------------
+class NrmsStepFn(torch.autograd.Function):
+    """The differentiable part of ``NRMSModule.model_step`` (``nrms_module.py:230-255,277,288``: both news-encoder calls,
+    ragged->dense, user encoder or late fusion, scorer, soft-target CE) as ONE autograd node on the fused C calls:
+    ``forward`` = ``nrl_nrms_step`` without gradients (scores + loss; the workspace keeps every saved activation),
+    ``backward`` = ``nrl_nrms_step_bwd`` with ``d objective / d loss`` read on the device.  Same kernels as the fused
+    trainer step, so what a Lightning user drives (``training_step`` -> ``loss.backward()``) is the measured path and the
+    host issues two library calls per step instead of ten ``autograd.Function``s.
+
+    ``scores`` is returned for the metrics and is NOT differentiable here (a loss built from it needs the per-op path).
+    ``grad_targets``: ``None`` -> gradients are returned to autograd (fresh zeroed buffers; what DDP / any optimizer
+    expects); a list of 15 preallocated fp32 tensors (table, 7 title-block, 7 user-block or ``None``) -> the kernels
+    accumulate (``+=``) straight into them and autograd gets ``None`` (``ModuleTrainer``: its flat gradient buffer)."""
+
+    @staticmethod
+    def forward(ctx, table, nw_in, nb_in, nw_out, nb_out, nw_add, nb_add, nq, uw_in, ub_in, uw_out, ub_out, uw_add,
+                ub_add, uq, hist_ids, cand_ids, seg_h, seg_c, labels, cfg):
+        B, Hmax, Cmax, num_heads, late_fusion, dropout_p, training, seed, precision, grad_targets = cfg
+        news = [nw_in, nb_in, nw_out, nb_out, nw_add, nb_add, nq]
+        user = None if late_fusion else [uw_in, ub_in, uw_out, ub_out, uw_add, ub_add, uq]
+        dims = dims_of(table.shape[1], num_heads, nq.numel())
+        batch = {"x_hist": {"title": hist_ids.contiguous()}, "x_cand": {"title": cand_ids.contiguous()},
+                 "batch_hist": seg_h.contiguous(), "batch_cand": seg_c.contiguous(),
+                 "labels": labels.float().contiguous()}
+        scores, loss, ws = nrms_step(batch, table, news, user, dims, B=B, Hmax=Hmax, Cmax=Cmax, late_fusion=late_fusion,
+                                     dropout_p=dropout_p, training=training, seed=seed, precision=precision)
+        ctx.save_for_backward(table, *news, *(user or []), batch["labels"])
+        ctx.ws, ctx.dims, ctx.cfg = ws, dims, cfg
+        ctx.sizes = (hist_ids.shape[0], cand_ids.shape[0], hist_ids.shape[1])
+        ctx.mark_non_differentiable(scores)
+        return scores, loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, _g_scores, g_loss):
+        lib = _lib.load()
+        B, Hmax, Cmax, num_heads, late_fusion, dropout_p, training, seed, precision, grad_targets = ctx.cfg
+        if ctx.ws is None:
+            raise RuntimeError("NrmsStepFn: backward called twice (the saved activations live in a workspace that is "
+                               "released after the first backward; retain_graph is not supported on the fused step)")
+        saved = ctx.saved_tensors
+        table, news, labels = saved[0], list(saved[1:8]), saved[-1]
+        user = None if late_fusion else list(saved[8:15])
+        if grad_targets is None:
+            d_table = torch.zeros_like(table)
+            ng, ug = [torch.zeros_like(t) for t in news], (None if user is None else [torch.zeros_like(t) for t in user])
+        else:
+            d_table, ng, ug = grad_targets[0], list(grad_targets[1:8]), (None if user is None else list(grad_targets[8:15]))
+            for t, p in zip([d_table] + ng + (ug or []), [table] + news + (user or [])):
+                if t is None or t.shape != p.shape or t.dtype != torch.float32 or not t.is_contiguous() or t.device != p.device:
+                    raise RuntimeError("NrmsStepFn: grad_targets must be contiguous fp32 tensors shaped like the parameters")
+        g = g_loss.detach().float().reshape(1).contiguous()
+        nh, nc, L = ctx.sizes
+        nb, ub = block_struct(news), (block_struct(user) if user is not None else None)
+        ngs, ugs = block_struct(ng), (block_struct(ug) if ug is not None else None)
+        _lib.check(lib.nrl_nrms_step_bwd(
+            _p(labels), _p(g), nh, nc, L, B, Hmax, Cmax, table.shape[0], C.byref(nb),
+            C.byref(ub) if ub is not None else None, ctx.dims, int(late_fusion), float(dropout_p), int(training),
+            int(seed), C.byref(ngs), C.byref(ugs) if ugs is not None else None, _p(d_table), _p(ctx.ws),
+            ctx.ws.numel(), precision, _stream()), "nrl_nrms_step_bwd")
+        ctx.ws = None
+        if grad_targets is not None:
+            return (None,) * 21
+        return (d_table, *ng, *(ug if ug is not None else [None] * 7), None, None, None, None, None, None)
+
+
 class NewsEncoderFn(torch.autograd.Function):
     """``MHSAAddAtt.forward`` (reference ``encoders/news/text.py:222-236``)."""
 
@@ -331,6 +395,19 @@ class ToDenseFn(torch.autograd.Function):
         dx = torch.zeros(n, E, dtype=torch.float32, device=d_dense.device)
         _lib.check(lib.nrl_to_dense_bwd(_p(d_dense), _p(off), B, M, E, _p(dx), _stream()), "nrl_to_dense_bwd")
         return dx, None, None, None
+
+
+def dense_to_ragged(dense: torch.Tensor, off: torch.Tensor, n: int) -> torch.Tensor:
+    """Rows of a dense ``[B, M]`` / ``[B, M, E]`` batch back in ragged order (``[n]`` / ``[n, E]``): what boolean-mask
+    indexing ``dense[mask]`` returns (``abstract_recommender.py:126-130``), without the host sync of ``nonzero`` -- the
+    number of rows is known from the batch.  No gradient (used for the metric outputs)."""
+    lib = _lib.load()
+    dense = _chk(dense.detach().contiguous(), torch.float32, "dense")
+    B, M = dense.shape[0], dense.shape[1]
+    E = 1 if dense.dim() == 2 else dense.shape[2]
+    out = torch.zeros((n,) if dense.dim() == 2 else (n, E), dtype=torch.float32, device=dense.device)
+    _lib.check(lib.nrl_to_dense_bwd(_p(dense), _p(off), B, M, E, _p(out), _stream()), "nrl_to_dense_bwd")
+    return out
 
 
 class LateFusionFn(torch.autograd.Function):

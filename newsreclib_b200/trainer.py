@@ -379,6 +379,10 @@ class ModuleTrainer:
             self.flat[o:o + n].copy_(p.data.reshape(-1))
             p.data = self.flat[o:o + n].view_as(p)
             p.grad = self.grad[o:o + n].view_as(p)  # autograd accumulates in place into the flat buffer
+        if hasattr(module, "grad_targets"):
+            # modules whose model_step is one fused autograd node (NRMSModule -> ops.NrmsStepFn) let the kernels
+            # accumulate straight into these views: no zeroed copy of the table gradient, no AccumulateGrad pass
+            module.grad_targets = "param.grad"
         self.lr, self.betas, self.eps = lr, betas, eps
         self.step_count = 0
         self.exchange_epoch = 0

@@ -116,3 +116,48 @@ def test_component_interfaces():
     assert rel_err(add(x), ref) <= 1e-4
     u, c = torch.randn(6, 1, 300).cuda(), torch.randn(6, 300, 9).cuda()
     assert rel_err(DotProduct()(u, c), torch.bmm(u, c).squeeze(1)) <= 1e-5
+
+
+@pytest.mark.parametrize("late_fusion", [False, True])
+def test_fused_model_step_node_matches_per_op_functions(late_fusion):
+    """NRMSModule.model_step as ONE autograd node (ops.NrmsStepFn: nrl_nrms_step forward, nrl_nrms_step_bwd backward) against
+    the same module on the per-op autograd.Functions: eval mode and train mode (same CPU-RNG seed -> same keep-bit words),
+    a scaled objective (d objective / d loss is read on the device), direct accumulation into preallocated .grad
+    buffers (what ModuleTrainer uses), and a second backward refusing loudly."""
+    V = 1800
+    params = make_nrms_params(V, seed=13)
+    use = {k: v for k, v in params.items() if not (late_fusion and not k.startswith(TITLE))}
+    batch = full_batch(make_batch(10, V, hist="ragged", cand="train", seed=13, max_hist=12))
+
+    def run(fused, train, scale=1.0, direct=False):
+        m = make_module(params, late_fusion=late_fusion)
+        m.load_state_dict(use, strict=True)
+        m = m.cuda()
+        m.train(train)
+        m.fused_model_step = fused
+        if direct:
+            for p in m.parameters():
+                p.grad = torch.full_like(p, 0.25)          # accumulation (+=) into what is already there
+            m.grad_targets = "param.grad"
+        torch.manual_seed(3)
+        out = m.model_step(batch)
+        (out[0] * scale).backward()
+        grads = {k: p.grad.clone() - (0.25 if direct else 0.0) for k, p in m.named_parameters()}
+        return m, out, grads
+
+    for train in (True, False):
+        _, ref_out, ref_g = run(False, train)
+        m, out, g = run(True, train)
+        assert len(out) == 11 and not out[1].requires_grad
+        assert rel_err(out[0].detach(), ref_out[0].detach()) <= 1e-5 and rel_err(out[1], ref_out[1].detach()) <= 1e-5
+        worst = max(rel_err(g[k], ref_g[k]) for k in ref_g if float(ref_g[k].abs().max()) > 1e-9)
+        print(f"fused model_step vs per-op Functions (late_fusion={late_fusion}, train={train}): worst gradient rel {worst:.2e} (tol 2e-4)")
+        assert worst <= 2e-4
+        with pytest.raises(RuntimeError, match="backward called twice"):
+            out[0].backward()
+    _, _, g_half = run(True, False, scale=0.5)
+    _, _, g_direct = run(True, False, direct=True)
+    for k in ref_g:
+        if float(ref_g[k].abs().max()) > 1e-9:
+            assert rel_err(2.0 * g_half[k], g[k]) <= 1e-5, k
+            assert rel_err(g_direct[k], g[k]) <= 1e-5, k
