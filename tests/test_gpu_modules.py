@@ -137,12 +137,12 @@ def test_fused_model_step_node_matches_per_op_functions(late_fusion):
         m.fused_model_step = fused
         if direct:
             for p in m.parameters():
-                p.grad = torch.full_like(p, 0.25)          # accumulation (+=) into what is already there
+                p.grad = torch.full_like(p, 2.0 ** -12)    # accumulation (+=) into what is already there
             m.grad_targets = "param.grad"
         torch.manual_seed(3)
         out = m.model_step(batch)
         (out[0] * scale).backward()
-        grads = {k: p.grad.clone() - (0.25 if direct else 0.0) for k, p in m.named_parameters()}
+        grads = {k: p.grad.clone() - (2.0 ** -12 if direct else 0.0) for k, p in m.named_parameters()}
         return m, out, grads
 
     for train in (True, False):
@@ -160,4 +160,4 @@ def test_fused_model_step_node_matches_per_op_functions(late_fusion):
     for k in ref_g:
         if float(ref_g[k].abs().max()) > 1e-9:
             assert rel_err(2.0 * g_half[k], g[k]) <= 1e-5, k
-            assert rel_err(g_direct[k], g[k]) <= 1e-5, k
+            assert rel_err(g_direct[k], g[k]) <= 5e-5, k   # (2^-12 + g) - 2^-12 rounds g to 2^-36
