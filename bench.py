@@ -471,6 +471,12 @@ def extra_configs(args, dev, rank, world, exchange_mode, steps=15, warmup=3):
                 opt.step()
             ms2 = _timed_steps(step, steps, warmup, dev, world)
             r["with_torch_optim_adam"] = imps(ms2, B)
+            # the same loop with optimizer._target_ = newsreclib_b200.optim.Adam (one Adam launch per parameter)
+            from newsreclib_b200.optim import Adam as NrlAdam
+            del m, opt
+            m = build()
+            opt = NrlAdam(m.parameters(), lr=1e-4)
+            r["with_nrl_optim_adam"] = imps(_timed_steps(step, steps, warmup, dev, world), B)
         return r
     entry("nrms_module_dropin", nrms_module)
 

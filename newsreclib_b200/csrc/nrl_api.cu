@@ -1388,14 +1388,28 @@ int nrl_supcon_bwd(const float* scores, const float* labels, const int* cand_off
   return NRL_OK;
 }
 
+// torch.optim.Adam keeps its betas as Python doubles: the bias corrections 1 - beta^step and the factor (1 - beta) of the
+// moment updates are formed in double and only then rounded to fp32 (1 - 0.999 -> 0.001f), while beta itself multiplies
+// the moment as fp32.  This ABI carries fp32 betas, and 1 - 0.999f is 1.3e-5 off 0.001f: the decimal the caller wrote is
+// recovered as the <= 7-digit decimal that rounds to the same fp32 (any beta typed as a short decimal; otherwise the fp32
+// value itself).
+static double beta_as_double(float beta) {
+  char buf[32];
+  snprintf(buf, sizeof(buf), "%.7g", (double)beta);
+  const double d = strtod(buf, nullptr);
+  return (float)d == beta ? d : (double)beta;
+}
+
 static int adam_impl(float* p, float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                      float eps, long long step, float grad_scale, int zero_grad, void* stream) {
   if (!p || !g || !m || !v || n <= 0 || step <= 0) return fail(NRL_ERR_INVALID_ARG, "nrl_adam_step: bad argument");
-  const double bc1 = 1.0 - std::pow((double)beta1, (double)step);
-  const double bc2 = 1.0 - std::pow((double)beta2, (double)step);
+  const double b1d = beta_as_double(beta1), b2d = beta_as_double(beta2);
+  const double bc1 = 1.0 - std::pow(b1d, (double)step);
+  const double bc2 = 1.0 - std::pow(b2d, (double)step);
   TRY(device_init());
   adam_kernel<<<grid_for(n, 256 * 4, 8 * g_dev.sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      p, g, m, v, n, lr, beta1, beta2, eps, (float)bc1, (float)std::sqrt(bc2), grad_scale, zero_grad);
+      p, g, m, v, n, lr, beta1, beta2, (float)(1.0 - b1d), (float)(1.0 - b2d), eps, (float)bc1, (float)std::sqrt(bc2),
+      grad_scale, zero_grad);
   LAUNCH_CHECK("adam");
   return NRL_OK;
 }
@@ -1514,8 +1528,9 @@ int nrl_exchange_adam_step(const nrl_peer_set* peers, float* m, float* v, long l
   TRY(device_init());
   PeerSet ps;
   std::memcpy(&ps, peers, sizeof(ps));
-  const double bc1 = 1.0 - std::pow((double)beta1, (double)step);
-  const double bc2 = 1.0 - std::pow((double)beta2, (double)step);
+  const double b1d = beta_as_double(beta1), b2d = beta_as_double(beta2);
+  const double bc1 = 1.0 - std::pow(b1d, (double)step);
+  const double bc2 = 1.0 - std::pow(b2d, (double)step);
   const long long n4 = n / 4, per = (n4 + ps.world - 1) / ps.world;
   if (timeout_ns == 0) timeout_ns = 5000000000ull;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1530,7 +1545,8 @@ int nrl_exchange_adam_step(const nrl_peer_set* peers, float* m, float* v, long l
     if (cap > occ * g_dev.sm_count) cap = occ * g_dev.sm_count;                                              \
     long long work = per > (long long)sp.bm_words * 64 ? per : (long long)sp.bm_words * 64;                  \
     const int grid = grid_for(work, 256, cap);                                                               \
-    exchange_adam_kernel<W><<<grid, 256, 0, st>>>(ps, m, v, n4, epoch, timeout_ns, lr, beta1, beta2, eps,    \
+    exchange_adam_kernel<W><<<grid, 256, 0, st>>>(ps, m, v, n4, epoch, timeout_ns, lr, beta1, beta2,         \
+                                                  (float)(1.0 - b1d), (float)(1.0 - b2d), eps,                 \
                                                   (float)bc1, (float)std::sqrt(bc2), grad_scale, sp);        \
   } while (0)
   switch (ps.world) {

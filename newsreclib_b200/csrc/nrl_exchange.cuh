@@ -101,11 +101,11 @@ __device__ __forceinline__ bool wait_flag(const unsigned long long* p, unsigned 
 }
 
 // torch.optim.Adam on one element (same expression as adam_kernel: the division by sqrt_bc2 is kept)
-__device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v, float b1, float b2,
-                                          float eps, float lr_bc1, float sqrt_bc2, float g_scale) {
+__device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v, float b1, float b2, float omb1,
+                                          float omb2, float eps, float lr_bc1, float sqrt_bc2, float g_scale) {
   const float gi = g * g_scale;
-  const float mi = b1 * m + (1.f - b1) * gi;
-  const float vi = b2 * v + (1.f - b2) * gi * gi;
+  const float mi = b1 * m + omb1 * gi;
+  const float vi = b2 * v + omb2 * gi * gi;
   m = mi;
   v = vi;
   const float denom = sqrtf(vi) / sqrt_bc2 + eps;
@@ -128,7 +128,8 @@ template <int W>
 __global__ void __launch_bounds__(256)
 exchange_adam_kernel(PeerSet ps, float* __restrict__ m, float* __restrict__ v, long long n4,
                      unsigned long long epoch, unsigned long long timeout_ns, float lr, float b1,
-                     float b2, float eps, float bc1, float sqrt_bc2, float g_scale, SparseCfg sp) {
+                     float b2, float omb1, float omb2, float eps, float bc1, float sqrt_bc2, float g_scale,
+                     SparseCfg sp) {
   const int world = W ? W : ps.world, rank = ps.rank;
   unsigned long long* my_flags = ps.flags[rank];
   __shared__ int s_flag;
@@ -283,10 +284,10 @@ exchange_adam_kernel(PeerSet ps, float* __restrict__ m, float* __restrict__ v, l
         if (i >= hi) break;
         float4 p4 = p_loc[i];
         float4 m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i];
-        adam_elem(p4.x, g4[u].x, m4.x, v4.x, b1, b2, eps, lr_bc1, sqrt_bc2, g_scale);
-        adam_elem(p4.y, g4[u].y, m4.y, v4.y, b1, b2, eps, lr_bc1, sqrt_bc2, g_scale);
-        adam_elem(p4.z, g4[u].z, m4.z, v4.z, b1, b2, eps, lr_bc1, sqrt_bc2, g_scale);
-        adam_elem(p4.w, g4[u].w, m4.w, v4.w, b1, b2, eps, lr_bc1, sqrt_bc2, g_scale);
+        adam_elem(p4.x, g4[u].x, m4.x, v4.x, b1, b2, omb1, omb2, eps, lr_bc1, sqrt_bc2, g_scale);
+        adam_elem(p4.y, g4[u].y, m4.y, v4.y, b1, b2, omb1, omb2, eps, lr_bc1, sqrt_bc2, g_scale);
+        adam_elem(p4.z, g4[u].z, m4.z, v4.z, b1, b2, omb1, omb2, eps, lr_bc1, sqrt_bc2, g_scale);
+        adam_elem(p4.w, g4[u].w, m4.w, v4.w, b1, b2, omb1, omb2, eps, lr_bc1, sqrt_bc2, g_scale);
         reinterpret_cast<float4*>(m)[i] = m4;
         reinterpret_cast<float4*>(v)[i] = v4;
 #pragma unroll

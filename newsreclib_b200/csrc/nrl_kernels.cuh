@@ -1852,8 +1852,8 @@ __global__ void emb_grad_kernel(const long long* __restrict__ ids, long long R, 
 // zero_grad != 0: the gradient element is overwritten with 0 after it has been consumed (optimizer.zero_grad()
 // folded into the step: the buffers accumulate, so they must be clean before the next backward pass).
 __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
-                            float* __restrict__ v, long long n, float lr, float b1, float b2,
-                            float eps, float bc1, float sqrt_bc2, float g_scale, int zero_grad) {
+                            float* __restrict__ v, long long n, float lr, float b1, float b2, float omb1,
+                            float omb2, float eps, float bc1, float sqrt_bc2, float g_scale, int zero_grad) {
   const float lr_bc1 = lr / bc1;
   const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long nth = (long long)gridDim.x * blockDim.x;
@@ -1869,8 +1869,8 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float*
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float gi = gg[k] * g_scale;
-        const float mi = b1 * mm[k] + (1.f - b1) * gi;
-        const float vi = b2 * vv[k] + (1.f - b2) * gi * gi;
+        const float mi = b1 * mm[k] + omb1 * gi;   // omb = fp32(1 - beta) formed in double on the host, as torch does
+        const float vi = b2 * vv[k] + omb2 * gi * gi;
         mm[k] = mi;
         vv[k] = vi;
         const float denom = sqrtf(vi) / sqrt_bc2 + eps;
@@ -1886,8 +1886,8 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float*
   for (long long i = 4 * n4 + tid; i < n; i += nth) {
     const float gi = g[i] * g_scale;
     if (zero_grad) g[i] = 0.f;
-    const float mi = b1 * m[i] + (1.f - b1) * gi;
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    const float mi = b1 * m[i] + omb1 * gi;
+    const float vi = b2 * v[i] + omb2 * gi * gi;
     m[i] = mi;
     v[i] = vi;
     const float denom = sqrtf(vi) / sqrt_bc2 + eps;
