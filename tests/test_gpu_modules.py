@@ -160,8 +160,8 @@ def test_fused_model_step_node_matches_per_op_functions(late_fusion):
     for k in ref_g:
         if float(ref_g[k].abs().max()) > 1e-9:
             assert rel_err(2.0 * g_half[k], g[k]) <= 1e-5, k
-            # (2^-12 + g) - 2^-12 rounds g to a multiple of 2^-36
-            assert float((g_direct[k] - g[k]).abs().max()) <= 1e-5 * float(g[k].abs().max()) + 2.0 ** -35, k
+            # every partial sum the kernels add into the prefilled 2^-12 is rounded at 2^-36: an absolute floor on top
+            assert float((g_direct[k] - g[k]).abs().max()) <= 1e-5 * float(g[k].abs().max()) + 1e-9, k
 
 
 def test_optim_adam_matches_torch_adam():
