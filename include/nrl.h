@@ -215,6 +215,16 @@ int nrl_ce_soft_fwd(const float* scores, const float* labels, const int* cand_of
 int nrl_ce_soft_bwd(const float* scores, const float* labels, const int* cand_off, int B,
                     int Cmax, const float* g_loss, float g_scale, float* d_scores, void* stream);
 
+/* ---- RetrievalMRR / RetrievalNormalizedDCG(top_k) of the epoch-end hooks, nrms_module.py:182-191,380-396,480 ----
+ * (torchmetrics retrieval metrics grouped by `indexes` = the impression of each candidate; third-party, restated.)
+ * scores / labels [N] concatenated per impression, off [B + 1] (int64, host-side cumsum of cand_news_size stays on the
+ * device), top_k [n_k] HOST array of n_k <= 4 cut-offs.  out [B][1 + n_k] = {reciprocal rank of the first positive (0
+ * without one), nDCG@top_k[0], ...} per impression: the epoch value is the mean over B.  Scores are ranked descending
+ * with ties in input order (stable), labels are the gains, discount 1 / log2(rank + 1), ideal ordering = the labels
+ * sorted descending; ranks [N] (may be NULL) receives each candidate's 1-based rank within its impression. */
+int nrl_rank_metrics(const float* scores, const float* labels, const long long* off, int B,
+                     const int* top_k, int n_k, float* out, int* ranks, void* stream);
+
 /* ---- SupConLoss()(embeddings=scores, indices_tuple=...) , nrms_module.py:289-316 + components/losses.py:6-40 ----
  * Supervised-contrastive loss over the dense [B, Cmax] score matrix (positives = real candidates with a non-zero
  * label, negatives = real candidates with label 0, padded slots in neither set; per-row

@@ -129,6 +129,7 @@ SIGNATURES = {
     "nrl_score_bwd": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _VP, _VP, _VP]),
     "nrl_ce_soft_fwd": (_I, [_VP, _VP, _VP, _I, _I, _VP, _VP, _VP, _VP]),
     "nrl_ce_soft_bwd": (_I, [_VP, _VP, _VP, _I, _I, _VP, _F, _VP, _VP]),
+    "nrl_rank_metrics": (_I, [_VP, _VP, _VP, _I, C.POINTER(C.c_int), _I, _VP, _VP, _VP]),
     "nrl_supcon_fwd": (_I, [_VP, _VP, _VP, _I, _I, _F, _VP, _F, _VP, _VP, _VP, _VP]),
     "nrl_supcon_bwd": (_I, [_VP, _VP, _VP, _I, _I, _F, _VP, _VP, _VP, _F, _I, _VP, _VP]),
     "nrl_adam_step": (_I, [_VP, _VP, _VP, _VP, _LL, _F, _F, _F, _F, _LL, _F, _VP]),

@@ -1366,6 +1366,20 @@ int nrl_ce_soft_bwd(const float* scores, const float* labels, const int* cand_of
   return NRL_OK;
 }
 
+int nrl_rank_metrics(const float* scores, const float* labels, const long long* off, int B, const int* top_k, int n_k,
+                     float* out, int* ranks, void* stream) {
+  if (!scores || !labels || !off || !out || B <= 0 || n_k < 0 || n_k > RM_MAXK || (n_k > 0 && !top_k))
+    return fail(NRL_ERR_INVALID_ARG, "nrl_rank_metrics: bad argument (at most %d cut-offs)", RM_MAXK);
+  RankKs ks;
+  ks.n = n_k;
+  for (int q = 0; q < RM_MAXK; ++q) ks.k[q] = q < n_k ? top_k[q] : 0;
+  for (int q = 0; q < n_k; ++q)
+    if (top_k[q] <= 0) return fail(NRL_ERR_INVALID_ARG, "nrl_rank_metrics: top_k must be positive");
+  rank_metrics_kernel<<<B, 128, 0, static_cast<cudaStream_t>(stream)>>>(scores, labels, off, B, ks, out, ranks);
+  LAUNCH_CHECK("rank_metrics");
+  return NRL_OK;
+}
+
 int nrl_supcon_fwd(const float* scores, const float* labels, const int* cand_off, int B, int Cmax, float temperature,
                    const float* ce_loss, float dual_loss_coef, float* row_loss, float* loss, float* stats,
                    void* stream) {

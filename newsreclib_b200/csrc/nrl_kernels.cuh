@@ -1632,6 +1632,92 @@ __global__ void ce_bwd_kernel(const float* __restrict__ scores, const float* __r
 }
 
 // ------------------------------------------------------------------------------------
+// f4: per-impression retrieval metrics of the epoch-end hooks (nrms_module.py:182-191,380-396: torchmetrics
+// RetrievalMRR and RetrievalNormalizedDCG(top_k) grouped by `indexes` = the impression of each candidate).
+// One CTA per impression over the ragged epoch outputs (scores / labels concatenated per impression, 64-bit offsets):
+//   rank_i  = 1 + #{j : s_j > s_i or (s_j == s_i and j < i)}        (descending, stable -- an O(c^2) count in shared
+//   lrank_i = the same over the labels                                 memory instead of a sort: c <= a few hundred)
+//   mrr     = 1 / min{rank_i : y_i > 0}                   (0 without a positive: empty_target_action = "neg")
+//   ndcg@k  = sum_{rank_i <= k} y_i / log2(rank_i + 1)  /  sum_{lrank_i <= k} y_i / log2(lrank_i + 1)   (0 when the ideal is 0)
+// out [B][1 + nk]; ranks [N] (optional) receives rank_i for callers that need the top-k membership.
+// Impressions longer than RM_SMEM candidates are ranked straight from global memory.
+// ------------------------------------------------------------------------------------
+constexpr int RM_SMEM = 2048;
+constexpr int RM_MAXK = 4;
+struct RankKs {
+  int n;
+  int k[RM_MAXK];
+};
+__global__ void __launch_bounds__(128)
+rank_metrics_kernel(const float* __restrict__ scores, const float* __restrict__ labels,
+                    const long long* __restrict__ off, int B, RankKs ks, float* __restrict__ out,
+                    int* __restrict__ ranks) {
+  __shared__ float s_s[RM_SMEM], s_y[RM_SMEM];
+  __shared__ float s_red[4][2 * RM_MAXK + 1];
+  const int b = blockIdx.x;
+  const long long o = off[b];
+  const int c = (int)(off[b + 1] - o);
+  const float* gs = scores + o;
+  const float* gy = labels + o;
+  const bool in_smem = c <= RM_SMEM;
+  if (in_smem) {
+    for (int i = threadIdx.x; i < c; i += blockDim.x) {
+      s_s[i] = gs[i];
+      s_y[i] = gy[i];
+    }
+    __syncthreads();
+  }
+  const float* ps = in_smem ? s_s : gs;
+  const float* py = in_smem ? s_y : gy;
+  float dcg[RM_MAXK], idcg[RM_MAXK];
+#pragma unroll
+  for (int q = 0; q < RM_MAXK; ++q) dcg[q] = idcg[q] = 0.f;
+  float best = 0.f;  // 1 / (smallest rank of a positive) seen by this thread
+  for (int i = threadIdx.x; i < c; i += blockDim.x) {
+    const float si = ps[i], yi = py[i];
+    int r = 1, lr = 1;
+    for (int j = 0; j < c; ++j) {
+      const float sj = ps[j], yj = py[j];
+      r += (sj > si) || (sj == si && j < i);
+      lr += (yj > yi) || (yj == yi && j < i);
+    }
+    if (ranks) ranks[o + i] = r;
+    if (yi > 0.f) best = fmaxf(best, 1.f / (float)r);
+#pragma unroll
+    for (int q = 0; q < RM_MAXK; ++q)
+      if (q < ks.n) {
+        if (r <= ks.k[q]) dcg[q] += yi / log2f((float)r + 1.f);
+        if (lr <= ks.k[q]) idcg[q] += yi / log2f((float)lr + 1.f);
+      }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  best = warp_max(best);
+#pragma unroll
+  for (int q = 0; q < RM_MAXK; ++q) {
+    dcg[q] = warp_sum(dcg[q]);
+    idcg[q] = warp_sum(idcg[q]);
+  }
+  if (lane == 0) {
+    s_red[warp][0] = best;
+#pragma unroll
+    for (int q = 0; q < RM_MAXK; ++q) {
+      s_red[warp][1 + 2 * q] = dcg[q];
+      s_red[warp][2 + 2 * q] = idcg[q];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float* ob = out + (long long)b * (1 + ks.n);
+    ob[0] = fmaxf(fmaxf(s_red[0][0], s_red[1][0]), fmaxf(s_red[2][0], s_red[3][0]));
+    for (int q = 0; q < ks.n; ++q) {
+      const float d_ = s_red[0][1 + 2 * q] + s_red[1][1 + 2 * q] + s_red[2][1 + 2 * q] + s_red[3][1 + 2 * q];
+      const float i_ = s_red[0][2 + 2 * q] + s_red[1][2 + 2 * q] + s_red[2][2 + 2 * q] + s_red[3][2 + 2 * q];
+      ob[1 + q] = i_ > 0.f ? d_ / i_ : 0.f;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // f4: supervised-contrastive loss over the dense score matrix (nrms_module.py:290-316 + components/losses.py:12-40 on
 // pytorch-metric-learning's SupConLoss; temperature is the constructor default 0.1, abstract_recommender.py:117-120).
 // Row b: positives = real slots with a non-zero label, negatives = real slots with label 0, padded slots in neither.

@@ -12,8 +12,9 @@ definitions (third-party, torchmetrics 1.x):
 * AUROC is the global binary AUROC over every candidate, ties in the scores counted half (mid-ranks), which is
   what the trapezoidal ROC integral gives.
 
-One dense ``[impressions, max candidates]`` sort, no python loop over impressions, no host sync except the
-width; not part of the timed hot path.
+On CUDA tensors MRR / nDCG@k come from ``nrl_rank_metrics`` (one CTA per impression, ranks counted in shared memory);
+the torch formulation below (one dense ``[impressions, max candidates]`` sort) states the same definitions for host
+tensors and is what the CPU tests pin against scikit-learn.  AUROC is global over the epoch: one ``torch.unique``.
 """
 from __future__ import annotations
 
@@ -50,6 +51,14 @@ def ranking_metrics(preds: torch.Tensor, targets: torch.Tensor, sizes: torch.Ten
                     top_k_list: List[int]) -> Dict[str, torch.Tensor]:
     """preds/targets: concatenated per-impression scores/labels; sizes: candidates per impression."""
     sizes = sizes.to(preds.device)
+    if preds.is_cuda and len(top_k_list) <= 4:
+        # the sm_100a kernel: one CTA per impression ranks its candidates in shared memory (no dense [B, Cmax] sort)
+        from . import ops
+        per = ops.rank_metrics(preds, targets, sizes, top_k_list).mean(dim=0)
+        out = {"mrr": per[0]}
+        out.update({f"ndcg@{k}": per[1 + i] for i, k in enumerate(top_k_list)})
+        out["auc"] = binary_auroc(preds, targets)
+        return out
     p, t, _ = _dense(preds, targets, sizes)
     order = p.argsort(dim=1, descending=True, stable=True)
     ts = t.gather(1, order)

@@ -397,6 +397,24 @@ class ToDenseFn(torch.autograd.Function):
         return dx, None, None, None
 
 
+def rank_metrics(preds: torch.Tensor, targets: torch.Tensor, sizes: torch.Tensor, top_k_list, want_ranks: bool = False):
+    """Per-impression reciprocal rank and nDCG@k (``nrl_rank_metrics``): ``[B, 1 + len(top_k_list)]`` (and, optionally,
+    every candidate's rank within its impression)."""
+    lib = _lib.load()
+    preds = _chk(preds.detach().contiguous().float(), torch.float32, "preds")
+    targets = targets.detach().to(preds.device).contiguous().float()
+    sizes = sizes.to(preds.device).long()
+    B = sizes.numel()
+    off = torch.zeros(B + 1, dtype=torch.int64, device=preds.device)
+    off[1:] = sizes.cumsum(0)
+    ks = (C.c_int * max(1, len(top_k_list)))(*[int(k) for k in top_k_list])
+    out = torch.empty(B, 1 + len(top_k_list), dtype=torch.float32, device=preds.device)
+    ranks = torch.empty(preds.numel(), dtype=torch.int32, device=preds.device) if want_ranks else None
+    _lib.check(lib.nrl_rank_metrics(_p(preds), _p(targets), _p(off), B, ks, len(top_k_list), _p(out), _p(ranks),
+                                    _stream()), "nrl_rank_metrics")
+    return (out, ranks) if want_ranks else out
+
+
 def dense_to_ragged(dense: torch.Tensor, off: torch.Tensor, n: int) -> torch.Tensor:
     """Rows of a dense ``[B, M]`` / ``[B, M, E]`` batch back in ragged order (``[n]`` / ``[n, E]``): what boolean-mask
     indexing ``dense[mask]`` returns (``abstract_recommender.py:126-130``), without the host sync of ``nonzero`` -- the

@@ -243,3 +243,39 @@ def test_train_step_from_host_buffers_matches_device_resident_step(split, monkey
     with pytest.raises(RuntimeError, match="token id"):
         t_host.train_step_host(bad, B, Hmax, Cmax, torch.empty(B, Cmax).pin_memory(), torch.empty(1).pin_memory())
     assert ops.device_status(raise_on_error=False) == 0                      # reported once, then clear
+
+
+@pytest.mark.parametrize("quantise,long_imp", [(False, False), (True, False), (False, True)])
+def test_rank_metrics_kernel_matches_host_definitions(quantise, long_imp):
+    """nrl_rank_metrics (one CTA per impression, ranks counted in shared memory) against the torch formulation of the same
+    definitions on the host (metrics.ranking_metrics on CPU tensors: the one tests/test_metrics_cpu.py pins against
+    scikit-learn): tied scores (stable order), impressions without a positive, a single candidate, an impression longer
+    than the shared-memory tile, and the per-candidate ranks against a stable argsort."""
+    from newsreclib_b200 import ops
+    from newsreclib_b200.metrics import ranking_metrics
+    g = torch.Generator().manual_seed(11 + int(quantise))
+    sizes = torch.randint(1, 300, (50,), generator=g)
+    sizes[3] = 1
+    if long_imp:
+        sizes[7] = 2500
+    N = int(sizes.sum())
+    preds = torch.randn(N, generator=g)
+    if quantise:
+        preds = (preds * 2).round() / 2
+    targets = (torch.rand(N, generator=g) < 0.15).float()
+    off = torch.cat([torch.zeros(1, dtype=torch.long), sizes.cumsum(0)])
+    targets[off[5]:off[6]] = 0                                            # an impression without a positive
+    ks = [1, 5, 10, 400]
+    want = ranking_metrics(preds, targets, sizes, ks)
+    got = ranking_metrics(preds.cuda(), targets.cuda(), sizes.cuda(), ks)
+    for k in want:
+        assert abs(float(got[k]) - float(want[k])) <= 2e-6, (k, float(got[k]), float(want[k]))
+    per, ranks = ops.rank_metrics(preds.cuda(), targets.cuda(), sizes.cuda(), ks, want_ranks=True)
+    assert per.shape == (50, 5) and float(per[5].abs().max()) == 0.0
+    ranks = ranks.cpu()
+    for b in (0, 3, 7, 20):
+        s = preds[off[b]:off[b + 1]]
+        order = torch.argsort(s, descending=True, stable=True)
+        expect = torch.empty_like(order)
+        expect[order] = torch.arange(1, s.numel() + 1)
+        assert torch.equal(ranks[off[b]:off[b + 1]].long(), expect)
