@@ -612,7 +612,7 @@ def extra_configs(args, dev, rank, world, exchange_mode, steps=15, warmup=3):
         r = imps(ms_c, B)
         r.update(news_table_encode={"news": M, "ms": enc_ms, "news_per_s": M / (enc_ms / 1e3)},
                  candidates_per_batch=cands, cached_scores_only=imps(ms_s, B), plain_eval_forward_scores_only=imps(ms_p, B),
-                 note="value = cached scores + AUC/MRR/nDCG@5,10 on device (torch sort / unique: not library kernels); "
+                 note="value = cached scores + MRR/nDCG@5,10 (nrl_rank_metrics, one CTA per impression) + AUROC (torch.unique rank sums) per batch; "
                       "cached_scores_only / plain_eval_forward_scores_only compare the two ways of producing the scores",
                  workload=f"eval at MINDlarge-dev shape: B={B} whole impressions/GPU (ragged histories <= {HIST}, candidate lists "
                           f"lognormal up to 300), scores from news vectors cached once per epoch + AUC/MRR/nDCG on device; "
