@@ -317,7 +317,7 @@ static int launch_gemm(const Ctx& c, GemmParams& p, const CUtensorMap& ta, const
   // staging buffers, which an operand-stationary main loop could use.
   static const bool direct_on = [] { const char* e = getenv("NRL_EPI_DIRECT"); return e && e[0] == '1'; }();
   const GemmEpi& ee = p.epi;
-  p.direct = (direct_on && sk.f32 && !sk.reduce && !sk.sp && !ee.add_w && !ee.relu && !ee.pos_mask && !ee.qvec && !ee.gb && !ee.gelu &&
+  p.direct = (direct_on && sk.f32 && !sk.reduce && !sk.sp && !ee.add_w && !ee.relu && !ee.pos_mask && !ee.pos_words && !ee.qvec && !ee.gb && !ee.gelu &&
               !ee.add_mat && !ee.gelu_pre &&
               !(sk.f32_cols & 1) && !(sk.ld_f32 & 1) && !(reinterpret_cast<uintptr_t>(sk.f32) & 7)) ? 1 : 0;
   p.out = sk.f32; p.ld_out = sk.ld_f32;
@@ -1993,6 +1993,9 @@ int nrl_cnn_encoder_fwd(const long long* ids, long long n_news, int L, const flo
     GemmEpi e = epi_none();
     e.relu = 1;
     epi_dropout(e, drop, w.mask1, d.MW1);
+    // the keep-bit words of site 1 become "kept AND positive" words in place: the backward pass takes ReLU' and
+    // dropout' from them (one word per 32-column chunk) instead of re-reading the fp32 activations
+    e.pos_words = w.mask1; e.pos_mw = d.MW1;
     Sinks sk;
     sk.f32 = w.y; sk.ld_f32 = d.F; sk.f32_cols = d.F;
     sk.sp = w.yp; sk.ld_sp = d.Fp; sk.sp_cols = d.Fp; sk.ones_col = d.F;
@@ -2033,8 +2036,8 @@ int nrl_cnn_encoder_bwd(const long long* ids, long long n_news, int L, long long
   {  // dPre = relu'(.) dropout1'( w_r dVec + dApre W_add )  -> split planes
     GemmEpi e = epi_none();
     e.add_w = w.w; e.add_vec = d_out; e.ld_addvec = d.F; e.add_L = L;
-    epi_dropout(e, drop, w.mask1, d.MW1);
-    e.pos_mask = w.y; e.ld_pos = d.F;
+    // mask1 = keep AND (relu(conv) > 0), written by the forward conv epilogue (all ones kept when dropout is off)
+    e.drop_words = w.mask1; e.drop_mw = d.MW1; e.drop_scale = drop.on ? drop.scale : 1.f;
     Sinks sk;
     sk.sp = w.dyp; sk.ld_sp = d.Fp; sk.sp_cols = d.Fp; sk.ones_col = -1;
     TRY(gemm_nt(c, w.dap, R, d.Qp, w.wadd_t, d.F, d.Qp, d.Qp, e, sk, "gemm additive dgrad"));

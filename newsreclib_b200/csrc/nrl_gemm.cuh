@@ -58,6 +58,9 @@ struct GemmEpi {
   const float* gelu_pre; long long ld_gelu;   // x *= gelu'(gelu_pre[row, col])  (feed-forward backward)
   const float* pos_mask; long long ld_pos;  // x = pos_mask[row, col] > 0 ? x : 0  (ReLU backward)
   const uint32_t* drop_words; int drop_mw; float drop_scale;  // keep-bit words [row][drop_mw], or null
+  uint32_t* pos_words; int pos_mw;  // out: bit i of word [row][col / 32] = (x > 0) after relu + dropout.  May alias
+                                    // drop_words (each word is read and then written by the one thread that owns the
+                                    // chunk): the backward pass then applies ReLU' and dropout' from ONE word per chunk
   const float* qvec;    float* score;         // x = tanh(x); score[row] = sum_col x * qvec[col]
   int f32_sink;         // 0 none, 1 TMA store of x to tmOut, 2 TMA reduce-add of x into tmOut
   int f32_cols;         // column extent of tmOut
@@ -257,10 +260,17 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const CU
           for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
         }
         if (e.drop_words) {  // col_base % 32 == 0: one word holds this chunk's keep-bits
-          const uint32_t bits =
-              row_ok ? __ldg(e.drop_words + (long long)row * e.drop_mw + (col_base >> 5)) : 0u;
+          const uint32_t* wp = e.drop_words + (long long)row * e.drop_mw + (col_base >> 5);
+          // a word this launch also writes (pos_words aliasing drop_words) must not go through the read-only path
+          const uint32_t bits = row_ok ? (e.pos_words ? *wp : __ldg(wp)) : 0u;
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = ((bits >> i) & 1u) ? v[i] * e.drop_scale : 0.f;
+        }
+        if (e.pos_words && row_ok && col_base < p.N) {  // chunks of pad columns own no word
+          uint32_t pos = 0u;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) pos |= (col_base + i < p.N && v[i] > 0.f) ? (1u << i) : 0u;
+          e.pos_words[(long long)row * e.pos_mw + (col_base >> 5)] = pos;
         }
         if (e.add_mat && row_ok) {
           const float* am = e.add_mat + (long long)row * e.ld_addmat + col_base;
