@@ -44,6 +44,15 @@ def _p(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+def _ws(ctx) -> torch.Tensor:
+    """The workspace a Function's forward left on ``ctx`` (it holds the saved activations and is released after the first
+    backward, so a second backward through the same node -- ``retain_graph=True`` -- cannot be served)."""
+    if ctx.ws is None:
+        raise RuntimeError("backward called twice through a newsreclib_b200 op: the saved activations live in a workspace "
+                           "that is released after the first backward (retain_graph is not supported)")
+    return ctx.ws
+
+
 def block_struct(tensors) -> BlockParams:
     """Seven tensors in ``BLOCK_KEYS`` order -> ``nrl_block_params``."""
     s = BlockParams()
@@ -289,7 +298,7 @@ class NrmsStepFn(torch.autograd.Function):
         _lib.check(lib.nrl_nrms_step_bwd(
             _p(labels), _p(g), nh, nc, L, B, Hmax, Cmax, table.shape[0], C.byref(nb),
             C.byref(ub) if ub is not None else None, ctx.dims, int(late_fusion), float(dropout_p), int(training),
-            int(seed), C.byref(ngs), C.byref(ugs) if ugs is not None else None, _p(d_table), _p(ctx.ws),
+            int(seed), C.byref(ngs), C.byref(ugs) if ugs is not None else None, _p(d_table), _p(_ws(ctx)),
             ctx.ws.numel(), precision, _stream()), "nrl_nrms_step_bwd")
         ctx.ws = None
         if grad_targets is not None:
@@ -329,7 +338,7 @@ class NewsEncoderFn(torch.autograd.Function):
         d_table = torch.zeros_like(table)
         bs, gs = block_struct(blk), block_struct(grads)
         _lib.check(lib.nrl_news_encoder_bwd(_p(ids), n, L, table.shape[0], C.byref(bs), ctx.dims, p, training,
-                                            seed, _p(d_out), C.byref(gs), _p(d_table), _p(ctx.ws),
+                                            seed, _p(d_out), C.byref(gs), _p(d_table), _p(_ws(ctx)),
                                             ctx.ws.numel(), precision, _stream()), "nrl_news_encoder_bwd")
         ctx.ws = None
         return (None, d_table, *grads, None, None, None, None, None)
@@ -366,7 +375,7 @@ class UserEncoderFn(torch.autograd.Function):
         d_hist = torch.empty(B, Hmax, E, dtype=torch.float32, device=d_user.device)
         bs, gs = block_struct(blk), block_struct(grads)
         _lib.check(lib.nrl_user_encoder_bwd(B, Hmax, C.byref(bs), ctx.dims, axis, _p(d_user), C.byref(gs),
-                                            _p(d_hist), _p(ctx.ws), ctx.ws.numel(), precision, _stream()),
+                                            _p(d_hist), _p(_ws(ctx)), ctx.ws.numel(), precision, _stream()),
                    "nrl_user_encoder_bwd")
         ctx.ws = None
         return (d_hist, *grads, None, None, None)
@@ -580,7 +589,7 @@ class AdditiveFn(torch.autograd.Function):
         dx = torch.empty_like(x)
         gw, gb, gq = torch.zeros_like(weight), torch.zeros_like(bias), torch.zeros_like(query)
         _lib.check(lib.nrl_additive_bwd(_p(x), G, L, D, Q, _p(weight), _p(query), _p(d_out), _p(dx), _p(gw),
-                                        _p(gb), _p(gq), _p(ctx.ws), ctx.ws.numel(), ctx.precision, _stream()),
+                                        _p(gb), _p(gq), _p(_ws(ctx)), ctx.ws.numel(), ctx.precision, _stream()),
                    "nrl_additive_bwd")
         ctx.ws = None
         return dx, gw, gb, gq, None
@@ -632,7 +641,7 @@ class CnnEncoderFn(torch.autograd.Function):
         d_table = torch.zeros_like(table)
         ps, gs = cnn_struct(prm), cnn_struct(grads)
         _lib.check(lib.nrl_cnn_encoder_bwd(_p(ids), n, L, table.shape[0], C.byref(ps), ctx.dims, p, training, seed,
-                                           _p(d_out), C.byref(gs), _p(d_table), _p(ctx.ws), ctx.ws.numel(),
+                                           _p(d_out), C.byref(gs), _p(d_table), _p(_ws(ctx)), ctx.ws.numel(),
                                            precision, _stream()), "nrl_cnn_encoder_bwd")
         ctx.ws = None
         return (None, d_table, *grads, None, None, None, None, None)
@@ -667,7 +676,7 @@ class LinearEncoderFn(torch.autograd.Function):
         d_out = d_out.contiguous().float()
         gw, gb, d_table = torch.zeros_like(weight), torch.zeros_like(bias), torch.zeros_like(table)
         _lib.check(lib.nrl_linear_encoder_bwd(_p(ids), n, table.shape[0], CE, _p(weight), O, p, training, seed,
-                                              _p(out), _p(d_out), _p(gw), _p(gb), _p(d_table), _p(ctx.ws),
+                                              _p(out), _p(d_out), _p(gw), _p(gb), _p(d_table), _p(_ws(ctx)),
                                               ctx.ws.numel(), precision, _stream()), "nrl_linear_encoder_bwd")
         ctx.ws = None
         return None, d_table, gw, gb, None, None, None, None
@@ -710,7 +719,7 @@ class PlmHeadFn(torch.autograd.Function):
         d_x = torch.empty(N, T, E, dtype=torch.float32, device=d_out.device)
         bs, gs = block_struct(blk), block_struct(grads)
         _lib.check(lib.nrl_plm_head_bwd(N, T, C.byref(bs), ctx.dims, axis, p, training, seed, _p(d_out),
-                                        C.byref(gs), _p(d_x), _p(ctx.ws), ctx.ws.numel(), precision, _stream()),
+                                        C.byref(gs), _p(d_x), _p(_ws(ctx)), ctx.ws.numel(), precision, _stream()),
                    "nrl_plm_head_bwd")
         ctx.ws = None
         return (d_x, *grads, None, None, None, None, None, None)
@@ -835,7 +844,7 @@ class TfmEncoderFn(torch.autograd.Function):
                 setattr(lg[l], n, _p(grads[5 + 16 * l + i]))
         _lib.check(lib.nrl_tfm_encoder_bwd(_p(ids), _p(ctx.mask), N, T, C.byref(emb), layers, dims, training, seed,
                                            _p(ctx.wpack), _p(d_out), C.byref(eg) if eg is not None else None, lg,
-                                           _p(ctx.ws), ctx.ws.numel(), precision, _stream()), "nrl_tfm_encoder_bwd")
+                                           _p(_ws(ctx)), ctx.ws.numel(), precision, _stream()), "nrl_tfm_encoder_bwd")
         ctx.ws = None
         return (None, None, None, None, None, None, *grads)
 
