@@ -1421,10 +1421,12 @@ static int adam_impl(float* p, float* g, float* m, float* v, long long n, float 
   const double bc1 = 1.0 - std::pow(b1d, (double)step);
   const double bc2 = 1.0 - std::pow(b2d, (double)step);
   TRY(device_init());
-  // grid: 3 CTAs of 256 threads per SM.  Measured on B200 (experiments/adam_bw.py, profiles/r02u_adam_bw.txt; 8 streams of
-  // 87 / 160 MB each, cold L2): 2 per SM 5.3 TB/s, 3: 6.2-6.4, 4: 5.9-6.0, 5 (= the occupancy limit at 46 registers):
-  // 5.7-5.8, 6: 5.5, 8 (the previous grid, 1.6 waves): 6.0, 16: 6.1-6.2.  NRL_ADAM_CTAS_PER_SM overrides.
-  int per_sm = 3;
+  // grid: 8 CTAs of 256 threads per SM.  Measured on B200: ALONE with a cold L2 (experiments/adam_bw.py,
+  // profiles/r02u_adam_bw.txt; 8 streams of 87 / 160 MB) 3 per SM is the fastest (6.2-6.4 TB/s against 6.0 for 8, 5.7-5.8
+  // for the occupancy limit of 5); INSIDE the training step, right behind the embedding-gradient scatter whose output is
+  // still in L2, 8 per SM takes 0.121 ms and 3 per SM 0.136 ms (profiles/r02p_bench.json / r02_final2_bench.json).  The
+  // step is what counts.  NRL_ADAM_CTAS_PER_SM overrides.
+  int per_sm = 8;
   if (const char* e = getenv("NRL_ADAM_CTAS_PER_SM")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;
   adam_kernel<<<grid_for(n, 256 * 4, per_sm * g_dev.sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       p, g, m, v, n, lr, beta1, beta2, (float)(1.0 - b1d), (float)(1.0 - b2d), eps, (float)bc1, (float)std::sqrt(bc2),
