@@ -389,10 +389,14 @@ static void set_segs(const Ctx& c, GemmParams& p) { p.planes = c.two_planes() ? 
 // balanced n-tiles: as few tiles as possible (<= 256 columns each), all the same width, and
 // narrow enough that at least two pipeline stages fit beside the epilogue staging buffers
 static int balanced_bn(int n_extent, int planes, bool both_sinks, int mn_major, bool single_tile = false,
-                       bool pair = false) {
+                       bool pair = false, bool small = false) {
   const int avail = GEMM_SMEM_LIMIT - 1024 - GEMM_BAR_BYTES - GEMM_EPI_WARPS * 1 * (both_sinks ? 8192 : 4096);
   static const int bn_max = [] { const char* e = getenv("NRL_GEMM_BN_MAX"); return e ? atoi(e) : 256; }();
-  const int cap = single_tile ? 256 : bn_max;
+  // small = a launch that cannot fill the machine with 256-wide tiles (the user block's 3 200 rows): it is bound by the
+  // latency of ONE tile, and a 64-wide tile keeps all of K = 304 in flight (4-5 stages instead of 2) and spreads the work
+  // over more SMs.  Measured (experiments/small_gemm_latency.py, profiles/r02y_small_gemm_latency.txt): 3 200 x 300 x 304
+  // 15.4 -> 11.3 us, 3 200 x 200 x 304 17.4 -> 11.2 us, 3 200 x 900 x 304 19.5 -> 17.4 us; large launches unchanged.
+  const int cap = single_tile ? 256 : (small && bn_max > 64 ? 64 : bn_max);
   for (int nt = (n_extent + cap - 1) / cap;; ++nt) {
     // multiple of 32: the epilogue stores 32-column boxes, which must not straddle two n-tiles
     // (the overhang of the LAST tile lies outside the tensor and is clipped by TMA)
@@ -414,7 +418,10 @@ static int gemm_nt(const Ctx& c, const bf16* A, long long M, int a_pitch, const 
   // big row-streaming GEMMs run on CTA pairs (NRL_GEMM_PAIR=0 keeps the 1-CTA kernel: A/B runs)
   static const bool pair_on = [] { const char* e = getenv("NRL_GEMM_PAIR"); return !(e && e[0] == '0'); }();
   p.pair = (pair_on && (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM) >= g_dev.sm_count / 2) ? 1 : 0;
-  p.BN = balanced_bn(p.n_extent, p.planes, sk.f32 && sk.sp, 0, epi.score != nullptr, p.pair != 0);
+  static const bool small_on = [] { const char* e = getenv("NRL_GEMM_SMALL_BN"); return !(e && e[0] == '0'); }();
+  const bool small = small_on && !p.pair &&
+                     (M + GEMM_BM - 1) / GEMM_BM * ((p.n_extent + 255) / 256) < (long long)g_dev.sm_count;
+  p.BN = balanced_bn(p.n_extent, p.planes, sk.f32 && sk.sp, 0, epi.score != nullptr, p.pair != 0, small);
   // A-stationary pair kernel (nrl_gemm_tc2a_kernel) for plain / dropout fp32-sink GEMMs whose A panel fits: the n-tile is
   // narrowed until THREE B stages fit beside the panel (measured: 240-wide tiles with a 2-deep ring 0.183 ms, 160-wide
   // with a 3-deep ring 0.175 ms for the in-projection, against 0.189 ms for the streaming kernel; NRL_GEMM_ASTAT=0: off)
