@@ -379,7 +379,26 @@ static int launch_gemm(const Ctx& c, GemmParams& p, const CUtensorMap& ta, const
   p.tiles_per_unit = (p.k_splits == 1 && n_tiles > 1 && m_tiles >= 2 * g_dev.sm_count) ? n_tiles : 1;
   const int units = tiles / p.tiles_per_unit;
   const int grid = units < g_dev.sm_count ? units : g_dev.sm_count;
-  nrl_gemm_tc_kernel<<<grid, GEMM_THREADS, smem, c.stream>>>(ta, tb, tout, tsp, p);
+  // programmatic dependent launch: the kernel's prologue (barrier init, TMEM allocation, tensor-map prefetch) and its
+  // launch latency overlap the tail of whatever precedes it in the stream; it waits (griddepcontrol.wait) before its
+  // first global access.  Matters for the chains of small dependent launches (the user block).  NRL_PDL=0: plain launch.
+  static const bool pdl_on = [] { const char* e = getenv("NRL_PDL"); return !(e && e[0] == '0'); }();
+  if (pdl_on && !p.mn_major) {  // the NT GEMMs of the main stream; the weight-gradient (TN) GEMMs follow event waits on the side stream
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = c.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, nrl_gemm_tc_kernel, ta, tb, tout, tsp, p));
+  } else {
+    nrl_gemm_tc_kernel<<<grid, GEMM_THREADS, smem, c.stream>>>(ta, tb, tout, tsp, p);
+  }
   LAUNCH_CHECK(name);
   return NRL_OK;
 }

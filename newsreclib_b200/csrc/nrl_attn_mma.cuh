@@ -703,6 +703,7 @@ __global__ void __launch_bounds__(128)
 attn_fwd_mma64_kernel(const float* __restrict__ qkv, int E, int ldq, int heads, int S, long long seq_stride,
                       int NB, long long batch_stride, float scale, __nv_bfloat16* __restrict__ o_hi,
                       __nv_bfloat16* __restrict__ o_lo, int ep, float* __restrict__ lse) {
+  pdl_launch_dependents();  // the next launch (a PDL-launched GEMM) may begin its prologue while this grid runs
   constexpr int KS = (DH + 15) / 16, ND = (DH + 7) / 8;
   const int lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
   const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;

@@ -51,6 +51,7 @@ attn_bwd_ldsm_kernel(const float* __restrict__ qkv, const float* __restrict__ d_
                      const float* __restrict__ lse, int E, int ldq, int heads, int S, long long seq_stride, int NB,
                      long long batch_stride, float scale, __nv_bfloat16* __restrict__ g_hi,
                      __nv_bfloat16* __restrict__ g_lo, int p3, int three_i) {
+  pdl_launch_dependents();  // the next launch (a PDL-launched GEMM) may begin its prologue while this grid runs
   using C = TitleCfg<DH, NK32>;
   constexpr int ROWB = C::ROWB, C4 = C::DHP / 4, R4 = DH / 4, SK = C::SK, NT = C::NT, HT = C::HEAD_THREADS;
   static_assert(DH % 4 == 0, "16-byte row segments");

@@ -397,6 +397,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 nrl_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmSp,
                    const GemmParams p) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_boxes = (uint32_t)(p.BN + 63) / 64u;  // mn_major: 64-column boxes of 8 KB
@@ -444,6 +445,9 @@ nrl_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     tmem_alloc(tmem_ptr_addr, GEMM_TMEM_COLS);
     tmem_relinquish();
   }
+  // everything above touches only this CTA's shared memory, TMEM and the kernel parameters: under a programmatic
+  // dependent launch it overlaps the tail of the previous kernel; from here on global memory is read
+  pdl_wait();
   if (p.epi.qvec)
     for (int i = threadIdx.x; i < p.N && i < 256; i += blockDim.x)
       asm volatile("st.shared.f32 [%0], %1;" ::"r"(bar_base + 256u + 4u * (uint32_t)i), "f"(__ldg(p.epi.qvec + i)) : "memory");

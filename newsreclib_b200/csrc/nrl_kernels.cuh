@@ -1110,6 +1110,7 @@ attn_bwd_s32_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o
 __global__ void __launch_bounds__(128)
 pool_fwd_kernel(const float* __restrict__ score, const float* __restrict__ Y, int E, int L,
                 long long G, float* __restrict__ w_out, float* __restrict__ out) {
+  pdl_launch_dependents();  // the next launch (a PDL-launched GEMM) may begin its prologue while this grid runs
   extern __shared__ float sw[];  // L weights
   __shared__ float red[33];
   // blockIdx.y = block of 4 * blockDim columns (every CTA recomputes the L softmax weights: cheap)
@@ -1262,6 +1263,7 @@ pool_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ Y,
                 float* __restrict__ dY1, __nv_bfloat16* __restrict__ da_hi,
                 __nv_bfloat16* __restrict__ da_lo, float* __restrict__ dq_accum,
                 float* __restrict__ db_accum) {
+  pdl_launch_dependents();  // the next launch (a PDL-launched GEMM) may begin its prologue while this grid runs
   extern __shared__ float sm[];  // [L] ds
   float* s_ds = sm;
   __shared__ float red[33];
@@ -1486,6 +1488,7 @@ __global__ void segment_offsets2_kernel(const long long* __restrict__ seg0, long
 __global__ void dense_scatter_kernel(const float* __restrict__ x, const int* __restrict__ off,
                                      int B, int M, int E, int ep, float* __restrict__ dense,
                                      __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  pdl_launch_dependents();  // the next launch (a PDL-launched GEMM) may begin its prologue while this grid runs
   for (long long r = blockIdx.x; r < (long long)B * M; r += gridDim.x) {
     const int b = (int)(r / M), j = (int)(r % M);
     // off == nullptr: identity (every dense row present, M == 1 per "segment")
@@ -1506,6 +1509,7 @@ __global__ void dense_scatter_kernel(const float* __restrict__ x, const int* __r
 
 __global__ void dense_gather_kernel(const float* __restrict__ d_dense, const int* __restrict__ off,
                                     int B, int M, int E, float* __restrict__ dx) {
+  pdl_launch_dependents();  // the next launch (a PDL-launched GEMM) may begin its prologue while this grid runs
   for (int b = blockIdx.y; b < B; b += gridDim.y) {
     const int cnt = min(off[b + 1] - off[b], M);  // longer segments were flagged by segment_offsets_kernel
     for (int j = blockIdx.x; j < cnt; j += gridDim.x)
@@ -1842,6 +1846,7 @@ score_loss_kernel(const float* __restrict__ user, const float* __restrict__ cand
                   const int* __restrict__ off, int B, int C, int E, float* __restrict__ scores,
                   float* __restrict__ loss_mean, const float* __restrict__ g_loss, float* __restrict__ d_scores,
                   float* __restrict__ d_user, float* __restrict__ d_cand) {
+  pdl_launch_dependents();  // the next launch (a PDL-launched GEMM) may begin its prologue while this grid runs
   extern __shared__ float sl_smem[];
   float* s_sc = sl_smem;       // [C] scores of this row
   float* s_ds = sl_smem + C;   // [C] d loss / d scores

@@ -103,6 +103,15 @@ __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch (sm_90+)
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start (prologue, block scheduling)
+// while its stream predecessor is still running; pdl_wait() blocks until the predecessor grid has completed and its
+// memory is visible -- it must precede the first access to anything the predecessor produces.
+// pdl_launch_dependents() lets the successor's launch begin once every CTA of this grid has executed it.  Both are
+// no-ops in a launch without the attribute / without a dependent.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------ tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst),
