@@ -20,6 +20,11 @@ the ``-m "not gpu"`` suite re-checks the oracle against on every run.
 is restated from its published algorithm and is "parity unpinned" by the
 reference; it is anchored on the reference call sites
 (``newsreclib/models/general_rec/nrms_module.py:233,237,277-284``).
+The supervised-contrastive loss (``sup_con_loss``) sits on pytorch-metric-learning
+2.2.0 (``setup.py:26``; third-party, absent): the reference's own ``losses.py`` and
+``model_step`` run unmodified over ``oracle/pml_standins.py`` (a restatement of the
+few published pieces they call -- "parity unpinned" for those) and
+``oracle/make_module_golden.py`` asserts that ``sup_con_loss`` reproduces them.
 """
 from __future__ import annotations
 
