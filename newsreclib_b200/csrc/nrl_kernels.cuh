@@ -1990,8 +1990,10 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float*
 // (the Philox rounds are a long dependent chain: far too slow for the four epilogue warps of
 // the GEMM) and read back by the gather kernel, the GEMM epilogues and the backward pass:
 // words[site][r * mw + w], bit i = element (r, 32 w + i) of site `site` is kept.
+// row0: index of this buffer's first row in the numbering the draws follow (a pass split over two buffers keeps the bits
+// of the unsplit pass).
 __global__ void dropout_words_kernel(unsigned long long seed, uint32_t thr, long long R, int E, int mw,
-                                     uint32_t* __restrict__ w0, uint32_t* __restrict__ w1) {
+                                     uint32_t* __restrict__ w0, uint32_t* __restrict__ w1, long long row0 = 0) {
   const long long per_site = R * mw;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < 2 * per_site;
        i += (long long)gridDim.x * blockDim.x) {
@@ -1999,7 +2001,7 @@ __global__ void dropout_words_kernel(unsigned long long seed, uint32_t thr, long
     const long long j = i - site * per_site;
     const long long r = j / mw;
     const int w = (int)(j - r * mw);
-    const uint32_t bits = drop_keep_bits32(seed, site, (unsigned long long)r * (unsigned)E + 32u * (unsigned)w, thr);
+    const uint32_t bits = drop_keep_bits32(seed, site, (unsigned long long)(r + row0) * (unsigned)E + 32u * (unsigned)w, thr);
     (site ? w1 : w0)[j] = bits;
   }
 }
