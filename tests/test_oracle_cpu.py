@@ -181,6 +181,16 @@ def test_product_path_refuses_cpu_tensors():
     from newsreclib_b200 import ops
     with pytest.raises(RuntimeError, match="CUDA tensor"):
         ops.gemm_test(torch.zeros(4, 16), torch.zeros(4, 16), False)
+    # the optimizer and the loss / metric wrappers have no host path either
+    from newsreclib_b200.optim import Adam
+    p = torch.nn.Parameter(torch.zeros(8))
+    p.grad = torch.ones(8)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        Adam([p], lr=1e-3).step()
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ops.SupConFn.apply(torch.zeros(2, 3), torch.zeros(6), torch.tensor([0, 3, 6], dtype=torch.int32), None)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ops.rank_metrics(torch.zeros(6), torch.zeros(6), torch.tensor([3, 3]), [5])
 
 
 def test_hydra_model_configs_match_module_constructors():
